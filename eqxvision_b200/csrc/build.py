@@ -1,0 +1,90 @@
+"""Builds eqxvision_b200/lib/libeqxv_b200.so for sm_100a with nvcc (in-tree, no JIT cache).
+
+Usage: python -m eqxvision_b200.csrc.build [--force] [--verbose]
+nvcc cross-compiles without a GPU, so this runs in the CPU-only build container as well.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+ROOT = os.path.dirname(PKG)
+LIB_DIR = os.path.join(PKG, "lib")
+OBJ_DIR = os.path.join(HERE, "_obj")
+LIB_PATH = os.path.join(LIB_DIR, "libeqxv_b200.so")
+
+SOURCES = ["capi.cu", "igemm.cu", "pointwise.cu", "attention.cu", "depthwise.cu", "segment.cu"]
+HEADERS = ["ptx.cuh", "common.h", os.path.join(ROOT, "include", "eqxv_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+    return nvcc
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    hdrs = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+    jobs = []
+    objs = []
+    for s in srcs:
+        src = os.path.join(HERE, s)
+        obj = os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _stale(obj, [src] + hdrs + [os.path.abspath(__file__)]):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            jobs.append((s, cmd))
+
+    def run(job):
+        name, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return name, r
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for name, r in ex.map(run, jobs):
+                if verbose or r.returncode != 0:
+                    sys.stderr.write(f"--- nvcc {name} ---\n{r.stdout}{r.stderr}\n")
+                if r.returncode != 0:
+                    raise RuntimeError(f"nvcc failed on {name}")
+    if force or jobs or _stale(LIB_PATH, objs):
+        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                          "-Xcompiler", "-fPIC"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose))

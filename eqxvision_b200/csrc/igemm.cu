@@ -1,0 +1,635 @@
+// Implicit-GEMM convolution / linear layer on the 5th-generation tensor cores (tcgen05), sm_100a.
+//
+//   D[128 pixels x block_n channels] (fp32, TMEM)  +=  A[128 x 64] (bf16, smem)  x  B[block_n x 64]^T
+//
+// * persistent kernel, one CTA per SM, static round-robin tile schedule (n-tiles fastest so CTAs
+//   that run together share the same activation tile through L2)
+// * warp 0 (one thread): TMA producer.  A tiles are 4-D boxes (64 ch, tw, th, tn) of the NHWC
+//   activation: the (kh,kw) taps are the same box shifted by (r*dil-pad, s*dil-pad); out-of-bounds
+//   zero fill is the convolution padding, the box traversal stride is the convolution stride.
+//   B tiles are [block_n x 64] slabs of the K-major packed filter.
+// * warp 1 (one thread): tcgen05.mma issuer, 4 x (128 x block_n x 16) per 64-wide K block,
+//   accumulators double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of i+1.
+// * warps 2..5: epilogue. tcgen05.ld -> +bias(folded BN shift) -> (+residual) -> activation ->
+//   bf16 -> 128B-swizzled smem -> TMA store; the residual tile is prefetched by TMA.
+//
+// Replaces the XLA:CPU conv/dot thunks behind equinox.nn.Conv2d / Linear + BatchNorm(inference) +
+// jax.nn activation as composed in resnet.py:144-162, conv_norm_activation.py:61-85, vit.py:64,74,
+// mlps.py:61-65 (reference paths; see include/eqxv_b200.h).
+#include <algorithm>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace eqxv {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kThreads = 192;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kStageBuf = 16384;                // one epilogue staging buffer (128 rows x 128 B)
+constexpr int kMaxSmem = 232448;                // 227 KiB
+
+struct alignas(64) IgemmParams {
+  CUtensorMap tmA, tmB, tmC, tmR;
+  const float* bias;
+  int tiles_w, tiles_h, tiles_n, n_tiles, num_tiles;
+  int tw, th, tn;
+  int block_n, acc_stride, tmem_cols;
+  int kh, kw, dil_h, dil_w, pad_h, pad_w, mul_h, mul_w;
+  int in_h, in_w;   // extent of A dims 2 / 1 (tap skipping)
+  int kchunks;      // ceil(cin / 64)
+  int cin_pack;     // K offset between consecutive taps in B
+  int cout;
+  int act, res_after_act, has_res;
+  int stages;
+  // shared-memory carve-up (byte offsets from the 1024-aligned base)
+  int off_out, off_res, off_bias, off_bars;
+};
+
+struct TileCoord {
+  int ncol0, w0, h0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  t.ncol0 = nt * p.block_n;
+  t.w0 = (m % p.tiles_w) * p.tw;
+  m /= p.tiles_w;
+  t.h0 = (m % p.tiles_h) * p.th;
+  t.n0 = (m / p.tiles_h) * p.tn;
+  return t;
+}
+
+// A tap whose whole box lies in the zero padding contributes nothing (dilated ASPP convs,
+// deeplabv3.py:43-53 with d=24/36 on a 64x64 map): producer and MMA issuer skip it identically.
+__device__ __forceinline__ bool tap_valid(const IgemmParams& p, const TileCoord& t, int r, int s,
+                                          int& hc, int& wc) {
+  hc = t.h0 * p.mul_h + r * p.dil_h - p.pad_h;
+  wc = t.w0 * p.mul_w + s * p.dil_w - p.pad_w;
+  const bool h_ok = (hc + (p.th - 1) * p.mul_h >= 0) && (hc < p.in_h);
+  const bool w_ok = (wc + (p.tw - 1) * p.mul_w >= 0) && (wc < p.in_w);
+  return h_ok && w_ok;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case EQXV_ACT_RELU: return fmaxf(v, 0.f);
+    case EQXV_ACT_SILU: return v * __frcp_rn(1.f + __expf(-v));
+    case EQXV_ACT_GELU_TANH: {
+      const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+      float th;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+      return 0.5f * v * (1.f + th);
+    }
+    case EQXV_ACT_HARDSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case EQXV_ACT_SIGMOID: return __frcp_rn(1.f + __expf(-v));
+    case EQXV_ACT_HARDSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case EQXV_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
+    default: return v;
+  }
+}
+
+template <bool kOutF32>
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t stage_bytes = kABytes + p.block_n * 128;
+
+  const uint32_t bars = base + p.off_bars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 6);
+  volatile uint32_t* tmem_slot_g =
+      reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 6));
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmC);
+    if (p.has_res) tma_prefetch_desc(&p.tmR);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+      mbar_init(rfull_bar(a), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  const int taps = p.kh * p.kw;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          int hc, wc;
+          if (!tap_valid(p, t, r, s, hc, wc)) continue;
+          for (int c = 0; c < p.kchunks; ++c) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = base + stage * stage_bytes;
+            const uint32_t b_dst = a_dst + kABytes;
+            mbar_expect_tx(full_bar(stage), stage_bytes);
+            tma_load_4d(a_dst, &p.tmA, full_bar(stage), c * kBlockK, wc, hc, t.n0);
+            tma_load_2d(b_dst, &p.tmB, full_bar(stage), tap * p.cin_pack + c * kBlockK, t.ncol0);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          int hc, wc;
+          if (!tap_valid(p, t, r, s, hc, wc)) continue;
+          for (int c = 0; c < p.kchunks; ++c) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_src = base + stage * stage_bytes;
+            const uint32_t b_src = a_src + kABytes;
+            const uint64_t adesc = umma_desc_sw128(a_src);
+            const uint64_t bdesc = umma_desc_sw128(b_src);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // +32 bytes per 16-element K step inside the 128-byte swizzle row
+              umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                        accumulate);
+              accumulate = 1;
+            }
+            umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ============================== epilogue (warps 2..5) ==============================
+    constexpr int CH = kOutF32 ? 32 : 64;  // columns per staged chunk (128 B per row)
+    const int e = threadIdx.x - 64;
+    const bool leader = (e == 0);
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const uint32_t row = quad * 32 + lane;
+    const int cpt = (p.block_n + CH - 1) / CH;
+    float* s_bias = reinterpret_cast<float*>(gbase + p.off_bias);
+    const bool has_res = p.has_res != 0;
+
+    auto issue_res = [&](uint32_t gg) {
+      const int ti = gg / cpt, c = gg - ti * cpt;
+      const long long tile = (long long)blockIdx.x + (long long)ti * gridDim.x;
+      if (tile >= p.num_tiles) return;
+      const TileCoord t = decode_tile(p, (int)tile);
+      const uint32_t b = gg & 1u;
+      mbar_expect_tx(rfull_bar(b), kStageBuf);
+      tma_load_4d(base + p.off_res + b * kStageBuf, &p.tmR, rfull_bar(b), t.ncol0 + c * CH, t.w0,
+                  t.h0, t.n0);
+    };
+
+    uint32_t g = 0;
+    if (has_res && leader) {
+      issue_res(0);
+      issue_res(1);
+    }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      for (int i = e; i < p.block_n; i += 128) {
+        const int col = t.ncol0 + i;
+        s_bias[i] = (p.bias != nullptr && col < p.cout) ? __ldg(p.bias + col) : 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+
+      for (int c = 0; c < cpt; ++c, ++g) {
+        const uint32_t buf = g & 1u;
+        const uint32_t rphase = (g >> 1) & 1u;
+        const int ncols = min(CH, p.block_n - c * CH);
+        float v[CH];
+#pragma unroll
+        for (int j = 0; j < CH / 16; ++j) {
+          if (j * 16 < ncols) {
+            tmem_ld_x16(t_acc + (uint32_t)(c * CH + j * 16), &v[j * 16]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[j * 16 + q] = 0.f;
+          }
+        }
+        tmem_ld_wait();
+        if (c == cpt - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        const float* bias_c = s_bias + c * CH;
+        if constexpr (!kOutF32) {
+          uint4 packed[8];
+          if (has_res) mbar_wait(rfull_bar(buf), rphase);
+          const uint8_t* res_row = gbase + p.off_res + buf * kStageBuf;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float r8[8];
+            if (has_res) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(res_row + sw128_off(row, j));
+              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __bfloat1622float2(rb[q]);
+                r8[2 * q] = f.x;
+                r8[2 * q + 1] = f.y;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) r8[q] = 0.f;
+            }
+            float o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float x = v[j * 8 + q] + bias_c[j * 8 + q];
+              if (p.res_after_act) {
+                x = apply_act(x, p.act) + r8[q];
+              } else {
+                x = apply_act(x + r8[q], p.act);
+              }
+              o[q] = x;
+            }
+            __nv_bfloat162 ob[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
+            packed[j] = *reinterpret_cast<const uint4*>(ob);
+          }
+          if (leader) tma_store_wait_read<1>();  // the store that last used out[buf] has read it
+          named_bar_sync(1, 128);
+          uint8_t* out_row = gbase + p.off_out + buf * kStageBuf;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(out_row + sw128_off(row, j)) = packed[j];
+        } else {
+#pragma unroll
+          for (int q = 0; q < CH; ++q) v[q] = apply_act(v[q] + bias_c[q], p.act);
+          if (leader) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          uint8_t* out_row = gbase + p.off_out + buf * kStageBuf;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(out_row + sw128_off(row, j)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (leader) {
+          tma_store_4d(&p.tmC, base + p.off_out + buf * kStageBuf, t.ncol0 + c * CH, t.w0, t.h0,
+                       t.n0);
+          tma_store_commit();
+          if (has_res) issue_res(g + 2);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (leader) tma_store_wait_all();
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct IgemmProblem {
+  // A operand tensor map (4-D)
+  TmapSpec a;
+  // B operand: packed weights [cout, ktot]
+  const void* wgt;
+  int ktot;
+  const float* bias;
+  // output / residual: [n, ho, wo, pitch] viewed with the M-tile geometry
+  void* y;
+  const void* res;
+  int y_pitch, res_pitch;
+  int out_n, out_h, out_w;  // logical M grid (flat views use out_w = M, out_h = out_n = 1)
+  int tw, th, tn;
+  int cout;
+  int kh, kw, dil_h, dil_w, pad_h, pad_w, mul_h, mul_w;
+  int in_h, in_w;
+  int kchunks, cin_pack;
+  int act, flags;
+};
+
+static void choose_tile(int n, int ho, int wo, int& tw, int& th, int& tn) {
+  long long best = -1;
+  for (int w = 128; w >= 1; w >>= 1) {
+    for (int h = 128 / w; h >= 1; h >>= 1) {
+      const int b = 128 / (w * h);
+      const long long padded = (long long)ceil_div(wo, w) * w * (long long)ceil_div(ho, h) * h *
+                               (long long)ceil_div(n, b) * b;
+      if (best < 0 || padded < best) {  // ties keep the wider (more contiguous) tile found first
+        best = padded;
+        tw = w;
+        th = h;
+        tn = b;
+      }
+    }
+  }
+}
+
+static int choose_block_n(int cout) {
+  if (cout <= 32) return 32;
+  const int nt = ceil_div(cout, 256);
+  int bn = ceil_div(ceil_div(cout, nt), 16) * 16;
+  if (bn < 64) bn = 64;
+  return bn;
+}
+
+static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  const bool out_f32 = (q.flags & EQXV_FLAG_OUT_F32) != 0;
+  EQXV_CHECK_ARG(!(out_f32 && q.res), "igemm: residual is not supported with fp32 output");
+  const int block_n = choose_block_n(q.cout);
+  p.block_n = block_n;
+  p.acc_stride = ceil_div(block_n, 32) * 32;
+  int cols = 32;
+  while (cols < 2 * p.acc_stride) cols <<= 1;
+  p.tmem_cols = cols;
+  p.n_tiles = ceil_div(q.cout, block_n);
+  p.tw = q.tw, p.th = q.th, p.tn = q.tn;
+  p.tiles_w = ceil_div(q.out_w, q.tw);
+  p.tiles_h = ceil_div(q.out_h, q.th);
+  p.tiles_n = ceil_div(q.out_n, q.tn);
+  const long long num_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  EQXV_CHECK_ARG(num_tiles > 0 && num_tiles < (1ll << 30), "igemm: bad tile count %lld", num_tiles);
+  p.num_tiles = (int)num_tiles;
+  p.kh = q.kh, p.kw = q.kw, p.dil_h = q.dil_h, p.dil_w = q.dil_w;
+  p.pad_h = q.pad_h, p.pad_w = q.pad_w, p.mul_h = q.mul_h, p.mul_w = q.mul_w;
+  p.in_h = q.in_h, p.in_w = q.in_w;
+  p.kchunks = q.kchunks, p.cin_pack = q.cin_pack;
+  p.cout = q.cout;
+  p.act = q.act;
+  p.res_after_act = (q.flags & EQXV_FLAG_RES_AFTER_ACT) ? 1 : 0;
+  p.has_res = q.res ? 1 : 0;
+  p.bias = q.bias;
+
+  // shared memory carve-up
+  const int stage_bytes = kABytes + block_n * 128;
+  const int fixed = 2 * kStageBuf + (p.has_res ? 2 * kStageBuf : 0) + 1024 + 256;
+  int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
+  stages = std::min(stages, 8);
+  EQXV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for block_n=%d", block_n);
+  p.stages = stages;
+  p.off_out = stages * stage_bytes;
+  p.off_res = p.off_out + 2 * kStageBuf;
+  p.off_bias = p.off_res + (p.has_res ? 2 * kStageBuf : 0);
+  p.off_bars = p.off_bias + 1024;
+  const int smem_bytes = p.off_bars + 256 + 1024;
+
+  int rc = encode_tmap(&p.tmA, q.a);
+  if (rc) return rc;
+  TmapSpec b{};
+  b.base = const_cast<void*>(q.wgt);
+  b.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  b.rank = 2;
+  b.dims[0] = (uint64_t)q.ktot, b.dims[1] = (uint64_t)q.cout;
+  b.strides_bytes[0] = (uint64_t)q.ktot * 2;
+  b.box[0] = kBlockK, b.box[1] = (uint32_t)block_n;
+  b.estride[0] = b.estride[1] = 1;
+  b.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+  rc = encode_tmap(&p.tmB, b);
+  if (rc) return rc;
+
+  auto make_out = [&](CUtensorMap* m, void* ptr, int pitch, bool f32) -> int {
+    TmapSpec c{};
+    const uint64_t es = f32 ? 4 : 2;
+    c.base = ptr;
+    c.dtype = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    c.rank = 4;
+    c.dims[0] = (uint64_t)q.cout, c.dims[1] = (uint64_t)q.out_w, c.dims[2] = (uint64_t)q.out_h,
+    c.dims[3] = (uint64_t)q.out_n;
+    c.strides_bytes[0] = (uint64_t)pitch * es;
+    c.strides_bytes[1] = c.strides_bytes[0] * (uint64_t)q.out_w;
+    c.strides_bytes[2] = c.strides_bytes[1] * (uint64_t)q.out_h;
+    c.box[0] = f32 ? 32 : 64, c.box[1] = (uint32_t)q.tw, c.box[2] = (uint32_t)q.th,
+    c.box[3] = (uint32_t)q.tn;
+    c.estride[0] = c.estride[1] = c.estride[2] = c.estride[3] = 1;
+    c.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+    return encode_tmap(m, c);
+  };
+  rc = make_out(&p.tmC, q.y, q.y_pitch, out_f32);
+  if (rc) return rc;
+  if (q.res) {
+    rc = make_out(&p.tmR, const_cast<void*>(q.res), q.res_pitch, false);
+    if (rc) return rc;
+  }
+
+  const int grid = std::min(p.num_tiles, device_sm_count());
+  if (out_f32) {
+    igemm_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(p);
+  } else {
+    igemm_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
+  }
+  EQXV_CUDA(cudaGetLastError());
+  return EQXV_OK;
+}
+
+int igemm_init() {
+  EQXV_CUDA(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMaxSmem));
+  EQXV_CUDA(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMaxSmem));
+  return EQXV_OK;
+}
+
+}  // namespace eqxv
+
+using namespace eqxv;
+
+extern "C" int eqxv_conv2d_igemm_bf16(const eqxv_conv_desc* d, void* stream) {
+  EQXV_CHECK_ARG(d != nullptr, "conv: null descriptor");
+  EQXV_CHECK_ARG(d->x && d->wgt && d->y, "conv: null tensor pointer");
+  EQXV_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "conv: bad shape");
+  EQXV_CHECK_ARG(d->kh >= 1 && d->kw >= 1 && d->stride >= 1 && d->dil >= 1 && d->pad >= 0,
+                 "conv: bad kernel geometry");
+  EQXV_CHECK_ARG(d->cin % 8 == 0, "conv: cin (%d) must be a multiple of 8 (pad the input)", d->cin);
+  EQXV_CHECK_ARG(d->x_pitch % 8 == 0 && d->x_pitch >= d->cin, "conv: bad x_pitch %d", d->x_pitch);
+  const bool f32 = (d->flags & EQXV_FLAG_OUT_F32) != 0;
+  EQXV_CHECK_ARG(d->y_pitch >= d->cout && d->y_pitch % (f32 ? 4 : 8) == 0, "conv: bad y_pitch %d",
+                 d->y_pitch);
+  EQXV_CHECK_ARG(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->y & 15) == 0 &&
+                     ((uintptr_t)d->wgt & 15) == 0,
+                 "conv: pointers must be 16-byte aligned");
+  if (d->residual) {
+    EQXV_CHECK_ARG(d->res_pitch % 8 == 0 && d->res_pitch >= d->cout, "conv: bad res_pitch");
+    EQXV_CHECK_ARG(((uintptr_t)d->residual & 15) == 0, "conv: residual must be 16-byte aligned");
+  }
+  const int ho = (d->h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+  const int wo = (d->w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
+  EQXV_CHECK_ARG(ho > 0 && wo > 0, "conv: empty output");
+
+  IgemmProblem q{};
+  q.wgt = d->wgt;
+  q.ktot = d->kh * d->kw * d->cin;
+  q.bias = d->bias;
+  q.y = d->y;
+  q.res = d->residual;
+  q.y_pitch = d->y_pitch;
+  q.res_pitch = d->res_pitch;
+  q.cout = d->cout;
+  q.act = d->act;
+  q.flags = d->flags;
+  q.kchunks = ceil_div(d->cin, kBlockK);
+  q.cin_pack = d->cin;
+  q.a.base = const_cast<void*>(d->x);
+  q.a.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  q.a.rank = 4;
+  q.a.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+
+  const bool pointwise = (d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0);
+  if (pointwise) {
+    // plain GEMM over the flattened pixel index
+    const long long m = (long long)d->n * d->h * d->w;
+    EQXV_CHECK_ARG(m < (1ll << 31), "conv: too many pixels");
+    q.out_w = (int)m, q.out_h = 1, q.out_n = 1;
+    q.tw = 128, q.th = 1, q.tn = 1;
+    q.kh = q.kw = 1, q.dil_h = q.dil_w = 1, q.pad_h = q.pad_w = 0, q.mul_h = q.mul_w = 1;
+    q.in_h = 1, q.in_w = (int)m;
+    q.a.dims[0] = (uint64_t)d->cin, q.a.dims[1] = (uint64_t)m, q.a.dims[2] = 1, q.a.dims[3] = 1;
+    q.a.strides_bytes[0] = (uint64_t)d->x_pitch * 2;
+    q.a.strides_bytes[1] = q.a.strides_bytes[0] * (uint64_t)m;
+    q.a.strides_bytes[2] = q.a.strides_bytes[1];
+    q.a.box[0] = kBlockK, q.a.box[1] = 128, q.a.box[2] = 1, q.a.box[3] = 1;
+    q.a.estride[0] = q.a.estride[1] = q.a.estride[2] = q.a.estride[3] = 1;
+  } else {
+    q.out_w = wo, q.out_h = ho, q.out_n = d->n;
+    choose_tile(d->n, ho, wo, q.tw, q.th, q.tn);
+    EQXV_CHECK_ARG(q.tw * d->stride <= 256 && q.th * d->stride <= 256, "conv: stride too large");
+    q.kh = d->kh, q.kw = d->kw, q.dil_h = q.dil_w = d->dil, q.pad_h = q.pad_w = d->pad;
+    q.mul_h = q.mul_w = d->stride;
+    q.in_h = d->h, q.in_w = d->w;
+    q.a.dims[0] = (uint64_t)d->cin, q.a.dims[1] = (uint64_t)d->w, q.a.dims[2] = (uint64_t)d->h,
+    q.a.dims[3] = (uint64_t)d->n;
+    q.a.strides_bytes[0] = (uint64_t)d->x_pitch * 2;
+    q.a.strides_bytes[1] = q.a.strides_bytes[0] * (uint64_t)d->w;
+    q.a.strides_bytes[2] = q.a.strides_bytes[1] * (uint64_t)d->h;
+    q.a.box[0] = kBlockK;
+    q.a.box[1] = (uint32_t)(q.tw * d->stride);
+    q.a.box[2] = (uint32_t)(q.th * d->stride);
+    q.a.box[3] = (uint32_t)q.tn;
+    q.a.estride[0] = 1, q.a.estride[1] = (uint32_t)d->stride, q.a.estride[2] = (uint32_t)d->stride,
+    q.a.estride[3] = 1;
+  }
+  return launch_igemm(q, (cudaStream_t)stream);
+}
+
+extern "C" int eqxv_gemm_bias_act_res_bf16(const void* a, int64_t lda, const void* w,
+                                           const float* bias, const void* residual, int64_t ldr,
+                                           void* out, int64_t ldo, int64_t m, int32_t n, int32_t k,
+                                           int32_t act, int32_t flags, void* stream) {
+  EQXV_CHECK_ARG(m > 0 && m < (1ll << 31) && n > 0 && k > 0, "gemm: bad shape");
+  EQXV_CHECK_ARG(k % 8 == 0, "gemm: k (%d) must be a multiple of 8", k);
+  eqxv_conv_desc d{};
+  d.x = a, d.wgt = w, d.bias = bias, d.residual = residual, d.y = out;
+  d.n = 1, d.h = 1, d.w = (int32_t)m, d.cin = k, d.cout = n;
+  d.kh = d.kw = 1, d.stride = 1, d.pad = 0, d.dil = 1;
+  d.x_pitch = (int32_t)lda, d.y_pitch = (int32_t)ldo, d.res_pitch = (int32_t)ldr;
+  d.act = act, d.flags = flags;
+  return eqxv_conv2d_igemm_bf16(&d, stream);
+}
+
+extern "C" int eqxv_conv_stem7x7_bf16(const void* xpad, const void* wgt, const float* bias, void* y,
+                                      int32_t n, int32_t h, int32_t w, int32_t cout, int32_t y_pitch,
+                                      int32_t act, void* stream) {
+  EQXV_CHECK_ARG(xpad && wgt && y, "stem: null pointer");
+  EQXV_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0, "stem: bad shape");
+  EQXV_CHECK_ARG(h % 2 == 0 && w % 2 == 0, "stem: h and w must be even");
+  EQXV_CHECK_ARG(y_pitch % 8 == 0 && y_pitch >= cout, "stem: bad y_pitch");
+  const int ho = h / 2, wo = w / 2;
+  const int hp = h + 6, wp = w + 8;  // layout written by eqxv_pack_stem_input
+  IgemmProblem q{};
+  q.wgt = wgt;
+  q.ktot = 7 * 64;
+  q.bias = bias;
+  q.y = y;
+  q.res = nullptr;
+  q.y_pitch = y_pitch;
+  q.cout = cout;
+  q.act = act;
+  q.flags = 0;
+  q.kchunks = 1;
+  q.cin_pack = 64;
+  q.out_w = wo, q.out_h = ho, q.out_n = n;
+  choose_tile(n, ho, wo, q.tw, q.th, q.tn);
+  EQXV_CHECK_ARG(q.th * 2 <= 256, "stem: tile too tall");
+  // 7 taps = the 7 filter rows; one "channel block" = an 8-pixel x 8-channel window (64 elements,
+  // 128 B) starting at padded column 2*wo. Window starts overlap (stride 2 pixels = 32 B), so the
+  // "w" dimension of the map is the OUTPUT column; rows are traversed with stride 2.
+  q.kh = 7, q.kw = 1, q.dil_h = q.dil_w = 1, q.pad_h = q.pad_w = 0, q.mul_h = 2, q.mul_w = 1;
+  q.in_h = hp, q.in_w = wo;
+  q.a.base = const_cast<void*>(xpad);
+  q.a.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  q.a.rank = 4;
+  q.a.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+  q.a.dims[0] = 64, q.a.dims[1] = (uint64_t)wo, q.a.dims[2] = (uint64_t)hp, q.a.dims[3] = (uint64_t)n;
+  q.a.strides_bytes[0] = 32;                                   // 2 pixels x 8 ch x 2 B
+  q.a.strides_bytes[1] = (uint64_t)wp * 16;                    // one padded row
+  q.a.strides_bytes[2] = (uint64_t)wp * 16 * (uint64_t)hp;     // one padded image
+  q.a.box[0] = 64, q.a.box[1] = (uint32_t)q.tw, q.a.box[2] = (uint32_t)(q.th * 2),
+  q.a.box[3] = (uint32_t)q.tn;
+  q.a.estride[0] = 1, q.a.estride[1] = 1, q.a.estride[2] = 2, q.a.estride[3] = 1;
+  return launch_igemm(q, (cudaStream_t)stream);
+}

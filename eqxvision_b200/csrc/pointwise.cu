@@ -1,0 +1,422 @@
+// HBM-bound helper kernels: layout changes at the boundary, pooling, LayerNorm, ViT token glue.
+// All of them move 16-byte vectors (8 bf16 channels) per thread over channels-last data so that a
+// warp touches whole 128-byte lines; none of them uses shared memory (no reuse to exploit) except
+// the NHWC->NCHW transpose.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace eqxv {
+
+constexpr int kPwThreads = 256;
+
+static inline int grid_for(long long work, int threads = kPwThreads) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& a, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(a.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem input: fp32 NCHW [n,3,h,w] -> bf16 [n, h+6, w+8, 8], image at (3,3), zeros elsewhere
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict__ y, int n, int h,
+                                 int w) {
+  const int hp = h + 6, wp = w + 8;
+  const long long total = (long long)n * hp * wp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int pw = (int)(i % wp);
+    const int ph = (int)((i / wp) % hp);
+    const int img = (int)(i / ((long long)wp * hp));
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int sh = ph - 3, sw = pw - 3;
+    if (sh >= 0 && sh < h && sw >= 0 && sw < w) {
+      const long long plane = (long long)h * w;
+      const float* src = x + (long long)img * 3 * plane + (long long)sh * w + sw;
+      f[0] = __ldg(src);
+      f[1] = __ldg(src + plane);
+      f[2] = __ldg(src + 2 * plane);
+    }
+    y[i] = pack8(f);
+  }
+}
+
+// fp32 NCHW -> bf16 NHWC (channels padded with zeros to c_pad)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16x8* __restrict__ y, int n, int c,
+                                    int h, int w, int c_pad) {
+  const int groups = c_pad / 8;
+  const long long plane = (long long)h * w;
+  const long long total = (long long)n * plane * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // pixel index fastest so that a warp reads 32 consecutive floats of one plane
+    const long long pix = i % plane;
+    const int g = (int)((i / plane) % groups);
+    const int img = (int)(i / (plane * groups));
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ch = g * 8 + q;
+      f[q] = ch < c ? __ldg(x + ((long long)img * c + ch) * plane + pix) : 0.f;
+    }
+    y[((long long)img * plane + pix) * groups + g] = pack8(f);
+  }
+}
+
+// bf16 NHWC (pitch) -> fp32 NCHW through a 32x33 shared tile (pixels x channels)
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int c,
+                                    long long plane, int pitch) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const long long pix = p0 + r;
+    const int ch = c0 + tx;
+    float v = 0.f;
+    if (pix < plane && ch < c) v = __bfloat162float(x[((long long)img * plane + pix) * pitch + ch]);
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ch = c0 + r;
+    const long long pix = p0 + tx;
+    if (pix < plane && ch < c) y[((long long)img * c + ch) * plane + pix] = tile[tx][r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooling (channels-last, 8 channels per thread)
+// ---------------------------------------------------------------------------------------------
+template <bool kMax>
+__global__ void pool2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                              int n, int h, int w, int c, int kh, int kw, int sh, int sw, int pad,
+                              int ho, int wo, int xp, int yp) {
+  const int groups = c / 8;
+  const long long total = (long long)n * ho * wo * groups;
+  const float inv = 1.f / (float)(kh * kw);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long t = i / groups;
+    const int ow = (int)(t % wo);
+    t /= wo;
+    const int oh = (int)(t % ho);
+    const int img = (int)(t / ho);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = kMax ? -INFINITY : 0.f;
+    for (int r = 0; r < kh; ++r) {
+      const int ih = oh * sh - pad + r;
+      if (ih < 0 || ih >= h) continue;
+      for (int s = 0; s < kw; ++s) {
+        const int iw = ow * sw - pad + s;
+        if (iw < 0 || iw >= w) continue;
+        const bf16x8 v = *reinterpret_cast<const bf16x8*>(
+            x + (((long long)img * h + ih) * w + iw) * xp + g * 8);
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = kMax ? fmaxf(acc[q], f[q]) : acc[q] + f[q];
+      }
+    }
+    if (!kMax) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] *= inv;
+    }
+    *reinterpret_cast<bf16x8*>(y + (((long long)img * ho + oh) * wo + ow) * yp + g * 8) = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row is kept in registers (d <= 2048), fp32 statistics,
+// two-pass (mean, then centred variance) as equinox.nn.LayerNorm does.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnMaxVec = 8;  // 8 vectors x 8 elements x 32 lanes = 2048
+
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 __nv_bfloat16* __restrict__ y, long long ldy, long long rows, int d,
+                                 float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = d / 8;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows;
+       row += (long long)gridDim.x * wpb) {
+    const __nv_bfloat16* xr = x + row * ldx;
+    float f[kLnMaxVec][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        unpack8(*reinterpret_cast<const bf16x8*>(xr + v * 8), f[i]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum += f[i][q];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float dlt = f[i][q] - mean;
+          sq += dlt * dlt;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)d + eps);
+    __nv_bfloat16* yr = y + row * ldy;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float o[8];
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = (f[i][q] - mean) * rstd * gg[q] + bb[q];
+        *reinterpret_cast<bf16x8*>(yr + v * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ViT glue
+// ---------------------------------------------------------------------------------------------
+// rows[(img*gh + gy)*gw + gx, (ch*p + py)*p + px] = x[img, ch, gy*p+py, gx*p+px]
+__global__ void patchify_kernel(const float* __restrict__ x, bf16x8* __restrict__ rows, int n, int c,
+                                int h, int w, int p) {
+  const int gh = h / p, gw = w / p;
+  const int kvec = c * p * p / 8;
+  const int pv = p / 8;  // vectors per patch row
+  const long long total = (long long)n * gh * gw * kvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kv = (int)(i % kvec);
+    const long long prow = i / kvec;
+    const int gx = (int)(prow % gw);
+    const int gy = (int)((prow / gw) % gh);
+    const int img = (int)(prow / ((long long)gw * gh));
+    const int px0 = (kv % pv) * 8;
+    const int py = (kv / pv) % p;
+    const int ch = kv / (pv * p);
+    const float* src = x + (((long long)img * c + ch) * h + gy * p + py) * w + gx * p + px0;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    rows[i] = pack8(f);
+  }
+}
+
+__global__ void assemble_tokens_kernel(const bf16x8* __restrict__ patches, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, bf16x8* __restrict__ out, int n,
+                                       int np, int d) {
+  const int dv = d / 8;
+  const long long total = (long long)n * (np + 1) * dv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % dv);
+    const long long r = i / dv;
+    const int t = (int)(r % (np + 1));
+    const int img = (int)(r / (np + 1));
+    float f[8];
+    if (t == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = __ldg(cls + v * 8 + q);
+    } else {
+      unpack8(patches[((long long)img * np + (t - 1)) * dv + v], f);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] += __ldg(pos + (long long)t * d + v * 8 + q);
+    out[i] = pack8(f);
+  }
+}
+
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                   __nv_bfloat16* __restrict__ y, long long ldy, int n, int tokens,
+                                   int row, int d) {
+  const int dv = d / 8;
+  const long long total = (long long)n * dv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % dv);
+    const int img = (int)(i / dv);
+    *reinterpret_cast<bf16x8*>(y + (long long)img * ldy + v * 8) =
+        *reinterpret_cast<const bf16x8*>(x + ((long long)img * tokens + row) * ldx + v * 8);
+  }
+}
+
+}  // namespace eqxv
+
+using namespace eqxv;
+
+#define EQXV_LAUNCH_CHECK() EQXV_CUDA(cudaGetLastError())
+
+extern "C" int eqxv_pack_stem_input(const float* x, void* xpad, int32_t n, int32_t h, int32_t w,
+                                    void* stream) {
+  EQXV_CHECK_ARG(x && xpad && n > 0 && h > 0 && w > 0, "pack_stem_input: bad arguments");
+  const long long total = (long long)n * (h + 6) * (w + 8);
+  pack_stem_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<bf16x8*>(xpad), n, h, w);
+  EQXV_LAUNCH_CHECK();
+  return EQXV_OK;
+}
+
+extern "C" int eqxv_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h,
+                                          int32_t w, int32_t c_pad, void* stream) {
+  EQXV_CHECK_ARG(x && y && n > 0 && c > 0 && h > 0 && w > 0, "nchw_to_nhwc: bad arguments");
+  EQXV_CHECK_ARG(c_pad >= c && c_pad % 8 == 0, "nchw_to_nhwc: c_pad must be a multiple of 8 >= c");
+  const long long total = (long long)n * h * w * (c_pad / 8);
+  nchw_to_nhwc_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<bf16x8*>(y), n, c, h, w, c_pad);
+  EQXV_LAUNCH_CHECK();
+  return EQXV_OK;
+}
+
+extern "C" int eqxv_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t n, int32_t c, int32_t h,
+                                          int32_t w, int32_t x_pitch, void* stream) {
+  EQXV_CHECK_ARG(x && y && n > 0 && c > 0 && h > 0 && w > 0 && x_pitch >= c,
+                 "nhwc_to_nchw: bad arguments");
+  const long long plane = (long long)h * w;
+  dim3 grid((unsigned)((plane + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), y, c, plane, x_pitch);
+  EQXV_LAUNCH_CHECK();
+  return EQXV_OK;
+}
+
+static int pool_common(bool is_max, const void* x, void* y, int n, int h, int w, int c, int kh, int kw,
+                       int sh, int sw, int pad, int ho, int wo, int xp, int yp, cudaStream_t stream) {
+  EQXV_CHECK_ARG(x && y && n > 0 && h > 0 && w > 0 && c > 0, "pool: bad arguments");
+  EQXV_CHECK_ARG(c % 8 == 0 && xp % 8 == 0 && yp % 8 == 0 && xp >= c && yp >= c,
+                 "pool: channels and pitches must be multiples of 8");
+  EQXV_CHECK_ARG(ho > 0 && wo > 0, "pool: empty output");
+  const long long total = (long long)n * ho * wo * (c / 8);
+  if (is_max) {
+    pool2d_kernel<true><<<grid_for(total), kPwThreads, 0, stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, kh, kw, sh, sw, pad, ho, wo, xp, yp);
+  } else {
+    pool2d_kernel<false><<<grid_for(total), kPwThreads, 0, stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, kh, kw, sh, sw, pad, ho, wo, xp, yp);
+  }
+  EQXV_LAUNCH_CHECK();
+  return EQXV_OK;
+}
+
+extern "C" int eqxv_maxpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w,
+                                        int32_t c, int32_t k, int32_t stride, int32_t pad,
+                                        int32_t x_pitch, int32_t y_pitch, void* stream) {
+  EQXV_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && 2 * pad <= k, "maxpool: bad window");
+  const int ho = (h + 2 * pad - k) / stride + 1;
+  const int wo = (w + 2 * pad - k) / stride + 1;
+  return pool_common(true, x, y, n, h, w, c, k, k, stride, stride, pad, ho, wo, x_pitch, y_pitch,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int eqxv_avgpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w,
+                                        int32_t c, int32_t k, int32_t stride, int32_t x_pitch,
+                                        int32_t y_pitch, void* stream) {
+  EQXV_CHECK_ARG(k >= 1 && stride >= 1, "avgpool: bad window");
+  const int ho = (h - k) / stride + 1;
+  const int wo = (w - k) / stride + 1;
+  return pool_common(false, x, y, n, h, w, c, k, k, stride, stride, 0, ho, wo, x_pitch, y_pitch,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w,
+                                               int32_t c, int32_t oh, int32_t ow, int32_t x_pitch,
+                                               int32_t y_pitch, void* stream) {
+  EQXV_CHECK_ARG(oh >= 1 && ow >= 1, "adaptive_avgpool: bad output size");
+  if (h % oh != 0 || w % ow != 0) {
+    set_error("adaptive_avgpool: %dx%d -> %dx%d is not an even split (unsupported)", h, w, oh, ow);
+    return EQXV_ERR_UNSUPPORTED;
+  }
+  return pool_common(false, x, y, n, h, w, c, h / oh, w / ow, h / oh, w / ow, 0, oh, ow, x_pitch,
+                     y_pitch, (cudaStream_t)stream);
+}
+
+extern "C" int eqxv_layernorm_bf16(const void* x, int64_t ldx, const float* gamma, const float* beta,
+                                   void* y, int64_t ldy, int64_t rows, int32_t d, float eps,
+                                   void* stream) {
+  EQXV_CHECK_ARG(x && y && gamma && beta && rows > 0 && d > 0, "layernorm: bad arguments");
+  EQXV_CHECK_ARG(d % 8 == 0 && d <= kLnMaxVec * 256, "layernorm: d must be a multiple of 8, <= 2048");
+  EQXV_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= d && ldy >= d, "layernorm: bad row pitch");
+  const int wpb = 8;
+  long long blocks = (rows + wpb - 1) / wpb;
+  const long long cap = (long long)device_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  layernorm_kernel<<<(int)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, gamma, beta, (__nv_bfloat16*)y, ldy, rows, d, eps);
+  EQXV_LAUNCH_CHECK();
+  return EQXV_OK;
+}
+
+extern "C" int eqxv_patchify_nchw_f32_bf16(const float* x, void* rows, int32_t n, int32_t c, int32_t h,
+                                           int32_t w, int32_t p, void* stream) {
+  EQXV_CHECK_ARG(x && rows && n > 0 && c > 0 && h > 0 && w > 0, "patchify: bad arguments");
+  EQXV_CHECK_ARG(p % 8 == 0 && h % p == 0 && w % p == 0 && w % 4 == 0,
+                 "patchify: patch size must be a multiple of 8 dividing h and w");
+  const long long total = (long long)n * (h / p) * (w / p) * (c * p * p / 8);
+  patchify_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<bf16x8*>(rows), n, c, h, w, p);
+  EQXV_LAUNCH_CHECK();
+  return EQXV_OK;
+}
+
+extern "C" int eqxv_vit_assemble_tokens_bf16(const void* patches, const float* cls, const float* pos,
+                                             void* out, int32_t n, int32_t np, int32_t d,
+                                             void* stream) {
+  EQXV_CHECK_ARG(patches && cls && pos && out && n > 0 && np > 0 && d > 0 && d % 8 == 0,
+                 "assemble_tokens: bad arguments");
+  const long long total = (long long)n * (np + 1) * (d / 8);
+  assemble_tokens_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16x8*>(patches), cls, pos, reinterpret_cast<bf16x8*>(out), n, np, d);
+  EQXV_LAUNCH_CHECK();
+  return EQXV_OK;
+}
+
+extern "C" int eqxv_gather_rows_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t n,
+                                     int32_t tokens, int32_t row, int32_t d, void* stream) {
+  EQXV_CHECK_ARG(x && y && n > 0 && tokens > 0 && row >= 0 && row < tokens && d > 0 && d % 8 == 0 &&
+                     ldx % 8 == 0 && ldy % 8 == 0,
+                 "gather_rows: bad arguments");
+  const long long total = (long long)n * (d / 8);
+  gather_rows_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, n, tokens, row, d);
+  EQXV_LAUNCH_CHECK();
+  return EQXV_OK;
+}

@@ -1,0 +1,180 @@
+"""Thin host-side wrappers: one Python function per C-ABI kernel entry.
+
+Tensors are torch CUDA tensors used purely as device-memory holders (pointer + shape); all
+arithmetic happens in libeqxv_b200.so. Every wrapper takes an explicit `stream` (raw cudaStream_t
+handle as int, 0 = legacy default stream) and never synchronises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, call, ptr
+
+BF16 = torch.bfloat16
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.EqxvError("eqxvision_b200 ops need CUDA tensors: there is no CPU fallback")
+
+
+def conv_out_size(h, k, stride, pad, dil):
+    return (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def conv2d(x, wgt, bias, *, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, residual=None,
+           res_after_act=False, out=None, out_f32=False, stream=0):
+    """x: [N,H,W,x_pitch] bf16 view (last-dim stride 1); wgt: [cout, kh*kw*cin] bf16; bias fp32 [cout]."""
+    _check_cuda(x, wgt, bias, residual, out)
+    n, h, w, _ = x.shape
+    x_pitch = x.stride(2)
+    ho = conv_out_size(h, kh, stride, pad, dil)
+    wo = conv_out_size(w, kw, stride, pad, dil)
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), dtype=torch.float32 if out_f32 else BF16, device=x.device)
+    d = ConvDesc()
+    d.x, d.wgt, d.bias, d.residual, d.y = ptr(x), ptr(wgt), ptr(bias), ptr(residual), ptr(out)
+    d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
+    d.kh, d.kw, d.stride, d.pad, d.dil = kh, kw, stride, pad, dil
+    d.x_pitch, d.y_pitch = x_pitch, out.stride(2)
+    d.res_pitch = residual.stride(2) if residual is not None else 0
+    d.act = act
+    d.flags = (_lib.FLAG_OUT_F32 if out_f32 else 0) | (_lib.FLAG_RES_AFTER_ACT if res_after_act else 0)
+    call("eqxv_conv2d_igemm_bf16", C.byref(d), stream)
+    return out
+
+
+def gemm(a, wgt, bias, *, act=0, residual=None, out=None, out_f32=False, res_after_act=False, stream=0):
+    """out[m, n] = act(a[m, :k] @ wgt[n, :k]^T + bias (+ residual)); a/out row-major with pitch."""
+    _check_cuda(a, wgt, bias, residual, out)
+    m, k = a.shape
+    n = wgt.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32 if out_f32 else BF16, device=a.device)
+    flags = (_lib.FLAG_OUT_F32 if out_f32 else 0) | (_lib.FLAG_RES_AFTER_ACT if res_after_act else 0)
+    call("eqxv_gemm_bias_act_res_bf16", ptr(a), a.stride(0), ptr(wgt), ptr(bias), ptr(residual),
+         residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), m, n, k, act, flags,
+         stream)
+    return out
+
+
+def pack_stem_input(x_nchw, out=None, stream=0):
+    _check_cuda(x_nchw, out)
+    n, c, h, w = x_nchw.shape
+    assert c == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    if out is None:
+        out = torch.empty((n, h + 6, w + 8, 8), dtype=BF16, device=x_nchw.device)
+    call("eqxv_pack_stem_input", ptr(x_nchw), ptr(out), n, h, w, stream)
+    return out
+
+
+def conv_stem7x7(xpad, wgt, bias, *, n, h, w, cout, act=1, out=None, stream=0):
+    _check_cuda(xpad, wgt, bias, out)
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, cout), dtype=BF16, device=xpad.device)
+    call("eqxv_conv_stem7x7_bf16", ptr(xpad), ptr(wgt), ptr(bias), ptr(out), n, h, w, cout,
+         out.stride(2), act, stream)
+    return out
+
+
+def nchw_to_nhwc(x, c_pad=None, out=None, stream=0):
+    _check_cuda(x, out)
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    c_pad = c_pad or (c + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((n, h, w, c_pad), dtype=BF16, device=x.device)
+    call("eqxv_nchw_f32_to_nhwc_bf16", ptr(x), ptr(out), n, c, h, w, c_pad, stream)
+    return out
+
+
+def nhwc_to_nchw(x, c=None, out=None, stream=0):
+    _check_cuda(x, out)
+    n, h, w, cc = x.shape
+    c = c or cc
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    call("eqxv_nhwc_bf16_to_nchw_f32", ptr(x), ptr(out), n, c, h, w, x.stride(2), stream)
+    return out
+
+
+def maxpool2d(x, k, stride, pad, out=None, stream=0):
+    _check_cuda(x, out)
+    n, h, w, c = x.shape
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    call("eqxv_maxpool2d_nhwc_bf16", ptr(x), ptr(out), n, h, w, c, k, stride, pad, x.stride(2),
+         out.stride(2), stream)
+    return out
+
+
+def avgpool2d(x, k, stride, out=None, stream=0):
+    _check_cuda(x, out)
+    n, h, w, c = x.shape
+    ho, wo = (h - k) // stride + 1, (w - k) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    call("eqxv_avgpool2d_nhwc_bf16", ptr(x), ptr(out), n, h, w, c, k, stride, x.stride(2),
+         out.stride(2), stream)
+    return out
+
+
+def adaptive_avgpool(x, oh, ow, out=None, stream=0):
+    _check_cuda(x, out)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, oh, ow, c), dtype=BF16, device=x.device)
+    call("eqxv_adaptive_avgpool_nhwc_bf16", ptr(x), ptr(out), n, h, w, c, oh, ow, x.stride(2),
+         out.stride(2), stream)
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None, stream=0):
+    _check_cuda(x, gamma, beta, out)
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty((rows, d), dtype=BF16, device=x.device)
+    call("eqxv_layernorm_bf16", ptr(x), x.stride(0), ptr(gamma), ptr(beta), ptr(out), out.stride(0),
+         rows, d, float(eps), stream)
+    return out
+
+
+def attention(qkv, images, tokens, heads, head_dim, scale, out=None, stream=0):
+    _check_cuda(qkv, out)
+    if out is None:
+        out = torch.empty((images * tokens, heads * head_dim), dtype=BF16, device=qkv.device)
+    call("eqxv_attention_fwd_bf16", ptr(qkv), ptr(out), None, images, tokens, heads, head_dim,
+         float(scale), stream)
+    return out
+
+
+def patchify(x_nchw, p, out=None, stream=0):
+    _check_cuda(x_nchw, out)
+    n, c, h, w = x_nchw.shape
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    if out is None:
+        out = torch.empty((n * (h // p) * (w // p), c * p * p), dtype=BF16, device=x_nchw.device)
+    call("eqxv_patchify_nchw_f32_bf16", ptr(x_nchw), ptr(out), n, c, h, w, p, stream)
+    return out
+
+
+def vit_assemble_tokens(patches, cls, pos, n, np_, d, out=None, stream=0):
+    _check_cuda(patches, cls, pos, out)
+    if out is None:
+        out = torch.empty((n * (np_ + 1), d), dtype=BF16, device=patches.device)
+    call("eqxv_vit_assemble_tokens_bf16", ptr(patches), ptr(cls), ptr(pos), ptr(out), n, np_, d, stream)
+    return out
+
+
+def gather_rows(x, n, tokens, row, out=None, stream=0):
+    _check_cuda(x, out)
+    d = x.shape[1]
+    if out is None:
+        out = torch.empty((n, d), dtype=BF16, device=x.device)
+    call("eqxv_gather_rows_bf16", ptr(x), x.stride(0), ptr(out), out.stride(0), n, tokens, row, d, stream)
+    return out

@@ -1,0 +1,171 @@
+/*
+ * eqxv_b200.h — C ABI of libeqxv_b200.so: the B200 (sm_100a) implementation of eqxvision's
+ * vmapped inference forward pass.
+ *
+ * The reference (paganpasta/eqxvision) has no FFI: its boundary is the Python API, and all
+ * arithmetic is delegated to equinox.nn / jax.lax (third party). Each entry point below therefore
+ * cites the reference call site(s) whose arithmetic it replaces. Paths are relative to the
+ * reference checkout.
+ *
+ * Conventions
+ *   - every function returns 0 (EQXV_OK) or a negative eqxv_status; the text of the last failure
+ *     on the calling thread is returned by eqxv_last_error().
+ *   - the caller owns every buffer (device pointers; PyTorch CUDA tensors are used as holders),
+ *     nothing is allocated inside, nothing synchronises the host: all launches go to `stream`
+ *     (a cudaStream_t passed as void*) and are CUDA-Graph capturable.
+ *   - activations are channels-last bf16: [N, H, W, pitch] with `pitch >= C` elements per pixel
+ *     (pitch % 8 == 0, base 16-byte aligned). Token matrices are row-major [rows, pitch].
+ *   - convolution / linear weights are bf16, K-major: [Cout, kh*kw*Cin] with the BatchNorm scale
+ *     already folded in (see eqxvision_b200/_pack.py); `bias` is the fp32 folded shift.
+ */
+#ifndef EQXV_B200_H_
+#define EQXV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum eqxv_status {
+  EQXV_OK = 0,
+  EQXV_ERR_INVALID_ARGUMENT = -1,
+  EQXV_ERR_UNSUPPORTED = -2,
+  EQXV_ERR_CUDA = -3,
+  EQXV_ERR_NO_DEVICE = -4
+} eqxv_status;
+
+/* epilogue activations (jax.nn.* used by the reference models) */
+typedef enum eqxv_act {
+  EQXV_ACT_NONE = 0,
+  EQXV_ACT_RELU = 1,        /* jnn.relu         resnet.py:70, vgg.py:141 */
+  EQXV_ACT_SILU = 2,        /* jnn.silu         efficientnet.py:134 */
+  EQXV_ACT_GELU_TANH = 3,   /* jnn.gelu (approximate=True default)  vit.py:96, mlps.py:62 */
+  EQXV_ACT_HARDSWISH = 4,   /* jnn.hard_swish   mobilenetv3.py:79 */
+  EQXV_ACT_SIGMOID = 5,     /* jnn.sigmoid      squeeze.py:42 */
+  EQXV_ACT_HARDSIGMOID = 6, /* jnn.hard_sigmoid mobilenetv3.py:57 */
+  EQXV_ACT_RELU6 = 7
+} eqxv_act;
+
+enum {
+  EQXV_FLAG_OUT_F32 = 1,        /* y is fp32 (logits); residual not allowed */
+  EQXV_FLAG_RES_AFTER_ACT = 2   /* y = act(conv + bias) + residual  (default: act(conv+bias+res)) */
+};
+
+const char* eqxv_version(void);
+const char* eqxv_last_error(void);
+/* Binds the calling thread to `device`, raises the kernels' dynamic shared-memory limits and
+ * resolves cuTensorMapEncodeTiled. Must be called once per process before any other entry. */
+int eqxv_init(int device);
+int eqxv_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1/K2: dense convolution as implicit GEMM on tcgen05 tensor cores, fused epilogue
+ *   y = act( conv(x, w) + bias [+ residual] )      (or act(...) + residual with RES_AFTER_ACT)
+ * Replaces  equinox.nn.Conv2d -> lax.conv_general_dilated  +  experimental.BatchNorm(inference)
+ *           + jnn.<act>  (+ `out += identity`)  as composed in
+ *   resnet.py:144-162 (_ResNetBottleneck.__call__), resnet.py:80-92, resnet.py:344-346 (stem),
+ *   layers/conv_norm_activation.py:61-85, vgg.py:137-145, deeplabv3.py:43-53, densenet.py:66.
+ * groups must be 1. kh*kw taps are walked over 64-channel K blocks; A tiles are 4-D TMA boxes of
+ * the NHWC input (zero fill gives the padding, box traversal stride gives the conv stride).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct eqxv_conv_desc {
+  const void* x;        /* bf16 [n, h, w, x_pitch]            */
+  const void* wgt;      /* bf16 [cout, kh*kw*cin]             */
+  const float* bias;    /* fp32 [cout] or NULL                */
+  const void* residual; /* bf16 [n, ho, wo, res_pitch] or NULL */
+  void* y;              /* bf16 (fp32 with OUT_F32) [n, ho, wo, y_pitch] */
+  int32_t n, h, w, cin, cout;
+  int32_t kh, kw, stride, pad, dil;
+  int32_t x_pitch, y_pitch, res_pitch;
+  int32_t act;   /* eqxv_act */
+  int32_t flags; /* EQXV_FLAG_* */
+} eqxv_conv_desc;
+int eqxv_conv2d_igemm_bf16(const eqxv_conv_desc* d, void* stream);
+
+/* K5: out[m, :n] = act(a[m, :k] @ w[n, :k]^T + bias [+ residual])  — the same tcgen05 kernel with
+ * one tap. Replaces equinox.nn.Linear under jax.vmap: vit.py:64,74 (qkv, proj), mlps.py:61-65
+ * (fc1/fc2), resnet.py:356 (fc), vgg.py:97-106, and every 1x1 stride-1 Conv2d. */
+int eqxv_gemm_bias_act_res_bf16(const void* a, int64_t lda, const void* w, const float* bias,
+                                const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t m,
+                                int32_t n, int32_t k, int32_t act, int32_t flags, void* stream);
+
+/* ResNet stem: conv 7x7 stride 2 pad 3, 3 -> cout channels (+ folded BN + ReLU), resnet.py:243-251,
+ * 344-346. Input is the padded 8-channel image written by eqxv_pack_stem_input; weights are
+ * [cout, 7, 8, 8] bf16 (tap row, 8 columns of which 7 are real, 8 channels of which 3 are real). */
+int eqxv_conv_stem7x7_bf16(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n,
+                           int32_t h, int32_t w, int32_t cout, int32_t y_pitch, int32_t act,
+                           void* stream);
+/* fp32 NCHW [n,3,h,w] (the reference's input layout, README.md:45) -> bf16 [n, h+6, w+8, 8]:
+ * the image sits at rows 3..h+2, columns 3..w+2; border and channels 3..7 are zero. */
+int eqxv_pack_stem_input(const float* x_nchw, void* xpad, int32_t n, int32_t h, int32_t w,
+                         void* stream);
+
+/* input boundary: fp32 NCHW -> bf16 NHWC with channels zero-padded to c_pad (multiple of 8) */
+int eqxv_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t c_pad, void* stream);
+/* output boundary: bf16 NHWC -> fp32 NCHW (feature maps returned to the caller, test_vgg.py:30) */
+int eqxv_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t x_pitch, void* stream);
+
+/* K9: equinox.nn.MaxPool2d(k, stride, padding) (-inf padding): resnet.py:254, vgg.py:134 */
+int eqxv_maxpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                             int32_t k, int32_t stride, int32_t pad, int32_t x_pitch, int32_t y_pitch,
+                             void* stream);
+/* K10: equinox.nn.AvgPool2d(k, stride) (densenet.py:128) */
+int eqxv_avgpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                             int32_t k, int32_t stride, int32_t x_pitch, int32_t y_pitch, void* stream);
+/* K10: AdaptiveAvgPool2d((oh, ow)) with h % oh == 0 and w % ow == 0 (block mean), resnet.py:283,
+ * vgg.py:90; (1,1) is the global pool that feeds the classifier. */
+int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w,
+                                    int32_t c, int32_t oh, int32_t ow, int32_t x_pitch,
+                                    int32_t y_pitch, void* stream);
+
+/* K7: equinox.nn.LayerNorm(d, eps) per row (vit.py:149,154,272 under jax.vmap) */
+int eqxv_layernorm_bf16(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y,
+                        int64_t ldy, int64_t rows, int32_t d, float eps, void* stream);
+
+/* K6: softmax(q k^T * scale) v for `heads` heads of dim 64 over `tokens` tokens per image,
+ * vit.py:62-73. qkv is [images*tokens, 3*heads*64] with column order (3, heads, 64) as produced by
+ * reshape(N,3,H,d) (vit.py:65); out is [images*tokens, heads*64] (vit.py:73). If `attn_out` is
+ * non-NULL the fp32 probabilities [images, heads, tokens, tokens] are also written
+ * (return_attention path, vit.py:151-152). */
+int eqxv_attention_fwd_bf16(const void* qkv, void* out, float* attn_out, int32_t images,
+                            int32_t tokens, int32_t heads, int32_t head_dim, float scale,
+                            void* stream);
+
+/* K12: patch rows for PatchEmbed (layers/patch_embed.py:79-82): fp32 NCHW [n,c,h,w] ->
+ * bf16 [n*gh*gw, c*p*p] with the K order (c, py, px) of the conv weight flattened. */
+int eqxv_patchify_nchw_f32_bf16(const float* x, void* rows, int32_t n, int32_t c, int32_t h,
+                                int32_t w, int32_t p, void* stream);
+/* tokens = concat([cls_token, patches]) + pos_embed  (vit.py:269); patches [n*np, d] bf16,
+ * cls [d] / pos [(np+1), d] fp32, out [n*(np+1), d] bf16 */
+int eqxv_vit_assemble_tokens_bf16(const void* patches, const float* cls, const float* pos, void* out,
+                                  int32_t n, int32_t np, int32_t d, void* stream);
+/* gather row `row` of every image's token block: [n*tokens, d] -> [n, d]  (x[0], vit.py:273) */
+int eqxv_gather_rows_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t n,
+                          int32_t tokens, int32_t row, int32_t d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * plumbing: streams, CUDA graphs, events (cudaStream_t / cudaGraphExec_t / cudaEvent_t as void*)
+ * ------------------------------------------------------------------------------------------- */
+int eqxv_stream_create(void** stream);
+int eqxv_stream_destroy(void* stream);
+int eqxv_stream_sync(void* stream);
+int eqxv_graph_begin(void* stream);
+int eqxv_graph_end(void* stream, void** graph_exec);
+int eqxv_graph_launch(void* graph_exec, void* stream);
+int eqxv_graph_destroy(void* graph_exec);
+int eqxv_event_create(void** ev);
+int eqxv_event_destroy(void* ev);
+int eqxv_event_record(void* ev, void* stream);
+int eqxv_event_sync(void* ev);
+int eqxv_event_elapsed_ms(void* start, void* stop, float* ms);
+int eqxv_memcpy_h2d_async(void* dst, const void* src, int64_t bytes, void* stream);
+int eqxv_memcpy_d2h_async(void* dst, const void* src, int64_t bytes, void* stream);
+int eqxv_memset_async(void* dst, int value, int64_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQXV_B200_H_ */
