@@ -1,0 +1,396 @@
+"""Symbolic per-sample values and the lazy expression DAG the models are written against.
+
+The reference models are per-sample functions batched by `jax.vmap` and traced once by
+`eqx.filter_jit` (README.md:37-46). Here a model's `__call__` runs once on a `Sym` (a per-sample
+shape plus an expression node); nothing is computed while tracing. Conv/Linear nodes absorb the
+BatchNorm, activation and residual-add that follow them (immutably: folding returns a new node), so
+that what reaches the plan builder (`_engine.py`) is already the fused-kernel granularity of
+libeqxv_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+# ------------------------------------------------------------------------------------------------
+# expression nodes
+# ------------------------------------------------------------------------------------------------
+
+
+class Expr:
+    __slots__ = ()
+
+
+class Input(Expr):
+    """the fp32 NCHW image batch handed to the model"""
+    __slots__ = ()
+
+
+class Const(Expr):
+    """a parameter tensor used as a data operand (cls_token, pos_embed, ...)"""
+    __slots__ = ("value",)
+
+    def __init__(self, value):
+        self.value = value
+
+
+class Conv(Expr):
+    __slots__ = ("x", "weight", "bias", "stride", "padding", "dilation", "groups", "bn", "act1", "res", "act2")
+
+    def __init__(self, x, weight, bias, stride, padding, dilation, groups, bn=None, act1=None, res=None,
+                 act2=None):
+        self.x, self.weight, self.bias = x, weight, bias
+        self.stride, self.padding, self.dilation, self.groups = stride, padding, dilation, groups
+        self.bn, self.act1, self.res, self.act2 = bn, act1, res, act2
+
+    def replace(self, **kw):
+        d = {k: getattr(self, k) for k in self.__slots__}
+        d.update(kw)
+        return Conv(**d)
+
+
+class Linear(Expr):
+    __slots__ = ("x", "weight", "bias", "act1", "res", "act2")
+
+    def __init__(self, x, weight, bias, act1=None, res=None, act2=None):
+        self.x, self.weight, self.bias, self.act1, self.res, self.act2 = x, weight, bias, act1, res, act2
+
+    def replace(self, **kw):
+        d = {k: getattr(self, k) for k in self.__slots__}
+        d.update(kw)
+        return Linear(**d)
+
+
+class BNAct(Expr):  # standalone per-channel affine (+activation): densenet.py:64-65
+    __slots__ = ("x", "bn", "act")
+
+    def __init__(self, x, bn, act=None):
+        self.x, self.bn, self.act = x, bn, act
+
+
+class Act(Expr):
+    __slots__ = ("x", "act")
+
+    def __init__(self, x, act):
+        self.x, self.act = x, act
+
+
+class Add(Expr):
+    __slots__ = ("a", "b", "act")
+
+    def __init__(self, a, b, act=None):
+        self.a, self.b, self.act = a, b, act
+
+
+class ChannelScale(Expr):  # x * s with s of shape (C,1,1): squeeze.py:61
+    __slots__ = ("x", "s")
+
+    def __init__(self, x, s):
+        self.x, self.s = x, s
+
+
+class Pool(Expr):
+    __slots__ = ("x", "mode", "k", "stride", "pad")
+
+    def __init__(self, x, mode, k, stride, pad):
+        self.x, self.mode, self.k, self.stride, self.pad = x, mode, k, stride, pad
+
+
+class AdaptiveAvgPool(Expr):
+    __slots__ = ("x", "oh", "ow")
+
+    def __init__(self, x, oh, ow):
+        self.x, self.oh, self.ow = x, oh, ow
+
+
+class Ravel(Expr):  # (C,H,W) -> (C*H*W,) in C,H,W order (jnp.ravel)
+    __slots__ = ("x",)
+
+    def __init__(self, x):
+        self.x = x
+
+
+class ToTokens(Expr):  # (C,H,W) -> (H*W, C): vmap(ravel) + moveaxis, patch_embed.py:81-82
+    __slots__ = ("x",)
+
+    def __init__(self, x):
+        self.x = x
+
+
+class ToMap(Expr):  # (H*W, C) -> (C,H,W): extensions_2d.py:27-28
+    __slots__ = ("x", "h", "w")
+
+    def __init__(self, x, h, w):
+        self.x, self.h, self.w = x, h, w
+
+
+class LayerNormE(Expr):
+    __slots__ = ("x", "weight", "bias", "eps")
+
+    def __init__(self, x, weight, bias, eps):
+        self.x, self.weight, self.bias, self.eps = x, weight, bias, eps
+
+
+class Attention(Expr):  # vit.py:62-73
+    __slots__ = ("qkv", "heads", "scale")
+
+    def __init__(self, qkv, heads, scale):
+        self.qkv, self.heads, self.scale = qkv, heads, scale
+
+
+class AttentionProbs(Expr):  # the (1, heads, T, T) softmax matrix, vit.py:70 / 151-152
+    __slots__ = ("qkv", "heads", "scale")
+
+    def __init__(self, qkv, heads, scale):
+        self.qkv, self.heads, self.scale = qkv, heads, scale
+
+
+class ClsPos(Expr):  # concat([cls, x]) + pos_embed, vit.py:269
+    __slots__ = ("x", "cls", "pos")
+
+    def __init__(self, x, cls, pos):
+        self.x, self.cls, self.pos = x, cls, pos
+
+
+class SelectRow(Expr):
+    __slots__ = ("x", "row")
+
+    def __init__(self, x, row):
+        self.x, self.row = x, row
+
+
+class Concat(Expr):  # channel concatenation, densenet.py:63, deeplabv3.py:134
+    __slots__ = ("xs",)
+
+    def __init__(self, xs):
+        self.xs = tuple(xs)
+
+
+class Resize(Expr):  # jax.image.resize(method="bilinear"), _utils.py:52
+    __slots__ = ("x", "h", "w")
+
+    def __init__(self, x, h, w):
+        self.x, self.h, self.w = x, h, w
+
+
+# ------------------------------------------------------------------------------------------------
+# symbolic value
+# ------------------------------------------------------------------------------------------------
+
+
+class Sym:
+    """A per-sample array placeholder. kind: 'chw' (C,H,W), 'tokens' (T,D), 'vec' (D,), 'attn'."""
+    __slots__ = ("kind", "shape", "expr", "__weakref__")
+
+    def __init__(self, kind: str, shape: Tuple[int, ...], expr: Expr):
+        self.kind, self.shape, self.expr = kind, tuple(int(s) for s in shape), expr
+
+    # -- arithmetic the reference models use on activations --
+    def __add__(self, other):
+        return add(self, other)
+
+    __radd__ = __add__
+
+    def __iadd__(self, other):  # `out += identity` (resnet.py:159): Syms are immutable
+        return add(self, other)
+
+    def __mul__(self, other):
+        return mul(self, other)
+
+    __rmul__ = __mul__
+
+    def __getitem__(self, idx):
+        if self.kind == "tokens" and isinstance(idx, int):
+            return select_row(self, idx)
+        raise TypeError(f"unsupported index {idx!r} on a {self.kind} Sym")
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def __repr__(self):
+        return f"Sym({self.kind}{self.shape} <- {type(self.expr).__name__})"
+
+
+def is_sym(x) -> bool:
+    return isinstance(x, Sym)
+
+
+def _act_name(fn) -> Optional[str]:
+    if fn is None:
+        return None
+    if isinstance(fn, str):
+        return fn
+    name = getattr(fn, "act_name", None)
+    if name is None:
+        raise TypeError(f"{fn!r} is not an eqxvision_b200 activation (use eqxvision_b200.functional.*)")
+    return name
+
+
+# ------------------------------------------------------------------------------------------------
+# graph-building primitives (used by eqxvision_b200.nn / functional)
+# ------------------------------------------------------------------------------------------------
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def conv2d(x: Sym, weight, bias, stride, padding, dilation, groups) -> Sym:
+    if x.kind != "chw":
+        raise ValueError(f"Conv2d expects a (C,H,W) input, got {x}")
+    cout, cin_g, kh, kw = weight.shape
+    c, h, w = x.shape
+    if c != cin_g * groups:
+        raise ValueError(f"Conv2d: input has {c} channels, weight expects {cin_g * groups}")
+    (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
+    ho = (h + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    wo = (w + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    return Sym("chw", (cout, ho, wo), Conv(x, weight, bias, (sh, sw), (ph, pw), (dh, dw), groups))
+
+
+def linear(x: Sym, weight, bias) -> Sym:
+    out_f, in_f = weight.shape
+    if x.kind == "vec":
+        if x.shape[0] != in_f:
+            raise ValueError(f"Linear: expected {in_f} features, got {x.shape[0]}")
+        return Sym("vec", (out_f,), Linear(x, weight, bias))
+    if x.kind == "tokens":
+        if x.shape[1] != in_f:
+            raise ValueError(f"Linear: expected {in_f} features, got {x.shape[1]}")
+        return Sym("tokens", (x.shape[0], out_f), Linear(x, weight, bias))
+    raise ValueError(f"Linear expects a vector or token matrix, got {x}")
+
+
+def batch_norm(x: Sym, bn) -> Sym:
+    e = x.expr
+    if isinstance(e, Conv) and e.bn is None and e.act1 is None and e.res is None and e.act2 is None:
+        return Sym(x.kind, x.shape, e.replace(bn=bn))
+    return Sym(x.kind, x.shape, BNAct(x, bn))
+
+
+def activation(x: Sym, fn) -> Sym:
+    name = _act_name(fn)
+    if name is None:
+        return x
+    e = x.expr
+    if isinstance(e, (Conv, Linear)):
+        if e.res is None and e.act1 is None and e.act2 is None:
+            return Sym(x.kind, x.shape, e.replace(act1=name))
+        if e.res is not None and e.act1 is None and e.act2 is None:
+            return Sym(x.kind, x.shape, e.replace(act2=name))
+    if isinstance(e, BNAct) and e.act is None:
+        return Sym(x.kind, x.shape, BNAct(e.x, e.bn, name))
+    if isinstance(e, Add) and e.act is None:
+        return Sym(x.kind, x.shape, Add(e.a, e.b, name))
+    return Sym(x.kind, x.shape, Act(x, name))
+
+
+def add(a, b) -> Sym:
+    if not is_sym(a) or not is_sym(b):
+        raise TypeError("add: both operands must be symbolic activations")
+    if a.shape != b.shape:
+        raise ValueError(f"add: shape mismatch {a.shape} vs {b.shape}")
+    for p, q in ((a, b), (b, a)):
+        e = p.expr
+        if isinstance(e, (Conv, Linear)) and e.res is None and e.act2 is None:
+            return Sym(p.kind, p.shape, e.replace(res=q))
+    return Sym(a.kind, a.shape, Add(a, b))
+
+
+def mul(a, b) -> Sym:
+    if is_sym(a) and is_sym(b):
+        for x, s in ((a, b), (b, a)):
+            if x.kind == "chw" and s.kind == "chw" and s.shape == (x.shape[0], 1, 1):
+                return Sym("chw", x.shape, ChannelScale(x, s))
+    raise TypeError(f"mul: unsupported operands {a!r} * {b!r}")
+
+
+def pool2d(x: Sym, mode: str, k, stride, pad) -> Sym:
+    (kh, kw), (sh, sw), (ph, pw) = _pair(k), _pair(stride), _pair(pad)
+    if kh != kw or sh != sw or ph != pw:
+        raise NotImplementedError("only square pooling windows are supported")
+    c, h, w = x.shape
+    ho = (h + 2 * ph - kh) // sh + 1
+    wo = (w + 2 * pw - kw) // sw + 1
+    return Sym("chw", (c, ho, wo), Pool(x, mode, kh, sh, ph))
+
+
+def adaptive_avg_pool2d(x: Sym, target) -> Sym:
+    oh, ow = _pair(target)
+    c, h, w = x.shape
+    if (oh, ow) == (h, w):
+        return x
+    return Sym("chw", (c, oh, ow), AdaptiveAvgPool(x, oh, ow))
+
+
+def ravel(x: Sym) -> Sym:
+    if x.kind == "vec":
+        return x
+    if x.kind != "chw":
+        raise ValueError(f"ravel expects (C,H,W), got {x}")
+    c, h, w = x.shape
+    return Sym("vec", (c * h * w,), Ravel(x))
+
+
+def to_tokens(x: Sym) -> Sym:
+    c, h, w = x.shape
+    return Sym("tokens", (h * w, c), ToTokens(x))
+
+
+def to_map(x: Sym, h: int, w: int) -> Sym:
+    t, d = x.shape
+    assert t == h * w
+    return Sym("chw", (d, h, w), ToMap(x, h, w))
+
+
+def layer_norm(x: Sym, weight, bias, eps) -> Sym:
+    if x.kind not in ("tokens", "vec"):
+        raise ValueError(f"LayerNorm expects tokens or a vector, got {x}")
+    return Sym(x.kind, x.shape, LayerNormE(x, weight, bias, eps))
+
+
+def attention(qkv: Sym, heads: int, scale: float):
+    t, c3 = qkv.shape
+    c = c3 // 3
+    out = Sym("tokens", (t, c), Attention(qkv, heads, scale))
+    probs = Sym("attn", (1, heads, t, t), AttentionProbs(qkv, heads, scale))
+    return out, probs
+
+
+def prepend_cls_add_pos(x: Sym, cls_token, pos_embed) -> Sym:
+    t, d = x.shape
+    if tuple(pos_embed.shape) != (t + 1, d) or tuple(cls_token.shape) != (1, d):
+        raise ValueError("cls_token / pos_embed shape mismatch")
+    return Sym("tokens", (t + 1, d), ClsPos(x, cls_token, pos_embed))
+
+
+def select_row(x: Sym, row: int) -> Sym:
+    t, d = x.shape
+    if row < 0:
+        row += t
+    e = x.expr
+    if isinstance(e, LayerNormE):  # LayerNorm is row-wise: normalise only the selected row
+        return Sym("vec", (d,), LayerNormE(select_row(e.x, row), e.weight, e.bias, e.eps))
+    return Sym("vec", (d,), SelectRow(x, row))
+
+
+def concat_channels(xs: Sequence[Sym]) -> Sym:
+    xs = list(xs)
+    if len(xs) == 1:
+        return xs[0]
+    h, w = xs[0].shape[1:]
+    for x in xs:
+        if x.kind != "chw" or x.shape[1:] != (h, w):
+            raise ValueError("concat_channels: spatial shape mismatch")
+    return Sym("chw", (sum(x.shape[0] for x in xs), h, w), Concat(xs))
+
+
+def resize_bilinear(x: Sym, h: int, w: int) -> Sym:
+    c = x.shape[0]
+    return Sym("chw", (c, h, w), Resize(x, h, w))
+
+
+def const_like(t: torch.Tensor) -> Const:
+    return Const(t)
