@@ -1,0 +1,69 @@
+"""Host-side weight packing (one-off, at plan-build time).
+
+Same positional/reshape contract as the reference keeps its weights in (OIHW conv filters,
+(out,in) Linear matrices — utils.py:196-197 never transposes); the device layout is what the
+kernels want:
+  * conv filter OIHW fp32  ->  [O, kh*kw*I_pad] bf16, K-major (tap-major, channel-minor), with the
+    inference BatchNorm scale gamma/sqrt(var+eps) folded into the filter in fp32 before rounding;
+  * the remaining per-channel shift  beta - mean*scale (+ conv bias * scale)  stays fp32 and is
+    added in the GEMM epilogue.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def fold_bn(weight: torch.Tensor, bias: Optional[torch.Tensor], bn) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """weight (O, ...) fp32, bias (O,) or None, bn a nn.BatchNorm or None -> (w', b')"""
+    w = weight.detach().double()
+    b = None if bias is None else bias.detach().double().reshape(-1)
+    if bn is not None:
+        scale, shift = bn.folded()
+        scale, shift = scale.double(), shift.double()
+        w = w * scale.reshape(-1, *([1] * (w.dim() - 1)))
+        b = shift if b is None else b * scale + shift
+    return w.float(), (None if b is None else b.float())
+
+
+def pack_conv_weight(w_oihw: torch.Tensor, cin_pad: int) -> torch.Tensor:
+    """OIHW fp32 -> [O, kh*kw*cin_pad] bf16 (zero-padded input channels)"""
+    o, i, kh, kw = w_oihw.shape
+    w = w_oihw.permute(0, 2, 3, 1).contiguous()  # O, kh, kw, I
+    if cin_pad != i:
+        wp = torch.zeros(o, kh, kw, cin_pad, dtype=w.dtype)
+        wp[..., :i] = w
+        w = wp
+    return w.reshape(o, kh * kw * cin_pad).to(torch.bfloat16).contiguous()
+
+
+def pack_stem_weight(w_oihw: torch.Tensor) -> torch.Tensor:
+    """[O,3,7,7] -> [O, 7(r), 8(s), 8(c)] bf16 with zero taps/channels (see eqxv_conv_stem7x7_bf16)"""
+    o, i, kh, kw = w_oihw.shape
+    assert (i, kh, kw) == (3, 7, 7)
+    wp = torch.zeros(o, 7, 8, 8, dtype=torch.float32)
+    wp[:, :, :7, :3] = w_oihw.permute(0, 2, 3, 1)
+    return wp.reshape(o, 448).to(torch.bfloat16).contiguous()
+
+
+def pack_linear_weight(w: torch.Tensor, in_pad: int) -> torch.Tensor:
+    o, i = w.shape
+    if in_pad != i:
+        wp = torch.zeros(o, in_pad, dtype=w.dtype)
+        wp[:, :i] = w
+        w = wp
+    return w.to(torch.bfloat16).contiguous()
+
+
+def pack_depthwise_weight(w: torch.Tensor, c_pad: int) -> torch.Tensor:
+    """[C,1,kh,kw] fp32 -> [kh*kw, c_pad] fp32 (tap-major so a thread reads 8 contiguous channels)"""
+    c, one, kh, kw = w.shape
+    assert one == 1
+    out = torch.zeros(kh * kw, c_pad, dtype=torch.float32)
+    out[:, :c] = w.reshape(c, kh * kw).t()
+    return out.contiguous()

@@ -1,0 +1,190 @@
+"""ORACLE (test infrastructure, not product code) — CPU fp32 restatement of the third-party ops the
+reference delegates to (equinox.nn / equinox.experimental / jax.nn / jax.image; none of them is
+under /root/reference).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this package.
+
+Parity status: the reference cannot be imported here (jax / equinox are not installed and cannot
+be), so these functions are pinned (a) against torchvision on identical state_dicts at the
+reference's own tolerance atol=1e-4 (tests/test_oracle.py) for the families whose reference tests
+assert exactly that, and (b) by running the reference's OWN model files on top of these ops through
+the import shim in oracle/refshim (tests/test_refshim.py).  ViT has shape-only tests in the
+reference => "parity unpinned" beyond (b).
+
+Everything is plain torch on CPU in float32 (float64 where noted), written op by op.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    """equinox.nn.Conv2d.__call__: lax.conv_general_dilated(x[None], W, stride, [(p,p),(p,p)],
+    rhs_dilation=dil, feature_group_count=groups) + bias(O,1,1).  x: (N,C,H,W) batched here."""
+    b = None if bias is None else bias.reshape(-1)
+    return F.conv2d(x, weight, b, _pair(stride), _pair(padding), _pair(dilation), groups)
+
+
+def linear(x, weight, bias=None):
+    """equinox.nn.Linear: W @ x + b on the last axis"""
+    y = x @ weight.t()
+    return y if bias is None else y + bias
+
+
+def batch_norm_inference(x, weight, bias, mean, var, eps=1e-5):
+    """equinox.experimental.BatchNorm(inference): (x - mean)/sqrt(var+eps) * weight + bias, per channel"""
+    shape = (1, -1) + (1,) * (x.dim() - 2)
+    y = (x - mean.reshape(shape)) / torch.sqrt(var.reshape(shape) + eps)
+    if weight is not None:
+        y = y * weight.reshape(shape)
+    if bias is not None:
+        y = y + bias.reshape(shape)
+    return y
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    """equinox.nn.LayerNorm: biased variance over the last axis"""
+    mean = x.mean(-1, keepdim=True)
+    var = ((x - mean) ** 2).mean(-1, keepdim=True)
+    y = (x - mean) * torch.rsqrt(var + eps)
+    if weight is not None:
+        y = y * weight
+    if bias is not None:
+        y = y + bias
+    return y
+
+
+def max_pool2d(x, k, stride, padding=0):
+    """equinox.nn.MaxPool2d: reduce_window(max) with -inf padding (use_ceil=False)"""
+    return F.max_pool2d(x, _pair(k), _pair(stride), _pair(padding))
+
+
+def avg_pool2d(x, k, stride):
+    return F.avg_pool2d(x, _pair(k), _pair(stride))
+
+
+def adaptive_avg_pool2d(x, target):
+    """equinox.nn.AdaptiveAvgPool2d for the even-split case (dim % target == 0): block mean"""
+    oh, ow = _pair(target)
+    n, c, h, w = x.shape
+    if h % oh or w % ow:
+        raise NotImplementedError("uneven adaptive pooling differs between equinox and torch")
+    return x.reshape(n, c, oh, h // oh, ow, w // ow).mean((3, 5))
+
+
+# jax.nn activations ---------------------------------------------------------------------------
+def relu(x):
+    return torch.clamp_min(x, 0.0)
+
+
+def relu6(x):
+    return torch.clamp(x, 0.0, 6.0)
+
+
+def silu(x):
+    return x * torch.sigmoid(x)
+
+
+def gelu_tanh(x):
+    """jax.nn.gelu(approximate=True), the default used by vit.py:96 / mlps.py:62"""
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
+
+
+def hard_sigmoid(x):
+    return relu6(x + 3.0) / 6.0
+
+
+def hard_swish(x):
+    return x * hard_sigmoid(x)
+
+
+def sigmoid(x):
+    return torch.sigmoid(x)
+
+
+ACTS = {None: lambda v: v, "relu": relu, "relu6": relu6, "silu": silu, "gelu": gelu_tanh,
+        "hard_sigmoid": hard_sigmoid, "hard_swish": hard_swish, "sigmoid": sigmoid}
+
+
+def softmax(x, dim=-1):
+    m = x.max(dim, keepdim=True).values
+    e = torch.exp(x - m)
+    return e / e.sum(dim, keepdim=True)
+
+
+def resize_bilinear(x, h, w):
+    """jax.image.resize(method='bilinear') when upsampling == half-pixel centres, edge clamped
+    (== F.interpolate(mode='bilinear', align_corners=False); asserted by test_deeplabv3.py:27)"""
+    return F.interpolate(x, size=(h, w), mode="bilinear", align_corners=False)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused-op helpers + optional bf16 emulation
+# ------------------------------------------------------------------------------------------------
+# The device path stores every activation in bf16 and rounds exactly once per fused kernel
+# (conv + folded BN + activation (+ residual)), with the BatchNorm scale folded into the bf16
+# filter.  With `emulate_bf16(True)` the helpers below round at the same points, so the oracle
+# becomes a bit-faithful model of the device arithmetic up to fp32 summation order; the tests use it
+# to separate implementation errors (tight tolerance vs the emulation) from the precision gap
+# (stated tolerance vs the plain fp32 oracle).
+_EMULATE = False
+
+
+class emulate_bf16:
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        global _EMULATE
+        self.prev, _EMULATE = _EMULATE, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global _EMULATE
+        _EMULATE = self.prev
+
+
+def rnd(x):
+    """round to bf16 (round-to-nearest-even) when emulating, identity otherwise"""
+    return x.to(torch.bfloat16).to(torch.float32) if _EMULATE else x
+
+
+def conv_bn_act(x, weight, bias=None, bn=None, stride=1, padding=0, dilation=1, groups=1, act=None, res=None,
+                res_after_act=False, eps=1e-5, round_out=True):
+    """Conv2d -> [BatchNorm(inference)] -> act, with the residual added before (default) or after the
+    activation: one fused device kernel.  bn = (weight, bias, mean, var)."""
+    if _EMULATE:
+        w = weight.double()
+        b = None if bias is None else bias.double().reshape(-1)
+        if bn is not None:
+            scale = bn[0].double() / torch.sqrt(bn[3].double() + eps)
+            shift = bn[1].double() - bn[2].double() * scale
+            w = w * scale.reshape(-1, 1, 1, 1)
+            b = shift if b is None else b * scale + shift
+        y = conv2d(rnd(x), rnd(w.float()), None if b is None else b.float(), stride, padding, dilation, groups)
+    else:
+        y = conv2d(x, weight, bias, stride, padding, dilation, groups)
+        if bn is not None:
+            y = batch_norm_inference(y, bn[0], bn[1], bn[2], bn[3], eps)
+    if res is not None and not res_after_act:
+        y = y + res
+    y = ACTS[act](y)
+    if res is not None and res_after_act:
+        y = y + res
+    return rnd(y) if round_out else y
+
+
+def linear_act(x, weight, bias=None, act=None, res=None, round_out=True):
+    """Linear -> act (+ residual after): one fused device GEMM"""
+    y = linear(rnd(x), rnd(weight), bias)
+    y = ACTS[act](y)
+    if res is not None:
+        y = y + res
+    return rnd(y) if round_out else y

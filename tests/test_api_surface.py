@@ -1,0 +1,173 @@
+"""Host-side surface: constructor names/signatures, error conventions and the
+tracer's fusion decisions — all without a GPU."""
+import inspect
+
+import pytest
+import torch
+
+import eqxvision_b200 as eb
+from eqxvision_b200 import _trace as T
+from eqxvision_b200 import functional as F
+from eqxvision_b200 import layers, models, nn
+
+KEY = eb.random.PRNGKey(0)
+
+
+def trace(module, shape, kind="chw", method="__call__", **kw):
+    fn = getattr(type(module), method)
+    fn = getattr(fn, "__wrapped__", fn)
+    kw.setdefault("key", KEY)
+    return fn(module, T.Sym(kind, shape, T.Input()), **kw)
+
+
+def test_exported_names():
+    for name in ["resnet18", "resnet50", "resnet101", "wide_resnet50_2", "resnext50_32x4d", "ResNet",
+                 "vit_tiny", "vit_small", "vit_base", "VisionTransformer", "_VitAttention", "_VitBlock"]:
+        assert hasattr(models, name), name
+    for name in ["ConvNormActivation", "SqueezeExcitation", "PatchEmbed", "MlpProjection", "DropPath",
+                 "LayerNorm2d", "Linear2d"]:
+        assert hasattr(layers, name), name
+    assert callable(eb.vmap) and callable(eb.filter_jit) and callable(eb.tree_inference)
+
+
+def test_constructor_signatures_match_reference():
+    p = inspect.signature(models.ResNet.__init__).parameters
+    assert list(p)[1:] == ["block", "layers", "num_classes", "groups", "width_per_group",
+                           "replace_stride_with_dilation", "norm_layer", "key"]
+    assert p["num_classes"].default == 1000 and p["key"].kind is inspect.Parameter.KEYWORD_ONLY
+    p = inspect.signature(models.VisionTransformer.__init__).parameters
+    assert list(p)[1:] == ["img_size", "patch_size", "in_chans", "num_classes", "embed_dim", "depth", "num_heads",
+                           "mlp_ratio", "qkv_bias", "qk_scale", "drop_rate", "attn_drop_rate", "drop_path_rate",
+                           "norm_layer", "key"]
+    assert p["num_classes"].default == 0 and p["qkv_bias"].default is True
+    p = inspect.signature(models.vit_base).parameters
+    assert [p[k].default for k in ("patch_size", "embed_dim", "depth", "num_heads", "mlp_ratio")] == [16, 768, 12, 12, 4]
+    p = inspect.signature(layers.ConvNormActivation.__init__).parameters
+    assert list(p)[1:] == ["in_channels", "out_channels", "kernel_size", "stride", "padding", "groups",
+                           "norm_layer", "activation_layer", "dilation", "use_bias", "key"]
+
+
+def test_resnet_requires_key_and_traces_to_fused_graph():
+    net = eb.tree_inference(models.resnet50(), True)
+    with pytest.raises(RuntimeError, match="PRNGKey"):
+        trace(net, (3, 224, 224), key=None)
+    out = trace(net, (3, 224, 224))
+    assert out.kind == "vec" and out.shape == (1000,)
+    e = out.expr
+    assert isinstance(e, T.Linear) and isinstance(e.x.expr, T.Ravel)
+    last = e.x.expr.x.expr.x.expr           # ravel <- avgpool <- last bottleneck output
+    assert isinstance(last, T.Conv) and last.bn is not None and last.res is not None and last.act2 == "relu"
+    assert isinstance(last.x.expr, T.Conv) and last.x.expr.act1 == "relu" and last.x.expr.weight.shape[-1] == 3
+
+    def count(expr, seen):
+        if id(expr) in seen or not isinstance(expr, T.Expr):
+            return 0
+        seen.add(id(expr))
+        n = 1 if isinstance(expr, T.Conv) else 0
+        for s in getattr(expr, "__slots__", ()):
+            v = getattr(expr, s)
+            for u in (v if isinstance(v, (tuple, list)) else (v,)):
+                if isinstance(u, T.Sym):
+                    n += count(u.expr, seen)
+        return n
+
+    assert count(e, set()) == 53  # every BatchNorm / ReLU / residual add folded into its conv
+
+
+def test_resnet_errors():
+    with pytest.raises(ValueError):
+        models.ResNet(models.classification.resnet._ResNetBottleneck, [1, 1, 1, 1],
+                      replace_stride_with_dilation=[True])
+    with pytest.raises(NotImplementedError):
+        models.ResNet(models.classification.resnet._ResNetBottleneck, [1, 1, 1, 1], norm_layer=nn.LayerNorm)
+    with pytest.raises(NotImplementedError, match="tree_inference"):
+        trace(models.resnet18(), (3, 64, 64))  # training-mode BatchNorm is out of scope: loud, not silent
+
+
+def test_dilated_resnet_keeps_resolution():
+    net = eb.tree_inference(models.resnet50(replace_stride_with_dilation=[False, True, True]), True)
+    x = T.Sym("chw", (3, 128, 128), T.Input())
+    y = net.maxpool(net.relu(net.bn1(net.conv1(x))))
+    y = net.layer3(net.layer2(net.layer1(y, key=KEY), key=KEY), key=KEY)
+    assert y.shape == (1024, 16, 16)
+    assert net.layer3.layers[0].conv2.dilation == (1, 1) and net.layer3.layers[1].conv2.dilation == (2, 2)
+    assert net.layer4.layers[0].conv2.dilation == (2, 2) and net.layer4.layers[2].conv2.dilation == (4, 4)
+
+
+def test_patch_embed_shape_and_size_check():
+    pe = layers.PatchEmbed(224, 16, 3, 768, flatten=True, key=KEY)
+    out = trace(pe, (3, 224, 224))
+    assert out.kind == "tokens" and out.shape == (196, 768)       # reference test_layers.py:17
+    with pytest.raises(ValueError):
+        trace(pe, (3, 225, 224))
+
+
+def test_vit_shapes_and_modes():
+    for fn, dim in [(models.vit_tiny, 192), (models.vit_small, 384), (models.vit_base, 768)]:
+        net = fn(num_classes=1000)
+        assert trace(net, (3, 224, 224)).shape == (1000,)          # reference test_vit.py:101
+    assert trace(models.vit_small(num_classes=0), (3, 224, 224)).shape == (384,)  # test_vit.py:113
+    net = models.VisionTransformer(img_size=224, patch_size=16)
+    with pytest.raises(ValueError):
+        trace(net, (3, 224, 224), method="get_last_self_attention")  # test_vit.py:75-76
+    net = eb.tree_inference(net, True)
+    attn = trace(net, (3, 224, 224), method="get_last_self_attention")
+    assert attn.shape == (1, 12, 197, 197)                          # test_vit.py:66
+    out = trace(models.vit_base(num_classes=10), (3, 224, 224))
+    head = out.expr
+    assert isinstance(head, T.Linear) and isinstance(head.x.expr, T.LayerNormE)
+    assert isinstance(head.x.expr.x.expr, T.SelectRow)              # final LayerNorm only on the CLS row
+
+
+def test_vit_attention_and_block_submodules():
+    att = models._VitAttention(32, num_heads=4, qkv_bias=True, key=KEY)
+    out, probs = trace(att, (8, 32), kind="tokens")
+    assert out.shape == (8, 32) and probs.shape == (1, 4, 8, 8)    # reference test_vit.py:19-29
+    blk = models._VitBlock(32, num_heads=4, key=KEY)
+    assert trace(blk, (8, 32), kind="tokens").shape == (8, 32)
+    assert trace(blk, (8, 32), kind="tokens", return_attention=True).shape == (1, 4, 8, 8)
+
+
+def test_mlp_and_droppath_and_dropout():
+    mlp = layers.MlpProjection(16, 32, 8, act_layer=F.gelu, key=KEY)
+    out = trace(mlp, (5, 16), kind="tokens")
+    assert out.shape == (5, 8) and out.expr.x.expr.act1 == "gelu"
+    dp = layers.DropPath(p=0.5)
+    x = T.Sym("tokens", (4, 8), T.Input())
+    with pytest.raises(RuntimeError):
+        dp(x, key=None)
+    assert eb.tree_inference(dp, True)(x, key=None) is x           # drop_path.py:44-45
+    assert layers.DropPath(p=0.0)(x, key=None) is x
+    with pytest.raises(NotImplementedError):
+        nn.Dropout(0.5)(x, key=KEY)
+    assert nn.Dropout(0.5, inference=True)(x) is x
+
+
+def test_conv_norm_activation_and_se_trace():
+    cna = eb.tree_inference(layers.ConvNormActivation(8, 16, 3, key=KEY), True)
+    y = trace(cna, (8, 10, 10))
+    assert y.shape == (16, 10, 10) and y.expr.bn is not None and y.expr.act1 == "relu"
+    assert cna.layers[0].bias is None                               # bias only without a norm layer
+    assert layers.ConvNormActivation(8, 16, 3, norm_layer=None, key=KEY).layers[0].bias is not None
+    se = layers.SqueezeExcitation(16, 4, key=KEY)
+    z = trace(se, (16, 6, 6))
+    assert z.shape == (16, 6, 6) and isinstance(z.expr, T.ChannelScale)
+    assert z.expr.s.expr.act1 == "sigmoid" and z.expr.s.expr.x.expr.act1 == "relu"
+
+
+def test_tree_inference_is_functional():
+    net = models.resnet18()
+    inf = eb.tree_inference(net, True)
+    assert inf is not net and inf.bn1.inference and not net.bn1.inference
+    assert inf.conv1.weight is net.conv1.weight                     # arrays are shared, flags are not
+
+
+def test_vmap_rejects_unsupported_axes_and_needs_cuda():
+    net = eb.tree_inference(models.resnet18(), True)
+    with pytest.raises(NotImplementedError):
+        eb.vmap(net, in_axes=1)
+    with pytest.raises(TypeError):
+        eb.vmap(lambda x: x)
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception, match="CUDA|fallback"):
+            eb.vmap(net, axis_name="batch")(torch.zeros(1, 3, 64, 64), key=[KEY])

@@ -1,0 +1,186 @@
+"""Kernel-level parity on a B200: every C-ABI compute entry against a torch fp32 functional
+reference on bf16-rounded inputs. bf16 outputs: rel-L2 <= 4e-3 (one rounding, 2^-9 relative),
+fp32 outputs: rel-L2 <= 1e-5; pure data-movement kernels must be bit exact."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+ACTS = {0: lambda v: v, 1: F.relu, 2: F.silu, 3: lambda v: F.gelu(v, approximate="tanh"), 4: F.hardswish,
+        5: torch.sigmoid, 6: F.hardsigmoid, 7: F.relu6}
+TOL_BF16 = 4e-3
+
+
+def rb(device, *shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(device)
+
+
+def rel_l2(got, ref):
+    got, ref = got.float(), ref.float()
+    assert not torch.isnan(got).any()
+    return ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, dil, act, res, res_after
+    (4, 56, 56, 64, 256, 1, 1, 0, 1, 1, True, False),     # R50 layer1 expand + identity + relu
+    (2, 56, 56, 64, 64, 3, 1, 1, 1, 1, False, False),
+    (8, 28, 28, 128, 128, 3, 1, 1, 1, 0, False, False),
+    (32, 14, 14, 256, 256, 3, 1, 1, 1, 1, False, False),
+    (5, 7, 7, 512, 512, 3, 1, 1, 1, 0, False, False),      # n not a multiple of the image tile
+    (3, 17, 13, 72, 40, 3, 1, 1, 1, 2, False, False),      # ragged everything
+    (2, 32, 32, 64, 64, 3, 1, 2, 2, 0, False, False),      # dilation 2 (DeepLab backbone)
+    (2, 16, 16, 64, 64, 3, 1, 12, 12, 0, False, False),    # ASPP d12: taps skipped when fully padded
+    (2, 28, 28, 64, 64, 3, 1, 1, 1, 2, True, True),        # act then residual (FusedMBConv order)
+    (2, 56, 56, 256, 512, 1, 2, 0, 1, 0, False, False),    # downsample 1x1 stride 2
+    (2, 56, 56, 128, 128, 3, 2, 1, 1, 1, False, False),    # 3x3 stride 2
+    (8, 14, 14, 512, 512, 3, 2, 1, 1, 0, False, False),
+    (2, 224, 224, 8, 48, 3, 2, 1, 1, 2, False, False),     # EfficientNet stem on the padded image
+    (1, 1, 1, 2048, 272, 1, 1, 0, 1, 4, False, False),     # SE-style 1x1 on a 1x1 map, odd N
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv2d_igemm(device, case):
+    from eqxvision_b200 import ops
+
+    n, h, w, cin, cout, k, stride, pad, dil, act, res, res_after = case
+    x = rb(device, n, h, w, cin, seed=1)
+    wt = rb(device, cout, k, k, cin, scale=(k * k * cin) ** -0.5, seed=2)
+    bias = torch.randn(cout, generator=torch.Generator().manual_seed(3)).to(device)
+    ho, wo = ops.conv_out_size(h, k, stride, pad, dil), ops.conv_out_size(w, k, stride, pad, dil)
+    r = rb(device, n, ho, wo, cout, seed=4) if res else None
+    y = ops.conv2d(x, wt.reshape(cout, -1), bias, cin=cin, cout=cout, kh=k, kw=k, stride=stride, pad=pad,
+                   dil=dil, act=act, residual=r, res_after_act=res_after)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, stride=stride,
+                   padding=pad, dilation=dil)
+    rr = r.float().permute(0, 3, 1, 2) if res else 0
+    ref = ACTS[act](ref) + rr if res_after else ACTS[act](ref + rr)
+    assert rel_l2(y, ref.permute(0, 2, 3, 1)) < TOL_BF16
+
+
+GEMM_CASES = [
+    (128, 64, 64, 0, False, False), (1000, 128, 192, 0, False, False), (40000, 64, 64, 1, False, False),
+    (12608, 2304, 768, 0, False, False), (12608, 768, 3072, 0, True, False), (12608, 3072, 768, 3, False, False),
+    (256, 1000, 2048, 0, False, True), (300, 272, 1632, 0, False, False), (512, 24, 144, 2, False, False),
+    (512, 64, 24, 1, False, False), (7, 448, 8, 5, False, False), (130, 2688, 112, 6, False, False),
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_gemm(device, case):
+    from eqxvision_b200 import ops
+
+    m, n, k, act, res, f32 = case
+    a = rb(device, m, k, seed=1)
+    wt = rb(device, n, k, scale=k ** -0.5, seed=2)
+    bias = torch.randn(n, generator=torch.Generator().manual_seed(3)).to(device)
+    r = rb(device, m, n, seed=4) if res else None
+    y = ops.gemm(a, wt, bias, act=act, residual=r, out_f32=f32)
+    ref = ACTS[act](a.float() @ wt.float().t() + bias + (r.float() if res else 0))
+    assert rel_l2(y, ref) < (1e-5 if f32 else TOL_BF16)
+
+
+def test_gemm_strided_views_and_padding_columns_stay_untouched(device):
+    from eqxvision_b200 import ops
+
+    big_in = rb(device, 300, 96, seed=1)
+    big_out = torch.full((300, 80), 7.0, dtype=torch.bfloat16, device=device)
+    a = big_in[:, 16:80]                      # pitch 96, 64 columns, 32-byte offset
+    out = big_out[:, 8:48]                    # pitch 80, 40 columns
+    wt = rb(device, 40, 64, scale=0.125, seed=2)
+    ops.gemm(a, wt, None, out=out)
+    ref = a.float() @ wt.float().t()
+    assert rel_l2(out, ref) < TOL_BF16
+    assert (big_out[:, :8] == 7).all() and (big_out[:, 48:] == 7).all()
+
+
+def test_stem(device):
+    from eqxvision_b200 import _pack, ops
+
+    n, h, w, cout = 3, 224, 224, 64
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(n, 3, h, w, generator=g).to(device)
+    wt = torch.randn(cout, 3, 7, 7, generator=g) * 0.1
+    bias = torch.randn(cout, generator=g).to(device)
+    xpad = ops.pack_stem_input(x)
+    ref_pad = torch.zeros(n, h + 6, w + 8, 8, device=device)
+    ref_pad[:, 3:h + 3, 3:w + 3, :3] = x.permute(0, 2, 3, 1)
+    assert torch.equal(xpad, ref_pad.to(torch.bfloat16))
+    y = ops.conv_stem7x7(xpad, _pack.pack_stem_weight(wt).to(device), bias, n=n, h=h, w=w, cout=cout, act=1)
+    ref = F.relu(F.conv2d(x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float().to(device), bias,
+                          stride=2, padding=3))
+    assert rel_l2(y, ref.permute(0, 2, 3, 1)) < TOL_BF16
+
+
+def test_pooling_and_layout(device):
+    from eqxvision_b200 import ops
+
+    x = rb(device, 4, 112, 112, 64)
+    xn = x.float().permute(0, 3, 1, 2)
+    assert torch.equal(ops.maxpool2d(x, 3, 2, 1).float(), F.max_pool2d(xn, 3, 2, 1).permute(0, 2, 3, 1))
+    assert torch.equal(ops.maxpool2d(x, 2, 2, 0).float(), F.max_pool2d(xn, 2, 2, 0).permute(0, 2, 3, 1))
+    assert rel_l2(ops.avgpool2d(x, 2, 2), F.avg_pool2d(xn, 2, 2).permute(0, 2, 3, 1)) < TOL_BF16
+    x7 = rb(device, 6, 7, 7, 2048)
+    assert rel_l2(ops.adaptive_avgpool(x7, 1, 1), x7.float().mean((1, 2), keepdim=True)) < TOL_BF16
+    x14 = rb(device, 2, 14, 14, 512)
+    ref = F.adaptive_avg_pool2d(x14.float().permute(0, 3, 1, 2), 7).permute(0, 2, 3, 1)
+    assert rel_l2(ops.adaptive_avgpool(x14, 7, 7), ref) < TOL_BF16
+    xi = torch.rand(3, 3, 32, 40, device=device)
+    ref = torch.zeros(3, 32, 40, 8, device=device)
+    ref[..., :3] = xi.permute(0, 2, 3, 1)
+    assert torch.equal(ops.nchw_to_nhwc(xi, 8), ref.to(torch.bfloat16))
+    xb = rb(device, 2, 9, 11, 40)
+    assert torch.equal(ops.nhwc_to_nchw(xb), xb.float().permute(0, 3, 1, 2))
+
+
+@pytest.mark.parametrize("rows,d", [(1000, 768), (333, 96), (64, 2048), (5, 192)])
+def test_layernorm(device, rows, d):
+    from eqxvision_b200 import ops
+
+    x = rb(device, rows, d, scale=2.0)
+    g = torch.randn(d, device=device)
+    b = torch.randn(d, device=device)
+    assert rel_l2(ops.layernorm(x, g, b, 1e-5), F.layer_norm(x.float(), (d,), g, b, 1e-5)) < TOL_BF16
+
+
+@pytest.mark.parametrize("imgs,tokens,heads", [(2, 197, 12), (1, 64, 3), (3, 50, 6), (1, 785, 6), (2, 1, 2)])
+def test_attention(device, imgs, tokens, heads):
+    from eqxvision_b200 import ops
+
+    qkv = rb(device, imgs * tokens, 3 * heads * 64, seed=tokens)
+    out = ops.attention(qkv, imgs, tokens, heads, 64, 0.125)
+    q, k, v = qkv.float().reshape(imgs, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1)
+    ref = (att @ v).permute(0, 2, 1, 3).reshape(imgs * tokens, heads * 64)
+    assert rel_l2(out, ref) < 6e-3  # P is rounded to bf16 before P.V
+
+
+def test_vit_glue(device):
+    from eqxvision_b200 import ops
+
+    xi = torch.rand(2, 3, 224, 224, device=device)
+    rows = ops.patchify(xi, 16)
+    ref = xi.reshape(2, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(2 * 196, 768)
+    assert torch.equal(rows, ref.to(torch.bfloat16))
+    cls = torch.randn(768, device=device)
+    pos = torch.randn(197, 768, device=device)
+    tok = ops.vit_assemble_tokens(rows, cls, pos, 2, 196, 768)
+    ref = torch.cat([cls.expand(2, 1, 768), rows.float().reshape(2, 196, 768)], 1) + pos
+    assert rel_l2(tok, ref.reshape(-1, 768)) < TOL_BF16
+    assert torch.equal(ops.gather_rows(tok, 2, 197, 0), tok.reshape(2, 197, 768)[:, 0])
+
+
+def test_argument_errors_are_reported_not_crashed(device):
+    from eqxvision_b200 import _lib, ops
+
+    x = rb(device, 1, 8, 8, 12)  # 12 channels: not a multiple of 8
+    with pytest.raises(_lib.EqxvError, match="multiple of 8"):
+        ops.conv2d(x, rb(device, 16, 12), None, cin=12, cout=16, kh=1, kw=1)
+    with pytest.raises(_lib.EqxvError, match="unsupported"):
+        ops.attention(rb(device, 8, 3 * 2 * 32), 1, 8, 2, 32, 0.1)
+    with pytest.raises(_lib.EqxvError):
+        ops.conv2d(torch.zeros(1, 8, 8, 8, dtype=torch.bfloat16), rb(device, 16, 8), None, cin=8, cout=16,
+                   kh=1, kw=1)  # CPU tensor: no fallback

@@ -1,0 +1,160 @@
+"""Model-level parity on a B200, through the public surface (constructors + load_torch_weights +
+vmap) and therefore through the C ABI.
+
+Two comparisons per model:
+  * against the bf16-EMULATING oracle (rounds where the device rounds): implementation check,
+  * against the plain fp32 oracle (the reference's arithmetic): the stated bf16 tolerance.
+Tolerances are rel-L2 over the logits of seeded synthetic checkpoints (oracle/checkpoints.py).
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def build(name, sd, save_checkpoint, **kw):
+    import eqxvision_b200 as eb
+
+    net = getattr(eb.models, name)(torch_weights=save_checkpoint(sd, name + ".pth"), **kw)
+    return eb.tree_inference(net, True)
+
+
+def keys(n):
+    import eqxvision_b200 as eb
+
+    return eb.random.split(eb.random.PRNGKey(0), n)
+
+
+# (arch, input hw, batch, tol vs emulation, tol vs fp32)
+RESNETS = [("resnet18", 224, 4, 1.0e-2, 3e-2), ("resnet34", 128, 3, 1.5e-2, 4e-2), ("resnet50", 224, 4, 2.0e-2, 6e-2)]
+
+
+@pytest.mark.parametrize("arch,hw,batch,tol_emu,tol_f32", RESNETS)
+def test_resnet_parity(device, save_checkpoint, arch, hw, batch, tol_emu, tol_f32):
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    sd = ck.torchvision_state_dict(arch, seed=1)
+    net = build(arch, sd, save_checkpoint)
+    x = ck.synthetic_images(batch, h=hw, w=hw, seed=2)
+    got = eb.vmap(net, axis_name="batch")(x, key=keys(batch))
+    assert got.shape == (batch, 1000) and got.dtype == torch.float32 and got.is_cuda
+    ref = om.resnet(sd, x, arch)
+    with O.emulate_bf16():
+        emu = om.resnet(sd, x, arch)
+    assert rel(got, emu) < tol_emu, ("vs bf16-emulating oracle", rel(got, emu))
+    assert rel(got, ref) < tol_f32, ("vs fp32 oracle", rel(got, ref))
+    assert (got.cpu().argmax(1) == emu.argmax(1)).float().mean() >= 0.75
+
+
+def test_vit_base_parity(device, save_checkpoint):
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    sd = ck.vit_state_dict(embed_dim=768, depth=12, heads=12, num_classes=1000, seed=3)
+    net = build("vit_base", sd, save_checkpoint, num_classes=1000)
+    x = ck.synthetic_images(2, seed=4)
+    got = eb.vmap(net)(x, key=keys(2))
+    ref = om.vit(sd, x, heads=12)
+    with O.emulate_bf16():
+        emu = om.vit(sd, x, heads=12)
+    assert got.shape == (2, 1000)
+    assert rel(got, emu) < 1.5e-2 and rel(got, ref) < 3e-2, (rel(got, emu), rel(got, ref))
+
+
+def test_vit_small_default_returns_cls_feature(device, save_checkpoint):
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+
+    sd = ck.vit_state_dict(embed_dim=384, depth=3, heads=6, num_classes=0, seed=5)
+    net = build("vit_small", sd, save_checkpoint, depth=3)
+    x = ck.synthetic_images(3, seed=6)
+    got = eb.vmap(net)(x, key=keys(3))
+    assert got.shape == (3, 384)                  # reference test_vit.py:113
+    assert rel(got, om.vit(sd, x, heads=6)) < 2e-2
+
+
+def test_single_sample_call_equals_batched_row(device, save_checkpoint):
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+
+    sd = ck.torchvision_state_dict("resnet18", seed=1)
+    net = build("resnet18", sd, save_checkpoint)
+    x = ck.synthetic_images(4, h=96, w=96, seed=2)
+    batched = eb.vmap(net, axis_name="batch")(x, key=keys(4))
+    one = net(x[2], key=eb.random.PRNGKey(1))   # the reference's native per-sample convention
+    assert one.shape == (1000,)
+    assert torch.equal(one, batched[2])
+    with pytest.raises(RuntimeError, match="PRNGKey"):
+        net(x[0], key=None)
+
+
+def test_batch_is_a_pure_map_bitwise(device, save_checkpoint):
+    """sharding property (multi-GPU correctness without a collective): logits of an image do not
+    depend on which batch / position it is processed in."""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+
+    sd = ck.torchvision_state_dict("resnet50", seed=1)
+    net = build("resnet50", sd, save_checkpoint)
+    x = ck.synthetic_images(8, seed=9)
+    full = eb.vmap(net, axis_name="batch")(x, key=keys(8))
+    lo = eb.vmap(net, axis_name="batch")(x[:4], key=keys(4))
+    hi = eb.vmap(net, axis_name="batch")(x[4:], key=keys(4))
+    assert torch.equal(full, torch.cat([lo, hi]))
+    perm = torch.tensor([3, 1, 7, 0, 5, 2, 6, 4])
+    assert torch.equal(eb.vmap(net, axis_name="batch")(x[perm], key=keys(8)), full[perm])
+
+
+def test_full_size_batch_properties(device, save_checkpoint):
+    """BASELINE size (ResNet-50, batch 256): the oracle is too slow for 256 images, so check
+    size-independent properties: finite, duplicate images give identical rows, and the first rows
+    equal the small-batch result that IS oracle-checked above."""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+
+    sd = ck.torchvision_state_dict("resnet50", seed=1)
+    net = build("resnet50", sd, save_checkpoint)
+    x4 = ck.synthetic_images(4, seed=2)
+    x = x4.repeat(64, 1, 1, 1)
+    out = eb.vmap(net, axis_name="batch")(x, key=keys(256))
+    assert out.shape == (256, 1000) and torch.isfinite(out).all()
+    small = eb.vmap(net, axis_name="batch")(x4, key=keys(4))
+    assert torch.equal(out.reshape(64, 4, 1000), small.unsqueeze(0).expand(64, 4, 1000))
+
+
+def test_golden_vectors(device, save_checkpoint):
+    """committed fixtures (tests/golden/make_golden.py): expected outputs of the fp32 oracle for
+    seeded inputs/checkpoints, regenerated weights must reproduce them through the CUDA path."""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+
+    g = torch.load(os.path.join(GOLDEN, "golden_v1.pt"))
+    for name, rec in g.items():
+        if rec["family"] == "resnet":
+            sd = ck.torchvision_state_dict(rec["arch"], seed=rec["seed"])
+            net = build(rec["arch"], sd, save_checkpoint)
+            x = ck.synthetic_images(rec["n"], h=rec["hw"], w=rec["hw"], seed=rec["img_seed"])
+            got = eb.vmap(net, axis_name="batch")(x, key=keys(rec["n"]))
+        elif rec["family"] == "vit":
+            sd = ck.vit_state_dict(seed=rec["seed"], **rec["cfg"])
+            net = build(rec["ctor"], sd, save_checkpoint, **rec["ctor_kw"])
+            x = ck.synthetic_images(rec["n"], seed=rec["img_seed"])
+            got = eb.vmap(net)(x, key=keys(rec["n"]))
+        else:
+            continue
+        assert rel(got, rec["expected"]) < rec["tol"], (name, rel(got, rec["expected"]))

@@ -1,0 +1,142 @@
+"""Pins the CPU oracle: (1) against torchvision on identical seeded state_dicts at the reference's
+own tolerance (atol=1e-4: tests/test_models/test_resnet.py:24 of the reference), (2) ViT against an
+independent einsum restatement, (3) the bf16-emulating mode stays within the stated gap."""
+import math
+
+import pytest
+import torch
+
+from oracle import checkpoints as ck
+from oracle import models as om
+from oracle import ops as O
+
+
+@pytest.mark.parametrize("arch,hw", [("resnet18", 96), ("resnet34", 64), ("resnet50", 96)])
+def test_resnet_oracle_matches_torchvision(arch, hw):
+    m = ck.torchvision_model(arch, seed=1)
+    x = ck.synthetic_images(2, h=hw, w=hw, seed=2)
+    with torch.no_grad():
+        ref = m(x)
+    got = om.resnet(m.state_dict(), x, arch)
+    assert torch.isclose(got, ref, atol=1e-4).all(), (got - ref).abs().max()
+
+
+def test_resnet_oracle_dilated_stages_match_torchvision():
+    import torchvision
+
+    torch.manual_seed(0)
+    m = torchvision.models.resnet50(weights=None, replace_stride_with_dilation=[False, True, True])
+    ck._perturb_and_calibrate(m, 5, (2, 3, 64, 64))
+    x = ck.synthetic_images(1, h=64, w=64, seed=3)
+    with torch.no_grad():
+        t = m.maxpool(m.relu(m.bn1(m.conv1(x))))
+        l3 = m.layer3(m.layer2(m.layer1(t)))
+        l4 = m.layer4(l3)
+    stages = om.resnet_features(om.Stream(m.state_dict()), x, "resnet50", (False, True, True))
+    assert stages[2].shape == l3.shape == (1, 1024, 8, 8)
+    assert torch.isclose(stages[2], l3, atol=1e-4).all()
+    assert torch.isclose(stages[3], l4, atol=1e-4).all()
+
+
+def _vit_einsum(sd, x, heads):
+    """independent restatement of vit.py:56-76,139-157,261-273 with einsum / explicit formulas"""
+    w = [v.double() for v in sd.values()]
+    cls, pos, pw, pb = w[0].reshape(1, -1), w[1].reshape(-1, w[1].shape[-1]), w[2], w[3]
+    d = pw.shape[0]
+    p = pw.shape[-1]
+    b = x.shape[0]
+    g = x.shape[-1] // p
+    patches = x.double().reshape(b, 3, g, p, g, p)
+    tok = torch.einsum("bcipjq,dcpq->bijd", patches, pw).reshape(b, g * g, d) + pb
+    t = torch.cat([cls.expand(b, 1, d), tok], 1) + pos
+    i = 4
+
+    def ln(v, gw, gb):
+        mu = v.mean(-1, keepdim=True)
+        var = (v * v).mean(-1, keepdim=True) - mu * mu
+        return (v - mu) / torch.sqrt(var + 1e-5) * gw + gb
+
+    depth = (len(w) - 4 - 2) // 12
+    for _ in range(depth):
+        n1w, n1b, qw, qb, ow, ob, n2w, n2b, f1w, f1b, f2w, f2b = w[i:i + 12]
+        i += 12
+        y = ln(t, n1w, n1b)
+        qkv = torch.einsum("bnc,oc->bno", y, qw) + qb
+        q, k, v = qkv.reshape(b, -1, 3, heads, d // heads).unbind(2)
+        s = torch.einsum("bnhd,bmhd->bhnm", q, k) * (d // heads) ** -0.5
+        a = torch.exp(s - s.amax(-1, keepdim=True))
+        a = a / a.sum(-1, keepdim=True)
+        o = torch.einsum("bhnm,bmhd->bnhd", a, v).reshape(b, -1, d)
+        t = t + torch.einsum("bnc,oc->bno", o, ow) + ob
+        y = ln(t, n2w, n2b)
+        h = torch.einsum("bnc,oc->bno", y, f1w) + f1b
+        h = 0.5 * h * (1 + torch.tanh(math.sqrt(2 / math.pi) * (h + 0.044715 * h ** 3)))
+        t = t + torch.einsum("bnc,oc->bno", h, f2w) + f2b
+    out = ln(t, w[i], w[i + 1])[:, 0]
+    if len(w) > i + 2:
+        out = out @ w[i + 2].t() + w[i + 3]
+    return out.float()
+
+
+def test_vit_oracle_matches_independent_restatement():
+    sd = ck.vit_state_dict(embed_dim=192, depth=3, heads=3, num_classes=10, seed=3)
+    x = ck.synthetic_images(2, seed=4)
+    assert torch.isclose(om.vit(sd, x, heads=3), _vit_einsum(sd, x, 3), atol=1e-4).all()
+
+
+def test_vit_oracle_default_has_no_head():
+    """num_classes=0 (the reference default, vit.py:178): output is the normalised CLS feature"""
+    sd = ck.vit_state_dict(embed_dim=192, depth=1, heads=3, num_classes=0, seed=3)
+    out = om.vit(sd, ck.synthetic_images(1, seed=4), heads=3)
+    assert out.shape == (1, 192)
+
+
+def test_vit_oracle_matches_torchvision_encoder_block():
+    """one encoder block against torchvision's EncoderBlock configured with the reference's
+    eps=1e-5 and tanh-GELU"""
+    import functools
+
+    from torchvision.models.vision_transformer import EncoderBlock
+
+    torch.manual_seed(0)
+    blk = EncoderBlock(3, 192, 768, 0.0, 0.0, norm_layer=functools.partial(torch.nn.LayerNorm, eps=1e-5)).eval()
+    blk.mlp[1] = torch.nn.GELU(approximate="tanh")
+    t = torch.randn(2, 17, 192)
+    with torch.no_grad():
+        ref = blk(t)
+    sa = blk.self_attention
+    y = O.layer_norm(t, blk.ln_1.weight, blk.ln_1.bias, 1e-5)
+    # torch packs q,k,v as three row blocks: the same (3, heads, d) column order as vit.py:65
+    t2, _ = om.vit_attention(y, sa.in_proj_weight, sa.in_proj_bias, sa.out_proj.weight, sa.out_proj.bias, 3,
+                             res=t)
+    y = O.layer_norm(t2, blk.ln_2.weight, blk.ln_2.bias, 1e-5)
+    y = O.linear_act(y, blk.mlp[0].weight, blk.mlp[0].bias, act="gelu")
+    got = O.linear_act(y, blk.mlp[3].weight, blk.mlp[3].bias, res=t2)
+    assert torch.isclose(got.detach(), ref, atol=1e-4).all()
+
+
+def test_bf16_emulation_gap_is_small_and_off_by_default():
+    sd = ck.torchvision_state_dict("resnet18", seed=1)
+    x = ck.synthetic_images(2, h=64, w=64, seed=2)
+    ref = om.resnet(sd, x, "resnet18")
+    assert not O._EMULATE
+    with O.emulate_bf16():
+        emu = om.resnet(sd, x, "resnet18")
+    assert not O._EMULATE
+    rel = ((emu - ref).norm() / ref.norm()).item()
+    assert 1e-4 < rel < 3e-2, rel
+
+
+def test_activation_definitions():
+    x = torch.linspace(-5, 5, 101)
+    assert torch.allclose(O.hard_sigmoid(x), torch.nn.functional.hardsigmoid(x), atol=1e-6)
+    assert torch.allclose(O.hard_swish(x), torch.nn.functional.hardswish(x), atol=1e-6)
+    assert torch.allclose(O.gelu_tanh(x), torch.nn.functional.gelu(x, approximate="tanh"), atol=1e-6)
+    assert torch.allclose(O.silu(x), torch.nn.functional.silu(x), atol=1e-6)
+
+
+def test_adaptive_pool_even_split_only():
+    x = torch.arange(2 * 3 * 14 * 14, dtype=torch.float32).reshape(2, 3, 14, 14)
+    assert torch.allclose(O.adaptive_avg_pool2d(x, 7), torch.nn.functional.adaptive_avg_pool2d(x, 7))
+    with pytest.raises(NotImplementedError):
+        O.adaptive_avg_pool2d(x, 5)
