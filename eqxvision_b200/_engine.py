@@ -472,7 +472,8 @@ def _static_key(v):
 def get_plan(module, method: str, batch: int, in_shape, args=(), kwargs=None) -> Plan:
     kwargs = kwargs or {}
     key = (method, batch, tuple(in_shape), tuple(_static_key(a) for a in args),
-           tuple(sorted((k, _static_key(v)) for k, v in kwargs.items() if k != "key")))
+           tuple(sorted((k, _static_key(v)) for k, v in kwargs.items() if k != "key")),
+           kwargs.get("key") is None)  # ResNet raises without a key (resnet.py:341-342): trace both ways
     cache = _plan_cache(module)
     if key not in cache:
         cache[key] = build_plan(module, method, batch, tuple(in_shape), args, kwargs)

@@ -65,14 +65,6 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
 
 // A tap whose whole box lies in the zero padding contributes nothing (dilated ASPP convs,
 // deeplabv3.py:43-53 with d=24/36 on a 64x64 map): producer and MMA issuer skip it identically.
-__device__ __forceinline__ bool tap_valid(const IgemmParams& p, const TileCoord& t, int r, int s,
-                                          int& hc, int& wc) {
-  hc = t.h0 * p.mul_h + r * p.dil_h - p.pad_h;
-  wc = t.w0 * p.mul_w + s * p.dil_w - p.pad_w;
-  const bool h_ok = (hc + (p.th - 1) * p.mul_h >= 0) && (hc < p.in_h);
-  const bool w_ok = (wc + (p.tw - 1) * p.mul_w >= 0) && (wc < p.in_w);
-  return h_ok && w_ok;
-}
 
 // The activation is a template parameter of the kernel: a per-element runtime switch inside the
 // fully unrolled epilogue turned it into ~200 KB of branchy code and made every chunk I-cache bound
@@ -118,10 +110,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
-  const uint32_t tmem_slot = bars + 8u * (2 * S + 6);
+  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };  // 8: (epilogue warp, buffer)
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 12);
   volatile uint32_t* tmem_slot_g =
-      reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 6));
+      reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 12));
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -135,9 +127,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 128);
-      mbar_init(rfull_bar(a), 1);
     }
+    for (int b = 0; b < 8; ++b) mbar_init(rfull_bar(b), 1);
     mbar_fence_init();
+  }
+  // folded-BN shift / bias for every output column, once per CTA (zero beyond cout)
+  {
+    float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
+    const int ncols_pad = p.n_tiles * p.block_n + 64;
+    for (int i = threadIdx.x; i < ncols_pad; i += kThreads)
+      sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -152,22 +151,30 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        for (int tap = 0; tap < taps; ++tap) {
-          const int r = tap / p.kw, s = tap - r * p.kw;
-          int hc, wc;
-          if (!tap_valid(p, t, r, s, hc, wc)) continue;
+    // The whole warp walks the (uniform) loop and ONE elected lane issues: keeping control flow
+    // warp-uniform lets the compiler hold descriptors/coordinates in uniform registers. (A
+    // single-thread `if (lane == 0)` region made every UTMALDG/UTCHMMA an ELECT+BRA.U.ANY loop and
+    // the issue thread, not the tensor pipe, the bottleneck: profiles/r01_igemm_*.)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      for (int r = 0; r < p.kh; ++r) {
+        const int hc = t.h0 * p.mul_h + r * p.dil_h - p.pad_h;
+        if (hc + (p.th - 1) * p.mul_h < 0 || hc >= p.in_h) continue;  // tap row entirely in the padding
+        for (int s = 0; s < p.kw; ++s) {
+          const int wc = t.w0 * p.mul_w + s * p.dil_w - p.pad_w;
+          if (wc + (p.tw - 1) * p.mul_w < 0 || wc >= p.in_w) continue;
+          const int kb = (r * p.kw + s) * p.cin_pack;
           for (int c = 0; c < p.kchunks; ++c) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = base + stage * stage_bytes;
-            const uint32_t b_dst = a_dst + kABytes;
-            mbar_expect_tx(full_bar(stage), stage_bytes);
-            tma_load_4d(a_dst, &p.tmA, full_bar(stage), c * kBlockK, wc, hc, t.n0);
-            tma_load_2d(b_dst, &p.tmB, full_bar(stage), tap * p.cin_pack + c * kBlockK, t.ncol0);
+            if (elect_one()) {
+              const uint32_t a_dst = base + stage * stage_bytes;
+              mbar_expect_tx(full_bar(stage), stage_bytes);
+              tma_load_4d(a_dst, &p.tmA, full_bar(stage), c * kBlockK, wc, hc, t.n0);
+              tma_load_2d(a_dst + kABytes, &p.tmB, full_bar(stage), kb + c * kBlockK, t.ncol0);
+            }
+            __syncwarp();
             if (++stage == S) {
               stage = 0;
               phase ^= 1u;
@@ -178,85 +185,96 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-        uint32_t accumulate = 0;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int r = tap / p.kw, s = tap - r * p.kw;
-          int hc, wc;
-          if (!tap_valid(p, t, r, s, hc, wc)) continue;
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
+    const uint64_t desc_hi = umma_desc_sw128(0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+      uint32_t accumulate = 0;
+      for (int r = 0; r < p.kh; ++r) {
+        const int hc = t.h0 * p.mul_h + r * p.dil_h - p.pad_h;
+        if (hc + (p.th - 1) * p.mul_h < 0 || hc >= p.in_h) continue;
+        for (int s = 0; s < p.kw; ++s) {
+          const int wc = t.w0 * p.mul_w + s * p.dil_w - p.pad_w;
+          if (wc + (p.tw - 1) * p.mul_w < 0 || wc >= p.in_w) continue;
           for (int c = 0; c < p.kchunks; ++c) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t a_src = base + stage * stage_bytes;
-            const uint32_t b_src = a_src + kABytes;
-            const uint64_t adesc = umma_desc_sw128(a_src);
-            const uint64_t bdesc = umma_desc_sw128(b_src);
+            if (elect_one()) {
+              const uint32_t a_src = base + stage * stage_bytes;
+              const uint64_t adesc = desc_hi | (uint64_t)((a_src & 0x3FFFF) >> 4);
+              const uint64_t bdesc = desc_hi | (uint64_t)(((a_src + kABytes) & 0x3FFFF) >> 4);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // +32 bytes per 16-element K step inside the 128-byte swizzle row
-              umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                        accumulate);
-              accumulate = 1;
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // +32 bytes per 16-element K step inside the 128-byte swizzle row
+                umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                          accumulate | (uint32_t)k);
+              }
+              umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
             }
-            umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            __syncwarp();
+            accumulate = 1;
             if (++stage == S) {
               stage = 0;
               phase ^= 1u;
             }
           }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
+      if (elect_one()) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     // ============================== epilogue (warps 2..5) ==============================
+    // Every warp owns the 32 accumulator rows of its TMEM lane quadrant as an independent slab:
+    // its own staging buffers, its own TMA stores / residual loads (issued by an elected lane) and
+    // its own mbarriers. There is no CTA-wide barrier on this path, so one warp waiting on a TMA
+    // store or a residual tile never stalls the other three.
     constexpr int CH = kOutF32 ? 32 : 64;  // columns per staged chunk (128 B per row)
-    const int e = threadIdx.x - 64;
-    const bool leader = (e == 0);
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
-    const uint32_t row = quad * 32 + lane;
     const int cpt = (p.block_n + CH - 1) / CH;
-    float* s_bias = reinterpret_cast<float*>(gbase + p.off_bias);
+    const float* s_bias = reinterpret_cast<const float*>(gbase + p.off_bias);
     const bool has_res = p.has_res != 0;
     const bool res_after_act = p.res_after_act != 0;
+    // slab origin inside the (tn, th, tw) tile: rows are ordered n, h, w (w fastest)
+    const int so = quad * 32;
+    const int w_off = so % p.tw, h_off = (so / p.tw) % p.th, n_off = so / (p.tw * p.th);
+    constexpr uint32_t kSlab = 32 * 128;  // 4 KiB per warp per buffer
+    const uint32_t out_u32 = base + p.off_out + quad * kSlab;   // + buf * kStageBuf
+    const uint32_t res_u32 = base + p.off_res + quad * kSlab;
+    uint8_t* out_g = gbase + p.off_out + quad * kSlab;
+    const uint8_t* res_g = gbase + p.off_res + quad * kSlab;
+    auto rbar = [&](uint32_t b) { return rfull_bar(quad * 2 + b); };
 
-    auto issue_res = [&](uint32_t gg) {
+    auto issue_res = [&](uint32_t gg) {  // called by ONE lane
       const int ti = gg / cpt, c = gg - ti * cpt;
       const long long tile = (long long)blockIdx.x + (long long)ti * gridDim.x;
       if (tile >= p.num_tiles) return;
       const TileCoord t = decode_tile(p, (int)tile);
       const uint32_t b = gg & 1u;
-      mbar_expect_tx(rfull_bar(b), kStageBuf);
-      tma_load_4d(base + p.off_res + b * kStageBuf, &p.tmR, rfull_bar(b), t.ncol0 + c * CH, t.w0,
-                  t.h0, t.n0);
+      mbar_expect_tx(rbar(b), kSlab);
+      tma_load_4d(res_u32 + b * kStageBuf, &p.tmR, rbar(b), t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
+                  t.n0 + n_off);
     };
 
     uint32_t g = 0;
-    if (has_res && leader) {
+    if (has_res && lane == 0) {
       issue_res(0);
       issue_res(1);
     }
+    __syncwarp();
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      for (int i = e; i < 256; i += 128) {
-        const int col = t.ncol0 + i;
-        s_bias[i] = (p.bias != nullptr && i < p.block_n && col < p.cout) ? __ldg(p.bias + col) : 0.f;
-      }
-      named_bar_sync(1, 128);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_stride);
@@ -281,16 +299,17 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
-        const float* bias_c = s_bias + c * CH;
+        const float* bias_c = s_bias + t.ncol0 + c * CH;
+        uint8_t* out_row = out_g + buf * kStageBuf;
         if constexpr (!kOutF32) {
           uint4 packed[8];
-          if (has_res) mbar_wait(rfull_bar(buf), rphase);
-          const uint8_t* res_row = gbase + p.off_res + buf * kStageBuf;
+          if (has_res) mbar_wait(rbar(buf), rphase);
+          const uint8_t* res_row = res_g + buf * kStageBuf;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float r8[8];
             if (has_res) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(res_row + sw128_off(row, j));
+              const uint4 rv = *reinterpret_cast<const uint4*>(res_row + sw128_off(lane, j));
               const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -302,10 +321,13 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 #pragma unroll
               for (int q = 0; q < 8; ++q) r8[q] = 0.f;
             }
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_c + j * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_c + j * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float o[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              float x = v[j * 8 + q] + bias_c[j * 8 + q];
+              float x = v[j * 8 + q] + bb[q];
               if (res_after_act) {
                 x = apply_act<kAct>(x) + r8[q];
               } else {
@@ -318,36 +340,36 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
             packed[j] = *reinterpret_cast<const uint4*>(ob);
           }
-          if (leader) tma_store_wait_read<1>();  // the store that last used out[buf] has read it
-          named_bar_sync(1, 128);
-          uint8_t* out_row = gbase + p.off_out + buf * kStageBuf;
+          if (lane == 0) tma_store_wait_read<1>();  // this warp's store that last used out[buf] is done
+          __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(out_row + sw128_off(row, j)) = packed[j];
+            *reinterpret_cast<uint4*>(out_row + sw128_off(lane, j)) = packed[j];
         } else {
 #pragma unroll
           for (int q = 0; q < CH; ++q) v[q] = apply_act<kAct>(v[q] + bias_c[q]);
-          if (leader) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-          uint8_t* out_row = gbase + p.off_out + buf * kStageBuf;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(out_row + sw128_off(row, j)) =
+            *reinterpret_cast<float4*>(out_row + sw128_off(lane, j)) =
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (leader) {
-          tma_store_4d(&p.tmC, base + p.off_out + buf * kStageBuf, t.ncol0 + c * CH, t.w0, t.h0,
-                       t.n0);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&p.tmC, out_u32 + buf * kStageBuf, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
+                       t.n0 + n_off);
           tma_store_commit();
           if (has_res) issue_res(g + 2);
         }
+        __syncwarp();
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (leader) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
   }
 
   // ---- teardown ----
@@ -463,7 +485,9 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
 
   // shared memory carve-up
   const int stage_bytes = kABytes + block_n * 128;
-  const int fixed = 2 * kStageBuf + (p.has_res ? 2 * kStageBuf : 0) + 1024 + 256;
+  const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
+  EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "igemm: cout %d too large for the bias staging area", q.cout);
+  const int fixed = 2 * kStageBuf + (p.has_res ? 2 * kStageBuf : 0) + bias_bytes + 256;
   int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
   stages = std::min(stages, 8);
   EQXV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for block_n=%d", block_n);
@@ -471,7 +495,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   p.off_out = stages * stage_bytes;
   p.off_res = p.off_out + 2 * kStageBuf;
   p.off_bias = p.off_res + (p.has_res ? 2 * kStageBuf : 0);
-  p.off_bars = p.off_bias + 1024;
+  p.off_bars = p.off_bias + bias_bytes;
   const int smem_bytes = p.off_bars + 256 + 1024;
 
   int rc = encode_tmap(&p.tmA, q.a);
@@ -499,8 +523,9 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
     c.strides_bytes[0] = (uint64_t)pitch * es;
     c.strides_bytes[1] = c.strides_bytes[0] * (uint64_t)q.out_w;
     c.strides_bytes[2] = c.strides_bytes[1] * (uint64_t)q.out_h;
-    c.box[0] = f32 ? 32 : 64, c.box[1] = (uint32_t)q.tw, c.box[2] = (uint32_t)q.th,
-    c.box[3] = (uint32_t)q.tn;
+    // one box = one epilogue warp's slab: 32 consecutive rows of the (tn, th, tw) tile
+    const int bw = std::min(q.tw, 32), bh = std::min(q.th, 32 / bw), bn = 32 / (bw * bh);
+    c.box[0] = f32 ? 32 : 64, c.box[1] = (uint32_t)bw, c.box[2] = (uint32_t)bh, c.box[3] = (uint32_t)bn;
     c.estride[0] = c.estride[1] = c.estride[2] = c.estride[3] = 1;
     c.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
     return encode_tmap(m, c);
