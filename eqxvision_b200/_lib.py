@@ -69,6 +69,7 @@ SIGNATURES = {
     "eqxv_event_destroy": [_vp],
     "eqxv_event_record": [_vp, _vp],
     "eqxv_event_sync": [_vp],
+    "eqxv_stream_wait_event": [_vp, _vp],
     "eqxv_event_elapsed_ms": [_vp, _vp, C.POINTER(_f32)],
     "eqxv_memcpy_h2d_async": [_vp, _vp, _i64, _vp],
     "eqxv_memcpy_d2h_async": [_vp, _vp, _i64, _vp],

@@ -166,6 +166,10 @@ extern "C" int eqxv_event_sync(void* ev) {
   EQXV_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
   return EQXV_OK;
 }
+extern "C" int eqxv_stream_wait_event(void* stream, void* ev) {
+  EQXV_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0));
+  return EQXV_OK;
+}
 extern "C" int eqxv_event_elapsed_ms(void* start, void* stop, float* ms) {
   EQXV_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
   return EQXV_OK;

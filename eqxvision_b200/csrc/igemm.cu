@@ -93,7 +93,81 @@ __device__ __forceinline__ float apply_act(float v) {
   }
 }
 
-template <bool kOutF32, int kAct>
+// ---- packed fp32x2 epilogue math (sm_100 add.f32x2) -------------------------------------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// bf16x2 (as u32) -> two fp32 (exact)
+__device__ __forceinline__ uint64_t bf2_to_f2(uint32_t v) {
+  return f2_pack(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(uint64_t v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+// 8 accumulator columns -> 8 bf16 outputs: + bias (+ residual) -> activation -> round. The common
+// "none"/"relu" epilogues run on packed pairs (add.f32x2, max.bf16x2: half the FP32 issue slots);
+// relu commutes with the bf16 rounding, so applying it after the conversion is exact.
+template <int kAct, int kRes>
+__device__ __forceinline__ uint4 epilogue8(const float* v, const float* bias_smem, const uint4 rv) {
+  const float4 b0 = *reinterpret_cast<const float4*>(bias_smem);
+  const float4 b1 = *reinterpret_cast<const float4*>(bias_smem + 4);
+  const uint32_t r[4] = {rv.x, rv.y, rv.z, rv.w};
+  uint32_t o[4];
+  if constexpr (kAct == EQXV_ACT_NONE || (kAct == EQXV_ACT_RELU && kRes != 2)) {
+    const uint64_t bb[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y), f2_pack(b1.z, b1.w)};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint64_t x = f2_add(f2_pack(v[2 * q], v[2 * q + 1]), bb[q]);
+      if constexpr (kRes != 0) x = f2_add(x, bf2_to_f2(r[q]));
+      uint32_t y = f2_to_bf2(x);
+      if constexpr (kAct == EQXV_ACT_RELU) {
+        const __nv_bfloat162 z = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&y),
+                                         __floats2bfloat162_rn(0.f, 0.f));
+        y = *reinterpret_cast<const uint32_t*>(&z);
+      }
+      o[q] = y;
+    }
+  } else {
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float x0 = v[2 * q] + bb[2 * q], x1 = v[2 * q + 1] + bb[2 * q + 1];
+      const float r0 = __uint_as_float(r[q] << 16), r1 = __uint_as_float(r[q] & 0xffff0000u);
+      if constexpr (kRes == 1) {
+        x0 += r0;
+        x1 += r1;
+      }
+      x0 = apply_act<kAct>(x0);
+      x1 = apply_act<kAct>(x1);
+      if constexpr (kRes == 2) {
+        x0 += r0;
+        x1 += r1;
+      }
+      const __nv_bfloat162 t = __floats2bfloat162_rn(x0, x1);
+      o[q] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// kRes: 0 = no residual, 1 = act(acc + bias + res), 2 = act(acc + bias) + res. Compile-time so that the
+// unrolled epilogue is straight-line code (a runtime flag doubled its instruction count and made the
+// epilogue warps issue-bound on the HBM-bound layers: profiles/r01_layers_v4).
+template <bool kOutF32, int kAct, int kRes>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -242,8 +316,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int cpt = (p.block_n + CH - 1) / CH;
     const float* s_bias = reinterpret_cast<const float*>(gbase + p.off_bias);
-    const bool has_res = p.has_res != 0;
-    const bool res_after_act = p.res_after_act != 0;
+    constexpr bool has_res = kRes != 0;
+    constexpr bool res_after_act = kRes == 2;
     // slab origin inside the (tn, th, tw) tile: rows are ordered n, h, w (w fastest)
     const int so = quad * 32;
     const int w_off = so % p.tw, h_off = (so / p.tw) % p.th, n_off = so / (p.tw * p.th);
@@ -307,38 +381,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           const uint8_t* res_row = res_g + buf * kStageBuf;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float r8[8];
-            if (has_res) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(res_row + sw128_off(lane, j));
-              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = __bfloat1622float2(rb[q]);
-                r8[2 * q] = f.x;
-                r8[2 * q + 1] = f.y;
-              }
-            } else {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) r8[q] = 0.f;
-            }
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_c + j * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_c + j * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float o[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float x = v[j * 8 + q] + bb[q];
-              if (res_after_act) {
-                x = apply_act<kAct>(x) + r8[q];
-              } else {
-                x = apply_act<kAct>(x + r8[q]);
-              }
-              o[q] = x;
-            }
-            __nv_bfloat162 ob[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ob[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
-            packed[j] = *reinterpret_cast<const uint4*>(ob);
+            uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (has_res) rv = *reinterpret_cast<const uint4*>(res_row + sw128_off(lane, j));
+            packed[j] = epilogue8<kAct, kRes>(&v[j * 8], bias_c + j * 8, rv);
           }
           if (lane == 0) tma_store_wait_read<1>();  // this warp's store that last used out[buf] is done
           __syncwarp();
@@ -387,15 +432,18 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 constexpr int kNumActs = 8;
 using KernelFn = void (*)(const IgemmParams);
 struct KernelTable {
-  KernelFn bf16[kNumActs];
+  KernelFn bf16[3][kNumActs];  // [residual mode][activation]
   KernelFn f32[kNumActs];
 };
+#define EQXV_ACT_ROW(F32, RES)                                                                        \
+  {                                                                                                   \
+    igemm_kernel<F32, 0, RES>, igemm_kernel<F32, 1, RES>, igemm_kernel<F32, 2, RES>,                  \
+        igemm_kernel<F32, 3, RES>, igemm_kernel<F32, 4, RES>, igemm_kernel<F32, 5, RES>,              \
+        igemm_kernel<F32, 6, RES>, igemm_kernel<F32, 7, RES>                                          \
+  }
 static const KernelTable& kernel_table() {
-  static const KernelTable t = {
-      {igemm_kernel<false, 0>, igemm_kernel<false, 1>, igemm_kernel<false, 2>, igemm_kernel<false, 3>,
-       igemm_kernel<false, 4>, igemm_kernel<false, 5>, igemm_kernel<false, 6>, igemm_kernel<false, 7>},
-      {igemm_kernel<true, 0>, igemm_kernel<true, 1>, igemm_kernel<true, 2>, igemm_kernel<true, 3>,
-       igemm_kernel<true, 4>, igemm_kernel<true, 5>, igemm_kernel<true, 6>, igemm_kernel<true, 7>}};
+  static const KernelTable t = {{EQXV_ACT_ROW(false, 0), EQXV_ACT_ROW(false, 1), EQXV_ACT_ROW(false, 2)},
+                                EQXV_ACT_ROW(true, 0)};
   return t;
 }
 
@@ -539,7 +587,8 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
 
   const int grid = std::min(p.num_tiles, device_sm_count());
   EQXV_CHECK_ARG(q.act >= 0 && q.act < kNumActs, "igemm: unknown activation %d", q.act);
-  const KernelFn fn = out_f32 ? kernel_table().f32[q.act] : kernel_table().bf16[q.act];
+  const int res_mode = q.res ? (p.res_after_act ? 2 : 1) : 0;
+  const KernelFn fn = out_f32 ? kernel_table().f32[q.act] : kernel_table().bf16[res_mode][q.act];
   fn<<<grid, kThreads, smem_bytes, stream>>>(p);
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
@@ -547,8 +596,9 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
 
 int igemm_init() {
   for (int a = 0; a < kNumActs; ++a) {
-    EQXV_CUDA(cudaFuncSetAttribute(kernel_table().bf16[a], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kMaxSmem));
+    for (int r = 0; r < 3; ++r)
+      EQXV_CUDA(cudaFuncSetAttribute(kernel_table().bf16[r][a], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kMaxSmem));
     EQXV_CUDA(cudaFuncSetAttribute(kernel_table().f32[a], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kMaxSmem));
   }

@@ -11,7 +11,7 @@ constexpr int kPwThreads = 256;
 
 static inline int grid_for(long long work, int threads = kPwThreads) {
   long long b = (work + threads - 1) / threads;
-  const long long cap = (long long)device_sm_count() * 16;
+  const long long cap = (long long)device_sm_count() * 32;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -144,6 +144,58 @@ __global__ void pool2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
     if (!kMax) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] *= inv;
+    }
+    *reinterpret_cast<bf16x8*>(y + (((long long)img * ho + oh) * wo + ow) * yp + g * 8) = pack8(acc);
+  }
+}
+
+// Compile-time window/stride variant: all K*K 16-byte loads of a thread are issued before any is
+// consumed (memory-level parallelism), out-of-range taps are predicated instead of branched.
+template <bool kMax, int K, int S>
+__global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                    int n, int h, int w, int c, int pad, int ho, int wo, int xp, int yp) {
+  const int groups = c / 8;
+  const long long total = (long long)n * ho * wo * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long t = i / groups;
+    const int ow = (int)(t % wo);
+    t /= wo;
+    const int oh = (int)(t % ho);
+    const int img = (int)(t / ho);
+    uint4 raw[K * K];
+    bool ok[K * K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+#pragma unroll
+      for (int q = 0; q < K; ++q) {
+        const int ih = oh * S - pad + r, iw = ow * S - pad + q;
+        ok[r * K + q] = ih >= 0 && ih < h && iw >= 0 && iw < w;
+        const int ihc = min(max(ih, 0), h - 1), iwc = min(max(iw, 0), w - 1);
+        raw[r * K + q] = __ldg(reinterpret_cast<const uint4*>(
+            x + (((long long)img * h + ihc) * w + iwc) * xp + g * 8));
+      }
+    }
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = kMax ? -INFINITY : 0.f;
+#pragma unroll
+    for (int k = 0; k < K * K; ++k) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(&raw[k]), f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (kMax) {
+          acc[q] = ok[k] ? fmaxf(acc[q], f[q]) : acc[q];
+        } else {
+          acc[q] += ok[k] ? f[q] : 0.f;
+        }
+      }
+    }
+    if (!kMax) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] *= 1.f / (float)(K * K);
     }
     *reinterpret_cast<bf16x8*>(y + (((long long)img * ho + oh) * wo + ow) * yp + g * 8) = pack8(acc);
   }
@@ -326,6 +378,26 @@ static int pool_common(bool is_max, const void* x, void* y, int n, int h, int w,
                  "pool: channels and pitches must be multiples of 8");
   EQXV_CHECK_ARG(ho > 0 && wo > 0, "pool: empty output");
   const long long total = (long long)n * ho * wo * (c / 8);
+  if (kh == kw && sh == sw && kh == 3 && sh == 2) {
+    if (is_max)
+      pool2d_fixed_kernel<true, 3, 2><<<grid_for(total), kPwThreads, 0, stream>>>(
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp);
+    else
+      pool2d_fixed_kernel<false, 3, 2><<<grid_for(total), kPwThreads, 0, stream>>>(
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp);
+    EQXV_LAUNCH_CHECK();
+    return EQXV_OK;
+  }
+  if (kh == kw && sh == sw && kh == 2 && sh == 2) {
+    if (is_max)
+      pool2d_fixed_kernel<true, 2, 2><<<grid_for(total), kPwThreads, 0, stream>>>(
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp);
+    else
+      pool2d_fixed_kernel<false, 2, 2><<<grid_for(total), kPwThreads, 0, stream>>>(
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp);
+    EQXV_LAUNCH_CHECK();
+    return EQXV_OK;
+  }
   if (is_max) {
     pool2d_kernel<true><<<grid_for(total), kPwThreads, 0, stream>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, kh, kw, sh, sw, pad, ho, wo, xp, yp);

@@ -56,9 +56,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin on a phase parity. A watchdog turns a protocol deadlock into a trap (the launch then
-// fails with an error instead of hanging the device): ~4 s at 2 GHz.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// fails with an error instead of hanging the device): ~4 s at 2 GHz. The slow path is kept out of
+// line so that the many wait sites do not bloat the instruction stream.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -68,6 +68,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // ----------------------------------------------------------------------------------------------

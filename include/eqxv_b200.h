@@ -160,6 +160,7 @@ int eqxv_event_create(void** ev);
 int eqxv_event_destroy(void* ev);
 int eqxv_event_record(void* ev, void* stream);
 int eqxv_event_sync(void* ev);
+int eqxv_stream_wait_event(void* stream, void* ev);
 int eqxv_event_elapsed_ms(void* start, void* stop, float* ms);
 int eqxv_memcpy_h2d_async(void* dst, const void* src, int64_t bytes, void* stream);
 int eqxv_memcpy_d2h_async(void* dst, const void* src, int64_t bytes, void* stream);
