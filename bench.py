@@ -200,7 +200,7 @@ def measure(name, model, batch, steps, warmup, dist, rank):
     del plan2
 
     # (3) per-launch device time of the igemm (conv / linear) launches, eager replay with events
-    igemm_fns = (ops.conv2d, ops.gemm, ops.conv_stem7x7)
+    igemm_fns = (ops.conv2d, ops.gemm, ops.conv_stem, ops.conv_stem7x7)
     plan.run_steps(st)
     _lib.call("eqxv_stream_sync", st)
     evs = []

@@ -68,7 +68,8 @@ class Plan:
         self.keep: List[Any] = []             # keeps traced exprs alive (ids are memo keys)
         self.x_in = torch.empty((batch,) + self.in_shape, dtype=torch.float32, device=device)
         self._input_nhwc: Dict[int, Buf] = {}
-        self._input_stem: Optional[torch.Tensor] = None
+        self._input_stem: Dict[int, torch.Tensor] = {}
+        self._concat_groups: Dict[int, dict] = {}
         self.outputs: List[Tuple[torch.Tensor, Tuple[int, ...]]] = []
         self.out_struct = None
         self.graph = None
@@ -90,16 +91,33 @@ class Plan:
         self.steps.append((fn, kw))
 
     # -------------------------------------------------------------- emission
-    def emit(self, sym: T.Sym, out_f32: bool = False) -> Buf:
+    _DIRECT_DST = (T.Conv, T.Pool, T.Resize)  # nodes that can write straight into a caller-provided slice
+
+    def emit(self, sym: T.Sym, out_f32: bool = False, dst: Optional[Buf] = None) -> Buf:
+        """Lower `sym` (memoised). With `dst` the result must end up in that buffer slice: producers
+        that support it store there directly, anything else is computed and copied."""
         key = id(sym.expr)
         if key in self.memo and not out_f32:
-            return self.memo[key]
+            buf = self.memo[key]
+            if dst is not None and buf.t.data_ptr() != dst.t.data_ptr():
+                self.step(ops.copy2d, dst=dst.rows(), src=buf.rows(dst.cpad))
+            return buf
         e = sym.expr
         fn = getattr(self, "_emit_" + type(e).__name__, None)
         if fn is None:
             raise NotImplementedError(f"no lowering for {type(e).__name__}")
         self.keep.append(e)
-        buf = fn(sym, e, out_f32) if isinstance(e, (T.Conv, T.Linear)) else fn(sym, e)
+        if isinstance(e, T.Conv):
+            buf = fn(sym, e, out_f32, dst)
+        elif isinstance(e, T.Linear):
+            buf = fn(sym, e, out_f32)
+        elif dst is not None and isinstance(e, self._DIRECT_DST):
+            buf = fn(sym, e, dst)
+        else:
+            buf = fn(sym, e)
+            if dst is not None:
+                self.step(ops.copy2d, dst=dst.rows(), src=buf.rows(dst.cpad))
+                buf = dst
         if not out_f32:
             self.memo[key] = buf
         return buf
@@ -126,7 +144,7 @@ class Plan:
             return ACT_BY_NAME[e.act1], True
         return ACT_BY_NAME[e.act2 if e.res is not None else e.act1], False
 
-    def _emit_Conv(self, sym, e: T.Conv, out_f32=False):
+    def _emit_Conv(self, sym, e: T.Conv, out_f32=False, dst: Optional[Buf] = None):
         cout, cin_g, kh, kw = e.weight.shape
         (sh, sw), (ph, pw), (dh, dw) = e.stride, e.padding, e.dilation
         ho, wo = sym.shape[1:]
@@ -138,24 +156,31 @@ class Plan:
 
         if e.groups != 1:
             if e.groups == c_in and cin_g == 1 and cout == c_in:
-                return self._emit_depthwise(sym, e, w, b, act, res, res_after)
+                return self._emit_depthwise(sym, e, w, b, act, res, dst)
             raise NotImplementedError("grouped convolution (ResNeXt/RegNet) is not on the hot path yet")
         if sh != sw or ph != pw or dh != dw:
             raise NotImplementedError("anisotropic stride/padding/dilation is not supported")
 
         bias_d = self.const(b) if b is not None else None
-        out = self.alloc(self.n * ho * wo, cout, (ho, wo), dtype=torch.float32 if out_f32 else BF16)
+        if dst is not None:
+            if dst.c != cout or out_f32:
+                raise EqxvError("internal: destination slice does not match the convolution output")
+            out = dst
+        else:
+            out = self.alloc(self.n * ho * wo, cout, (ho, wo), dtype=torch.float32 if out_f32 else BF16)
 
         if isinstance(xin.expr, T.Input):
-            if (kh, kw, sh, ph, dh, c_in) == (7, 7, 2, 3, 1, 3) and h % 2 == 0 and wd % 2 == 0 \
-                    and res is None and not out_f32:
-                # ResNet stem (resnet.py:243-251): padded NHWC8 image + 7-tap window GEMM
-                if self._input_stem is None:
-                    self._input_stem = torch.zeros((self.n, h + 6, wd + 8, 8), dtype=BF16, device=self.device)
-                    self.step(ops.pack_stem_input, x_nchw=self.x_in, out=self._input_stem)
+            if c_in <= 8 and kh <= 8 and kw <= 8 and sh in (1, 2) and dh == 1 and 2 * ph <= kw \
+                    and res is None and not out_f32 and dst is None:
+                # first-layer conv on the raw image (resnet.py:243-251, vgg.py:137, efficientnet.py:327):
+                # padded NHWC8 image + one GEMM K-block per filter row (eqxv_conv_stem_bf16)
+                if ph not in self._input_stem:
+                    xp = torch.zeros((self.n, h + 2 * ph, wd + 8, 8), dtype=BF16, device=self.device)
+                    self.step(ops.pack_stem_input, x_nchw=self.x_in, pad=ph, out=xp)
+                    self._input_stem[ph] = xp
                 wp = self.const(_pack.pack_stem_weight(w))
-                self.step(ops.conv_stem7x7, xpad=self._input_stem, wgt=wp, bias=bias_d, n=self.n, h=h, w=wd,
-                          cout=cout, act=act, out=out.map(ho, wo))
+                self.step(ops.conv_stem, xpad=self._input_stem[ph], wgt=wp, bias=bias_d, n=self.n, h=h, w=wd,
+                          cout=cout, kh=kh, kw=kw, stride=sh, pad=ph, act=act, out=out.map(ho, wo))
                 return out
             xb = self.input_nhwc(_round8(c_in))
         else:
@@ -168,8 +193,27 @@ class Plan:
                   out=out.map(ho, wo, cout if out_f32 else None), out_f32=out_f32)
         return out
 
-    def _emit_depthwise(self, sym, e, w, b, act, res, res_after):
-        raise NotImplementedError("depthwise convolution kernel is not built yet")
+    def _emit_depthwise(self, sym, e, w, b, act, res, dst):
+        """groups == channels: shared-memory-free channels-last stencil (csrc/depthwise.cu)"""
+        if res is not None:
+            raise NotImplementedError("residual on a depthwise convolution")
+        c, h, wd = e.x.shape
+        k = e.weight.shape[2]
+        (sh, sw), (ph, pw), (dh, dw) = e.stride, e.padding, e.dilation
+        if e.weight.shape[2] != e.weight.shape[3] or sh != sw or ph != pw or dh != dw:
+            raise NotImplementedError("anisotropic depthwise convolution")
+        xb = self.emit(e.x)
+        cp = xb.cpad
+        wp = self.const(_pack.pack_depthwise_weight(w, cp))
+        bias = torch.zeros(cp)
+        if b is not None:
+            bias[:c] = b
+        bias_d = self.const(bias)
+        ho, wo = sym.shape[1:]
+        out = dst if dst is not None else self.alloc(self.n * ho * wo, c, (ho, wo))
+        self.step(ops.dwconv, x=xb.map(h, wd, cp), wgt=wp, bias=bias_d, k=k, stride=sh, pad=ph, dil=dh, act=act,
+                  out=out.map(ho, wo, cp))
+        return out
 
     # ---- linear ------------------------------------------------------------------------------
     def _emit_Linear(self, sym, e: T.Linear, out_f32=False):
@@ -244,11 +288,11 @@ class Plan:
         return Buf(src.t, src.c, self.n, (e.h, e.w))
 
     # ---- pooling -----------------------------------------------------------------------------
-    def _emit_Pool(self, sym, e: T.Pool):
+    def _emit_Pool(self, sym, e: T.Pool, dst: Optional[Buf] = None):
         xb = self.emit(e.x)
         c, h, w = e.x.shape
         ho, wo = sym.shape[1:]
-        out = self.alloc(self.n * ho * wo, c, (ho, wo))
+        out = dst if dst is not None else self.alloc(self.n * ho * wo, c, (ho, wo))
         if e.mode == "max":
             self.step(ops.maxpool2d, x=xb.map(h, w), k=e.k, stride=e.stride, pad=e.pad, out=out.map(ho, wo))
         else:
@@ -306,23 +350,79 @@ class Plan:
         return out
 
     # ---- elementwise nodes that could not be folded into a GEMM epilogue ----------------------
-    def _emit_BNAct(self, sym, e):
-        raise NotImplementedError("standalone BatchNorm kernel is not built yet")
+    def _padded(self, v: torch.Tensor, n: int) -> torch.Tensor:
+        out = torch.zeros(n, dtype=torch.float32)
+        out[: v.numel()] = v.detach().float().reshape(-1)
+        return self.const(out)
 
-    def _emit_Act(self, sym, e):
-        raise NotImplementedError("standalone activation kernel is not built yet")
+    def _like(self, src: Buf, sym) -> Buf:
+        return self.alloc(src.t.shape[0], sym.shape[0] if sym.kind == "chw" else sym.shape[-1], src.geom)
 
-    def _emit_Add(self, sym, e):
-        raise NotImplementedError("standalone add kernel is not built yet")
+    def _emit_BNAct(self, sym, e: T.BNAct):
+        """standalone inference BatchNorm (+activation), densenet.py:64-65,118,211"""
+        xb = self.emit(e.x)
+        scale, shift = e.bn.folded()
+        out = self._like(xb, sym)
+        self.step(ops.eltwise, x=xb.rows(), scale=self._padded(scale, xb.cpad), shift=self._padded(shift, xb.cpad),
+                  act=ACT_BY_NAME[e.act], out=out.rows())
+        return out
 
-    def _emit_ChannelScale(self, sym, e):
-        raise NotImplementedError("channel-scale kernel is not built yet")
+    def _emit_Act(self, sym, e: T.Act):
+        xb = self.emit(e.x)
+        out = self._like(xb, sym)
+        self.step(ops.eltwise, x=xb.rows(), act=ACT_BY_NAME[e.act], out=out.rows())
+        return out
 
-    def _emit_Concat(self, sym, e):
-        raise NotImplementedError("channel concat is not built yet")
+    def _emit_Add(self, sym, e: T.Add):
+        a, b = self.emit(e.a), self.emit(e.b)
+        out = self._like(a, sym)
+        self.step(ops.eltwise, x=a.rows(), other=b.rows(), act=ACT_BY_NAME[e.act], out=out.rows())
+        return out
 
-    def _emit_Resize(self, sym, e):
-        raise NotImplementedError("bilinear resize kernel is not built yet")
+    def _emit_ChannelScale(self, sym, e: T.ChannelScale):
+        """x * s with one gate per (image, channel): the SqueezeExcitation output (squeeze.py:61)"""
+        xb, sb = self.emit(e.x), self.emit(e.s)
+        c, h, w = e.x.shape
+        out = self._like(xb, sym)
+        self.step(ops.eltwise, x=xb.rows(), gate=sb.rows(xb.cpad), rows_per_image=h * w, out=out.rows())
+        return out
+
+    def _emit_Concat(self, sym, e: T.Concat):
+        """Channel concatenation without a concat pass: producers store into channel slices of one
+        buffer. Concats that extend an earlier concat (DenseNet: [x0,f1] -> [x0,f1,f2] -> ...) keep
+        growing inside the same buffer, sized by the `capacity` hint of the model code."""
+        c_tot, h, w = sym.shape
+        rows = self.n * h * w
+        gkey = id(e.xs[0].expr)
+        grp = self._concat_groups.get(gkey)
+        ids = [id(x.expr) for x in e.xs]
+        if grp is None or grp["cap"] < c_tot or grp["ids"] != ids[: len(grp["ids"])]:
+            cap = max(c_tot, e.capacity or 0)
+            base = torch.zeros((rows, _round8(cap)), dtype=BF16, device=self.device)
+            self.act_bytes += base.numel() * 2
+            grp = {"base": base, "cap": cap, "ids": [], "width": 0}
+            self._concat_groups[gkey] = grp
+        base = grp["base"]
+        for x in e.xs[len(grp["ids"]):]:
+            cx = x.shape[0]
+            off = grp["width"]
+            if off % 8 != 0:
+                raise NotImplementedError("concat slices must start at a multiple of 8 channels")
+            sl = Buf(torch.as_strided(base, (rows, cx), (base.stride(0), 1), base.storage_offset() + off), cx,
+                     self.n, (h, w))
+            self.emit(x, dst=sl)
+            grp["ids"].append(id(x.expr))
+            grp["width"] = off + cx
+        view = torch.as_strided(base, (rows, c_tot), (base.stride(0), 1), base.storage_offset())
+        return Buf(view, c_tot, self.n, (h, w))
+
+    def _emit_Resize(self, sym, e: T.Resize, dst: Optional[Buf] = None):
+        """bilinear upsample kept in NHWC bf16 (ASPP pooling branch broadcast, deeplabv3.py:74)"""
+        xb = self.emit(e.x)
+        c, h, w = e.x.shape
+        out = dst if dst is not None else self.alloc(self.n * e.h * e.w, c, (e.h, e.w))
+        self.step(ops.resize_bilinear, x=xb.map(h, w), oh=e.h, ow=e.w, out=out.map(e.h, e.w, xb.cpad))
+        return out
 
     # -------------------------------------------------------------- outputs
     def add_output(self, sym: T.Sym):
@@ -331,6 +431,14 @@ class Plan:
         if sym.kind == "vec" and isinstance(sym.expr, T.Linear) and id(sym.expr) not in self.memo:
             buf = self.emit(sym, out_f32=True)
             self.outputs.append((buf.rows(sym.shape[0]), (n,) + sym.shape))
+            return
+        if sym.kind == "chw" and isinstance(sym.expr, T.Resize) and id(sym.expr) not in self.memo:
+            # segmentation output (_utils.py:52,57): upsample straight into the fp32 NCHW result
+            src = self.emit(sym.expr.x)
+            c, hs, ws = sym.expr.x.shape
+            out = torch.empty((n, c, sym.expr.h, sym.expr.w), dtype=torch.float32, device=self.device)
+            self.step(ops.resize_bilinear_to_nchw, x=src.map(hs, ws), c=c, oh=sym.expr.h, ow=sym.expr.w, out=out)
+            self.outputs.append((out, (n,) + sym.shape))
             return
         buf = self.emit(sym)
         if sym.kind == "chw":

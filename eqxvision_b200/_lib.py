@@ -46,8 +46,8 @@ SIGNATURES = {
     "eqxv_init": [C.c_int],
     "eqxv_conv2d_igemm_bf16": [C.POINTER(ConvDesc), _vp],
     "eqxv_gemm_bias_act_res_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
-    "eqxv_conv_stem7x7_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
-    "eqxv_pack_stem_input": [_vp, _vp, _i32, _i32, _i32, _vp],
+    "eqxv_conv_stem_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_pack_stem_input": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_maxpool2d_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -58,6 +58,11 @@ SIGNATURES = {
     "eqxv_patchify_nchw_f32_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_vit_assemble_tokens_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "eqxv_gather_rows_bf16": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_dwconv_bn_act_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_eltwise_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_resize_bilinear_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_copy2d_async": [_vp, _i64, _vp, _i64, _i64, _i64, _vp],
     "eqxv_stream_create": [C.POINTER(_vp)],
     "eqxv_stream_destroy": [_vp],
     "eqxv_stream_sync": [_vp],
@@ -83,11 +88,12 @@ _initialised_device = None
 launch_count = 0  # number of kernel-launching C-ABI calls made by this process (bench bookkeeping)
 
 _LAUNCHING = {
-    "eqxv_conv2d_igemm_bf16", "eqxv_gemm_bias_act_res_bf16", "eqxv_conv_stem7x7_bf16",
+    "eqxv_conv2d_igemm_bf16", "eqxv_gemm_bias_act_res_bf16", "eqxv_conv_stem_bf16",
     "eqxv_pack_stem_input", "eqxv_nchw_f32_to_nhwc_bf16", "eqxv_nhwc_bf16_to_nchw_f32",
     "eqxv_maxpool2d_nhwc_bf16", "eqxv_avgpool2d_nhwc_bf16", "eqxv_adaptive_avgpool_nhwc_bf16",
     "eqxv_layernorm_bf16", "eqxv_attention_fwd_bf16", "eqxv_patchify_nchw_f32_bf16",
-    "eqxv_vit_assemble_tokens_bf16", "eqxv_gather_rows_bf16",
+    "eqxv_vit_assemble_tokens_bf16", "eqxv_gather_rows_bf16", "eqxv_dwconv_bn_act_bf16", "eqxv_eltwise_bf16",
+    "eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32", "eqxv_resize_bilinear_nhwc_bf16", "eqxv_copy2d_async",
 }
 
 

@@ -43,12 +43,13 @@ def pack_conv_weight(w_oihw: torch.Tensor, cin_pad: int) -> torch.Tensor:
 
 
 def pack_stem_weight(w_oihw: torch.Tensor) -> torch.Tensor:
-    """[O,3,7,7] -> [O, 7(r), 8(s), 8(c)] bf16 with zero taps/channels (see eqxv_conv_stem7x7_bf16)"""
+    """[O, I<=8, kh<=8, kw<=8] -> [O, kh(r), 8(s), 8(c)] bf16 with zero taps/channels
+    (see eqxv_conv_stem_bf16)"""
     o, i, kh, kw = w_oihw.shape
-    assert (i, kh, kw) == (3, 7, 7)
-    wp = torch.zeros(o, 7, 8, 8, dtype=torch.float32)
-    wp[:, :, :7, :3] = w_oihw.permute(0, 2, 3, 1)
-    return wp.reshape(o, 448).to(torch.bfloat16).contiguous()
+    assert i <= 8 and kh <= 8 and kw <= 8
+    wp = torch.zeros(o, kh, 8, 8, dtype=torch.float32)
+    wp[:, :, :kw, :i] = w_oihw.permute(0, 2, 3, 1)
+    return wp.reshape(o, kh * 64).to(torch.bfloat16).contiguous()
 
 
 def pack_linear_weight(w: torch.Tensor, in_pad: int) -> torch.Tensor:

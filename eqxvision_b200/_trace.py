@@ -161,10 +161,11 @@ class SelectRow(Expr):
 
 
 class Concat(Expr):  # channel concatenation, densenet.py:63, deeplabv3.py:134
-    __slots__ = ("xs",)
+    __slots__ = ("xs", "capacity")
 
-    def __init__(self, xs):
+    def __init__(self, xs, capacity=None):
         self.xs = tuple(xs)
+        self.capacity = capacity  # hint: final width of the buffer this concat will grow into
 
 
 class Resize(Expr):  # jax.image.resize(method="bilinear"), _utils.py:52
@@ -376,15 +377,15 @@ def select_row(x: Sym, row: int) -> Sym:
     return Sym("vec", (d,), SelectRow(x, row))
 
 
-def concat_channels(xs: Sequence[Sym]) -> Sym:
+def concat_channels(xs: Sequence[Sym], capacity: Optional[int] = None) -> Sym:
     xs = list(xs)
-    if len(xs) == 1:
+    if len(xs) == 1 and capacity is None:
         return xs[0]
     h, w = xs[0].shape[1:]
     for x in xs:
         if x.kind != "chw" or x.shape[1:] != (h, w):
             raise ValueError("concat_channels: spatial shape mismatch")
-    return Sym("chw", (sum(x.shape[0] for x in xs), h, w), Concat(xs))
+    return Sym("chw", (sum(x.shape[0] for x in xs), h, w), Concat(xs, capacity))
 
 
 def resize_bilinear(x: Sym, h: int, w: int) -> Sym:

@@ -701,18 +701,21 @@ extern "C" int eqxv_gemm_bias_act_res_bf16(const void* a, int64_t lda, const voi
   return eqxv_conv2d_igemm_bf16(&d, stream);
 }
 
-extern "C" int eqxv_conv_stem7x7_bf16(const void* xpad, const void* wgt, const float* bias, void* y,
-                                      int32_t n, int32_t h, int32_t w, int32_t cout, int32_t y_pitch,
-                                      int32_t act, void* stream) {
+extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n,
+                                   int32_t h, int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride,
+                                   int32_t pad, int32_t y_pitch, int32_t act, void* stream) {
   EQXV_CHECK_ARG(xpad && wgt && y, "stem: null pointer");
   EQXV_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0, "stem: bad shape");
-  EQXV_CHECK_ARG(h % 2 == 0 && w % 2 == 0, "stem: h and w must be even");
+  EQXV_CHECK_ARG(kh >= 1 && kh <= 8 && kw >= 1 && kw <= 8 && stride >= 1 && stride <= 2 && pad >= 0 &&
+                     2 * pad <= kw,
+                 "stem: unsupported geometry k=%dx%d stride %d pad %d", kh, kw, stride, pad);
   EQXV_CHECK_ARG(y_pitch % 8 == 0 && y_pitch >= cout, "stem: bad y_pitch");
-  const int ho = h / 2, wo = w / 2;
-  const int hp = h + 6, wp = w + 8;  // layout written by eqxv_pack_stem_input
+  const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
+  EQXV_CHECK_ARG(ho > 0 && wo > 0, "stem: empty output");
+  const int hp = h + 2 * pad, wp = w + 8;  // layout written by eqxv_pack_stem_input
   IgemmProblem q{};
   q.wgt = wgt;
-  q.ktot = 7 * 64;
+  q.ktot = kh * 64;
   q.bias = bias;
   q.y = y;
   q.res = nullptr;
@@ -724,22 +727,23 @@ extern "C" int eqxv_conv_stem7x7_bf16(const void* xpad, const void* wgt, const f
   q.cin_pack = 64;
   q.out_w = wo, q.out_h = ho, q.out_n = n;
   choose_tile(n, ho, wo, q.tw, q.th, q.tn);
-  EQXV_CHECK_ARG(q.th * 2 <= 256, "stem: tile too tall");
-  // 7 taps = the 7 filter rows; one "channel block" = an 8-pixel x 8-channel window (64 elements,
-  // 128 B) starting at padded column 2*wo. Window starts overlap (stride 2 pixels = 32 B), so the
-  // "w" dimension of the map is the OUTPUT column; rows are traversed with stride 2.
-  q.kh = 7, q.kw = 1, q.dil_h = q.dil_w = 1, q.pad_h = q.pad_w = 0, q.mul_h = 2, q.mul_w = 1;
+  EQXV_CHECK_ARG(q.th * stride <= 256, "stem: tile too tall");
+  // kh taps = the filter rows; one "channel block" = an 8-pixel x 8-channel window (64 elements,
+  // 128 B) starting at padded column stride*wo. Windows of neighbouring outputs overlap, so the "w"
+  // dimension of the map is the OUTPUT column (stride = `stride` pixels); rows are traversed with
+  // element stride `stride`. Filter columns >= kw and channels >= cin carry zero weights.
+  q.kh = kh, q.kw = 1, q.dil_h = q.dil_w = 1, q.pad_h = q.pad_w = 0, q.mul_h = stride, q.mul_w = 1;
   q.in_h = hp, q.in_w = wo;
   q.a.base = const_cast<void*>(xpad);
   q.a.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   q.a.rank = 4;
   q.a.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
   q.a.dims[0] = 64, q.a.dims[1] = (uint64_t)wo, q.a.dims[2] = (uint64_t)hp, q.a.dims[3] = (uint64_t)n;
-  q.a.strides_bytes[0] = 32;                                   // 2 pixels x 8 ch x 2 B
+  q.a.strides_bytes[0] = (uint64_t)stride * 16;                // `stride` pixels x 8 ch x 2 B
   q.a.strides_bytes[1] = (uint64_t)wp * 16;                    // one padded row
   q.a.strides_bytes[2] = (uint64_t)wp * 16 * (uint64_t)hp;     // one padded image
-  q.a.box[0] = 64, q.a.box[1] = (uint32_t)q.tw, q.a.box[2] = (uint32_t)(q.th * 2),
+  q.a.box[0] = 64, q.a.box[1] = (uint32_t)q.tw, q.a.box[2] = (uint32_t)(q.th * stride),
   q.a.box[3] = (uint32_t)q.tn;
-  q.a.estride[0] = 1, q.a.estride[1] = 1, q.a.estride[2] = 2, q.a.estride[3] = 1;
+  q.a.estride[0] = 1, q.a.estride[1] = 1, q.a.estride[2] = (uint32_t)stride, q.a.estride[3] = 1;
   return launch_igemm(q, (cudaStream_t)stream);
 }

@@ -37,11 +37,11 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// stem input: fp32 NCHW [n,3,h,w] -> bf16 [n, h+6, w+8, 8], image at (3,3), zeros elsewhere
+// stem input: fp32 NCHW [n,c<=8,h,w] -> bf16 [n, h+2*pad, w+8, 8], image at (pad,pad), zeros elsewhere
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict__ y, int n, int h,
-                                 int w) {
-  const int hp = h + 6, wp = w + 8;
+__global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict__ y, int n, int c, int h,
+                                 int w, int pad) {
+  const int hp = h + 2 * pad, wp = w + 8;
   const long long total = (long long)n * hp * wp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -49,13 +49,13 @@ __global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict
     const int ph = (int)((i / wp) % hp);
     const int img = (int)(i / ((long long)wp * hp));
     float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int sh = ph - 3, sw = pw - 3;
+    const int sh = ph - pad, sw = pw - pad;
     if (sh >= 0 && sh < h && sw >= 0 && sw < w) {
       const long long plane = (long long)h * w;
-      const float* src = x + (long long)img * 3 * plane + (long long)sh * w + sw;
-      f[0] = __ldg(src);
-      f[1] = __ldg(src + plane);
-      f[2] = __ldg(src + 2 * plane);
+      const float* src = x + (long long)img * c * plane + (long long)sh * w + sw;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < c) f[q] = __ldg(src + q * plane);
     }
     y[i] = pack8(f);
   }
@@ -201,6 +201,46 @@ __global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
   }
 }
 
+// Global average pool (adaptive pool to 1x1: the SE squeeze, the classifier pool, the ASPP pooling
+// branch). One block per (image, group of <= 8 channel vectors): the 256 threads are laid out as
+// (pixel lane, channel vector) so that each pixel contributes one contiguous <=128-byte read, every
+// thread strides over the pixels, and the lanes are combined through shared memory.
+__global__ void __launch_bounds__(256) global_avgpool_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             __nv_bfloat16* __restrict__ y, int hw, int c,
+                                                             int xp, int yp) {
+  __shared__ float red[256][9];
+  const int groups = c / 8;
+  const int g0 = blockIdx.x * 8;
+  const int gc = min(8, groups - g0);          // channel vectors handled by this block
+  const int lanes = 256 / gc;                  // pixel lanes
+  const int img = blockIdx.y;
+  const int gi = threadIdx.x % gc, lane = threadIdx.x / gc;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (lane < lanes) {
+    const __nv_bfloat16* base = x + (long long)img * hw * xp + (g0 + gi) * 8;
+    for (int p = lane; p < hw; p += lanes) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)p * xp), f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += f[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) red[threadIdx.x][q] = acc[q];
+  __syncthreads();
+  if (threadIdx.x < gc) {
+    float tot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < lanes; ++l) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot[q] += red[l * gc + threadIdx.x][q];
+    }
+    const float inv = 1.f / (float)hw;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tot[q] *= inv;
+    *reinterpret_cast<bf16x8*>(y + (long long)img * yp + (g0 + threadIdx.x) * 8) = pack8(tot);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row is kept in registers (d <= 2048), fp32 statistics,
 // two-pass (mean, then centred variance) as equinox.nn.LayerNorm does.
@@ -338,12 +378,13 @@ using namespace eqxv;
 
 #define EQXV_LAUNCH_CHECK() EQXV_CUDA(cudaGetLastError())
 
-extern "C" int eqxv_pack_stem_input(const float* x, void* xpad, int32_t n, int32_t h, int32_t w,
-                                    void* stream) {
-  EQXV_CHECK_ARG(x && xpad && n > 0 && h > 0 && w > 0, "pack_stem_input: bad arguments");
-  const long long total = (long long)n * (h + 6) * (w + 8);
+extern "C" int eqxv_pack_stem_input(const float* x, void* xpad, int32_t n, int32_t c, int32_t h, int32_t w,
+                                    int32_t pad, void* stream) {
+  EQXV_CHECK_ARG(x && xpad && n > 0 && h > 0 && w > 0 && c >= 1 && c <= 8 && pad >= 0 && pad <= 4,
+                 "pack_stem_input: bad arguments");
+  const long long total = (long long)n * (h + 2 * pad) * (w + 8);
   pack_stem_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<bf16x8*>(xpad), n, h, w);
+      x, reinterpret_cast<bf16x8*>(xpad), n, c, h, w, pad);
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }
@@ -436,6 +477,16 @@ extern "C" int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n
   if (h % oh != 0 || w % ow != 0) {
     set_error("adaptive_avgpool: %dx%d -> %dx%d is not an even split (unsupported)", h, w, oh, ow);
     return EQXV_ERR_UNSUPPORTED;
+  }
+  if (oh == 1 && ow == 1 && h * w >= 32) {
+    EQXV_CHECK_ARG(x && y && n > 0 && c > 0 && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 &&
+                       x_pitch >= c && y_pitch >= c && n <= 65535,
+                   "global_avgpool: bad arguments");
+    dim3 grid((unsigned)((c / 8 + 7) / 8), (unsigned)n);
+    global_avgpool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+                                                                  h * w, c, x_pitch, y_pitch);
+    EQXV_LAUNCH_CHECK();
+    return EQXV_OK;
   }
   return pool_common(false, x, y, n, h, w, c, h / oh, w / ow, h / oh, w / ow, 0, oh, ow, x_pitch,
                      y_pitch, (cudaStream_t)stream);

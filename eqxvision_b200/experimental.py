@@ -27,27 +27,6 @@ class _TapWrapper(nn.Module):
         return out
 
 
-def _replace_modules(obj, targets, wrappers):
-    """structure-preserving copy of `obj` with each module in `targets` (by identity) wrapped"""
-    for t, w in zip(targets, wrappers):
-        if obj is t:
-            return w
-    if isinstance(obj, nn.Module):
-        import copy
-
-        new = copy.copy(obj)
-        new.__dict__.pop("_eqxv_plans", None)
-        for f in obj._fields:
-            if f in obj.__dict__:
-                object.__setattr__(new, f, _replace_modules(obj.__dict__[f], targets, wrappers))
-        return new
-    if isinstance(obj, list):
-        return [_replace_modules(v, targets, wrappers) for v in obj]
-    if isinstance(obj, tuple):
-        return tuple(_replace_modules(v, targets, wrappers) for v in obj)
-    return obj
-
-
 def intermediate_layer_getter(model: nn.Module, get_target_layers: Callable) -> nn.Module:
     targets = list(get_target_layers(model))
     taps = [_Tap() for _ in targets]
@@ -57,7 +36,7 @@ def intermediate_layer_getter(model: nn.Module, get_target_layers: Callable) -> 
         wrapped = nn.Sequential(layers)
     else:
         wrappers = [_TapWrapper(t, tap) for t, tap in zip(targets, taps)]
-        wrapped = _replace_modules(model, targets, wrappers)
+        wrapped = nn.tree_at(lambda m: targets, model, replace=wrappers)
 
     class IntermediateLayerGetter(nn.Module):
         model: nn.Module

@@ -18,3 +18,22 @@ from .classification.vit import (  # noqa: F401
     vit_small,
     vit_tiny,
 )
+from .classification.densenet import DenseNet, densenet121, densenet161, densenet169, densenet201  # noqa: F401
+from .classification.efficientnet import (  # noqa: F401
+    EfficientNet,
+    efficientnet_b0,
+    efficientnet_b1,
+    efficientnet_b2,
+    efficientnet_b3,
+    efficientnet_b4,
+    efficientnet_b5,
+    efficientnet_b6,
+    efficientnet_b7,
+    efficientnet_v2_l,
+    efficientnet_v2_m,
+    efficientnet_v2_s,
+)
+from .classification.mobilenetv3 import MobileNetV3, mobilenet_v3_large, mobilenet_v3_small  # noqa: F401
+from .classification.vgg import VGG, vgg11, vgg11_bn, vgg13, vgg13_bn, vgg16, vgg16_bn, vgg19, vgg19_bn  # noqa: F401
+from .segmentation.deeplabv3 import DeepLabV3, deeplabv3  # noqa: F401
+from .segmentation.fcn import FCN, fcn  # noqa: F401

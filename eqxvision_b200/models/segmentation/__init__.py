@@ -1,0 +1,2 @@
+from .deeplabv3 import ASPP, ASPPConv, ASPPPooling, DeepLabHead, DeepLabV3, deeplabv3  # noqa: F401
+from .fcn import FCN, FCNHead, fcn  # noqa: F401

@@ -157,6 +157,39 @@ def tree_inference(pytree, value: bool):
     return rec(pytree)
 
 
+def tree_at(where: Callable, pytree, replace=None, replace_fn: Callable = None):
+    """`equinox.tree_at` for module nodes: copy of `pytree` in which the node(s) returned by
+    `where(pytree)` are replaced (matched by identity), as used by deeplabv3.py:209."""
+    targets = where(pytree)
+    single = not isinstance(targets, (list, tuple))
+    targets = [targets] if single else list(targets)
+    if replace is not None:
+        repl = [replace] if single else list(replace)
+    else:
+        repl = [replace_fn(t) for t in targets]
+
+    def rec(obj):
+        for t, r in zip(targets, repl):
+            if obj is t:
+                return r
+        if isinstance(obj, Module):
+            new = copy.copy(obj)
+            new.__dict__.pop("_eqxv_plans", None)
+            for f in obj._fields:
+                if f in obj.__dict__:
+                    object.__setattr__(new, f, rec(obj.__dict__[f]))
+            return new
+        if isinstance(obj, list):
+            return [rec(v) for v in obj]
+        if isinstance(obj, tuple):
+            return tuple(rec(v) for v in obj)
+        if isinstance(obj, dict):
+            return {k: rec(v) for k, v in obj.items()}
+        return obj
+
+    return rec(pytree)
+
+
 def _uniform_init(key, shape, fan_in) -> torch.Tensor:
     lim = 1.0 / math.sqrt(max(fan_in, 1))
     return jrandom.uniform(key, shape, -lim, lim)

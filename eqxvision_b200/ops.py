@@ -62,23 +62,29 @@ def gemm(a, wgt, bias, *, act=0, residual=None, out=None, out_f32=False, res_aft
     return out
 
 
-def pack_stem_input(x_nchw, out=None, stream=0):
+def pack_stem_input(x_nchw, pad=3, out=None, stream=0):
     _check_cuda(x_nchw, out)
     n, c, h, w = x_nchw.shape
-    assert c == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    assert c <= 8 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
     if out is None:
-        out = torch.empty((n, h + 6, w + 8, 8), dtype=BF16, device=x_nchw.device)
-    call("eqxv_pack_stem_input", ptr(x_nchw), ptr(out), n, h, w, stream)
+        out = torch.empty((n, h + 2 * pad, w + 8, 8), dtype=BF16, device=x_nchw.device)
+    call("eqxv_pack_stem_input", ptr(x_nchw), ptr(out), n, c, h, w, pad, stream)
+    return out
+
+
+def conv_stem(xpad, wgt, bias, *, n, h, w, cout, kh=7, kw=7, stride=2, pad=3, act=1, out=None, stream=0):
+    _check_cuda(xpad, wgt, bias, out)
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), dtype=BF16, device=xpad.device)
+    call("eqxv_conv_stem_bf16", ptr(xpad), ptr(wgt), ptr(bias), ptr(out), n, h, w, cout, kh, kw, stride, pad,
+         out.stride(2), act, stream)
     return out
 
 
 def conv_stem7x7(xpad, wgt, bias, *, n, h, w, cout, act=1, out=None, stream=0):
-    _check_cuda(xpad, wgt, bias, out)
-    if out is None:
-        out = torch.empty((n, h // 2, w // 2, cout), dtype=BF16, device=xpad.device)
-    call("eqxv_conv_stem7x7_bf16", ptr(xpad), ptr(wgt), ptr(bias), ptr(out), n, h, w, cout,
-         out.stride(2), act, stream)
-    return out
+    return conv_stem(xpad, wgt, bias, n=n, h=h, w=w, cout=cout, kh=7, kw=7, stride=2, pad=3, act=act, out=out,
+                     stream=stream)
 
 
 def nchw_to_nhwc(x, c_pad=None, out=None, stream=0):
@@ -178,3 +184,54 @@ def gather_rows(x, n, tokens, row, out=None, stream=0):
         out = torch.empty((n, d), dtype=BF16, device=x.device)
     call("eqxv_gather_rows_bf16", ptr(x), x.stride(0), ptr(out), out.stride(0), n, tokens, row, d, stream)
     return out
+
+
+def dwconv(x, wgt, bias, *, k, stride=1, pad=0, dil=1, act=0, out=None, stream=0):
+    """depthwise conv; x [N,H,W,C] bf16 view, wgt fp32 [k*k, w_pitch], bias fp32 [C]"""
+    _check_cuda(x, wgt, bias, out)
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, k, stride, pad, dil), conv_out_size(w, k, stride, pad, dil)
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    call("eqxv_dwconv_bn_act_bf16", ptr(x), ptr(wgt), ptr(bias), ptr(out), n, h, w, c, k, stride, pad, dil,
+         x.stride(2), out.stride(2), wgt.stride(0), act, stream)
+    return out
+
+
+def eltwise(x, *, scale=None, shift=None, other=None, gate=None, rows_per_image=1, act=0, out=None, stream=0):
+    """rows x c: out = act(x*scale + shift + other) * gate[row // rows_per_image]"""
+    _check_cuda(x, scale, shift, other, gate, out)
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty((rows, c), dtype=BF16, device=x.device)
+    call("eqxv_eltwise_bf16", ptr(x), ptr(scale), ptr(shift), ptr(other), ptr(gate), ptr(out), rows, c,
+         x.stride(0), other.stride(0) if other is not None else 0, gate.stride(0) if gate is not None else 0,
+         out.stride(0), rows_per_image, act, stream)
+    return out
+
+
+def resize_bilinear_to_nchw(x, c, oh, ow, out=None, stream=0):
+    _check_cuda(x, out)
+    n, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+    call("eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32", ptr(x), ptr(out), n, c, h, w, oh, ow, x.stride(2), stream)
+    return out
+
+
+def resize_bilinear(x, oh, ow, out=None, stream=0):
+    _check_cuda(x, out)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, oh, ow, c), dtype=BF16, device=x.device)
+    call("eqxv_resize_bilinear_nhwc_bf16", ptr(x), ptr(out), n, c, h, w, oh, ow, x.stride(2), out.stride(2), stream)
+    return out
+
+
+def copy2d(dst, src, stream=0):
+    """dst[:, :c] = src[:, :c] for 2-D views with arbitrary row pitch"""
+    _check_cuda(dst, src)
+    rows, c = src.shape
+    es = src.element_size()
+    call("eqxv_copy2d_async", ptr(dst), dst.stride(0) * es, ptr(src), src.stride(0) * es, c * es, rows, stream)
+    return dst

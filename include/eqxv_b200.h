@@ -90,16 +90,18 @@ int eqxv_gemm_bias_act_res_bf16(const void* a, int64_t lda, const void* w, const
                                 const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t m,
                                 int32_t n, int32_t k, int32_t act, int32_t flags, void* stream);
 
-/* ResNet stem: conv 7x7 stride 2 pad 3, 3 -> cout channels (+ folded BN + ReLU), resnet.py:243-251,
- * 344-346. Input is the padded 8-channel image written by eqxv_pack_stem_input; weights are
- * [cout, 7, 8, 8] bf16 (tap row, 8 columns of which 7 are real, 8 channels of which 3 are real). */
-int eqxv_conv_stem7x7_bf16(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n,
-                           int32_t h, int32_t w, int32_t cout, int32_t y_pitch, int32_t act,
-                           void* stream);
-/* fp32 NCHW [n,3,h,w] (the reference's input layout, README.md:45) -> bf16 [n, h+6, w+8, 8]:
- * the image sits at rows 3..h+2, columns 3..w+2; border and channels 3..7 are zero. */
-int eqxv_pack_stem_input(const float* x_nchw, void* xpad, int32_t n, int32_t h, int32_t w,
-                         void* stream);
+/* First-layer ("stem") convolution on the raw image, cin <= 8: resnet.py:243-251 (7x7 s2 p3),
+ * vgg.py:137 (3x3 s1 p1), efficientnet.py:327-337 / mobilenetv3.py:196-206 (3x3 s2 p1), densenet.py:175.
+ * Input is the padded 8-channel image written by eqxv_pack_stem_input; weights are [cout, kh, 8, 8] bf16
+ * (filter row, 8 columns of which kw are real, 8 channels of which cin are real). One filter row is
+ * one 64-wide K block of the tcgen05 GEMM (kh <= 8, kw <= 8, stride 1/2, 2*pad <= kw). */
+int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n, int32_t h,
+                        int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
+                        int32_t y_pitch, int32_t act, void* stream);
+/* fp32 NCHW [n,c<=8,h,w] (the reference's input layout, README.md:45) -> bf16 [n, h+2*pad, w+8, 8]:
+ * the image sits at rows pad..h+pad-1, columns pad..w+pad-1; border and channels >= c are zero. */
+int eqxv_pack_stem_input(const float* x_nchw, void* xpad, int32_t n, int32_t c, int32_t h, int32_t w,
+                         int32_t pad, void* stream);
 
 /* input boundary: fp32 NCHW -> bf16 NHWC with channels zero-padded to c_pad (multiple of 8) */
 int eqxv_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w,
@@ -145,6 +147,31 @@ int eqxv_vit_assemble_tokens_bf16(const void* patches, const float* cls, const f
 /* gather row `row` of every image's token block: [n*tokens, d] -> [n, d]  (x[0], vit.py:273) */
 int eqxv_gather_rows_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t n,
                           int32_t tokens, int32_t row, int32_t d, void* stream);
+
+/* K3: depthwise KxK convolution (groups == channels; k in {3,5,7}, stride 1/2) + folded BatchNorm +
+ * activation: layers/conv_norm_activation.py:61-85 with groups=C as built by efficientnet.py:140-151 and
+ * mobilenetv3.py:88-101. wgt: fp32 [k*k, w_pitch] (tap-major, BN scale folded), bias: fp32 [c]. */
+int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const float* bias, void* y, int32_t n,
+                            int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad,
+                            int32_t dil, int32_t x_pitch, int32_t y_pitch, int32_t w_pitch, int32_t act,
+                            void* stream);
+/* K8/K11/K15: y = act(x * scale[c] + shift[c] + other) * gate[row / rows_per_image, c]; every operand
+ * except x may be NULL. Standalone BatchNorm+ReLU (densenet.py:64-65,118,211), unfused residual adds,
+ * the SqueezeExcitation gate `x * scale` (layers/squeeze.py:61). */
+int eqxv_eltwise_bf16(const void* x, const float* scale, const float* shift, const void* other,
+                      const void* gate, void* y, int64_t rows, int32_t c, int32_t x_pitch,
+                      int32_t other_pitch, int32_t gate_pitch, int32_t y_pitch, int32_t rows_per_image,
+                      int32_t act, void* stream);
+/* K14: jax.image.resize(method="bilinear") upsampling (half-pixel centres, edge clamp):
+ * models/segmentation/_utils.py:52,57 (-> fp32 NCHW model output) and deeplabv3.py:74 (-> bf16 NHWC). */
+int eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t n, int32_t c, int32_t h,
+                                               int32_t w, int32_t oh, int32_t ow, int32_t x_pitch,
+                                               void* stream);
+int eqxv_resize_bilinear_nhwc_bf16(const void* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w,
+                                   int32_t oh, int32_t ow, int32_t x_pitch, int32_t y_pitch, void* stream);
+/* K13 fallback: strided device-to-device copy (channel slices of a concat buffer) */
+int eqxv_copy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                      int64_t width_bytes, int64_t rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * plumbing: streams, CUDA graphs, events (cudaStream_t / cudaGraphExec_t / cudaEvent_t as void*)

@@ -175,3 +175,238 @@ def vit(state_dict, x, heads=12, patch=16, eps=1e-5, return_last_attention=False
         out = O.linear_act(out, s.take(), s.take(), round_out=False)
     assert s.done()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# shared pieces for the mobile families
+# ------------------------------------------------------------------------------------------------
+def _make_divisible(v, divisor, min_value=None):
+    """utils.py:104-117"""
+    if min_value is None:
+        min_value = divisor
+    new_v = max(min_value, int(v + divisor / 2) // divisor * divisor)
+    if new_v < 0.9 * v:
+        new_v += divisor
+    return new_v
+
+
+def squeeze_excitation(s: Stream, x, act, gate):
+    """SqueezeExcitation.__call__ (layers/squeeze.py:51-61); fc1/fc2 are 1x1 convs WITH bias"""
+    w1, b1, w2, b2 = s.take(), s.take(), s.take(), s.take()
+    scale = O.rnd(O.adaptive_avg_pool2d(x, 1))
+    scale = O.conv_bn_act(scale, w1, b1, None, act=act)
+    scale = O.conv_bn_act(scale, w2, b2, None, act=gate)
+    return O.rnd(x * scale)
+
+
+def _cna(s: Stream, x, stride=1, padding=0, dilation=1, groups=1, act=None, eps=1e-5, res=None):
+    """ConvNormActivation with BatchNorm and no conv bias (conv_norm_activation.py:56-85)"""
+    w = s.take()
+    return O.conv_bn_act(x, w, None, s.take_bn(), stride, padding, dilation, groups, act=act, res=res, eps=eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# EfficientNet (efficientnet.py)
+# ------------------------------------------------------------------------------------------------
+_EFFNET_V1 = [(1, 3, 1, 32, 16, 1), (6, 3, 2, 16, 24, 2), (6, 5, 2, 24, 40, 2), (6, 3, 2, 40, 80, 3),
+              (6, 5, 1, 80, 112, 3), (6, 5, 2, 112, 192, 4), (6, 3, 1, 192, 320, 1)]  # efficientnet.py:434-442
+_EFFNET_MULT = {"efficientnet_b0": (1.0, 1.0, 1e-5), "efficientnet_b1": (1.0, 1.1, 1e-5),
+                "efficientnet_b2": (1.1, 1.2, 1e-5), "efficientnet_b3": (1.2, 1.4, 1e-5),
+                "efficientnet_b4": (1.4, 1.8, 1e-5), "efficientnet_b5": (1.6, 2.2, 1e-3),
+                "efficientnet_b6": (1.8, 2.6, 1e-3), "efficientnet_b7": (2.0, 3.1, 1e-3)}
+_EFFNET_V2 = {"efficientnet_v2_s": [("F", 1, 3, 1, 24, 24, 2), ("F", 4, 3, 2, 24, 48, 4), ("F", 4, 3, 2, 48, 64, 4),
+                                    ("M", 4, 3, 2, 64, 128, 6), ("M", 6, 3, 1, 128, 160, 9),
+                                    ("M", 6, 3, 2, 160, 256, 15)]}  # efficientnet.py:445-453
+
+
+def efficientnet(state_dict, x, arch="efficientnet_b4"):
+    """EfficientNet.__call__ (efficientnet.py:392-403) with _MBConv (101-186) / _FusedMBConv (195-266)"""
+    import math
+
+    s = Stream(state_dict)
+    if arch in _EFFNET_MULT:
+        wm, dm, eps = _EFFNET_MULT[arch]
+        rows = [("M", e, k, st, _make_divisible(ci * wm, 8), _make_divisible(co * wm, 8), int(math.ceil(n * dm)))
+                for (e, k, st, ci, co, n) in _EFFNET_V1]
+    else:
+        rows, eps = _EFFNET_V2[arch], 1e-3
+    x = _cna(s, x, 2, 1, act="silu", eps=eps)                                  # stem 3x3 s2
+    for kind, e, k, st, ci, co, n in rows:
+        for i in range(n):
+            cin, stride = (ci, st) if i == 0 else (co, 1)
+            exp = _make_divisible(cin * e, 8)
+            use_res = stride == 1 and cin == co
+            inp = x
+            if kind == "M":
+                if exp != cin:                                                  # expand (efficientnet.py:127)
+                    x = _cna(s, x, act="silu", eps=eps)
+                x = _cna(s, x, stride, (k - 1) // 2, groups=exp, act="silu", eps=eps)   # depthwise
+                x = squeeze_excitation(s, x, "silu", "sigmoid")                  # squeeze = max(1, cin//4)
+                x = _cna(s, x, eps=eps, res=inp if use_res else None)            # project (+ x)
+            else:
+                if exp != cin:
+                    x = _cna(s, x, stride, (k - 1) // 2, act="silu", eps=eps)
+                    x = _cna(s, x, eps=eps, res=inp if use_res else None)
+                else:                                                            # single conv, act then + x
+                    w = s.take()
+                    x = O.conv_bn_act(x, w, None, s.take_bn(), stride, (k - 1) // 2, act="silu", eps=eps,
+                                      res=inp if use_res else None, res_after_act=True)
+    x = _cna(s, x, act="silu", eps=eps)                                         # head 1x1
+    x = O.rnd(O.adaptive_avg_pool2d(x, 1).flatten(1))
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)                  # Dropout is a no-op
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# MobileNetV3 (mobilenetv3.py)
+# ------------------------------------------------------------------------------------------------
+_MBV3 = {
+    "mobilenet_v3_large": ([(16, 3, 16, 16, False, "RE", 1), (16, 3, 64, 24, False, "RE", 2),
+                            (24, 3, 72, 24, False, "RE", 1), (24, 5, 72, 40, True, "RE", 2),
+                            (40, 5, 120, 40, True, "RE", 1), (40, 5, 120, 40, True, "RE", 1),
+                            (40, 3, 240, 80, False, "HS", 2), (80, 3, 200, 80, False, "HS", 1),
+                            (80, 3, 184, 80, False, "HS", 1), (80, 3, 184, 80, False, "HS", 1),
+                            (80, 3, 480, 112, True, "HS", 1), (112, 3, 672, 112, True, "HS", 1),
+                            (112, 5, 672, 160, True, "HS", 2), (160, 5, 960, 160, True, "HS", 1),
+                            (160, 5, 960, 160, True, "HS", 1)], 1280),
+    "mobilenet_v3_small": ([(16, 3, 16, 16, True, "RE", 2), (16, 3, 72, 24, False, "RE", 2),
+                            (24, 3, 88, 24, False, "RE", 1), (24, 5, 96, 40, True, "HS", 2),
+                            (40, 5, 240, 40, True, "HS", 1), (40, 5, 240, 40, True, "HS", 1),
+                            (40, 5, 120, 48, True, "HS", 1), (48, 5, 144, 48, True, "HS", 1),
+                            (48, 5, 288, 96, True, "HS", 2), (96, 5, 576, 96, True, "HS", 1),
+                            (96, 5, 576, 96, True, "HS", 1)], 1024),
+}  # mobilenetv3.py:265-336 (width_mult 1, not dilated, not reduced)
+
+
+def mobilenet_v3(state_dict, x, arch="mobilenet_v3_small"):
+    """MobileNetV3.__call__ (mobilenetv3.py:236-247) with _InvertedResidual (62-132); BN eps 1e-3 (:189)"""
+    s = Stream(state_dict)
+    rows, _ = _MBV3[arch]
+    eps = 1e-3
+    x = _cna(s, x, 2, 1, act="hard_swish", eps=eps)
+    for cin, k, exp, cout, use_se, a, stride in rows:
+        act = "hard_swish" if a == "HS" else "relu"
+        inp = x
+        if exp != cin:
+            x = _cna(s, x, act=act, eps=eps)
+        x = _cna(s, x, stride, (k - 1) // 2, groups=exp, act=act, eps=eps)
+        if use_se:
+            x = squeeze_excitation(s, x, "relu", "hard_sigmoid")                # mobilenetv3.py:56-58,103
+        x = _cna(s, x, eps=eps, res=inp if (stride == 1 and cin == cout) else None)
+    x = _cna(s, x, act="hard_swish", eps=eps)                                   # 6 * last channels
+    x = O.rnd(O.adaptive_avg_pool2d(x, 1).flatten(1))
+    x = O.linear_act(x, s.take(), s.take(), act="hard_swish")                   # Linear -> hswish -> Dropout
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# VGG (vgg.py)
+# ------------------------------------------------------------------------------------------------
+_VGG = {"A": [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+        "B": [64, 64, "M", 128, 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+        "D": [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"],
+        "E": [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512,
+              "M"]}
+_VGG_ARCH = {"vgg11": "A", "vgg13": "B", "vgg16": "D", "vgg19": "E"}
+
+
+def vgg_features(s: Stream, x, cfg, batch_norm):
+    """_make_layers (vgg.py:122-150): conv3x3 pad 1 WITH bias, [BN], ReLU; 'M' = maxpool 2x2/2"""
+    for v in cfg:
+        if v == "M":
+            x = O.max_pool2d(x, 2, 2)
+        else:
+            w, b = s.take(), s.take()
+            x = O.conv_bn_act(x, w, b, s.take_bn() if batch_norm else None, 1, 1, act="relu")
+    return x
+
+
+def vgg(state_dict, x, arch="vgg11", features_only=False):
+    """VGG.__call__ (vgg.py:108-119). Classifier = Linear, Dropout, Linear, ReLU, Dropout, Linear: NO ReLU
+    after the first Linear (vgg.py:97-106) - the reference's deviation from torchvision."""
+    bn = arch.endswith("_bn")
+    s = Stream(state_dict)
+    x = vgg_features(s, x, _VGG[_VGG_ARCH[arch.replace("_bn", "")]], bn)
+    if features_only:
+        return x
+    x = O.rnd(O.adaptive_avg_pool2d(x, 7)).flatten(1)                            # ravel in C,H,W order
+    x = O.linear_act(x, s.take(), s.take())
+    x = O.linear_act(x, s.take(), s.take(), act="relu")
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# DenseNet (densenet.py)
+# ------------------------------------------------------------------------------------------------
+_DENSENET = {"densenet121": (32, (6, 12, 24, 16), 64), "densenet161": (48, (6, 12, 36, 24), 96),
+             "densenet169": (32, (6, 12, 32, 32), 64), "densenet201": (32, (6, 12, 48, 32), 64)}
+
+
+def _bn_relu(x, p):
+    return O.rnd(O.relu(_bn(x, p)))
+
+
+def densenet(state_dict, x, arch="densenet121"):
+    """DenseNet.__call__ (densenet.py:220-229): pre-activation dense layers (55-67), transitions (106-133)"""
+    growth, blocks, init = _DENSENET[arch]
+    s = Stream(state_dict)
+    w = s.take()
+    x = O.conv_bn_act(x, w, None, s.take_bn(), 2, 3, act="relu")
+    x = O.max_pool2d(x, 3, 2, 1)
+    for bi, depth in enumerate(blocks):
+        feats = [x]
+        for _ in range(depth):
+            n1 = s.take_bn()
+            w1 = s.take()
+            n2 = s.take_bn()
+            w2 = s.take()
+            cat = torch.cat(feats, 1)                                            # densenet.py:63
+            y = O.conv_bn_act(_bn_relu(cat, n1), w1, None, n2, act="relu")       # norm1,relu,conv1,norm2,relu
+            feats.append(O.conv_bn_act(y, w2, None, None, 1, 1))                 # conv2 (growth channels)
+        x = torch.cat(feats, 1)
+        if bi != len(blocks) - 1:                                                # transition
+            n = s.take_bn()
+            w = s.take()
+            x = O.rnd(O.avg_pool2d(O.conv_bn_act(_bn_relu(x, n), w), 2, 2))
+    x = _bn_relu(x, s.take_bn())                                                 # norm5 + relu
+    x = O.rnd(O.adaptive_avg_pool2d(x, 1).flatten(1))
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# DeepLabV3-ResNet50 (segmentation/deeplabv3.py, fcn.py, _utils.py)
+# ------------------------------------------------------------------------------------------------
+def deeplabv3_resnet50(state_dict, x, rates=(12, 24, 36)):
+    """_SimpleSegmentationModel.__call__ (_utils.py:36-60) -> (aux, out), both (N, classes, H, W).
+    Checkpoint order: backbone (no fc), classifier.0.convs.{0..4}, classifier.0.project, classifier.1/2/4,
+    aux_classifier.0/1/4."""
+    s = Stream(state_dict)
+    h, w = x.shape[-2:]
+    stages = resnet_features(s, x, "resnet50", (False, True, True))              # deeplabv3.py:191-194
+    c3, c4 = stages[2], stages[3]                                               # taps layer3 / layer4
+    # ASPP (deeplabv3.py:77-135)
+    branches = [_cna(s, c4, act="relu")]
+    for r in rates:
+        branches.append(_cna(s, c4, 1, r, r, act="relu"))                       # padding == dilation
+    pooled = O.rnd(O.adaptive_avg_pool2d(c4, 1))
+    pooled = _cna(s, pooled, act="relu")
+    branches.append(O.rnd(O.resize_bilinear(pooled, c4.shape[-2], c4.shape[-1])))   # deeplabv3.py:74
+    y = _cna(s, torch.cat(branches, 1), act="relu")                             # project (+Dropout no-op)
+    y = _cna(s, y, 1, 1, act="relu")                                            # head 3x3
+    wcls, bcls = s.take(), s.take()
+    y = O.conv_bn_act(y, wcls, bcls, None)                                      # 1x1 with bias
+    out = O.resize_bilinear(y, h, w)                                            # _utils.py:51-52
+    # aux FCNHead on layer3 (fcn.py:19-34)
+    a = _cna(s, c3, 1, 1, act="relu")
+    wa, ba = s.take(), s.take()
+    a = O.conv_bn_act(a, wa, ba, None)
+    aux = O.resize_bilinear(a, h, w)
+    assert s.done()
+    return aux, out

@@ -184,3 +184,95 @@ def test_argument_errors_are_reported_not_crashed(device):
     with pytest.raises(_lib.EqxvError):
         ops.conv2d(torch.zeros(1, 8, 8, 8, dtype=torch.bfloat16), rb(device, 16, 8), None, cin=8, cout=16,
                    kh=1, kw=1)  # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("kh,kw,stride,pad,cin,cout,hw", [(7, 7, 2, 3, 3, 64, 224), (3, 3, 1, 1, 3, 64, 64),
+                                                        (3, 3, 2, 1, 3, 48, 224), (3, 3, 2, 1, 3, 16, 96),
+                                                        (5, 5, 1, 2, 4, 40, 33)])
+def test_stem_conv_variants(device, kh, kw, stride, pad, cin, cout, hw):
+    """first-layer convs on the raw fp32 image (ResNet/DenseNet 7x7 s2, VGG 3x3 s1, EfficientNet/MobileNet 3x3 s2)"""
+    from eqxvision_b200 import _pack, ops
+
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, cin, hw, hw, generator=g).to(device)
+    wt = torch.randn(cout, cin, kh, kw, generator=g) * (cin * kh * kw) ** -0.5
+    bias = torch.randn(cout, generator=g).to(device)
+    xpad = ops.pack_stem_input(x, pad=pad)
+    y = ops.conv_stem(xpad, _pack.pack_stem_weight(wt).to(device), bias, n=2, h=hw, w=hw, cout=cout, kh=kh, kw=kw,
+                      stride=stride, pad=pad, act=2)
+    ref = F.silu(F.conv2d(x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float().to(device), bias,
+                          stride=stride, padding=pad))
+    assert rel_l2(y, ref.permute(0, 2, 3, 1)) < TOL_BF16
+
+
+@pytest.mark.parametrize("c,hw,k,stride,dil,act", [(48, 112, 3, 1, 1, 2), (144, 112, 3, 2, 1, 2), (336, 28, 5, 1, 1, 2),
+                                                   (192, 56, 5, 2, 1, 4), (960, 14, 5, 1, 1, 4), (96, 7, 5, 1, 1, 1),
+                                                   (72, 17, 3, 1, 2, 1), (40, 3, 5, 1, 1, 0)])
+def test_depthwise(device, c, hw, k, stride, dil, act):
+    from eqxvision_b200 import _pack, ops
+
+    n = 3
+    pad = (k - 1) // 2 * dil
+    x = rb(device, n, hw, hw, c, seed=1)
+    g = torch.Generator().manual_seed(2)
+    wt = torch.randn(c, 1, k, k, generator=g) * (k * k) ** -0.5
+    bias = torch.randn(c, generator=g)
+    y = ops.dwconv(x, _pack.pack_depthwise_weight(wt, c).to(device), bias.to(device), k=k, stride=stride, pad=pad,
+                   dil=dil, act=act)
+    ref = ACTS[act](F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(device), bias.to(device), stride=stride,
+                             padding=pad, dilation=dil, groups=c))
+    assert rel_l2(y, ref.permute(0, 2, 3, 1)) < TOL_BF16
+
+
+def test_eltwise_variants(device):
+    from eqxvision_b200 import ops
+
+    rows, c, hw = 4 * 49, 272, 49
+    x = rb(device, rows, c, seed=1)
+    o = rb(device, rows, c, seed=2)
+    gate = rb(device, 4, c, seed=3)
+    sc = torch.rand(c, device=device) + 0.5
+    sh = torch.randn(c, device=device)
+    y = ops.eltwise(x, scale=sc, shift=sh, act=1)                         # BatchNorm + ReLU
+    assert rel_l2(y, F.relu(x.float() * sc + sh)) < TOL_BF16
+    y = ops.eltwise(x, other=o, act=1)                                    # residual add + ReLU
+    assert rel_l2(y, F.relu(x.float() + o.float())) < TOL_BF16
+    y = ops.eltwise(x, gate=gate, rows_per_image=hw)                      # SE gate
+    ref = x.float().reshape(4, hw, c) * gate.float().reshape(4, 1, c)
+    assert rel_l2(y, ref.reshape(rows, c)) < TOL_BF16
+    big = torch.zeros(rows, 512, dtype=torch.bfloat16, device=device)
+    ops.eltwise(x, act=4, out=big[:, 64:64 + c])                          # strided destination slice
+    assert rel_l2(big[:, 64:64 + c], F.hardswish(x.float())) < TOL_BF16
+    assert (big[:, :64] == 0).all() and (big[:, 64 + c:] == 0).all()
+
+
+def test_global_avgpool_shapes(device):
+    from eqxvision_b200 import ops
+
+    for (n, hw, c) in [(5, 112, 48), (2, 64, 2048), (3, 14, 960), (7, 7, 24), (2, 5, 8)]:
+        x = rb(device, n, hw, hw, c, seed=c)
+        assert rel_l2(ops.adaptive_avgpool(x, 1, 1), x.float().mean((1, 2), keepdim=True)) < TOL_BF16
+
+
+def test_bilinear_resize(device):
+    from eqxvision_b200 import ops
+
+    x = rb(device, 2, 16, 12, 24, seed=1)
+    xn = x.float().permute(0, 3, 1, 2)
+    y = ops.resize_bilinear_to_nchw(x, 21, 128, 96)
+    ref = F.interpolate(xn[:, :21], size=(128, 96), mode="bilinear", align_corners=False)
+    assert torch.allclose(y, ref, atol=1e-5)
+    yb = ops.resize_bilinear(x, 40, 30)
+    refb = F.interpolate(xn, size=(40, 30), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    assert rel_l2(yb, refb) < TOL_BF16
+    one = rb(device, 2, 1, 1, 256, seed=2)                               # ASPP pooling branch: pure broadcast
+    assert torch.equal(ops.resize_bilinear(one, 8, 8), one.expand(2, 8, 8, 256))
+
+
+def test_copy2d(device):
+    from eqxvision_b200 import ops
+
+    src = rb(device, 100, 64, seed=1)
+    dst = torch.zeros(100, 160, dtype=torch.bfloat16, device=device)
+    ops.copy2d(dst[:, 32:96], src)
+    assert torch.equal(dst[:, 32:96], src) and (dst[:, :32] == 0).all() and (dst[:, 96:] == 0).all()

@@ -58,6 +58,72 @@ def test_resnet_parity(device, save_checkpoint, arch, hw, batch, tol_emu, tol_f3
     assert (got.cpu().argmax(1) == emu.argmax(1)).float().mean() >= 0.75
 
 
+# (ctor, oracle fn name, input hw, batch, tol vs emulation, tol vs fp32)
+FAMILIES = [("vgg11", "vgg", 224, 2, 1.5e-2, 5e-2), ("vgg11_bn", "vgg", 224, 2, 1.5e-2, 5e-2),
+            ("densenet121", "densenet", 224, 2, 2.5e-2, 6e-2), ("mobilenet_v3_small", "mobilenet_v3", 224, 4, 1e-2, 2e-2),
+            ("mobilenet_v3_large", "mobilenet_v3", 224, 2, 1e-2, 2e-2), ("efficientnet_b0", "efficientnet", 224, 4, 1e-2, 2e-2),
+            ("efficientnet_b4", "efficientnet", 224, 2, 1e-2, 2e-2), ("efficientnet_v2_s", "efficientnet", 224, 2, 1.5e-2, 3e-2)]
+
+
+@pytest.mark.parametrize("arch,fn,hw,batch,tol_emu,tol_f32", FAMILIES)
+def test_cnn_family_parity(device, save_checkpoint, arch, fn, hw, batch, tol_emu, tol_f32):
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    sd = ck.torchvision_state_dict(arch, seed=1)
+    net = build(arch, sd, save_checkpoint)
+    x = ck.synthetic_images(batch, h=hw, w=hw, seed=2)
+    got = eb.vmap(net, axis_name="batch")(x, key=keys(batch))
+    oracle = getattr(om, fn)
+    ref = oracle(sd, x, arch)
+    with O.emulate_bf16():
+        emu = oracle(sd, x, arch)
+    assert got.shape == ref.shape
+    assert rel(got, emu) < tol_emu, ("vs bf16-emulating oracle", rel(got, emu))
+    assert rel(got, ref) < tol_f32, ("vs fp32 oracle", rel(got, ref))
+
+
+def test_vgg_features_attribute(device, save_checkpoint):
+    """the reference's VGG test only compares `model.features` (tests/test_models/test_vgg.py:30)"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+
+    sd = ck.torchvision_state_dict("vgg11_bn", seed=1)
+    net = build("vgg11_bn", sd, save_checkpoint)
+    x = ck.synthetic_images(2, h=64, w=64, seed=2)
+    feats = eb.vmap(net.features, axis_name="batch")(x, key=keys(2))
+    ref = om.vgg(sd, x, "vgg11_bn", features_only=True)
+    assert feats.shape == (2, 512, 2, 2)
+    assert rel(feats, ref) < 4e-2
+
+
+def test_deeplabv3_parity(device, save_checkpoint):
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    tv = ck.torchvision_model("deeplabv3_resnet50", seed=1, calib_hw=64, aux_loss=True)
+    sd = tv.state_dict()
+    net = eb.models.deeplabv3(intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024,
+                              torch_weights=save_checkpoint(sd))
+    net = eb.tree_inference(net, True)
+    x = ck.synthetic_images(2, h=128, w=128, seed=2)
+    aux, out = eb.vmap(net, axis_name="batch")(x, key=keys(2))      # (aux, out) order: _utils.py:58
+    assert out.shape == (2, 21, 128, 128) and aux.shape == (2, 21, 128, 128)
+    aux_r, out_r = om.deeplabv3_resnet50(sd, x)
+    with O.emulate_bf16():
+        aux_e, out_e = om.deeplabv3_resnet50(sd, x)
+    # dense per-pixel outputs of an untrained net: no pooling averages the rounding noise away
+    assert rel(out, out_e) < 8e-2 and rel(aux, aux_e) < 4e-2, (rel(out, out_e), rel(aux, aux_e))
+    assert rel(out, out_r) < 2e-1 and rel(aux, aux_r) < 1e-1, (rel(out, out_r), rel(aux, aux_r))
+    agree = (out.cpu().argmax(1) == out_e.argmax(1)).float().mean().item()
+    assert agree > 0.9, agree
+
+
 def test_vit_base_parity(device, save_checkpoint):
     import eqxvision_b200 as eb
     from oracle import checkpoints as ck

@@ -75,12 +75,42 @@ def run(name):
         got = eb.vmap(model)(x, key=eb.random.split(key, 4))
         metrics(name, got, ref)
         bench(model, 64)
+    elif name == "deeplabv3":
+        tv = ck.torchvision_model("deeplabv3_resnet50", seed=1, calib_hw=64, aux_loss=True)
+        sd = tv.state_dict()
+        model = eb.models.deeplabv3(intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024,
+                                    torch_weights=save_sd(sd))
+        model = eb.tree_inference(model, True)
+        x = ck.synthetic_images(2, h=128, w=128, seed=2)
+        aux_r, out_r = om.deeplabv3_resnet50(sd, x)
+        aux, out = eb.vmap(model, axis_name="batch")(x, key=eb.random.split(key, 2))
+        metrics(name + " out", out, out_r)
+        metrics(name + " aux", aux, aux_r)
+        bench(model, 4, (3, 512, 512), iters=5)
     else:
-        raise SystemExit(f"unknown model {name}")
+        fam = {"efficientnet": om.efficientnet, "mobilenet": om.mobilenet_v3, "vgg": om.vgg, "densenet": om.densenet}
+        fn = next(v for k, v in fam.items() if name.startswith(k))
+        sd = ck.torchvision_state_dict(name, seed=1)
+        model = getattr(eb.models, name)(torch_weights=save_sd(sd))
+        model = eb.tree_inference(model, True)
+        x = ck.synthetic_images(4, seed=2)
+        ref = fn(sd, x, name)
+        from oracle import ops as O
+        with O.emulate_bf16():
+            emu = fn(sd, x, name)
+        got = eb.vmap(model, axis_name="batch")(x, key=eb.random.split(key, 4))
+        metrics(name + " vs fp32", got, ref)
+        metrics(name + " vs emu ", got, emu)
+        bench(model, 128)
 
 
 if __name__ == "__main__":
     for n in (sys.argv[1:] or ["resnet18", "resnet50", "vit_base"]):
         t0 = time.time()
-        run(n)
+        try:
+            run(n)
+        except Exception as ex:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            print(f"[{n}] FAILED: {type(ex).__name__}: {ex}", flush=True)
         print(f"   ({n}: {time.time() - t0:.1f}s)", flush=True)
