@@ -170,7 +170,7 @@ class Plan:
             out = self.alloc(self.n * ho * wo, cout, (ho, wo), dtype=torch.float32 if out_f32 else BF16)
 
         if isinstance(xin.expr, T.Input):
-            if c_in <= 8 and kh <= 8 and kw <= 8 and sh in (1, 2) and dh == 1 and 2 * ph <= kw \
+            if c_in <= 8 and kh <= 8 and kw <= 8 and sh in (1, 2, 4) and dh == 1 and 2 * ph <= kw \
                     and res is None and not out_f32 and dst is None:
                 # first-layer conv on the raw image (resnet.py:243-251, vgg.py:137, efficientnet.py:327):
                 # padded NHWC8 image + one GEMM K-block per filter row (eqxv_conv_stem_bf16)
@@ -327,6 +327,31 @@ class Plan:
         out = self.alloc(self.n * t, c, (t,))
         self.step(ops.attention, qkv=qkv.rows(3 * c), images=self.n, tokens=t, heads=e.heads, head_dim=hd,
                   scale=float(e.scale), out=out.rows(c))
+        return out
+
+    def _emit_WindowAttention(self, sym, e: T.WindowAttention):
+        """Swin attention core (swin.py:117-253): roll / window partition / mask are index arithmetic
+        inside eqxv_window_attention_bf16, nothing is permuted in memory."""
+        qkv = self.emit(e.qkv)
+        t, c = sym.shape
+        hd = c // e.heads
+        if qkv.pitch != 3 * c:
+            raise NotImplementedError("window attention expects a dense qkv matrix")
+        if e.window[0] != e.window[1]:
+            raise NotImplementedError("non-square attention windows")
+        out = self.alloc(self.n * t, c, (t,))
+        bias = self.const(e.bias.detach().float().contiguous())
+        self.step(ops.window_attention, qkv=qkv.rows(3 * c), bias=bias, n=self.n, h=e.h, w=e.w, heads=e.heads,
+                  head_dim=hd, window=e.window[0], shift=e.shift, scale=float(e.scale), out=out.rows(c))
+        return out
+
+    def _emit_PatchMerge(self, sym, e: T.PatchMerge):
+        xb = self.emit(e.x)
+        c, h, w = e.x.shape
+        if c % 8 != 0:
+            raise NotImplementedError("patch merging needs a channel count that is a multiple of 8")
+        out = self.alloc(self.n * (h // 2) * (w // 2), 4 * c, (h // 2, w // 2))
+        self.step(ops.patch_merge, x=xb.map(h, w), out=out.map(h // 2, w // 2))
         return out
 
     def _emit_AttentionProbs(self, sym, e):

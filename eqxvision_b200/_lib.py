@@ -63,6 +63,8 @@ SIGNATURES = {
     "eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_resize_bilinear_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_copy2d_async": [_vp, _i64, _vp, _i64, _i64, _i64, _vp],
+    "eqxv_window_attention_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
+    "eqxv_patch_merge_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_stream_create": [C.POINTER(_vp)],
     "eqxv_stream_destroy": [_vp],
     "eqxv_stream_sync": [_vp],
@@ -94,6 +96,7 @@ _LAUNCHING = {
     "eqxv_layernorm_bf16", "eqxv_attention_fwd_bf16", "eqxv_patchify_nchw_f32_bf16",
     "eqxv_vit_assemble_tokens_bf16", "eqxv_gather_rows_bf16", "eqxv_dwconv_bn_act_bf16", "eqxv_eltwise_bf16",
     "eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32", "eqxv_resize_bilinear_nhwc_bf16", "eqxv_copy2d_async",
+    "eqxv_window_attention_bf16", "eqxv_patch_merge_bf16",
 }
 
 

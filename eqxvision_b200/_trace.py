@@ -175,6 +175,21 @@ class Resize(Expr):  # jax.image.resize(method="bilinear"), _utils.py:52
         self.x, self.h, self.w = x, h, w
 
 
+class WindowAttention(Expr):  # swin.py:90-255 between the qkv and proj matmuls
+    __slots__ = ("qkv", "h", "w", "heads", "window", "shift", "bias", "scale")
+
+    def __init__(self, qkv, h, w, heads, window, shift, bias, scale):
+        self.qkv, self.h, self.w, self.heads = qkv, h, w, heads
+        self.window, self.shift, self.bias, self.scale = window, shift, bias, scale
+
+
+class PatchMerge(Expr):  # swin.py:23-33: 2x2 strided gather, channels (x0,x1,x2,x3)
+    __slots__ = ("x",)
+
+    def __init__(self, x):
+        self.x = x
+
+
 # ------------------------------------------------------------------------------------------------
 # symbolic value
 # ------------------------------------------------------------------------------------------------
@@ -271,10 +286,22 @@ def batch_norm(x: Sym, bn) -> Sym:
     return Sym(x.kind, x.shape, BNAct(x, bn))
 
 
+def _under_view(x: Sym):
+    """(C,H,W) <-> (H*W,C) re-interpretations share one channels-last buffer (extensions_2d.py): look
+    through them so that an activation / residual add still folds into the producing GEMM."""
+    e = x.expr
+    if isinstance(e, ToMap):
+        return e.x, lambda y: to_map(y, e.h, e.w)
+    return None, None
+
+
 def activation(x: Sym, fn) -> Sym:
     name = _act_name(fn)
     if name is None:
         return x
+    inner, rewrap = _under_view(x)
+    if inner is not None and isinstance(inner.expr, Linear):
+        return rewrap(activation(inner, name))
     e = x.expr
     if isinstance(e, (Conv, Linear)):
         if e.res is None and e.act1 is None and e.act2 is None:
@@ -293,6 +320,11 @@ def add(a, b) -> Sym:
         raise TypeError("add: both operands must be symbolic activations")
     if a.shape != b.shape:
         raise ValueError(f"add: shape mismatch {a.shape} vs {b.shape}")
+    for p, q in ((a, b), (b, a)):
+        inner, rewrap = _under_view(p)
+        if inner is not None and isinstance(inner.expr, Linear) and inner.expr.res is None \
+                and inner.expr.act2 is None and q.kind == "chw":
+            return rewrap(add(inner, to_tokens(q)))
     for p, q in ((a, b), (b, a)):
         e = p.expr
         if isinstance(e, (Conv, Linear)) and e.res is None and e.act2 is None:
@@ -337,12 +369,16 @@ def ravel(x: Sym) -> Sym:
 
 def to_tokens(x: Sym) -> Sym:
     c, h, w = x.shape
+    if isinstance(x.expr, ToMap):  # (T,C) -> (C,H,W) -> (T,C): the same buffer
+        return x.expr.x
     return Sym("tokens", (h * w, c), ToTokens(x))
 
 
 def to_map(x: Sym, h: int, w: int) -> Sym:
     t, d = x.shape
     assert t == h * w
+    if isinstance(x.expr, ToTokens) and x.expr.x.shape == (d, h, w):
+        return x.expr.x
     return Sym("chw", (d, h, w), ToMap(x, h, w))
 
 
@@ -391,6 +427,25 @@ def concat_channels(xs: Sequence[Sym], capacity: Optional[int] = None) -> Sym:
 def resize_bilinear(x: Sym, h: int, w: int) -> Sym:
     c = x.shape[0]
     return Sym("chw", (c, h, w), Resize(x, h, w))
+
+
+def window_attention(qkv: Sym, h: int, w: int, heads: int, window, shift, bias, scale: float) -> Sym:
+    """softmax(q*scale k^T + bias + shift_mask) v per window; qkv is the (H*W, 3C) token matrix in
+    spatial order, the result is the (H*W, C) matrix in the same order (swin.py:117-253)."""
+    t, c3 = qkv.shape
+    if t != h * w or c3 % (3 * heads) != 0:
+        raise ValueError(f"window_attention: qkv {qkv.shape} does not match a {h}x{w} map with {heads} heads")
+    if h % window[0] != 0 or w % window[1] != 0:
+        # the reference has the padding commented out (swin.py:107-112): its reshape raises
+        raise ValueError(f"feature map {h}x{w} is not a multiple of the window {tuple(window)}")
+    return Sym("tokens", (t, c3 // 3), WindowAttention(qkv, h, w, heads, tuple(window), tuple(shift), bias, scale))
+
+
+def patch_merge(x: Sym) -> Sym:
+    c, h, w = x.shape
+    if h % 2 or w % 2:
+        raise NotImplementedError("patch merging of odd feature maps (zero padding, swin.py:25)")
+    return Sym("chw", (4 * c, h // 2, w // 2), PatchMerge(x))
 
 
 def const_like(t: torch.Tensor) -> Const:

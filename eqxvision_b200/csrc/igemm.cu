@@ -706,7 +706,7 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
                                    int32_t pad, int32_t y_pitch, int32_t act, void* stream) {
   EQXV_CHECK_ARG(xpad && wgt && y, "stem: null pointer");
   EQXV_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0, "stem: bad shape");
-  EQXV_CHECK_ARG(kh >= 1 && kh <= 8 && kw >= 1 && kw <= 8 && stride >= 1 && stride <= 2 && pad >= 0 &&
+  EQXV_CHECK_ARG(kh >= 1 && kh <= 8 && kw >= 1 && kw <= 8 && stride >= 1 && stride <= 4 && pad >= 0 &&
                      2 * pad <= kw,
                  "stem: unsupported geometry k=%dx%d stride %d pad %d", kh, kw, stride, pad);
   EQXV_CHECK_ARG(y_pitch % 8 == 0 && y_pitch >= cout, "stem: bad y_pitch");

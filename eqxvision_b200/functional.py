@@ -49,3 +49,5 @@ prepend_cls_add_pos = T.prepend_cls_add_pos
 attention = T.attention
 to_tokens = T.to_tokens
 to_map = T.to_map
+window_attention = T.window_attention
+patch_merge = T.patch_merge

@@ -235,3 +235,21 @@ def copy2d(dst, src, stream=0):
     es = src.element_size()
     call("eqxv_copy2d_async", ptr(dst), dst.stride(0) * es, ptr(src), src.stride(0) * es, c * es, rows, stream)
     return dst
+
+
+def window_attention(qkv, bias, *, n, h, w, heads, head_dim, window, shift, scale, out=None, stream=0):
+    _check_cuda(qkv, bias, out)
+    if out is None:
+        out = torch.empty((n * h * w, heads * head_dim), dtype=BF16, device=qkv.device)
+    call("eqxv_window_attention_bf16", ptr(qkv), ptr(bias), ptr(out), n, h, w, heads, head_dim, window,
+         shift[0], shift[1], float(scale), stream)
+    return out
+
+
+def patch_merge(x, out=None, stream=0):
+    _check_cuda(x, out)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, 4 * c), dtype=BF16, device=x.device)
+    call("eqxv_patch_merge_bf16", ptr(x), ptr(out), n, h, w, c, x.stride(2), out.stride(2), stream)
+    return out

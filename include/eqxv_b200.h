@@ -169,6 +169,18 @@ int eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t 
                                                void* stream);
 int eqxv_resize_bilinear_nhwc_bf16(const void* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w,
                                    int32_t oh, int32_t ow, int32_t x_pitch, int32_t y_pitch, void* stream);
+/* K16/K6: Swin shifted-window attention (swin.py:90-255): softmax(q*d^-1/2 k^T + rel_pos_bias + shift_mask) v
+ * per (window, head); the cyclic roll, window partition/reverse and the -100 shift mask are index
+ * arithmetic. qkv: [n*h*w, 3*heads*32] in spatial row order, columns (3, heads, 32); bias: fp32
+ * [heads, window^2, window^2] = relative_position_bias_table[relative_position_index] (swin.py:46-57);
+ * out: [n*h*w, heads*32]. */
+int eqxv_window_attention_bf16(const void* qkv, const float* bias, void* out, int32_t n, int32_t h, int32_t w,
+                               int32_t heads, int32_t head_dim, int32_t window, int32_t shift_h,
+                               int32_t shift_w, float scale, void* stream);
+/* K16: patch merging gather (swin.py:23-33): [n,h,w,c] -> [n,h/2,w/2,4c] = concat(x[0::2,0::2],
+ * x[1::2,0::2], x[0::2,1::2], x[1::2,1::2]) along channels. */
+int eqxv_patch_merge_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t x_pitch,
+                          int32_t y_pitch, void* stream);
 /* K13 fallback: strided device-to-device copy (channel slices of a concat buffer) */
 int eqxv_copy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
                       int64_t width_bytes, int64_t rows, void* stream);

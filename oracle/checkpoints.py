@@ -125,3 +125,28 @@ def vit_state_dict(embed_dim=768, depth=12, heads=12, mlp_ratio=4, patch=16, img
         sd["head.weight"] = rn(num_classes, d, std=d ** -0.5)
         sd["head.bias"] = rn(num_classes, std=0.1)
     return sd
+
+
+def swin_model(arch: str = "swin_t", seed: int = 0, tanh_gelu: bool = True) -> torch.nn.Module:
+    """Seeded torchvision Swin (the lineage of the reference's swin.py) with perturbed LayerNorm affine
+    parameters, biases and relative-position tables. `tanh_gelu` swaps torchvision's erf-GELU for the
+    tanh approximation the reference computes (jnn.gelu default, swin.py:567) so that the torchvision
+    forward is a known-answer generator for the reference's arithmetic."""
+    import torchvision
+
+    torch.manual_seed(seed)
+    m = getattr(torchvision.models, arch)(weights=None).eval()
+    g = torch.Generator().manual_seed(seed + 1000)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+            elif n.endswith("bias"):
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+            elif "relative_position_bias_table" in n:
+                p.copy_(0.5 * torch.randn(p.shape, generator=g))
+    if tanh_gelu:
+        for mod in m.modules():
+            if isinstance(mod, torchvision.ops.misc.MLP):
+                mod[1] = torch.nn.GELU(approximate="tanh")
+    return m

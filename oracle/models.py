@@ -410,3 +410,92 @@ def deeplabv3_resnet50(state_dict, x, rates=(12, 24, 36)):
     aux = O.resize_bilinear(a, h, w)
     assert s.done()
     return aux, out
+
+
+# ------------------------------------------------------------------------------------------------
+# Swin Transformer v1 (swin.py)
+# ------------------------------------------------------------------------------------------------
+_SWINS = {
+    "swin_t": (96, [2, 2, 6, 2], [3, 6, 12, 24], 7),
+    "swin_s": (96, [2, 2, 18, 2], [3, 6, 12, 24], 7),
+    "swin_b": (128, [2, 2, 18, 2], [4, 8, 16, 32], 7),
+}
+
+
+def swin_shift_mask(h, w, ws, shift):
+    """the -100 mask of swin.py:184-229, built the way the reference builds it: 3x3 region labels over
+    the ROLLED map, window partition, pairwise label difference. Returns (num_windows, ws*ws, ws*ws)."""
+    labels = torch.zeros(h, w)
+    bands_h = ((0, h - ws), (h - ws, h - shift[0]), (h - shift[0], h))
+    bands_w = ((0, w - ws), (w - ws, w - shift[1]), (w - shift[1], w))
+    for i, (h0, h1) in enumerate(bands_h):
+        for j, (w0, w1) in enumerate(bands_w):
+            labels[h0:h1, w0:w1] = i * 3 + j
+    lab = labels.reshape(h // ws, ws, w // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    diff = lab[:, None, :] - lab[:, :, None]
+    return torch.where(diff == 0, 0.0, -100.0)
+
+
+def swin_attention(x, qkv_w, qkv_b, proj_w, proj_b, table, index, heads, ws, shift, res=None):
+    """_shifted_window_attention (swin.py:90-255) on a batch of channels-last maps (B,H,W,C).
+    Returns proj(...) [+ res] with the windows reversed and the roll undone."""
+    b, h, w, c = x.shape
+    d = c // heads
+    shift = [0 if ws >= h else shift[0], 0 if ws >= w else shift[1]]          # swin.py:115-119
+    if sum(shift) > 0:
+        x = torch.roll(x, shifts=(-shift[0], -shift[1]), dims=(1, 2))          # swin.py:122-123
+    nw = (h // ws) * (w // ws)
+    xw = x.reshape(b, h // ws, ws, w // ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(b * nw, ws * ws, c)
+    qkv = O.linear_act(xw, qkv_w, qkv_b)                                       # swin.py:155-157
+    qkv = qkv.reshape(b * nw, ws * ws, 3, heads, d).permute(2, 0, 3, 1, 4)     # swin.py:158-161
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    n = ws * ws
+    bias = table[index.long()].reshape(n, n, -1).permute(2, 0, 1)              # swin.py:36-46
+    logits = (q * d ** -0.5) @ k.transpose(-1, -2) + bias                      # swin.py:180-183
+    if sum(shift) > 0:
+        mask = swin_shift_mask(h, w, ws, shift)                                # swin.py:185-229
+        logits = (logits.reshape(b, nw, heads, n, n) + mask[None, :, None]).reshape(b * nw, heads, n, n)
+    attn = O.softmax(logits, -1)                                               # swin.py:231
+    out = (attn @ v).permute(0, 2, 1, 3).reshape(b * nw, n, c)                 # swin.py:235-237
+    out = O.rnd(out)
+    # the device adds the residual (in spatial order) inside the proj GEMM; un-window first
+    out = out.reshape(b, h // ws, w // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h, w, c)
+    if sum(shift) > 0:
+        out = torch.roll(out, shifts=(shift[0], shift[1]), dims=(1, 2))        # swin.py:249-250
+    return O.linear_act(out, proj_w, proj_b, res=res)                          # swin.py:238 (+ :572)
+
+
+def swin(state_dict, x, arch="swin_t", eps=1e-5):
+    """SwinTransformer.__call__ (swin.py:762-772), torchvision key order: features.0.{0 conv, 2 norm},
+    per block norm1, attn.{relative_position_bias_table, relative_position_index, qkv, proj}, norm2,
+    mlp.{0,3}; per merge reduction.weight, norm; norm; head."""
+    dim, depths, heads, ws = _SWINS[arch]
+    s = Stream(state_dict)
+    pw, pb = s.take(), s.take()
+    t = O.conv_bn_act(x, pw, pb, None, pw.shape[-1], 0)                        # swin.py:705-713
+    t = t.permute(0, 2, 3, 1)                                                  # channels-last (B,H,W,C)
+    t = O.rnd(O.layer_norm(t, s.take(), s.take(), eps))                        # LayerNorm2d, extensions_2d.py:24-28
+    for i_stage, depth in enumerate(depths):
+        for i_layer in range(depth):
+            n1w, n1b = s.take(), s.take()
+            table, index = s.take(), s.take()
+            qw, qb, ow, ob = s.take(), s.take(), s.take(), s.take()
+            n2w, n2b = s.take(), s.take()
+            f1w, f1b, f2w, f2b = s.take(), s.take(), s.take(), s.take()
+            shift = [0, 0] if i_layer % 2 == 0 else [ws // 2, ws // 2]         # swin.py:733-735
+            y = O.rnd(O.layer_norm(t, n1w, n1b, eps))
+            t = swin_attention(y, qw, qb, ow, ob, table, index, heads[i_stage], ws, shift, res=t)  # swin.py:572-574
+            y = O.rnd(O.layer_norm(t, n2w, n2b, eps))
+            y = O.linear_act(y, f1w, f1b, act="gelu")                          # mlps.py:61-62, tanh GELU
+            t = O.linear_act(y, f2w, f2b, res=t)                               # swin.py:575
+        if i_stage < len(depths) - 1:
+            rw = s.take()                                                      # reduction (no bias) comes first
+            nw_, nb_ = s.take(), s.take()
+            t = torch.cat([t[:, 0::2, 0::2], t[:, 1::2, 0::2], t[:, 0::2, 1::2], t[:, 1::2, 1::2]], -1)  # swin.py:26-31
+            t = O.rnd(O.layer_norm(t, nw_, nb_, eps))                          # swin.py:62
+            t = O.linear_act(t, rw, None)                                      # swin.py:63
+    t = O.rnd(O.layer_norm(t, s.take(), s.take(), eps))                        # swin.py:767
+    pooled = O.rnd(t.mean(dim=(1, 2)))                                         # avgpool + ravel
+    logits = O.linear_act(pooled, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return logits

@@ -171,3 +171,52 @@ def test_vmap_rejects_unsupported_axes_and_needs_cuda():
     if not torch.cuda.is_available():
         with pytest.raises(Exception, match="CUDA|fallback"):
             eb.vmap(net, axis_name="batch")(torch.zeros(1, 3, 64, 64), key=[KEY])
+
+
+def test_swin_traces_to_fused_blocks_and_loads_positionally(tmp_path):
+    """swin.py: field order == torchvision state_dict order (incl. the integer relative_position_index
+    buffer); the (C,H,W)<->(HW,C) transposes of Linear2d/LayerNorm2d vanish; residual adds and the GELU
+    fold into the GEMM epilogues"""
+    from oracle import checkpoints as ck
+
+    for name in ["SwinTransformer", "swin_t", "swin_s", "swin_b", "swin_v2_t", "swin_v2_s", "swin_v2_b"]:
+        assert hasattr(models, name), name
+    p = inspect.signature(models.SwinTransformer.__init__).parameters
+    assert list(p)[1:] == ["patch_size", "embed_dim", "depths", "num_heads", "window_size", "mlp_ratio", "dropout",
+                           "attention_dropout", "stochastic_depth_prob", "num_classes", "norm_layer", "block",
+                           "downsample_layer", "key"]
+    tv = ck.swin_model("swin_t", seed=3)
+    path = tmp_path / "swin_t.pth"
+    torch.save(tv.state_dict(), path)
+    with pytest.warns(UserWarning, match="dynamic padding"):
+        net = models.swin_t(torch_weights=str(path))
+    blk = net.features[1][1]
+    assert blk.attn.shift_size == [3, 3] and blk.attn.relative_position_index.dtype == torch.int64
+    assert torch.equal(blk.attn.relative_position_index, tv.features[1][1].attn.relative_position_index)
+    assert torch.equal(blk.attn.qkv.weight, tv.features[1][1].attn.qkv.weight.detach())
+    assert torch.equal(net.features[2].reduction.weight, tv.features[2].reduction.weight.detach())
+    assert torch.equal(net.head.bias, tv.head.bias.detach())
+    # un-loaded model: the reference's index quirk (sum of relative coordinates, partly negative)
+    with pytest.warns(UserWarning):
+        raw = models.swin_t()
+    idx = raw.features[1][0].attn.relative_position_index
+    assert idx.shape == (49 * 49,) and idx.min() == -12 and idx.max() == 12
+    assert raw.features[1][0].attn.get_relative_position_bias().shape == (3, 49, 49)
+
+    out = trace(eb.tree_inference(net, True), (3, 224, 224))
+    assert out.kind == "vec" and out.shape == (1000,)
+    # walk back: head <- ravel <- avgpool <- ToMap(LayerNorm(tokens))
+    pooled = out.expr.x.expr.x.expr
+    assert isinstance(pooled, T.AdaptiveAvgPool)
+    ln = pooled.x.expr.x.expr
+    assert isinstance(ln, T.LayerNormE)
+    fc2 = ln.x.expr                      # last block: x + mlp(norm2(x)) folded into fc2's epilogue
+    assert isinstance(fc2, T.Linear) and fc2.res is not None
+    fc1 = fc2.x.expr
+    assert isinstance(fc1, T.Linear) and fc1.act1 == "gelu"
+    proj = fc2.res.expr                  # x = x + attn(...) folded into proj's epilogue
+    assert isinstance(proj, T.Linear) and proj.res is not None
+    wa = proj.x.expr
+    assert isinstance(wa, T.WindowAttention) and wa.window == (7, 7) and wa.shift == (0, 0) and wa.heads == 24
+    with pytest.raises(ValueError, match="multiple of the window"):
+        trace(eb.tree_inference(net, True), (3, 200, 200))

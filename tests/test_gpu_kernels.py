@@ -276,3 +276,50 @@ def test_copy2d(device):
     dst = torch.zeros(100, 160, dtype=torch.bfloat16, device=device)
     ops.copy2d(dst[:, 32:96], src)
     assert torch.equal(dst[:, 32:96], src) and (dst[:, :32] == 0).all() and (dst[:, 96:] == 0).all()
+
+
+@pytest.mark.parametrize("n,h,w,heads,shift", [(2, 14, 14, 3, (0, 0)), (2, 14, 14, 3, (3, 3)), (1, 56, 56, 3, (3, 3)),
+                                               (3, 7, 7, 24, (0, 0)), (1, 28, 14, 6, (3, 3))])
+def test_window_attention(device, n, h, w, heads, shift):
+    """eqxv_window_attention_bf16 vs the oracle's swin.py:117-253 restatement (identity qkv/proj)"""
+    from eqxvision_b200 import ops
+    from oracle import models as om
+
+    BF16 = torch.bfloat16
+    ws, d = 7, 32
+    c = heads * d
+    g = torch.Generator().manual_seed(h * 100 + heads + shift[0])
+    qkv = torch.randn((n, h, w, 3 * c), generator=g).to(BF16)
+    table = 0.5 * torch.randn(((2 * ws - 1) ** 2, heads), generator=g)
+    idx = torch.randint(0, (2 * ws - 1) ** 2, (ws ** 4,), generator=g)
+    bias = table[idx].reshape(ws * ws, ws * ws, heads).permute(2, 0, 1).contiguous()
+    got = ops.window_attention(qkv.reshape(-1, 3 * c).to(device), bias.to(device), n=n, h=h, w=w, heads=heads,
+                               head_dim=d, window=ws, shift=shift, scale=d ** -0.5)
+    torch.cuda.synchronize()
+    # oracle: feed qkv through identity "linears" by calling the attention core on pre-computed qkv
+    x = qkv.float()
+    sh = [0 if ws >= h else shift[0], 0 if ws >= w else shift[1]]
+    xr = torch.roll(x, shifts=(-sh[0], -sh[1]), dims=(1, 2)) if sum(sh) else x
+    nw = (h // ws) * (w // ws)
+    xw = xr.reshape(n, h // ws, ws, w // ws, ws, 3 * c).permute(0, 1, 3, 2, 4, 5).reshape(n * nw, ws * ws, 3 * c)
+    q, k, v = xw.reshape(n * nw, ws * ws, 3, heads, d).permute(2, 0, 3, 1, 4)
+    logits = (q * d ** -0.5) @ k.transpose(-1, -2) + bias
+    if sum(sh):
+        mask = om.swin_shift_mask(h, w, ws, sh)
+        logits = (logits.reshape(n, nw, heads, ws * ws, ws * ws) + mask[None, :, None]).reshape(logits.shape)
+    out = (torch.softmax(logits, -1) @ v).permute(0, 2, 1, 3).reshape(n * nw, ws * ws, c)
+    out = out.reshape(n, h // ws, w // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h, w, c)
+    if sum(sh):
+        out = torch.roll(out, shifts=(sh[0], sh[1]), dims=(1, 2))
+    assert rel_l2(got.float().cpu().reshape(n, h, w, c), out) < 4e-3
+
+
+def test_patch_merge_is_bit_exact(device):
+    from eqxvision_b200 import ops
+
+    BF16 = torch.bfloat16
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((3, 8, 6, 24), generator=g).to(BF16)
+    got = ops.patch_merge(x.to(device)).cpu()
+    ref = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)  # swin.py:26-31
+    assert torch.equal(got, ref)

@@ -124,6 +124,26 @@ def test_deeplabv3_parity(device, save_checkpoint):
     assert agree > 0.9, agree
 
 
+def test_swin_t_parity(device, save_checkpoint):
+    """Swin-T through the positional loader (torchvision checkpoint incl. relative_position_index)"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    sd = ck.swin_model("swin_t", seed=1).state_dict()
+    with pytest.warns(UserWarning):
+        net = build("swin_t", sd, save_checkpoint)
+    x = ck.synthetic_images(3, seed=2)
+    got = eb.vmap(net, axis_name="batch")(x, key=keys(3))
+    assert got.shape == (3, 1000) and got.dtype == torch.float32
+    ref = om.swin(sd, x, "swin_t")
+    with O.emulate_bf16():
+        emu = om.swin(sd, x, "swin_t")
+    assert rel(got, emu) < 1.5e-2, ("vs bf16-emulating oracle", rel(got, emu))
+    assert rel(got, ref) < 3e-2, ("vs fp32 oracle", rel(got, ref))
+
+
 def test_vit_base_parity(device, save_checkpoint):
     import eqxvision_b200 as eb
     from oracle import checkpoints as ck

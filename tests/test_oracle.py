@@ -140,3 +140,32 @@ def test_adaptive_pool_even_split_only():
     assert torch.allclose(O.adaptive_avg_pool2d(x, 7), torch.nn.functional.adaptive_avg_pool2d(x, 7))
     with pytest.raises(NotImplementedError):
         O.adaptive_avg_pool2d(x, 5)
+
+
+def test_swin_oracle_matches_torchvision_with_tanh_gelu():
+    """the reference is a torchvision port that differs only in its GELU (jnn.gelu = tanh approximation,
+    swin.py:567); the reference's own check is argmax-only (tests/test_models/test_swin.py:40)"""
+    m = ck.swin_model("swin_t", seed=1)
+    x = ck.synthetic_images(2, seed=2)
+    with torch.no_grad():
+        ref = m(x)
+    got = om.swin(m.state_dict(), x, "swin_t")
+    assert torch.isclose(got, ref, atol=1e-4).all(), (got - ref).abs().max()
+
+
+def test_swin_shift_mask_matches_torchvision_construction():
+    """torchvision builds the mask from slices of the rolled map; the reference from concatenated blocks
+    (swin.py:185-229): same labels"""
+    h = w = 14
+    ws, sh = 7, 3
+    mask = om.swin_shift_mask(h, w, ws, [sh, sh])
+    ref = torch.zeros(h, w)
+    cnt = 0
+    for hs in ((0, -ws), (-ws, -sh), (-sh, None)):
+        for wsl in ((0, -ws), (-ws, -sh), (-sh, None)):
+            ref[hs[0]:hs[1], wsl[0]:wsl[1]] = cnt
+            cnt += 1
+    ref = ref.view(h // ws, ws, w // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    ref = ref.unsqueeze(1) - ref.unsqueeze(2)
+    ref = ref.masked_fill(ref != 0, -100.0)
+    assert torch.equal(mask, ref)
