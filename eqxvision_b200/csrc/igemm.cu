@@ -45,6 +45,9 @@ struct alignas(64) IgemmParams {
   int stages;
   // shared-memory carve-up (byte offsets from the 1024-aligned base)
   int off_out, off_res, off_bias, off_bars;
+  // first-layer (halo) kernel only
+  int h_stride, h_planes, h_px, h_rows, h_plane_pitch, h_stage_bytes, h_ksteps, h_off_b;
+  const void* h_src;  // padded NHWC8 image [n, in_h, in_w, 8]
 };
 
 struct TileCoord {
@@ -164,149 +167,17 @@ __device__ __forceinline__ uint4 epilogue8(const float* v, const float* bias_sme
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// kRes: 0 = no residual, 1 = act(acc + bias + res), 2 = act(acc + bias) + res. Compile-time so that the
-// unrolled epilogue is straight-line code (a runtime flag doubled its instruction count and made the
-// epilogue warps issue-bound on the HBM-bound layers: profiles/r01_layers_v4).
+// ============================== epilogue (warps 2..5) ==============================
+// Shared by the generic implicit-GEMM kernel and the first-layer (halo) kernel.
 template <bool kOutF32, int kAct, int kRes>
-__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* gbase = smem_raw + (base - raw);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
+                                               const uint32_t tmem_base, const int warp, const int lane) {
   const int S = p.stages;
-  const uint32_t stage_bytes = kABytes + p.block_n * 128;
-
   const uint32_t bars = base + p.off_bars;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };  // 8: (epilogue warp, buffer)
-  const uint32_t tmem_slot = bars + 8u * (2 * S + 12);
-  volatile uint32_t* tmem_slot_g =
-      reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 12));
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&p.tmA);
-    tma_prefetch_desc(&p.tmB);
-    tma_prefetch_desc(&p.tmC);
-    if (p.has_res) tma_prefetch_desc(&p.tmR);
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
-    }
-    for (int b = 0; b < 8; ++b) mbar_init(rfull_bar(b), 1);
-    mbar_fence_init();
-  }
-  // folded-BN shift / bias for every output column, once per CTA (zero beyond cout)
+  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
   {
-    float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
-    const int ncols_pad = p.n_tiles * p.block_n + 64;
-    for (int i = threadIdx.x; i < ncols_pad; i += kThreads)
-      sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_g;
-
-  const int taps = p.kh * p.kw;
-
-  if (warp == 0) {
-    // ============================== TMA producer ==============================
-    // The whole warp walks the (uniform) loop and ONE elected lane issues: keeping control flow
-    // warp-uniform lets the compiler hold descriptors/coordinates in uniform registers. (A
-    // single-thread `if (lane == 0)` region made every UTMALDG/UTCHMMA an ELECT+BRA.U.ANY loop and
-    // the issue thread, not the tensor pipe, the bottleneck: profiles/r01_igemm_*.)
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
-      for (int r = 0; r < p.kh; ++r) {
-        const int hc = t.h0 * p.mul_h + r * p.dil_h - p.pad_h;
-        if (hc + (p.th - 1) * p.mul_h < 0 || hc >= p.in_h) continue;  // tap row entirely in the padding
-        for (int s = 0; s < p.kw; ++s) {
-          const int wc = t.w0 * p.mul_w + s * p.dil_w - p.pad_w;
-          if (wc + (p.tw - 1) * p.mul_w < 0 || wc >= p.in_w) continue;
-          const int kb = (r * p.kw + s) * p.cin_pack;
-          for (int c = 0; c < p.kchunks; ++c) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (elect_one()) {
-              const uint32_t a_dst = base + stage * stage_bytes;
-              mbar_expect_tx(full_bar(stage), stage_bytes);
-              tma_load_4d(a_dst, &p.tmA, full_bar(stage), c * kBlockK, wc, hc, t.n0);
-              tma_load_2d(a_dst + kABytes, &p.tmB, full_bar(stage), kb + c * kBlockK, t.ncol0);
-            }
-            __syncwarp();
-            if (++stage == S) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
-    const uint64_t desc_hi = umma_desc_sw128(0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-      uint32_t accumulate = 0;
-      for (int r = 0; r < p.kh; ++r) {
-        const int hc = t.h0 * p.mul_h + r * p.dil_h - p.pad_h;
-        if (hc + (p.th - 1) * p.mul_h < 0 || hc >= p.in_h) continue;
-        for (int s = 0; s < p.kw; ++s) {
-          const int wc = t.w0 * p.mul_w + s * p.dil_w - p.pad_w;
-          if (wc + (p.tw - 1) * p.mul_w < 0 || wc >= p.in_w) continue;
-          for (int c = 0; c < p.kchunks; ++c) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t a_src = base + stage * stage_bytes;
-              const uint64_t adesc = desc_hi | (uint64_t)((a_src & 0x3FFFF) >> 4);
-              const uint64_t bdesc = desc_hi | (uint64_t)(((a_src + kABytes) & 0x3FFFF) >> 4);
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                // +32 bytes per 16-element K step inside the 128-byte swizzle row
-                umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                          accumulate | (uint32_t)k);
-              }
-              umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-            }
-            __syncwarp();
-            accumulate = 1;
-            if (++stage == S) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-        }
-      }
-      if (elect_one()) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
-    }
-  } else {
     // ============================== epilogue (warps 2..5) ==============================
     // Every warp owns the 32 accumulator rows of its TMEM lane quadrant as an independent slab:
     // its own staging buffers, its own TMA stores / residual loads (issued by an elected lane) and
@@ -416,8 +287,539 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     if (lane == 0) tma_store_wait_all();
     __syncwarp();
   }
+}
+
+// kRes: 0 = no residual, 1 = act(acc + bias + res), 2 = act(acc + bias) + res. Compile-time so that the
+// unrolled epilogue is straight-line code (a runtime flag doubled its instruction count and made the
+// epilogue warps issue-bound on the HBM-bound layers: profiles/r01_layers_v4).
+template <bool kOutF32, int kAct, int kRes>
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t stage_bytes = kABytes + p.block_n * 128;
+
+  const uint32_t bars = base + p.off_bars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };  // 8: (epilogue warp, buffer)
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 12);
+  volatile uint32_t* tmem_slot_g =
+      reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 12));
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmC);
+    if (p.has_res) tma_prefetch_desc(&p.tmR);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    for (int b = 0; b < 8; ++b) mbar_init(rfull_bar(b), 1);
+    mbar_fence_init();
+  }
+  // folded-BN shift / bias for every output column, once per CTA (zero beyond cout)
+  {
+    float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
+    const int ncols_pad = p.n_tiles * p.block_n + 64;
+    for (int i = threadIdx.x; i < ncols_pad; i += kThreads)
+      sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  const int taps = p.kh * p.kw;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    // One elected thread runs the whole role (same reasoning as the MMA issuer below): per K block a
+    // barrier wait, an expect_tx and two bulk-tensor loads; ring addresses advance incrementally.
+    if (elect_one()) {
+      uint32_t dst = base, fb = full_bar(0), eb = empty_bar(0);
+      const uint32_t dst_end = base + (uint32_t)S * stage_bytes, fb0 = fb, eb0 = eb;
+      uint32_t phase = 0;
+      const int kh = p.kh, kw = p.kw, kchunks = p.kchunks;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int r = 0; r < kh; ++r) {
+          const int hc = t.h0 * p.mul_h + r * p.dil_h - p.pad_h;
+          if (hc + (p.th - 1) * p.mul_h < 0 || hc >= p.in_h) continue;  // tap row entirely in the padding
+          for (int s = 0; s < kw; ++s) {
+            const int wc = t.w0 * p.mul_w + s * p.dil_w - p.pad_w;
+            if (wc + (p.tw - 1) * p.mul_w < 0 || wc >= p.in_w) continue;
+            int kb = (r * kw + s) * p.cin_pack;
+            for (int c = 0; c < kchunks; ++c, kb += kBlockK) {
+              mbar_wait(eb, phase ^ 1u);
+              mbar_expect_tx(fb, stage_bytes);
+              tma_load_4d(dst, &p.tmA, fb, c * kBlockK, wc, hc, t.n0);
+              tma_load_2d(dst + kABytes, &p.tmB, fb, kb, t.ncol0);
+              dst += stage_bytes, fb += 8, eb += 8;
+              if (dst == dst_end) {
+                dst = base, fb = fb0, eb = eb0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    // ONE thread runs the whole role. Per 64-deep K block it needs: a barrier wait, 4 UTCHMMA, a
+    // commit. Everything else is kept out of the loop (running descriptor / barrier addresses, the
+    // number of K blocks of the tile computed once per tile), because this thread's instruction
+    // latency -- not the tensor pipe -- bounded every layer (profiles/r01_stem_v3: ~70 SASS
+    // instructions and ~650 cycles per K block against 128..512 cycles of MMA work).
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
+      const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+      const uint32_t lbo = 1u << 16;
+      const uint32_t step = stage_bytes >> 4;
+      const uint32_t a_lo0 = ((base & 0x3FFFF) >> 4) | lbo;
+      const uint32_t a_end = a_lo0 + (uint32_t)S * step;
+      const uint32_t b_off = kABytes >> 4;
+      uint32_t a_lo = a_lo0;
+      uint32_t fb = full_bar(0), eb = empty_bar(0);
+      const uint32_t fb0 = fb, eb0 = eb;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int kh = p.kh, kw = p.kw, kchunks = p.kchunks;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int nk = kchunks;
+        if (kh * kw > 1) {  // count the taps the producer does not skip (same predicate)
+          const TileCoord t = decode_tile(p, tile);
+          int vr = 0, vs = 0;
+          for (int r = 0; r < kh; ++r) {
+            const int hc = t.h0 * p.mul_h + r * p.dil_h - p.pad_h;
+            vr += !(hc + (p.th - 1) * p.mul_h < 0 || hc >= p.in_h);
+          }
+          for (int s2 = 0; s2 < kw; ++s2) {
+            const int wc = t.w0 * p.mul_w + s2 * p.dil_w - p.pad_w;
+            vs += !(wc + (p.tw - 1) * p.mul_w < 0 || wc >= p.in_w);
+          }
+          nk = vr * vs * kchunks;
+        }
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        uint32_t accumulate = 0;
+        for (int i = 0; i < nk; ++i) {
+          mbar_wait(fb, phase);
+          tc_fence_after();
+          umma_bf16_kblock64(d_tmem, a_lo, a_lo + b_off, desc_hi, desc_hi, idesc, accumulate, eb);
+          accumulate = 1;
+          a_lo += step, fb += 8, eb += 8;
+          if (a_lo == a_end) {
+            a_lo = a_lo0, fb = fb0, eb = eb0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    epilogue_warps<kOutF32, kAct, kRes>(p, base, gbase, tmem_base, warp, lane);
+  }
 
   // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// First-layer convolution (Cin <= 8 on the raw image): halo tile + overlapping UMMA descriptors.
+//
+// The generic path re-reads every input pixel once per filter row through TMA (7x for the ResNet
+// stem: measured L2->SM bound, 0.46 ms for B=256). Here the padded NHWC8 image tile needed by 128
+// outputs (8 wide x 16 high) is staged ONCE, un-swizzled, and every (filter row r, tap pair 2j/2j+1)
+// MMA reads it in place through a SWIZZLE_NONE K-major descriptor:
+//   * a core matrix = 8 consecutive output columns x one tap (8 channels, 16 B): with the image
+//     columns de-interleaved into `stride` phase planes (a TMA box with element stride `stride`),
+//     those 8 rows are 8 consecutive 16-byte pixels of one plane -> the canonical 128-byte core matrix;
+//   * LBO (second core matrix along K = the next tap) = one pixel (stride 1) or one plane (stride 2/4);
+//   * SBO (next 8 rows = next output row) = `stride` input rows of the plane.
+// Different taps are the same bytes at shifted start addresses; nothing is replicated in shared
+// memory. The whole packed filter (kh x [N x 64] slabs) stays resident for the lifetime of the CTA.
+// Call sites replaced: resnet.py:243-251 (7x7 s2), vgg.py:137 (3x3 s1), efficientnet.py:327 /
+// mobilenetv3.py:193 (3x3 s2), swin.py:705-713 (4x4 s4).
+constexpr int kStemProducers = 4;                       // warps 0, 6, 7, 8
+constexpr int kStemThreads = kThreads + 32 * (kStemProducers - 1);
+
+// The halo tile is gathered with cp.async: its natural granule is one pixel (16 B), which a TMA box can
+// only move as one request per pixel (measured ~5900 cycles per tile). Here a warp instruction moves
+// one contiguous image-row segment and de-interleaves the column phases on the fly. One warp alone is
+// issue-bound on the address arithmetic (profiles/r01_stem_v2: the producer warp never idles), so the
+// rows of a tile are dealt round-robin to kStemProducers warps; every lane arrives on the stage's
+// barrier after ITS copies have landed and been fenced for the async proxy (tcgen05.mma reads).
+__device__ __forceinline__ void stem_gather(const IgemmParams& p, const uint32_t base, const int pw) {
+  const int S = p.stages;
+  const uint32_t bars = base + p.off_bars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  const int lane = threadIdx.x & 31;
+  const int hp = p.in_h, wp = p.in_w;
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(p.h_src);
+  const int span = p.h_px * p.h_stride;  // input pixels per halo row
+  const long long row_b = (long long)wp * 16;
+  const uint32_t drow_b = (uint32_t)(p.h_px * 16);
+  constexpr int kLookahead = 3;          // tiles in flight per warp (cp.async groups)
+  int stage = 0, cstage = 0, pending = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const TileCoord t = decode_tile(p, tile);
+    mbar_wait(empty_bar(stage), phase ^ 1u);
+    const uint32_t a_dst = base + stage * p.h_stage_bytes;
+    const int gy0 = t.h0 * p.h_stride, gx0 = t.w0 * p.h_stride;
+    const int rows_ok = min(p.h_rows, hp - gy0);
+    for (int px = lane; px < span; px += 32) {
+      const int gx = gx0 + px;
+      const bool okx = gx < wp;
+      uint32_t dst = a_dst + (uint32_t)((px % p.h_stride) * p.h_plane_pitch + (px / p.h_stride) * 16) +
+                     (uint32_t)pw * drow_b;
+      const uint8_t* src = img + (((long long)t.n0 * hp + gy0 + pw) * wp + (okx ? gx : 0)) * 16;
+      int y = pw;
+      if (okx) {
+        for (; y < rows_ok; y += kStemProducers) {
+          cp_async_16(dst, src, true);
+          dst += kStemProducers * drow_b;
+          src += kStemProducers * row_b;
+        }
+      }
+      for (; y < p.h_rows; y += kStemProducers) {  // beyond the padded image: zeros
+        cp_async_16(dst, img, false);
+        dst += kStemProducers * drow_b;
+      }
+    }
+    cp_async_commit();
+    if (++pending == kLookahead) {
+      cp_async_wait<kLookahead - 1>();
+      fence_proxy_async_smem();
+      mbar_arrive(full_bar(cstage));
+      if (++cstage == S) cstage = 0;
+      --pending;
+    }
+    if (++stage == S) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  for (; pending > 0; --pending) {
+    mbar_arrive(full_bar(cstage));
+    if (++cstage == S) cstage = 0;
+  }
+}
+
+template <int kAct>
+__global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5;
+  const int S = p.stages;
+  const uint32_t bars = base + p.off_bars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 12);
+  const uint32_t wfull_bar = bars + 8u * (2 * S + 14);
+  volatile uint32_t* tmem_slot_g =
+      reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 12));
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmC);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 32 * kStemProducers);  // every producer lane arrives once its copies landed
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_fence_init();
+  }
+  {
+    float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
+    for (int i = threadIdx.x; i < p.block_n + 64; i += kStemThreads)
+      sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const uint32_t b_smem = base + p.h_off_b;
+  const uint32_t b_slab = (uint32_t)p.block_n * 128u;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (elect_one()) {
+      mbar_expect_tx(wfull_bar, (uint32_t)p.kh * b_slab);
+      for (int r = 0; r < p.kh; ++r) tma_load_2d(b_smem + r * b_slab, &p.tmB, wfull_bar, r * kBlockK, 0);
+    }
+    __syncwarp();
+    stem_gather(p, base, 0);
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
+    const uint64_t bdesc_hi = umma_desc_sw128(0);
+    // A: SWIZZLE_NONE, K-major. LBO = byte distance tap 2j -> tap 2j+1, SBO = next output row.
+    const uint32_t lbo = (p.h_stride == 1) ? 16u : (uint32_t)p.h_plane_pitch;
+    const uint32_t sbo = (uint32_t)(p.h_stride * p.h_px * 16);
+    const uint64_t adesc_hi = ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+    // per-K-step start offsets (tap 2j: plane (2j % stride), pixel 2j / stride), hoisted out of the
+    // issue loop: the single issuing thread must not spend cycles on integer division
+    uint32_t joff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      joff[j] = (uint32_t)(((2 * j) % p.h_stride) * p.h_plane_pitch + ((2 * j) / p.h_stride) * 16) >> 4;
+    const uint32_t row_step = (uint32_t)(p.h_px * 16) >> 4;
+    const int ksteps = p.h_ksteps, kh = p.kh;
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      mbar_wait(wfull_bar, 0);
+      const uint64_t bdesc0 = bdesc_hi | (uint64_t)((b_smem & 0x3FFFF) >> 4);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        const uint32_t a_src = base + stage * p.h_stage_bytes;
+        uint64_t adesc = adesc_hi | (uint64_t)((a_src & 0x3FFFF) >> 4);
+        uint64_t bdesc = bdesc0;
+        for (int r = 0; r < kh; ++r) {
+          umma_bf16(d_tmem, adesc + joff[0], bdesc, idesc, (uint32_t)(r != 0));
+          if (ksteps > 1) umma_bf16(d_tmem, adesc + joff[1], bdesc + 2, idesc, 1u);
+          if (ksteps > 2) umma_bf16(d_tmem, adesc + joff[2], bdesc + 4, idesc, 1u);
+          if (ksteps > 3) umma_bf16(d_tmem, adesc + joff[3], bdesc + 6, idesc, 1u);
+          adesc += row_step;
+          bdesc += b_slab >> 4;
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    epilogue_warps<false, kAct, 0>(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
+  } else {
+    stem_gather(p, base, warp - 5);  // producer warps 1..3
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo-tile convolution (kh x kw, stride 1, small dilation) for large feature maps.
+//
+// The generic kernel moves the A tile once per filter tap (9x for a 3x3), which on the 56x56..224x224
+// layers is bound by the L2->SM path, not by HBM or the tensor pipe (ResNet-50 layer1 3x3: 1.5 TB/s of
+// HBM, 19% tensor). Here ONE 4-D TMA box (64 ch, tw + (kw-1)*dil, th + (kh-1)*dil, 1 image) per 64-deep
+// channel block serves all taps: tap (r, s) is the same 128B-swizzled tile read through a descriptor
+// whose start address is shifted by ((r*dil)*box_w + s*dil) rows and whose 8-row-group stride (SBO) is
+// box_w rows, i.e. one output row (tw = 8). The UMMA swizzle is a function of the shared-memory
+// address bits, exactly like the TMA write pattern, so an unaligned start row is legal with
+// base_offset = 0 (verified on B200 by csrc/debug_umma.cu: gpurun_out/umma_shift.log).
+// B slabs ([block_n x 64] per tap) run through their own ring.
+template <int kAct, int kRes>
+__global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5;
+  const int S = p.stages;        // B ring depth (barrier layout shared with the generic kernel)
+  const int SA = p.h_planes;     // A ring depth
+  const uint32_t bars = base + p.off_bars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 12);
+  auto afull_bar = [&](int s) { return bars + 8u * (2 * S + 14 + s); };
+  auto aempty_bar = [&](int s) { return bars + 8u * (2 * S + 14 + SA + s); };
+  volatile uint32_t* tmem_slot_g =
+      reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 12));
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmC);
+    if (p.has_res) tma_prefetch_desc(&p.tmR);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    for (int b = 0; b < 8; ++b) mbar_init(rfull_bar(b), 1);
+    mbar_fence_init();
+  }
+  {
+    float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
+    const int ncols_pad = p.n_tiles * p.block_n + 64;
+    for (int i = threadIdx.x; i < ncols_pad; i += kThreads)
+      sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const uint32_t a_smem = base + p.h_off_b;          // A ring follows the B ring
+  const uint32_t b_slab = (uint32_t)p.block_n * 128u;
+  const uint32_t a_bytes = (uint32_t)(p.h_px * p.h_rows * 128);
+  const int taps = p.kh * p.kw;
+
+  if (warp == 0) {
+    // ============================== TMA producer (one elected thread) ==============================
+    if (elect_one()) {
+      int sa = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t bdst = base, fb = full_bar(0), eb = empty_bar(0);
+      const uint32_t bdst_end = base + (uint32_t)S * b_slab, fb0 = fb, eb0 = eb;
+      const int kchunks = p.kchunks;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int c = 0; c < kchunks; ++c) {
+          mbar_wait(aempty_bar(sa), pa ^ 1u);
+          mbar_expect_tx(afull_bar(sa), a_bytes);
+          tma_load_4d(a_smem + sa * p.h_stage_bytes, &p.tmA, afull_bar(sa), c * kBlockK, t.w0 - p.pad_w,
+                      t.h0 - p.pad_h, t.n0);
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+          int kb = c * kBlockK;
+          for (int tap = 0; tap < taps; ++tap, kb += p.cin_pack) {
+            mbar_wait(eb, pb ^ 1u);
+            mbar_expect_tx(fb, b_slab);
+            tma_load_2d(bdst, &p.tmB, fb, kb, t.ncol0);
+            bdst += b_slab, fb += 8, eb += 8;
+            if (bdst == bdst_end) {
+              bdst = base, fb = fb0, eb = eb0;
+              pb ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer (one elected thread) ==============================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
+      const uint32_t b_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+      // A: 128B swizzle, K-major, 8-row groups strided by one halo row (SBO = box_w * 128 B)
+      const uint32_t a_hi = ((uint32_t)(p.h_px * 128) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t lbo = 1u << 16;
+      const uint32_t bstep = b_slab >> 4;
+      const uint32_t b_lo0 = ((base & 0x3FFFF) >> 4) | lbo, b_end = b_lo0 + (uint32_t)S * bstep;
+      uint32_t b_lo = b_lo0, fb = full_bar(0), eb = empty_bar(0);
+      const uint32_t fb0 = fb, eb0 = eb;
+      const uint32_t row_step = (uint32_t)(p.dil_h * p.h_px) * 8u, col_step = (uint32_t)p.dil_w * 8u;
+      const int kh = p.kh, kw = p.kw, kchunks = p.kchunks;
+      int sa = 0;
+      uint32_t pa = 0, pb = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        uint32_t accumulate = 0;
+        for (int c = 0; c < kchunks; ++c) {
+          mbar_wait(afull_bar(sa), pa);
+          uint32_t a_row = (((a_smem + sa * p.h_stage_bytes) & 0x3FFFF) >> 4) | lbo;
+          for (int r = 0; r < kh; ++r, a_row += row_step) {
+            uint32_t a_lo = a_row;
+            for (int s2 = 0; s2 < kw; ++s2, a_lo += col_step) {
+              mbar_wait(fb, pb);
+              tc_fence_after();
+              umma_bf16_kblock64(d_tmem, a_lo, b_lo, a_hi, b_hi, idesc, accumulate, eb);
+              accumulate = 1;
+              b_lo += bstep, fb += 8, eb += 8;
+              if (b_lo == b_end) {
+                b_lo = b_lo0, fb = fb0, eb = eb0;
+                pb ^= 1u;
+              }
+            }
+          }
+          umma_commit(aempty_bar(sa));
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    epilogue_warps<false, kAct, kRes>(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
+  }
+
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -487,18 +889,30 @@ static void choose_tile(int n, int ho, int wo, int& tw, int& th, int& tn) {
 // N tile. A single n-tile may be any multiple of 16 (the 64-wide store boxes are clipped at the
 // tensor edge). With several n-tiles the tile width must be a multiple of 64 so that no store box
 // reaches into the neighbouring tile's columns.
-static int choose_block_n(int cout) {
-  if (cout <= 256) return std::max(32, ceil_div(cout, 16) * 16);
-  int best_bn = 256;
-  long long best_cost = -1;
-  for (int bn = 256; bn >= 64; bn -= 64) {
-    const int nt = ceil_div(cout, bn);
-    const long long cost = (long long)nt * bn + 32ll * nt;  // padded MMA work + per-tile A re-read
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
+// The width is chosen against the persistent schedule: the launch takes ceil(tiles / SMs) rounds and a
+// round lasts as long as one tile, so a narrower tile that fills the last round beats a wide one that
+// leaves most SMs idle in it (ViT-B: 99 m-tiles x N=768 is 2.007 rounds of 128x256 but 2.68 of 128x192;
+// ResNet layer4: 98 m-tiles x N=512). Tile time model, in tensor-pipe cycles: 2*bn per 64-deep K block
+// (4 MMAs of bn/2 cycles, B300_MICROARCH.md "tcgen05 floor"), never less than the TMA fill of the
+// stage (A 16 KiB + B bn*128 B at ~48 B/cycle/SM), plus a fixed prologue/drain.
+static int choose_block_n(int cout, long long m_tiles, int kblocks, int sms) {
+  const int single = std::max(32, ceil_div(cout, 16) * 16);
+  int best_bn = 0;
+  double best_cost = 0;
+  auto consider = [&](int bn) {
+    const long long nt = ceil_div(cout, bn);
+    const long long rounds = (m_tiles * nt + sms - 1) / sms;
+    const double mma = 2.0 * bn, fill = (16384.0 + 128.0 * bn) / 48.0;
+    const double tile = (double)kblocks * std::max(mma, fill) + 600.0;
+    const double cost = (double)rounds * tile;
+    if (best_bn == 0 || cost < best_cost * 0.97) {  // prefer the wider tile unless clearly beaten
       best_bn = bn;
+      best_cost = cost;
     }
-  }
+  };
+  if (cout <= 256) consider(single);
+  for (int bn = 256; bn >= 64; bn -= 64)
+    if (bn < cout) consider(bn);
   return best_bn;
 }
 
@@ -507,7 +921,9 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   const bool out_f32 = (q.flags & EQXV_FLAG_OUT_F32) != 0;
   EQXV_CHECK_ARG(!(out_f32 && q.res), "igemm: residual is not supported with fp32 output");
-  const int block_n = choose_block_n(q.cout);
+  const long long m_tiles =
+      (long long)ceil_div(q.out_w, q.tw) * ceil_div(q.out_h, q.th) * ceil_div(q.out_n, q.tn);
+  const int block_n = choose_block_n(q.cout, m_tiles, q.kh * q.kw * q.kchunks, device_sm_count());
   p.block_n = block_n;
   p.acc_stride = ceil_div(block_n, 32) * 32;
   int cols = 32;
@@ -594,7 +1010,27 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   return EQXV_OK;
 }
 
+// halo kernel instantiations: the activations that follow large-map 3x3 convolutions
+static KernelFn halo_table(int act, int res_mode) {
+  static const KernelFn t[3][3] = {{halo_kernel<0, 0>, halo_kernel<1, 0>, halo_kernel<2, 0>},
+                                   {halo_kernel<0, 1>, halo_kernel<1, 1>, halo_kernel<2, 1>},
+                                   {halo_kernel<0, 2>, halo_kernel<1, 2>, halo_kernel<2, 2>}};
+  return (act >= 0 && act <= 2) ? t[res_mode][act] : nullptr;
+}
+
+using StemFn = void (*)(const IgemmParams);
+static StemFn stem_table(int act) {
+  static const StemFn t[kNumActs] = {stem_kernel<0>, stem_kernel<1>, stem_kernel<2>, stem_kernel<3>,
+                                     stem_kernel<4>, stem_kernel<5>, stem_kernel<6>, stem_kernel<7>};
+  return t[act];
+}
+
 int igemm_init() {
+  for (int a = 0; a < kNumActs; ++a)
+    EQXV_CUDA(cudaFuncSetAttribute(stem_table(a), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  for (int a = 0; a < 3; ++a)
+    for (int r = 0; r < 3; ++r)
+      EQXV_CUDA(cudaFuncSetAttribute(halo_table(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < kNumActs; ++a) {
     for (int r = 0; r < 3; ++r)
       EQXV_CUDA(cudaFuncSetAttribute(kernel_table().bf16[r][a], cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -602,6 +1038,119 @@ int igemm_init() {
     EQXV_CUDA(cudaFuncSetAttribute(kernel_table().f32[a], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kMaxSmem));
   }
+  return EQXV_OK;
+}
+
+// Halo-tile variant (see halo_kernel): worthwhile when the map tiles well into 8 x 16 output blocks.
+static bool halo_eligible(const eqxv_conv_desc* d, int ho, int wo) {
+  if (d->stride != 1 || d->dil > 2 || d->kh * d->kw < 4 || d->kh > 5 || d->kw > 5) return false;
+  if (d->flags & EQXV_FLAG_OUT_F32) return false;
+  if (d->act < 0 || d->act > 2) return false;
+  const long long padded = (long long)ceil_div(wo, 8) * 8 * ceil_div(ho, 16) * 16;
+  if (padded * 100 > (long long)wo * ho * 116) return false;           // <= 16 % wasted rows
+  const int bw = 8 + (d->kw - 1) * d->dil, bh = 16 + (d->kh - 1) * d->dil;
+  if (bw * bh * 128 > 48 * 1024) return false;
+  return true;
+}
+
+static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t stream) {
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.tw = 8, p.th = 16, p.tn = 1;
+  p.tiles_w = ceil_div(wo, 8), p.tiles_h = ceil_div(ho, 16), p.tiles_n = d->n;
+  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+  const int kchunks = ceil_div(d->cin, kBlockK);
+  const int block_n = choose_block_n(d->cout, m_tiles, d->kh * d->kw * kchunks, device_sm_count());
+  p.block_n = block_n;
+  p.acc_stride = ceil_div(block_n, 32) * 32;
+  int cols = 32;
+  while (cols < 2 * p.acc_stride) cols <<= 1;
+  p.tmem_cols = cols;
+  p.n_tiles = ceil_div(d->cout, block_n);
+  const long long num_tiles = m_tiles * p.n_tiles;
+  EQXV_CHECK_ARG(num_tiles > 0 && num_tiles < (1ll << 30), "conv: bad tile count %lld", num_tiles);
+  p.num_tiles = (int)num_tiles;
+  p.kh = d->kh, p.kw = d->kw, p.dil_h = p.dil_w = d->dil, p.pad_h = p.pad_w = d->pad;
+  p.mul_h = p.mul_w = 1;
+  p.in_h = d->h, p.in_w = d->w;
+  p.kchunks = kchunks, p.cin_pack = d->cin;
+  p.cout = d->cout, p.act = d->act, p.bias = d->bias;
+  p.res_after_act = (d->flags & EQXV_FLAG_RES_AFTER_ACT) ? 1 : 0;
+  p.has_res = d->residual ? 1 : 0;
+  p.h_px = 8 + (d->kw - 1) * d->dil;     // halo box width (pixels = 128-byte rows)
+  p.h_rows = 16 + (d->kh - 1) * d->dil;  // halo box height
+  p.h_stage_bytes = ceil_div(p.h_px * p.h_rows * 128, 1024) * 1024;
+
+  const int b_slab = block_n * 128;
+  const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
+  EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "conv: cout %d too large for the bias staging area", d->cout);
+  const int fixed = 2 * kStageBuf + (p.has_res ? 2 * kStageBuf : 0) + bias_bytes + 512;
+  int sa = 3;
+  int sb = (kMaxSmem - 1024 - fixed - sa * p.h_stage_bytes) / b_slab;
+  if (sb < 4) {
+    sa = 2;
+    sb = (kMaxSmem - 1024 - fixed - sa * p.h_stage_bytes) / b_slab;
+  }
+  sb = std::min(sb, 8);
+  EQXV_CHECK_ARG(sb >= 2, "conv: not enough shared memory for the halo pipeline");
+  p.stages = sb;
+  p.h_planes = sa;
+  p.h_off_b = sb * b_slab;
+  p.off_out = p.h_off_b + sa * p.h_stage_bytes;
+  p.off_res = p.off_out + 2 * kStageBuf;
+  p.off_bias = p.off_res + (p.has_res ? 2 * kStageBuf : 0);
+  p.off_bars = p.off_bias + bias_bytes;
+  const int smem_bytes = p.off_bars + 512 + 1024;
+
+  TmapSpec a{};
+  a.base = const_cast<void*>(d->x);
+  a.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  a.rank = 4;
+  a.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+  a.dims[0] = (uint64_t)d->cin, a.dims[1] = (uint64_t)d->w, a.dims[2] = (uint64_t)d->h, a.dims[3] = (uint64_t)d->n;
+  a.strides_bytes[0] = (uint64_t)d->x_pitch * 2;
+  a.strides_bytes[1] = a.strides_bytes[0] * (uint64_t)d->w;
+  a.strides_bytes[2] = a.strides_bytes[1] * (uint64_t)d->h;
+  a.box[0] = kBlockK, a.box[1] = (uint32_t)p.h_px, a.box[2] = (uint32_t)p.h_rows, a.box[3] = 1;
+  a.estride[0] = a.estride[1] = a.estride[2] = a.estride[3] = 1;
+  int rc = encode_tmap(&p.tmA, a);
+  if (rc) return rc;
+  TmapSpec b{};
+  b.base = const_cast<void*>(d->wgt);
+  b.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  b.rank = 2;
+  const int ktot = d->kh * d->kw * d->cin;
+  b.dims[0] = (uint64_t)ktot, b.dims[1] = (uint64_t)d->cout;
+  b.strides_bytes[0] = (uint64_t)ktot * 2;
+  b.box[0] = kBlockK, b.box[1] = (uint32_t)block_n;
+  b.estride[0] = b.estride[1] = 1;
+  b.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+  rc = encode_tmap(&p.tmB, b);
+  if (rc) return rc;
+  auto make_out = [&](CUtensorMap* m, const void* ptr, int pitch) -> int {
+    TmapSpec c{};
+    c.base = const_cast<void*>(ptr);
+    c.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    c.rank = 4;
+    c.dims[0] = (uint64_t)d->cout, c.dims[1] = (uint64_t)wo, c.dims[2] = (uint64_t)ho, c.dims[3] = (uint64_t)d->n;
+    c.strides_bytes[0] = (uint64_t)pitch * 2;
+    c.strides_bytes[1] = c.strides_bytes[0] * (uint64_t)wo;
+    c.strides_bytes[2] = c.strides_bytes[1] * (uint64_t)ho;
+    c.box[0] = 64, c.box[1] = 8, c.box[2] = 4, c.box[3] = 1;
+    c.estride[0] = c.estride[1] = c.estride[2] = c.estride[3] = 1;
+    c.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+    return encode_tmap(m, c);
+  };
+  rc = make_out(&p.tmC, d->y, d->y_pitch);
+  if (rc) return rc;
+  if (d->residual) {
+    rc = make_out(&p.tmR, d->residual, d->res_pitch);
+    if (rc) return rc;
+  }
+  const int res_mode = d->residual ? (p.res_after_act ? 2 : 1) : 0;
+  const int grid = std::min(p.num_tiles, device_sm_count());
+  halo_table(d->act, res_mode)<<<grid, kThreads, smem_bytes, stream>>>(p);
+  EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
 
@@ -630,6 +1179,7 @@ extern "C" int eqxv_conv2d_igemm_bf16(const eqxv_conv_desc* d, void* stream) {
   const int ho = (d->h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
   const int wo = (d->w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
   EQXV_CHECK_ARG(ho > 0 && wo > 0, "conv: empty output");
+  if (halo_eligible(d, ho, wo)) return launch_halo(d, ho, wo, (cudaStream_t)stream);
 
   IgemmProblem q{};
   q.wgt = d->wgt;
@@ -713,6 +1263,78 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
   const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
   EQXV_CHECK_ARG(ho > 0 && wo > 0, "stem: empty output");
   const int hp = h + 2 * pad, wp = w + 8;  // layout written by eqxv_pack_stem_input
+  EQXV_CHECK_ARG(act >= 0 && act < kNumActs, "stem: unknown activation %d", act);
+  if (cout <= 256 && (stride == 1 || stride == 2 || stride == 4)) {
+    // ---- halo kernel: one staged image tile serves every filter tap ----
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int block_n = std::max(32, ceil_div(cout, 16) * 16);
+    p.block_n = block_n;
+    p.acc_stride = ceil_div(block_n, 32) * 32;
+    int cols = 32;
+    while (cols < 2 * p.acc_stride) cols <<= 1;
+    p.tmem_cols = cols;
+    p.n_tiles = 1;
+    p.tw = 8, p.th = 16, p.tn = 1;
+    p.tiles_w = ceil_div(wo, p.tw), p.tiles_h = ceil_div(ho, p.th), p.tiles_n = n;
+    const long long num_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    EQXV_CHECK_ARG(num_tiles < (1ll << 30), "stem: too many tiles");
+    p.num_tiles = (int)num_tiles;
+    p.kh = kh, p.kw = kw;
+    p.cout = cout, p.act = act, p.bias = bias;
+    p.h_stride = stride, p.h_planes = stride;
+    p.h_ksteps = ceil_div(kw, 2);
+    const int kw_pad = 2 * p.h_ksteps;
+    p.h_px = p.tw + (kw_pad - 1) / stride;
+    p.h_rows = (p.th - 1) * stride + kh;
+    p.h_plane_pitch = ceil_div(p.h_rows * p.h_px * 16, 128) * 128;
+    p.h_stage_bytes = ceil_div(p.h_plane_pitch * p.h_planes, 1024) * 1024;
+    const int b_bytes = kh * block_n * 128;
+    const int bias_bytes = ceil_div((block_n + 64) * 4, 1024) * 1024;
+    int stages = (kMaxSmem - 1024 - b_bytes - 2 * kStageBuf - bias_bytes - 256) / p.h_stage_bytes;
+    stages = std::min(stages, 6);
+    EQXV_CHECK_ARG(stages >= 2, "stem: not enough shared memory (k=%dx%d cout=%d)", kh, kw, cout);
+    p.stages = stages;
+    p.h_off_b = stages * p.h_stage_bytes;
+    p.off_out = p.h_off_b + b_bytes;
+    p.off_res = p.off_out + 2 * kStageBuf;
+    p.off_bias = p.off_res;
+    p.off_bars = p.off_bias + bias_bytes;
+    const int smem_bytes = p.off_bars + 256 + 1024;
+
+    p.h_src = xpad;
+    p.in_h = hp, p.in_w = wp;
+    EQXV_CHECK_ARG(stages >= 4, "stem: pipeline too shallow");
+    int rc;
+    TmapSpec b{};
+    b.base = const_cast<void*>(wgt);
+    b.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    b.rank = 2;
+    b.dims[0] = (uint64_t)(kh * 64), b.dims[1] = (uint64_t)cout;
+    b.strides_bytes[0] = (uint64_t)(kh * 64) * 2;
+    b.box[0] = kBlockK, b.box[1] = (uint32_t)block_n;
+    b.estride[0] = b.estride[1] = 1;
+    b.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+    rc = encode_tmap(&p.tmB, b);
+    if (rc) return rc;
+    TmapSpec c{};
+    c.base = y;
+    c.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    c.rank = 4;
+    c.dims[0] = (uint64_t)cout, c.dims[1] = (uint64_t)wo, c.dims[2] = (uint64_t)ho, c.dims[3] = (uint64_t)n;
+    c.strides_bytes[0] = (uint64_t)y_pitch * 2;
+    c.strides_bytes[1] = c.strides_bytes[0] * (uint64_t)wo;
+    c.strides_bytes[2] = c.strides_bytes[1] * (uint64_t)ho;
+    c.box[0] = 64, c.box[1] = 8, c.box[2] = 4, c.box[3] = 1;   // one epilogue warp's slab: 4 rows x 8 columns
+    c.estride[0] = c.estride[1] = c.estride[2] = c.estride[3] = 1;
+    c.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+    rc = encode_tmap(&p.tmC, c);
+    if (rc) return rc;
+    const int grid = std::min(p.num_tiles, device_sm_count());
+    stem_table(act)<<<grid, kStemThreads, smem_bytes, (cudaStream_t)stream>>>(p);
+    EQXV_CUDA(cudaGetLastError());
+    return EQXV_OK;
+  }
   IgemmProblem q{};
   q.wgt = wgt;
   q.ktot = kh * 64;

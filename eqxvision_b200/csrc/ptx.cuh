@@ -119,6 +119,20 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// cp.async (LDGSTS): 16-byte gathers whose granularity is too fine for TMA boxes
+// ----------------------------------------------------------------------------------------------
+// copies 16 bytes, or writes 16 zero bytes when `valid` is false (src-size 0)
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -149,6 +163,43 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One 64-deep K block: 4 x (128 x N x 16) MMAs on 128B-swizzled K-major operands (+32 B per K step
+// inside the swizzle row) followed by the commit that releases the smem stage. One asm block so that
+// the single issuing thread spends its cycles on UTCHMMA, not on descriptor arithmetic. a_lo / b_lo are
+// the low descriptor words ((addr & 0x3FFFF) >> 4); desc_hi the constant high word.
+__device__ __forceinline__ void umma_bf16_kblock64(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                   uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                                   uint32_t accumulate, uint32_t commit_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 a1, b1;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "setp.eq.b32 p, 0, 0;\n"
+      "add.u32 a1, %1, 2;\n"
+      "add.u32 b1, %2, 2;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "add.u32 a1, %1, 4;\n"
+      "add.u32 b1, %2, 4;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "add.u32 a1, %1, 6;\n"
+      "add.u32 b1, %2, 6;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(commit_bar)
       : "memory");
 }
 // All previously issued tcgen05.mma of this thread arrive on `bar` when complete.

@@ -39,6 +39,14 @@ CONV_CASES = [
     (8, 14, 14, 512, 512, 3, 2, 1, 1, 0, False, False),
     (2, 224, 224, 8, 48, 3, 2, 1, 1, 2, False, False),     # EfficientNet stem on the padded image
     (1, 1, 1, 2048, 272, 1, 1, 0, 1, 4, False, False),     # SE-style 1x1 on a 1x1 map, odd N
+    # halo-tile path (stride 1, maps that tile into 8x16 blocks): one staged tile serves all taps
+    (2, 112, 112, 24, 24, 3, 1, 1, 1, 2, True, True),      # FusedMBConv single conv: act then residual, cin < 64
+    (1, 56, 56, 128, 320, 3, 1, 1, 1, 1, True, False),     # two n-tiles + residual before relu
+    (2, 64, 64, 64, 64, 3, 1, 2, 2, 1, False, False),      # dilation 2 halo
+    (1, 224, 224, 64, 64, 3, 1, 1, 1, 1, False, False),    # VGG conv1_2
+    (2, 48, 40, 72, 40, 5, 1, 2, 1, 0, False, False),      # 5x5, channels not a multiple of 64
+    (3, 56, 56, 256, 256, 3, 1, 1, 1, 0, False, False),    # several K blocks through the A ring
+    (2, 30, 23, 64, 96, 3, 1, 1, 1, 1, False, False),      # ragged edges inside the halo tiles
 ]
 
 
@@ -188,7 +196,8 @@ def test_argument_errors_are_reported_not_crashed(device):
 
 @pytest.mark.parametrize("kh,kw,stride,pad,cin,cout,hw", [(7, 7, 2, 3, 3, 64, 224), (3, 3, 1, 1, 3, 64, 64),
                                                         (3, 3, 2, 1, 3, 48, 224), (3, 3, 2, 1, 3, 16, 96),
-                                                        (5, 5, 1, 2, 4, 40, 33)])
+                                                        (5, 5, 1, 2, 4, 40, 33), (4, 4, 4, 0, 3, 96, 224),
+                                                        (7, 7, 2, 3, 3, 64, 50), (3, 3, 2, 1, 3, 24, 31)])
 def test_stem_conv_variants(device, kh, kw, stride, pad, cin, cout, hw):
     """first-layer convs on the raw fp32 image (ResNet/DenseNet 7x7 s2, VGG 3x3 s1, EfficientNet/MobileNet 3x3 s2)"""
     from eqxvision_b200 import _pack, ops
