@@ -7,6 +7,9 @@
 // shuffles across the 4 lanes that share a row), so S = q k^T never leaves the SM.
 // v1 uses the legacy mma.sync tensor path (HMMA): attention is ~4 % of ViT-B/16 FLOPs; the tcgen05
 // version is tracked in DESIGN.md.
+#include <algorithm>
+#include <cstring>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -195,7 +198,299 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
   }
 }
 
-int attention_init() { return EQXV_OK; }
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 version (tokens <= 208): persistent, one CTA per SM, a flat sequence of 128-query tiles
+// g = 0, 1, ... over the (image, head) pairs of this CTA.
+//
+//   S_g[128 x Tk] = Q_g K^T          tcgen05.mma, A = Q tile, B = K (both K-major SW128), fp32 in TMEM;
+//                                    two S regions (g & 1) so that S_{g+2} is produced while g+1 is in softmax
+//   P_g = exp2((S_g - rowmax) * scale*log2e)   8 softmax warps, TWO threads per query row, each holds half
+//                                    of the row's scores in registers (one TMEM pass, no online rescaling:
+//                                    the whole key axis fits), bf16 P -> SW128 smem
+//   O_g[128 x 64] = P_g V            A = P (K-major), B = V read MN-major straight from the TMA tile
+//   out = O_g / rowsum               fp32 row sums accumulated from the unrounded probabilities
+//
+// Software pipeline of the softmax warps: softmax(g) | drain O_{g-1} | write P_g: the exponentials
+// (MUFU-bound) of tile g overlap the P.V product of tile g-1 and the Q.K^T of tile g+1; they only ever
+// wait for work that was issued a whole softmax earlier.
+// warp 0: one thread issues the TMA loads (Q/K/V of the next pair are prefetched into the second smem
+// buffer) and all MMAs. Tk = tokens rounded up to 16; rows/keys beyond `tokens` are zero-filled by TMA
+// (3-D map: column, token, image) and masked. Reference arithmetic: vit.py:62-73.
+constexpr int kAtThreads = 288;
+
+struct alignas(64) AttnParams {
+  CUtensorMap tm;        // qkv as [images][tokens][3*heads*64]
+  __nv_bfloat16* out;
+  int tokens, tk, heads, pairs, ntile;
+  int op_bytes;          // bytes per operand buffer (tk * 128 rounded up to 1024)
+  float scale_log2;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr uint32_t kAtS = 208;   // TMEM columns per S region; O lives at [2*kAtS, 2*kAtS + 64)
+
+template <int NCH>  // 8-key chunks held per softmax thread (2 threads per row): 13 covers Tk <= 208
+__global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t buf_bytes = 3u * (uint32_t)p.op_bytes;
+  const uint32_t p_smem = base + 2 * buf_bytes;            // P: 4 K-blocks of [128 x 64] (64 KiB)
+  uint8_t* p_g = gbase + 2 * buf_bytes;
+  float* red_g = reinterpret_cast<float*>(gbase + 2 * buf_bytes + 65536);   // [2 halves][128] x {max, sum}
+  const uint32_t bars = p_smem + 65536 + 2048;
+  auto bar_load = [&](int b) { return bars + 8u * b; };
+  auto bar_s = [&](int r) { return bars + 16u + 8u * r; };
+  const uint32_t bar_p = bars + 32u, bar_o = bars + 40u;
+  const uint32_t tmem_slot = bars + 48u;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbase + 2 * buf_bytes + 65536 + 2048 + 48);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tm);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_load(i), 1);
+      mbar_init(bar_s(i), 1);
+    }
+    mbar_init(bar_p, 256);
+    mbar_init(bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const int C = p.heads * 64;
+  const int my_pairs = ((int)blockIdx.x < p.pairs) ? (p.pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int G = my_pairs * p.ntile;   // tiles this CTA processes
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint64_t hi = (uint64_t)(umma_desc_sw128(0) >> 32) << 32;   // SBO 1024, SW128 (K-major and MN-major)
+      const uint32_t lbo = 1u << 16;
+      const uint32_t idesc_s = umma_idesc_bf16_m128((uint32_t)p.tk);
+      const uint32_t idesc_o = umma_idesc_bf16_m128_bmn(64);
+      const int ksteps = p.tk / 16;
+      const uint32_t p_lo = ((p_smem & 0x3FFFF) >> 4) | lbo;
+      auto issue_load = [&](int pi) {   // pi: index of the pair inside this CTA's sequence
+        const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
+        const int img = pair / p.heads, head = pair - img * p.heads;
+        const int b = pi & 1;
+        const uint32_t dst = base + b * buf_bytes;
+        mbar_expect_tx(bar_load(b), 3u * (uint32_t)(p.tk * 128));
+        for (int o = 0; o < 3; ++o) {
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+              ::"r"(dst + o * p.op_bytes), "l"(reinterpret_cast<uint64_t>(&p.tm)), "r"(bar_load(b)),
+                "r"(o * C + head * 64), "r"(0), "r"(img)
+              : "memory");
+        }
+      };
+      auto issue_qk = [&](int g) {      // S_g -> region g & 1
+        const int pi = g / p.ntile, t = g - pi * p.ntile;
+        if (t == 0) mbar_wait(bar_load(pi & 1), (uint32_t)((pi >> 1) & 1));
+        const uint32_t q_s = base + (pi & 1) * buf_bytes;
+        const uint32_t q_lo = (((q_s + t * 16384) & 0x3FFFF) >> 4) | lbo;
+        const uint32_t k_lo = (((q_s + p.op_bytes) & 0x3FFFF) >> 4) | lbo;
+        const uint32_t d = tmem_base + (uint32_t)(g & 1) * kAtS;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, hi | (q_lo + 2 * k), hi | (k_lo + 2 * k), idesc_s, (uint32_t)k);
+        umma_commit(bar_s(g & 1));
+      };
+      if (my_pairs > 0) issue_load(0);
+      if (my_pairs > 1) issue_load(1);
+      if (G > 0) issue_qk(0);
+      if (G > 1) issue_qk(1);
+      for (int g = 0; g < G; ++g) {
+        const int pi = g / p.ntile, t = g - pi * p.ntile;
+        mbar_wait(bar_p, (uint32_t)(g & 1));    // P_g written; S_g fully read; O_{g-1} drained
+        tc_fence_after();
+        const uint32_t v_s = base + (pi & 1) * buf_bytes + 2 * p.op_bytes;
+        const uint32_t v_lo = ((v_s & 0x3FFFF) >> 4) | lbo;
+        const uint32_t d = tmem_base + 2 * kAtS;
+        for (int j = 0; j < ksteps; ++j)
+          umma_bf16(d, hi | (p_lo + (uint32_t)((j >> 2) * 1024 + (j & 3) * 2)), hi | (v_lo + (uint32_t)(j * 128)),
+                    idesc_o, (uint32_t)j);
+        umma_commit(bar_o);
+        if (t == p.ntile - 1 && pi + 2 < my_pairs) {
+          mbar_wait(bar_o, (uint32_t)(g & 1));  // last reader of this pair's buffer has finished
+          issue_load(pi + 2);
+        }
+        if (g + 2 < G) issue_qk(g + 2);         // region g & 1 is free again
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== softmax + output: warps 1..8 ==============================
+    const int sw = warp - 1;                 // 0..7
+    const int half = sw >> 2;                // which half of the key axis this thread owns
+    const int quad = warp & 3;               // TMEM lane quadrant
+    const int row = quad * 32 + lane;        // query row inside the tile
+    // column split in units of 8 keys. Every thread processes NCH chunks starting at ch0; chunks past the
+    // key axis are masked to -inf / never written, so the loops below are fully unrolled with the scores
+    // in registers.
+    const int nch_tot = p.tk / 8;
+    const int ch0 = half ? (nch_tot + 1) / 2 : 0;
+    const int ch_end = half ? nch_tot : (nch_tot + 1) / 2;   // first chunk NOT owned by this thread
+    const int lim = min(p.tokens, ch_end * 8);               // keys >= lim are not this thread's (or do not exist)
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+
+    // drain O of tile `g` (TMEM -> registers -> global), scaled by the row's 1/sum
+    auto drain = [&](int g, float inv, bool live) {
+      mbar_wait(bar_o, (uint32_t)(g & 1));
+      tc_fence_after();
+      if (live) {
+        const int pi = g / p.ntile, t = g - pi * p.ntile;
+        const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
+        const int img = pair / p.heads, head = pair - img * p.heads;
+        float o[32];
+        const uint32_t oaddr = lane_addr + 2 * kAtS + (uint32_t)(half * 32);
+        tmem_ld_x16(oaddr, o);
+        tmem_ld_x16(oaddr + 16, o + 16);
+        tmem_ld_wait();
+        const int tok = t * 128 + row;
+        if (tok < p.tokens) {
+          __nv_bfloat16* dst = p.out + ((long long)img * p.tokens + tok) * C + head * 64 + half * 32;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(o[q * 8 + 2 * e] * inv, o[q * 8 + 2 * e + 1] * inv);
+              w[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    };
+
+    float inv_prev = 0.f;
+    bool live_prev = false;
+    for (int g = 0; g < G; ++g) {
+      const int t = g % p.ntile;
+      const bool live = t * 128 + quad * 32 < p.tokens;   // warp-uniform: any valid row in this warp's slab
+      float inv = 0.f;
+      uint32_t pk[NCH][4];
+      mbar_wait(bar_s(g & 1), (uint32_t)((g >> 1) & 1));
+      tc_fence_after();
+      if (live) {
+        float s[NCH][8];
+        const uint32_t taddr = lane_addr + (uint32_t)(g & 1) * kAtS + (uint32_t)(ch0 * 8);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_ld_x8(taddr + c * 8, s[c]);
+        tmem_ld_wait();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if ((ch0 + c) * 8 + 8 > lim) {   // warp-uniform: only the chunk(s) straddling the end need masking
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if ((ch0 + c) * 8 + e >= lim) s[c][e] = -INFINITY;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) mx = fmaxf(mx, s[c][e]);
+        }
+        red_g[half * 128 + row] = mx;
+        named_bar_sync(1, 256);
+        mx = fmaxf(mx, red_g[(half ^ 1) * 128 + row]);
+        const float mb = mx * p.scale_log2;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const float p0 = ex2_approx(fmaf(s[c][e], p.scale_log2, -mb));       // ex2(-inf) = 0: masked keys
+            const float p1 = ex2_approx(fmaf(s[c][e + 1], p.scale_log2, -mb));
+            sum += p0 + p1;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+            pk[c][e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+        }
+        red_g[256 + half * 128 + row] = sum;
+        named_bar_sync(2, 256);
+        sum += red_g[256 + (half ^ 1) * 128 + row];
+        inv = 1.f / sum;
+      } else {
+        named_bar_sync(1, 256);
+        named_bar_sync(2, 256);
+      }
+      // O_{g-1}: its P.V was issued a whole softmax ago. Draining it here also means the P buffer is free.
+      if (g > 0) drain(g - 1, inv_prev, live_prev);
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col = (ch0 + c) * 8;
+          if (col < ch_end * 8) {   // chunks past this thread's range belong to the other half
+            uint8_t* dst = p_g + (col >> 6) * 16384 + sw128_off((uint32_t)row, (uint32_t)((col & 63) >> 3));
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+          }
+        }
+      }
+      tc_fence_before();           // TMEM reads (S_g, O_{g-1}) ordered before the MMAs that overwrite them
+      fence_proxy_async_smem();    // P visible to the tensor core (async proxy)
+      mbar_arrive(bar_p);
+      inv_prev = inv;
+      live_prev = live;
+    }
+    if (G > 0) drain(G - 1, inv_prev, live_prev);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_attention_tc(const void* qkv, void* out, int images, int tokens, int heads, float scale,
+                               cudaStream_t stream) {
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.tokens = tokens, p.heads = heads, p.pairs = images * heads;
+  p.tk = ceil_div(tokens, 16) * 16;
+  p.ntile = ceil_div(tokens, 128);
+  p.op_bytes = ceil_div(p.tk * 128, 1024) * 1024;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  TmapSpec m{};
+  m.base = const_cast<void*>(qkv);
+  m.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  m.rank = 3;
+  const uint64_t ld = 3ull * heads * 64;
+  m.dims[0] = ld, m.dims[1] = (uint64_t)tokens, m.dims[2] = (uint64_t)images;
+  m.strides_bytes[0] = ld * 2, m.strides_bytes[1] = ld * 2 * (uint64_t)tokens;
+  m.box[0] = 64, m.box[1] = (uint32_t)p.tk, m.box[2] = 1;
+  m.estride[0] = m.estride[1] = m.estride[2] = 1;
+  m.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+  int rc = encode_tmap(&p.tm, m);
+  if (rc) return rc;
+  // smem: 2 x (Q,K,V) + P (64 KiB) + reductions (2 KiB) + barriers; the Q tile of the second M block may be
+  // read up to row 255 of a tk-row buffer: the bytes behind it (K, V, P) are finite garbage feeding rows
+  // that are never stored.
+  const int smem = 2 * 3 * p.op_bytes + 65536 + 2048 + 128 + 1024;
+  const int grid = std::min(p.pairs, device_sm_count());
+  attention_tc_kernel<13><<<grid, kAtThreads, smem, stream>>>(p);
+  EQXV_CUDA(cudaGetLastError());
+  return EQXV_OK;
+}
+
+int attention_init() {
+  EQXV_CUDA(cudaFuncSetAttribute(attention_tc_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  return EQXV_OK;
+}
 
 }  // namespace eqxv
 
@@ -213,6 +508,9 @@ extern "C" int eqxv_attention_fwd_bf16(const void* qkv, void* out, float* attn_o
     set_error("attention: returning the probability matrix is not implemented yet");
     return EQXV_ERR_UNSUPPORTED;
   }
+  // tcgen05 path: the double-buffered Q/K/V tiles + P fit in shared memory up to 208 keys (ViT @224: 197)
+  if (tokens <= 208 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0)
+    return launch_attention_tc(qkv, out, images, tokens, heads, scale, (cudaStream_t)stream);
   EQXV_CHECK_ARG(heads <= 65535 && images <= 65535, "attention: grid too large");
   dim3 grid((unsigned)((tokens + kQT - 1) / kQT), (unsigned)heads, (unsigned)images);
   attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(

@@ -219,6 +219,14 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 8 consecutive fp32 columns -> 8 registers per thread
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -244,6 +252,12 @@ __host__ __device__ inline uint32_t umma_idesc_bf16_m128(uint32_t n) {
   d |= (n >> 3) << 17;   // N / 8
   d |= (128u >> 4) << 24;  // M / 16
   return d;
+}
+
+// kind::f16 instruction descriptor with B read MN-major (b_major bit 16): B[n][k] stored with n
+// contiguous, e.g. the V operand of attention ([key][head_dim] rows) used as B[head_dim x key].
+__host__ __device__ inline uint32_t umma_idesc_bf16_m128_bmn(uint32_t n) {
+  return umma_idesc_bf16_m128(n) | (1u << 16);
 }
 
 // Byte offset of 16-byte chunk `j` (0..7) of row `r` inside a 128B-swizzled tile whose base is

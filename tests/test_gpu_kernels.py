@@ -154,7 +154,8 @@ def test_layernorm(device, rows, d):
     assert rel_l2(ops.layernorm(x, g, b, 1e-5), F.layer_norm(x.float(), (d,), g, b, 1e-5)) < TOL_BF16
 
 
-@pytest.mark.parametrize("imgs,tokens,heads", [(2, 197, 12), (1, 64, 3), (3, 50, 6), (1, 785, 6), (2, 1, 2)])
+@pytest.mark.parametrize("imgs,tokens,heads", [(2, 197, 12), (1, 64, 3), (3, 50, 6), (1, 785, 6), (2, 1, 2), (64, 197, 12),
+                                               (5, 256, 4), (3, 128, 2), (2, 129, 3), (7, 210, 5), (1, 16, 1)])
 def test_attention(device, imgs, tokens, heads):
     from eqxvision_b200 import ops
 
