@@ -65,6 +65,7 @@ SIGNATURES = {
     "eqxv_copy2d_async": [_vp, _i64, _vp, _i64, _i64, _i64, _vp],
     "eqxv_window_attention_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "eqxv_patch_merge_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_debug_attention_timeline": [_vp],
     "eqxv_stream_create": [C.POINTER(_vp)],
     "eqxv_stream_destroy": [_vp],
     "eqxv_stream_sync": [_vp],

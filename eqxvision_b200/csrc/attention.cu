@@ -8,6 +8,7 @@
 // v1 uses the legacy mma.sync tensor path (HMMA): attention is ~4 % of ViT-B/16 FLOPs; the tcgen05
 // version is tracked in DESIGN.md.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -225,6 +226,7 @@ struct alignas(64) AttnParams {
   int tokens, tk, heads, pairs, ntile;
   int op_bytes;          // bytes per operand buffer (tk * 128 rounded up to 1024)
   float scale_log2;
+  long long* ts;   // optional phase timestamps of CTA 0 (tools/attn_timeline.py); NULL in production
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -232,6 +234,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// phase timestamps: slot = tile * 16 + event, events 0..7 MMA thread, 8..15 softmax warp 1 lane 0
+#define AT_TS(ev, g)                                                                          \
+  do {                                                                                        \
+    if (p.ts != nullptr && blockIdx.x == 0 && (g) < 16) p.ts[(g) * 16 + (ev)] = clock64();    \
+  } while (0)
 
 constexpr uint32_t kAtS = 208;   // TMEM columns per S region; O lives at [2*kAtS, 2*kAtS + 64)
 
@@ -314,8 +322,10 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       if (G > 1) issue_qk(1);
       for (int g = 0; g < G; ++g) {
         const int pi = g / p.ntile, t = g - pi * p.ntile;
+        AT_TS(0, g);
         mbar_wait(bar_p, (uint32_t)(g & 1));    // P_g written; S_g fully read; O_{g-1} drained
         tc_fence_after();
+        AT_TS(1, g);
         const uint32_t v_s = base + (pi & 1) * buf_bytes + 2 * p.op_bytes;
         const uint32_t v_lo = ((v_s & 0x3FFFF) >> 4) | lbo;
         const uint32_t d = tmem_base + 2 * kAtS;
@@ -323,11 +333,14 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
           umma_bf16(d, hi | (p_lo + (uint32_t)((j >> 2) * 1024 + (j & 3) * 2)), hi | (v_lo + (uint32_t)(j * 128)),
                     idesc_o, (uint32_t)j);
         umma_commit(bar_o);
+        AT_TS(2, g);
         if (t == p.ntile - 1 && pi + 2 < my_pairs) {
           mbar_wait(bar_o, (uint32_t)(g & 1));  // last reader of this pair's buffer has finished
           issue_load(pi + 2);
         }
+        AT_TS(3, g);
         if (g + 2 < G) issue_qk(g + 2);         // region g & 1 is free again
+        AT_TS(4, g);
       }
     }
     __syncwarp();
@@ -346,35 +359,29 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
     const int lim = min(p.tokens, ch_end * 8);               // keys >= lim are not this thread's (or do not exist)
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 
-    // drain O of tile `g` (TMEM -> registers -> global), scaled by the row's 1/sum
-    auto drain = [&](int g, float inv, bool live) {
-      mbar_wait(bar_o, (uint32_t)(g & 1));
-      tc_fence_after();
-      if (live) {
-        const int pi = g / p.ntile, t = g - pi * p.ntile;
-        const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
-        const int img = pair / p.heads, head = pair - img * p.heads;
-        float o[32];
-        const uint32_t oaddr = lane_addr + 2 * kAtS + (uint32_t)(half * 32);
-        tmem_ld_x16(oaddr, o);
-        tmem_ld_x16(oaddr + 16, o + 16);
-        tmem_ld_wait();
-        const int tok = t * 128 + row;
-        if (tok < p.tokens) {
-          __nv_bfloat16* dst = p.out + ((long long)img * p.tokens + tok) * C + head * 64 + half * 32;
+    // O of tile g: TMEM -> registers (before the P write of the next tile is announced: the next P.V
+    // overwrites O), registers -> global AFTER the announcement so that neither the proxy fence nor the
+    // MMA issuer ever waits on global stores.
+    auto store_o = [&](const float* o, int g, float inv) {
+      const int pi = g / p.ntile, t = g - pi * p.ntile;
+      const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
+      const int img = pair / p.heads, head = pair - img * p.heads;
+      const int tok = t * 128 + row;
+      if (tok < p.tokens) {
+        __nv_bfloat16* dst = p.out + ((long long)img * p.tokens + tok) * C + head * 64 + half * 32;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t w[4];
+        for (int q = 0; q < 4; ++q) {
+          uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(o[q * 8 + 2 * e] * inv, o[q * 8 + 2 * e + 1] * inv);
-              w[e] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(o[q * 8 + 2 * e] * inv, o[q * 8 + 2 * e + 1] * inv);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
           }
+          *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
     };
+    const uint32_t oaddr = lane_addr + 2 * kAtS + (uint32_t)(half * 32);
 
     float inv_prev = 0.f;
     bool live_prev = false;
@@ -383,15 +390,18 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       const bool live = t * 128 + quad * 32 < p.tokens;   // warp-uniform: any valid row in this warp's slab
       float inv = 0.f;
       uint32_t pk[NCH][4];
+      const bool rec = threadIdx.x == 32;
+      if (rec) AT_TS(8, g);
       mbar_wait(bar_s(g & 1), (uint32_t)((g >> 1) & 1));
       tc_fence_after();
+      if (rec) AT_TS(9, g);
       if (live) {
         float s[NCH][8];
         const uint32_t taddr = lane_addr + (uint32_t)(g & 1) * kAtS + (uint32_t)(ch0 * 8);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) tmem_ld_x8(taddr + c * 8, s[c]);
         tmem_ld_wait();
-        float mx = -INFINITY;
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains (ILP)
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           if ((ch0 + c) * 8 + 8 > lim) {   // warp-uniform: only the chunk(s) straddling the end need masking
@@ -400,25 +410,29 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
               if ((ch0 + c) * 8 + e >= lim) s[c][e] = -INFINITY;
           }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) mx = fmaxf(mx, s[c][e]);
+          for (int e = 0; e < 8; ++e) m4[e & 3] = fmaxf(m4[e & 3], s[c][e]);
         }
+        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         red_g[half * 128 + row] = mx;
+        if (rec) AT_TS(10, g);
         named_bar_sync(1, 256);
         mx = fmaxf(mx, red_g[(half ^ 1) * 128 + row]);
         const float mb = mx * p.scale_log2;
-        float sum = 0.f;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
             const float p0 = ex2_approx(fmaf(s[c][e], p.scale_log2, -mb));       // ex2(-inf) = 0: masked keys
             const float p1 = ex2_approx(fmaf(s[c][e + 1], p.scale_log2, -mb));
-            sum += p0 + p1;
+            s4[(e >> 1) & 3] += p0 + p1;
             const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
             pk[c][e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           }
         }
+        float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         red_g[256 + half * 128 + row] = sum;
+        if (rec) AT_TS(11, g);
         named_bar_sync(2, 256);
         sum += red_g[256 + (half ^ 1) * 128 + row];
         inv = 1.f / sum;
@@ -426,8 +440,19 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
         named_bar_sync(1, 256);
         named_bar_sync(2, 256);
       }
-      // O_{g-1}: its P.V was issued a whole softmax ago. Draining it here also means the P buffer is free.
-      if (g > 0) drain(g - 1, inv_prev, live_prev);
+      // O_{g-1}: its P.V was issued a whole softmax ago; once it is complete the P buffer is free as well.
+      if (rec) AT_TS(12, g);
+      float o[32];
+      if (g > 0) {
+        mbar_wait(bar_o, (uint32_t)((g - 1) & 1));
+        tc_fence_after();
+        if (live_prev) {
+          tmem_ld_x16(oaddr, o);
+          tmem_ld_x16(oaddr + 16, o + 16);
+          tmem_ld_wait();
+        }
+      }
+      if (rec) AT_TS(13, g);
       if (live) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -441,10 +466,22 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
       tc_fence_before();           // TMEM reads (S_g, O_{g-1}) ordered before the MMAs that overwrite them
       fence_proxy_async_smem();    // P visible to the tensor core (async proxy)
       mbar_arrive(bar_p);
+      if (rec) AT_TS(14, g);
+      if (g > 0 && live_prev) store_o(o, g - 1, inv_prev);
       inv_prev = inv;
       live_prev = live;
     }
-    if (G > 0) drain(G - 1, inv_prev, live_prev);
+    if (G > 0) {
+      mbar_wait(bar_o, (uint32_t)((G - 1) & 1));
+      tc_fence_after();
+      if (live_prev) {
+        float o[32];
+        tmem_ld_x16(oaddr, o);
+        tmem_ld_x16(oaddr + 16, o + 16);
+        tmem_ld_wait();
+        store_o(o, G - 1, inv_prev);
+      }
+    }
   }
 
   tc_fence_before();
@@ -454,6 +491,8 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+static long long* g_attn_ts = nullptr;   // set by eqxv_debug_attention_timeline
 
 static int launch_attention_tc(const void* qkv, void* out, int images, int tokens, int heads, float scale,
                                cudaStream_t stream) {
@@ -465,6 +504,7 @@ static int launch_attention_tc(const void* qkv, void* out, int images, int token
   p.ntile = ceil_div(tokens, 128);
   p.op_bytes = ceil_div(p.tk * 128, 1024) * 1024;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.ts = g_attn_ts;
   TmapSpec m{};
   m.base = const_cast<void*>(qkv);
   m.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -516,5 +556,12 @@ extern "C" int eqxv_attention_fwd_bf16(const void* qkv, void* out, float* attn_o
   attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, tokens, heads, scale * 1.4426950408889634f);
   EQXV_CUDA(cudaGetLastError());
+  return EQXV_OK;
+}
+
+// Debug aid (not on the product path): when `ts` is non-NULL the tcgen05 attention kernel records clock64()
+// phase timestamps of CTA 0 into ts[16 tiles][16 events]; pass NULL to switch it off again.
+extern "C" int eqxv_debug_attention_timeline(long long* ts) {
+  g_attn_ts = ts;
   return EQXV_OK;
 }

@@ -144,7 +144,8 @@ def test_pooling_and_layout(device):
     assert torch.equal(ops.nhwc_to_nchw(xb), xb.float().permute(0, 3, 1, 2))
 
 
-@pytest.mark.parametrize("rows,d", [(1000, 768), (333, 96), (64, 2048), (5, 192)])
+@pytest.mark.parametrize("rows,d", [(1000, 768), (333, 96), (64, 2048), (5, 192), (12608, 768), (700, 1024), (3, 256),
+                                     (50, 512)])
 def test_layernorm(device, rows, d):
     from eqxvision_b200 import ops
 
