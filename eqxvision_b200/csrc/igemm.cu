@@ -17,6 +17,7 @@
 // jax.nn activation as composed in resnet.py:144-162, conv_norm_activation.py:61-85, vit.py:64,74,
 // mlps.py:61-65 (reference paths; see include/eqxv_b200.h).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -54,10 +55,15 @@ struct TileCoord {
   int ncol0, w0, h0, n0;
 };
 
+// kPair: `tile` counts pairs of m-tiles; the CTA's rank inside its cluster picks the m-tile. An m-tile
+// past the end (odd m-tile count) decodes to an out-of-range image index: TMA zero-fills its loads and
+// clips its stores.
+template <bool kPair = false>
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
   TileCoord t;
   const int nt = tile % p.n_tiles;
   int m = tile / p.n_tiles;
+  if constexpr (kPair) m = 2 * m + (int)(blockIdx.x & 1u);
   t.ncol0 = nt * p.block_n;
   t.w0 = (m % p.tiles_w) * p.tw;
   m /= p.tiles_w;
@@ -169,10 +175,12 @@ __device__ __forceinline__ uint4 epilogue8(const float* v, const float* bias_sme
 
 // ============================== epilogue (warps 2..5) ==============================
 // Shared by the generic implicit-GEMM kernel and the first-layer (halo) kernel.
-template <bool kOutF32, int kAct, int kRes>
+template <bool kOutF32, int kAct, int kRes, bool kPair = false>
 __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
                                                const uint32_t tmem_base, const int warp, const int lane) {
   const int S = p.stages;
+  const int t_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // persistent schedule of this CTA
+  const int t_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t bars = base + p.off_bars;
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
@@ -201,9 +209,9 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
 
     auto issue_res = [&](uint32_t gg) {  // called by ONE lane
       const int ti = gg / cpt, c = gg - ti * cpt;
-      const long long tile = (long long)blockIdx.x + (long long)ti * gridDim.x;
+      const long long tile = (long long)t_first + (long long)ti * t_stride;
       if (tile >= p.num_tiles) return;
-      const TileCoord t = decode_tile(p, (int)tile);
+      const TileCoord t = decode_tile<kPair>(p, (int)tile);
       const uint32_t b = gg & 1u;
       mbar_expect_tx(rbar(b), kSlab);
       tma_load_4d(res_u32 + b * kStageBuf, &p.tmR, rbar(b), t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
@@ -218,8 +226,8 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
     __syncwarp();
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = t_first; tile < p.num_tiles; tile += t_stride) {
+      const TileCoord t = decode_tile<kPair>(p, tile);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_stride);
@@ -242,7 +250,11 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
         if (c == cpt - 1) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
           tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
+          if constexpr (kPair) {
+            mbar_arrive_leader(tempty_bar(acc));   // the leader's issuer waits for both CTAs' epilogues
+          } else {
+            mbar_arrive(tempty_bar(acc));
+          }
         }
         const float* bias_c = s_bias + t.ncol0 + c * CH;
         uint8_t* out_row = out_g + buf * kStageBuf;
@@ -451,6 +463,164 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the K-deep layers.
+//
+// With one CTA per tile every 64-deep K block moves 16 KiB of A plus block_n*128 B of B into the SM
+// (48 KiB for a 128x256 tile) against 512 tensor-pipe cycles of work; the layers with K >= 256 ran at
+// ~900 cycles per K block, i.e. at the L2->SM fill rate (~54 B/cycle/SM), not at the MMA rate. Here
+// two CTAs of a cluster (one TPC) compute a 256 x block_n tile with ONE tcgen05.mma.cta_group::2
+// stream issued by the leader: each CTA loads only its own 128 A rows and HALF of the B slab, so the
+// fill per SM and K block drops to 16 KiB + block_n*64 B (32 KiB) for the same 512 cycles.
+// Protocol: full[s] lives in the leader (both producers' TMA bytes are credited to it), the MMA
+// commits are multicast to empty[s] / tfull[a] of both CTAs, both epilogues arrive on the leader's
+// tempty[a]. The epilogue itself is the single-CTA one (each CTA drains its own 128 TMEM lanes).
+template <int kAct, int kRes>
+__device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t rank = blockIdx.x & 1u;            // == %cluster_ctarank for a (2,1,1) cluster
+  const uint32_t b_half = (uint32_t)p.block_n * 64u;   // bytes of this CTA's half of the B slab
+  const uint32_t stage_bytes = kABytes + b_half;
+
+  const uint32_t bars = base + p.off_bars;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 12);
+  volatile uint32_t* tmem_slot_g =
+      reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 12));
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmC);
+    if (p.has_res) tma_prefetch_desc(&p.tmR);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);    // used in the leader only: its producer's arrive.expect_tx
+      mbar_init(empty_bar(s), 1);   // one multicast commit per phase
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 256);  // leader: 4 epilogue warps of each CTA
+    }
+    for (int b = 0; b < 8; ++b) mbar_init(rfull_bar(b), 1);
+    mbar_fence_init();
+  }
+  {
+    float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
+    const int ncols_pad = p.n_tiles * p.block_n + 64;
+    for (int i = threadIdx.x; i < ncols_pad; i += kThreads)
+      sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything is signalled remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const int t_first = (int)(blockIdx.x >> 1), t_stride = (int)(gridDim.x >> 1);
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs) ==============================
+    if (elect_one()) {
+      uint32_t dst = base, fb = full_bar(0), eb = empty_bar(0);
+      const uint32_t dst_end = base + (uint32_t)S * stage_bytes, fb0 = fb, eb0 = eb;
+      uint32_t phase = 0;
+      const int kh = p.kh, kw = p.kw, kchunks = p.kchunks;
+      const int nrow = (int)rank * (p.block_n / 2);   // this CTA's rows of the B slab
+      for (int tile = t_first; tile < p.num_tiles; tile += t_stride) {
+        const TileCoord t = decode_tile<true>(p, tile);
+        for (int r = 0; r < kh; ++r) {
+          const int hc = t.h0 * p.mul_h + r * p.dil_h - p.pad_h;
+          for (int s = 0; s < kw; ++s) {
+            const int wc = t.w0 * p.mul_w + s * p.dil_w - p.pad_w;
+            int kb = (r * kw + s) * p.cin_pack;
+            for (int c = 0; c < kchunks; ++c, kb += kBlockK) {
+              mbar_wait(eb, phase ^ 1u);
+              if (rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);   // both CTAs' bytes land on this barrier
+              tma_load_4d_pair(dst, &p.tmA, fb, c * kBlockK, wc, hc, t.n0);
+              tma_load_2d_pair(dst + kABytes, &p.tmB, fb, kb, t.ncol0 + nrow);
+              dst += stage_bytes, fb += 8, eb += 8;
+              if (dst == dst_end) {
+                dst = base, fb = fb0, eb = eb0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer (leader CTA only) ==============================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16_m256((uint32_t)p.block_n);
+      const uint32_t desc_hi = (uint32_t)(umma_desc_sw128(0) >> 32);
+      const uint32_t lbo = 1u << 16;
+      const uint32_t step = stage_bytes >> 4;
+      const uint32_t a_lo0 = ((base & 0x3FFFF) >> 4) | lbo;
+      const uint32_t a_end = a_lo0 + (uint32_t)S * step;
+      const uint32_t b_off = kABytes >> 4;
+      uint32_t a_lo = a_lo0;
+      uint32_t fb = full_bar(0), eb = empty_bar(0);
+      const uint32_t fb0 = fb, eb0 = eb;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int nk = p.kh * p.kw * p.kchunks;
+      for (int tile = t_first; tile < p.num_tiles; tile += t_stride) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        uint32_t accumulate = 0;
+        for (int i = 0; i < nk; ++i) {
+          mbar_wait(fb, phase);
+          tc_fence_after();
+          umma_bf16_kblock64_pair(d_tmem, a_lo, a_lo + b_off, desc_hi, desc_hi, idesc, accumulate, eb);
+          accumulate = 1;
+          a_lo += step, fb += 8, eb += 8;
+          if (a_lo == a_end) {
+            a_lo = a_lo0, fb = fb0, eb = eb0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_pair(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    epilogue_warps<false, kAct, kRes, true>(p, base, gbase, tmem_base, warp, lane);
+  }
+
+  // ---- teardown: neither CTA may leave while its peer can still touch its smem / TMEM / barriers ----
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+template <int kAct, int kRes>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    pair_kernel(const __grid_constant__ IgemmParams p) {
+  pair_kernel_body<kAct, kRes>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -892,9 +1062,7 @@ static void choose_tile(int n, int ho, int wo, int& tw, int& th, int& tn) {
 // The width is chosen against the persistent schedule: the launch takes ceil(tiles / SMs) rounds and a
 // round lasts as long as one tile, so a narrower tile that fills the last round beats a wide one that
 // leaves most SMs idle in it (ViT-B: 99 m-tiles x N=768 is 2.007 rounds of 128x256 but 2.68 of 128x192;
-// ResNet layer4: 98 m-tiles x N=512). Tile time model, in tensor-pipe cycles: 2*bn per 64-deep K block
-// (4 MMAs of bn/2 cycles, B300_MICROARCH.md "tcgen05 floor"), never less than the TMA fill of the
-// stage (A 16 KiB + B bn*128 B at ~48 B/cycle/SM), plus a fixed prologue/drain.
+// ResNet layer4: 98 m-tiles x N=512). The tile time model is fitted to B200 measurements.
 static int choose_block_n(int cout, long long m_tiles, int kblocks, int sms) {
   const int single = std::max(32, ceil_div(cout, 16) * 16);
   int best_bn = 0;
@@ -902,8 +1070,8 @@ static int choose_block_n(int cout, long long m_tiles, int kblocks, int sms) {
   auto consider = [&](int bn) {
     const long long nt = ceil_div(cout, bn);
     const long long rounds = (m_tiles * nt + sms - 1) / sms;
-    const double mma = 2.0 * bn, fill = (16384.0 + 128.0 * bn) / 48.0;
-    const double tile = (double)kblocks * std::max(mma, fill) + 600.0;
+    // measured per-K-block time of the single-CTA kernel: ~245 + 2.6*bn cycles (908 @256, 575 @128)
+    const double tile = (double)kblocks * (245.0 + 2.6 * bn) + 1000.0;
     const double cost = (double)rounds * tile;
     if (best_bn == 0 || cost < best_cost * 0.97) {  // prefer the wider tile unless clearly beaten
       best_bn = bn;
@@ -916,6 +1084,37 @@ static int choose_block_n(int cout, long long m_tiles, int kblocks, int sms) {
   return best_bn;
 }
 
+#define EQXV_PAIR_ROW(RES)                                                                              \
+  {                                                                                                     \
+    pair_kernel<0, RES>, pair_kernel<1, RES>, pair_kernel<2, RES>, pair_kernel<3, RES>,                 \
+        pair_kernel<4, RES>, pair_kernel<5, RES>, pair_kernel<6, RES>, pair_kernel<7, RES>              \
+  }
+static KernelFn pair_table(int act, int res_mode) {
+  static const KernelFn t[3][kNumActs] = {EQXV_PAIR_ROW(0), EQXV_PAIR_ROW(1), EQXV_PAIR_ROW(2)};
+  return t[res_mode][act];
+}
+
+static bool g_pair_enabled = getenv("EQXV_NO_PAIR") == nullptr;   // A/B switch for profiling
+
+// pair variant: the tile is 256 x bn for two SMs; per SM and K block: 16 KiB of A + bn*64 B of B
+static int choose_block_n_pair(int cout, long long pair_m_tiles, int kblocks, int clusters) {
+  int best_bn = 0;
+  double best_cost = 0;
+  for (int bn = 256; bn >= 64; bn -= 64) {
+    if (bn > 64 && bn >= 2 * cout) continue;
+    const long long nt = ceil_div(cout, bn);
+    const long long rounds = (pair_m_tiles * nt + clusters - 1) / clusters;
+    // measured on B200 (gpurun_out/ab_pair.log): ~190 + 2.2*bn cycles per K block (753 @256, 472 @128):
+    // operand reads + TMA fill share the 128 B/cycle shared-memory port
+    const double cost = (double)rounds * ((double)kblocks * (190.0 + 2.2 * bn) + 1000.0);
+    if (best_bn == 0 || cost < best_cost * 0.97) {
+      best_bn = bn;
+      best_cost = cost;
+    }
+  }
+  return best_bn;
+}
+
 static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -923,7 +1122,15 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   EQXV_CHECK_ARG(!(out_f32 && q.res), "igemm: residual is not supported with fp32 output");
   const long long m_tiles =
       (long long)ceil_div(q.out_w, q.tw) * ceil_div(q.out_h, q.th) * ceil_div(q.out_n, q.tn);
-  const int block_n = choose_block_n(q.cout, m_tiles, q.kh * q.kw * q.kchunks, device_sm_count());
+  const int kblocks = q.kh * q.kw * q.kchunks;
+  // CTA pairs pay off when the K loop (not HBM or the epilogue) dominates: deep K, wide N, enough tiles
+  const bool pair = !out_f32 && kblocks >= 4 && q.cout >= 128 && m_tiles >= 2 && q.dil_h == 1 && g_pair_enabled;
+  int block_n;
+  if (pair) {
+    block_n = choose_block_n_pair(q.cout, (m_tiles + 1) / 2, kblocks, device_sm_count() / 2);
+  } else {
+    block_n = choose_block_n(q.cout, m_tiles, kblocks, device_sm_count());
+  }
   p.block_n = block_n;
   p.acc_stride = ceil_div(block_n, 32) * 32;
   int cols = 32;
@@ -934,7 +1141,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   p.tiles_w = ceil_div(q.out_w, q.tw);
   p.tiles_h = ceil_div(q.out_h, q.th);
   p.tiles_n = ceil_div(q.out_n, q.tn);
-  const long long num_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const long long num_tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;
   EQXV_CHECK_ARG(num_tiles > 0 && num_tiles < (1ll << 30), "igemm: bad tile count %lld", num_tiles);
   p.num_tiles = (int)num_tiles;
   p.kh = q.kh, p.kw = q.kw, p.dil_h = q.dil_h, p.dil_w = q.dil_w;
@@ -948,7 +1155,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   p.bias = q.bias;
 
   // shared memory carve-up
-  const int stage_bytes = kABytes + block_n * 128;
+  const int stage_bytes = kABytes + (pair ? block_n * 64 : block_n * 128);
   const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
   EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "igemm: cout %d too large for the bias staging area", q.cout);
   const int fixed = 2 * kStageBuf + (p.has_res ? 2 * kStageBuf : 0) + bias_bytes + 256;
@@ -970,7 +1177,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   b.rank = 2;
   b.dims[0] = (uint64_t)q.ktot, b.dims[1] = (uint64_t)q.cout;
   b.strides_bytes[0] = (uint64_t)q.ktot * 2;
-  b.box[0] = kBlockK, b.box[1] = (uint32_t)block_n;
+  b.box[0] = kBlockK, b.box[1] = (uint32_t)(pair ? block_n / 2 : block_n);
   b.estride[0] = b.estride[1] = 1;
   b.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
   rc = encode_tmap(&p.tmB, b);
@@ -1001,9 +1208,15 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
     if (rc) return rc;
   }
 
-  const int grid = std::min(p.num_tiles, device_sm_count());
   EQXV_CHECK_ARG(q.act >= 0 && q.act < kNumActs, "igemm: unknown activation %d", q.act);
   const int res_mode = q.res ? (p.res_after_act ? 2 : 1) : 0;
+  if (pair) {
+    const int clusters = std::min(p.num_tiles, device_sm_count() / 2);
+    pair_table(q.act, res_mode)<<<2 * clusters, kThreads, smem_bytes, stream>>>(p);
+    EQXV_CUDA(cudaGetLastError());
+    return EQXV_OK;
+  }
+  const int grid = std::min(p.num_tiles, device_sm_count());
   const KernelFn fn = out_f32 ? kernel_table().f32[q.act] : kernel_table().bf16[res_mode][q.act];
   fn<<<grid, kThreads, smem_bytes, stream>>>(p);
   EQXV_CUDA(cudaGetLastError());
@@ -1031,6 +1244,9 @@ int igemm_init() {
   for (int a = 0; a < 3; ++a)
     for (int r = 0; r < 3; ++r)
       EQXV_CUDA(cudaFuncSetAttribute(halo_table(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  for (int a = 0; a < kNumActs; ++a)
+    for (int r = 0; r < 3; ++r)
+      EQXV_CUDA(cudaFuncSetAttribute(pair_table(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < kNumActs; ++a) {
     for (int r = 0; r < 3; ++r)
       EQXV_CUDA(cudaFuncSetAttribute(kernel_table().bf16[r][a], cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -260,6 +260,108 @@ __host__ __device__ inline uint32_t umma_idesc_bf16_m128_bmn(uint32_t n) {
   return umma_idesc_bf16_m128(n) | (1u << 16);
 }
 
+// ----------------------------------------------------------------------------------------------
+// CTA pair (cta_group::2): two SMs of one TPC execute one 256-row MMA; the leader (cluster rank 0)
+// issues it, both CTAs feed their own shared memory. A shared::cta address with bit 24 cleared
+// names the same offset in the leader CTA's shared memory (shared::cluster window).
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the LEADER CTA's barrier at the same offset (valid from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+// TMA loads whose completion bytes are credited to the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of the pair's MMAs, delivered to the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b16 m;\n"
+      "mov.b16 m, 3;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}\n" ::"r"(bar)
+      : "memory");
+}
+// one 64-deep K block of a 256 x N pair MMA (see umma_bf16_kblock64) + multicast release of the stage
+__device__ __forceinline__ void umma_bf16_kblock64_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                        uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                                        uint32_t accumulate, uint32_t commit_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 a1, b1;\n"
+      ".reg .b16 m;\n"
+      "mov.b16 m, 3;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "setp.eq.b32 p, 0, 0;\n"
+      "add.u32 a1, %1, 2;\n"
+      "add.u32 b1, %2, 2;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "add.u32 a1, %1, 4;\n"
+      "add.u32 b1, %2, 4;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "add.u32 a1, %1, 6;\n"
+      "add.u32 b1, %2, 6;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], m;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(commit_bar)
+      : "memory");
+}
+// kind::f16 instruction descriptor for the 256-row pair MMA
+__host__ __device__ inline uint32_t umma_idesc_bf16_m256(uint32_t n) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 1u << 7;
+  d |= 1u << 10;
+  d |= (n >> 3) << 17;
+  d |= (256u >> 4) << 24;
+  return d;
+}
+
 // Byte offset of 16-byte chunk `j` (0..7) of row `r` inside a 128B-swizzled tile whose base is
 // 1024-byte aligned (the layout TMA writes/reads with CU_TENSOR_MAP_SWIZZLE_128B).
 __device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t j) {
