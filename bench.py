@@ -31,9 +31,22 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_IMG = {"resnet50": 8.178e9, "vit_base": 35.13e9}
-BYTES_PER_IMG = {"resnet50": 56.8e6, "vit_base": 94.4e6}           # layer-wise bf16 traffic
-PER_GPU_BATCH = {"resnet50": 256, "vit_base": 64}
+# algorithmic FLOPs / bytes per image (bf16 activations, every conv/linear reads its
+# input once and writes its output once, norm + activation + residual fused), the roofline that binds,
+# per-GPU batch (BASELINE.json configs) and the bounded CPU sample.
+MODELS = {
+    "resnet50": dict(batch=256, hw=224, flop=8.178e9, bytes=56.8e6, bound="tensor", cpu_batch=16,
+                     config="BASELINE.json configs[1]"),
+    "vit_base": dict(batch=64, hw=224, flop=35.13e9, bytes=94.4e6, bound="tensor", cpu_batch=8,
+                     config="BASELINE.json configs[2]: 512 images over 8 GPUs = 64 per GPU"),
+    "efficientnet_b4": dict(batch=128, hw=224, flop=3.007e9, bytes=70.54e6, bound="hbm", cpu_batch=8,
+                            config="BASELINE.json configs[3]"),
+    "deeplabv3_resnet50": dict(batch=4, hw=512, flop=346.5e9, bytes=0.69e9, bound="tensor", cpu_batch=1,
+                               config="BASELINE.json configs[4]"),
+}
+FLOP_PER_IMG = {k: v["flop"] for k, v in MODELS.items()}
+BYTES_PER_IMG = {k: v["bytes"] for k, v in MODELS.items()}
+PER_GPU_BATCH = {k: v["batch"] for k, v in MODELS.items()}
 
 
 def load_peaks():
@@ -90,21 +103,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def synthetic_state_dict(name: str):
+    from tools import synthetic as syn   # workload generator (not the oracle)
+
+    if name == "vit_base":
+        return syn.vit_state_dict(embed_dim=768, depth=12, heads=12, num_classes=1000, seed=3)
+    if name == "deeplabv3_resnet50":
+        return syn.torchvision_model(name, seed=1, calib_hw=64, aux_loss=True).state_dict()
+    return syn.torchvision_state_dict(name, seed=1)
+
+
 def build_model(name: str):
     """seeded synthetic checkpoint -> .pth -> constructor(torch_weights=...) -> inference mode"""
     import torch
 
     import eqxvision_b200 as eb
-    from oracle import checkpoints as ck
 
-    if name == "resnet50":
-        sd = ck.torchvision_state_dict("resnet50", seed=1)
-    else:
-        sd = ck.vit_state_dict(embed_dim=768, depth=12, heads=12, num_classes=1000, seed=3)
+    sd = synthetic_state_dict(name)
     f = tempfile.NamedTemporaryFile(suffix=".pth", delete=False)
     torch.save(sd, f.name)
-    model = getattr(eb.models, name)(torch_weights=f.name) if name == "resnet50" else \
-        eb.models.vit_base(num_classes=1000, torch_weights=f.name)
+    if name == "vit_base":
+        model = eb.models.vit_base(num_classes=1000, torch_weights=f.name)
+    elif name == "deeplabv3_resnet50":
+        model = eb.models.deeplabv3(intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024,
+                                    torch_weights=f.name)
+    else:
+        model = getattr(eb.models, name)(torch_weights=f.name)
     os.unlink(f.name)
     return eb.tree_inference(model, True), sd
 
@@ -116,12 +140,21 @@ def measure(name, model, batch, steps, warmup, dist, rank):
     import eqxvision_b200 as eb
     from eqxvision_b200 import _engine, _lib, ops
 
-    plan = _engine.get_plan(model, "__call__", batch, (3, 224, 224), (), {"key": eb.random.PRNGKey(0)})
+    hw = MODELS[name]["hw"]
+    in_shape = (3, hw, hw)
+    plan = _engine.get_plan(model, "__call__", batch, in_shape, (), {"key": eb.random.PRNGKey(0)})
     st = _engine.stream_handle()
     g = torch.Generator().manual_seed(100 + rank)
-    host_in = torch.rand((batch, 3, 224, 224), generator=g).pin_memory()
-    out_t, _ = plan.outputs[0]
-    host_out = torch.empty(tuple(out_t.shape), dtype=out_t.dtype).pin_memory()
+    host_in = torch.rand((batch,) + in_shape, generator=g).pin_memory()
+
+    def host_mirrors(pl):   # one pinned host buffer per model output (DeepLabV3 returns (aux, out))
+        pairs = []
+        for o, _ in pl.outputs:
+            assert o.is_contiguous()
+            pairs.append((o, torch.empty(tuple(o.shape), dtype=o.dtype).pin_memory()))
+        return pairs
+
+    outs1 = host_mirrors(plan)
     plan.x_in.copy_(host_in)
     torch.cuda.synchronize()
 
@@ -158,23 +191,21 @@ def measure(name, model, batch, steps, warmup, dist, rank):
     # device, replays the graph and copies the logits back. Two plans (own buffers, own stream) are
     # alternated so that the H2D copy of step i+1 overlaps the kernels of step i (copy engine vs SMs).
     nbytes_in = host_in.numel() * 4
-    nbytes_out = out_t.numel() * out_t.element_size()
-    assert out_t.is_contiguous()
-    plan2 = _engine.build_plan(model, "__call__", batch, (3, 224, 224), (), {"key": eb.random.PRNGKey(0)})
+    nbytes_out = sum(o.numel() * o.element_size() for o, _ in outs1)
+    plan2 = _engine.build_plan(model, "__call__", batch, in_shape, (), {"key": eb.random.PRNGKey(0)})
     st2 = C.c_void_p()
     _lib.call("eqxv_stream_create", C.byref(st2))
     st2 = st2.value
-    out2, _ = plan2.outputs[0]
-    host_out2 = torch.empty(tuple(out2.shape), dtype=out2.dtype).pin_memory()
-    lanes = [(plan, st, out_t, host_out), (plan2, st2, out2, host_out2)]
+    lanes = [(plan, st, outs1), (plan2, st2, host_mirrors(plan2))]
     counter = [0]
 
     def e2e_step():
-        pl, s, o, ho = lanes[counter[0] & 1]
+        pl, s, outs = lanes[counter[0] & 1]
         counter[0] += 1
         _lib.call("eqxv_memcpy_h2d_async", pl.x_in.data_ptr(), host_in.data_ptr(), nbytes_in, s)
         pl.launch(s)
-        _lib.call("eqxv_memcpy_d2h_async", ho.data_ptr(), o.data_ptr(), nbytes_out, s)
+        for o, ho in outs:
+            _lib.call("eqxv_memcpy_d2h_async", ho.data_ptr(), o.data_ptr(), o.numel() * o.element_size(), s)
 
     def timed_two_streams():
         for _ in range(max(warmup, 2)):
@@ -224,15 +255,28 @@ def measure(name, model, batch, steps, warmup, dist, rank):
             "h2d": nbytes_in, "d2h": nbytes_out, "act_bytes": plan.act_bytes}
 
 
+def oracle_forward(name, sd, batch):
+    """the CPU oracle (torch fp32 restatement of the reference) as a zero-argument callable on a seeded
+    `batch`-image sample; the ONLY place bench.py touches oracle/ (cpu_baseline leg + --impl reference)"""
+    from oracle import models as om
+    from tools import synthetic as syn
+
+    hw = MODELS[name]["hw"]
+    x = syn.synthetic_images(batch, h=hw, w=hw, seed=7)
+    if name == "vit_base":
+        return lambda: om.vit(sd, x, heads=12)
+    if name == "deeplabv3_resnet50":
+        return lambda: om.deeplabv3_resnet50(sd, x)
+    if name.startswith("efficientnet"):
+        return lambda: om.efficientnet(sd, x, name)
+    return lambda: om.resnet(sd, x, name)
+
+
 def cpu_port(name, sd, batch, iters):
-    """the CPU oracle (restatement of the reference) on a bounded sample; returns (img/s, cores, sample)"""
+    """bounded CPU sample; returns (img/s, cores, sample)"""
     import torch
 
-    from oracle import checkpoints as ck
-    from oracle import models as om
-
-    x = ck.synthetic_images(batch, seed=7)
-    fn = (lambda: om.resnet(sd, x, "resnet50")) if name == "resnet50" else (lambda: om.vit(sd, x, heads=12))
+    fn = oracle_forward(name, sd, batch)
     with torch.no_grad():
         fn()  # warm-up
         t0 = time.perf_counter()
@@ -249,16 +293,11 @@ def run_reference_arm(args, rank):
         return
     import torch
 
-    from oracle import checkpoints as ck
-
     name = args.model
-    sd = ck.torchvision_state_dict("resnet50", seed=1) if name == "resnet50" else \
-        ck.vit_state_dict(num_classes=1000, seed=3)
-    sample_batch = 16 if name == "resnet50" else 8
-    from oracle import models as om
-
-    x = ck.synthetic_images(sample_batch, seed=7)
-    fn = (lambda: om.resnet(sd, x, "resnet50")) if name == "resnet50" else (lambda: om.vit(sd, x, heads=12))
+    hw = MODELS[name]["hw"]
+    sd = synthetic_state_dict(name)
+    sample_batch = MODELS[name]["cpu_batch"]
+    fn = oracle_forward(name, sd, sample_batch)
     with torch.no_grad():
         for _ in range(max(1, min(args.warmup, 2))):
             fn()
@@ -274,7 +313,7 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": "images/sec", "value": round(v, 2), "unit": "img/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name} inference 3x224x224, batch {PER_GPU_BATCH[name]} per GPU",
+        "config": {"workload": f"{name} inference 3x{hw}x{hw}, batch {PER_GPU_BATCH[name]} per GPU",
                    "global_batch": PER_GPU_BATCH[name] * args.gpus},
         "cpu_baseline": {"value": round(v, 2), "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -289,8 +328,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="resnet50", choices=["resnet50", "vit_base"])
+    ap.add_argument("--model", default="resnet50", choices=sorted(MODELS))
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--all-configs", action="store_true",
+                    help="also measure EfficientNet-B4 (B=128) and DeepLabV3-R50 (4x3x512x512) as secondary lines")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -341,9 +382,40 @@ def main():
     value = total_imgs / ms * 1e3
     e2e_value = total_imgs / e2e_ms * 1e3
 
+    def roofline_of(nm, mm, step_ms):
+        """the model's binding roofline for the dominant kernel family"""
+        nb = PER_GPU_BATCH[nm]
+        if MODELS[nm]["bound"] == "tensor":
+            tf = FLOP_PER_IMG[nm] * nb / mm["igemm_ms"] / 1e9
+            r = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM family (all conv/linear launches of one step: "
+                                              "igemm_kernel, pair_kernel, halo_kernel, stem_kernel)",
+                 "achieved": round(tf, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                 "frac": round(tf / peaks["tflops_sustained"], 4), "traffic": None,
+                 "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
+                 "launches": mm["igemm_launches"], "kernel_ms_per_step": round(mm["igemm_ms"], 4),
+                 "flop_per_image": FLOP_PER_IMG[nm]}
+        else:
+            gbs = BYTES_PER_IMG[nm] * nb / step_ms / 1e6
+            r = {"bound": "hbm", "kernel": "whole step (pointwise 1x1 GEMMs + depthwise stencils + SE; HBM-bound model)",
+                 "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
+                 "peak_source": peaks["source"] + " (copy bandwidth)", "launches": mm["launches"],
+                 "kernel_ms_per_step": round(step_ms, 4), "bytes_per_image": BYTES_PER_IMG[nm]}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per step from the committed ncu pass
+        if os.path.exists(tp):
+            t = json.load(open(tp)).get(nm)
+            if t:
+                r["traffic"] = t["dram_bytes_per_step"]
+                r["traffic_source"] = t["source"]
+        return r
+
     secondary = {}
+    others = []
     if not args.no_secondary:
-        other = "vit_base" if name == "resnet50" else "resnet50"
+        others.append("vit_base" if name == "resnet50" else "resnet50")
+    if args.all_configs:
+        others += [k for k in ("efficientnet_b4", "deeplabv3_resnet50") if k != name and k not in others]
+    for other in others:
         om_model, _ = build_model(other)
         ob = PER_GPU_BATCH[other]
         sm = measure(other, om_model, ob, max(10, args.steps // 2), args.warmup, dist, rank)
@@ -351,12 +423,14 @@ def main():
         s_e2e = max_over_ranks(sm["e2e_ms"])
         secondary[other] = {
             "value": round(ob * world / s_ms * 1e3, 1), "unit": "img/s", "ms_per_step": round(s_ms, 4),
-            "per_gpu_batch": ob, "e2e": round(ob * world / s_e2e * 1e3, 1),
-            "tflops_per_gpu": round(FLOP_PER_IMG[other] * ob / s_ms / 1e9, 1),
-            "frac_of_sustained_peak": round(FLOP_PER_IMG[other] * ob / s_ms / 1e9 / peaks["tflops_sustained"], 4),
-            "igemm_tflops": round(FLOP_PER_IMG[other] * ob / sm["igemm_ms"] / 1e9, 1),
+            "per_gpu_batch": ob, "e2e": round(ob * world / s_e2e * 1e3, 1), "config": MODELS[other]["config"],
+            "step_tflops_per_gpu": round(FLOP_PER_IMG[other] * ob / s_ms / 1e9, 1),
+            "step_hbm_gbs_per_gpu": round(BYTES_PER_IMG[other] * ob / s_ms / 1e6, 1),
+            "roofline": roofline_of(other, sm, s_ms),
             "by_kernel_ms": sm["by_kernel_ms"], "launches": sm["launches"],
         }
+        del om_model
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if dist is not None:
@@ -364,13 +438,13 @@ def main():
             dist.destroy_process_group()
         return
 
-    igemm_tflops = FLOP_PER_IMG[name] * batch / m["igemm_ms"] / 1e9
+    hw = MODELS[name]["hw"]
     line = {
         "metric": "images/sec", "value": round(value, 1), "unit": "img/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": f"{name} inference 3x224x224, batch {batch} per GPU (BASELINE.json configs[1])",
+            "workload": f"{name} inference 3x{hw}x{hw}, batch {batch} per GPU ({MODELS[name]['config']})",
             "global_batch": total_imgs, "parallelism": f"dp{world} (batch sharded, weights replicated, no collective)",
             "l2": f"per-step working set {m['act_bytes'] / 2**30:.1f} GiB of activations + "
                   f"{m['h2d'] / 2**20:.0f} MiB input >> 126 MB L2 (no explicit flush needed)",
@@ -380,27 +454,18 @@ def main():
                 "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
         "gpu_launches": m["launches"] * args.steps,
         "launches_per_step": m["launches"],
-        "roofline": {
-            "bound": "tensor", "kernel": "eqxv::igemm_kernel (all conv/linear launches of one step)",
-            "achieved": round(igemm_tflops, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-            "frac": round(igemm_tflops / peaks["tflops_sustained"], 4), "traffic": None,
-            "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
-            "launches": m["igemm_launches"], "kernel_ms_per_step": round(m["igemm_ms"], 4),
-            "flop_per_image": FLOP_PER_IMG[name],
-        },
-        "roofline_hbm": {
-            "bound": "hbm", "achieved": round(BYTES_PER_IMG[name] * batch / ms / 1e6, 1), "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": round(BYTES_PER_IMG[name] * batch / ms / 1e6 / peaks["hbm_gbs"], 4),
-            "note": "whole step, layer-wise algorithmic bytes (SURVEY.md §8(d)): the practical ceiling of "
-                    "unfused ResNet-50 in bf16",
-        },
+        "roofline": roofline_of(name, m, ms),
         "step_tflops": round(FLOP_PER_IMG[name] * batch / ms / 1e9, 1),
+        "step_hbm": {"achieved": round(BYTES_PER_IMG[name] * batch / ms / 1e6, 1), "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": round(BYTES_PER_IMG[name] * batch / ms / 1e6 / peaks["hbm_gbs"], 4),
+                     "note": "whole step against the layer-wise algorithmic bytes (SURVEY.md §8(d)): the practical "
+                             "ceiling of a layer-by-layer bf16 forward"},
         "by_kernel_ms": m["by_kernel_ms"],
         "clocks": clocks,
         "secondary": secondary,
     }
     if not args.no_cpu_baseline:
-        v, cores, sample = cpu_port(name, sd, 16 if name == "resnet50" else 8, 3)
+        v, cores, sample = cpu_port(name, sd, MODELS[name]["cpu_batch"], 3)
         line["cpu_baseline"] = {"value": round(v, 2), "unit": "img/s", "cores": cores, "kind": "port",
                                 "sample": sample}
     print(json.dumps(line), flush=True)

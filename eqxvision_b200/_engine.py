@@ -157,7 +157,7 @@ class Plan:
         if e.groups != 1:
             if e.groups == c_in and cin_g == 1 and cout == c_in:
                 return self._emit_depthwise(sym, e, w, b, act, res, dst)
-            raise NotImplementedError("grouped convolution (ResNeXt/RegNet) is not on the hot path yet")
+            return self._emit_grouped(sym, e, w, b, act, res_after, res, dst, out_f32)
         if sh != sw or ph != pw or dh != dw:
             raise NotImplementedError("anisotropic stride/padding/dilation is not supported")
 
@@ -191,6 +191,27 @@ class Plan:
                   kw=kw, stride=sh, pad=ph, dil=dh, act=act,
                   residual=None if res is None else res.map(ho, wo), res_after_act=res_after,
                   out=out.map(ho, wo, cout if out_f32 else None), out_f32=out_f32)
+        return out
+
+    def _emit_grouped(self, sym, e, w, b, act, res_after, res, dst, out_f32):
+        """ResNeXt conv2 (resnet.py:83 with groups=32): block-diagonal implicit GEMM over 64-channel blocks
+        (EQXV_FLAG_GROUPED_BLOCK64): C/64 independent dense 64->64 convolutions in one launch."""
+        cout, cin_g, kh, kw = e.weight.shape
+        c_in, h, wd = e.x.shape
+        (sh, sw), (ph, pw), (dh, dw) = e.stride, e.padding, e.dilation
+        if sh != sw or ph != pw or dh != dw or out_f32:
+            raise NotImplementedError("anisotropic / fp32-output grouped convolution")
+        if cout != c_in or c_in % 64 != 0 or 64 % cin_g != 0:
+            raise NotImplementedError(f"grouped convolution {c_in}->{cout} with groups={e.groups} "
+                                      "(only cin == cout, cin % 64 == 0, 64 % (cin/groups) == 0 is built)")
+        xb = self.emit(e.x)
+        ho, wo = sym.shape[1:]
+        out = dst if dst is not None else self.alloc(self.n * ho * wo, cout, (ho, wo))
+        wp = self.const(_pack.pack_grouped_weight(w, e.groups))
+        bias_d = self.const(b) if b is not None else None
+        self.step(ops.conv2d, x=xb.map(h, wd, c_in), wgt=wp, bias=bias_d, cin=c_in, cout=cout, kh=kh, kw=kw,
+                  stride=sh, pad=ph, dil=dh, act=act, residual=None if res is None else res.map(ho, wo),
+                  res_after_act=res_after, out=out.map(ho, wo), grouped_block64=True)
         return out
 
     def _emit_depthwise(self, sym, e, w, b, act, res, dst):
@@ -355,7 +376,7 @@ class Plan:
         return out
 
     def _emit_AttentionProbs(self, sym, e):
-        raise NotImplementedError("returning the attention matrix (vit.py:151-152) is not built yet")
+        raise EqxvError("the attention matrix (vit.py:151-152) can only be a model output")
 
     def _emit_ClsPos(self, sym, e: T.ClsPos):
         xb = self.emit(e.x)
@@ -463,6 +484,20 @@ class Plan:
             c, hs, ws = sym.expr.x.shape
             out = torch.empty((n, c, sym.expr.h, sym.expr.w), dtype=torch.float32, device=self.device)
             self.step(ops.resize_bilinear_to_nchw, x=src.map(hs, ws), c=c, oh=sym.expr.h, ow=sym.expr.w, out=out)
+            self.outputs.append((out, (n,) + sym.shape))
+            return
+        if sym.kind == "attn" and isinstance(sym.expr, T.AttentionProbs):
+            # _VitBlock(return_attention=True) / get_last_self_attention (vit.py:151-152, 275-292):
+            # fp32 probabilities (1, heads, T, T) per sample, written directly by the kernel
+            e = sym.expr
+            qkv = self.emit(e.qkv)
+            _, heads, t, _ = sym.shape
+            c = qkv.pitch // 3
+            if qkv.pitch != 3 * heads * (c // heads):
+                raise NotImplementedError("attention expects a dense qkv matrix")
+            out = torch.empty((n, 1, heads, t, t), dtype=torch.float32, device=self.device)
+            self.step(ops.attention_probs, qkv=qkv.rows(3 * c), images=n, tokens=t, heads=heads,
+                      head_dim=c // heads, scale=float(e.scale), out=out)
             self.outputs.append((out, (n,) + sym.shape))
             return
         buf = self.emit(sym)

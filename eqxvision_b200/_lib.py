@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libeqxv_b200.so")
 ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU_TANH, ACT_HARDSWISH, ACT_SIGMOID, ACT_HARDSIGMOID, ACT_RELU6 = range(8)
 FLAG_OUT_F32 = 1
 FLAG_RES_AFTER_ACT = 2
+FLAG_GROUPED_BLOCK64 = 4
 
 ACT_BY_NAME = {
     None: ACT_NONE, "none": ACT_NONE, "identity": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU,

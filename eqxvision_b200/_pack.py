@@ -42,6 +42,23 @@ def pack_conv_weight(w_oihw: torch.Tensor, cin_pad: int) -> torch.Tensor:
     return w.reshape(o, kh * kw * cin_pad).to(torch.bfloat16).contiguous()
 
 
+def pack_grouped_weight(w: torch.Tensor, groups: int) -> torch.Tensor:
+    """Grouped filter [O, I/G, kh, kw] (equinox.nn.Conv2d(groups=G), resnet.py:19-23) -> block-diagonal
+    [O, kh*kw*64] bf16: output channel o lives in the 64-channel block b = o // 64 and its K axis spans the
+    input channels [64b, 64b+64) of every tap; only the channels of o's own group are non-zero.
+    Requires I == O (per group), O % 64 == 0 and 64 % (I/G) == 0 (EQXV_FLAG_GROUPED_BLOCK64)."""
+    o, ig, kh, kw = w.shape
+    og = o // groups
+    assert og == ig and o % 64 == 0 and 64 % ig == 0, "unsupported group geometry"
+    out = torch.zeros(o, kh, kw, 64, dtype=torch.float32)
+    oc = torch.arange(o)
+    first = (oc // og) * ig % 64          # first input channel of o's group inside its 64-block
+    wt = w.permute(0, 2, 3, 1).float()    # O, kh, kw, I/G
+    for j in range(ig):
+        out[oc, :, :, first + j] = wt[:, :, :, j]
+    return out.reshape(o, kh * kw * 64).to(torch.bfloat16).contiguous()
+
+
 def pack_stem_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     """[O, I<=8, kh<=8, kw<=8] -> [O, kh(r), 8(s), 8(c)] bf16 with zero taps/channels
     (see eqxv_conv_stem_bf16)"""

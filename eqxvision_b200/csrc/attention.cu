@@ -53,6 +53,8 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
 __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                         __nv_bfloat16* __restrict__ out, int tokens,
                                                         int heads, float scale_log2) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   __shared__ __align__(16) __nv_bfloat16 Qs[kQT * kPitch];
   __shared__ __align__(16) __nv_bfloat16 Ks[kKB * kPitch];
   __shared__ __align__(16) __nv_bfloat16 Vs[kKB * kPitch];
@@ -275,8 +277,10 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  griddep_wait();     // PDL: everything above overlapped the previous kernel's tail
   tc_fence_before();
   __syncthreads();
+  griddep_launch();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
   const int C = p.heads * 64;
@@ -492,6 +496,83 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_tc_kernel(const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Attention probabilities as an OUTPUT (vit.py:70 returned through _VitBlock(return_attention=True),
+// vit.py:151-152, VisionTransformer.get_last_self_attention vit.py:275-292): fp32
+// softmax(q k^T * scale) [images, heads, tokens, tokens]. Runs once per call on the last block only
+// and is bound by its own fp32 store (tokens^2 * 4 B per head); CUDA-core dot products from smem.
+// One CTA per (32-query tile, head, image), 256 threads: thread j owns key j (+256, ...), keeps that
+// key's 64 dims in registers and sweeps the 32 query rows (broadcast smem reads); then one warp per
+// row normalises and streams the row out.
+constexpr int kPrQ = 32;
+__global__ void __launch_bounds__(256) attention_probs_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                              float* __restrict__ probs, int tokens, int heads,
+                                                              float scale_log2) {
+  griddep_wait();
+  griddep_launch();
+  extern __shared__ __align__(16) uint8_t pr_smem[];
+  const int tpad = (tokens + 3) & ~3;
+  float* qs = reinterpret_cast<float*>(pr_smem);             // [32][64] fp32
+  float* sc = qs + kPrQ * kHd;                               // [32][tpad] scores
+  const int q0 = blockIdx.x * kPrQ, head = blockIdx.y, img = blockIdx.z;
+  const long long ld = 3ll * heads * kHd;
+  const __nv_bfloat16* base = qkv + (long long)img * tokens * ld + head * kHd;
+  const __nv_bfloat16* kptr = base + (long long)heads * kHd;
+  const int nq = min(kPrQ, tokens - q0);
+  for (int i = threadIdx.x; i < kPrQ * kHd; i += 256) {
+    const int r = i >> 6, d = i & 63;
+    qs[i] = r < nq ? __bfloat162float(base[(long long)(q0 + r) * ld + d]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < tokens; j += 256) {
+    float kf[kHd];
+    const uint4* kr = reinterpret_cast<const uint4*>(kptr + (long long)j * ld);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const uint4 u = __ldg(kr + v);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        kf[v * 8 + 2 * e] = __uint_as_float(w[e] << 16);
+        kf[v * 8 + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+      }
+    }
+    for (int r = 0; r < nq; ++r) {
+      const float4* q4 = reinterpret_cast<const float4*>(qs + r * kHd);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const float4 q = q4[d];
+        a0 = fmaf(q.x, kf[4 * d], a0);
+        a1 = fmaf(q.y, kf[4 * d + 1], a1);
+        a2 = fmaf(q.z, kf[4 * d + 2], a2);
+        a3 = fmaf(q.w, kf[4 * d + 3], a3);
+      }
+      sc[r * tpad + j] = (a0 + a1) + (a2 + a3);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < nq; r += 8) {
+    float* row = sc + r * tpad;
+    float mx = -INFINITY;
+    for (int j = lane; j < tokens; j += 32) mx = fmaxf(mx, row[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < tokens; j += 32) {
+      const float e = exp2f((row[j] - mx) * scale_log2);   // scale applied after the product (vit.py:69)
+      row[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    float* dst = probs + (((long long)img * heads + head) * tokens + (q0 + r)) * tokens;
+    for (int j = lane; j < tokens; j += 32) dst[j] = row[j] * inv;
+  }
+}
+
 static long long* g_attn_ts = nullptr;   // set by eqxv_debug_attention_timeline
 
 static int launch_attention_tc(const void* qkv, void* out, int images, int tokens, int heads, float scale,
@@ -522,13 +603,14 @@ static int launch_attention_tc(const void* qkv, void* out, int images, int token
   // that are never stored.
   const int smem = 2 * 3 * p.op_bytes + 65536 + 2048 + 128 + 1024;
   const int grid = std::min(p.pairs, device_sm_count());
-  attention_tc_kernel<13><<<grid, kAtThreads, smem, stream>>>(p);
+  EQXV_CUDA(launch_kernel(attention_tc_kernel<13>, dim3(grid), dim3(kAtThreads), (size_t)(smem), stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
 
 int attention_init() {
   EQXV_CUDA(cudaFuncSetAttribute(attention_tc_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  EQXV_CUDA(cudaFuncSetAttribute(attention_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return EQXV_OK;
 }
 
@@ -539,22 +621,29 @@ using namespace eqxv;
 extern "C" int eqxv_attention_fwd_bf16(const void* qkv, void* out, float* attn_out, int32_t images,
                                        int32_t tokens, int32_t heads, int32_t head_dim, float scale,
                                        void* stream) {
-  EQXV_CHECK_ARG(qkv && out && images > 0 && tokens > 0 && heads > 0, "attention: bad arguments");
+  EQXV_CHECK_ARG(qkv && (out || attn_out) && images > 0 && tokens > 0 && heads > 0, "attention: bad arguments");
   if (head_dim != kHd) {
     set_error("attention: head_dim %d unsupported (only 64)", head_dim);
     return EQXV_ERR_UNSUPPORTED;
   }
   if (attn_out != nullptr) {
-    set_error("attention: returning the probability matrix is not implemented yet");
-    return EQXV_ERR_UNSUPPORTED;
+    const int tpad = (tokens + 3) & ~3;
+    const size_t smem = (size_t)(kPrQ * kHd + kPrQ * tpad) * sizeof(float);
+    EQXV_CHECK_ARG(smem <= 200 * 1024 && heads <= 65535 && images <= 65535 && ((uintptr_t)qkv & 15) == 0,
+                   "attention: probability output supports up to ~1500 tokens");
+    EQXV_CUDA(launch_kernel(attention_probs_kernel, dim3((unsigned)((tokens + kPrQ - 1) / kPrQ), (unsigned)heads,
+                                                         (unsigned)images),
+                            dim3(256), smem, (cudaStream_t)stream, (const __nv_bfloat16*)qkv, attn_out, tokens,
+                            heads, scale * 1.4426950408889634f));
+    if (out == nullptr) return EQXV_OK;   // probabilities only (return_attention=True discards the values)
   }
   // tcgen05 path: the double-buffered Q/K/V tiles + P fit in shared memory up to 208 keys (ViT @224: 197)
   if (tokens <= 208 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0)
     return launch_attention_tc(qkv, out, images, tokens, heads, scale, (cudaStream_t)stream);
   EQXV_CHECK_ARG(heads <= 65535 && images <= 65535, "attention: grid too large");
   dim3 grid((unsigned)((tokens + kQT - 1) / kQT), (unsigned)heads, (unsigned)images);
-  attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, tokens, heads, scale * 1.4426950408889634f);
+  EQXV_CUDA(launch_kernel(attention_kernel, dim3(grid), dim3(128), (size_t)(0), (cudaStream_t)stream, 
+      (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, tokens, heads, scale * 1.4426950408889634f));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }

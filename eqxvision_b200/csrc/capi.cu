@@ -1,5 +1,6 @@
 // Library context, error reporting, tensor-map encoding and stream/graph/event plumbing.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -29,6 +30,11 @@ static int g_sm_count = 0;
 static int g_device = -1;
 
 int device_sm_count() { return g_sm_count; }
+
+bool pdl_enabled() {
+  static const bool on = getenv("EQXV_NO_PDL") == nullptr;
+  return on;
+}
 
 int encode_tmap(CUtensorMap* out, const TmapSpec& s) {
   if (!g_encode) {

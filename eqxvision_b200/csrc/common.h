@@ -42,6 +42,26 @@ int encode_tmap(CUtensorMap* out, const TmapSpec& s);
 
 int device_sm_count();
 
+// Kernel launch with the programmatic-dependent-launch attribute (see ptx.cuh: griddep_wait). Works
+// under stream capture (the edge becomes a programmatic graph dependency). EQXV_NO_PDL=1 switches the
+// attribute off (A/B measurements); the griddepcontrol instructions are no-ops then.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace eqxv

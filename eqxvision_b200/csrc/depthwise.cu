@@ -64,6 +64,8 @@ __global__ void dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* 
                               const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int n, int h,
                               int w, int c, int pad, int dil, int ho, int wo, int xp, int yp, int wp,
                               int act) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int groups = c / 8;
   const long long total = (long long)n * ho * wo * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -129,6 +131,8 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_strip_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
     __nv_bfloat16* __restrict__ y, int n, int h, int w, int c, int pad, int ho, int wo, int xp, int yp, int wp,
     int act) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   constexpr int NC = (TW - 1) * S + K;
   const int groups = c / 8;
   const int strips = (wo + TW - 1) / TW;
@@ -212,6 +216,8 @@ __global__ void eltwise_kernel(const __nv_bfloat16* __restrict__ x, const float*
                                const __nv_bfloat16* __restrict__ gate, __nv_bfloat16* __restrict__ y,
                                long long rows, int c, int xp, int op, int gp, int yp, int rows_per_image,
                                int act) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int groups = c / 8;
   const long long total = rows * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -269,10 +275,11 @@ extern "C" int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
   __nv_bfloat16* yo = (__nv_bfloat16*)y;
-#define EQXV_DWS(K, S, TW)                                                                             \
-  dwconv_strip_kernel<K, S, TW><<<grid_for((long long)n * ho * ((wo + TW - 1) / TW) * (c / 8)), kDwThreads, 0, \
-                                    st>>>(xi, wgt, bias, yo, n, h, w, c, pad, ho, wo, x_pitch, y_pitch,      \
-                                          w_pitch, act)
+#define EQXV_DWS(K, S, TW)                                                                          \
+  EQXV_CUDA(launch_kernel(dwconv_strip_kernel<K, S, TW>,                                            \
+                          dim3(grid_for((long long)n * ho * ((wo + TW - 1) / TW) * (c / 8))),       \
+                          dim3(kDwThreads), (size_t)0, st, xi, wgt, bias, yo, n, h, w, c, pad, ho,   \
+                          wo, x_pitch, y_pitch, w_pitch, act))
   if (dil == 1 && wo >= 4) {
     bool done = true;
     if (k == 3 && stride == 1) {
@@ -292,9 +299,9 @@ extern "C" int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const fl
     }
   }
 #undef EQXV_DWS
-#define EQXV_DW(K, S)                                                                                  \
-  dwconv_kernel<K, S><<<grid, kDwThreads, 0, st>>>(xi, wgt, bias, yo, n, h, w, c, pad, dil, ho, wo,    \
-                                                   x_pitch, y_pitch, w_pitch, act)
+#define EQXV_DW(K, S)                                                                               \
+  EQXV_CUDA(launch_kernel(dwconv_kernel<K, S>, dim3(grid), dim3(kDwThreads), (size_t)0, st, xi, wgt, \
+                          bias, yo, n, h, w, c, pad, dil, ho, wo, x_pitch, y_pitch, w_pitch, act))
   if (k == 3 && stride == 1) {
     EQXV_DW(3, 1);
   } else if (k == 3 && stride == 2) {
@@ -325,10 +332,10 @@ extern "C" int eqxv_eltwise_bf16(const void* x, const float* scale, const float*
   if (other) EQXV_CHECK_ARG(other_pitch % 8 == 0 && other_pitch >= c, "eltwise: bad other pitch");
   if (gate) EQXV_CHECK_ARG(gate_pitch % 8 == 0 && gate_pitch >= c && rows_per_image > 0, "eltwise: bad gate");
   const long long total = rows * (c / 8);
-  eltwise_kernel<<<grid_for(total), kDwThreads, 0, (cudaStream_t)stream>>>(
+  EQXV_CUDA(launch_kernel(eltwise_kernel, dim3(grid_for(total)), dim3(kDwThreads), (size_t)(0), (cudaStream_t)stream, 
       (const __nv_bfloat16*)x, scale, shift, (const __nv_bfloat16*)other, (const __nv_bfloat16*)gate,
       (__nv_bfloat16*)y, rows, c, x_pitch, other_pitch, gate_pitch, y_pitch, rows_per_image > 0 ? rows_per_image : 1,
-      act);
+      act));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }

@@ -44,6 +44,9 @@ struct alignas(64) IgemmParams {
   int cout;
   int act, res_after_act, has_res;
   int stages;
+  int b_resident;   // halo kernel: the whole packed filter stays in the B ring (loaded once per CTA)
+  int grouped;      // 1: block-diagonal grouped conv, the A channel offset follows the n-tile (block_n == 64)
+  int res_bufs, res_shift;   // residual prefetch ring per epilogue warp (2 or 4 slabs), log2
   // shared-memory carve-up (byte offsets from the 1024-aligned base)
   int off_out, off_res, off_bias, off_bars;
   // first-layer (halo) kernel only
@@ -184,7 +187,6 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
   const uint32_t bars = base + p.off_bars;
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
   {
     // ============================== epilogue (warps 2..5) ==============================
     // Every warp owns the 32 accumulator rows of its TMEM lane quadrant as an independent slab:
@@ -205,14 +207,18 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
     const uint32_t res_u32 = base + p.off_res + quad * kSlab;
     uint8_t* out_g = gbase + p.off_out + quad * kSlab;
     const uint8_t* res_g = gbase + p.off_res + quad * kSlab;
-    auto rbar = [&](uint32_t b) { return rfull_bar(quad * 2 + b); };
+    // residual ring: R slabs per warp, prefetched R chunks ahead (R = 4 on the HBM-bound layers: with 2
+    // the residual stream had only 8 KiB per warp in flight and the c3 convolutions of ResNet sat at
+    // ~78 % of the HBM roofline, profiles/r01_layer_roofline_v3.txt)
+    const uint32_t R = (uint32_t)p.res_bufs, rshift = (uint32_t)p.res_shift;
+    auto rbar = [&](uint32_t b) { return bars + 8u * (48u + (uint32_t)quad * 4u + b); };
 
     auto issue_res = [&](uint32_t gg) {  // called by ONE lane
       const int ti = gg / cpt, c = gg - ti * cpt;
       const long long tile = (long long)t_first + (long long)ti * t_stride;
       if (tile >= p.num_tiles) return;
       const TileCoord t = decode_tile<kPair>(p, (int)tile);
-      const uint32_t b = gg & 1u;
+      const uint32_t b = gg & (R - 1u);
       mbar_expect_tx(rbar(b), kSlab);
       tma_load_4d(res_u32 + b * kStageBuf, &p.tmR, rbar(b), t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
                   t.n0 + n_off);
@@ -220,8 +226,7 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
 
     uint32_t g = 0;
     if (has_res && lane == 0) {
-      issue_res(0);
-      issue_res(1);
+      for (uint32_t i = 0; i < R; ++i) issue_res(i);
     }
     __syncwarp();
     int acc = 0;
@@ -234,7 +239,8 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
 
       for (int c = 0; c < cpt; ++c, ++g) {
         const uint32_t buf = g & 1u;
-        const uint32_t rphase = (g >> 1) & 1u;
+        const uint32_t rb = g & (R - 1u);
+        const uint32_t rphase = (g >> rshift) & 1u;
         const int ncols = min(CH, p.block_n - c * CH);
         float v[CH];
 #pragma unroll
@@ -260,8 +266,8 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
         uint8_t* out_row = out_g + buf * kStageBuf;
         if constexpr (!kOutF32) {
           uint4 packed[8];
-          if (has_res) mbar_wait(rbar(buf), rphase);
-          const uint8_t* res_row = res_g + buf * kStageBuf;
+          if (has_res) mbar_wait(rbar(rb), rphase);
+          const uint8_t* res_row = res_g + rb * kStageBuf;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             uint4 rv = make_uint4(0u, 0u, 0u, 0u);
@@ -289,7 +295,7 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
           tma_store_4d(&p.tmC, out_u32 + buf * kStageBuf, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
                        t.n0 + n_off);
           tma_store_commit();
-          if (has_res) issue_res(g + 2);
+          if (has_res) issue_res(g + R);
         }
         __syncwarp();
       }
@@ -321,7 +327,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };  // 8: (epilogue warp, buffer)
   const uint32_t tmem_slot = bars + 8u * (2 * S + 12);
   volatile uint32_t* tmem_slot_g =
       reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 12));
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 128);
     }
-    for (int b = 0; b < 8; ++b) mbar_init(rfull_bar(b), 1);
+    for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (48 + b), 1);   // residual ring (epilogue_warps)
     mbar_fence_init();
   }
   // folded-BN shift / bias for every output column, once per CTA (zero beyond cout)
@@ -353,8 +358,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
+  griddep_wait();     // PDL: everything above overlapped the previous kernel's tail
   tc_fence_before();
   __syncthreads();
+  griddep_launch();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
 
@@ -381,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             for (int c = 0; c < kchunks; ++c, kb += kBlockK) {
               mbar_wait(eb, phase ^ 1u);
               mbar_expect_tx(fb, stage_bytes);
-              tma_load_4d(dst, &p.tmA, fb, c * kBlockK, wc, hc, t.n0);
+              tma_load_4d(dst, &p.tmA, fb, c * kBlockK + (p.grouped ? t.ncol0 : 0), wc, hc, t.n0);
               tma_load_2d(dst + kABytes, &p.tmB, fb, kb, t.ncol0);
               dst += stage_bytes, fb += 8, eb += 8;
               if (dst == dst_end) {
@@ -495,7 +502,6 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 12);
   volatile uint32_t* tmem_slot_g =
       reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * (2 * S + 12));
@@ -513,7 +519,7 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 256);  // leader: 4 epilogue warps of each CTA
     }
-    for (int b = 0; b < 8; ++b) mbar_init(rfull_bar(b), 1);
+    for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (48 + b), 1);   // residual ring (epilogue_warps)
     mbar_fence_init();
   }
   {
@@ -526,8 +532,10 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
     tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish_pair();
   }
+  griddep_wait();     // PDL: everything above overlapped the previous kernel's tail
   tc_fence_before();
   __syncthreads();
+  griddep_launch();
   cluster_sync_all();   // the peer's barriers are initialised before anything is signalled remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
@@ -749,8 +757,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
+  griddep_wait();     // PDL: everything above overlapped the previous kernel's tail
   tc_fence_before();
   __syncthreads();
+  griddep_launch();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
   const uint32_t b_smem = base + p.h_off_b;
@@ -854,7 +864,6 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto rfull_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 12);
   auto afull_bar = [&](int s) { return bars + 8u * (2 * S + 14 + s); };
   auto aempty_bar = [&](int s) { return bars + 8u * (2 * S + 14 + SA + s); };
@@ -878,7 +887,7 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 128);
     }
-    for (int b = 0; b < 8; ++b) mbar_init(rfull_bar(b), 1);
+    for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (48 + b), 1);   // residual ring (epilogue_warps)
     mbar_fence_init();
   }
   {
@@ -891,8 +900,10 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
+  griddep_wait();     // PDL: everything above overlapped the previous kernel's tail
   tc_fence_before();
   __syncthreads();
+  griddep_launch();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
   const uint32_t a_smem = base + p.h_off_b;          // A ring follows the B ring
@@ -921,9 +932,11 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
           }
           int kb = c * kBlockK;
           for (int tap = 0; tap < taps; ++tap, kb += p.cin_pack) {
-            mbar_wait(eb, pb ^ 1u);
-            mbar_expect_tx(fb, b_slab);
-            tma_load_2d(bdst, &p.tmB, fb, kb, t.ncol0);
+            if (!p.b_resident || tile == (int)blockIdx.x) {   // resident filter: one pass over the ring, ever
+              mbar_wait(eb, pb ^ 1u);
+              mbar_expect_tx(fb, b_slab);
+              tma_load_2d(bdst, &p.tmB, fb, kb, t.ncol0);
+            }
             bdst += b_slab, fb += 8, eb += 8;
             if (bdst == bdst_end) {
               bdst = base, fb = fb0, eb = eb0;
@@ -963,7 +976,7 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
           for (int r = 0; r < kh; ++r, a_row += row_step) {
             uint32_t a_lo = a_row;
             for (int s2 = 0; s2 < kw; ++s2, a_lo += col_step) {
-              mbar_wait(fb, pb);
+              mbar_wait(fb, p.b_resident ? 0u : pb);   // resident slabs: phase 0 completed once and for all
               tc_fence_after();
               umma_bf16_kblock64(d_tmem, a_lo, b_lo, a_hi, b_hi, idesc, accumulate, eb);
               accumulate = 1;
@@ -1037,6 +1050,7 @@ struct IgemmProblem {
   int in_h, in_w;
   int kchunks, cin_pack;
   int act, flags;
+  int grouped;
 };
 
 static void choose_tile(int n, int ho, int wo, int& tw, int& th, int& tn) {
@@ -1124,13 +1138,16 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
       (long long)ceil_div(q.out_w, q.tw) * ceil_div(q.out_h, q.th) * ceil_div(q.out_n, q.tn);
   const int kblocks = q.kh * q.kw * q.kchunks;
   // CTA pairs pay off when the K loop (not HBM or the epilogue) dominates: deep K, wide N, enough tiles
-  const bool pair = !out_f32 && kblocks >= 4 && q.cout >= 128 && m_tiles >= 2 && q.dil_h == 1 && g_pair_enabled;
+  const bool pair = !out_f32 && kblocks >= 4 && q.cout >= 128 && m_tiles >= 2 && q.dil_h == 1 && g_pair_enabled &&
+                    !q.grouped;
   int block_n;
   if (pair) {
     block_n = choose_block_n_pair(q.cout, (m_tiles + 1) / 2, kblocks, device_sm_count() / 2);
   } else {
     block_n = choose_block_n(q.cout, m_tiles, kblocks, device_sm_count());
   }
+  if (q.grouped) block_n = 64;   // one n-tile = one 64-channel block of the block-diagonal filter
+  p.grouped = q.grouped;
   p.block_n = block_n;
   p.acc_stride = ceil_div(block_n, 32) * 32;
   int cols = 32;
@@ -1158,16 +1175,21 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   const int stage_bytes = kABytes + (pair ? block_n * 64 : block_n * 128);
   const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
   EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "igemm: cout %d too large for the bias staging area", q.cout);
-  const int fixed = 2 * kStageBuf + (p.has_res ? 2 * kStageBuf : 0) + bias_bytes + 256;
+  // residual ring depth: 4 slabs per warp on the shallow-K (HBM-bound) layers, 2 where the smem is
+  // better spent on operand stages
+  static const int forced_rb = getenv("EQXV_RES_BUFS") ? atoi(getenv("EQXV_RES_BUFS")) : 0;
+  p.res_bufs = (forced_rb == 2 || forced_rb == 4) ? forced_rb : (kblocks <= 4 ? 4 : 2);
+  p.res_shift = p.res_bufs == 4 ? 2 : 1;
+  const int fixed = 2 * kStageBuf + (p.has_res ? p.res_bufs * kStageBuf : 0) + bias_bytes + 512;
   int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
   stages = std::min(stages, 8);
   EQXV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for block_n=%d", block_n);
   p.stages = stages;
   p.off_out = stages * stage_bytes;
   p.off_res = p.off_out + 2 * kStageBuf;
-  p.off_bias = p.off_res + (p.has_res ? 2 * kStageBuf : 0);
+  p.off_bias = p.off_res + (p.has_res ? p.res_bufs * kStageBuf : 0);
   p.off_bars = p.off_bias + bias_bytes;
-  const int smem_bytes = p.off_bars + 256 + 1024;
+  const int smem_bytes = p.off_bars + 512 + 1024;
 
   int rc = encode_tmap(&p.tmA, q.a);
   if (rc) return rc;
@@ -1212,13 +1234,13 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   const int res_mode = q.res ? (p.res_after_act ? 2 : 1) : 0;
   if (pair) {
     const int clusters = std::min(p.num_tiles, device_sm_count() / 2);
-    pair_table(q.act, res_mode)<<<2 * clusters, kThreads, smem_bytes, stream>>>(p);
+    EQXV_CUDA(launch_kernel(pair_table(q.act, res_mode), dim3(2 * clusters), dim3(kThreads), (size_t)(smem_bytes), stream, p));
     EQXV_CUDA(cudaGetLastError());
     return EQXV_OK;
   }
   const int grid = std::min(p.num_tiles, device_sm_count());
   const KernelFn fn = out_f32 ? kernel_table().f32[q.act] : kernel_table().bf16[res_mode][q.act];
-  fn<<<grid, kThreads, smem_bytes, stream>>>(p);
+  EQXV_CUDA(launch_kernel(fn, dim3(grid), dim3(kThreads), (size_t)(smem_bytes), stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
@@ -1300,6 +1322,7 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
   const int b_slab = block_n * 128;
   const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
   EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "conv: cout %d too large for the bias staging area", d->cout);
+  p.res_bufs = 2, p.res_shift = 1;
   const int fixed = 2 * kStageBuf + (p.has_res ? 2 * kStageBuf : 0) + bias_bytes + 512;
   int sa = 3;
   int sb = (kMaxSmem - 1024 - fixed - sa * p.h_stage_bytes) / b_slab;
@@ -1307,7 +1330,17 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
     sa = 2;
     sb = (kMaxSmem - 1024 - fixed - sa * p.h_stage_bytes) / b_slab;
   }
-  sb = std::min(sb, 8);
+  // The B slabs ([block_n x 64] per tap and K chunk) used to stream through an 8-deep ring for EVERY tile
+  // (ResNet layer1 3x3: 72 KiB of filter per 23 KiB of activation tile, L2->SM bound at 43 % of its
+  // roofline, profiles/r01_layer_roofline_v3.txt). When the whole filter fits it is loaded once per CTA.
+  const int slabs = d->kh * d->kw * kchunks;
+  static const bool no_bres = getenv("EQXV_NO_BRES") != nullptr;
+  if (p.n_tiles == 1 && slabs <= sb && slabs <= 12 && !no_bres) {
+    sb = slabs;
+    p.b_resident = 1;
+  } else {
+    sb = std::min(sb, 8);
+  }
   EQXV_CHECK_ARG(sb >= 2, "conv: not enough shared memory for the halo pipeline");
   p.stages = sb;
   p.h_planes = sa;
@@ -1365,7 +1398,7 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
   }
   const int res_mode = d->residual ? (p.res_after_act ? 2 : 1) : 0;
   const int grid = std::min(p.num_tiles, device_sm_count());
-  halo_table(d->act, res_mode)<<<grid, kThreads, smem_bytes, stream>>>(p);
+  EQXV_CUDA(launch_kernel(halo_table(d->act, res_mode), dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
@@ -1395,11 +1428,16 @@ extern "C" int eqxv_conv2d_igemm_bf16(const eqxv_conv_desc* d, void* stream) {
   const int ho = (d->h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
   const int wo = (d->w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
   EQXV_CHECK_ARG(ho > 0 && wo > 0, "conv: empty output");
-  if (halo_eligible(d, ho, wo)) return launch_halo(d, ho, wo, (cudaStream_t)stream);
+  const bool grouped = (d->flags & EQXV_FLAG_GROUPED_BLOCK64) != 0;
+  if (grouped)
+    EQXV_CHECK_ARG(d->cin == d->cout && d->cin % 64 == 0 && !f32,
+                   "conv: GROUPED_BLOCK64 needs cin == cout, a multiple of 64, bf16 output");
+  if (!grouped && halo_eligible(d, ho, wo)) return launch_halo(d, ho, wo, (cudaStream_t)stream);
 
   IgemmProblem q{};
+  q.grouped = grouped ? 1 : 0;
   q.wgt = d->wgt;
-  q.ktot = d->kh * d->kw * d->cin;
+  q.ktot = d->kh * d->kw * (grouped ? 64 : d->cin);
   q.bias = d->bias;
   q.y = d->y;
   q.res = d->residual;
@@ -1408,8 +1446,8 @@ extern "C" int eqxv_conv2d_igemm_bf16(const eqxv_conv_desc* d, void* stream) {
   q.cout = d->cout;
   q.act = d->act;
   q.flags = d->flags;
-  q.kchunks = ceil_div(d->cin, kBlockK);
-  q.cin_pack = d->cin;
+  q.kchunks = grouped ? 1 : ceil_div(d->cin, kBlockK);
+  q.cin_pack = grouped ? 64 : d->cin;
   q.a.base = const_cast<void*>(d->x);
   q.a.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   q.a.rank = 4;
@@ -1514,6 +1552,7 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
     p.h_off_b = stages * p.h_stage_bytes;
     p.off_out = p.h_off_b + b_bytes;
     p.off_res = p.off_out + 2 * kStageBuf;
+    p.res_bufs = 2, p.res_shift = 1;   // no residual on the first layer
     p.off_bias = p.off_res;
     p.off_bars = p.off_bias + bias_bytes;
     const int smem_bytes = p.off_bars + 256 + 1024;
@@ -1547,7 +1586,7 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
     rc = encode_tmap(&p.tmC, c);
     if (rc) return rc;
     const int grid = std::min(p.num_tiles, device_sm_count());
-    stem_table(act)<<<grid, kStemThreads, smem_bytes, (cudaStream_t)stream>>>(p);
+    EQXV_CUDA(launch_kernel(stem_table(act), dim3(grid), dim3(kStemThreads), (size_t)(smem_bytes), (cudaStream_t)stream, p));
     EQXV_CUDA(cudaGetLastError());
     return EQXV_OK;
   }

@@ -41,6 +41,8 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict__ y, int n, int c, int h,
                                  int w, int pad) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int hp = h + 2 * pad, wp = w + 8;
   const long long total = (long long)n * hp * wp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -64,6 +66,8 @@ __global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict
 // fp32 NCHW -> bf16 NHWC (channels padded with zeros to c_pad)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16x8* __restrict__ y, int n, int c,
                                     int h, int w, int c_pad) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int groups = c_pad / 8;
   const long long plane = (long long)h * w;
   const long long total = (long long)n * plane * groups;
@@ -86,6 +90,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16x8* __restr
 // bf16 NHWC (pitch) -> fp32 NCHW through a 32x33 shared tile (pixels x channels)
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int c,
                                     long long plane, int pitch) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   __shared__ float tile[32][33];
   const int img = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -113,6 +119,8 @@ template <bool kMax>
 __global__ void pool2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                               int n, int h, int w, int c, int kh, int kw, int sh, int sw, int pad,
                               int ho, int wo, int xp, int yp) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int groups = c / 8;
   const long long total = (long long)n * ho * wo * groups;
   const float inv = 1.f / (float)(kh * kw);
@@ -154,6 +162,8 @@ __global__ void pool2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
 template <bool kMax, int K, int S>
 __global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                     int n, int h, int w, int c, int pad, int ho, int wo, int xp, int yp) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int groups = c / 8;
   const long long total = (long long)n * ho * wo * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -208,6 +218,8 @@ __global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 __global__ void __launch_bounds__(256) global_avgpool_kernel(const __nv_bfloat16* __restrict__ x,
                                                              __nv_bfloat16* __restrict__ y, int hw, int c,
                                                              int xp, int yp) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   __shared__ float red[256][9];
   const int groups = c / 8;
   const int g0 = blockIdx.x * 8;
@@ -251,6 +263,8 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  __nv_bfloat16* __restrict__ y, long long ldy, long long rows, int d,
                                  float eps) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = d / 8;
@@ -320,11 +334,8 @@ __global__ void __launch_bounds__(256) layernorm_fixed_kernel(const __nv_bfloat1
   const int lane = threadIdx.x & 31;
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  bf16x8 cur[NV], nxt[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) cur[i] = *reinterpret_cast<const bf16x8*>(x + row * ldx + (lane + i * 32) * 8);
-  // affine parameters of this lane's columns (same for every row)
+  // affine parameters of this lane's columns (same for every row; constants, so they are fetched
+  // BEFORE the PDL wait and overlap the tail of the kernel that produces x)
   float gg[NV][8], bb[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -334,6 +345,12 @@ __global__ void __launch_bounds__(256) layernorm_fixed_kernel(const __nv_bfloat1
     gg[i][0] = g0.x, gg[i][1] = g0.y, gg[i][2] = g0.z, gg[i][3] = g0.w, gg[i][4] = g1.x, gg[i][5] = g1.y, gg[i][6] = g1.z, gg[i][7] = g1.w;
     bb[i][0] = b0.x, bb[i][1] = b0.y, bb[i][2] = b0.z, bb[i][3] = b0.w, bb[i][4] = b1.x, bb[i][5] = b1.y, bb[i][6] = b1.z, bb[i][7] = b1.w;
   }
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
+  if (row >= rows) return;
+  bf16x8 cur[NV], nxt[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) cur[i] = *reinterpret_cast<const bf16x8*>(x + row * ldx + (lane + i * 32) * 8);
   for (; row < rows; row += wstride) {
     const long long nrow = row + wstride;
     if (nrow < rows) {
@@ -381,6 +398,8 @@ __global__ void __launch_bounds__(256) layernorm_fixed_kernel(const __nv_bfloat1
 // rows[(img*gh + gy)*gw + gx, (ch*p + py)*p + px] = x[img, ch, gy*p+py, gx*p+px]
 __global__ void patchify_kernel(const float* __restrict__ x, bf16x8* __restrict__ rows, int n, int c,
                                 int h, int w, int p) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int gh = h / p, gw = w / p;
   const int kvec = c * p * p / 8;
   const int pv = p / 8;  // vectors per patch row
@@ -406,6 +425,8 @@ __global__ void patchify_kernel(const float* __restrict__ x, bf16x8* __restrict_
 __global__ void assemble_tokens_kernel(const bf16x8* __restrict__ patches, const float* __restrict__ cls,
                                        const float* __restrict__ pos, bf16x8* __restrict__ out, int n,
                                        int np, int d) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int dv = d / 8;
   const long long total = (long long)n * (np + 1) * dv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -430,6 +451,8 @@ __global__ void assemble_tokens_kernel(const bf16x8* __restrict__ patches, const
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                    __nv_bfloat16* __restrict__ y, long long ldy, int n, int tokens,
                                    int row, int d) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int dv = d / 8;
   const long long total = (long long)n * dv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -452,8 +475,8 @@ extern "C" int eqxv_pack_stem_input(const float* x, void* xpad, int32_t n, int32
   EQXV_CHECK_ARG(x && xpad && n > 0 && h > 0 && w > 0 && c >= 1 && c <= 8 && pad >= 0 && pad <= 4,
                  "pack_stem_input: bad arguments");
   const long long total = (long long)n * (h + 2 * pad) * (w + 8);
-  pack_stem_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<bf16x8*>(xpad), n, c, h, w, pad);
+  EQXV_CUDA(launch_kernel(pack_stem_kernel, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), (cudaStream_t)stream, 
+      x, reinterpret_cast<bf16x8*>(xpad), n, c, h, w, pad));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }
@@ -463,8 +486,8 @@ extern "C" int eqxv_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, in
   EQXV_CHECK_ARG(x && y && n > 0 && c > 0 && h > 0 && w > 0, "nchw_to_nhwc: bad arguments");
   EQXV_CHECK_ARG(c_pad >= c && c_pad % 8 == 0, "nchw_to_nhwc: c_pad must be a multiple of 8 >= c");
   const long long total = (long long)n * h * w * (c_pad / 8);
-  nchw_to_nhwc_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<bf16x8*>(y), n, c, h, w, c_pad);
+  EQXV_CUDA(launch_kernel(nchw_to_nhwc_kernel, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), (cudaStream_t)stream, 
+      x, reinterpret_cast<bf16x8*>(y), n, c, h, w, c_pad));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }
@@ -475,8 +498,8 @@ extern "C" int eqxv_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t n, in
                  "nhwc_to_nchw: bad arguments");
   const long long plane = (long long)h * w;
   dim3 grid((unsigned)((plane + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
-  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), y, c, plane, x_pitch);
+  EQXV_CUDA(launch_kernel(nhwc_to_nchw_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), (cudaStream_t)stream, 
+      reinterpret_cast<const __nv_bfloat16*>(x), y, c, plane, x_pitch));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }
@@ -490,30 +513,30 @@ static int pool_common(bool is_max, const void* x, void* y, int n, int h, int w,
   const long long total = (long long)n * ho * wo * (c / 8);
   if (kh == kw && sh == sw && kh == 3 && sh == 2) {
     if (is_max)
-      pool2d_fixed_kernel<true, 3, 2><<<grid_for(total), kPwThreads, 0, stream>>>(
-          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp);
+      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<true, 3, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
     else
-      pool2d_fixed_kernel<false, 3, 2><<<grid_for(total), kPwThreads, 0, stream>>>(
-          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp);
+      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<false, 3, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
     EQXV_LAUNCH_CHECK();
     return EQXV_OK;
   }
   if (kh == kw && sh == sw && kh == 2 && sh == 2) {
     if (is_max)
-      pool2d_fixed_kernel<true, 2, 2><<<grid_for(total), kPwThreads, 0, stream>>>(
-          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp);
+      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<true, 2, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
     else
-      pool2d_fixed_kernel<false, 2, 2><<<grid_for(total), kPwThreads, 0, stream>>>(
-          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp);
+      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<false, 2, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
     EQXV_LAUNCH_CHECK();
     return EQXV_OK;
   }
   if (is_max) {
-    pool2d_kernel<true><<<grid_for(total), kPwThreads, 0, stream>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, kh, kw, sh, sw, pad, ho, wo, xp, yp);
+    EQXV_CUDA(launch_kernel(pool2d_kernel<true>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, kh, kw, sh, sw, pad, ho, wo, xp, yp));
   } else {
-    pool2d_kernel<false><<<grid_for(total), kPwThreads, 0, stream>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, kh, kw, sh, sw, pad, ho, wo, xp, yp);
+    EQXV_CUDA(launch_kernel(pool2d_kernel<false>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, kh, kw, sh, sw, pad, ho, wo, xp, yp));
   }
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
@@ -552,8 +575,8 @@ extern "C" int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n
                        x_pitch >= c && y_pitch >= c && n <= 65535,
                    "global_avgpool: bad arguments");
     dim3 grid((unsigned)((c / 8 + 7) / 8), (unsigned)n);
-    global_avgpool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
-                                                                  h * w, c, x_pitch, y_pitch);
+    EQXV_CUDA(launch_kernel(global_avgpool_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+                                                                  h * w, c, x_pitch, y_pitch));
     EQXV_LAUNCH_CHECK();
     return EQXV_OK;
   }
@@ -578,16 +601,16 @@ extern "C" int eqxv_layernorm_bf16(const void* x, int64_t ldx, const float* gamm
     const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
     __nv_bfloat16* yb = (__nv_bfloat16*)y;
     switch (d / 256) {
-      case 1: layernorm_fixed_kernel<1><<<(int)fb, wpb * 32, 0, (cudaStream_t)stream>>>(xb, ldx, gamma, beta, yb, ldy, rows, eps); break;
-      case 2: layernorm_fixed_kernel<2><<<(int)fb, wpb * 32, 0, (cudaStream_t)stream>>>(xb, ldx, gamma, beta, yb, ldy, rows, eps); break;
-      case 3: layernorm_fixed_kernel<3><<<(int)fb, wpb * 32, 0, (cudaStream_t)stream>>>(xb, ldx, gamma, beta, yb, ldy, rows, eps); break;
-      default: layernorm_fixed_kernel<4><<<(int)fb, wpb * 32, 0, (cudaStream_t)stream>>>(xb, ldx, gamma, beta, yb, ldy, rows, eps); break;
+      case 1: EQXV_CUDA(launch_kernel(layernorm_fixed_kernel<1>, dim3((int)fb), dim3(wpb * 32), (size_t)(0), (cudaStream_t)stream, xb, ldx, gamma, beta, yb, ldy, rows, eps)); break;
+      case 2: EQXV_CUDA(launch_kernel(layernorm_fixed_kernel<2>, dim3((int)fb), dim3(wpb * 32), (size_t)(0), (cudaStream_t)stream, xb, ldx, gamma, beta, yb, ldy, rows, eps)); break;
+      case 3: EQXV_CUDA(launch_kernel(layernorm_fixed_kernel<3>, dim3((int)fb), dim3(wpb * 32), (size_t)(0), (cudaStream_t)stream, xb, ldx, gamma, beta, yb, ldy, rows, eps)); break;
+      default: EQXV_CUDA(launch_kernel(layernorm_fixed_kernel<4>, dim3((int)fb), dim3(wpb * 32), (size_t)(0), (cudaStream_t)stream, xb, ldx, gamma, beta, yb, ldy, rows, eps)); break;
     }
     EQXV_LAUNCH_CHECK();
     return EQXV_OK;
   }
-  layernorm_kernel<<<(int)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, gamma, beta, (__nv_bfloat16*)y, ldy, rows, d, eps);
+  EQXV_CUDA(launch_kernel(layernorm_kernel, dim3((int)blocks), dim3(wpb * 32), (size_t)(0), (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, ldx, gamma, beta, (__nv_bfloat16*)y, ldy, rows, d, eps));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }
@@ -598,8 +621,8 @@ extern "C" int eqxv_patchify_nchw_f32_bf16(const float* x, void* rows, int32_t n
   EQXV_CHECK_ARG(p % 8 == 0 && h % p == 0 && w % p == 0 && w % 4 == 0,
                  "patchify: patch size must be a multiple of 8 dividing h and w");
   const long long total = (long long)n * (h / p) * (w / p) * (c * p * p / 8);
-  patchify_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<bf16x8*>(rows), n, c, h, w, p);
+  EQXV_CUDA(launch_kernel(patchify_kernel, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), (cudaStream_t)stream, 
+      x, reinterpret_cast<bf16x8*>(rows), n, c, h, w, p));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }
@@ -610,8 +633,8 @@ extern "C" int eqxv_vit_assemble_tokens_bf16(const void* patches, const float* c
   EQXV_CHECK_ARG(patches && cls && pos && out && n > 0 && np > 0 && d > 0 && d % 8 == 0,
                  "assemble_tokens: bad arguments");
   const long long total = (long long)n * (np + 1) * (d / 8);
-  assemble_tokens_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const bf16x8*>(patches), cls, pos, reinterpret_cast<bf16x8*>(out), n, np, d);
+  EQXV_CUDA(launch_kernel(assemble_tokens_kernel, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), (cudaStream_t)stream, 
+      reinterpret_cast<const bf16x8*>(patches), cls, pos, reinterpret_cast<bf16x8*>(out), n, np, d));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }
@@ -622,8 +645,8 @@ extern "C" int eqxv_gather_rows_bf16(const void* x, int64_t ldx, void* y, int64_
                      ldx % 8 == 0 && ldy % 8 == 0,
                  "gather_rows: bad arguments");
   const long long total = (long long)n * (d / 8);
-  gather_rows_kernel<<<grid_for(total), kPwThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, n, tokens, row, d);
+  EQXV_CUDA(launch_kernel(gather_rows_kernel, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, n, tokens, row, d));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }

@@ -29,6 +29,17 @@ __device__ __forceinline__ bool elect_one() {
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (common.h: launch_kernel). griddep_wait() blocks until the preceding kernel of the stream has
+// completed and its memory is visible; everything a kernel does before it (barrier init, TMEM
+// allocation, tensor-map prefetch, constant loads) overlaps the predecessor's tail. EVERY kernel
+// executes it (all threads, before the first access to activation memory): completion of kernel i
+// then implies completion of kernel i-1, so dependencies further back than one launch stay ordered.
+// griddep_launch() lets the successor's CTAs be scheduled as soon as this grid's CTAs are all resident.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }

@@ -19,6 +19,8 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in, int& i0,
 // 64x larger than the input for the x8 DeepLab upsample, so the stores are what matters).
 __global__ void resize_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n,
                                       int c, int h, int w, int oh, int ow, int xp, float sh, float sw) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const long long total = (long long)n * c * oh * ow;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -46,6 +48,8 @@ __global__ void resize_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float
 // NHWC bf16 -> NHWC bf16 (ASPP pooling branch: a 1x1 map broadcast to HxW), 8 channels per thread
 __global__ void resize_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n,
                                    int c, int h, int w, int oh, int ow, int xp, int yp, float sh, float sw) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int groups = c / 8;
   const long long total = (long long)n * oh * ow * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -100,8 +104,8 @@ extern "C" int eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32(const void* x, float* 
                  "resize: bad arguments");
   EQXV_CHECK_ARG(oh >= h && ow >= w, "resize: only upsampling matches jax.image.resize here");
   const long long total = (long long)n * c * oh * ow;
-  resize_to_nchw_kernel<<<grid_for2(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, y, n, c, h, w, oh, ow, x_pitch, (float)h / (float)oh, (float)w / (float)ow);
+  EQXV_CUDA(launch_kernel(resize_to_nchw_kernel, dim3(grid_for2(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, y, n, c, h, w, oh, ow, x_pitch, (float)h / (float)oh, (float)w / (float)ow));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
@@ -114,9 +118,9 @@ extern "C" int eqxv_resize_bilinear_nhwc_bf16(const void* x, void* y, int32_t n,
                  "resize: channels/pitches must be multiples of 8");
   EQXV_CHECK_ARG(oh >= h && ow >= w, "resize: only upsampling matches jax.image.resize here");
   const long long total = (long long)n * oh * ow * (c / 8);
-  resize_nhwc_kernel<<<grid_for2(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  EQXV_CUDA(launch_kernel(resize_nhwc_kernel, dim3(grid_for2(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, c, h, w, oh, ow, x_pitch, y_pitch, (float)h / (float)oh,
-      (float)w / (float)ow);
+      (float)w / (float)ow));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }

@@ -16,6 +16,8 @@ template <int HD>
 __global__ void __launch_bounds__(128) window_attention_kernel(
     const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
     int H, int W, int heads, int ws, int shift_h, int shift_w, float scale) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   extern __shared__ float sm[];
   const int T = ws * ws;                 // tokens per window (<= 64)
   float* q = sm;                         // [T][HD+1]
@@ -108,6 +110,8 @@ __global__ void __launch_bounds__(128) window_attention_kernel(
 // (x0,x1,x2,x3 of swin.py:26-31); H, W even.
 __global__ void patch_merge_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h,
                                    int w, int c, int xp, int yp) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
   const int groups = c / 8;
   const int h2 = h / 2, w2 = w / 2;
   const long long total = (long long)n * h2 * w2 * 4 * groups;
@@ -152,8 +156,8 @@ extern "C" int eqxv_window_attention_bf16(const void* qkv, const float* bias, vo
     attr = true;
   }
   dim3 grid((unsigned)((h / window) * (w / window)), (unsigned)n);
-  window_attention_kernel<32><<<grid, 128, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv, bias, (__nv_bfloat16*)out, h, w, heads, window, shift_h, shift_w, scale);
+  EQXV_CUDA(launch_kernel(window_attention_kernel<32>, dim3(grid), dim3(128), (size_t)(smem), (cudaStream_t)stream, 
+      (const __nv_bfloat16*)qkv, bias, (__nv_bfloat16*)out, h, w, heads, window, shift_h, shift_w, scale));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
@@ -168,8 +172,8 @@ extern "C" int eqxv_patch_merge_bf16(const void* x, void* y, int32_t n, int32_t 
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)device_sm_count() * 32;
   if (blocks > cap) blocks = cap;
-  patch_merge_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h,
-                                                                    w, c, x_pitch, y_pitch);
+  EQXV_CUDA(launch_kernel(patch_merge_kernel, dim3((int)blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h,
+                                                                    w, c, x_pitch, y_pitch));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }

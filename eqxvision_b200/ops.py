@@ -27,8 +27,9 @@ def conv_out_size(h, k, stride, pad, dil):
 
 
 def conv2d(x, wgt, bias, *, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, residual=None,
-           res_after_act=False, out=None, out_f32=False, stream=0):
-    """x: [N,H,W,x_pitch] bf16 view (last-dim stride 1); wgt: [cout, kh*kw*cin] bf16; bias fp32 [cout]."""
+           res_after_act=False, out=None, out_f32=False, grouped_block64=False, stream=0):
+    """x: [N,H,W,x_pitch] bf16 view (last-dim stride 1); wgt: [cout, kh*kw*cin] bf16; bias fp32 [cout].
+    grouped_block64: block-diagonal grouped convolution, wgt [cout, kh*kw*64] (_pack.pack_grouped_weight)."""
     _check_cuda(x, wgt, bias, residual, out)
     n, h, w, _ = x.shape
     x_pitch = x.stride(2)
@@ -43,7 +44,8 @@ def conv2d(x, wgt, bias, *, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, re
     d.x_pitch, d.y_pitch = x_pitch, out.stride(2)
     d.res_pitch = residual.stride(2) if residual is not None else 0
     d.act = act
-    d.flags = (_lib.FLAG_OUT_F32 if out_f32 else 0) | (_lib.FLAG_RES_AFTER_ACT if res_after_act else 0)
+    d.flags = (_lib.FLAG_OUT_F32 if out_f32 else 0) | (_lib.FLAG_RES_AFTER_ACT if res_after_act else 0) | \
+        (_lib.FLAG_GROUPED_BLOCK64 if grouped_block64 else 0)
     call("eqxv_conv2d_igemm_bf16", C.byref(d), stream)
     return out
 
@@ -156,6 +158,16 @@ def attention(qkv, images, tokens, heads, head_dim, scale, out=None, stream=0):
         out = torch.empty((images * tokens, heads * head_dim), dtype=BF16, device=qkv.device)
     call("eqxv_attention_fwd_bf16", ptr(qkv), ptr(out), None, images, tokens, heads, head_dim,
          float(scale), stream)
+    return out
+
+
+def attention_probs(qkv, images, tokens, heads, head_dim, scale, out=None, stream=0):
+    """fp32 softmax(q k^T * scale) [images, heads, tokens, tokens] (vit.py:70, return_attention path)"""
+    _check_cuda(qkv, out)
+    if out is None:
+        out = torch.empty((images, heads, tokens, tokens), dtype=torch.float32, device=qkv.device)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    call("eqxv_attention_fwd_bf16", ptr(qkv), None, ptr(out), images, tokens, heads, head_dim, float(scale), stream)
     return out
 
 

@@ -49,7 +49,11 @@ typedef enum eqxv_act {
 
 enum {
   EQXV_FLAG_OUT_F32 = 1,        /* y is fp32 (logits); residual not allowed */
-  EQXV_FLAG_RES_AFTER_ACT = 2   /* y = act(conv + bias) + residual  (default: act(conv+bias+res)) */
+  EQXV_FLAG_RES_AFTER_ACT = 2,  /* y = act(conv + bias) + residual  (default: act(conv+bias+res)) */
+  /* grouped convolution (equinox.nn.Conv2d(groups=G), resnet.py:19-23,83: ResNeXt) stored block-diagonally:
+   * output channels [64b, 64b+64) read only input channels [64b, 64b+64); wgt is [cout, kh*kw*64]
+   * (zero outside a group's own channels). Requires cin == cout, cin % 64 == 0, 64 % (cin/G) == 0. */
+  EQXV_FLAG_GROUPED_BLOCK64 = 4
 };
 
 const char* eqxv_version(void);

@@ -55,6 +55,9 @@ _RESNETS = {
     "resnet18": ("basic", [2, 2, 2, 2]), "resnet34": ("basic", [3, 4, 6, 3]),
     "resnet50": ("bottleneck", [3, 4, 6, 3]), "resnet101": ("bottleneck", [3, 4, 23, 3]),
     "resnet152": ("bottleneck", [3, 8, 36, 3]),
+    # resnet.py:440-511: same block lists, groups / width_per_group only change the conv2 weights' shapes
+    "resnext50_32x4d": ("bottleneck", [3, 4, 6, 3]), "resnext101_32x8d": ("bottleneck", [3, 4, 23, 3]),
+    "wide_resnet50_2": ("bottleneck", [3, 4, 6, 3]), "wide_resnet101_2": ("bottleneck", [3, 4, 23, 3]),
 }
 
 
@@ -79,7 +82,8 @@ def _resnet_block(x, kind, convs, ds, stride, dilation):
         return O.conv_bn_act(out, convs[1][0], None, convs[1][1], 1, 1, act="relu", res=identity)
     # resnet.py:144-162; stride and dilation on conv2, padding == dilation (resnet.py:15-27)
     out = O.conv_bn_act(x, convs[0][0], None, convs[0][1], act="relu")
-    out = O.conv_bn_act(out, convs[1][0], None, convs[1][1], stride, dilation, dilation, act="relu")
+    groups = out.shape[1] // convs[1][0].shape[1]     # ResNeXt: conv2 is grouped (resnet.py:83, _conv3x3 :19-23)
+    out = O.conv_bn_act(out, convs[1][0], None, convs[1][1], stride, dilation, dilation, groups, act="relu")
     return O.conv_bn_act(out, convs[2][0], None, convs[2][1], act="relu", res=identity)  # out += identity; relu
 
 

@@ -69,6 +69,38 @@ def test_conv2d_igemm(device, case):
     assert rel_l2(y, ref.permute(0, 2, 3, 1)) < TOL_BF16
 
 
+# n, h, w, channels, groups, k, stride, dil, act, res
+GROUPED_CASES = [(2, 56, 56, 128, 32, 3, 1, 1, 1, False), (2, 28, 28, 256, 32, 3, 2, 1, 1, False),
+                 (3, 14, 14, 512, 32, 3, 1, 1, 1, True), (2, 7, 7, 1024, 32, 3, 1, 1, 0, False),
+                 (1, 16, 16, 256, 32, 3, 1, 2, 1, False), (2, 9, 11, 64, 1, 1, 1, 1, 2, False),
+                 (2, 14, 14, 128, 2, 3, 1, 1, 0, False)]
+
+
+@pytest.mark.parametrize("case", GROUPED_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_grouped_conv_block_diagonal(device, case):
+    """equinox.nn.Conv2d(groups=G) as used by ResNeXt (resnet.py:19-23, 83) through the block-diagonal
+    64-channel packing (EQXV_FLAG_GROUPED_BLOCK64) against torch's grouped convolution"""
+    from eqxvision_b200 import _pack, ops
+
+    n, h, w, c, groups, k, stride, dil, act, res = case
+    pad = dil * (k - 1) // 2
+    x = rb(device, n, h, w, c, seed=1)
+    wt = torch.randn(c, c // groups, k, k, generator=torch.Generator().manual_seed(2)) * (k * k * c / groups) ** -0.5
+    wt = wt.to(torch.bfloat16).float()
+    bias = torch.randn(c, generator=torch.Generator().manual_seed(3)).to(device)
+    ho, wo = ops.conv_out_size(h, k, stride, pad, dil), ops.conv_out_size(w, k, stride, pad, dil)
+    r = rb(device, n, ho, wo, c, seed=4) if res else None
+    wp = _pack.pack_grouped_weight(wt, groups).to(device)
+    assert wp.shape == (c, k * k * 64)
+    y = ops.conv2d(x, wp, bias, cin=c, cout=c, kh=k, kw=k, stride=stride, pad=pad, dil=dil, act=act, residual=r,
+                   grouped_block64=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(device), bias, stride=stride, padding=pad, dilation=dil,
+                   groups=groups)
+    if res:
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    assert rel_l2(y, ACTS[act](ref).permute(0, 2, 3, 1)) < TOL_BF16
+
+
 GEMM_CASES = [
     (128, 64, 64, 0, False, False), (1000, 128, 192, 0, False, False), (40000, 64, 64, 1, False, False),
     (12608, 2304, 768, 0, False, False), (12608, 768, 3072, 0, True, False), (12608, 3072, 768, 3, False, False),
@@ -166,6 +198,21 @@ def test_attention(device, imgs, tokens, heads):
     att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1)
     ref = (att @ v).permute(0, 2, 1, 3).reshape(imgs * tokens, heads * 64)
     assert rel_l2(out, ref) < 6e-3  # P is rounded to bf16 before P.V
+
+
+@pytest.mark.parametrize("imgs,tokens,heads", [(2, 197, 12), (1, 64, 3), (3, 50, 6), (1, 785, 2), (2, 1, 2), (1, 33, 1)])
+def test_attention_probabilities_output(device, imgs, tokens, heads):
+    """the materialised softmax matrix (vit.py:70, returned by _VitBlock(return_attention=True)): fp32,
+    rows sum to one, equal to the fp32 softmax of the bf16 q/k the device holds"""
+    from eqxvision_b200 import ops
+
+    qkv = rb(device, imgs * tokens, 3 * heads * 64, seed=tokens + 1)
+    probs = ops.attention_probs(qkv, imgs, tokens, heads, 64, 0.125)
+    assert probs.shape == (imgs, heads, tokens, tokens) and probs.dtype == torch.float32
+    q, k, _ = qkv.float().reshape(imgs, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1)
+    assert (probs - ref).abs().max().item() < 2e-5          # fp32 accumulation order only
+    assert (probs.sum(-1) - 1).abs().max().item() < 1e-5
 
 
 def test_vit_glue(device):

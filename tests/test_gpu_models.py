@@ -35,7 +35,8 @@ def keys(n):
 
 
 # (arch, input hw, batch, tol vs emulation, tol vs fp32)
-RESNETS = [("resnet18", 224, 4, 1.0e-2, 3e-2), ("resnet34", 128, 3, 1.5e-2, 4e-2), ("resnet50", 224, 4, 2.0e-2, 6e-2)]
+RESNETS = [("resnet18", 224, 4, 1.0e-2, 3e-2), ("resnet34", 128, 3, 1.5e-2, 4e-2), ("resnet50", 224, 4, 2.0e-2, 6e-2),
+           ("resnext50_32x4d", 128, 2, 2.0e-2, 6e-2), ("wide_resnet50_2", 96, 2, 2.0e-2, 6e-2)]
 
 
 @pytest.mark.parametrize("arch,hw,batch,tol_emu,tol_f32", RESNETS)
@@ -172,6 +173,28 @@ def test_vit_small_default_returns_cls_feature(device, save_checkpoint):
     got = eb.vmap(net)(x, key=keys(3))
     assert got.shape == (3, 384)                  # reference test_vit.py:113
     assert rel(got, om.vit(sd, x, heads=6)) < 2e-2
+
+
+def test_vit_get_last_self_attention(device, save_checkpoint):
+    """reference tests/test_models/test_vit.py:62-83: shape (B, 1, heads, T, T), ValueError outside
+    inference mode; values against the oracle's last-block attention matrix"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+
+    sd = ck.vit_state_dict(embed_dim=192, depth=3, heads=3, num_classes=0, seed=8)
+    net = eb.models.vit_tiny(depth=3, torch_weights=save_checkpoint(sd, "vit_attn.pth"))
+    x = ck.synthetic_images(2, seed=9)
+    with pytest.raises(ValueError):
+        eb.vmap(net.get_last_self_attention)(x, key=keys(2))
+    net = eb.tree_inference(net, True)
+    attn = eb.vmap(net.get_last_self_attention)(x, key=keys(2))
+    assert attn.shape == (2, 1, 3, 197, 197) and attn.dtype == torch.float32
+    ref = om.vit(sd, x, heads=3, return_last_attention=True)
+    assert tuple(ref.shape) in ((2, 1, 3, 197, 197), (2, 3, 197, 197))
+    ref = ref.reshape(attn.shape)
+    assert (attn.cpu().sum(-1) - 1).abs().max().item() < 1e-4
+    assert rel(attn, ref) < 3e-2, rel(attn, ref)             # bf16 activations feeding an fp32 softmax
 
 
 def test_single_sample_call_equals_batched_row(device, save_checkpoint):

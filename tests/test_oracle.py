@@ -169,3 +169,36 @@ def test_swin_shift_mask_matches_torchvision_construction():
     ref = ref.unsqueeze(1) - ref.unsqueeze(2)
     ref = ref.masked_fill(ref != 0, -100.0)
     assert torch.equal(mask, ref)
+
+
+def test_grouped_weight_packing_is_block_diagonal():
+    """_pack.pack_grouped_weight (ResNeXt conv2): a dense conv over the packed 64-channel blocks equals
+    torch's grouped convolution"""
+    import torch.nn.functional as F
+
+    from eqxvision_b200 import _pack
+
+    g = torch.Generator().manual_seed(0)
+    for c, groups in ((128, 32), (256, 32), (64, 1), (128, 2)):
+        w = torch.randn(c, c // groups, 3, 3, generator=g).to(torch.bfloat16).float()
+        x = torch.randn(2, c, 9, 9, generator=g)
+        ref = F.conv2d(x, w, padding=1, groups=groups)
+        wp = _pack.pack_grouped_weight(w, groups).float().reshape(c, 3, 3, 64)
+        outs = []
+        for b in range(c // 64):   # block b: dense 64 -> 64 convolution
+            wb = wp[64 * b:64 * b + 64].permute(0, 3, 1, 2)
+            outs.append(F.conv2d(x[:, 64 * b:64 * b + 64], wb, padding=1))
+        assert torch.allclose(torch.cat(outs, 1), ref, atol=1e-4, rtol=1e-4)
+
+
+def test_oracle_resnext_matches_torchvision():
+    """the grouped conv2 of ResNeXt (resnet.py:83) in the oracle against torchvision's resnext50_32x4d"""
+    from oracle import checkpoints as ck
+    from oracle import models as om
+
+    tv = ck.torchvision_model("resnext50_32x4d", seed=1)
+    x = ck.synthetic_images(1, h=64, w=64, seed=2)
+    with torch.no_grad():
+        ref = tv(x)
+    got = om.resnet(tv.state_dict(), x, "resnext50_32x4d")
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4)

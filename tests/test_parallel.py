@@ -59,7 +59,8 @@ def test_two_rank_shard_and_gather_equals_single_process(tmp_path, n_images):
     mp.spawn(_worker, args=(2, port, n_images, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["full"].shape == (n_images, 5)
-    assert torch.allclose(r["full"], r["ref"], atol=1e-6)
+    # the CPU stand-in runs torch GEMMs whose blocking (hence fp32 summation order) depends on the shard size
+    assert torch.allclose(r["full"], r["ref"], atol=2e-5, rtol=1e-4)
 
 
 def test_single_process_is_identity():
