@@ -1,6 +1,10 @@
 // Depthwise convolution and the elementwise passes that cannot ride in a GEMM epilogue.
 // HBM-bound, integer-free data paths: channels-last, 16-byte vectors (8 bf16 channels) per thread,
 // no tensor cores (K3/K8/K11 of SURVEY.md §2.1).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -254,6 +258,217 @@ __global__ void eltwise_kernel(const __nv_bfloat16* __restrict__ x, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-memory stencil variant (the production path for K in {3,5}, stride 1/2, dilation 1).
+//
+// The register-strip kernels above re-read every input row K/S times through L2 (vertical neighbours
+// live in different blocks): EfficientNet-B4's depthwise layers sat at 0.7-1.5 TB/s of DRAM traffic,
+// L2-bandwidth bound. Here a persistent CTA stages the input halo tile of a
+// (64-channel block) x (THo x TWo outputs) tile ONCE with a single TMA box -- out-of-bounds zero fill
+// is the convolution padding -- together with the block's K*K x 64 fp32 filter slab, double-buffered so
+// that the next tile is in flight while the current one is computed.
+// Thread = 8 channels (one 16-byte vector) of one output column and RH consecutive output rows: each
+// staged input row is read once per thread (K vectors) and feeds up to K output rows held in
+// registers. A warp covers 4 adjacent pixels x 64 channels = 512 contiguous bytes per shared-memory
+// read (conflict free) and per global store (full 128-byte lines).
+// Reference: equinox.nn.Conv2d(groups=C) + BatchNorm + activation of _MBConv (efficientnet.py:138-150)
+// and _InvertedResidual (mobilenetv3.py:88-101).
+// ---------------------------------------------------------------------------------------------
+struct alignas(64) DwTileParams {
+  CUtensorMap tmX, tmW;
+  const float* bias;
+  __nv_bfloat16* y;
+  int h, w, c, ho, wo, yp, pad, act;
+  int two, rg;                       // output columns per tile, row groups (two * rg == 32)
+  int tiles_x, tiles_y, cblocks, num_tiles;
+  int iw, ih;                        // staged input tile (pixels)
+  int in_bytes, w_bytes, buf_bytes;  // per buffer: input tile, filter slab, total (128-byte multiples)
+};
+
+template <int K, int S>
+__global__ void __launch_bounds__(256, (K == 3 && S == 1) ? 2 : 1) dwconv_tile_kernel(const __grid_constant__ DwTileParams p) {
+  constexpr int RH = S == 1 ? 8 : 4;          // output rows per thread
+  constexpr int IHT = (RH - 1) * S + K;       // input rows one thread walks over
+  constexpr int W = (K - 1) / S + 1;          // output rows in flight per thread
+  extern __shared__ uint8_t dw_smem_raw[];
+  const uint32_t raw = smem_u32(dw_smem_raw);
+  const uint32_t base = (raw + 127u) & ~127u;
+  uint8_t* gbase = dw_smem_raw + (base - raw);
+  const uint32_t bars = base + 2u * (uint32_t)p.buf_bytes;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmW);
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    mbar_fence_init();
+  }
+  const int cg = threadIdx.x & 7;
+  const int slot = threadIdx.x >> 3;          // 0..31
+  const int col = slot % p.two, rgi = slot / p.two;
+  const int tho = p.rg * RH;
+
+  auto issue = [&](int tile, uint32_t b) {    // one thread
+    int t = tile;
+    const int cb = t % p.cblocks;
+    t /= p.cblocks;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int img = t / p.tiles_y;
+    const uint32_t dst = base + b * (uint32_t)p.buf_bytes;
+    mbar_expect_tx(bars + 8u * b, (uint32_t)(p.in_bytes + p.w_bytes));
+    tma_load_4d(dst, &p.tmX, bars + 8u * b, cb * 64, tx * p.two * S - p.pad, ty * tho * S - p.pad, img);
+    tma_load_2d(dst + (uint32_t)p.in_bytes, &p.tmW, bars + 8u * b, cb * 64, 0);
+  };
+
+  griddep_wait();   // PDL: the producer of x has completed
+  __syncthreads();
+  griddep_launch();
+  if (threadIdx.x == 0 && (int)blockIdx.x < p.num_tiles) issue((int)blockIdx.x, 0u);
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t b = (uint32_t)it & 1u;
+    if (threadIdx.x == 0 && tile + (int)gridDim.x < p.num_tiles) issue(tile + (int)gridDim.x, b ^ 1u);
+    int t = tile;
+    const int cb = t % p.cblocks;
+    t /= p.cblocks;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int img = t / p.tiles_y;
+    const int ch = cb * 64 + cg * 8;
+    float bia[8];
+    {
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+      if (ch < p.c) {
+        b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+        b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + 4));
+      }
+      bia[0] = b0.x, bia[1] = b0.y, bia[2] = b0.z, bia[3] = b0.w;
+      bia[4] = b1.x, bia[5] = b1.y, bia[6] = b1.z, bia[7] = b1.w;
+    }
+    // Sliding window over the input rows: win[d] accumulates output row (j - d) of this thread's column;
+    // step j consumes input rows j*S .. j*S+S-1, after which output row j-(W-1) is complete and leaves
+    // through global memory. Registers: W*8 accumulators whatever RH is.
+    float win[W][8];
+#pragma unroll
+    for (int d = 0; d < W; ++d)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) win[d][e] = bia[e];
+    mbar_wait(bars + 8u * b, (uint32_t)(it >> 1) & 1u);
+    const uint8_t* in = gbase + b * p.buf_bytes + ((size_t)(rgi * RH * S) * p.iw + col * S) * 128 + cg * 16;
+    const float* wsm = reinterpret_cast<const float*>(gbase + b * p.buf_bytes + p.in_bytes) + cg * 8;
+    const int ow = tx * p.two + col;
+    const int oh0 = ty * tho + rgi * RH;
+    const bool live = ow < p.wo && ch < p.c;
+    __nv_bfloat16* yout = p.y + (((long long)img * p.ho + oh0) * p.wo + ow) * p.yp + ch;
+#pragma unroll 1
+    for (int j = 0; j < RH + W - 1; ++j) {
+#pragma unroll
+      for (int sr = 0; sr < S; ++sr) {
+        const int i = j * S + sr;
+        if (i < IHT) {
+          const uint8_t* row = in + (size_t)i * p.iw * 128;
+#pragma unroll
+          for (int q = 0; q < K; ++q) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(row + q * 128), f);
+#pragma unroll
+            for (int r = sr; r < K; r += S) {
+              const int d = (r - sr) / S;
+              const float4 w0 = *reinterpret_cast<const float4*>(wsm + (r * K + q) * 64);
+              const float4 w1 = *reinterpret_cast<const float4*>(wsm + (r * K + q) * 64 + 4);
+              win[d][0] = fmaf(f[0], w0.x, win[d][0]);
+              win[d][1] = fmaf(f[1], w0.y, win[d][1]);
+              win[d][2] = fmaf(f[2], w0.z, win[d][2]);
+              win[d][3] = fmaf(f[3], w0.w, win[d][3]);
+              win[d][4] = fmaf(f[4], w1.x, win[d][4]);
+              win[d][5] = fmaf(f[5], w1.y, win[d][5]);
+              win[d][6] = fmaf(f[6], w1.z, win[d][6]);
+              win[d][7] = fmaf(f[7], w1.w, win[d][7]);
+            }
+          }
+        }
+      }
+      const int o = j - (W - 1);
+      if (o >= 0 && live && oh0 + o < p.ho) {
+        float r8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r8[e] = act_rt(win[W - 1][e], p.act);
+        *reinterpret_cast<uint4*>(yout + (long long)o * p.wo * p.yp) = pack8(r8);
+      }
+#pragma unroll
+      for (int d = W - 1; d > 0; --d)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) win[d][e] = win[d - 1][e];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) win[0][e] = bia[e];
+    }
+    __syncthreads();   // every thread is done with buffer b before the TMA of iteration it+1 refills it
+  }
+}
+
+template <int K, int S>
+static int launch_dw_tile(const void* x, const float* wgt, const float* bias, void* y, int n, int h, int w, int c,
+                          int pad, int ho, int wo, int xp, int yp, int wp, int act, cudaStream_t st) {
+  constexpr int RH = S == 1 ? 8 : 4;
+  DwTileParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.h = h, p.w = w, p.c = c, p.ho = ho, p.wo = wo, p.yp = yp, p.pad = pad, p.act = act;
+  p.two = wo >= 24 ? 32 : (wo >= 12 ? 16 : 8);
+  p.rg = 32 / p.two;
+  const int tho = p.rg * RH;
+  p.tiles_x = ceil_div(wo, p.two);
+  p.tiles_y = ceil_div(ho, tho);
+  p.cblocks = ceil_div(c, 64);
+  const long long nt = (long long)n * p.tiles_x * p.tiles_y * p.cblocks;
+  EQXV_CHECK_ARG(nt > 0 && nt < (1ll << 30), "dwconv: bad tile count");
+  p.num_tiles = (int)nt;
+  p.iw = (p.two - 1) * S + K;
+  p.ih = (tho - 1) * S + K;
+  p.in_bytes = p.iw * p.ih * 128;
+  p.w_bytes = K * K * 64 * 4;
+  p.buf_bytes = ceil_div(p.in_bytes + p.w_bytes, 128) * 128;
+  const int smem = 2 * p.buf_bytes + 16 + 128;
+  EQXV_CHECK_ARG(smem <= 232448 && p.iw <= 256 && p.ih <= 256, "dwconv: tile does not fit in shared memory");
+  TmapSpec a{};
+  a.base = const_cast<void*>(x);
+  a.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  a.rank = 4;
+  a.swizzle = CU_TENSOR_MAP_SWIZZLE_NONE;
+  a.dims[0] = (uint64_t)c, a.dims[1] = (uint64_t)w, a.dims[2] = (uint64_t)h, a.dims[3] = (uint64_t)n;
+  a.strides_bytes[0] = (uint64_t)xp * 2;
+  a.strides_bytes[1] = a.strides_bytes[0] * (uint64_t)w;
+  a.strides_bytes[2] = a.strides_bytes[1] * (uint64_t)h;
+  a.box[0] = 64, a.box[1] = (uint32_t)p.iw, a.box[2] = (uint32_t)p.ih, a.box[3] = 1;
+  a.estride[0] = a.estride[1] = a.estride[2] = a.estride[3] = 1;
+  int rc = encode_tmap(&p.tmX, a);
+  if (rc) return rc;
+  TmapSpec wm{};
+  wm.base = const_cast<float*>(wgt);
+  wm.dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  wm.rank = 2;
+  wm.swizzle = CU_TENSOR_MAP_SWIZZLE_NONE;
+  wm.dims[0] = (uint64_t)wp, wm.dims[1] = (uint64_t)(K * K);
+  wm.strides_bytes[0] = (uint64_t)wp * 4;
+  wm.box[0] = 64, wm.box[1] = (uint32_t)(K * K);
+  wm.estride[0] = wm.estride[1] = 1;
+  rc = encode_tmap(&p.tmW, wm);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EQXV_CUDA(cudaFuncSetAttribute(dwconv_tile_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_done = true;
+  }
+  const int per_sm = std::max(1, std::min(2, 232448 / (smem + 1024)));
+  const int grid = std::min(p.num_tiles, device_sm_count() * per_sm);
+  EQXV_CUDA(launch_kernel(dwconv_tile_kernel<K, S>, dim3(grid), dim3(256), (size_t)smem, st, p));
+  return EQXV_OK;
+}
+
 }  // namespace eqxv
 
 using namespace eqxv;
@@ -275,6 +490,15 @@ extern "C" int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
   __nv_bfloat16* yo = (__nv_bfloat16*)y;
+  // shared-memory stencil path (TMA-staged halo tiles); EQXV_NO_DWTILE=1 falls back to the register strips
+  static const bool no_tile = getenv("EQXV_NO_DWTILE") != nullptr;
+  if (!no_tile && dil == 1 && (k == 3 || k == 5) && ((uintptr_t)x & 15) == 0 && ((uintptr_t)wgt & 15) == 0 &&
+      w_pitch % 4 == 0 && 2 * pad <= k) {
+    if (k == 3 && stride == 1) return launch_dw_tile<3, 1>(x, wgt, bias, y, n, h, w, c, pad, ho, wo, x_pitch, y_pitch, w_pitch, act, st);
+    if (k == 3 && stride == 2) return launch_dw_tile<3, 2>(x, wgt, bias, y, n, h, w, c, pad, ho, wo, x_pitch, y_pitch, w_pitch, act, st);
+    if (k == 5 && stride == 1) return launch_dw_tile<5, 1>(x, wgt, bias, y, n, h, w, c, pad, ho, wo, x_pitch, y_pitch, w_pitch, act, st);
+    if (k == 5 && stride == 2) return launch_dw_tile<5, 2>(x, wgt, bias, y, n, h, w, c, pad, ho, wo, x_pitch, y_pitch, w_pitch, act, st);
+  }
 #define EQXV_DWS(K, S, TW)                                                                          \
   EQXV_CUDA(launch_kernel(dwconv_strip_kernel<K, S, TW>,                                            \
                           dim3(grid_for((long long)n * ho * ((wo + TW - 1) / TW) * (c / 8))),       \

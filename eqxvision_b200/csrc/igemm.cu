@@ -26,7 +26,8 @@ namespace eqxv {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarpsMax = 8;                 // two epilogue warps per TMEM lane quadrant
+constexpr int kThreads = 64 + 32 * kEpiWarpsMax;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kStageBuf = 16384;                // one epilogue staging buffer (128 rows x 128 B)
 constexpr int kMaxSmem = 232448;                // 227 KiB
@@ -46,7 +47,7 @@ struct alignas(64) IgemmParams {
   int stages;
   int b_resident;   // halo kernel: the whole packed filter stays in the B ring (loaded once per CTA)
   int grouped;      // 1: block-diagonal grouped conv, the A channel offset follows the n-tile (block_n == 64)
-  int res_bufs, res_shift;   // residual prefetch ring per epilogue warp (2 or 4 slabs), log2
+  int epi_sub;      // epilogue warps per TMEM lane quadrant (1 or 2): blockDim = 64 + 128 * epi_sub
   // shared-memory carve-up (byte offsets from the 1024-aligned base)
   int off_out, off_res, off_bias, off_bars;
   // first-layer (halo) kernel only
@@ -176,8 +177,17 @@ __device__ __forceinline__ uint4 epilogue8(const float* v, const float* bias_sme
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// ============================== epilogue (warps 2..5) ==============================
-// Shared by the generic implicit-GEMM kernel and the first-layer (halo) kernel.
+// ============================== epilogue (warps 2..) ==============================
+// Shared by the generic implicit-GEMM kernel, the CTA-pair kernel, the halo kernel and the first-layer
+// kernel. EIGHT warps (kEpiWarps): two per TMEM lane quadrant (a warp may only touch the 32 lanes
+// 32*(warp%4)..), which take alternate 64-column chunks of the quadrant's 32 accumulator rows.
+// With one warp per quadrant (= one per SM sub-partition) every chunk was a serial latency chain
+// (tcgen05.ld -> residual wait -> math -> st.shared -> proxy fence -> TMA store) with nothing to overlap
+// it: a 128 x 256 tile took ~8000 cycles of epilogue whatever the layer (ResNet c3 layers: 5.1 us per
+// tile at K = 256, profiles/r01_layer_roofline_v3.txt), i.e. the epilogue, not HBM or the tensor
+// pipe, bounded every shallow-K layer. Two warps per sub-partition hide each other's latencies.
+// Every warp owns its slab privately: its own staging buffer, its own TMA stores / residual loads
+// (issued by an elected lane) and its own mbarriers; there is no CTA-wide barrier on this path.
 template <bool kOutF32, int kAct, int kRes, bool kPair = false>
 __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
                                                const uint32_t tmem_base, const int warp, const int lane) {
@@ -187,124 +197,130 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
   const uint32_t bars = base + p.off_bars;
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  {
-    // ============================== epilogue (warps 2..5) ==============================
-    // Every warp owns the 32 accumulator rows of its TMEM lane quadrant as an independent slab:
-    // its own staging buffers, its own TMA stores / residual loads (issued by an elected lane) and
-    // its own mbarriers. There is no CTA-wide barrier on this path, so one warp waiting on a TMA
-    // store or a residual tile never stalls the other three.
-    constexpr int CH = kOutF32 ? 32 : 64;  // columns per staged chunk (128 B per row)
-    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
-    const int cpt = (p.block_n + CH - 1) / CH;
-    const float* s_bias = reinterpret_cast<const float*>(gbase + p.off_bias);
-    constexpr bool has_res = kRes != 0;
-    constexpr bool res_after_act = kRes == 2;
-    // slab origin inside the (tn, th, tw) tile: rows are ordered n, h, w (w fastest)
-    const int so = quad * 32;
-    const int w_off = so % p.tw, h_off = (so / p.tw) % p.th, n_off = so / (p.tw * p.th);
-    constexpr uint32_t kSlab = 32 * 128;  // 4 KiB per warp per buffer
-    const uint32_t out_u32 = base + p.off_out + quad * kSlab;   // + buf * kStageBuf
-    const uint32_t res_u32 = base + p.off_res + quad * kSlab;
-    uint8_t* out_g = gbase + p.off_out + quad * kSlab;
-    const uint8_t* res_g = gbase + p.off_res + quad * kSlab;
-    // residual ring: R slabs per warp, prefetched R chunks ahead (R = 4 on the HBM-bound layers: with 2
-    // the residual stream had only 8 KiB per warp in flight and the c3 convolutions of ResNet sat at
-    // ~78 % of the HBM roofline, profiles/r01_layer_roofline_v3.txt)
-    const uint32_t R = (uint32_t)p.res_bufs, rshift = (uint32_t)p.res_shift;
-    auto rbar = [&](uint32_t b) { return bars + 8u * (48u + (uint32_t)quad * 4u + b); };
+  constexpr int CH = kOutF32 ? 32 : 64;  // columns per staged chunk (128 B per row)
+  const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+  const int nsub = p.epi_sub;            // warps per quadrant (1 or 2)
+  const int sub = ((warp - 2) >> 2) % nsub;
+  const int wid = quad * nsub + sub;     // private slab index
+  const int cpt = (p.block_n + CH - 1) / CH;
+  const float* s_bias = reinterpret_cast<const float*>(gbase + p.off_bias);
+  constexpr bool has_res = kRes != 0;
+  // slab origin inside the (tn, th, tw) tile: rows are ordered n, h, w (w fastest)
+  const int so = quad * 32;
+  const int w_off = so % p.tw, h_off = (so / p.tw) % p.th, n_off = so / (p.tw * p.th);
+  constexpr uint32_t kSlab = 32 * 128;  // 4 KiB: 32 rows x 128 B
+  const uint32_t obufs = 2u / (uint32_t)nsub;                       // staging buffers of this warp (8 slabs in all)
+  const uint32_t out_u32 = base + p.off_out + (uint32_t)wid * obufs * kSlab;
+  uint8_t* out_g = gbase + p.off_out + (uint32_t)wid * obufs * kSlab;
+  const uint32_t res_u32 = base + p.off_res + (uint32_t)wid * 2u * kSlab;   // residual ring: 2 slabs per warp
+  const uint8_t* res_g = gbase + p.off_res + (uint32_t)wid * 2u * kSlab;
+  auto rbar = [&](uint32_t b) { return bars + 8u * (48u + (uint32_t)wid * 2u + b); };
 
-    auto issue_res = [&](uint32_t gg) {  // called by ONE lane
-      const int ti = gg / cpt, c = gg - ti * cpt;
-      const long long tile = (long long)t_first + (long long)ti * t_stride;
-      if (tile >= p.num_tiles) return;
-      const TileCoord t = decode_tile<kPair>(p, (int)tile);
-      const uint32_t b = gg & (R - 1u);
-      mbar_expect_tx(rbar(b), kSlab);
-      tma_load_4d(res_u32 + b * kStageBuf, &p.tmR, rbar(b), t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
-                  t.n0 + n_off);
-    };
-
-    uint32_t g = 0;
-    if (has_res && lane == 0) {
-      for (uint32_t i = 0; i < R; ++i) issue_res(i);
+  // this warp's chunk sequence: local index l -> global chunk g = nsub*l + sub of the CTA's tile sequence
+  auto issue_res = [&](uint32_t l) {  // called by ONE lane
+    const int g = nsub * (int)l + sub;
+    const int ti = g / cpt, c = g - ti * cpt;
+    const long long tile = (long long)t_first + (long long)ti * t_stride;
+    if (tile >= p.num_tiles) return;
+    const TileCoord t = decode_tile<kPair>(p, (int)tile);
+    const uint32_t b = l & 1u;
+    mbar_expect_tx(rbar(b), kSlab);
+    tma_load_4d(res_u32 + b * kSlab, &p.tmR, rbar(b), t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off, t.n0 + n_off);
+  };
+  auto release_acc = [&](int ti) {   // all of this warp's TMEM reads of tile ti are done
+    tc_fence_before();
+    if constexpr (kPair) {
+      mbar_arrive_leader(tempty_bar(ti & 1));   // the leader's issuer waits for both CTAs' epilogues
+    } else {
+      mbar_arrive(tempty_bar(ti & 1));
     }
-    __syncwarp();
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = t_first; tile < p.num_tiles; tile += t_stride) {
-      const TileCoord t = decode_tile<kPair>(p, tile);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+  };
 
-      for (int c = 0; c < cpt; ++c, ++g) {
-        const uint32_t buf = g & 1u;
-        const uint32_t rb = g & (R - 1u);
-        const uint32_t rphase = (g >> rshift) & 1u;
-        const int ncols = min(CH, p.block_n - c * CH);
-        float v[CH];
-#pragma unroll
-        for (int j = 0; j < CH / 16; ++j) {
-          if (j * 16 < ncols) {
-            tmem_ld_x16(t_acc + (uint32_t)(c * CH + j * 16), &v[j * 16]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[j * 16 + q] = 0.f;
-          }
-        }
-        tmem_ld_wait();
-        if (c == cpt - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
-          tc_fence_before();
-          if constexpr (kPair) {
-            mbar_arrive_leader(tempty_bar(acc));   // the leader's issuer waits for both CTAs' epilogues
-          } else {
-            mbar_arrive(tempty_bar(acc));
-          }
-        }
-        const float* bias_c = s_bias + t.ncol0 + c * CH;
-        uint8_t* out_row = out_g + buf * kStageBuf;
-        if constexpr (!kOutF32) {
-          uint4 packed[8];
-          if (has_res) mbar_wait(rbar(rb), rphase);
-          const uint8_t* res_row = res_g + rb * kStageBuf;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-            if constexpr (has_res) rv = *reinterpret_cast<const uint4*>(res_row + sw128_off(lane, j));
-            packed[j] = epilogue8<kAct, kRes>(&v[j * 8], bias_c + j * 8, rv);
-          }
-          if (lane == 0) tma_store_wait_read<1>();  // this warp's store that last used out[buf] is done
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(out_row + sw128_off(lane, j)) = packed[j];
-        } else {
-#pragma unroll
-          for (int q = 0; q < CH; ++q) v[q] = apply_act<kAct>(v[q] + bias_c[q]);
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(out_row + sw128_off(lane, j)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(&p.tmC, out_u32 + buf * kStageBuf, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
-                       t.n0 + n_off);
-          tma_store_commit();
-          if (has_res) issue_res(g + R);
-        }
-        __syncwarp();
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
-    }
-    if (lane == 0) tma_store_wait_all();
-    __syncwarp();
+  if (has_res && lane == 0) {
+    issue_res(0);
+    issue_res(1);
   }
+  __syncwarp();
+  int cur_ti = -1;   // last tile whose accumulator this warp has seen complete
+  int ti = sub / cpt, c = sub - ti * cpt;   // chunk g = nsub*l + sub, advanced incrementally
+  for (uint32_t l = 0;; ++l) {
+    // tile coordinates (integer divisions) are resolved BEFORE the accumulator wait, off the critical path;
+    // a tile index past the end decodes to harmless numbers and is never used
+    const TileCoord t = decode_tile<kPair>(p, t_first + ti * t_stride);
+    bool done = false;
+    while (cur_ti < ti) {   // step over tiles (a tile without a chunk of this warp is released at once)
+      ++cur_ti;
+      if ((long long)t_first + (long long)cur_ti * t_stride >= p.num_tiles) {
+        done = true;
+        break;
+      }
+      mbar_wait(tfull_bar(cur_ti & 1), (uint32_t)((cur_ti >> 1) & 1));
+      tc_fence_after();
+      if (cur_ti < ti) release_acc(cur_ti);
+    }
+    if (done) break;
+    const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ti & 1) * p.acc_stride);
+    const uint32_t ob = l & (obufs - 1u);
+    const uint32_t rb = l & 1u, rphase = (l >> 1) & 1u;
+    const int ncols = min(CH, p.block_n - c * CH);
+    float v[CH];
+#pragma unroll
+    for (int j = 0; j < CH / 16; ++j) {
+      if (j * 16 < ncols) {
+        tmem_ld_x16(t_acc + (uint32_t)(c * CH + j * 16), &v[j * 16]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[j * 16 + q] = 0.f;
+      }
+    }
+    tmem_ld_wait();
+    if (c + nsub >= cpt) release_acc(ti);   // this warp's last chunk of the tile
+    const float* bias_c = s_bias + t.ncol0 + c * CH;
+    uint8_t* out_row = out_g + ob * kSlab;
+    if constexpr (!kOutF32) {
+      uint4 packed[8];
+      if (has_res) mbar_wait(rbar(rb), rphase);
+      const uint8_t* res_row = res_g + rb * kSlab;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (has_res) rv = *reinterpret_cast<const uint4*>(res_row + sw128_off(lane, j));
+        packed[j] = epilogue8<kAct, kRes>(&v[j * 8], bias_c + j * 8, rv);
+      }
+      if (lane == 0) {   // the store that last used this staging buffer has read it
+        if (obufs == 2u) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(out_row + sw128_off(lane, j)) = packed[j];
+    } else {
+#pragma unroll
+      for (int q = 0; q < CH; ++q) v[q] = apply_act<kAct>(v[q] + bias_c[q]);
+      if (lane == 0) {
+        if (obufs == 2u) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(out_row + sw128_off(lane, j)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(&p.tmC, out_u32 + ob * kSlab, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off, t.n0 + n_off);
+      tma_store_commit();
+      if (has_res) issue_res(l + 2);
+    }
+    __syncwarp();
+    c += nsub;
+    while (c >= cpt) {
+      c -= cpt;
+      ++ti;
+    }
+  }
+  if (lane == 0) tma_store_wait_all();
+  __syncwarp();
 }
 
 // kRes: 0 = no residual, 1 = act(acc + bias + res), 2 = act(acc + bias) + res. Compile-time so that the
@@ -342,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 128u * (uint32_t)p.epi_sub);
     }
     for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (48 + b), 1);   // residual ring (epilogue_warps)
     mbar_fence_init();
@@ -351,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   {
     float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
     const int ncols_pad = p.n_tiles * p.block_n + 64;
-    for (int i = threadIdx.x; i < ncols_pad; i += kThreads)
+    for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x)
       sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
   }
   if (warp == 1) {
@@ -517,7 +533,7 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 256);  // leader: 4 epilogue warps of each CTA
+      mbar_init(tempty_bar(a), 256u * (uint32_t)p.epi_sub);  // leader: the epilogue warps of both CTAs
     }
     for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (48 + b), 1);   // residual ring (epilogue_warps)
     mbar_fence_init();
@@ -525,7 +541,7 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
   {
     float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
     const int ncols_pad = p.n_tiles * p.block_n + 64;
-    for (int i = threadIdx.x; i < ncols_pad; i += kThreads)
+    for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x)
       sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
   }
   if (warp == 1) {
@@ -648,7 +664,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 // Call sites replaced: resnet.py:243-251 (7x7 s2), vgg.py:137 (3x3 s1), efficientnet.py:327 /
 // mobilenetv3.py:193 (3x3 s2), swin.py:705-713 (4x4 s4).
 constexpr int kStemProducers = 4;                       // warps 0, 6, 7, 8
-constexpr int kStemThreads = kThreads + 32 * (kStemProducers - 1);
+constexpr int kStemThreads = 192 + 32 * (kStemProducers - 1);   // warps 0 (producer), 1 (MMA), 2..5 epilogue, 6..8 producers
 
 // The halo tile is gathered with cp.async: its natural granule is one pixel (16 B), which a TMA box can
 // only move as one request per pixel (measured ~5900 cycles per tile). Here a warp instruction moves
@@ -743,7 +759,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 128u * (uint32_t)p.epi_sub);
     }
     mbar_init(wfull_bar, 1);
     mbar_fence_init();
@@ -885,7 +901,7 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 128u * (uint32_t)p.epi_sub);
     }
     for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (48 + b), 1);   // residual ring (epilogue_warps)
     mbar_fence_init();
@@ -893,7 +909,7 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
   {
     float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
     const int ncols_pad = p.n_tiles * p.block_n + 64;
-    for (int i = threadIdx.x; i < ncols_pad; i += kThreads)
+    for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x)
       sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
   }
   if (warp == 1) {
@@ -1175,19 +1191,20 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   const int stage_bytes = kABytes + (pair ? block_n * 64 : block_n * 128);
   const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
   EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "igemm: cout %d too large for the bias staging area", q.cout);
-  // residual ring depth: 4 slabs per warp on the shallow-K (HBM-bound) layers, 2 where the smem is
-  // better spent on operand stages
-  static const int forced_rb = getenv("EQXV_RES_BUFS") ? atoi(getenv("EQXV_RES_BUFS")) : 0;
-  p.res_bufs = (forced_rb == 2 || forced_rb == 4) ? forced_rb : (kblocks <= 4 ? 4 : 2);
-  p.res_shift = p.res_bufs == 4 ? 2 : 1;
-  const int fixed = 2 * kStageBuf + (p.has_res ? p.res_bufs * kStageBuf : 0) + bias_bytes + 512;
+  // epilogue warps per TMEM lane quadrant; every warp owns 2 residual slabs, the 8 staging slabs are shared out
+  static const int forced_sub = getenv("EQXV_EPI_SUB") ? atoi(getenv("EQXV_EPI_SUB")) : 0;
+  // Two warps per quadrant where the epilogue bounds the tile (shallow K: ResNet c3 / downsample layers went
+  // from 78 % to 99 % of their HBM roofline); one where the K loop hides it anyway and the shared memory
+  // of the second residual ring is better spent on operand stages (ViT GEMMs, 3x3 layers).
+  p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : (kblocks <= 8 ? 2 : 1);
+  const int fixed = 2 * kStageBuf + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
   int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
   stages = std::min(stages, 8);
   EQXV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for block_n=%d", block_n);
   p.stages = stages;
   p.off_out = stages * stage_bytes;
   p.off_res = p.off_out + 2 * kStageBuf;
-  p.off_bias = p.off_res + (p.has_res ? p.res_bufs * kStageBuf : 0);
+  p.off_bias = p.off_res + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0);
   p.off_bars = p.off_bias + bias_bytes;
   const int smem_bytes = p.off_bars + 512 + 1024;
 
@@ -1234,13 +1251,13 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   const int res_mode = q.res ? (p.res_after_act ? 2 : 1) : 0;
   if (pair) {
     const int clusters = std::min(p.num_tiles, device_sm_count() / 2);
-    EQXV_CUDA(launch_kernel(pair_table(q.act, res_mode), dim3(2 * clusters), dim3(kThreads), (size_t)(smem_bytes), stream, p));
+    EQXV_CUDA(launch_kernel(pair_table(q.act, res_mode), dim3(2 * clusters), dim3(64 + 128 * p.epi_sub), (size_t)(smem_bytes), stream, p));
     EQXV_CUDA(cudaGetLastError());
     return EQXV_OK;
   }
   const int grid = std::min(p.num_tiles, device_sm_count());
   const KernelFn fn = out_f32 ? kernel_table().f32[q.act] : kernel_table().bf16[res_mode][q.act];
-  EQXV_CUDA(launch_kernel(fn, dim3(grid), dim3(kThreads), (size_t)(smem_bytes), stream, p));
+  EQXV_CUDA(launch_kernel(fn, dim3(grid), dim3(64 + 128 * p.epi_sub), (size_t)(smem_bytes), stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
@@ -1322,8 +1339,9 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
   const int b_slab = block_n * 128;
   const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
   EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "conv: cout %d too large for the bias staging area", d->cout);
-  p.res_bufs = 2, p.res_shift = 1;
-  const int fixed = 2 * kStageBuf + (p.has_res ? 2 * kStageBuf : 0) + bias_bytes + 512;
+  static const int forced_sub = getenv("EQXV_EPI_SUB") ? atoi(getenv("EQXV_EPI_SUB")) : 0;
+  p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : 1;   // K >= 9 blocks: the MMA loop bounds the tile
+  const int fixed = 2 * kStageBuf + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
   int sa = 3;
   int sb = (kMaxSmem - 1024 - fixed - sa * p.h_stage_bytes) / b_slab;
   if (sb < 4) {
@@ -1347,7 +1365,7 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
   p.h_off_b = sb * b_slab;
   p.off_out = p.h_off_b + sa * p.h_stage_bytes;
   p.off_res = p.off_out + 2 * kStageBuf;
-  p.off_bias = p.off_res + (p.has_res ? 2 * kStageBuf : 0);
+  p.off_bias = p.off_res + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0);
   p.off_bars = p.off_bias + bias_bytes;
   const int smem_bytes = p.off_bars + 512 + 1024;
 
@@ -1398,7 +1416,7 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
   }
   const int res_mode = d->residual ? (p.res_after_act ? 2 : 1) : 0;
   const int grid = std::min(p.num_tiles, device_sm_count());
-  EQXV_CUDA(launch_kernel(halo_table(d->act, res_mode), dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream, p));
+  EQXV_CUDA(launch_kernel(halo_table(d->act, res_mode), dim3(grid), dim3(64 + 128 * p.epi_sub), (size_t)smem_bytes, stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
@@ -1552,7 +1570,7 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
     p.h_off_b = stages * p.h_stage_bytes;
     p.off_out = p.h_off_b + b_bytes;
     p.off_res = p.off_out + 2 * kStageBuf;
-    p.res_bufs = 2, p.res_shift = 1;   // no residual on the first layer
+    p.epi_sub = 1;   // first layer: N = 64 is one chunk per tile; the extra warps are cp.async producers
     p.off_bias = p.off_res;
     p.off_bars = p.off_bias + bias_bytes;
     const int smem_bytes = p.off_bars + 256 + 1024;

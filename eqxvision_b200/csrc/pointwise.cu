@@ -230,7 +230,22 @@ __global__ void __launch_bounds__(256) global_avgpool_kernel(const __nv_bfloat16
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (lane < lanes) {
     const __nv_bfloat16* base = x + (long long)img * hw * xp + (g0 + gi) * 8;
-    for (int p = lane; p < hw; p += lanes) {
+    // four independent 16-byte loads in flight per thread: with one, the SE squeeze of EfficientNet-B4
+    // streamed at 1.8 TB/s (latency-bound, profiles/r01_launch_metrics_efficientnet_b4.txt)
+    int p = lane;
+    for (; p + 3 * lanes < hw; p += 4 * lanes) {
+      bf16x8 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const bf16x8*>(base + (long long)(p + u * lanes) * xp);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(r[u], f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += f[q];
+      }
+    }
+    for (; p < hw; p += lanes) {
       float f[8];
       unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)p * xp), f);
 #pragma unroll

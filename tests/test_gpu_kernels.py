@@ -265,7 +265,12 @@ def test_stem_conv_variants(device, kh, kw, stride, pad, cin, cout, hw):
 
 @pytest.mark.parametrize("c,hw,k,stride,dil,act", [(48, 112, 3, 1, 1, 2), (144, 112, 3, 2, 1, 2), (336, 28, 5, 1, 1, 2),
                                                    (192, 56, 5, 2, 1, 4), (960, 14, 5, 1, 1, 4), (96, 7, 5, 1, 1, 1),
-                                                   (72, 17, 3, 1, 2, 1), (40, 3, 5, 1, 1, 0)])
+                                                   (72, 17, 3, 1, 2, 1), (40, 3, 5, 1, 1, 0),
+                                                   # shared-memory stencil path: ragged tiles, partial channel blocks,
+                                                   # every (k, stride) instantiation, all three tile widths
+                                                   (64, 56, 3, 1, 1, 2), (24, 33, 3, 2, 1, 2), (200, 15, 3, 1, 1, 1),
+                                                   (136, 29, 5, 2, 1, 4), (8, 9, 5, 1, 1, 0), (1632, 7, 5, 1, 1, 2),
+                                                   (672, 14, 5, 2, 1, 2), (32, 112, 3, 1, 1, 2), (88, 25, 3, 2, 1, 6)])
 def test_depthwise(device, c, hw, k, stride, dil, act):
     from eqxvision_b200 import _pack, ops
 
