@@ -279,17 +279,17 @@ struct alignas(64) DwTileParams {
   const float* bias;
   __nv_bfloat16* y;
   int h, w, c, ho, wo, yp, pad, act;
-  int two, rg;                       // output columns per tile, row groups (two * rg == 32)
+  int two, rg, rh;                   // output columns per tile, row groups (two * rg == 32), output rows per thread
   int tiles_x, tiles_y, cblocks, num_tiles;
   int iw, ih;                        // staged input tile (pixels)
   int in_bytes, w_bytes, buf_bytes;  // per buffer: input tile, filter slab, total (128-byte multiples)
 };
 
 template <int K, int S>
-__global__ void __launch_bounds__(256, (K == 3 && S == 1) ? 2 : 1) dwconv_tile_kernel(const __grid_constant__ DwTileParams p) {
-  constexpr int RH = S == 1 ? 8 : 4;          // output rows per thread
-  constexpr int IHT = (RH - 1) * S + K;       // input rows one thread walks over
+__global__ void __launch_bounds__(256, 1) dwconv_tile_kernel(const __grid_constant__ DwTileParams p) {
   constexpr int W = (K - 1) / S + 1;          // output rows in flight per thread
+  const int RH = p.rh;                        // output rows per thread (<= 8 for stride 1, <= 4 for stride 2)
+  const int IHT = (RH - 1) * S + K;           // input rows one thread walks over
   extern __shared__ uint8_t dw_smem_raw[];
   const uint32_t raw = smem_u32(dw_smem_raw);
   const uint32_t base = (raw + 127u) & ~127u;
@@ -363,6 +363,28 @@ __global__ void __launch_bounds__(256, (K == 3 && S == 1) ? 2 : 1) dwconv_tile_k
     const int oh0 = ty * tho + rgi * RH;
     const bool live = ow < p.wo && ch < p.c;
     __nv_bfloat16* yout = p.y + (((long long)img * p.ho + oh0) * p.wo + ow) * p.yp + ch;
+    // The block's filter moves from shared memory to REGISTERS once per tile: read per use, the 8 lanes of a
+    // quarter-warp fetch 8 different 32-byte rows (2 wavefronts x 4 quarters per load) and the filter reads
+    // were 90 % of the shared-memory traffic (ncu r01s8: 60 % of all wavefronts were bank conflicts, issue
+    // slots 24 % busy). K = 3: fp32 (72 registers); K = 5: bf16 pairs (100 registers, one rounding of the
+    // BN-folded filter, the same rounding the dense convolutions apply to theirs).
+    constexpr int WREG = K == 3 ? 8 : 4;
+    uint32_t wr[K * K][WREG];
+#pragma unroll
+    for (int tp = 0; tp < K * K; ++tp) {
+      const float4 w0 = *reinterpret_cast<const float4*>(wsm + tp * 64);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsm + tp * 64 + 4);
+      if constexpr (K == 3) {
+        wr[tp][0] = __float_as_uint(w0.x), wr[tp][1] = __float_as_uint(w0.y), wr[tp][2] = __float_as_uint(w0.z);
+        wr[tp][3] = __float_as_uint(w0.w), wr[tp][4] = __float_as_uint(w1.x), wr[tp][5] = __float_as_uint(w1.y);
+        wr[tp][6] = __float_as_uint(w1.z), wr[tp][7] = __float_as_uint(w1.w);
+      } else {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(w0.x, w0.y), bq = __floats2bfloat162_rn(w0.z, w0.w);
+        const __nv_bfloat162 cq = __floats2bfloat162_rn(w1.x, w1.y), dq = __floats2bfloat162_rn(w1.z, w1.w);
+        wr[tp][0] = *reinterpret_cast<const uint32_t*>(&a), wr[tp][1] = *reinterpret_cast<const uint32_t*>(&bq);
+        wr[tp][2] = *reinterpret_cast<const uint32_t*>(&cq), wr[tp][3] = *reinterpret_cast<const uint32_t*>(&dq);
+      }
+    }
 #pragma unroll 1
     for (int j = 0; j < RH + W - 1; ++j) {
 #pragma unroll
@@ -377,16 +399,19 @@ __global__ void __launch_bounds__(256, (K == 3 && S == 1) ? 2 : 1) dwconv_tile_k
 #pragma unroll
             for (int r = sr; r < K; r += S) {
               const int d = (r - sr) / S;
-              const float4 w0 = *reinterpret_cast<const float4*>(wsm + (r * K + q) * 64);
-              const float4 w1 = *reinterpret_cast<const float4*>(wsm + (r * K + q) * 64 + 4);
-              win[d][0] = fmaf(f[0], w0.x, win[d][0]);
-              win[d][1] = fmaf(f[1], w0.y, win[d][1]);
-              win[d][2] = fmaf(f[2], w0.z, win[d][2]);
-              win[d][3] = fmaf(f[3], w0.w, win[d][3]);
-              win[d][4] = fmaf(f[4], w1.x, win[d][4]);
-              win[d][5] = fmaf(f[5], w1.y, win[d][5]);
-              win[d][6] = fmaf(f[6], w1.z, win[d][6]);
-              win[d][7] = fmaf(f[7], w1.w, win[d][7]);
+              float w8[8];
+              if constexpr (K == 3) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w8[e] = __uint_as_float(wr[r * K + q][e]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  w8[2 * e] = __uint_as_float(wr[r * K + q][e] << 16);
+                  w8[2 * e + 1] = __uint_as_float(wr[r * K + q][e] & 0xffff0000u);
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) win[d][e] = fmaf(f[e], w8[e], win[d][e]);
             }
           }
         }
@@ -412,7 +437,7 @@ __global__ void __launch_bounds__(256, (K == 3 && S == 1) ? 2 : 1) dwconv_tile_k
 template <int K, int S>
 static int launch_dw_tile(const void* x, const float* wgt, const float* bias, void* y, int n, int h, int w, int c,
                           int pad, int ho, int wo, int xp, int yp, int wp, int act, cudaStream_t st) {
-  constexpr int RH = S == 1 ? 8 : 4;
+  constexpr int RH_MAX = S == 1 ? 8 : 4;
   DwTileParams p;
   memset(&p, 0, sizeof(p));
   p.bias = bias;
@@ -420,7 +445,12 @@ static int launch_dw_tile(const void* x, const float* wgt, const float* bias, vo
   p.h = h, p.w = w, p.c = c, p.ho = ho, p.wo = wo, p.yp = yp, p.pad = pad, p.act = act;
   p.two = wo >= 24 ? 32 : (wo >= 12 ? 16 : 8);
   p.rg = 32 / p.two;
-  const int tho = p.rg * RH;
+  // rows per thread: as many as fit RH_MAX while wasting as few tile rows as possible (7x7 maps: 4 row groups x 2)
+  {
+    const int tiles_y = ceil_div(ho, p.rg * RH_MAX);
+    p.rh = std::max(1, ceil_div(ceil_div(ho, tiles_y), p.rg));
+  }
+  const int tho = p.rg * p.rh;
   p.tiles_x = ceil_div(wo, p.two);
   p.tiles_y = ceil_div(ho, tho);
   p.cblocks = ceil_div(c, 64);
@@ -463,8 +493,7 @@ static int launch_dw_tile(const void* x, const float* wgt, const float* bias, vo
     EQXV_CUDA(cudaFuncSetAttribute(dwconv_tile_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_done = true;
   }
-  const int per_sm = std::max(1, std::min(2, 232448 / (smem + 1024)));
-  const int grid = std::min(p.num_tiles, device_sm_count() * per_sm);
+  const int grid = std::min(p.num_tiles, device_sm_count());   // one persistent CTA per SM (filter in registers)
   EQXV_CUDA(launch_kernel(dwconv_tile_kernel<K, S>, dim3(grid), dim3(256), (size_t)smem, st, p));
   return EQXV_OK;
 }
@@ -473,10 +502,9 @@ static int launch_dw_tile(const void* x, const float* wgt, const float* bias, vo
 
 using namespace eqxv;
 
-extern "C" int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const float* bias, void* y,
-                                       int32_t n, int32_t h, int32_t w, int32_t c, int32_t k,
-                                       int32_t stride, int32_t pad, int32_t dil, int32_t x_pitch,
-                                       int32_t y_pitch, int32_t w_pitch, int32_t act, void* stream) {
+static int dwconv_impl(const void* x, const float* wgt, const float* bias, void* y, int32_t n, int32_t h, int32_t w,
+                       int32_t c, int32_t k, int32_t stride, int32_t pad, int32_t dil, int32_t x_pitch,
+                       int32_t y_pitch, int32_t w_pitch, int32_t act, void* stream, bool force_tile) {
   EQXV_CHECK_ARG(x && wgt && bias && y && n > 0 && h > 0 && w > 0 && c > 0, "dwconv: bad arguments");
   EQXV_CHECK_ARG(c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && w_pitch % 4 == 0 && x_pitch >= c &&
                      y_pitch >= c && w_pitch >= c,
@@ -490,14 +518,19 @@ extern "C" int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
   __nv_bfloat16* yo = (__nv_bfloat16*)y;
-  // shared-memory stencil path (TMA-staged halo tiles); EQXV_NO_DWTILE=1 falls back to the register strips
-  static const bool no_tile = getenv("EQXV_NO_DWTILE") != nullptr;
-  if (!no_tile && dil == 1 && (k == 3 || k == 5) && ((uintptr_t)x & 15) == 0 && ((uintptr_t)wgt & 15) == 0 &&
+  // Shared-memory stencil path (TMA-staged halo tiles): opt-in (EQXV_DWTILE=1 or eqxv_dwconv_tile_bf16)
+  // until it beats the register strips on every EfficientNet/MobileNet shape (tools/bench_dw.py).
+  static const bool use_tile = getenv("EQXV_DWTILE") != nullptr;
+  if ((use_tile || force_tile) && dil == 1 && (k == 3 || k == 5) && ((uintptr_t)x & 15) == 0 && ((uintptr_t)wgt & 15) == 0 &&
       w_pitch % 4 == 0 && 2 * pad <= k) {
     if (k == 3 && stride == 1) return launch_dw_tile<3, 1>(x, wgt, bias, y, n, h, w, c, pad, ho, wo, x_pitch, y_pitch, w_pitch, act, st);
     if (k == 3 && stride == 2) return launch_dw_tile<3, 2>(x, wgt, bias, y, n, h, w, c, pad, ho, wo, x_pitch, y_pitch, w_pitch, act, st);
     if (k == 5 && stride == 1) return launch_dw_tile<5, 1>(x, wgt, bias, y, n, h, w, c, pad, ho, wo, x_pitch, y_pitch, w_pitch, act, st);
     if (k == 5 && stride == 2) return launch_dw_tile<5, 2>(x, wgt, bias, y, n, h, w, c, pad, ho, wo, x_pitch, y_pitch, w_pitch, act, st);
+  }
+  if (force_tile) {
+    set_error("dwconv: the shared-memory stencil kernel needs k in {3,5}, dilation 1, 16-byte aligned operands");
+    return EQXV_ERR_UNSUPPORTED;
   }
 #define EQXV_DWS(K, S, TW)                                                                          \
   EQXV_CUDA(launch_kernel(dwconv_strip_kernel<K, S, TW>,                                            \
@@ -543,6 +576,20 @@ extern "C" int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const fl
 #undef EQXV_DW
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
+}
+
+extern "C" int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const float* bias, void* y,
+                                       int32_t n, int32_t h, int32_t w, int32_t c, int32_t k,
+                                       int32_t stride, int32_t pad, int32_t dil, int32_t x_pitch,
+                                       int32_t y_pitch, int32_t w_pitch, int32_t act, void* stream) {
+  return dwconv_impl(x, wgt, bias, y, n, h, w, c, k, stride, pad, dil, x_pitch, y_pitch, w_pitch, act, stream, false);
+}
+
+extern "C" int eqxv_dwconv_tile_bf16(const void* x, const float* wgt, const float* bias, void* y, int32_t n,
+                                     int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad,
+                                     int32_t dil, int32_t x_pitch, int32_t y_pitch, int32_t w_pitch, int32_t act,
+                                     void* stream) {
+  return dwconv_impl(x, wgt, bias, y, n, h, w, c, k, stride, pad, dil, x_pitch, y_pitch, w_pitch, act, stream, true);
 }
 
 extern "C" int eqxv_eltwise_bf16(const void* x, const float* scale, const float* shift, const void* other,

@@ -177,6 +177,136 @@ __device__ __forceinline__ uint4 epilogue8(const float* v, const float* bias_sme
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// ============================== epilogue, four warps (epi_sub == 1) ==============================
+// One warp per TMEM lane quadrant, tile-major loop, double-buffered staging slab per warp. Used where the
+// K loop hides the epilogue (first layer, halo kernel, deep-K residual GEMMs): it is measurably leaner per
+// chunk than the generic two-warps-per-quadrant loop below (first layer 183 vs 205 us on B200).
+template <bool kOutF32, int kAct, int kRes, bool kPair = false>
+__device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
+                                               const uint32_t tmem_base, const int warp, const int lane) {
+  const int S = p.stages;
+  const int t_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // persistent schedule of this CTA
+  const int t_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t bars = base + p.off_bars;
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  {
+    // ============================== epilogue (warps 2..5) ==============================
+    // Every warp owns the 32 accumulator rows of its TMEM lane quadrant as an independent slab:
+    // its own staging buffers, its own TMA stores / residual loads (issued by an elected lane) and
+    // its own mbarriers. There is no CTA-wide barrier on this path, so one warp waiting on a TMA
+    // store or a residual tile never stalls the other three.
+    constexpr int CH = kOutF32 ? 32 : 64;  // columns per staged chunk (128 B per row)
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int cpt = (p.block_n + CH - 1) / CH;
+    const float* s_bias = reinterpret_cast<const float*>(gbase + p.off_bias);
+    constexpr bool has_res = kRes != 0;
+    constexpr bool res_after_act = kRes == 2;
+    // slab origin inside the (tn, th, tw) tile: rows are ordered n, h, w (w fastest)
+    const int so = quad * 32;
+    const int w_off = so % p.tw, h_off = (so / p.tw) % p.th, n_off = so / (p.tw * p.th);
+    constexpr uint32_t kSlab = 32 * 128;  // 4 KiB per warp per buffer
+    const uint32_t out_u32 = base + p.off_out + quad * kSlab;   // + buf * kStageBuf
+    const uint32_t res_u32 = base + p.off_res + quad * kSlab;
+    uint8_t* out_g = gbase + p.off_out + quad * kSlab;
+    const uint8_t* res_g = gbase + p.off_res + quad * kSlab;
+    auto rbar = [&](uint32_t b) { return bars + 8u * (48u + (uint32_t)quad * 2u + b); };
+
+    auto issue_res = [&](uint32_t gg) {  // called by ONE lane
+      const int ti = gg / cpt, c = gg - ti * cpt;
+      const long long tile = (long long)t_first + (long long)ti * t_stride;
+      if (tile >= p.num_tiles) return;
+      const TileCoord t = decode_tile<kPair>(p, (int)tile);
+      const uint32_t b = gg & 1u;
+      mbar_expect_tx(rbar(b), kSlab);
+      tma_load_4d(res_u32 + b * kStageBuf, &p.tmR, rbar(b), t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
+                  t.n0 + n_off);
+    };
+
+    uint32_t g = 0;
+    if (has_res && lane == 0) {
+      issue_res(0);
+      issue_res(1);
+    }
+    __syncwarp();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = t_first; tile < p.num_tiles; tile += t_stride) {
+      const TileCoord t = decode_tile<kPair>(p, tile);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_stride);
+
+      for (int c = 0; c < cpt; ++c, ++g) {
+        const uint32_t buf = g & 1u;
+        const uint32_t rphase = (g >> 1) & 1u;
+        const int ncols = min(CH, p.block_n - c * CH);
+        float v[CH];
+#pragma unroll
+        for (int j = 0; j < CH / 16; ++j) {
+          if (j * 16 < ncols) {
+            tmem_ld_x16(t_acc + (uint32_t)(c * CH + j * 16), &v[j * 16]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[j * 16 + q] = 0.f;
+          }
+        }
+        tmem_ld_wait();
+        if (c == cpt - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
+          tc_fence_before();
+          if constexpr (kPair) {
+            mbar_arrive_leader(tempty_bar(acc));   // the leader's issuer waits for both CTAs' epilogues
+          } else {
+            mbar_arrive(tempty_bar(acc));
+          }
+        }
+        const float* bias_c = s_bias + t.ncol0 + c * CH;
+        uint8_t* out_row = out_g + buf * kStageBuf;
+        if constexpr (!kOutF32) {
+          uint4 packed[8];
+          if (has_res) mbar_wait(rbar(buf), rphase);
+          const uint8_t* res_row = res_g + buf * kStageBuf;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (has_res) rv = *reinterpret_cast<const uint4*>(res_row + sw128_off(lane, j));
+            packed[j] = epilogue8<kAct, kRes>(&v[j * 8], bias_c + j * 8, rv);
+          }
+          if (lane == 0) tma_store_wait_read<1>();  // this warp's store that last used out[buf] is done
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(out_row + sw128_off(lane, j)) = packed[j];
+        } else {
+#pragma unroll
+          for (int q = 0; q < CH; ++q) v[q] = apply_act<kAct>(v[q] + bias_c[q]);
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(out_row + sw128_off(lane, j)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&p.tmC, out_u32 + buf * kStageBuf, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
+                       t.n0 + n_off);
+          tma_store_commit();
+          if (has_res) issue_res(g + 2);
+        }
+        __syncwarp();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
+  }
+}
+
+
 // ============================== epilogue (warps 2..) ==============================
 // Shared by the generic implicit-GEMM kernel, the CTA-pair kernel, the halo kernel and the first-layer
 // kernel. EIGHT warps (kEpiWarps): two per TMEM lane quadrant (a warp may only touch the 32 lanes
@@ -191,6 +321,10 @@ __device__ __forceinline__ uint4 epilogue8(const float* v, const float* bias_sme
 template <bool kOutF32, int kAct, int kRes, bool kPair = false>
 __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
                                                const uint32_t tmem_base, const int warp, const int lane) {
+  if (p.epi_sub == 1) {   // CTA-uniform
+    epilogue_warps_x4<kOutF32, kAct, kRes, kPair>(p, base, gbase, tmem_base, warp, lane);
+    return;
+  }
   const int S = p.stages;
   const int t_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // persistent schedule of this CTA
   const int t_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -199,7 +333,7 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
   constexpr int CH = kOutF32 ? 32 : 64;  // columns per staged chunk (128 B per row)
   const int quad = warp & 3;             // TMEM lane quadrant this warp may access
-  const int nsub = p.epi_sub;            // warps per quadrant (1 or 2)
+  const int nsub = p.epi_sub;            // warps per quadrant (2 here)
   const int sub = ((warp - 2) >> 2) % nsub;
   const int wid = quad * nsub + sub;     // private slab index
   const int cpt = (p.block_n + CH - 1) / CH;
@@ -243,10 +377,15 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
   __syncwarp();
   int cur_ti = -1;   // last tile whose accumulator this warp has seen complete
   int ti = sub / cpt, c = sub - ti * cpt;   // chunk g = nsub*l + sub, advanced incrementally
+  int dec_ti = -1;
+  TileCoord t{};
   for (uint32_t l = 0;; ++l) {
-    // tile coordinates (integer divisions) are resolved BEFORE the accumulator wait, off the critical path;
-    // a tile index past the end decodes to harmless numbers and is never used
-    const TileCoord t = decode_tile<kPair>(p, t_first + ti * t_stride);
+    // tile coordinates (integer divisions) are resolved once per tile and BEFORE the accumulator wait, off
+    // the critical path; a tile index past the end decodes to harmless numbers and is never used
+    if (ti != dec_ti) {
+      t = decode_tile<kPair>(p, t_first + ti * t_stride);
+      dec_ti = ti;
+    }
     bool done = false;
     while (cur_ti < ti) {   // step over tiles (a tile without a chunk of this warp is released at once)
       ++cur_ti;
@@ -1194,9 +1333,9 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   // epilogue warps per TMEM lane quadrant; every warp owns 2 residual slabs, the 8 staging slabs are shared out
   static const int forced_sub = getenv("EQXV_EPI_SUB") ? atoi(getenv("EQXV_EPI_SUB")) : 0;
   // Two warps per quadrant where the epilogue bounds the tile (shallow K: ResNet c3 / downsample layers went
-  // from 78 % to 99 % of their HBM roofline); one where the K loop hides it anyway and the shared memory
-  // of the second residual ring is better spent on operand stages (ViT GEMMs, 3x3 layers).
-  p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : (kblocks <= 8 ? 2 : 1);
+  // from 78 % to 99 % of their HBM roofline) and wherever it costs no shared memory (no residual); one where
+  // the K loop hides it and the second residual ring would cost an operand stage (deep-K residual GEMMs).
+  p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : ((kblocks <= 8 || !p.has_res) ? 2 : 1);
   const int fixed = 2 * kStageBuf + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
   int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
   stages = std::min(stages, 8);

@@ -45,6 +45,8 @@ __global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict
   griddep_launch();
   const int hp = h + 2 * pad, wp = w + 8;
   const long long total = (long long)n * hp * wp;
+  // one output pixel (16 bytes) per thread: measured faster on B200 than 4 pixels per thread, consecutive
+  // (uncoalesced stores, 2x slower) or grid-strided (1.2x slower)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int pw = (int)(i % wp);

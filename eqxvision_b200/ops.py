@@ -198,14 +198,16 @@ def gather_rows(x, n, tokens, row, out=None, stream=0):
     return out
 
 
-def dwconv(x, wgt, bias, *, k, stride=1, pad=0, dil=1, act=0, out=None, stream=0):
-    """depthwise conv; x [N,H,W,C] bf16 view, wgt fp32 [k*k, w_pitch], bias fp32 [C]"""
+def dwconv(x, wgt, bias, *, k, stride=1, pad=0, dil=1, act=0, out=None, tile=False, stream=0):
+    """depthwise conv; x [N,H,W,C] bf16 view, wgt fp32 [k*k, w_pitch], bias fp32 [C];
+    tile=True forces the shared-memory stencil kernel (eqxv_dwconv_tile_bf16)"""
     _check_cuda(x, wgt, bias, out)
     n, h, w, c = x.shape
     ho, wo = conv_out_size(h, k, stride, pad, dil), conv_out_size(w, k, stride, pad, dil)
     if out is None:
         out = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
-    call("eqxv_dwconv_bn_act_bf16", ptr(x), ptr(wgt), ptr(bias), ptr(out), n, h, w, c, k, stride, pad, dil,
+    call("eqxv_dwconv_tile_bf16" if tile else "eqxv_dwconv_bn_act_bf16", ptr(x), ptr(wgt), ptr(bias), ptr(out),
+         n, h, w, c, k, stride, pad, dil,
          x.stride(2), out.stride(2), wgt.stride(0), act, stream)
     return out
 

@@ -159,6 +159,11 @@ int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const float* bias, 
                             int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad,
                             int32_t dil, int32_t x_pitch, int32_t y_pitch, int32_t w_pitch, int32_t act,
                             void* stream);
+/* Same contract, forced through the shared-memory stencil kernel (TMA-staged halo tile of a 64-channel block,
+ * sliding accumulator window; k in {3,5}, dilation 1). eqxv_dwconv_bn_act_bf16 picks it when EQXV_DWTILE=1. */
+int eqxv_dwconv_tile_bf16(const void* x, const float* wgt, const float* bias, void* y, int32_t n, int32_t h,
+                          int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad, int32_t dil,
+                          int32_t x_pitch, int32_t y_pitch, int32_t w_pitch, int32_t act, void* stream);
 /* K8/K11/K15: y = act(x * scale[c] + shift[c] + other) * gate[row / rows_per_image, c]; every operand
  * except x may be NULL. Standalone BatchNorm+ReLU (densenet.py:64-65,118,211), unfused residual adds,
  * the SqueezeExcitation gate `x * scale` (layers/squeeze.py:61). */

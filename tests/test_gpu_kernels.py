@@ -271,8 +271,12 @@ def test_stem_conv_variants(device, kh, kw, stride, pad, cin, cout, hw):
                                                    (64, 56, 3, 1, 1, 2), (24, 33, 3, 2, 1, 2), (200, 15, 3, 1, 1, 1),
                                                    (136, 29, 5, 2, 1, 4), (8, 9, 5, 1, 1, 0), (1632, 7, 5, 1, 1, 2),
                                                    (672, 14, 5, 2, 1, 2), (32, 112, 3, 1, 1, 2), (88, 25, 3, 2, 1, 6)])
-def test_depthwise(device, c, hw, k, stride, dil, act):
+@pytest.mark.parametrize("tile", [False, True], ids=["strip", "smem_stencil"])
+def test_depthwise(device, c, hw, k, stride, dil, act, tile):
     from eqxvision_b200 import _pack, ops
+
+    if tile and dil != 1:
+        pytest.skip("the shared-memory stencil kernel is dilation-1 only")
 
     n = 3
     pad = (k - 1) // 2 * dil
@@ -281,7 +285,7 @@ def test_depthwise(device, c, hw, k, stride, dil, act):
     wt = torch.randn(c, 1, k, k, generator=g) * (k * k) ** -0.5
     bias = torch.randn(c, generator=g)
     y = ops.dwconv(x, _pack.pack_depthwise_weight(wt, c).to(device), bias.to(device), k=k, stride=stride, pad=pad,
-                   dil=dil, act=act)
+                   dil=dil, act=act, tile=tile)
     ref = ACTS[act](F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(device), bias.to(device), stride=stride,
                              padding=pad, dilation=dil, groups=c))
     assert rel_l2(y, ref.permute(0, 2, 3, 1)) < TOL_BF16
