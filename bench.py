@@ -276,6 +276,7 @@ def cpu_port(name, sd, batch, iters):
     """bounded CPU sample; returns (img/s, cores, sample)"""
     import torch
 
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     fn = oracle_forward(name, sd, batch)
     with torch.no_grad():
         fn()  # warm-up
@@ -293,6 +294,8 @@ def run_reference_arm(args, rank):
         return
     import torch
 
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm uses all host cores explicitly
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     name = args.model
     hw = MODELS[name]["hw"]
     sd = synthetic_state_dict(name)
