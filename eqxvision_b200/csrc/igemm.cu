@@ -803,7 +803,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 // Call sites replaced: resnet.py:243-251 (7x7 s2), vgg.py:137 (3x3 s1), efficientnet.py:327 /
 // mobilenetv3.py:193 (3x3 s2), swin.py:705-713 (4x4 s4).
 constexpr int kStemProducers = 4;                       // warps 0, 6, 7, 8
-constexpr int kStemThreads = 192 + 32 * (kStemProducers - 1);   // warps 0 (producer), 1 (MMA), 2..5 epilogue, 6..8 producers
+constexpr int kStemThreads = kThreads + 32 * (kStemProducers - 1);   // warps 0 (producer), 1 (MMA), 2..9 epilogue, 10..12 producers
+                                                                   // (epi_sub == 1: 2..5 epilogue, 6..8 producers, 288 threads)
 
 // The halo tile is gathered with cp.async: its natural granule is one pixel (16 B), which a TMA box can
 // only move as one request per pixel (measured ~5900 cycles per tile). Here a warp instruction moves
@@ -905,7 +906,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
   }
   {
     float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
-    for (int i = threadIdx.x; i < p.block_n + 64; i += kStemThreads)
+    for (int i = threadIdx.x; i < p.block_n + 64; i += blockDim.x)
       sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
   }
   if (warp == 1) {
@@ -979,10 +980,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else if (warp < 2 + 4 * p.epi_sub) {
     epilogue_warps<false, kAct, 0>(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
   } else {
-    stem_gather(p, base, warp - 5);  // producer warps 1..3
+    stem_gather(p, base, warp - (1 + 4 * p.epi_sub));  // producer warps 1..3
   }
 
   tc_fence_before();
@@ -1120,6 +1121,41 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
       uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.b_resident && kh == 3 && kw == 3 && kchunks == 1) {
+        // Lean path for the resident 3x3 filter (ResNet layer1, VGG, DenseNet 64-channel layers): the generic
+        // loop below spends ~60 SASS instructions per tap on ring bookkeeping, barrier waits and
+        // register->uniform-register moves against 128 tensor-pipe cycles of work (4 MMAs of N = 64): the
+        // issuing thread, not the tensor pipe, bounded the kernel (ncu r01s12: tensor pipe 33 % active).
+        // Here the nine taps are straight-line code: constant filter descriptors, no waits, no commits.
+        for (int sl = 0; sl < 9; ++sl) mbar_wait(full_bar(sl), 0u);   // the filter has landed (once per CTA)
+        tc_fence_after();
+        const uint32_t stage_step = (uint32_t)p.h_stage_bytes >> 4;
+        const uint32_t a_base0 = ((a_smem & 0x3FFFF) >> 4) | lbo;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          mbar_wait(afull_bar(sa), pa);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+          const uint32_t a0 = a_base0 + (uint32_t)sa * stage_step;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int s2 = 0; s2 < 3; ++s2) {
+              umma_bf16_kblock64_nc(d_tmem, a0 + (uint32_t)r * row_step + (uint32_t)s2 * col_step,
+                                    b_lo0 + (uint32_t)(r * 3 + s2) * bstep, a_hi, b_hi, idesc,
+                                    (r | s2) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(aempty_bar(sa));
+          umma_commit(tfull_bar(acc));
+          if (++sa == SA) {
+            sa = 0;
+            pa ^= 1u;
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
@@ -1479,7 +1515,10 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
   const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
   EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "conv: cout %d too large for the bias staging area", d->cout);
   static const int forced_sub = getenv("EQXV_EPI_SUB") ? atoi(getenv("EQXV_EPI_SUB")) : 0;
-  p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : 1;   // K >= 9 blocks: the MMA loop bounds the tile
+  // K >= 9 blocks: the MMA loop bounds the tile, except on the lean resident-filter path (N = 64: ~1150
+  // tensor cycles per tile against a ~2000-cycle epilogue chain per warp), which gets two warps per quadrant
+  const bool lean = d->kh == 3 && d->kw == 3 && kchunks == 1 && block_n <= 64 && p.n_tiles == 1;
+  p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : (lean ? 2 : 1);
   const int fixed = 2 * kStageBuf + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
   int sa = 3;
   int sb = (kMaxSmem - 1024 - fixed - sa * p.h_stage_bytes) / b_slab;
@@ -1709,7 +1748,11 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
     p.h_off_b = stages * p.h_stage_bytes;
     p.off_out = p.h_off_b + b_bytes;
     p.off_res = p.off_out + 2 * kStageBuf;
-    p.epi_sub = 1;   // first layer: N = 64 is one chunk per tile; the extra warps are cp.async producers
+    // N = 64 is one chunk per tile and 28 MMAs (~900 tensor cycles): with one epilogue warp per quadrant its
+    // ~2000-cycle chain per tile bounded the kernel (188 us against 98 us of HBM traffic); two warps per
+    // quadrant take alternate tiles.
+    static const int stem_sub = getenv("EQXV_STEM_SUB") ? atoi(getenv("EQXV_STEM_SUB")) : 0;
+    p.epi_sub = stem_sub == 1 ? 1 : 2;
     p.off_bias = p.off_res;
     p.off_bars = p.off_bias + bias_bytes;
     const int smem_bytes = p.off_bars + 256 + 1024;
@@ -1743,7 +1786,7 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
     rc = encode_tmap(&p.tmC, c);
     if (rc) return rc;
     const int grid = std::min(p.num_tiles, device_sm_count());
-    EQXV_CUDA(launch_kernel(stem_table(act), dim3(grid), dim3(kStemThreads), (size_t)(smem_bytes), (cudaStream_t)stream, p));
+    EQXV_CUDA(launch_kernel(stem_table(act), dim3(grid), dim3(64 + 128 * p.epi_sub + 32 * (kStemProducers - 1)), (size_t)(smem_bytes), (cudaStream_t)stream, p));
     EQXV_CUDA(cudaGetLastError());
     return EQXV_OK;
   }
