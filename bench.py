@@ -188,47 +188,65 @@ def measure(name, model, batch, steps, warmup, dist, rank):
     ms = timed(lambda: plan.launch(st))
 
     # (2) end to end through host buffers: every step copies its own pinned fp32 NCHW batch to the
-    # device, replays the graph and copies the logits back. Two plans (own buffers, own stream) are
-    # alternated so that the H2D copy of step i+1 overlaps the kernels of step i (copy engine vs SMs).
+    # device, replays the graph and copies the logits back. LANES plans (own buffers, own stream) are used
+    # round-robin so that the H2D copy of step i+1 overlaps the kernels of step i (copy engine vs SMs);
+    # graph launches are chained with events across lanes (compute runs FIFO, never two graphs interleaved:
+    # interleaving delays the completion of BOTH graphs and with it the next copies).
     nbytes_in = host_in.numel() * 4
     nbytes_out = sum(o.numel() * o.element_size() for o, _ in outs1)
-    plan2 = _engine.build_plan(model, "__call__", batch, in_shape, (), {"key": eb.random.PRNGKey(0)})
-    st2 = C.c_void_p()
-    _lib.call("eqxv_stream_create", C.byref(st2))
-    st2 = st2.value
-    lanes = [(plan, st, outs1), (plan2, st2, host_mirrors(plan2))]
+    n_lanes = int(os.environ.get("EQXV_E2E_LANES", "3"))
+    lanes = [(plan, st, outs1)]
+    for _ in range(n_lanes - 1):
+        pl = _engine.build_plan(model, "__call__", batch, in_shape, (), {"key": eb.random.PRNGKey(0)})
+        sx = C.c_void_p()
+        _lib.call("eqxv_stream_create", C.byref(sx))
+        lanes.append((pl, sx.value, host_mirrors(pl)))
     counter = [0]
+    graph_done = [None]
+    ev_ring = [ev() for _ in range(8)]
 
     def e2e_step():
-        pl, s, outs = lanes[counter[0] & 1]
+        pl, s, outs = lanes[counter[0] % n_lanes]
         counter[0] += 1
         _lib.call("eqxv_memcpy_h2d_async", pl.x_in.data_ptr(), host_in.data_ptr(), nbytes_in, s)
+        if graph_done[0] is not None:
+            _lib.call("eqxv_stream_wait_event", s, graph_done[0])   # FIFO on the SMs
         pl.launch(s)
+        e = ev_ring[counter[0] % len(ev_ring)]
+        _lib.call("eqxv_event_record", e, s)
+        graph_done[0] = e
         for o, ho in outs:
             _lib.call("eqxv_memcpy_d2h_async", ho.data_ptr(), o.data_ptr(), o.numel() * o.element_size(), s)
 
-    def timed_two_streams():
-        for _ in range(max(warmup, 2)):
+    def sync_lanes():
+        for _, s, _ in lanes:
+            _lib.call("eqxv_stream_sync", s)
+
+    def timed_lanes():
+        for _ in range(max(warmup, n_lanes)):
             e2e_step()
-        _lib.call("eqxv_stream_sync", st2)
+        sync_lanes()
         barrier()
-        e0, e1, j = ev(), ev(), ev()
+        e0, e1 = ev(), ev()
         _lib.call("eqxv_event_record", e0, st)
-        _lib.call("eqxv_stream_wait_event", st2, e0)   # both lanes start after e0
+        for _, s, _ in lanes[1:]:
+            _lib.call("eqxv_stream_wait_event", s, e0)   # every lane starts after e0
         for _ in range(steps):
             e2e_step()
-        _lib.call("eqxv_event_record", j, st2)
-        _lib.call("eqxv_stream_wait_event", st, j)     # e1 is after the last step of BOTH lanes
+        for _, s, _ in lanes[1:]:                        # e1 is after the last step of EVERY lane
+            j = ev()
+            _lib.call("eqxv_event_record", j, s)
+            _lib.call("eqxv_stream_wait_event", st, j)
         _lib.call("eqxv_event_record", e1, st)
         _lib.call("eqxv_event_sync", e1)
-        _lib.call("eqxv_stream_sync", st2)
+        sync_lanes()
         barrier()
         ms_ = C.c_float()
         _lib.call("eqxv_event_elapsed_ms", e0, e1, C.byref(ms_))
         return ms_.value / steps
 
-    e2e_ms = timed_two_streams()
-    del plan2
+    e2e_ms = timed_lanes()
+    del lanes[1:]
 
     # (3) per-launch device time of the igemm (conv / linear) launches, eager replay with events
     igemm_fns = (ops.conv2d, ops.gemm, ops.conv_stem, ops.conv_stem7x7)

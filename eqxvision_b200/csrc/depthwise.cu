@@ -12,6 +12,22 @@ namespace eqxv {
 
 constexpr int kDwThreads = 256;
 
+// Grid-stride loop over `total` work items with a 32-bit index whenever it fits: the index decomposition
+// (i % groups, / wo, % ho ...) costs 3-4 divisions per item, and 64-bit integer division is a ~100-instruction
+// software routine -- as much issue time as the arithmetic of a depthwise strip.
+#define EQXV_GRID_STRIDE(total, body)                                                                        \
+  do {                                                                                                       \
+    if ((total) <= 0x7fffffffLL) {                                                                           \
+      for (unsigned i_ = blockIdx.x * blockDim.x + threadIdx.x; i_ < (unsigned)(total);                      \
+           i_ += gridDim.x * blockDim.x)                                                                     \
+        body(i_);                                                                                            \
+    } else {                                                                                                 \
+      for (long long i_ = blockIdx.x * (long long)blockDim.x + threadIdx.x; i_ < (total);                    \
+           i_ += (long long)gridDim.x * blockDim.x)                                                          \
+        body(i_);                                                                                            \
+    }                                                                                                        \
+  } while (0)
+
 struct alignas(16) bf16x8 {
   __nv_bfloat162 v[4];
 };
@@ -72,10 +88,9 @@ __global__ void dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* 
   griddep_launch();
   const int groups = c / 8;
   const long long total = (long long)n * ho * wo * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  auto body = [&](auto i) {
     const int g = (int)(i % groups);
-    long long t = i / groups;
+    auto t = i / groups;
     const int ow = (int)(t % wo);
     t /= wo;
     const int oh = (int)(t % ho);
@@ -123,7 +138,8 @@ __global__ void dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* 
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = act_rt(acc[q], act);
     *reinterpret_cast<uint4*>(y + (((long long)img * ho + oh) * wo + ow) * yp + g * 8) = pack8(acc);
-  }
+  };
+  EQXV_GRID_STRIDE(total, body);
 }
 
 // Strip variant (dilation 1): one thread produces TW horizontally adjacent outputs of 8 channels, so
@@ -141,10 +157,9 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_strip_kernel(
   const int groups = c / 8;
   const int strips = (wo + TW - 1) / TW;
   const long long total = (long long)n * ho * strips * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  auto body = [&](auto i) {
     const int g = (int)(i % groups);
-    long long t = i / groups;
+    auto t = i / groups;
     const int ow0 = (int)(t % strips) * TW;
     t /= strips;
     const int oh = (int)(t % ho);
@@ -207,7 +222,8 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_strip_kernel(
         *reinterpret_cast<uint4*>(y + (((long long)img * ho + oh) * wo + ow0 + o) * yp + g * 8) = pack8(acc[o]);
       }
     }
-  }
+  };
+  EQXV_GRID_STRIDE(total, body);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -224,12 +240,11 @@ __global__ void eltwise_kernel(const __nv_bfloat16* __restrict__ x, const float*
   griddep_launch();
   const int groups = c / 8;
   const long long total = rows * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  auto body = [&](auto i) {
     const int g = (int)(i % groups);
-    const long long row = i / groups;
+    const auto row = i / groups;
     float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * xp + g * 8)), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (long long)row * xp + g * 8)), f);
     if (scale != nullptr) {
       const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
       const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
@@ -242,7 +257,7 @@ __global__ void eltwise_kernel(const __nv_bfloat16* __restrict__ x, const float*
     }
     if (other != nullptr) {
       float o[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(other + row * op + g * 8)), o);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(other + (long long)row * op + g * 8)), o);
 #pragma unroll
       for (int q = 0; q < 8; ++q) f[q] += o[q];
     }
@@ -250,12 +265,13 @@ __global__ void eltwise_kernel(const __nv_bfloat16* __restrict__ x, const float*
     for (int q = 0; q < 8; ++q) f[q] = act_rt(f[q], act);
     if (gate != nullptr) {
       float s[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(gate + (row / rows_per_image) * gp + g * 8)), s);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gate + (long long)(row / rows_per_image) * gp + g * 8)), s);
 #pragma unroll
       for (int q = 0; q < 8; ++q) f[q] *= s[q];
     }
-    *reinterpret_cast<uint4*>(y + row * yp + g * 8) = pack8(f);
-  }
+    *reinterpret_cast<uint4*>(y + (long long)row * yp + g * 8) = pack8(f);
+  };
+  EQXV_GRID_STRIDE(total, body);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,6 +11,22 @@ namespace eqxv {
 
 constexpr int kPwThreads = 256;
 
+// Grid-stride loop over `total` work items with a 32-bit index whenever it fits: the index decomposition
+// (i % groups, / wo, % ho ...) costs 3-4 divisions per item, and 64-bit integer division is a ~100-instruction
+// software routine -- as much issue time as the arithmetic of a depthwise strip.
+#define EQXV_GRID_STRIDE(total, body)                                                                        \
+  do {                                                                                                       \
+    if ((total) <= 0x7fffffffLL) {                                                                           \
+      for (unsigned i_ = blockIdx.x * blockDim.x + threadIdx.x; i_ < (unsigned)(total);                      \
+           i_ += gridDim.x * blockDim.x)                                                                     \
+        body(i_);                                                                                            \
+    } else {                                                                                                 \
+      for (long long i_ = blockIdx.x * (long long)blockDim.x + threadIdx.x; i_ < (total);                    \
+           i_ += (long long)gridDim.x * blockDim.x)                                                          \
+        body(i_);                                                                                            \
+    }                                                                                                        \
+  } while (0)
+
 static inline int grid_for(long long work, int threads = kPwThreads) {
   long long b = (work + threads - 1) / threads;
   const long long cap = (long long)device_sm_count() * 32;
@@ -49,11 +65,11 @@ __global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict
   const long long total = (long long)n * hp * wp;
   // one output pixel (16 bytes) per thread: measured faster on B200 than 4 pixels per thread, consecutive
   // (uncoalesced stores, 2x slower) or grid-strided (1.2x slower)
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  auto body = [&](auto i) {
+    const auto t = i / wp;
     const int pw = (int)(i % wp);
-    const int ph = (int)((i / wp) % hp);
-    const int img = (int)(i / ((long long)wp * hp));
+    const int ph = (int)(t % hp);
+    const int img = (int)(t / hp);
     float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int sh = ph - pad, sw = pw - pad;
     if (sh >= 0 && sh < h && sw >= 0 && sw < w) {
@@ -64,7 +80,8 @@ __global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict
         if (q < c) f[q] = __ldg(src + q * plane);
     }
     y[i] = pack8(f);
-  }
+  };
+  EQXV_GRID_STRIDE(total, body);
 }
 
 // fp32 NCHW -> bf16 NHWC (channels padded with zeros to c_pad)
@@ -128,10 +145,9 @@ __global__ void pool2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
   const int groups = c / 8;
   const long long total = (long long)n * ho * wo * groups;
   const float inv = 1.f / (float)(kh * kw);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  auto body = [&](auto i) {
     const int g = (int)(i % groups);
-    long long t = i / groups;
+    auto t = i / groups;
     const int ow = (int)(t % wo);
     t /= wo;
     const int oh = (int)(t % ho);
@@ -158,7 +174,8 @@ __global__ void pool2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
       for (int q = 0; q < 8; ++q) acc[q] *= inv;
     }
     *reinterpret_cast<bf16x8*>(y + (((long long)img * ho + oh) * wo + ow) * yp + g * 8) = pack8(acc);
-  }
+  };
+  EQXV_GRID_STRIDE(total, body);
 }
 
 // Compile-time window/stride variant: all K*K 16-byte loads of a thread are issued before any is
@@ -170,10 +187,9 @@ __global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
   griddep_launch();
   const int groups = c / 8;
   const long long total = (long long)n * ho * wo * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  auto body = [&](auto i) {
     const int g = (int)(i % groups);
-    long long t = i / groups;
+    auto t = i / groups;
     const int ow = (int)(t % wo);
     t /= wo;
     const int oh = (int)(t % ho);
@@ -212,7 +228,8 @@ __global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
       for (int q = 0; q < 8; ++q) acc[q] *= 1.f / (float)(K * K);
     }
     *reinterpret_cast<bf16x8*>(y + (((long long)img * ho + oh) * wo + ow) * yp + g * 8) = pack8(acc);
-  }
+  };
+  EQXV_GRID_STRIDE(total, body);
 }
 
 // Global average pool (adaptive pool to 1x1: the SE squeeze, the classifier pool, the ASPP pooling
