@@ -1299,7 +1299,12 @@ static KernelFn pair_table(int act, int res_mode) {
   return t[res_mode][act];
 }
 
-static bool g_pair_enabled = getenv("EQXV_NO_PAIR") == nullptr;   // A/B switch for profiling
+// Tuning overrides, read at every launch (i.e. at plan-build / graph-capture time) so that a sweep can change
+// them inside one process (tools/sweep_igemm.py): EQXV_NO_PAIR=1, EQXV_FORCE_PAIR=1, EQXV_BLOCK_N=<n>, EQXV_EPI_SUB=<1|2>.
+static int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
 
 // pair variant: the tile is 256 x bn for two SMs; per SM and K block: 16 KiB of A + bn*64 B of B
 static int choose_block_n_pair(int cout, long long pair_m_tiles, int kblocks, int clusters) {
@@ -1329,13 +1334,17 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
       (long long)ceil_div(q.out_w, q.tw) * ceil_div(q.out_h, q.th) * ceil_div(q.out_n, q.tn);
   const int kblocks = q.kh * q.kw * q.kchunks;
   // CTA pairs pay off when the K loop (not HBM or the epilogue) dominates: deep K, wide N, enough tiles
-  const bool pair = !out_f32 && kblocks >= 4 && q.cout >= 128 && m_tiles >= 2 && q.dil_h == 1 && g_pair_enabled &&
-                    !q.grouped;
+  const bool pair_ok = !out_f32 && q.cout >= 128 && m_tiles >= 2 && q.dil_h == 1 && !q.grouped;
+  const bool pair = pair_ok && !env_int("EQXV_NO_PAIR") && (kblocks >= 4 || env_int("EQXV_FORCE_PAIR"));
   int block_n;
   if (pair) {
     block_n = choose_block_n_pair(q.cout, (m_tiles + 1) / 2, kblocks, device_sm_count() / 2);
   } else {
     block_n = choose_block_n(q.cout, m_tiles, kblocks, device_sm_count());
+  }
+  {
+    const int bn = env_int("EQXV_BLOCK_N");   // multiple of 64 below cout (several n-tiles) -- sweeps only
+    if (bn >= 64 && bn <= 256 && bn % 64 == 0 && bn < q.cout && !(pair && bn >= 2 * q.cout)) block_n = bn;
   }
   if (q.grouped) block_n = 64;   // one n-tile = one 64-channel block of the block-diagonal filter
   p.grouped = q.grouped;
@@ -1367,7 +1376,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
   EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "igemm: cout %d too large for the bias staging area", q.cout);
   // epilogue warps per TMEM lane quadrant; every warp owns 2 residual slabs, the 8 staging slabs are shared out
-  static const int forced_sub = getenv("EQXV_EPI_SUB") ? atoi(getenv("EQXV_EPI_SUB")) : 0;
+  const int forced_sub = env_int("EQXV_EPI_SUB");
   // Two warps per quadrant where the epilogue bounds the tile (shallow K: ResNet c3 / downsample layers went
   // from 78 % to 99 % of their HBM roofline) and wherever it costs no shared memory (no residual); one where
   // the K loop hides it and the second residual ring would cost an operand stage (deep-K residual GEMMs).
@@ -1514,7 +1523,7 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
   const int b_slab = block_n * 128;
   const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
   EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "conv: cout %d too large for the bias staging area", d->cout);
-  static const int forced_sub = getenv("EQXV_EPI_SUB") ? atoi(getenv("EQXV_EPI_SUB")) : 0;
+  const int forced_sub = env_int("EQXV_EPI_SUB");
   // K >= 9 blocks: the MMA loop bounds the tile, except on the lean resident-filter path (N = 64: ~1150
   // tensor cycles per tile against a ~2000-cycle epilogue chain per warp), which gets two warps per quadrant
   const bool lean = d->kh == 3 && d->kw == 3 && kchunks == 1 && block_n <= 64 && p.n_tiles == 1;

@@ -4,6 +4,8 @@
 // the NHWC->NCHW transpose.
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -61,27 +63,22 @@ __global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict
                                  int w, int pad) {
   griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
   griddep_launch();
-  const int hp = h + 2 * pad, wp = w + 8;
-  const long long total = (long long)n * hp * wp;
-  // one output pixel (16 bytes) per thread: measured faster on B200 than 4 pixels per thread, consecutive
-  // (uncoalesced stores, 2x slower) or grid-strided (1.2x slower)
-  auto body = [&](auto i) {
-    const auto t = i / wp;
-    const int pw = (int)(i % wp);
-    const int ph = (int)(t % hp);
-    const int img = (int)(t / hp);
-    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const int sh = ph - pad, sw = pw - pad;
-    if (sh >= 0 && sh < h && sw >= 0 && sw < w) {
-      const long long plane = (long long)h * w;
-      const float* src = x + (long long)img * c * plane + (long long)sh * w + sw;
+  // grid = (column blocks, padded rows, images): no index division at all (with a linear index the
+  // kernel was ALU bound on the div/mod decomposition: issue slots 80 % busy, profiles/r01_ncu_stem_trio_v15.txt)
+  const int wp = w + 8, hp = h + 2 * pad;
+  const int pw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ph = blockIdx.y, img = blockIdx.z;
+  if (pw >= wp) return;
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int sh = ph - pad, sw = pw - pad;
+  if (sh >= 0 && sh < h && sw >= 0 && sw < w) {
+    const long long plane = (long long)h * w;
+    const float* src = x + (long long)img * c * plane + (long long)sh * w + sw;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q < c) f[q] = __ldg(src + q * plane);
-    }
-    y[i] = pack8(f);
-  };
-  EQXV_GRID_STRIDE(total, body);
+    for (int q = 0; q < 8; ++q)
+      if (q < c) f[q] = __ldg(src + q * plane);
+  }
+  y[((long long)img * hp + ph) * wp + pw] = pack8(f);
 }
 
 // fp32 NCHW -> bf16 NHWC (channels padded with zeros to c_pad)
@@ -180,6 +177,9 @@ __global__ void pool2d_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
 
 // Compile-time window/stride variant: all K*K 16-byte loads of a thread are issued before any is
 // consumed (memory-level parallelism), out-of-range taps are predicated instead of branched.
+// The linear grid-stride order (channel vector, column, row fastest-to-slowest, <= 32 CTAs per SM) keeps
+// vertically overlapping windows in the same wave, i.e. in L2: a (column block, row, image) 3-D grid without
+// any index division measured 163 us against 121 us on the ResNet-50 max-pool (B200, ncu).
 template <bool kMax, int K, int S>
 __global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                     int n, int h, int w, int c, int pad, int ho, int wo, int xp, int yp) {
@@ -187,9 +187,10 @@ __global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
   griddep_launch();
   const int groups = c / 8;
   const long long total = (long long)n * ho * wo * groups;
-  auto body = [&](auto i) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i % groups);
-    auto t = i / groups;
+    long long t = i / groups;
     const int ow = (int)(t % wo);
     t /= wo;
     const int oh = (int)(t % ho);
@@ -228,8 +229,7 @@ __global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
       for (int q = 0; q < 8; ++q) acc[q] *= 1.f / (float)(K * K);
     }
     *reinterpret_cast<bf16x8*>(y + (((long long)img * ho + oh) * wo + ow) * yp + g * 8) = pack8(acc);
-  };
-  EQXV_GRID_STRIDE(total, body);
+  }
 }
 
 // Global average pool (adaptive pool to 1x1: the SE squeeze, the classifier pool, the ASPP pooling
@@ -287,6 +287,80 @@ __global__ void __launch_bounds__(256) global_avgpool_kernel(const __nv_bfloat16
     for (int q = 0; q < 8; ++q) tot[q] *= inv;
     *reinterpret_cast<bf16x8*>(y + (long long)img * yp + (g0 + threadIdx.x) * 8) = pack8(tot);
   }
+}
+
+// Cluster variant for large maps: the pixels of one (image, 64-channel slab) are split over the 8 CTAs of a
+// thread-block cluster; every CTA reduces its slice as above, the partial sums meet in the leader through
+// distributed shared memory in rank order (deterministic, no atomics, no scratch buffer). One CTA per slab
+// left the SE squeeze of EfficientNet-B4's 112x112 / 56x56 maps latency bound at ~1 TB/s.
+constexpr int kPoolCluster = 8;
+__global__ void __cluster_dims__(kPoolCluster, 1, 1) __launch_bounds__(256)
+    global_avgpool_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int hw, int c,
+                                  int xp, int yp) {
+  griddep_wait();
+  griddep_launch();
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float red[256][9];
+  __shared__ float part[8][8];                 // this CTA's partial sums: [channel vector][8 channels]
+  const int rank = (int)cluster.block_rank();
+  const int groups = c / 8;
+  const int g0 = (blockIdx.x / kPoolCluster) * 8;
+  const int gc = min(8, groups - g0);
+  const int lanes = 256 / gc;
+  const int img = blockIdx.y;
+  const int gi = threadIdx.x % gc, lane = threadIdx.x / gc;
+  const int per = (hw + kPoolCluster - 1) / kPoolCluster;
+  const int p_lo = rank * per, p_hi = min(hw, p_lo + per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (lane < lanes) {
+    const __nv_bfloat16* base = x + (long long)img * hw * xp + (g0 + gi) * 8;
+    int p = p_lo + lane;
+    for (; p + 3 * lanes < p_hi; p += 4 * lanes) {
+      bf16x8 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const bf16x8*>(base + (long long)(p + u * lanes) * xp);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(r[u], f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += f[q];
+      }
+    }
+    for (; p < p_hi; p += lanes) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)p * xp), f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += f[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) red[threadIdx.x][q] = acc[q];
+  __syncthreads();
+  if (threadIdx.x < gc) {
+    float tot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < lanes; ++l) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot[q] += red[l * gc + threadIdx.x][q];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) part[threadIdx.x][q] = tot[q];
+  }
+  cluster.sync();                              // every CTA's partial sums are visible cluster-wide
+  if (rank == 0 && threadIdx.x < gc) {
+    float tot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < kPoolCluster; ++r) {   // fixed order: bitwise reproducible
+      const float* rp = cluster.map_shared_rank(&part[0][0], r) + threadIdx.x * 8;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot[q] += rp[q];
+    }
+    const float inv = 1.f / (float)hw;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tot[q] *= inv;
+    *reinterpret_cast<bf16x8*>(y + (long long)img * yp + (g0 + threadIdx.x) * 8) = pack8(tot);
+  }
+  cluster.sync();                              // nobody leaves while the leader still reads its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -510,9 +584,10 @@ extern "C" int eqxv_pack_stem_input(const float* x, void* xpad, int32_t n, int32
                                     int32_t pad, void* stream) {
   EQXV_CHECK_ARG(x && xpad && n > 0 && h > 0 && w > 0 && c >= 1 && c <= 8 && pad >= 0 && pad <= 4,
                  "pack_stem_input: bad arguments");
-  const long long total = (long long)n * (h + 2 * pad) * (w + 8);
-  EQXV_CUDA(launch_kernel(pack_stem_kernel, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), (cudaStream_t)stream, 
-      x, reinterpret_cast<bf16x8*>(xpad), n, c, h, w, pad));
+  EQXV_CHECK_ARG(h + 2 * pad <= 65535 && n <= 65535, "pack_stem_input: image too tall / batch too large");
+  EQXV_CUDA(launch_kernel(pack_stem_kernel, dim3((unsigned)((w + 8 + 255) / 256), (unsigned)(h + 2 * pad), (unsigned)n),
+                          dim3(256), (size_t)0, (cudaStream_t)stream, x, reinterpret_cast<bf16x8*>(xpad), n, c, h, w,
+                          pad));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }
@@ -549,21 +624,21 @@ static int pool_common(bool is_max, const void* x, void* y, int n, int h, int w,
   const long long total = (long long)n * ho * wo * (c / 8);
   if (kh == kw && sh == sw && kh == 3 && sh == 2) {
     if (is_max)
-      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<true, 3, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
-          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
+      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<true, 3, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)0, stream,
+                              (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
     else
-      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<false, 3, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
-          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
+      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<false, 3, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)0, stream,
+                              (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
     EQXV_LAUNCH_CHECK();
     return EQXV_OK;
   }
   if (kh == kw && sh == sw && kh == 2 && sh == 2) {
     if (is_max)
-      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<true, 2, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
-          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
+      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<true, 2, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)0, stream,
+                              (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
     else
-      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<false, 2, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)(0), stream, 
-          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
+      EQXV_CUDA(launch_kernel(pool2d_fixed_kernel<false, 2, 2>, dim3(grid_for(total)), dim3(kPwThreads), (size_t)0, stream,
+                              (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, pad, ho, wo, xp, yp));
     EQXV_LAUNCH_CHECK();
     return EQXV_OK;
   }
@@ -610,6 +685,14 @@ extern "C" int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n
     EQXV_CHECK_ARG(x && y && n > 0 && c > 0 && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 &&
                        x_pitch >= c && y_pitch >= c && n <= 65535,
                    "global_avgpool: bad arguments");
+    static const bool no_cluster_pool = getenv("EQXV_NO_POOL_CLUSTER") != nullptr;
+    if (h * w >= 1024 && !no_cluster_pool) {   // big maps: split the pixels over an 8-CTA cluster
+      dim3 cgrid((unsigned)(((c / 8 + 7) / 8) * kPoolCluster), (unsigned)n);
+      EQXV_CUDA(launch_kernel(global_avgpool_cluster_kernel, cgrid, dim3(256), (size_t)0, (cudaStream_t)stream,
+                              (const __nv_bfloat16*)x, (__nv_bfloat16*)y, h * w, c, x_pitch, y_pitch));
+      EQXV_LAUNCH_CHECK();
+      return EQXV_OK;
+    }
     dim3 grid((unsigned)((c / 8 + 7) / 8), (unsigned)n);
     EQXV_CUDA(launch_kernel(global_avgpool_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y,
                                                                   h * w, c, x_pitch, y_pitch));

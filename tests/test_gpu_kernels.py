@@ -316,9 +316,14 @@ def test_eltwise_variants(device):
 def test_global_avgpool_shapes(device):
     from eqxvision_b200 import ops
 
-    for (n, hw, c) in [(5, 112, 48), (2, 64, 2048), (3, 14, 960), (7, 7, 24), (2, 5, 8)]:
+    # maps of >= 1024 pixels take the 8-CTA cluster kernel (partial sums meet through distributed shared memory),
+    # smaller ones the single-CTA kernel; (3, 33, 72): pixel count not divisible by the cluster size
+    for (n, hw, c) in [(5, 112, 48), (2, 64, 2048), (3, 14, 960), (7, 7, 24), (2, 5, 8), (3, 33, 72), (2, 56, 144),
+                       (1, 32, 8)]:
         x = rb(device, n, hw, hw, c, seed=c)
-        assert rel_l2(ops.adaptive_avgpool(x, 1, 1), x.float().mean((1, 2), keepdim=True)) < TOL_BF16
+        got = ops.adaptive_avgpool(x, 1, 1)
+        assert rel_l2(got, x.float().mean((1, 2), keepdim=True)) < TOL_BF16
+        assert torch.equal(got, ops.adaptive_avgpool(x, 1, 1))      # deterministic (fixed reduction order)
 
 
 def test_bilinear_resize(device):
