@@ -1377,10 +1377,10 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "igemm: cout %d too large for the bias staging area", q.cout);
   // epilogue warps per TMEM lane quadrant; every warp owns 2 residual slabs, the 8 staging slabs are shared out
   const int forced_sub = env_int("EQXV_EPI_SUB");
-  // Two warps per quadrant where the epilogue bounds the tile (shallow K: ResNet c3 / downsample layers went
-  // from 78 % to 99 % of their HBM roofline) and wherever it costs no shared memory (no residual); one where
-  // the K loop hides it and the second residual ring would cost an operand stage (deep-K residual GEMMs).
-  p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : ((kblocks <= 8 || !p.has_res) ? 2 : 1);
+  // Two warps per quadrant where the epilogue bounds the tile (shallow K, <= 4 K blocks: ResNet c3 / downsample
+  // layers went from 78 % to 99 % of their HBM roofline); one where the K loop hides it: the leaner tile-major
+  // loop wins there by 2-7 % with or without a residual (tools/sweep_igemm.py, profiles/r01_sweep_igemm_v18.txt).
+  p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : (kblocks <= 4 ? 2 : 1);
   const int fixed = 2 * kStageBuf + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
   int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
   stages = std::min(stages, 8);
