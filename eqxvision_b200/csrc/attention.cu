@@ -573,6 +573,255 @@ __global__ void __launch_bounds__(256) attention_probs_kernel(const __nv_bfloat1
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Ping-pong variant of the tcgen05 kernel (same operands, same MMAs, same shared-memory layout).
+//
+// In attention_tc_kernel all eight softmax warps work on the SAME tile in lock-step: every phase of a tile
+// (TMEM read + row max, exponentials, P write + proxy fence, O drain + global store) is a latency chain with
+// two warps per SM sub-partition and nothing to overlap it (ncu r01s12: issue slots 24 % busy, flat stall
+// profile; 7000 cycles per 128-row tile of which 2400 are the MUFU-bound exponentials).
+// Here the softmax warps form TWO groups of four (one thread per query row, the whole key axis in two passes
+// over TMEM: row max, then exp / sum / bf16 P), group g & 1 owns tile g and S region g & 1. While one group
+// is in its exponentials the other waits for its P.V product, drains O and stores it. No cross-thread
+// exchange is needed any more (one thread sees the whole row): no named barriers, no reduction scratch.
+// P never touches shared memory: the bf16 probabilities are written back into the group's own S region
+// (tcgen05.st, 2 values per 32-bit column) and the P.V product reads its A operand from tensor memory, so the
+// two groups only meet at the single O accumulator (the product of tile g waits for the drain of O_{g-1}).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAtThreads, 1) attention_pp_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t buf_bytes = 3u * (uint32_t)p.op_bytes;
+  const uint32_t p_smem = base + 2 * buf_bytes;            // P: 4 K-blocks of [128 x 64] (64 KiB)
+  const uint32_t bars = p_smem + 65536 + 2048;
+  auto bar_load = [&](int b) { return bars + 8u * b; };
+  auto bar_s = [&](int r) { return bars + 16u + 8u * r; };
+  auto bar_p = [&](int r) { return bars + 32u + 8u * r; };
+  // one O-ready barrier per group: a parity wait may lag its barrier by at most one phase, and a group only
+  // ever observes the products of its own tiles
+  auto bar_o = [&](int r) { return bars + 48u + 8u * r; };
+  const uint32_t bar_od = bars + 64u;
+  const uint32_t tmem_slot = bars + 72u;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbase + 2 * buf_bytes + 65536 + 2048 + 72);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tm);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_load(i), 1);
+      mbar_init(bar_s(i), 1);
+      mbar_init(bar_p(i), 128);
+    }
+    mbar_init(bar_o(0), 1);
+    mbar_init(bar_o(1), 1);
+    mbar_init(bar_od, 128);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  griddep_wait();     // PDL: everything above overlapped the previous kernel's tail
+  tc_fence_before();
+  __syncthreads();
+  griddep_launch();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const int C = p.heads * 64;
+  const int my_pairs = ((int)blockIdx.x < p.pairs) ? (p.pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int G = my_pairs * p.ntile;   // tiles this CTA processes
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint64_t hi = (uint64_t)(umma_desc_sw128(0) >> 32) << 32;
+      const uint32_t lbo = 1u << 16;
+      const uint32_t idesc_s = umma_idesc_bf16_m128((uint32_t)p.tk);
+      const uint32_t idesc_o = umma_idesc_bf16_m128_bmn(64);
+      const int ksteps = p.tk / 16;
+      auto issue_load = [&](int pi) {
+        const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
+        const int img = pair / p.heads, head = pair - img * p.heads;
+        const int b = pi & 1;
+        const uint32_t dst = base + b * buf_bytes;
+        mbar_expect_tx(bar_load(b), 3u * (uint32_t)(p.tk * 128));
+        for (int o = 0; o < 3; ++o) {
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+              ::"r"(dst + o * p.op_bytes), "l"(reinterpret_cast<uint64_t>(&p.tm)), "r"(bar_load(b)),
+                "r"(o * C + head * 64), "r"(0), "r"(img)
+              : "memory");
+        }
+      };
+      auto issue_qk = [&](int g) {      // S_g -> region g & 1
+        const int pi = g / p.ntile, t = g - pi * p.ntile;
+        if (t == 0) mbar_wait(bar_load(pi & 1), (uint32_t)((pi >> 1) & 1));
+        const uint32_t q_s = base + (pi & 1) * buf_bytes;
+        const uint32_t q_lo = (((q_s + t * 16384) & 0x3FFFF) >> 4) | lbo;
+        const uint32_t k_lo = (((q_s + p.op_bytes) & 0x3FFFF) >> 4) | lbo;
+        const uint32_t d = tmem_base + (uint32_t)(g & 1) * kAtS;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, hi | (q_lo + 2 * k), hi | (k_lo + 2 * k), idesc_s, (uint32_t)k);
+        umma_commit(bar_s(g & 1));
+      };
+      if (my_pairs > 0) issue_load(0);
+      if (my_pairs > 1) issue_load(1);
+      if (G > 0) issue_qk(0);
+      if (G > 1) issue_qk(1);
+      for (int g = 0; g < G; ++g) {
+        const int pi = g / p.ntile, t = g - pi * p.ntile;
+        AT_TS(0, g);
+        mbar_wait(bar_p(g & 1), (uint32_t)((g >> 1) & 1));      // P_g written, S_g fully read
+        if (g > 0) mbar_wait(bar_od, (uint32_t)((g - 1) & 1));  // O_{g-1} has left TMEM
+        tc_fence_after();
+        AT_TS(1, g);
+        const uint32_t v_s = base + (pi & 1) * buf_bytes + 2 * p.op_bytes;
+        const uint32_t v_lo = ((v_s & 0x3FFFF) >> 4) | lbo;
+        const uint32_t d = tmem_base + 2 * kAtS;
+        const uint32_t p_tmem = tmem_base + (uint32_t)(g & 1) * kAtS;   // P_g aliases the S region of its group
+        for (int j = 0; j < ksteps; ++j)
+          umma_bf16_ts(d, p_tmem + (uint32_t)(j * 8), hi | (v_lo + (uint32_t)(j * 128)), idesc_o, (uint32_t)j);
+        umma_commit(bar_o(g & 1));
+        AT_TS(2, g);
+        if (t == p.ntile - 1 && pi + 2 < my_pairs) {
+          mbar_wait(bar_o(g & 1), (uint32_t)((g >> 1) & 1));  // last reader of this pair's buffer has finished
+          issue_load(pi + 2);
+        }
+        if (g + 2 < G) issue_qk(g + 2);         // region g & 1 is free again
+        AT_TS(4, g);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== softmax groups: warps 1..4 and 5..8 ==============================
+    const int grp = (warp - 1) >> 2;         // tiles g with (g & 1) == grp
+    const int quad = warp & 3;               // TMEM lane quadrant
+    const int row = quad * 32 + lane;        // query row inside the tile
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t s_addr = lane_addr + (uint32_t)grp * kAtS;
+    const uint32_t o_addr = lane_addr + 2 * kAtS;
+    const int nch = p.tk / 16;               // 16-column chunks of the key axis
+    for (int g = grp; g < G; g += 2) {
+      const int pi = g / p.ntile, t = g - pi * p.ntile;
+      const bool live = t * 128 + quad * 32 < p.tokens;   // warp-uniform: any valid row in this warp's slab
+      const bool rec = lane == 0 && (warp == 1 || warp == 5);
+      if (rec) AT_TS(8, g);
+      mbar_wait(bar_s(grp), (uint32_t)((g >> 1) & 1));
+      tc_fence_after();
+      if (rec) AT_TS(9, g);
+      float mb = 0.f, inv = 0.f;
+      if (live) {
+        // ---- pass 1: row maximum ----
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        auto max16 = [&](int c, float* s) {
+          if (c * 16 + 16 > p.tokens) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (c * 16 + e >= p.tokens) s[e] = -INFINITY;
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], s[e]);
+        };
+        // software pipeline over stages of 32 columns: the TMEM loads of stage st+1 are in flight while stage
+        // st is reduced (tcgen05.wait::ld waits for ALL outstanding loads, so the wait follows the processing)
+        float ra[16], rb[16];
+        tmem_ld_x16(s_addr, ra);
+        tmem_ld_wait();
+        for (int c = 0; c < nch; c += 2) {
+          if (c + 1 < nch) tmem_ld_x16(s_addr + (c + 1) * 16, rb);
+          max16(c, ra);
+          tmem_ld_wait();
+          if (c + 1 < nch) {
+            if (c + 2 < nch) tmem_ld_x16(s_addr + (c + 2) * 16, ra);
+            max16(c + 1, rb);
+            tmem_ld_wait();
+          }
+        }
+        mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+      }
+      if (rec) AT_TS(10, g);
+      if (live) {
+        // ---- pass 2: exponentials, row sum, bf16 P into the swizzled A-operand layout ----
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        auto exp16 = [&](int c, const float* s) {
+          uint32_t pk[8];
+          const bool tail = c * 16 + 16 > p.tokens;     // warp-uniform: only the chunk straddling the end
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            float p0 = ex2_approx(fmaf(s[e], p.scale_log2, -mb));
+            float p1 = ex2_approx(fmaf(s[e + 1], p.scale_log2, -mb));
+            if (tail) {                                    // keys past the end (zero-filled K rows)
+              if (c * 16 + e >= p.tokens) p0 = 0.f;
+              if (c * 16 + e + 1 >= p.tokens) p1 = 0.f;
+            }
+            s4[(e >> 1) & 3] += p0 + p1;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+            pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          // P chunk c (16 bf16 = 8 packed columns) overwrites columns [8c, 8c+8) of the S region: they belong
+          // to S chunk c/2 <= c, which is already in registers
+          tmem_st_x8(s_addr + (uint32_t)(c * 8), pk);
+        };
+        float ra[16], rb[16];
+        tmem_ld_x16(s_addr, ra);
+        tmem_ld_wait();
+        for (int c = 0; c < nch; c += 2) {
+          if (c + 1 < nch) tmem_ld_x16(s_addr + (c + 1) * 16, rb);
+          exp16(c, ra);
+          tmem_ld_wait();
+          if (c + 1 < nch) {
+            if (c + 2 < nch) tmem_ld_x16(s_addr + (c + 2) * 16, ra);
+            exp16(c + 1, rb);
+            tmem_ld_wait();
+          }
+        }
+        inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+      }
+      if (rec) AT_TS(12, g);
+      tmem_st_wait();              // P_g is in tensor memory
+      tc_fence_before();           // ... and ordered before the MMA that reads it
+      mbar_arrive(bar_p(grp));
+      if (rec) AT_TS(13, g);
+      // ---- O_g: wait for the P.V product, drain, release the accumulator, store ----
+      mbar_wait(bar_o(grp), (uint32_t)((g >> 1) & 1));
+      tc_fence_after();
+      float o[64];
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld_x16(o_addr + q * 16, o + q * 16);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(bar_od);
+      if (rec) AT_TS(14, g);
+      const int tok = t * 128 + row;
+      if (live && tok < p.tokens) {
+        const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
+        const int img = pair / p.heads, head = pair - img * p.heads;
+        __nv_bfloat16* dst = p.out + ((long long)img * p.tokens + tok) * C + head * 64;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(o[q * 8 + 2 * e] * inv, o[q * 8 + 2 * e + 1] * inv);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static long long* g_attn_ts = nullptr;   // set by eqxv_debug_attention_timeline
 
 static int launch_attention_tc(const void* qkv, void* out, int images, int tokens, int heads, float scale,
@@ -603,13 +852,20 @@ static int launch_attention_tc(const void* qkv, void* out, int images, int token
   // that are never stored.
   const int smem = 2 * 3 * p.op_bytes + 65536 + 2048 + 128 + 1024;
   const int grid = std::min(p.pairs, device_sm_count());
-  EQXV_CUDA(launch_kernel(attention_tc_kernel<13>, dim3(grid), dim3(kAtThreads), (size_t)(smem), stream, p));
+  // two softmax groups ping-ponging on alternate tiles (default) or the lock-step kernel (EQXV_ATTN_PP=0)
+  const char* pp = getenv("EQXV_ATTN_PP");
+  if (pp == nullptr || atoi(pp) != 0) {
+    EQXV_CUDA(launch_kernel(attention_pp_kernel, dim3(grid), dim3(kAtThreads), (size_t)(smem), stream, p));
+  } else {
+    EQXV_CUDA(launch_kernel(attention_tc_kernel<13>, dim3(grid), dim3(kAtThreads), (size_t)(smem), stream, p));
+  }
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
 
 int attention_init() {
   EQXV_CUDA(cudaFuncSetAttribute(attention_tc_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  EQXV_CUDA(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   EQXV_CUDA(cudaFuncSetAttribute(attention_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return EQXV_OK;
 }

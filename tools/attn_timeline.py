@@ -1,4 +1,4 @@
-"""Phase timeline of the tcgen05 attention kernel (CTA 0, first 12 tiles), from clock64 stamps.
+"""Phase timeline of the tcgen05 attention kernels (CTA 0, first 12 tiles), from clock64 stamps (EQXV_ATTN_PP selects the kernel).
 MMA thread: 0 loop top, 1 P ready, 2 PV issued+committed, 3 after prefetch, 4 QK(g+2) issued.
 Softmax warp 1: 8 tile start, 9 S ready, 10 max done, 11 exp done, 12 sums exchanged, 13 O(g-1) drained, 14 P written."""
 import os, sys
