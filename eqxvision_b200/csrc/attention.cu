@@ -224,6 +224,7 @@ constexpr int kAtThreads = 288;
 
 struct alignas(64) AttnParams {
   CUtensorMap tm;        // qkv as [images][tokens][3*heads*64]
+  CUtensorMap tmO;       // out as [images][tokens][heads*64], box = 32 rows x 64 columns (ping-pong kernel)
   __nv_bfloat16* out;
   int tokens, tk, heads, pairs, ntile;
   int op_bytes;          // bytes per operand buffer (tk * 128 rounded up to 1024)
@@ -609,6 +610,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_pp_kernel(const __gri
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tm);
+    tma_prefetch_desc(&p.tmO);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_load(i), 1);
       mbar_init(bar_s(i), 1);
@@ -702,6 +704,12 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_pp_kernel(const __gri
     const uint32_t s_addr = lane_addr + (uint32_t)grp * kAtS;
     const uint32_t o_addr = lane_addr + 2 * kAtS;
     const int nch = p.tk / 16;               // 16-column chunks of the key axis
+    // O leaves through the shared memory the probabilities no longer need: every warp stages its 32 rows
+    // (4 KiB, 128B-swizzled) and one lane issues a TMA store (rows past `tokens` are clipped by the tensor
+    // map). Direct 16-byte global stores touched 32 different lines per warp instruction and cost ~1800
+    // cycles per tile on the softmax warps.
+    const uint32_t o_slab = p_smem + (uint32_t)(grp * 4 + quad) * 4096u;
+    uint8_t* o_slab_g = gbase + 2 * buf_bytes + (uint32_t)(grp * 4 + quad) * 4096u;
     for (int g = grp; g < G; g += 2) {
       const int pi = g / p.ntile, t = g - pi * p.ntile;
       const bool live = t * 128 + quad * 32 < p.tokens;   // warp-uniform: any valid row in this warp's slab
@@ -795,11 +803,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_pp_kernel(const __gri
       tc_fence_before();
       mbar_arrive(bar_od);
       if (rec) AT_TS(14, g);
-      const int tok = t * 128 + row;
-      if (live && tok < p.tokens) {
+      if (live) {
         const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
         const int img = pair / p.heads, head = pair - img * p.heads;
-        __nv_bfloat16* dst = p.out + ((long long)img * p.tokens + tok) * C + head * 64;
+        if (lane == 0) tma_store_wait_read<0>();   // this warp's previous store has read the slab
+        __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           uint32_t w[4];
@@ -808,10 +816,18 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_pp_kernel(const __gri
             const __nv_bfloat162 h = __floats2bfloat162_rn(o[q * 8 + 2 * e] * inv, o[q * 8 + 2 * e + 1] * inv);
             w[e] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(o_slab_g + sw128_off((uint32_t)lane, (uint32_t)q)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&p.tmO, o_slab, head * 64, t * 128 + quad * 32, img);
+          tma_store_commit();
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -846,6 +862,18 @@ static int launch_attention_tc(const void* qkv, void* out, int images, int token
   m.estride[0] = m.estride[1] = m.estride[2] = 1;
   m.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
   int rc = encode_tmap(&p.tm, m);
+  if (rc) return rc;
+  TmapSpec mo{};
+  mo.base = out;
+  mo.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  mo.rank = 3;
+  const uint64_t ldo = (uint64_t)heads * 64;
+  mo.dims[0] = ldo, mo.dims[1] = (uint64_t)tokens, mo.dims[2] = (uint64_t)images;
+  mo.strides_bytes[0] = ldo * 2, mo.strides_bytes[1] = ldo * 2 * (uint64_t)tokens;
+  mo.box[0] = 64, mo.box[1] = 32, mo.box[2] = 1;
+  mo.estride[0] = mo.estride[1] = mo.estride[2] = 1;
+  mo.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+  rc = encode_tmap(&p.tmO, mo);
   if (rc) return rc;
   // smem: 2 x (Q,K,V) + P (64 KiB) + reductions (2 KiB) + barriers; the Q tile of the second M block may be
   // read up to row 255 of a tk-row buffer: the bytes behind it (K, V, P) are finite garbage feeding rows
