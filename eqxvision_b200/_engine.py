@@ -569,6 +569,8 @@ def _flatten_out(out, acc: List[T.Sym]):
     if T.is_sym(out):
         acc.append(out)
         return ("leaf", len(acc) - 1)
+    if out is None:   # `(None, out)` of segmentation models without an auxiliary head (_utils.py:54, lraspp.py:68)
+        return ("none", None)
     if isinstance(out, (list, tuple)):
         return (type(out).__name__, [_flatten_out(o, acc) for o in out])
     raise EqxvError(f"model returned an unsupported value: {out!r}")
@@ -576,6 +578,8 @@ def _flatten_out(out, acc: List[T.Sym]):
 
 def _unflatten_out(struct, leaves):
     tag, payload = struct
+    if tag == "none":
+        return None
     if tag == "leaf":
         return leaves[payload]
     items = [_unflatten_out(s, leaves) for s in payload]
@@ -689,6 +693,8 @@ def run_single(module, method: str, x, args=(), kwargs=None):
     out = run_batched(module, method, xb, args, kwargs)
 
     def strip(o):
+        if o is None:
+            return None
         if isinstance(o, torch.Tensor):
             return o[0]
         return type(o)(strip(v) for v in o)

@@ -37,6 +37,7 @@ from .classification.mobilenetv3 import MobileNetV3, mobilenet_v3_large, mobilen
 from .classification.vgg import VGG, vgg11, vgg11_bn, vgg13, vgg13_bn, vgg16, vgg16_bn, vgg19, vgg19_bn  # noqa: F401
 from .segmentation.deeplabv3 import DeepLabV3, deeplabv3  # noqa: F401
 from .segmentation.fcn import FCN, fcn  # noqa: F401
+from .segmentation.lraspp import LRASPP, lraspp_mobilenet_v3_large  # noqa: F401
 from .classification.swin import (  # noqa: F401
     SwinTransformer,
     swin_b,

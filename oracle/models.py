@@ -283,22 +283,55 @@ _MBV3 = {
 }  # mobilenetv3.py:265-336 (width_mult 1, not dilated, not reduced)
 
 
-def mobilenet_v3(state_dict, x, arch="mobilenet_v3_small"):
-    """MobileNetV3.__call__ (mobilenetv3.py:236-247) with _InvertedResidual (62-132); BN eps 1e-3 (:189)"""
-    s = Stream(state_dict)
+def mobilenet_v3_features(s: Stream, x, arch="mobilenet_v3_small", dilated=False, taps=()):
+    """MobileNetV3.features (mobilenetv3.py:190-222): stem, _InvertedResidual stack (62-132), last 1x1 conv;
+    BN eps 1e-3 (:189). `dilated` (segmentation backbone, mobilenetv3.py:265-336 with dilated=True): the last three
+    blocks use dilation 2 and the stride-2 one of them stride 1 (:88). Returns (out, [outputs of features[i] for i in taps])."""
     rows, _ = _MBV3[arch]
     eps = 1e-3
+    feats = []
     x = _cna(s, x, 2, 1, act="hard_swish", eps=eps)
-    for cin, k, exp, cout, use_se, a, stride in rows:
+    feats.append(x)
+    for i, (cin, k, exp, cout, use_se, a, stride) in enumerate(rows):
         act = "hard_swish" if a == "HS" else "relu"
+        dil = 2 if (dilated and i >= len(rows) - 3) else 1
+        st = 1 if dil > 1 else stride                                           # mobilenetv3.py:88
         inp = x
         if exp != cin:
             x = _cna(s, x, act=act, eps=eps)
-        x = _cna(s, x, stride, (k - 1) // 2, groups=exp, act=act, eps=eps)
+        x = _cna(s, x, st, (k - 1) // 2 * dil, dil, groups=exp, act=act, eps=eps)
         if use_se:
             x = squeeze_excitation(s, x, "relu", "hard_sigmoid")                # mobilenetv3.py:56-58,103
         x = _cna(s, x, eps=eps, res=inp if (stride == 1 and cin == cout) else None)
+        feats.append(x)
     x = _cna(s, x, act="hard_swish", eps=eps)                                   # 6 * last channels
+    feats.append(x)
+    return x, [feats[t] for t in taps]
+
+
+def lraspp_mobilenet_v3_large(state_dict, x):
+    """LRASPP.__call__ (lraspp.py:56-68) with LRASPPHead (lraspp.py:71-116) on the dilated MobileNetV3-Large
+    backbone, taps features[4] (low, C2) and features[16] (high) (lraspp.py:160-166). Returns `out` (N, classes, H, W);
+    the reference returns (None, out)."""
+    s = Stream(state_dict)
+    h, w = x.shape[-2:]
+    _, (low, high) = mobilenet_v3_features(s, x, "mobilenet_v3_large", dilated=True, taps=(4, 16))
+    y = _cna(s, high, act="relu")                                               # cbr: conv1x1 -> BN -> relu
+    ws = s.take()                                                               # scale: pool -> conv1x1 -> sigmoid
+    g = O.conv_bn_act(O.rnd(O.adaptive_avg_pool2d(high, 1)), ws, None, None, act="sigmoid")
+    y = O.rnd(y * g)                                                            # lraspp.py:113
+    y = O.rnd(O.resize_bilinear(y, low.shape[-2], low.shape[-1]))               # lraspp.py:114
+    wl, bl, wh, bh = s.take(), s.take(), s.take(), s.take()
+    lo = O.conv_bn_act(low, wl, bl, None)                                       # low_classifier
+    out = O.conv_bn_act(y, wh, bh, None, res=lo)                                # + high_classifier (lraspp.py:116)
+    assert s.done()
+    return O.resize_bilinear(out, h, w)                                         # lraspp.py:67
+
+
+def mobilenet_v3(state_dict, x, arch="mobilenet_v3_small"):
+    """MobileNetV3.__call__ (mobilenetv3.py:236-247) with _InvertedResidual (62-132); BN eps 1e-3 (:189)"""
+    s = Stream(state_dict)
+    x, _ = mobilenet_v3_features(s, x, arch)
     x = O.rnd(O.adaptive_avg_pool2d(x, 1).flatten(1))
     x = O.linear_act(x, s.take(), s.take(), act="hard_swish")                   # Linear -> hswish -> Dropout
     out = O.linear_act(x, s.take(), s.take(), round_out=False)

@@ -125,6 +125,26 @@ def test_deeplabv3_parity(device, save_checkpoint):
     assert agree > 0.9, agree
 
 
+def test_lraspp_mobilenet_v3_large_parity(device, save_checkpoint):
+    """LRASPP (lraspp.py): dilated MobileNetV3-Large backbone taps [4, 16], gated head, `(None, out)`"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    tv = ck.torchvision_model("lraspp_mobilenet_v3_large", seed=1, calib_hw=64)
+    sd = tv.state_dict()
+    net = eb.tree_inference(eb.models.lraspp_mobilenet_v3_large(torch_weights=save_checkpoint(sd, "lraspp.pth")), True)
+    x = ck.synthetic_images(2, h=128, w=128, seed=2)
+    none, out = eb.vmap(net, axis_name="batch")(x, key=keys(2))
+    assert none is None and out.shape == (2, 21, 128, 128) and out.dtype == torch.float32
+    ref = om.lraspp_mobilenet_v3_large(sd, x)
+    with O.emulate_bf16():
+        emu = om.lraspp_mobilenet_v3_large(sd, x)
+    assert rel(out, emu) < 4e-2 and rel(out, ref) < 1e-1, (rel(out, emu), rel(out, ref))
+    assert (out.cpu().argmax(1) == emu.argmax(1)).float().mean().item() > 0.9
+
+
 def test_swin_t_parity(device, save_checkpoint):
     """Swin-T through the positional loader (torchvision checkpoint incl. relative_position_index)"""
     import eqxvision_b200 as eb

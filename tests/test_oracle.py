@@ -202,3 +202,18 @@ def test_oracle_resnext_matches_torchvision():
         ref = tv(x)
     got = om.resnet(tv.state_dict(), x, "resnext50_32x4d")
     assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_oracle_lraspp_matches_torchvision():
+    """LRASPP-MobileNetV3-Large (lraspp.py) restated in the oracle == torchvision on a seeded state_dict, at the
+    tolerance the reference's own test uses (tests/test_models/test_lraspp.py: atol 1e-4)"""
+    from oracle import checkpoints as ck
+    from oracle import models as om
+
+    tv = ck.torchvision_model("lraspp_mobilenet_v3_large", seed=1, calib_hw=64)
+    x = ck.synthetic_images(1, h=96, w=96, seed=2)
+    with torch.no_grad():
+        ref = tv(x)["out"]
+    got = om.lraspp_mobilenet_v3_large(tv.state_dict(), x)
+    assert got.shape == ref.shape == (1, 21, 96, 96)
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
