@@ -334,6 +334,10 @@ def test_bilinear_resize(device):
     y = ops.resize_bilinear_to_nchw(x, 21, 128, 96)
     ref = F.interpolate(xn[:, :21], size=(128, 96), mode="bilinear", align_corners=False)
     assert torch.allclose(y, ref, atol=1e-5)
+    for (oh, ow) in ((64, 50), (33, 517), (16, 12)):      # widths that are not multiples of 4 / wider than one block
+        y2 = ops.resize_bilinear_to_nchw(x, 21, oh, ow)
+        ref2 = F.interpolate(xn[:, :21], size=(oh, ow), mode="bilinear", align_corners=False)
+        assert torch.allclose(y2, ref2, atol=1e-5), (oh, ow)
     yb = ops.resize_bilinear(x, 40, 30)
     refb = F.interpolate(xn, size=(40, 30), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
     assert rel_l2(yb, refb) < TOL_BF16
