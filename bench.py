@@ -3,17 +3,23 @@
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port of the reference
-  torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, weak scaling
+  torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, weak scaling, no collective
 
 Workload at N=1 (BASELINE.json configs[1]): ResNet-50 inference, bf16, batch 256 per GPU, synthetic
 3x224x224 images, seeded synthetic checkpoint loaded through load_torch_weights. ViT-B/16 (64 images
-per GPU = 512 over 8, configs[2]) is measured in the same run and reported under "secondary".
+per GPU = 512 over 8, configs[2]) is measured in the same run and reported under "secondary";
+`--all-configs` adds EfficientNet-B4 (B=128, configs[3]) and DeepLabV3-ResNet50 (4x3x512x512, configs[4]).
 A "step" is one forward pass over one batch: one CUDA-graph replay (57 kernel launches for R50).
 
-  value  : inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e    : pinned host fp32 NCHW batch -> H2D -> graph -> D2H logits, every step, same events
-  roofline: the tcgen05 implicit-GEMM kernel (all conv/linear launches of a step), algorithmic FLOPs
-           (8.178 GFLOP/img) over the summed per-launch device time of those launches
+  value   : inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e     : pinned host fp32 NCHW batch -> H2D -> graph -> D2H of every model output, every step, same
+            events; EQXV_E2E_LANES (default 3) plans are used round-robin so that the copy of step i+1
+            overlaps the kernels of step i, graph launches are FIFO-chained across lanes
+  roofline: tensor-bound models: the tcgen05 implicit-GEMM family (all conv/linear launches of a step),
+            algorithmic FLOPs (8.178 GFLOP/img for R50) over the summed per-launch device
+            time of those launches, against the measured sustained cuBLAS bf16 peak; HBM-bound models
+            (EfficientNet-B4): whole-step algorithmic bytes against the measured copy bandwidth;
+            `traffic` = ncu DRAM bytes of those launches (profiles/traffic.json)
   cpu_baseline: the CPU oracle (torch fp32 restatement of the reference, kind "port") on a bounded sample
 """
 from __future__ import annotations
