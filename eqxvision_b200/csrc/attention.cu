@@ -699,7 +699,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attention_pp_kernel(const __gri
     // ============================== softmax groups: warps 1..4 and 5..8 ==============================
     const int grp = (warp - 1) >> 2;         // tiles g with (g & 1) == grp
     const int quad = warp & 3;               // TMEM lane quadrant
-    const int row = quad * 32 + lane;        // query row inside the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t s_addr = lane_addr + (uint32_t)grp * kAtS;
     const uint32_t o_addr = lane_addr + 2 * kAtS;

@@ -201,7 +201,6 @@ __device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const ui
     const int cpt = (p.block_n + CH - 1) / CH;
     const float* s_bias = reinterpret_cast<const float*>(gbase + p.off_bias);
     constexpr bool has_res = kRes != 0;
-    constexpr bool res_after_act = kRes == 2;
     // slab origin inside the (tn, th, tw) tile: rows are ordered n, h, w (w fastest)
     const int so = quad * 32;
     const int w_off = so % p.tw, h_off = (so / p.tw) % p.th, n_off = so / (p.tw * p.th);
@@ -520,7 +519,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
 
-  const int taps = p.kh * p.kw;
 
   if (warp == 0) {
     // ============================== TMA producer ==============================

@@ -289,6 +289,44 @@ __global__ void __launch_bounds__(256) global_avgpool_kernel(const __nv_bfloat16
   }
 }
 
+// Small maps (the 7x7 classifier pool of ResNet / EfficientNet heads): one thread per (image, channel vector),
+// consecutive threads = consecutive channel vectors, so every pixel is one coalesced row read and there is no
+// cross-thread reduction at all (the block kernel above left most of its 256 threads idle on 49 pixels).
+__global__ void __launch_bounds__(256) global_avgpool_small_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                   __nv_bfloat16* __restrict__ y, int hw, int c,
+                                                                   int xp, int yp) {
+  griddep_wait();
+  griddep_launch();
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int img = blockIdx.y;
+  if (g >= c / 8) return;
+  const __nv_bfloat16* base = x + (long long)img * hw * xp + g * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int p = 0;
+  for (; p + 3 < hw; p += 4) {
+    bf16x8 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const bf16x8*>(base + (long long)(p + u) * xp);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(r[u], f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += f[q];
+    }
+  }
+  for (; p < hw; ++p) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(base + (long long)p * xp), f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += f[q];
+  }
+  const float inv = 1.f / (float)hw;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] *= inv;
+  *reinterpret_cast<bf16x8*>(y + (long long)img * yp + g * 8) = pack8(acc);
+}
+
 // Cluster variant for large maps: the pixels of one (image, 64-channel slab) are split over the 8 CTAs of a
 // thread-block cluster; every CTA reduces its slice as above, the partial sums meet in the leader through
 // distributed shared memory in rank order (deterministic, no atomics, no scratch buffer). One CTA per slab
@@ -689,6 +727,13 @@ extern "C" int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n
     if (h * w >= 1024 && !no_cluster_pool) {   // big maps: split the pixels over an 8-CTA cluster
       dim3 cgrid((unsigned)(((c / 8 + 7) / 8) * kPoolCluster), (unsigned)n);
       EQXV_CUDA(launch_kernel(global_avgpool_cluster_kernel, cgrid, dim3(256), (size_t)0, (cudaStream_t)stream,
+                              (const __nv_bfloat16*)x, (__nv_bfloat16*)y, h * w, c, x_pitch, y_pitch));
+      EQXV_LAUNCH_CHECK();
+      return EQXV_OK;
+    }
+    if (h * w <= 256 && c >= 256) {   // small map, many channels: one thread per (image, channel vector)
+      dim3 sgrid((unsigned)((c / 8 + 255) / 256), (unsigned)n);
+      EQXV_CUDA(launch_kernel(global_avgpool_small_kernel, sgrid, dim3(256), (size_t)0, (cudaStream_t)stream,
                               (const __nv_bfloat16*)x, (__nv_bfloat16*)y, h * w, c, x_pitch, y_pitch));
       EQXV_LAUNCH_CHECK();
       return EQXV_OK;
