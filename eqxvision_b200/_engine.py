@@ -201,11 +201,21 @@ class Plan:
         (sh, sw), (ph, pw), (dh, dw) = e.stride, e.padding, e.dilation
         if sh != sw or ph != pw or dh != dw or out_f32:
             raise NotImplementedError("anisotropic / fp32-output grouped convolution")
-        if cout != c_in or c_in % 64 != 0 or 64 % cin_g != 0:
-            raise NotImplementedError(f"grouped convolution {c_in}->{cout} with groups={e.groups} "
-                                      "(only cin == cout, cin % 64 == 0, 64 % (cin/groups) == 0 is built)")
         xb = self.emit(e.x)
         ho, wo = sym.shape[1:]
+        if cout != c_in or c_in % 64 != 0 or 64 % cin_g != 0:
+            # group geometries outside the 64-channel block layout (RegNet: group widths 8/16/24/48... on stage
+            # widths such as 104 or 440, regnet.py:58-81): the filter is expanded to its dense block-diagonal
+            # [Cout, Cin] form on the host and runs as an ordinary implicit GEMM (zeros cost flops, not correctness)
+            cin_eff = xb.cpad
+            wp = self.const(_pack.pack_conv_weight(_pack.expand_grouped_weight(w, e.groups), cin_eff))
+            out = dst if dst is not None else self.alloc(self.n * ho * wo, cout, (ho, wo))
+            bias_d = self.const(b) if b is not None else None
+            self.step(ops.conv2d, x=xb.map(h, wd, cin_eff), wgt=wp, bias=bias_d, cin=cin_eff, cout=cout, kh=kh,
+                      kw=kw, stride=sh, pad=ph, dil=dh, act=act,
+                      residual=None if res is None else res.map(ho, wo), res_after_act=res_after,
+                      out=out.map(ho, wo))
+            return out
         out = dst if dst is not None else self.alloc(self.n * ho * wo, cout, (ho, wo))
         wp = self.const(_pack.pack_grouped_weight(w, e.groups))
         bias_d = self.const(b) if b is not None else None
@@ -315,7 +325,8 @@ class Plan:
         ho, wo = sym.shape[1:]
         out = dst if dst is not None else self.alloc(self.n * ho * wo, c, (ho, wo))
         if e.mode == "max":
-            self.step(ops.maxpool2d, x=xb.map(h, w), k=e.k, stride=e.stride, pad=e.pad, out=out.map(ho, wo))
+            self.step(ops.maxpool2d, x=xb.map(h, w), k=e.k, stride=e.stride, pad=e.pad, out=out.map(ho, wo),
+                      ceil_mode=e.ceil)
         else:
             self.step(ops.avgpool2d, x=xb.map(h, w), k=e.k, stride=e.stride, out=out.map(ho, wo))
         return out

@@ -52,6 +52,7 @@ SIGNATURES = {
     "eqxv_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_maxpool2d_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_maxpool2d_ceil_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_avgpool2d_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_adaptive_avgpool_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_layernorm_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _vp],
@@ -95,7 +96,7 @@ launch_count = 0  # number of kernel-launching C-ABI calls made by this process 
 _LAUNCHING = {
     "eqxv_conv2d_igemm_bf16", "eqxv_gemm_bias_act_res_bf16", "eqxv_conv_stem_bf16",
     "eqxv_pack_stem_input", "eqxv_nchw_f32_to_nhwc_bf16", "eqxv_nhwc_bf16_to_nchw_f32",
-    "eqxv_maxpool2d_nhwc_bf16", "eqxv_avgpool2d_nhwc_bf16", "eqxv_adaptive_avgpool_nhwc_bf16",
+    "eqxv_maxpool2d_nhwc_bf16", "eqxv_maxpool2d_ceil_nhwc_bf16", "eqxv_avgpool2d_nhwc_bf16", "eqxv_adaptive_avgpool_nhwc_bf16",
     "eqxv_layernorm_bf16", "eqxv_attention_fwd_bf16", "eqxv_patchify_nchw_f32_bf16",
     "eqxv_vit_assemble_tokens_bf16", "eqxv_gather_rows_bf16", "eqxv_dwconv_bn_act_bf16", "eqxv_dwconv_tile_bf16", "eqxv_eltwise_bf16",
     "eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32", "eqxv_resize_bilinear_nhwc_bf16", "eqxv_copy2d_async",

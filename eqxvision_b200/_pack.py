@@ -59,6 +59,17 @@ def pack_grouped_weight(w: torch.Tensor, groups: int) -> torch.Tensor:
     return out.reshape(o, kh * kw * 64).to(torch.bfloat16).contiguous()
 
 
+def expand_grouped_weight(w: torch.Tensor, groups: int) -> torch.Tensor:
+    """Grouped filter [O, I/G, kh, kw] -> dense [O, I, kh, kw] with zeros outside each output channel's own group
+    (the generic fallback for group geometries the 64-channel block layout does not cover)."""
+    o, ig, kh, kw = w.shape
+    og = o // groups
+    dense = torch.zeros(o, ig * groups, kh, kw, dtype=w.dtype)
+    for g in range(groups):
+        dense[g * og:(g + 1) * og, g * ig:(g + 1) * ig] = w[g * og:(g + 1) * og]
+    return dense
+
+
 def pack_stem_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     """[O, I<=8, kh<=8, kw<=8] -> [O, kh(r), 8(s), 8(c)] bf16 with zero taps/channels
     (see eqxv_conv_stem_bf16)"""

@@ -91,10 +91,10 @@ class ChannelScale(Expr):  # x * s with s of shape (C,1,1): squeeze.py:61
 
 
 class Pool(Expr):
-    __slots__ = ("x", "mode", "k", "stride", "pad")
+    __slots__ = ("x", "mode", "k", "stride", "pad", "ceil")
 
-    def __init__(self, x, mode, k, stride, pad):
-        self.x, self.mode, self.k, self.stride, self.pad = x, mode, k, stride, pad
+    def __init__(self, x, mode, k, stride, pad, ceil=False):
+        self.x, self.mode, self.k, self.stride, self.pad, self.ceil = x, mode, k, stride, pad, ceil
 
 
 class AdaptiveAvgPool(Expr):
@@ -325,11 +325,33 @@ def add(a, b) -> Sym:
         if inner is not None and isinstance(inner.expr, Linear) and inner.expr.res is None \
                 and inner.expr.act2 is None and q.kind == "chw":
             return rewrap(add(inner, to_tokens(q)))
-    for p, q in ((a, b), (b, a)):
+    # `x + block(x)` (mobilenetv2.py:86, regnet.py:166): x is an input of the other operand, so folding the add into
+    # x's producer would compute that producer twice (once plain for block(x), once with the residual); fold into
+    # the operand that is not an ancestor of the other one
+    order = ((b, a), (a, b)) if _feeds(a, b) else ((a, b), (b, a))
+    for p, q in order:
         e = p.expr
         if isinstance(e, (Conv, Linear)) and e.res is None and e.act2 is None:
             return Sym(p.kind, p.shape, e.replace(res=q))
     return Sym(a.kind, a.shape, Add(a, b))
+
+
+def _feeds(p: Sym, q: Sym, limit: int = 64) -> bool:
+    """True when p's expression is reachable from q through at most `limit` expression nodes"""
+    target = p.expr
+    stack, seen = [q.expr], 0
+    while stack and seen < limit:
+        e = stack.pop()
+        seen += 1
+        if e is target:
+            return True
+        for name in getattr(e, "__slots__", ()):
+            v = getattr(e, name, None)
+            if isinstance(v, Sym):
+                stack.append(v.expr)
+            elif isinstance(v, tuple):
+                stack.extend(i.expr for i in v if isinstance(i, Sym))
+    return False
 
 
 def mul(a, b) -> Sym:
@@ -340,14 +362,27 @@ def mul(a, b) -> Sym:
     raise TypeError(f"mul: unsupported operands {a!r} * {b!r}")
 
 
-def pool2d(x: Sym, mode: str, k, stride, pad) -> Sym:
+def _pool_out(size: int, k: int, stride: int, pad: int, ceil: bool) -> int:
+    if not ceil:
+        return (size + 2 * pad - k) // stride + 1
+    # use_ceil=True (squeezenet.py:84, googlenet.py:95): equinox pads the right edge by one more stride when the sweep
+    # does not divide evenly; the reference pins these models against torchvision, whose ceil_mode also drops a last
+    # window that would start beyond the input. The two rules agree unless that window is pure padding.
+    o = -((size + 2 * pad - k) // -stride) + 1
+    if (o - 1) * stride >= size + pad:
+        raise NotImplementedError("ceil-mode pooling whose last window lies entirely in the padding")
+    return o
+
+
+def pool2d(x: Sym, mode: str, k, stride, pad, ceil: bool = False) -> Sym:
     (kh, kw), (sh, sw), (ph, pw) = _pair(k), _pair(stride), _pair(pad)
     if kh != kw or sh != sw or ph != pw:
         raise NotImplementedError("only square pooling windows are supported")
+    if ceil and mode != "max":
+        raise NotImplementedError("ceil-mode average pooling is not on the hot path")
     c, h, w = x.shape
-    ho = (h + 2 * ph - kh) // sh + 1
-    wo = (w + 2 * pw - kw) // sw + 1
-    return Sym("chw", (c, ho, wo), Pool(x, mode, kh, sh, ph))
+    ho, wo = _pool_out(h, kh, sh, ph, ceil), _pool_out(w, kw, sw, pw, ceil)
+    return Sym("chw", (c, ho, wo), Pool(x, mode, kh, sh, ph, bool(ceil)))
 
 
 def adaptive_avg_pool2d(x: Sym, target) -> Sym:

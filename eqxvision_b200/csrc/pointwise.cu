@@ -701,6 +701,25 @@ extern "C" int eqxv_maxpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32
                      (cudaStream_t)stream);
 }
 
+// ceil-mode output size with torch's rule (the last window must start inside the input or its left padding);
+// that is the arithmetic the reference's own SqueezeNet / GoogLeNet tests pin against torchvision
+static int pool_out_ceil(int size, int k, int stride, int pad) {
+  int o = (size + 2 * pad - k + stride - 1) / stride + 1;
+  if ((o - 1) * stride >= size + pad) --o;
+  return o;
+}
+
+extern "C" int eqxv_maxpool2d_ceil_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w,
+                                             int32_t c, int32_t k, int32_t stride, int32_t pad,
+                                             int32_t x_pitch, int32_t y_pitch, void* stream) {
+  EQXV_CHECK_ARG(k >= 1 && stride >= 1 && pad >= 0 && 2 * pad <= k, "maxpool(ceil): bad window");
+  EQXV_CHECK_ARG(h + 2 * pad >= k && w + 2 * pad >= k, "maxpool(ceil): window larger than the padded input");
+  // windows are clipped to the input by the kernels, so the partial windows at the bottom / right edge need no
+  // extra padding: only the output extent changes
+  return pool_common(true, x, y, n, h, w, c, k, k, stride, stride, pad, pool_out_ceil(h, k, stride, pad),
+                     pool_out_ceil(w, k, stride, pad), x_pitch, y_pitch, (cudaStream_t)stream);
+}
+
 extern "C" int eqxv_avgpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w,
                                         int32_t c, int32_t k, int32_t stride, int32_t x_pitch,
                                         int32_t y_pitch, void* stream) {

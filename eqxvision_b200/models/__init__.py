@@ -1,3 +1,4 @@
+from .classification.alexnet import AlexNet, alexnet  # noqa: F401
 from .classification.resnet import (  # noqa: F401
     ResNet,
     resnet18,
@@ -33,7 +34,28 @@ from .classification.efficientnet import (  # noqa: F401
     efficientnet_v2_m,
     efficientnet_v2_s,
 )
+from .classification.googlenet import GoogLeNet, googlenet  # noqa: F401
+from .classification.mobilenetv2 import MobileNetV2, mobilenet_v2  # noqa: F401
 from .classification.mobilenetv3 import MobileNetV3, mobilenet_v3_large, mobilenet_v3_small  # noqa: F401
+from .classification.regnet import (  # noqa: F401
+    RegNet,
+    regnet_x_1_6gf,
+    regnet_x_3_2gf,
+    regnet_x_8gf,
+    regnet_x_16gf,
+    regnet_x_32gf,
+    regnet_x_400mf,
+    regnet_x_800mf,
+    regnet_y_1_6gf,
+    regnet_y_3_2gf,
+    regnet_y_8gf,
+    regnet_y_16gf,
+    regnet_y_32gf,
+    regnet_y_128gf,
+    regnet_y_400mf,
+    regnet_y_800mf,
+)
+from .classification.squeezenet import SqueezeNet, squeezenet1_0, squeezenet1_1  # noqa: F401
 from .classification.vgg import VGG, vgg11, vgg11_bn, vgg13, vgg13_bn, vgg16, vgg16_bn, vgg19, vgg19_bn  # noqa: F401
 from .segmentation.deeplabv3 import DeepLabV3, deeplabv3  # noqa: F401
 from .segmentation.fcn import FCN, fcn  # noqa: F401

@@ -380,12 +380,10 @@ class MaxPool2d(Module):
 
     def __init__(self, kernel_size, stride=1, padding=0, use_ceil=False, **kwargs):
         self.kernel_size, self.stride, self.padding = _tup2(kernel_size), _tup2(stride), _tup2(padding)
-        if use_ceil:
-            raise NotImplementedError("ceil-mode pooling is not on the hot path")
-        self.use_ceil = use_ceil
+        self.use_ceil = bool(use_ceil)
 
     def __call__(self, x, *, key=None):
-        return T.pool2d(x, "max", self.kernel_size, self.stride, self.padding)
+        return T.pool2d(x, "max", self.kernel_size, self.stride, self.padding, ceil=self.use_ceil)
 
 
 class AvgPool2d(Module):

@@ -110,14 +110,24 @@ def nhwc_to_nchw(x, c=None, out=None, stream=0):
     return out
 
 
-def maxpool2d(x, k, stride, pad, out=None, stream=0):
+def pool_out_size(size: int, k: int, stride: int, pad: int, ceil_mode: bool = False) -> int:
+    """output extent of a pooling window sweep; ceil mode follows torch's rule (see eqxv_maxpool2d_ceil_nhwc_bf16)"""
+    if not ceil_mode:
+        return (size + 2 * pad - k) // stride + 1
+    o = -((size + 2 * pad - k) // -stride) + 1
+    return o - 1 if (o - 1) * stride >= size + pad else o
+
+
+def maxpool2d(x, k, stride, pad, out=None, stream=0, ceil_mode=False):
     _check_cuda(x, out)
     n, h, w, c = x.shape
-    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    ho, wo = pool_out_size(h, k, stride, pad, ceil_mode), pool_out_size(w, k, stride, pad, ceil_mode)
     if out is None:
         out = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
-    call("eqxv_maxpool2d_nhwc_bf16", ptr(x), ptr(out), n, h, w, c, k, stride, pad, x.stride(2),
-         out.stride(2), stream)
+    elif tuple(out.shape[1:3]) != (ho, wo):
+        raise _lib.EqxvError(f"maxpool2d: output map {tuple(out.shape[1:3])} does not match {(ho, wo)}")
+    call("eqxv_maxpool2d_ceil_nhwc_bf16" if ceil_mode else "eqxv_maxpool2d_nhwc_bf16", ptr(x), ptr(out), n, h, w, c,
+         k, stride, pad, x.stride(2), out.stride(2), stream)
     return out
 
 

@@ -118,6 +118,12 @@ int eqxv_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t n, int32_t c, in
 int eqxv_maxpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
                              int32_t k, int32_t stride, int32_t pad, int32_t x_pitch, int32_t y_pitch,
                              void* stream);
+/* K9 with use_ceil=True (squeezenet.py:84,89,95; googlenet.py:95,98,103,112 and the inception pooling branch
+ * googlenet.py:228): output extent ceil((size + 2*pad - k) / stride) + 1, minus one when the last window would start
+ * beyond the input (torch's rule, which the reference's tests pin at 1e-4); partial windows are clipped. */
+int eqxv_maxpool2d_ceil_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                                  int32_t k, int32_t stride, int32_t pad, int32_t x_pitch, int32_t y_pitch,
+                                  void* stream);
 /* K10: equinox.nn.AvgPool2d(k, stride) (densenet.py:128) */
 int eqxv_avgpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
                              int32_t k, int32_t stride, int32_t x_pitch, int32_t y_pitch, void* stream);

@@ -340,6 +340,156 @@ def mobilenet_v3(state_dict, x, arch="mobilenet_v3_small"):
 
 
 # ------------------------------------------------------------------------------------------------
+# MobileNetV2 (mobilenetv2.py)
+# ------------------------------------------------------------------------------------------------
+_MBV2 = [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
+         (6, 320, 1, 1)]  # t, c, n, s: mobilenetv2.py:140-149
+
+
+def mobilenet_v2(state_dict, x, arch="mobilenet_v2"):
+    """MobileNetV2.__call__ (mobilenetv2.py:217-227) over _InvertedResidual (16-88): [expand 1x1 CNA if t != 1],
+    depthwise 3x3 CNA, 1x1 conv (no bias) -> BN, `x + conv(x)` when stride 1 and inp == oup (:42,:85-88).
+    REFERENCE QUIRK: activations are jnn.relu (:54,:67,:176,:200), not torchvision's ReLU6."""
+    s = Stream(state_dict)
+    x = _cna(s, x, 2, 1, act="relu")                                            # mobilenetv2.py:170-178
+    cin = 32
+    for t, c, n, st in _MBV2:
+        for i in range(n):
+            stride = st if i == 0 else 1
+            inp = x
+            hidden = int(round(cin * t))
+            if t != 1:
+                x = _cna(s, x, act="relu")
+            x = _cna(s, x, stride, 1, groups=hidden, act="relu")
+            x = _cna(s, x, res=inp if (stride == 1 and cin == c) else None)
+            cin = c
+    x = _cna(s, x, act="relu")                                                  # 1x1 -> 1280
+    x = O.rnd(O.adaptive_avg_pool2d(x, 1).flatten(1))
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)                  # Dropout (no-op) -> Linear
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# RegNet (regnet.py)
+# ------------------------------------------------------------------------------------------------
+def regnet(state_dict, x, arch="regnet_y_400mf", stages=None, group_width=None, se_ratio=None, stem_width=32):
+    """RegNet.__call__ (regnet.py:420-430). `stages` = [(width, depth)], per-stage stride 2 (regnet.py:254);
+    ResBottleneckBlock (regnet.py:113-167): relu(proj(x) + f(x)), f = 1x1 CNA, grouped 3x3 CNA (stride here),
+    [SE with squeeze width round(se_ratio * width_in), ReLU inside, sigmoid gate], 1x1 CNA without activation.
+    Checkpoint order per block = field order (proj, f): the projection's conv+BN first when present."""
+    if stages is None:
+        stages, group_width, se_ratio = _REGNET[arch]
+    s = Stream(state_dict)
+    x = _cna(s, x, 2, 1, act="relu")                                            # SimpleStemIN
+    cin = stem_width
+    for width, depth in stages:
+        for i in range(depth):
+            stride = 2 if i == 0 else 1
+            w_in = cin if i == 0 else width
+            proj = _cna(s, x, stride) if (w_in != width or stride != 1) else x  # 1x1, stride on the conv
+            gw = min(group_width, width)
+            y = _cna(s, x, act="relu")
+            y = _cna(s, y, stride, 1, groups=width // gw, act="relu")
+            if se_ratio:
+                y = squeeze_excitation(s, y, "relu", "sigmoid")
+            x = _cna(s, y, act="relu", res=proj)                                # relu(proj + f): regnet.py:166-167
+        cin = width
+    x = O.rnd(O.adaptive_avg_pool2d(x, 1).flatten(1))
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return out
+
+
+# (stage (width, depth) list, group width, se_ratio) as BlockParams.from_init_params yields them (regnet.py:222-297)
+_REGNET = {
+    "regnet_y_400mf": ([(48, 1), (104, 3), (208, 6), (440, 6)], 8, 0.25),
+    "regnet_x_400mf": ([(32, 1), (64, 2), (160, 7), (400, 12)], 16, None),
+    "regnet_y_800mf": ([(64, 1), (144, 3), (320, 8), (784, 2)], 16, 0.25),
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# SqueezeNet (squeezenet.py)
+# ------------------------------------------------------------------------------------------------
+_SQUEEZE = {  # "P" = max-pool 3x3/2 use_ceil=True, tuples = _Fire(in, squeeze, expand1x1, expand3x3): squeezenet.py:83-118
+    "squeezenet1_0": ((7, 96), ["P", (96, 16, 64, 64), (128, 16, 64, 64), (128, 32, 128, 128), "P",
+                                (256, 32, 128, 128), (256, 48, 192, 192), (384, 48, 192, 192), (384, 64, 256, 256), "P",
+                                (512, 64, 256, 256)]),
+    "squeezenet1_1": ((3, 64), ["P", (64, 16, 64, 64), (128, 16, 64, 64), "P", (128, 32, 128, 128),
+                                (256, 32, 128, 128), "P", (256, 48, 192, 192), (384, 48, 192, 192),
+                                (384, 64, 256, 256), (512, 64, 256, 256)]),
+}
+
+
+def squeezenet(state_dict, x, arch="squeezenet1_0"):
+    """SqueezeNet.__call__ (squeezenet.py:137-142): features -> [Dropout, conv1x1, ReLU, global avgpool] -> ravel.
+    _Fire.__call__ (squeezenet.py:47-55): relu(squeeze(x)) -> concat(relu(expand1x1), relu(expand3x3)) on channels."""
+    (k, _), layers = _SQUEEZE[arch]
+    s = Stream(state_dict)
+    x = O.conv_bn_act(x, s.take(), s.take(), None, 2, 0, act="relu")
+    for item in layers:
+        if item == "P":
+            x = O.max_pool2d(x, 3, 2, ceil_mode=True)
+            continue
+        y = O.conv_bn_act(x, s.take(), s.take(), None, act="relu")
+        e1 = O.conv_bn_act(y, s.take(), s.take(), None, act="relu")
+        e3 = O.conv_bn_act(y, s.take(), s.take(), None, 1, 1, act="relu")
+        x = torch.cat([e1, e3], 1)
+    x = O.conv_bn_act(x, s.take(), s.take(), None, act="relu")                  # classifier conv (with bias)
+    out = O.rnd(O.adaptive_avg_pool2d(x, 1)).flatten(1)
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GoogLeNet (googlenet.py)
+# ------------------------------------------------------------------------------------------------
+_INCEPTION = {  # in, 1x1, 3x3red, 3x3, 5x5red, 5x5, pool_proj: googlenet.py:97-112
+    "3a": (192, 64, 96, 128, 16, 32, 32), "3b": (256, 128, 128, 192, 32, 96, 64),
+    "4a": (480, 192, 96, 208, 16, 48, 64), "4b": (512, 160, 112, 224, 24, 64, 64),
+    "4c": (512, 128, 128, 256, 24, 64, 64), "4d": (512, 112, 144, 288, 32, 64, 64),
+    "4e": (528, 256, 160, 320, 32, 128, 128), "5a": (832, 256, 160, 320, 32, 128, 128),
+    "5b": (832, 384, 192, 384, 48, 128, 128)}
+
+
+def _inception(s: Stream, x):
+    """_Inception.__call__ (googlenet.py:232-240); BasicConv2d = conv(no bias) -> BN(eps 1e-3) -> relu (:287-311)"""
+    e = 1e-3
+    b1 = _cna(s, x, act="relu", eps=e)
+    b2 = _cna(s, _cna(s, x, act="relu", eps=e), 1, 1, act="relu", eps=e)
+    b3 = _cna(s, _cna(s, x, act="relu", eps=e), 1, 1, act="relu", eps=e)        # 3x3, not 5x5 (googlenet.py:214-216)
+    b4 = _cna(s, O.max_pool2d(x, 3, 1, 1, ceil_mode=True), act="relu", eps=e)
+    return torch.cat([b1, b2, b3, b4], 1)
+
+
+def googlenet(state_dict, x, arch="googlenet"):
+    """GoogLeNet.__call__ with aux_logits=False (googlenet.py:108-177). A checkpoint that carries the auxiliary heads
+    (torchvision saves them; the reference loads them positionally, googlenet.py:322-327) has them skipped here:
+    they sit between inception5b and fc in field order."""
+    e = 1e-3
+    s = Stream(state_dict)
+    x = _cna(s, x, 2, 3, act="relu", eps=e)
+    x = O.max_pool2d(x, 3, 2, ceil_mode=True)
+    x = _cna(s, x, act="relu", eps=e)
+    x = _cna(s, x, 1, 1, act="relu", eps=e)
+    x = O.max_pool2d(x, 3, 2, ceil_mode=True)
+    x = _inception(s, _inception(s, x))
+    x = O.max_pool2d(x, 3, 2, ceil_mode=True)
+    for _ in range(5):
+        x = _inception(s, x)
+    x = O.max_pool2d(x, 2, 2, ceil_mode=True)
+    x = _inception(s, _inception(s, x))
+    if any(k.startswith("aux1.") for k in state_dict):                          # 2 x (conv, bn.w, bn.b, fc1 w/b, fc2 w/b)
+        for _ in range(2):
+            s.take(), s.take_bn(), s.take(), s.take(), s.take(), s.take()
+    x = O.rnd(O.adaptive_avg_pool2d(x, 1).flatten(1))
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # VGG (vgg.py)
 # ------------------------------------------------------------------------------------------------
 _VGG = {"A": [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
@@ -371,6 +521,30 @@ def vgg(state_dict, x, arch="vgg11", features_only=False):
         return x
     x = O.rnd(O.adaptive_avg_pool2d(x, 7)).flatten(1)                            # ravel in C,H,W order
     x = O.linear_act(x, s.take(), s.take())
+    x = O.linear_act(x, s.take(), s.take(), act="relu")
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# AlexNet (alexnet.py) - BASELINE config 0 (README example)
+# ------------------------------------------------------------------------------------------------
+def alexnet(state_dict, x, arch="alexnet", features_only=False):
+    """AlexNet.__call__ (alexnet.py:72-85). features (alexnet.py:42-58): conv11x11/4 p2, conv5x5 p2, 3 x conv3x3 p1,
+    all WITH bias and followed by ReLU, max-pool 3x3/2 (no padding) after convs 1, 2 and 5; adaptive average pool to
+    6x6 (alexnet.py:59); classifier (alexnet.py:60-70): Dropout, Linear, ReLU, Dropout, Linear, ReLU, Linear -
+    identical to torchvision's, which is what the reference's own test pins at 1e-4 (tests/test_models/test_alexnet.py)."""
+    s = Stream(state_dict)
+    for stride, pad, pool in ((4, 2, True), (1, 2, True), (1, 1, False), (1, 1, False), (1, 1, True)):
+        w, b = s.take(), s.take()
+        x = O.conv_bn_act(x, w, b, None, stride, pad, act="relu")
+        if pool:
+            x = O.max_pool2d(x, 3, 2)
+    if features_only:
+        return x
+    x = O.rnd(O.adaptive_avg_pool2d(x, 6)).flatten(1)                            # jnp.ravel: C,H,W order
+    x = O.linear_act(x, s.take(), s.take(), act="relu")
     x = O.linear_act(x, s.take(), s.take(), act="relu")
     out = O.linear_act(x, s.take(), s.take(), round_out=False)
     assert s.done()

@@ -61,9 +61,12 @@ def layer_norm(x, weight, bias, eps=1e-5):
     return y
 
 
-def max_pool2d(x, k, stride, padding=0):
-    """equinox.nn.MaxPool2d: reduce_window(max) with -inf padding (use_ceil=False)"""
-    return F.max_pool2d(x, _pair(k), _pair(stride), _pair(padding))
+def max_pool2d(x, k, stride, padding=0, ceil_mode=False):
+    """equinox.nn.MaxPool2d: reduce_window(max) with -inf padding. use_ceil=True pads the right/bottom edge (with
+    -inf) by one extra stride when the window sweep does not divide evenly, i.e. partial windows at the edge; for
+    every shape on which the last window still overlaps the input this equals torch's ceil_mode, which is what the
+    reference's SqueezeNet / GoogLeNet tests pin at 1e-4."""
+    return F.max_pool2d(x, _pair(k), _pair(stride), _pair(padding), ceil_mode=ceil_mode)
 
 
 def avg_pool2d(x, k, stride):

@@ -220,3 +220,114 @@ def test_swin_traces_to_fused_blocks_and_loads_positionally(tmp_path):
     assert isinstance(wa, T.WindowAttention) and wa.window == (7, 7) and wa.shift == (0, 0) and wa.heads == 24
     with pytest.raises(ValueError, match="multiple of the window"):
         trace(eb.tree_inference(net, True), (3, 200, 200))
+
+
+# ---- the rest of the zoo: constructors, error conventions, and the launch plan each model lowers to
+def lower(net, shape=(3, 224, 224), batch=2, **kw):
+    """host-side dry run of the engine: trace + lower into C-ABI steps on a CPU-device plan, nothing is executed"""
+    from eqxvision_b200 import _engine as E
+
+    plan = E.Plan(torch.device("cpu"), batch, shape)
+    out = trace(net, shape, **kw)
+    syms = []
+    plan.out_struct = E._flatten_out(out, syms)
+    for s in syms:
+        plan.add_output(s)
+    names = [fn.__name__ for fn, _ in plan.steps]
+    return out, plan, {n: names.count(n) for n in set(names)}
+
+
+def test_zoo_constructors_exported_with_reference_signatures():
+    for name in ["alexnet", "AlexNet", "mobilenet_v2", "MobileNetV2", "squeezenet1_0", "squeezenet1_1", "SqueezeNet",
+                 "googlenet", "GoogLeNet", "RegNet", "regnet_y_400mf", "regnet_y_128gf", "regnet_x_400mf",
+                 "regnet_x_32gf"]:
+        assert hasattr(models, name), name
+    p = inspect.signature(models.AlexNet.__init__).parameters
+    assert list(p)[1:] == ["num_classes", "dropout", "key"] and p["dropout"].default == 0.5
+    p = inspect.signature(models.MobileNetV2.__init__).parameters
+    assert list(p)[1:] == ["num_classes", "width_mult", "inverted_residual_setting", "round_nearest", "block",
+                           "norm_layer", "dropout", "key"]
+    p = inspect.signature(models.SqueezeNet.__init__).parameters
+    assert list(p)[1:] == ["version", "num_classes", "dropout", "key"] and p["version"].default == "1_0"
+    p = inspect.signature(models.GoogLeNet.__init__).parameters
+    assert list(p)[1:] == ["num_classes", "aux_logits", "blocks", "dropout", "dropout_aux", "key"]
+    p = inspect.signature(models.RegNet.__init__).parameters
+    assert list(p)[1:] == ["block_params", "num_classes", "stem_width", "stem_type", "block_type", "norm_layer",
+                           "activation", "key"]
+
+
+def test_alexnet_lowers_to_twelve_launches_and_requires_key():
+    net = eb.tree_inference(models.alexnet(), True)
+    with pytest.raises(RuntimeError, match="PRNGKey"):          # alexnet.py:78-79
+        trace(net, (3, 224, 224), key=None)
+    out, plan, steps = lower(net)
+    assert out.shape == (1000,)
+    # 11x11/4 first layer on the generic implicit GEMM; ReLU and bias fused; 6x6 adaptive pool is the identity at 224
+    assert steps == {"nchw_to_nhwc": 1, "conv2d": 5, "maxpool2d": 3, "gemm": 3}
+    assert [f.shape for f in [trace(net.features, (3, 224, 224))]] == [(256, 6, 6)]   # test_alexnet.py:23 reaches in
+
+
+def test_mobilenet_v2_residual_folds_without_recomputing_the_producer():
+    net = eb.tree_inference(models.mobilenet_v2(), True)
+    out, plan, steps = lower(net)
+    assert out.shape == (1000,)
+    # 17 depthwise + 34 1x1 convs + stem + pool + head: `x + conv(x)` (mobilenetv2.py:86) must fold into the block's
+    # own projection conv, not into a second copy of the conv that produced x
+    assert steps["dwconv"] == 17 and steps["conv2d"] == 34 and steps["conv_stem"] == 1
+    with pytest.raises(ValueError):
+        models.MobileNetV2(inverted_residual_setting=[])
+
+
+def test_regnet_block_params_and_lowering():
+    from eqxvision_b200.models.classification.regnet import BlockParams
+
+    bp = BlockParams.from_init_params(depth=16, w_0=48, w_a=27.89, w_m=2.09, group_width=8, se_ratio=0.25)
+    assert (bp.widths, bp.depths, bp.group_widths) == ([48, 104, 208, 440], [1, 3, 6, 6], [8, 8, 8, 8])
+    bp = BlockParams.from_init_params(depth=23, w_0=80, w_a=49.56, w_m=2.88, group_width=120)
+    assert (bp.widths, bp.depths, bp.group_widths) == ([80, 240, 720, 1920], [2, 5, 15, 1], [80, 120, 120, 120])
+    with pytest.raises(ValueError):
+        BlockParams.from_init_params(depth=4, w_0=50, w_a=1.0, w_m=2.0, group_width=8)   # w_0 % 8 != 0
+    out, plan, steps = lower(eb.tree_inference(models.regnet_y_400mf(), True))
+    assert out.shape == (1000,)
+    assert steps["conv2d"] == 16 * 3 + 4 + 16 * 2 and steps["eltwise"] == 16     # 3 convs/block, 4 proj, SE fc1/fc2
+
+
+def test_grouped_weight_dense_expansion():
+    from eqxvision_b200 import _pack
+
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(24, 4, 3, 3, generator=g)                  # 6 groups of width 4 (RegNet-style geometry)
+    x = torch.randn(1, 24, 9, 9, generator=g)
+    dense = _pack.expand_grouped_weight(w, 6)
+    assert dense.shape == (24, 24, 3, 3)
+    ref = torch.nn.functional.conv2d(x, w, padding=1, groups=6)
+    assert torch.allclose(torch.nn.functional.conv2d(x, dense, padding=1), ref, atol=1e-5)
+
+
+def test_squeezenet_and_googlenet_lowering():
+    out, plan, steps = lower(eb.tree_inference(models.squeezenet1_0(), True))
+    assert out.shape == (1000,) and steps["maxpool2d"] == 3 and steps["conv2d"] == 8 * 3 + 1
+    assert sum(1 for fn, kw in plan.steps if fn.__name__ == "maxpool2d" and kw["ceil_mode"]) == 3
+    with pytest.raises(ValueError):
+        models.SqueezeNet("2_0")
+    net = eb.tree_inference(models.googlenet(), True)
+    with pytest.raises(RuntimeError, match="PRNGKey"):          # googlenet.py:112-113
+        trace(net, (3, 224, 224), key=None)
+    out, plan, steps = lower(net)
+    assert out.shape == (1000,)
+    assert steps["conv2d"] == 2 + 9 * 6 and steps["maxpool2d"] == 4 + 9     # no concat pass: branches store in place
+    assert "copy2d" not in steps and "eltwise" not in steps
+
+
+def test_googlenet_loads_torchvision_checkpoint_with_aux_heads(tmp_path):
+    """googlenet.py:320-335: the checkpoint carries aux1/aux2, the model is built with them, then aux_logits is cleared"""
+    import torchvision
+
+    torch.manual_seed(0)
+    tv = torchvision.models.googlenet(weights=None, aux_logits=True, transform_input=False, init_weights=False)
+    path = str(tmp_path / "g.pth")
+    torch.save(tv.state_dict(), path)
+    net = models.googlenet(torch_weights=path)
+    assert net.aux_logits is False and net.aux1 is not None
+    assert torch.equal(net.fc.weight, tv.fc.weight) and torch.equal(net.aux2.fc2.weight, tv.aux2.fc2.weight)
+    assert torch.equal(net.inception5b.branch4.layers[1].conv.weight, tv.inception5b.branch4[1].conv.weight)

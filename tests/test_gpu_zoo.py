@@ -1,0 +1,124 @@
+"""B200 parity for the families SURVEY.md 8(f) lists after the north-star path: AlexNet (BASELINE config 0, the
+README example), MobileNetV2, RegNet, SqueezeNet, GoogLeNet - through the public surface (constructors +
+load_torch_weights + vmap), i.e. through the C ABI. Same two comparisons as tests/test_gpu_models.py: against the
+bf16-EMULATING oracle (implementation check) and against the fp32 oracle (stated bf16 tolerance), rel-L2 over logits.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def keys(n):
+    import eqxvision_b200 as eb
+
+    return eb.random.split(eb.random.PRNGKey(0), n)
+
+
+def rb(device, *shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(device)
+
+
+@pytest.mark.parametrize("size,k,stride,pad", [(109, 3, 2, 0), (54, 3, 2, 0), (112, 3, 2, 0), (28, 3, 1, 1),
+                                               (14, 2, 2, 0), (13, 3, 2, 0)])
+def test_maxpool_ceil_mode_bit_exact(device, size, k, stride, pad):
+    """eqxv_maxpool2d_ceil_nhwc_bf16 (squeezenet.py:84, googlenet.py:95,228): selection of bf16 values, so bit exact"""
+    from eqxvision_b200 import ops
+
+    x = rb(device, 2, size, size - 1, 72, seed=size)
+    got = ops.maxpool2d(x, k, stride, pad, ceil_mode=True)
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), k, stride, pad, ceil_mode=True).permute(0, 2, 3, 1)
+    assert got.shape == ref.shape
+    assert torch.equal(got.float(), ref)
+
+
+@pytest.mark.parametrize("n,hw,cin,cout,k,stride,pad", [(2, 224, 8, 64, 11, 4, 2),     # AlexNet conv1 on the NHWC8 image
+                                                        (3, 27, 64, 192, 5, 1, 2),     # AlexNet conv2: 5x5, generic path
+                                                        (2, 13, 192, 384, 3, 1, 1),    # AlexNet conv3
+                                                        (1, 63, 8, 64, 11, 4, 2)])     # minimum input (alexnet.py:95)
+def test_alexnet_conv_shapes(device, n, hw, cin, cout, k, stride, pad):
+    from eqxvision_b200 import ops
+
+    x = rb(device, n, hw, hw, cin, seed=1)
+    if cin == 8:
+        x[..., 3:] = 0                                                    # channels 3..7 are the zero padding
+    wt = rb(device, cout, k, k, cin, scale=(k * k * min(cin, 64)) ** -0.5, seed=2)
+    bias = torch.randn(cout, generator=torch.Generator().manual_seed(3)).to(device)
+    y = ops.conv2d(x, wt.reshape(cout, -1), bias, cin=cin, cout=cout, kh=k, kw=k, stride=stride, pad=pad, act=1)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, stride=stride,
+                          padding=pad))
+    assert y.shape[1:3] == ref.shape[2:]
+    assert rel(y, ref.permute(0, 2, 3, 1)) < 4e-3
+
+
+@pytest.mark.parametrize("kh,stride,cout,hw", [(7, 2, 96, 224), (3, 2, 64, 224), (7, 2, 96, 21)])
+def test_unpadded_stem_convs(device, kh, stride, cout, hw):
+    """SqueezeNet's first layers have no padding (squeezenet.py:82,101)"""
+    from eqxvision_b200 import _pack, ops
+
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, hw, hw, generator=g).to(device)
+    wt = torch.randn(cout, 3, kh, kh, generator=g) * (3 * kh * kh) ** -0.5
+    bias = torch.randn(cout, generator=g).to(device)
+    xpad = ops.pack_stem_input(x, pad=0)
+    y = ops.conv_stem(xpad, _pack.pack_stem_weight(wt).to(device), bias, n=2, h=hw, w=hw, cout=cout, kh=kh, kw=kh,
+                      stride=stride, pad=0, act=1)
+    ref = F.relu(F.conv2d(x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float().to(device), bias, stride=stride))
+    assert rel(y, ref.permute(0, 2, 3, 1)) < 4e-3
+
+
+# (ctor, oracle fn, input hw, batch, tol vs emulation, tol vs fp32)
+ZOO = [("alexnet", "alexnet", 224, 3, 1e-2, 3e-2),
+       ("mobilenet_v2", "mobilenet_v2", 224, 2, 1e-2, 3e-2),
+       ("regnet_y_400mf", "regnet", 224, 2, 1.5e-2, 4e-2),
+       ("regnet_x_400mf", "regnet", 128, 2, 1.5e-2, 4e-2),
+       ("squeezenet1_0", "squeezenet", 224, 2, 1.5e-2, 4e-2),
+       ("squeezenet1_1", "squeezenet", 224, 2, 1.5e-2, 4e-2),
+       ("googlenet", "googlenet", 224, 2, 1.5e-2, 4e-2)]
+
+
+@pytest.mark.parametrize("arch,fn,hw,batch,tol_emu,tol_f32", ZOO, ids=[z[0] for z in ZOO])
+def test_zoo_parity(device, save_checkpoint, arch, fn, hw, batch, tol_emu, tol_f32):
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    kw = {"aux_logits": True, "transform_input": False, "init_weights": True} if arch == "googlenet" else {}
+    sd = ck.torchvision_state_dict(arch, seed=1, **kw)
+    net = eb.tree_inference(getattr(eb.models, arch)(torch_weights=save_checkpoint(sd, arch + ".pth")), True)
+    x = ck.synthetic_images(batch, h=hw, w=hw, seed=2)
+    got = eb.vmap(net, axis_name="batch")(x, key=keys(batch))
+    oracle = getattr(om, fn)
+    ref = oracle(sd, x, arch)
+    with O.emulate_bf16():
+        emu = oracle(sd, x, arch)
+    assert got.shape == ref.shape == (batch, 1000) and got.dtype == torch.float32 and got.is_cuda
+    assert rel(got, emu) < tol_emu, ("vs bf16-emulating oracle", rel(got, emu))
+    assert rel(got, ref) < tol_f32, ("vs fp32 oracle", rel(got, ref))
+
+
+def test_alexnet_readme_example_single_image(device, save_checkpoint):
+    """BASELINE config 0 / README.md:37-46: `filter_jit(vmap(net, axis_name="batch"))(images, key=keys)` on a
+    1x3x224x224 batch, and `.features` as the reference's own test reaches it (tests/test_models/test_alexnet.py:23)"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+
+    sd = ck.torchvision_state_dict("alexnet", seed=1)
+    net = eb.tree_inference(eb.models.alexnet(torch_weights=save_checkpoint(sd)), True)
+    x = ck.synthetic_images(1, seed=0, normalize=False)                    # jr.uniform(key, (1, 3, 224, 224))
+    fwd = eb.filter_jit(eb.vmap(net, axis_name="batch"))
+    out = fwd(x, key=keys(1))
+    assert out.shape == (1, 1000)
+    assert rel(out, om.alexnet(sd, x)) < 3e-2
+    feats = eb.vmap(net.features, axis_name="batch")(x, key=keys(1))
+    assert feats.shape == (1, 256, 6, 6)
+    assert rel(feats, om.alexnet(sd, x, features_only=True)) < 3e-2
