@@ -354,7 +354,30 @@ def _feeds(p: Sym, q: Sym, limit: int = 64) -> bool:
     return False
 
 
+def _scale_channels(x: Sym, s) -> Optional[Sym]:
+    """per-channel constant gain `s` (C,1,1) on a map produced by a Linear2d (ConvNeXt layer scale, convnext.py:62):
+    folded into that Linear's rows on the host, so the GEMM epilogue (and the residual add that follows) is unchanged"""
+    inner, rewrap = _under_view(x)
+    if inner is None or not isinstance(inner.expr, Linear):
+        return None
+    e = inner.expr
+    if e.act1 is not None or e.res is not None or e.act2 is not None:
+        return None
+    g = s.detach().float().reshape(-1)
+    if g.numel() != e.weight.shape[0]:
+        return None
+    w = e.weight.detach().float() * g[:, None]
+    b = None if e.bias is None else e.bias.detach().float().reshape(-1) * g
+    return rewrap(Sym(inner.kind, inner.shape, e.replace(weight=w, bias=b)))
+
+
 def mul(a, b) -> Sym:
+    for x, s in ((a, b), (b, a)):
+        if is_sym(x) and isinstance(s, torch.Tensor) and x.kind == "chw" and tuple(s.shape) == (x.shape[0], 1, 1):
+            y = _scale_channels(x, s)
+            if y is not None:
+                return y
+            raise NotImplementedError("constant per-channel scale is only built behind a Linear2d (ConvNeXt layer scale)")
     if is_sym(a) and is_sym(b):
         for x, s in ((a, b), (b, a)):
             if x.kind == "chw" and s.kind == "chw" and s.shape == (x.shape[0], 1, 1):

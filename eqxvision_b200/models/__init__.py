@@ -19,6 +19,13 @@ from .classification.vit import (  # noqa: F401
     vit_small,
     vit_tiny,
 )
+from .classification.convnext import (  # noqa: F401
+    ConvNeXt,
+    convnext_base,
+    convnext_large,
+    convnext_small,
+    convnext_tiny,
+)
 from .classification.densenet import DenseNet, densenet121, densenet161, densenet169, densenet201  # noqa: F401
 from .classification.efficientnet import (  # noqa: F401
     EfficientNet,

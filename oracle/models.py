@@ -490,6 +490,50 @@ def googlenet(state_dict, x, arch="googlenet"):
 
 
 # ------------------------------------------------------------------------------------------------
+# ConvNeXt (convnext.py)
+# ------------------------------------------------------------------------------------------------
+_CONVNEXT = {"convnext_tiny": [(96, 3), (192, 3), (384, 9), (768, 3)], "convnext_small": [(96, 3), (192, 3), (384, 27), (768, 3)],
+             "convnext_base": [(128, 3), (256, 3), (512, 27), (1024, 3)], "convnext_large": [(192, 3), (384, 3), (768, 27), (1536, 3)]}
+
+
+def _ln2d(x, w, b, eps):
+    """LayerNorm2d (layers/extensions_2d.py:24-28): per-pixel LayerNorm over channels"""
+    return O.rnd(O.layer_norm(x.permute(0, 2, 3, 1), w, b, eps).permute(0, 3, 1, 2))
+
+
+def convnext(state_dict, x, arch="convnext_tiny", block_eps=1e-5, eps=1e-6):
+    """ConvNeXt.__call__ (convnext.py:198-204) over CNBlock (convnext.py:16-66):
+    x + layer_scale * Linear2d(gelu_tanh(Linear2d(LayerNorm2d(dwconv7x7(x))))).
+    REFERENCE QUIRKS: jnn.gelu = tanh approximation (convnext.py:52); the block norm is `LayerNorm2d(dim)` with the
+    equinox default eps 1e-5 (convnext.py:24,39) while the other norms get 1e-6 (convnext.py:120).
+    Checkpoint order per block: layer_scale, dw w/b, norm w/b, fc1 w/b, fc2 w/b (field order convnext.py:17-19)."""
+    s = Stream(state_dict)
+    x = O.conv_bn_act(x, s.take(), s.take(), None, 4, 0)                        # stem conv 4x4/4 with bias
+    x = _ln2d(x, s.take(), s.take(), eps)
+    stages = _CONVNEXT[arch]
+    for si, (dim, depth) in enumerate(stages):
+        for _ in range(depth):
+            gamma = s.take().reshape(-1)
+            wd, bd = s.take(), s.take()
+            y = O.conv_bn_act(x, wd, bd, None, 1, 3, groups=dim)
+            y = _ln2d(y, s.take(), s.take(), block_eps)
+            t = y.permute(0, 2, 3, 1)
+            t = O.linear_act(t, s.take(), s.take(), act="gelu")
+            w2, b2 = s.take(), s.take()
+            # the device folds layer_scale into fc2's rows (fp32 product, one bf16 rounding of the weight)
+            t = O.linear_act(t, w2 * gamma[:, None], b2 * gamma, res=x.permute(0, 2, 3, 1))
+            x = t.permute(0, 3, 1, 2)
+        if si + 1 < len(stages):
+            x = _ln2d(x, s.take(), s.take(), eps)
+            x = O.conv_bn_act(x, s.take(), s.take(), None, 2, 0)                # downsample conv 2x2/2 with bias
+    x = O.rnd(O.adaptive_avg_pool2d(x, 1))
+    x = _ln2d(x, s.take(), s.take(), eps).flatten(1)
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # VGG (vgg.py)
 # ------------------------------------------------------------------------------------------------
 _VGG = {"A": [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],

@@ -240,7 +240,7 @@ def lower(net, shape=(3, 224, 224), batch=2, **kw):
 def test_zoo_constructors_exported_with_reference_signatures():
     for name in ["alexnet", "AlexNet", "mobilenet_v2", "MobileNetV2", "squeezenet1_0", "squeezenet1_1", "SqueezeNet",
                  "googlenet", "GoogLeNet", "RegNet", "regnet_y_400mf", "regnet_y_128gf", "regnet_x_400mf",
-                 "regnet_x_32gf"]:
+                 "regnet_x_32gf", "ConvNeXt", "convnext_tiny", "convnext_small", "convnext_base", "convnext_large"]:
         assert hasattr(models, name), name
     p = inspect.signature(models.AlexNet.__init__).parameters
     assert list(p)[1:] == ["num_classes", "dropout", "key"] and p["dropout"].default == 0.5
@@ -317,6 +317,26 @@ def test_squeezenet_and_googlenet_lowering():
     assert out.shape == (1000,)
     assert steps["conv2d"] == 2 + 9 * 6 and steps["maxpool2d"] == 4 + 9     # no concat pass: branches store in place
     assert "copy2d" not in steps and "eltwise" not in steps
+
+
+def test_convnext_layer_scale_folds_into_the_second_gemm():
+    net = eb.tree_inference(models.convnext_tiny(), True)
+    out, plan, steps = lower(net)
+    assert out.shape == (1000,)
+    # 18 blocks x (depthwise 7x7, LayerNorm, 2 GEMMs) + stem + 3 x (LayerNorm, conv2x2/2) + pool + LayerNorm + head:
+    # layer_scale and the residual add are not separate passes
+    assert steps == {"pack_stem_input": 1, "conv_stem": 1, "dwconv": 18, "layernorm": 18 + 1 + 3 + 1,
+                     "gemm": 36 + 1, "conv2d": 3, "adaptive_avgpool": 1}
+    blk = net.features.layers[1].layers[0]
+    assert blk.block.layers[1].eps == 1e-5 and net.features.layers[0].layers[1].eps == 1e-6   # convnext.py:24 vs :120
+    y = trace(blk, (96, 8, 8))
+    lin = y.expr.x.expr                                                    # ToMap(Linear)
+    assert isinstance(lin, T.Linear) and lin.res is not None
+    assert torch.allclose(lin.weight, blk.block.layers[4].weight * blk.layer_scale.reshape(-1, 1))
+    with pytest.raises(ValueError):
+        models.ConvNeXt([])
+    with pytest.raises(TypeError):
+        models.ConvNeXt([(96, 192, 3)])
 
 
 def test_googlenet_loads_torchvision_checkpoint_with_aux_heads(tmp_path):

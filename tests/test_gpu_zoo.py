@@ -74,14 +74,42 @@ def test_unpadded_stem_convs(device, kh, stride, cout, hw):
     assert rel(y, ref.permute(0, 2, 3, 1)) < 4e-3
 
 
+@pytest.mark.parametrize("c,hw", [(96, 56), (192, 28), (768, 7), (104, 9)])
+def test_depthwise_7x7(device, c, hw):
+    """ConvNeXt's depthwise 7x7 p3 with bias and no activation (convnext.py:38-46)"""
+    from eqxvision_b200 import _pack, ops
+
+    g = torch.Generator().manual_seed(c)
+    x = rb(device, 2, hw, hw, c, seed=c)
+    wt = torch.randn(c, 1, 7, 7, generator=g) / 7.0
+    bias = torch.randn(c, generator=g)
+    y = ops.dwconv(x, _pack.pack_depthwise_weight(wt, c).to(device), bias.to(device), k=7, stride=1, pad=3, dil=1, act=0)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(device), bias.to(device), padding=3, groups=c)
+    assert rel(y, ref.permute(0, 2, 3, 1)) < 4e-3
+
+
+@pytest.mark.parametrize("n,hw,cin,cout", [(2, 56, 96, 192), (3, 14, 384, 768), (1, 6, 104, 40)])
+def test_downsample_conv_2x2_stride_2(device, n, hw, cin, cout):
+    """ConvNeXt stage transitions: conv 2x2/2 with bias, no padding (convnext.py:157-163)"""
+    from eqxvision_b200 import ops
+
+    x = rb(device, n, hw, hw, cin, seed=1)
+    wt = rb(device, cout, 2, 2, cin, scale=(4 * cin) ** -0.5, seed=2)
+    bias = torch.randn(cout, generator=torch.Generator().manual_seed(3)).to(device)
+    y = ops.conv2d(x, wt.reshape(cout, -1), bias, cin=cin, cout=cout, kh=2, kw=2, stride=2, pad=0, act=0)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, stride=2)
+    assert rel(y, ref.permute(0, 2, 3, 1)) < 4e-3
+
+
 # (ctor, oracle fn, input hw, batch, tol vs emulation, tol vs fp32)
 ZOO = [("alexnet", "alexnet", 224, 3, 1e-2, 3e-2),
        ("mobilenet_v2", "mobilenet_v2", 224, 2, 1e-2, 3e-2),
        ("regnet_y_400mf", "regnet", 224, 2, 1.5e-2, 4e-2),
-       ("regnet_x_400mf", "regnet", 128, 2, 1.5e-2, 4e-2),
+       ("regnet_x_400mf", "regnet", 224, 2, 2e-2, 5e-2),
        ("squeezenet1_0", "squeezenet", 224, 2, 1.5e-2, 4e-2),
        ("squeezenet1_1", "squeezenet", 224, 2, 1.5e-2, 4e-2),
-       ("googlenet", "googlenet", 224, 2, 1.5e-2, 4e-2)]
+       ("googlenet", "googlenet", 224, 2, 1.5e-2, 4e-2),
+       ("convnext_tiny", "convnext", 224, 2, 1.5e-2, 4e-2)]
 
 
 @pytest.mark.parametrize("arch,fn,hw,batch,tol_emu,tol_f32", ZOO, ids=[z[0] for z in ZOO])

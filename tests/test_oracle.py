@@ -262,6 +262,25 @@ def test_family_oracle_matches_torchvision(arch, fn, hw, kw):
     assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
 
 
+def test_convnext_oracle_matches_torchvision_with_reference_quirks():
+    """ConvNeXt (convnext.py): the oracle == torchvision once torchvision is given the reference's two deviations:
+    tanh-GELU (jnn.gelu, convnext.py:52) and eps 1e-5 in the block LayerNorm (convnext.py:24,39); and it differs
+    from stock torchvision, i.e. the quirks are visible (tests/test_models/test_convnext.py is argmax-only)"""
+    m = ck.torchvision_model("convnext_tiny", seed=1)
+    x = ck.synthetic_images(2, h=64, w=64, seed=2)
+    with torch.no_grad():
+        stock = m(x)
+    for blk in m.modules():
+        if type(blk).__name__ == "CNBlock":
+            blk.block[2].eps = 1e-5
+            blk.block[4] = torch.nn.GELU(approximate="tanh")
+    with torch.no_grad():
+        ref = m(x)
+    got = om.convnext(m.state_dict(), x, "convnext_tiny")
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
+    assert not torch.allclose(got, stock, atol=1e-4, rtol=1e-4)
+
+
 @pytest.mark.parametrize("arch", ["vgg11", "vgg11_bn"])
 def test_vgg_features_oracle_matches_torchvision(arch):
     """the reference compares `.features` only (tests/test_models/test_vgg.py:30): its classifier deviates from

@@ -51,6 +51,14 @@ def _perturb_and_calibrate(model: torch.nn.Module, seed: int, calib_shape=(4, 3,
             if last is not None:
                 bn = getattr(m, last)
                 bn.weight.copy_(torch.rand(bn.weight.shape, generator=g) * 0.3 + 0.2)
+            if type(m).__name__ == "CNBlock":  # ConvNeXt: the default layer scale 1e-6 would hide the whole branch
+                m.layer_scale.copy_(torch.rand(m.layer_scale.shape, generator=g) * 0.4 + 0.1)
+            if type(m).__name__ == "LayerNorm2d":  # torchvision.models.convnext.LayerNorm2d only
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.8 + 0.6)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+            if type(m).__name__ == "ResBottleneckBlock":  # RegNet: x + f(x), the branch ends in f.c = (conv, bn)
+                bn = m.f.c[1]
+                bn.weight.copy_(torch.rand(bn.weight.shape, generator=g) * 0.3 + 0.2)
         for m in model.modules():
             if isinstance(m, (torch.nn.Linear, torch.nn.Conv2d)) and m.bias is not None:
                 m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
