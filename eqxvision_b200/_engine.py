@@ -91,7 +91,7 @@ class Plan:
         self.steps.append((fn, kw))
 
     # -------------------------------------------------------------- emission
-    _DIRECT_DST = (T.Conv, T.Pool, T.Resize)  # nodes that can write straight into a caller-provided slice
+    _DIRECT_DST = (T.Conv, T.Pool, T.Resize, T.ChannelView)  # nodes that can write straight into a caller-provided slice
 
     def emit(self, sym: T.Sym, out_f32: bool = False, dst: Optional[Buf] = None) -> Buf:
         """Lower `sym` (memoised). With `dst` the result must end up in that buffer slice: producers
@@ -462,7 +462,7 @@ class Plan:
         base = grp["base"]
         for x in e.xs[len(grp["ids"]):]:
             cx = x.shape[0]
-            off = grp["width"]
+            off = (grp["width"] + e.align - 1) // e.align * e.align
             if off % 8 != 0:
                 raise NotImplementedError("concat slices must start at a multiple of 8 channels")
             sl = Buf(torch.as_strided(base, (rows, cx), (base.stride(0), 1), base.storage_offset() + off), cx,
@@ -472,6 +472,17 @@ class Plan:
             grp["width"] = off + cx
         view = torch.as_strided(base, (rows, c_tot), (base.stride(0), 1), base.storage_offset())
         return Buf(view, c_tot, self.n, (h, w))
+
+    def _emit_ChannelView(self, sym, e: T.ChannelView, dst: Optional[Buf] = None):
+        """A channel gather that has to exist in memory (the pass-through half of a ShuffleNetV2 unit,
+        shufflenetv2.py:134-135, or the input of a depthwise conv): a 1x1 convolution with a 0/1 selection matrix on
+        the tensor-core GEMM. Exact: each output is one bf16 input times 1.0 in an fp32 accumulator. Dense
+        convolutions never get here, they absorb the gather into their filter (`_trace.conv2d`)."""
+        sel = torch.zeros((len(e.idx), e.x.shape[0], 1, 1), dtype=torch.float32)
+        sel[torch.arange(len(e.idx)), torch.tensor(e.idx, dtype=torch.long)] = 1.0
+        conv = T.Conv(e.x, sel, None, (1, 1), (0, 0), (1, 1), 1)
+        self.keep.append(conv)
+        return self._emit_Conv(sym, conv, False, dst)
 
     def _emit_Resize(self, sym, e: T.Resize, dst: Optional[Buf] = None):
         """bilinear upsample kept in NHWC bf16 (ASPP pooling branch broadcast, deeplabv3.py:74)"""

@@ -161,11 +161,19 @@ class SelectRow(Expr):
 
 
 class Concat(Expr):  # channel concatenation, densenet.py:63, deeplabv3.py:134
-    __slots__ = ("xs", "capacity")
+    __slots__ = ("xs", "capacity", "align")
 
-    def __init__(self, xs, capacity=None):
+    def __init__(self, xs, capacity=None, align=1):
         self.xs = tuple(xs)
         self.capacity = capacity  # hint: final width of the buffer this concat will grow into
+        self.align = align        # every member starts at a multiple of `align` channels (pad channels stay zero)
+
+
+class ChannelView(Expr):  # lazy channel gather: out[j] = x[idx[j]] (jnp.split / _channel_shuffle, shufflenetv2.py:14-20,134)
+    __slots__ = ("x", "idx")
+
+    def __init__(self, x, idx):
+        self.x, self.idx = x, tuple(int(i) for i in idx)
 
 
 class Resize(Expr):  # jax.image.resize(method="bilinear"), _utils.py:52
@@ -260,6 +268,13 @@ def conv2d(x: Sym, weight, bias, stride, padding, dilation, groups) -> Sym:
     c, h, w = x.shape
     if c != cin_g * groups:
         raise ValueError(f"Conv2d: input has {c} channels, weight expects {cin_g * groups}")
+    if isinstance(x.expr, ChannelView) and groups == 1:
+        # a dense convolution over gathered channels == the same convolution over the underlying buffer with the
+        # filter's input channels scattered to their physical positions (zeros elsewhere): the gather costs nothing
+        base = x.expr.x
+        wide = torch.zeros((cout, base.shape[0], kh, kw), dtype=torch.float32)
+        wide.index_add_(1, torch.tensor(x.expr.idx, dtype=torch.long), weight.detach().float())
+        x, weight, c = base, wide, base.shape[0]
     (sh, sw), (ph, pw), (dh, dw) = _pair(stride), _pair(padding), _pair(dilation)
     ho = (h + 2 * ph - dh * (kh - 1) - 1) // sh + 1
     wo = (w + 2 * pw - dw * (kw - 1) - 1) // sw + 1
@@ -479,7 +494,47 @@ def concat_channels(xs: Sequence[Sym], capacity: Optional[int] = None) -> Sym:
     for x in xs:
         if x.kind != "chw" or x.shape[1:] != (h, w):
             raise ValueError("concat_channels: spatial shape mismatch")
-    return Sym("chw", (sum(x.shape[0] for x in xs), h, w), Concat(xs, capacity))
+    widths = [x.shape[0] for x in xs]
+    if capacity is None and any(c % 8 for c in widths[:-1]):
+        # members that do not end on an 8-channel (16-byte) boundary (ShuffleNetV2 x1.0: 58 + 58): each member gets
+        # an aligned slot in a wider buffer whose pad channels stay zero; the logical tensor is a view that skips them
+        idx, off = [], 0
+        for c in widths:
+            idx.extend(range(off, off + c))
+            off += (c + 7) // 8 * 8
+        phys = Sym("chw", (off - ((widths[-1] + 7) // 8 * 8) + widths[-1], h, w), Concat(xs, None, align=8))
+        return channel_view(phys, idx)
+    return Sym("chw", (sum(widths), h, w), Concat(xs, capacity))
+
+
+def channel_view(x: Sym, idx) -> Sym:
+    """out[j] = x[idx[j]] over the channel axis of a (C,H,W) map, lazily (composes; the identity disappears)"""
+    if x.kind != "chw":
+        raise ValueError("channel_view expects a (C,H,W) map")
+    idx = [int(i) for i in idx]
+    if isinstance(x.expr, ChannelView):
+        inner = x.expr.idx
+        idx = [inner[i] for i in idx]
+        x = x.expr.x
+    if idx == list(range(x.shape[0])):
+        return x
+    return Sym("chw", (len(idx),) + x.shape[1:], ChannelView(x, idx))
+
+
+def split_channels(x: Sym, sections: int):
+    """jnp.split(x, sections, axis=0) on a (C,H,W) map (shufflenetv2.py:134)"""
+    c = x.shape[0]
+    if c % sections:
+        raise ValueError("array split does not result in an equal division")
+    step = c // sections
+    return [channel_view(x, range(i * step, (i + 1) * step)) for i in range(sections)]
+
+
+def channel_shuffle(x: Sym, groups: int) -> Sym:
+    """_channel_shuffle (shufflenetv2.py:14-20): (g, c/g, H, W) -> transpose(1, 0) -> flatten"""
+    c = x.shape[0]
+    cpg = c // groups
+    return channel_view(x, [(j % groups) * cpg + j // groups for j in range(c)])
 
 
 def resize_bilinear(x: Sym, h: int, w: int) -> Sym:

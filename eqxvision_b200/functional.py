@@ -44,6 +44,8 @@ identity.act_name = None
 # graph helpers re-exported for model code
 ravel = T.ravel
 concat_channels = T.concat_channels
+split_channels = T.split_channels
+channel_shuffle = T.channel_shuffle
 resize_bilinear = T.resize_bilinear
 prepend_cls_add_pos = T.prepend_cls_add_pos
 attention = T.attention

@@ -62,6 +62,13 @@ from .classification.regnet import (  # noqa: F401
     regnet_y_400mf,
     regnet_y_800mf,
 )
+from .classification.shufflenetv2 import (  # noqa: F401
+    ShuffleNetV2,
+    shufflenet_v2_x0_5,
+    shufflenet_v2_x1_0,
+    shufflenet_v2_x1_5,
+    shufflenet_v2_x2_0,
+)
 from .classification.squeezenet import SqueezeNet, squeezenet1_0, squeezenet1_1  # noqa: F401
 from .classification.vgg import VGG, vgg11, vgg11_bn, vgg13, vgg13_bn, vgg16, vgg16_bn, vgg19, vgg19_bn  # noqa: F401
 from .segmentation.deeplabv3 import DeepLabV3, deeplabv3  # noqa: F401

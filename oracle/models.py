@@ -534,6 +534,49 @@ def convnext(state_dict, x, arch="convnext_tiny", block_eps=1e-5, eps=1e-6):
 
 
 # ------------------------------------------------------------------------------------------------
+# ShuffleNetV2 (shufflenetv2.py)
+# ------------------------------------------------------------------------------------------------
+_SHUFFLENET = {"shufflenet_v2_x0_5": [24, 48, 96, 192, 1024], "shufflenet_v2_x1_0": [24, 116, 232, 464, 1024],
+               "shufflenet_v2_x1_5": [24, 176, 352, 704, 1024], "shufflenet_v2_x2_0": [24, 244, 488, 976, 2048]}
+
+
+def channel_shuffle(x, groups):
+    """_channel_shuffle (shufflenetv2.py:14-20)"""
+    n, c, h, w = x.shape
+    return x.reshape(n, groups, c // groups, h, w).transpose(1, 2).reshape(n, c, h, w)
+
+
+def shufflenet_v2(state_dict, x, arch="shufflenet_v2_x1_0"):
+    """ShuffleNetV2.__call__ (shufflenetv2.py:252-262) over _InvertedResidual (shufflenetv2.py:132-140).
+    The split / concat / shuffle only move bf16 values around, so they add no rounding in the emulating mode."""
+    ch = _SHUFFLENET[arch]
+    s = Stream(state_dict)
+    x = _cna(s, x, 2, 1, act="relu")
+    x = O.max_pool2d(x, 3, 2, 1)
+    for repeats, cout in zip([4, 8, 4], ch[1:4]):
+        for i in range(repeats):
+            if i == 0:                                                          # stride 2: both branches see x
+                b1 = _cna(s, x, 2, 1, groups=x.shape[1])
+                b1 = _cna(s, b1, act="relu")
+                b2 = _cna(s, x, act="relu")
+                b2 = _cna(s, b2, 2, 1, groups=cout // 2)
+                b2 = _cna(s, b2, act="relu")
+                x = torch.cat([b1, b2], 1)
+            else:                                                               # stride 1: x1 passes through
+                x1, x2 = x.chunk(2, 1)
+                b2 = _cna(s, x2, act="relu")
+                b2 = _cna(s, b2, 1, 1, groups=cout // 2)
+                b2 = _cna(s, b2, act="relu")
+                x = torch.cat([x1, b2], 1)
+            x = channel_shuffle(x, 2)
+    x = _cna(s, x, act="relu")
+    x = O.rnd(O.adaptive_avg_pool2d(x, 1).flatten(1))
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # VGG (vgg.py)
 # ------------------------------------------------------------------------------------------------
 _VGG = {"A": [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],

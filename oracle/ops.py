@@ -138,25 +138,36 @@ def resize_bilinear(x, h, w):
 # to separate implementation errors (tight tolerance vs the emulation) from the precision gap
 # (stated tolerance vs the plain fp32 oracle).
 _EMULATE = False
+_ROUND_ACTIVATIONS = True
 
 
 class emulate_bf16:
-    def __init__(self, on: bool = True):
-        self.on = on
+    """`activations=False` keeps the bf16 filters (BatchNorm folded before the rounding, as the device packs them)
+    but leaves every activation in fp32: the mode tests/test_plan_lowering.py compares the fp32 replay of a launch
+    plan against, where the only remaining difference is fp32 summation order."""
+
+    def __init__(self, on: bool = True, activations: bool = True):
+        self.on, self.activations = on, activations
 
     def __enter__(self):
-        global _EMULATE
-        self.prev, _EMULATE = _EMULATE, self.on
+        global _EMULATE, _ROUND_ACTIVATIONS
+        self.prev, _EMULATE = (_EMULATE, _ROUND_ACTIVATIONS), self.on
+        _ROUND_ACTIVATIONS = self.activations
         return self
 
     def __exit__(self, *exc):
-        global _EMULATE
-        _EMULATE = self.prev
+        global _EMULATE, _ROUND_ACTIVATIONS
+        _EMULATE, _ROUND_ACTIVATIONS = self.prev
 
 
 def rnd(x):
-    """round to bf16 (round-to-nearest-even) when emulating, identity otherwise"""
-    return x.to(torch.bfloat16).to(torch.float32) if _EMULATE else x
+    """round an ACTIVATION to bf16 (round-to-nearest-even) when emulating, identity otherwise"""
+    return x.to(torch.bfloat16).to(torch.float32) if (_EMULATE and _ROUND_ACTIVATIONS) else x
+
+
+def rnd_w(w):
+    """round a packed FILTER to bf16 when emulating"""
+    return w.to(torch.bfloat16).to(torch.float32) if _EMULATE else w
 
 
 def conv_bn_act(x, weight, bias=None, bn=None, stride=1, padding=0, dilation=1, groups=1, act=None, res=None,
@@ -171,7 +182,10 @@ def conv_bn_act(x, weight, bias=None, bn=None, stride=1, padding=0, dilation=1, 
             shift = bn[1].double() - bn[2].double() * scale
             w = w * scale.reshape(-1, 1, 1, 1)
             b = shift if b is None else b * scale + shift
-        y = conv2d(rnd(x), rnd(w.float()), None if b is None else b.float(), stride, padding, dilation, groups)
+        # depthwise filters stay fp32 on the device ([K*K][C] fp32, _pack.pack_depthwise_weight): no rounding there
+        depthwise = groups > 1 and groups == w.shape[0] and w.shape[1] == 1
+        wq = w.float() if depthwise else rnd_w(w.float())
+        y = conv2d(rnd(x), wq, None if b is None else b.float(), stride, padding, dilation, groups)
     else:
         y = conv2d(x, weight, bias, stride, padding, dilation, groups)
         if bn is not None:
@@ -186,7 +200,7 @@ def conv_bn_act(x, weight, bias=None, bn=None, stride=1, padding=0, dilation=1, 
 
 def linear_act(x, weight, bias=None, act=None, res=None, round_out=True):
     """Linear -> act (+ residual after): one fused device GEMM"""
-    y = linear(rnd(x), rnd(weight), bias)
+    y = linear(rnd(x), rnd_w(weight), bias)
     y = ACTS[act](y)
     if res is not None:
         y = y + res

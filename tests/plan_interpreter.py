@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE - a torch-CPU executor for the launch plans `_engine.Plan` records.
+
+The product has no CPU path: `ops.*` raise without a CUDA device. What this file checks is the HOST logic of the engine
+without a GPU - weight packing, BatchNorm folding, residual order, concat slots, channel views, flatten permutations:
+every recorded step `(ops.<fn>, kwargs)` is replayed with a plain torch implementation of that C entry's documented
+contract (include/eqxv_b200.h), writing into the plan's own (CPU-resident) buffers. Outputs are compared with the
+bf16-emulating oracle in tests/test_plan_lowering.py. Only tests import this module.
+"""
+import torch
+import torch.nn.functional as F
+
+BF16 = torch.bfloat16
+
+
+def _act(y, code):
+    from eqxvision_b200 import _lib as L
+
+    if code == L.ACT_NONE:
+        return y
+    if code == L.ACT_RELU:
+        return F.relu(y)
+    if code == L.ACT_SILU:
+        return F.silu(y)
+    if code == L.ACT_GELU_TANH:
+        return F.gelu(y, approximate="tanh")
+    if code == L.ACT_HARDSWISH:
+        return F.hardswish(y)
+    if code == L.ACT_SIGMOID:
+        return torch.sigmoid(y)
+    if code == L.ACT_HARDSIGMOID:
+        return F.hardsigmoid(y)
+    if code == L.ACT_RELU6:
+        return F.relu6(y)
+    raise ValueError(code)
+
+
+def _epilogue(y, bias, act, residual, res_after_act):
+    """y fp32 [..., C] channels-last: + bias, then (residual, act) in the order the flag says"""
+    if bias is not None:
+        y = y + bias.float()[: y.shape[-1]]
+    if residual is not None and not res_after_act:
+        y = y + residual.float()[..., : y.shape[-1]]
+    y = _act(y, act)
+    if residual is not None and res_after_act:
+        y = y + residual.float()[..., : y.shape[-1]]
+    return y
+
+
+def _store(out, y):
+    out[..., : y.shape[-1]].copy_(y.to(out.dtype))
+
+
+def nchw_to_nhwc(x, c_pad, out, **_):
+    out.zero_()
+    out[..., : x.shape[1]].copy_(x.permute(0, 2, 3, 1).to(out.dtype))
+
+
+def nhwc_to_nchw(x, c, out, **_):
+    out.copy_(x[..., :c].float().permute(0, 3, 1, 2))
+
+
+def pack_stem_input(x_nchw, pad, out, **_):
+    n, c, h, w = x_nchw.shape
+    out.zero_()
+    out[:, pad:pad + h, pad:pad + w, :c].copy_(x_nchw.permute(0, 2, 3, 1).to(out.dtype))
+
+
+def conv_stem(xpad, wgt, bias, n, h, w, cout, kh, kw, stride, pad, act, out, **_):
+    # xpad [n, h+2p, w+8, 8] with the image at (pad, pad); wgt [cout, kh, 8(s), 8(c)] with zero taps for s >= kw
+    img = xpad[:, :, : w + 2 * pad, :].float().permute(0, 3, 1, 2)
+    wt = wgt.float().reshape(cout, kh, 8, 8)[:, :, :kw, :].permute(0, 3, 1, 2)
+    y = F.conv2d(img, wt, None, stride=stride).permute(0, 2, 3, 1)
+    _store(out, _epilogue(y, bias, act, None, False))
+
+
+def conv2d(x, wgt, bias, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, residual=None, res_after_act=False,
+           out=None, out_f32=False, grouped_block64=False, **_):
+    xin = x[..., :cin].float().permute(0, 3, 1, 2)
+    if grouped_block64:
+        wt = wgt.float().reshape(cout, kh, kw, 64)
+        ys = []
+        for b in range(cout // 64):
+            ys.append(F.conv2d(xin[:, 64 * b:64 * b + 64], wt[64 * b:64 * b + 64].permute(0, 3, 1, 2), None, stride,
+                               pad, dil))
+        y = torch.cat(ys, 1)
+    else:
+        wt = wgt.float().reshape(cout, kh, kw, cin).permute(0, 3, 1, 2)
+        y = F.conv2d(xin, wt, None, stride, pad, dil)
+    _store(out, _epilogue(y.permute(0, 2, 3, 1), bias, act, residual, res_after_act))
+
+
+def gemm(a, wgt, bias, act=0, residual=None, res_after_act=False, out=None, out_f32=False, **_):
+    y = a.float() @ wgt.float().t()
+    _store(out, _epilogue(y, bias, act, residual, res_after_act))
+
+
+def dwconv(x, wgt, bias, k, stride, pad, dil, act, out, **_):
+    c = x.shape[-1]
+    wt = wgt.float()[:, :c].t().reshape(c, 1, k, k)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, stride, pad, dil, groups=c).permute(0, 2, 3, 1)
+    _store(out, _epilogue(y, bias, act, None, False))
+
+
+def maxpool2d(x, k, stride, pad, out, ceil_mode=False, **_):
+    y = F.max_pool2d(x.float().permute(0, 3, 1, 2), k, stride, pad, ceil_mode=ceil_mode).permute(0, 2, 3, 1)
+    _store(out, y)
+
+
+def avgpool2d(x, k, stride, out, **_):
+    _store(out, F.avg_pool2d(x.float().permute(0, 3, 1, 2), k, stride).permute(0, 2, 3, 1))
+
+
+def adaptive_avgpool(x, oh, ow, out, **_):
+    n, h, w, c = x.shape
+    y = x.float().reshape(n, oh, h // oh, ow, w // ow, c).mean((2, 4))
+    _store(out, y)
+
+
+def eltwise(x, scale=None, shift=None, other=None, gate=None, rows_per_image=1, act=0, out=None, **_):
+    y = x.float()
+    c = y.shape[-1]
+    if scale is not None:
+        y = y * scale.float()[:c] + shift.float()[:c]
+    if other is not None:
+        y = y + other.float()[..., :c]
+    y = _act(y, act)
+    if gate is not None:
+        y = y * gate.float()[..., :c].repeat_interleave(rows_per_image, 0)
+    _store(out, y)
+
+
+def layernorm(x, gamma, beta, eps, out, **_):
+    _store(out, F.layer_norm(x.float(), (x.shape[-1],), gamma.float(), beta.float(), eps))
+
+
+def copy2d(dst, src, **_):
+    dst[:, : src.shape[1]].copy_(src)
+
+
+IMPLS = {f.__name__: f for f in (nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
+                                 maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d)}
+
+
+def run(net, x, method="__call__", fp32_activations=False, **kw):
+    """lower `net` for the batch `x` on a CPU-device plan and replay the recorded steps with the torch stand-ins.
+    `fp32_activations`: allocate every activation buffer in fp32 (filters stay bf16 as packed), which removes the
+    bf16 rounding noise from the comparison and leaves a sharp check of the lowering itself."""
+    import eqxvision_b200 as eb
+    from eqxvision_b200 import _engine as E
+    from eqxvision_b200 import _trace as T
+
+    class _F32Plan(E.Plan):
+        def alloc(self, rows, c, geom=(), dtype=torch.bfloat16):
+            return super().alloc(rows, c, geom, torch.float32)
+
+    saved = E.BF16
+    if fp32_activations:
+        E.BF16 = torch.float32
+    try:
+        return _run(_F32Plan if fp32_activations else E.Plan, net, x, method, kw)
+    finally:
+        E.BF16 = saved
+
+
+def _run(plan_cls, net, x, method, kw):
+    import eqxvision_b200 as eb
+    from eqxvision_b200 import _engine as E
+    from eqxvision_b200 import _trace as T
+
+    plan = plan_cls(torch.device("cpu"), x.shape[0], tuple(x.shape[1:]))
+    fn = getattr(type(net), method)
+    fn = getattr(fn, "__wrapped__", fn)
+    kw.setdefault("key", eb.random.PRNGKey(0))
+    out = fn(net, T.Sym("chw", tuple(x.shape[1:]), T.Input()), **kw)
+    syms = []
+    plan.out_struct = E._flatten_out(out, syms)
+    for s in syms:
+        plan.add_output(s)
+    plan.x_in.copy_(x)
+    for step, kwargs in plan.steps:
+        impl = IMPLS.get(step.__name__)
+        if impl is None:
+            raise NotImplementedError(f"plan interpreter: no stand-in for ops.{step.__name__}")
+        impl(**kwargs)
+    leaves = [o.clone().reshape(shp) for (o, shp) in plan.outputs]
+    return E._unflatten_out(plan.out_struct, leaves), plan

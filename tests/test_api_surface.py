@@ -240,7 +240,8 @@ def lower(net, shape=(3, 224, 224), batch=2, **kw):
 def test_zoo_constructors_exported_with_reference_signatures():
     for name in ["alexnet", "AlexNet", "mobilenet_v2", "MobileNetV2", "squeezenet1_0", "squeezenet1_1", "SqueezeNet",
                  "googlenet", "GoogLeNet", "RegNet", "regnet_y_400mf", "regnet_y_128gf", "regnet_x_400mf",
-                 "regnet_x_32gf", "ConvNeXt", "convnext_tiny", "convnext_small", "convnext_base", "convnext_large"]:
+                 "regnet_x_32gf", "ShuffleNetV2", "shufflenet_v2_x0_5", "shufflenet_v2_x1_0", "shufflenet_v2_x1_5",
+                 "shufflenet_v2_x2_0", "ConvNeXt", "convnext_tiny", "convnext_small", "convnext_base", "convnext_large"]:
         assert hasattr(models, name), name
     p = inspect.signature(models.AlexNet.__init__).parameters
     assert list(p)[1:] == ["num_classes", "dropout", "key"] and p["dropout"].default == 0.5

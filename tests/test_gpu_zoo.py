@@ -109,7 +109,11 @@ ZOO = [("alexnet", "alexnet", 224, 3, 1e-2, 3e-2),
        ("squeezenet1_0", "squeezenet", 224, 2, 1.5e-2, 4e-2),
        ("squeezenet1_1", "squeezenet", 224, 2, 1.5e-2, 4e-2),
        ("googlenet", "googlenet", 224, 2, 1.5e-2, 4e-2),
-       ("convnext_tiny", "convnext", 224, 2, 1.5e-2, 4e-2)]
+       ("convnext_tiny", "convnext", 224, 2, 1.5e-2, 4e-2),
+       # untrained ShuffleNets amplify ANY rounding (fp32 oracle vs its own bf16 emulation: 6e-2 at 224): loose bounds
+       # here, the lowering itself is pinned to 5e-4 on the CPU (tests/test_plan_lowering.py)
+       ("shufflenet_v2_x0_5", "shufflenet_v2", 224, 2, 8e-2, 2e-1),
+       ("shufflenet_v2_x1_0", "shufflenet_v2", 224, 2, 8e-2, 2e-1)]
 
 
 @pytest.mark.parametrize("arch,fn,hw,batch,tol_emu,tol_f32", ZOO, ids=[z[0] for z in ZOO])

@@ -245,6 +245,8 @@ PINNED = [
     ("squeezenet1_0", "squeezenet", 96, {}),
     ("squeezenet1_1", "squeezenet", 96, {}),
     ("googlenet", "googlenet", 96, {"aux_logits": True, "transform_input": False, "init_weights": True}),
+    ("shufflenet_v2_x0_5", "shufflenet_v2", 64, {}),
+    ("shufflenet_v2_x1_0", "shufflenet_v2", 64, {}),
 ]
 
 

@@ -1,0 +1,74 @@
+"""Host-side lowering, checked without a GPU: the launch plan each model lowers to is replayed by the torch stand-ins
+of tests/plan_interpreter.py (one per C entry, following include/eqxv_b200.h) and compared with the bf16-emulating
+oracle. This pins weight packing, BatchNorm folding, epilogue order, concat slots, the ShuffleNetV2 channel views and
+the flatten permutations; the kernels themselves are pinned by the `-m gpu` tests."""
+import pytest
+import torch
+
+import eqxvision_b200 as eb
+from oracle import checkpoints as ck
+from oracle import models as om
+from oracle import ops as O
+
+import plan_interpreter as PI
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+CASES = [  # (ctor, oracle fn, input hw, torchvision kwargs)
+    ("alexnet", "alexnet", 224, {}),
+    ("resnet18", "resnet", 64, {}),
+    ("mobilenet_v2", "mobilenet_v2", 64, {}),
+    ("regnet_y_400mf", "regnet", 64, {}),
+    ("squeezenet1_1", "squeezenet", 64, {}),
+    ("googlenet", "googlenet", 64, {"aux_logits": True, "transform_input": False, "init_weights": True}),
+    ("convnext_tiny", "convnext", 64, {}),
+    ("shufflenet_v2_x0_5", "shufflenet_v2", 64, {}),
+    ("shufflenet_v2_x1_0", "shufflenet_v2", 64, {}),       # 58-channel branches: aligned concat slots
+    ("densenet121", "densenet", 64, {}),
+    ("efficientnet_b0", "efficientnet", 64, {}),
+    ("mobilenet_v3_small", "mobilenet_v3", 64, {}),
+    ("resnext50_32x4d", "resnet", 64, {}),                 # block-diagonal 64-channel grouped layout
+    ("regnet_x_400mf", "regnet", 64, {}),                  # dense expansion of the 16-wide groups
+]
+
+
+@pytest.mark.parametrize("arch,fn,hw,kw", CASES, ids=[c[0] for c in CASES])
+def test_lowered_plan_matches_emulating_oracle(tmp_path, arch, fn, hw, kw):
+    sd = ck.torchvision_state_dict(arch, seed=1, calib_hw=min(hw, 96), **kw)
+    path = str(tmp_path / "w.pth")
+    torch.save(sd, path)
+    net = eb.tree_inference(getattr(eb.models, arch)(torch_weights=path), True)
+    x = ck.synthetic_images(2, h=hw, w=hw, seed=2)
+    # fp32 activations on both sides, bf16 filters on both sides: what is left is fp32 summation order
+    got, plan = PI.run(net, x, fp32_activations=True)
+    with O.emulate_bf16(activations=False):
+        emu = getattr(om, fn)(sd, x, arch)
+    assert got.shape == emu.shape
+    assert rel(got, emu) < 5e-4, rel(got, emu)   # a packing or layout mistake gives O(1)
+    if arch in ("alexnet", "resnet18", "mobilenet_v2"):
+        # and the bf16 replay against the fully emulating oracle (rounding positions), at bf16 noise level
+        got16, _ = PI.run(net, x)
+        with O.emulate_bf16():
+            emu16 = getattr(om, fn)(sd, x, arch)
+        assert rel(got16, emu16) < 1e-2, rel(got16, emu16)
+
+
+def test_channel_views_compose_and_fold_into_dense_convs():
+    from eqxvision_b200 import _trace as T
+
+    x = T.Sym("chw", (8, 4, 4), T.Input())
+    a, b = T.split_channels(x, 2)
+    assert a.expr.idx == (0, 1, 2, 3) and b.expr.idx == (4, 5, 6, 7)
+    sh = T.channel_shuffle(x, 2)
+    assert sh.expr.idx == (0, 4, 1, 5, 2, 6, 3, 7)                     # shufflenetv2.py:14-20
+    assert T.split_channels(sh, 2)[1].expr.idx == (2, 6, 3, 7) and T.split_channels(sh, 2)[1].expr.x is x
+    assert T.channel_view(sh, [0, 2, 4, 6, 1, 3, 5, 7]) is x            # un-shuffling gives the identity back
+    w = torch.arange(2 * 4, dtype=torch.float32).reshape(2, 4, 1, 1)
+    y = T.conv2d(T.split_channels(sh, 2)[1], w, None, 1, 0, 1, 1)
+    assert y.expr.x is x and y.expr.weight.shape == (2, 8, 1, 1)
+    assert torch.equal(y.expr.weight[:, [2, 6, 3, 7], 0, 0], w[:, :, 0, 0]) and y.expr.weight.abs().sum() == w.abs().sum()
+    c = T.concat_channels([T.Sym("chw", (58, 4, 4), T.Input()), T.Sym("chw", (58, 4, 4), T.Input())])
+    assert c.shape == (116, 4, 4) and c.expr.x.shape == (122, 4, 4) and c.expr.idx[58] == 64
