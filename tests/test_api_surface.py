@@ -257,6 +257,32 @@ def test_zoo_constructors_exported_with_reference_signatures():
                            "activation", "key"]
 
 
+def test_every_name_the_reference_exports_from_models_exists():
+    """eqxvision/models/__init__.py of the reference, name by name (the Python surface is the boundary)"""
+    names = """AlexNet alexnet ConvNeXt convnext_base convnext_large convnext_small convnext_tiny DenseNet densenet121
+    densenet161 densenet169 densenet201 EfficientNet efficientnet_b0 efficientnet_b1 efficientnet_b2 efficientnet_b3
+    efficientnet_b4 efficientnet_b5 efficientnet_b6 efficientnet_b7 efficientnet_v2_l efficientnet_v2_m
+    efficientnet_v2_s GoogLeNet googlenet mobilenet_v2 MobileNetV2 mobilenet_v3_large mobilenet_v3_small MobileNetV3
+    RegNet regnet_x_1_6gf regnet_x_3_2gf regnet_x_8gf regnet_x_16gf regnet_x_32gf regnet_x_400mf regnet_x_800mf
+    regnet_y_1_6gf regnet_y_3_2gf regnet_y_8gf regnet_y_16gf regnet_y_32gf regnet_y_128gf regnet_y_400mf
+    regnet_y_800mf ResNet resnet18 resnet34 resnet50 resnet101 resnet152 resnext50_32x4d resnext101_32x8d
+    wide_resnet50_2 wide_resnet101_2 shufflenet_v2_x0_5 shufflenet_v2_x1_0 shufflenet_v2_x1_5 shufflenet_v2_x2_0
+    ShuffleNetV2 SqueezeNet squeezenet1_0 squeezenet1_1 swin_b swin_s swin_t swin_v2_b swin_v2_s swin_v2_t
+    SwinTransformer VGG vgg11 vgg11_bn vgg13 vgg13_bn vgg16 vgg16_bn vgg19 vgg19_bn _VitAttention _VitBlock
+    VisionTransformer vit_base vit_small vit_tiny DeepLabV3 deeplabv3 FCN fcn LRASPP lraspp_mobilenet_v3_large""".split()
+    missing = [n for n in names if not hasattr(models, n)]
+    assert not missing, missing
+    from eqxvision_b200.models import classification, segmentation
+
+    for sub in ("alexnet convnext densenet efficientnet googlenet mobilenetv2 mobilenetv3 regnet resnet shufflenetv2 "
+                "squeezenet swin vgg vit").split():
+        assert hasattr(classification, sub), sub
+    for sub in ("deeplabv3", "fcn", "lraspp"):
+        assert hasattr(segmentation, sub), sub
+    for n in ("experimental", "layers", "models", "utils"):
+        assert hasattr(eb, n), n
+
+
 def test_alexnet_lowers_to_twelve_launches_and_requires_key():
     net = eb.tree_inference(models.alexnet(), True)
     with pytest.raises(RuntimeError, match="PRNGKey"):          # alexnet.py:78-79
