@@ -8,7 +8,8 @@
 Workload at N=1 (BASELINE.json configs[1]): ResNet-50 inference, bf16, batch 256 per GPU, synthetic
 3x224x224 images, seeded synthetic checkpoint loaded through load_torch_weights. ViT-B/16 (64 images
 per GPU = 512 over 8, configs[2]) is measured in the same run and reported under "secondary";
-`--all-configs` adds EfficientNet-B4 (B=128, configs[3]) and DeepLabV3-ResNet50 (4x3x512x512, configs[4]).
+`--all-configs` adds EfficientNet-B4 (B=128, configs[3]), DeepLabV3-ResNet50 (4x3x512x512, configs[4]) and the
+README's single-image AlexNet forward (configs[0]).
 A "step" is one forward pass over one batch: one CUDA-graph replay (57 kernel launches for R50).
 
   value   : inputs resident in HBM, CUDA events on the launching stream, max over ranks
@@ -49,6 +50,10 @@ MODELS = {
                             config="BASELINE.json configs[3]"),
     "deeplabv3_resnet50": dict(batch=4, hw=512, flop=346.5e9, bytes=0.69e9, bound="tensor", cpu_batch=1,
                                config="BASELINE.json configs[4]"),
+    # configs[0], the README example: ONE image. At batch 1 the step is bound by reading the 61.1 M parameters
+    # once (122.2 MB of bf16 filters, 117 MB of them in the three classifier GEMMs) + 1.4 MB of activations
+    "alexnet": dict(batch=1, hw=224, flop=1.428e9, bytes=123.6e6, bound="hbm", cpu_batch=1,
+                    config="BASELINE.json configs[0] (README example, 1x3x224x224)"),
 }
 FLOP_PER_IMG = {k: v["flop"] for k, v in MODELS.items()}
 BYTES_PER_IMG = {k: v["bytes"] for k, v in MODELS.items()}
@@ -293,6 +298,8 @@ def oracle_forward(name, sd, batch):
         return lambda: om.deeplabv3_resnet50(sd, x)
     if name.startswith("efficientnet"):
         return lambda: om.efficientnet(sd, x, name)
+    if name == "alexnet":
+        return lambda: om.alexnet(sd, x)
     return lambda: om.resnet(sd, x, name)
 
 
@@ -358,7 +365,8 @@ def main():
     ap.add_argument("--model", default="resnet50", choices=sorted(MODELS))
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--all-configs", action="store_true",
-                    help="also measure EfficientNet-B4 (B=128) and DeepLabV3-R50 (4x3x512x512) as secondary lines")
+                    help="also measure EfficientNet-B4 (B=128), DeepLabV3-R50 (4x3x512x512) and AlexNet (1 image) "
+                         "as secondary lines")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -423,7 +431,10 @@ def main():
                  "flop_per_image": FLOP_PER_IMG[nm]}
         else:
             gbs = BYTES_PER_IMG[nm] * nb / step_ms / 1e6
-            r = {"bound": "hbm", "kernel": "whole step (pointwise 1x1 GEMMs + depthwise stencils + SE; HBM-bound model)",
+            what = ("whole step (batch 1: every filter is read once, the classifier GEMMs are weight-bandwidth bound)"
+                    if nm == "alexnet" else
+                    "whole step (pointwise 1x1 GEMMs + depthwise stencils + SE; HBM-bound model)")
+            r = {"bound": "hbm", "kernel": what,
                  "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                  "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
                  "peak_source": peaks["source"] + " (copy bandwidth)", "launches": mm["launches"],
@@ -441,7 +452,7 @@ def main():
     if not args.no_secondary:
         others.append("vit_base" if name == "resnet50" else "resnet50")
     if args.all_configs:
-        others += [k for k in ("efficientnet_b4", "deeplabv3_resnet50") if k != name and k not in others]
+        others += [k for k in ("efficientnet_b4", "deeplabv3_resnet50", "alexnet") if k != name and k not in others]
     for other in others:
         om_model, _ = build_model(other)
         ob = PER_GPU_BATCH[other]
