@@ -750,7 +750,11 @@ extern "C" int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n
       EQXV_LAUNCH_CHECK();
       return EQXV_OK;
     }
-    if (h * w <= 256 && c >= 256) {   // small map, many channels: one thread per (image, channel vector)
+    // small map and enough (image, channel vector) pairs to fill the machine with one thread each (ResNet-50 head,
+    // 256 x 7x7 x 2048: 24.8 us against 31-33 us for the block kernel). With fewer pairs or longer pixel loops the
+    // serial per-thread sum loses: EfficientNet-B4's 33 SE squeezes (128 images, 14x14 x 672..7x7 x 2688) measured
+    // 1.12 ms with this kernel against 0.74 ms with the block kernel (profiles/r01_bench_v24.json vs v26).
+    if (h * w <= 64 && (long long)n * (c / 8) >= 65536) {
       dim3 sgrid((unsigned)((c / 8 + 255) / 256), (unsigned)n);
       EQXV_CUDA(launch_kernel(global_avgpool_small_kernel, sgrid, dim3(256), (size_t)0, (cudaStream_t)stream,
                               (const __nv_bfloat16*)x, (__nv_bfloat16*)y, h * w, c, x_pitch, y_pitch));

@@ -39,6 +39,18 @@ def test_maxpool_ceil_mode_bit_exact(device, size, k, stride, pad):
     assert torch.equal(got.float(), ref)
 
 
+@pytest.mark.parametrize("n,hw,c", [(256, 7, 2048), (128, 7, 2688), (128, 14, 672), (3, 7, 2048), (2, 40, 64)])
+def test_global_avgpool_dispatch(device, n, hw, c):
+    """adaptive_avgpool(1,1) picks between three kernels by map size and (image x channel-vector) count: the
+    one-thread-per-vector kernel (ResNet-50 head at batch 256), the block kernel (SE squeezes), the cluster kernel"""
+    from eqxvision_b200 import ops
+
+    x = rb(device, n, hw, hw, c, seed=n + c)
+    got = ops.adaptive_avgpool(x, 1, 1)
+    ref = x.float().mean((1, 2), keepdim=True)
+    assert rel(got, ref) < 4e-3
+
+
 @pytest.mark.parametrize("n,hw,cin,cout,k,stride,pad", [(2, 224, 8, 64, 11, 4, 2),     # AlexNet conv1 on the NHWC8 image
                                                         (3, 27, 64, 192, 5, 1, 2),     # AlexNet conv2: 5x5, generic path
                                                         (2, 13, 192, 384, 3, 1, 1),    # AlexNet conv3
