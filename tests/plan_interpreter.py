@@ -137,8 +137,87 @@ def copy2d(dst, src, **_):
     dst[:, : src.shape[1]].copy_(src)
 
 
+def patchify(x_nchw, p, out, **_):
+    # rows = patches in raster order, columns in (c, py, px) order = the OIHW filter flattened (patch_embed.py:79)
+    n, c, h, w = x_nchw.shape
+    rows = x_nchw.reshape(n, c, h // p, p, w // p, p).permute(0, 2, 4, 1, 3, 5).reshape(n * (h // p) * (w // p), c * p * p)
+    out.copy_(rows.to(out.dtype))
+
+
+def vit_assemble_tokens(patches, cls, pos, n, np_, d, out, **_):
+    tok = torch.cat([cls.float().reshape(1, 1, d).expand(n, 1, d), patches.float().reshape(n, np_, d)], 1)
+    _store(out, (tok + pos.float().reshape(1, np_ + 1, d)).reshape(n * (np_ + 1), d))
+
+
+def _split_qkv(qkv, groups, tokens, heads, head_dim):
+    """[groups*tokens, 3*heads*head_dim], columns ordered (3, heads, head_dim) -> q, k, v [groups, heads, tokens, d]"""
+    t = qkv.float().reshape(groups, tokens, 3, heads, head_dim).permute(2, 0, 3, 1, 4)
+    return t[0], t[1], t[2]
+
+
+def attention(qkv, images, tokens, heads, head_dim, scale, out, **_):
+    q, k, v = _split_qkv(qkv, images, tokens, heads, head_dim)
+    p = torch.softmax((q @ k.transpose(-1, -2)) * scale, -1)          # scale after the product (vit.py:69)
+    _store(out, (p @ v).permute(0, 2, 1, 3).reshape(images * tokens, heads * head_dim))
+
+
+def attention_probs(qkv, images, tokens, heads, head_dim, scale, out, **_):
+    q, k, _v = _split_qkv(qkv, images, tokens, heads, head_dim)
+    out.copy_(torch.softmax((q @ k.transpose(-1, -2)) * scale, -1).reshape(out.shape))
+
+
+def gather_rows(x, n, tokens, row, out, **_):
+    _store(out, x.float().reshape(n, tokens, -1)[:, row])
+
+
+def resize_bilinear(x, oh, ow, out, **_):
+    y = F.interpolate(x.float().permute(0, 3, 1, 2), size=(oh, ow), mode="bilinear", align_corners=False)
+    _store(out, y.permute(0, 2, 3, 1))
+
+
+def resize_bilinear_to_nchw(x, c, oh, ow, out, **_):
+    out.copy_(F.interpolate(x[..., :c].float().permute(0, 3, 1, 2), size=(oh, ow), mode="bilinear",
+                            align_corners=False))
+
+
+def patch_merge(x, out, **_):
+    _store(out, torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1).float())
+
+
+def window_attention(qkv, bias, n, h, w, heads, head_dim, window, shift, scale, out, **_):
+    """include/eqxv_b200.h K16: roll by -shift, partition into window x window tiles, softmax(q*scale k^T + bias
+    + shift mask) v per (window, head), reverse the partition and the roll. Region labels are built on the rolled map
+    from three bands per axis ([0, size-window), [size-window, size-shift), [size-shift, size)); pairs of tokens
+    with different labels get -100."""
+    c = heads * head_dim
+    ws = window
+    sh = [0 if ws >= h else shift[0], 0 if ws >= w else shift[1]]
+    t = qkv.float().reshape(n, h, w, 3 * c)
+    if sum(sh) > 0:
+        t = torch.roll(t, shifts=(-sh[0], -sh[1]), dims=(1, 2))
+    nw = (h // ws) * (w // ws)
+    t = t.reshape(n, h // ws, ws, w // ws, ws, 3 * c).permute(0, 1, 3, 2, 4, 5).reshape(n * nw, ws * ws, 3 * c)
+    q, k, v = _split_qkv(t.reshape(n * nw * ws * ws, 3 * c), n * nw, ws * ws, heads, head_dim)
+    logits = (q * scale) @ k.transpose(-1, -2) + bias.float().reshape(1, heads, ws * ws, ws * ws)
+    if sum(sh) > 0:
+        lab = torch.zeros(h, w)
+        for i, (h0, h1) in enumerate(((0, h - ws), (h - ws, h - sh[0]), (h - sh[0], h))):
+            for j, (w0, w1) in enumerate(((0, w - ws), (w - ws, w - sh[1]), (w - sh[1], w))):
+                lab[h0:h1, w0:w1] = 3 * i + j
+        lab = lab.reshape(h // ws, ws, w // ws, ws).permute(0, 2, 1, 3).reshape(nw, ws * ws)
+        mask = torch.where(lab[:, None, :] == lab[:, :, None], 0.0, -100.0)
+        logits = (logits.reshape(n, nw, heads, ws * ws, ws * ws) + mask[None, :, None]).reshape(logits.shape)
+    o = (torch.softmax(logits, -1) @ v).permute(0, 2, 1, 3).reshape(n, h // ws, w // ws, ws, ws, c)
+    o = o.permute(0, 1, 3, 2, 4, 5).reshape(n, h, w, c)
+    if sum(sh) > 0:
+        o = torch.roll(o, shifts=(sh[0], sh[1]), dims=(1, 2))
+    _store(out, o.reshape(n * h * w, c))
+
+
 IMPLS = {f.__name__: f for f in (nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
-                                 maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d)}
+                                 maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d, patchify,
+                                 vit_assemble_tokens, attention, attention_probs, gather_rows, resize_bilinear,
+                                 resize_bilinear_to_nchw, patch_merge, window_attention)}
 
 
 def run(net, x, method="__call__", fp32_activations=False, **kw):
