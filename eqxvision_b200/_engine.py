@@ -308,7 +308,7 @@ class Plan:
         rows = torch.empty((self.n * np_, k), dtype=BF16, device=self.device)
         self.act_bytes += rows.numel() * 2
         self.step(ops.patchify, x_nchw=self.x_in, p=p, out=rows)
-        wp = self.const(w_f.reshape(d, k).to(BF16))
+        wp = self.const(w_f.reshape(d, k).to(torch.bfloat16))
         bias_d = self.const(b_f) if b_f is not None else None
         out = self.alloc(self.n * np_, d, (np_,))
         self.step(ops.gemm, a=rows, wgt=wp, bias=bias_d, act=act, out=out.rows())

@@ -72,3 +72,76 @@ def test_channel_views_compose_and_fold_into_dense_convs():
     assert torch.equal(y.expr.weight[:, [2, 6, 3, 7], 0, 0], w[:, :, 0, 0]) and y.expr.weight.abs().sum() == w.abs().sum()
     c = T.concat_channels([T.Sym("chw", (58, 4, 4), T.Input()), T.Sym("chw", (58, 4, 4), T.Input())])
     assert c.shape == (116, 4, 4) and c.expr.x.shape == (122, 4, 4) and c.expr.idx[58] == 64
+
+
+def _replay_f32(net, x, **kw):
+    return PI.run(net, x, fp32_activations=True, **kw)[0]
+
+
+def test_vit_lowering_matches_oracle(tmp_path):
+    """patchify GEMM, token assembly, LayerNorm, qkv / attention / proj (+residual), MLP (+residual), CLS gather, head"""
+    sd = ck.vit_state_dict(embed_dim=192, depth=3, heads=3, num_classes=10, seed=3)
+    path = str(tmp_path / "v.pth")
+    torch.save(sd, path)
+    net = eb.tree_inference(eb.models.vit_tiny(depth=3, num_classes=10, torch_weights=path), True)
+    x = ck.synthetic_images(2, seed=2)
+    with O.emulate_bf16(activations=False):
+        ref = om.vit(sd, x, heads=3)
+        ref_attn = om.vit(sd, x, heads=3, return_last_attention=True)
+    assert rel(_replay_f32(net, x), ref) < 5e-4
+    probs = _replay_f32(net, x, method="get_last_self_attention")          # vit.py:275-292
+    assert probs.shape == (2, 1, 3, 197, 197)
+    assert (probs.reshape(ref_attn.shape) - ref_attn).abs().max() < 1e-4
+
+
+def test_swin_lowering_matches_oracle(tmp_path):
+    """window attention (shifted and unshifted, mask, relative position bias), patch merging, LayerNorm2d / Linear2d views"""
+    tv = ck.swin_model("swin_t", seed=1)
+    sd = tv.state_dict()
+    path = str(tmp_path / "s.pth")
+    torch.save(sd, path)
+    net = eb.tree_inference(eb.models.swin_t(torch_weights=path), True)
+    x = ck.synthetic_images(1, seed=2)
+    with O.emulate_bf16(activations=False):
+        ref = om.swin(sd, x, "swin_t")
+    assert rel(_replay_f32(net, x), ref) < 5e-4
+
+
+def test_segmentation_lowering_matches_oracle(tmp_path):
+    """DeepLabV3: dilated backbone taps, ASPP branches into slices of one buffer, pooled branch broadcast, (aux, out)
+    order (_utils.py:58), bilinear resize straight into the fp32 NCHW outputs; LRASPP: gated head, (None, out)"""
+    tv = ck.torchvision_model("deeplabv3_resnet50", seed=1, calib_hw=64, aux_loss=True)
+    sd = tv.state_dict()
+    path = str(tmp_path / "d.pth")
+    torch.save(sd, path)
+    net = eb.models.deeplabv3(intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024,
+                              torch_weights=path)
+    net = eb.tree_inference(net, True)
+    x = ck.synthetic_images(1, h=64, w=64, seed=2)
+    aux, out = _replay_f32(net, x)
+    with O.emulate_bf16(activations=False):
+        aux_r, out_r = om.deeplabv3_resnet50(sd, x)
+    assert out.shape == out_r.shape == (1, 21, 64, 64)
+    assert rel(out, out_r) < 2e-3 and rel(aux, aux_r) < 2e-3   # dense per-pixel outputs of an untrained net on 8x8 maps
+
+    tv = ck.torchvision_model("lraspp_mobilenet_v3_large", seed=1, calib_hw=64)
+    sd = tv.state_dict()
+    torch.save(sd, path)
+    net = eb.tree_inference(eb.models.lraspp_mobilenet_v3_large(torch_weights=path), True)
+    none, out = _replay_f32(net, x)
+    with O.emulate_bf16(activations=False):
+        out_r = om.lraspp_mobilenet_v3_large(sd, x)
+    assert none is None and rel(out, out_r) < 2e-3
+
+
+def test_vgg_flatten_permutation_lowering(tmp_path):
+    """the (512,7,7) map is flattened in C,H,W order by jnp.ravel (vgg.py:116) while the buffer is H,W,C: the first
+    classifier GEMM runs on a column-permuted filter"""
+    sd = ck.torchvision_state_dict("vgg11_bn", seed=1)
+    path = str(tmp_path / "g.pth")
+    torch.save(sd, path)
+    net = eb.tree_inference(eb.models.vgg11_bn(torch_weights=path), True)
+    x = ck.synthetic_images(1, seed=2)
+    with O.emulate_bf16(activations=False):
+        ref = om.vgg(sd, x, "vgg11_bn")
+    assert rel(_replay_f32(net, x), ref) < 5e-4
