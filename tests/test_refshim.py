@@ -1,0 +1,72 @@
+"""The reference's OWN code against the oracle: /root/reference/eqxvision is imported unmodified on top of the
+stand-ins of oracle/refshim (jax / equinox are not installable here), its constructors build the models, its
+`load_torch_weights` loads the seeded checkpoints and its `__call__` under `jax.vmap(net, axis_name="batch")` produces
+the outputs the hand restatement in oracle/models.py must reproduce. Skipped where /root/reference does not exist
+(the GPU box); tests/golden/golden_ref_v1.pt carries outputs generated the same way to every box."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import checkpoints as ck
+from oracle import models as om
+from oracle import refshim
+
+needs_reference = pytest.mark.skipif(not refshim.available(), reason="reference sources not present on this box")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_ref_v1.pt")
+
+
+def run_reference(build, x, path, method=None):
+    """build(eqxvision, path) -> model; returns the batched output(s) of the reference code as torch tensors"""
+    with refshim.install() as ev:
+        import equinox as eqx
+        import jax
+
+        net = eqx.tree_inference(build(ev, path), True)
+        fn = net if method is None else getattr(net, method)
+        keys = jax.random.split(jax.random.PRNGKey(0), x.shape[0])
+        out = jax.vmap(fn, axis_name="batch")(jax.numpy.asarray(x.numpy()), key=keys)
+
+    def conv(o):
+        if o is None:
+            return None
+        if isinstance(o, (tuple, list)):
+            return type(o)(conv(i) for i in o)
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(o, dtype=np.float32)))
+
+    return conv(out)
+
+
+CASES = [  # (reference constructor, oracle function, input hw, torchvision kwargs)
+    ("alexnet", "alexnet", 224, {}),
+    ("resnet18", "resnet", 64, {}),
+    ("resnet50", "resnet", 64, {}),
+    ("resnext50_32x4d", "resnet", 64, {}),
+    ("vgg11", "vgg", 224, {}),
+    ("vgg11_bn", "vgg", 224, {}),
+    ("densenet121", "densenet", 64, {}),
+    ("mobilenet_v2", "mobilenet_v2", 64, {}),
+    ("mobilenet_v3_small", "mobilenet_v3", 64, {}),
+    ("mobilenet_v3_large", "mobilenet_v3", 64, {}),
+    ("efficientnet_b0", "efficientnet", 64, {}),
+    ("efficientnet_v2_s", "efficientnet", 64, {}),
+    ("regnet_y_400mf", "regnet", 64, {}),
+    ("regnet_x_400mf", "regnet", 64, {}),
+    ("squeezenet1_0", "squeezenet", 96, {}),
+    ("googlenet", "googlenet", 96, {"aux_logits": True, "transform_input": False, "init_weights": True}),
+    ("shufflenet_v2_x1_0", "shufflenet_v2", 64, {}),
+]
+
+
+@needs_reference
+@pytest.mark.parametrize("arch,fn,hw,kw", CASES, ids=[c[0] for c in CASES])
+def test_oracle_reproduces_the_reference_code(tmp_path, arch, fn, hw, kw):
+    sd = ck.torchvision_state_dict(arch, seed=1, calib_hw=min(hw, 96), **kw)
+    path = str(tmp_path / "w.pth")
+    torch.save(sd, path)
+    x = ck.synthetic_images(2, h=hw, w=hw, seed=2)
+    got = run_reference(lambda ev, p: getattr(ev.models, arch)(torch_weights=p), x, path)
+    ref = getattr(om, fn)(sd, x, arch)
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
