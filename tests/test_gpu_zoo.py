@@ -166,3 +166,32 @@ def test_alexnet_readme_example_single_image(device, save_checkpoint):
     feats = eb.vmap(net.features, axis_name="batch")(x, key=keys(1))
     assert feats.shape == (1, 256, 6, 6)
     assert rel(feats, om.alexnet(sd, x, features_only=True)) < 3e-2
+
+
+def test_reference_golden_vectors(device, save_checkpoint):
+    """tests/golden/golden_ref_v1.pt holds outputs of the REFERENCE'S OWN CODE (eqxvision's model files executed
+    through oracle/refshim in the build container, tests/golden/make_golden_ref.py). The B200 path is compared with
+    them directly - no oracle in between - at the stated bf16 tolerance (rel-L2 over the logits)."""
+    import os
+
+    import eqxvision_b200 as eb
+    from tools import synthetic as syn
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_ref_v1.pt"))
+    seen = 0
+    for key, e in g.items():
+        if not e["gpu"]:
+            continue
+        if e["arch"] == "vit_tiny":
+            sd = syn.vit_state_dict(seed=e["seed"], **e["cfg"])
+            net = eb.models.vit_tiny(torch_weights=save_checkpoint(sd, key + ".pth"), **e["ctor_kw"])
+        else:
+            sd = syn.torchvision_state_dict(e["arch"], seed=e["seed"], **e["tv_kwargs"])
+            net = getattr(eb.models, e["arch"])(torch_weights=save_checkpoint(sd, key + ".pth"))
+        net = eb.tree_inference(net, True)
+        x = syn.synthetic_images(e["n"], h=e["hw"], w=e["hw"], seed=e["img_seed"])
+        got = eb.vmap(net, axis_name="batch")(x, key=keys(e["n"]))
+        assert got.shape == e["expected"].shape, key
+        assert rel(got, e["expected"]) < e["tol"], (key, rel(got, e["expected"]))
+        seen += 1
+    assert seen >= 9

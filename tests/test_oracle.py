@@ -320,3 +320,33 @@ def test_ceil_mode_pool_rule():
         assert T._pool_out(size, k, s, p, True) == ref == ops.pool_out_size(size, k, s, p, True)
     with pytest.raises(NotImplementedError):
         T._pool_out(4, 1, 2, 0, True)   # last window would lie entirely in the padding: equinox and torch disagree
+
+
+def _oracle_for(arch):
+    for prefix, fn in (("resnet", "resnet"), ("resnext", "resnet"), ("alexnet", "alexnet"), ("mobilenet_v2", "mobilenet_v2"),
+                       ("mobilenet_v3", "mobilenet_v3"), ("efficientnet", "efficientnet"), ("densenet", "densenet"),
+                       ("regnet", "regnet"), ("squeezenet", "squeezenet"), ("googlenet", "googlenet"),
+                       ("shufflenet", "shufflenet_v2"), ("convnext", "convnext")):
+        if arch.startswith(prefix):
+            return getattr(om, fn)
+    raise KeyError(arch)
+
+
+def test_oracle_matches_golden_vectors_of_the_reference_code():
+    """tests/golden/golden_ref_v1.pt: outputs of the reference's own model files (run through oracle/refshim by
+    tests/golden/make_golden_ref.py). This test needs neither /root/reference nor the shim: it regenerates the seeded
+    checkpoints / images and holds the oracle to the reference's own tolerance (atol 1e-4)."""
+    import os
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_ref_v1.pt"))
+    assert len(g) >= 13
+    for key, e in g.items():
+        if e["arch"] == "vit_tiny":
+            sd = ck.vit_state_dict(seed=e["seed"], **e["cfg"])
+            got = om.vit(sd, ck.synthetic_images(e["n"], seed=e["img_seed"]), heads=e["cfg"]["heads"])
+        else:
+            sd = ck.torchvision_state_dict(e["arch"], seed=e["seed"], **e["tv_kwargs"])
+            x = ck.synthetic_images(e["n"], h=e["hw"], w=e["hw"], seed=e["img_seed"])
+            got = _oracle_for(e["arch"])(sd, x, e["arch"])
+        assert got.shape == e["expected"].shape, key
+        assert torch.allclose(got, e["expected"], atol=1e-4, rtol=1e-4), (key, (got - e["expected"]).abs().max())

@@ -70,3 +70,67 @@ def test_oracle_reproduces_the_reference_code(tmp_path, arch, fn, hw, kw):
     ref = getattr(om, fn)(sd, x, arch)
     assert got.shape == ref.shape
     assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
+
+
+@needs_reference
+def test_oracle_reproduces_the_reference_vit(tmp_path):
+    """ViT (vit.py): shape-only tests in the reference itself; pinned here by executing vit.py. Also the default
+    `num_classes=0` (CLS feature out) and `get_last_self_attention` (vit.py:275-292)."""
+    cfg = dict(embed_dim=192, depth=3, heads=3, num_classes=10)
+    sd = ck.vit_state_dict(seed=3, **cfg)
+    path = str(tmp_path / "v.pth")
+    torch.save(sd, path)
+    x = ck.synthetic_images(2, seed=2)
+    build = lambda ev, p: ev.models.vit_tiny(depth=3, num_classes=10, torch_weights=p)  # noqa: E731
+    got = run_reference(build, x, path)
+    ref = om.vit(sd, x, heads=3)
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
+    attn = run_reference(build, x, path, method="get_last_self_attention")
+    ref_attn = om.vit(sd, x, heads=3, return_last_attention=True)
+    assert attn.numel() == ref_attn.numel()
+    assert (attn.reshape(ref_attn.shape) - ref_attn).abs().max() < 1e-5
+
+
+@needs_reference
+def test_oracle_reproduces_the_reference_convnext(tmp_path):
+    sd = ck.torchvision_state_dict("convnext_tiny", seed=1)
+    path = str(tmp_path / "c.pth")
+    torch.save(sd, path)
+    x = ck.synthetic_images(1, h=64, w=64, seed=2)
+    got = run_reference(lambda ev, p: _convnext_from_path(ev, p), x, path)
+    ref = om.convnext(sd, x, "convnext_tiny")
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
+
+
+def _convnext_from_path(ev, path):
+    # convnext.py:218-221 ignores `torch_weights` and always fetches CLASSIFICATION_URLS[arch]: build, then load
+    net = ev.models.convnext_tiny()
+    return ev.utils.load_torch_weights(net, torch_weights=path)
+
+
+@needs_reference
+def test_oracle_reproduces_the_reference_swin(tmp_path):
+    sd = ck.swin_model("swin_t", seed=1).state_dict()
+    path = str(tmp_path / "s.pth")
+    torch.save(sd, path)
+    x = ck.synthetic_images(1, seed=2)
+    got = run_reference(lambda ev, p: ev.models.swin_t(torch_weights=p), x, path)
+    ref = om.swin(sd, x, "swin_t")
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
+
+
+@needs_reference
+def test_oracle_reproduces_the_reference_segmentation(tmp_path):
+    x = ck.synthetic_images(1, h=64, w=64, seed=2)
+    sd = ck.torchvision_model("deeplabv3_resnet50", seed=1, calib_hw=64, aux_loss=True).state_dict()
+    path = str(tmp_path / "d.pth")
+    torch.save(sd, path)
+    aux, out = run_reference(lambda ev, p: ev.models.deeplabv3(
+        intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024, torch_weights=p), x, path)
+    aux_r, out_r = om.deeplabv3_resnet50(sd, x)                       # (aux, out) order: _utils.py:58
+    assert torch.allclose(out, out_r, atol=1e-4, rtol=1e-4) and torch.allclose(aux, aux_r, atol=1e-4, rtol=1e-4)
+    sd = ck.torchvision_model("lraspp_mobilenet_v3_large", seed=1, calib_hw=64).state_dict()
+    torch.save(sd, path)
+    none, out = run_reference(lambda ev, p: ev.models.lraspp_mobilenet_v3_large(torch_weights=p), x, path)
+    assert none is None
+    assert torch.allclose(out, om.lraspp_mobilenet_v3_large(sd, x), atol=1e-4, rtol=1e-4)
