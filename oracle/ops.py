@@ -6,9 +6,10 @@ cpu_baseline / --impl reference legs may import this package.
 Parity status: the reference cannot be imported here (jax / equinox are not installed and cannot
 be), so these functions are pinned (a) against torchvision on identical state_dicts at the
 reference's own tolerance atol=1e-4 (tests/test_oracle.py) for the families whose reference tests
-assert exactly that, and (b) by running the reference's OWN model files on top of these ops through
-the import shim in oracle/refshim (tests/test_refshim.py).  ViT has shape-only tests in the
-reference => "parity unpinned" beyond (b).
+assert exactly that, and (b) by running the reference's OWN, unmodified model files on jax / equinox stand-ins
+(oracle/refshim: separate implementations of the third-party ops, numpy + torch CPU) and holding oracle/models.py
+to 1e-4 against their output (tests/test_refshim.py, 21 model configurations; golden vectors produced that way are
+committed under tests/golden/golden_ref_v1.pt).  ViT has shape-only tests in the reference, so (b) is its pin.
 
 Everything is plain torch on CPU in float32 (float64 where noted), written op by op.
 """

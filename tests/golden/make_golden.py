@@ -3,7 +3,7 @@
 Run in the build container:  python tests/golden/make_golden.py
 Source of the expected values: the CPU oracle (oracle/models.py), which is itself pinned against
 torchvision (tests/test_oracle.py) and against the reference's own model files executed through
-oracle/refshim (tests/test_refshim.py). Only seeds and outputs are stored; weights and images are
+oracle/refshim (tests/test_refshim.py; golden_ref_v1.pt holds outputs generated that way). Only seeds and outputs are stored; weights and images are
 regenerated from the seeds by oracle/checkpoints.py (CPU generator => identical on every box).
 """
 import os
