@@ -134,3 +134,40 @@ def test_oracle_reproduces_the_reference_segmentation(tmp_path):
     none, out = run_reference(lambda ev, p: ev.models.lraspp_mobilenet_v3_large(torch_weights=p), x, path)
     assert none is None
     assert torch.allclose(out, om.lraspp_mobilenet_v3_large(sd, x), atol=1e-4, rtol=1e-4)
+
+
+@needs_reference
+@pytest.mark.parametrize("arch,kw", [("resnet50", {}), ("efficientnet_b0", {}), ("densenet121", {}),
+                                     ("mobilenet_v3_large", {}), ("regnet_y_400mf", {}), ("shufflenet_v2_x1_0", {}),
+                                     ("googlenet", {"aux_logits": True, "transform_input": False, "init_weights": False})])
+def test_positional_loader_places_every_tensor_where_the_reference_does(tmp_path, arch, kw):
+    """utils.py:171-218: array leaves are replaced in pytree order, BatchNorm statistics in StateIndex order. The
+    reference's loader (run through the shim) and eqxvision_b200.utils.load_torch_weights must put the same tensor on
+    the same leaf, leaf by leaf."""
+    import eqxvision_b200 as eb
+    from eqxvision_b200 import nn as bnn
+
+    sd = ck.torchvision_state_dict(arch, seed=1, **kw)
+    path = str(tmp_path / "w.pth")
+    torch.save(sd, path)
+    with refshim.install() as ev:
+        import equinox as eqx
+        import jax.tree_util as jtu
+
+        ref_net = getattr(ev.models, arch)(torch_weights=path)
+        ref_arrays = [np.asarray(leaf) for leaf in jtu.tree_leaves(ref_net) if isinstance(leaf, np.ndarray)]
+        ref_stats = [leaf._state for leaf in jtu.tree_leaves(ref_net)
+                     if isinstance(leaf, eqx.experimental.StateIndex)]
+    ours = getattr(eb.models, arch)(torch_weights=path)
+    our_arrays = [leaf for leaf in bnn.tree_leaves(ours) if isinstance(leaf, torch.Tensor)]
+    our_stats = [leaf.value for leaf in bnn.tree_leaves(ours) if isinstance(leaf, bnn.StateIndex)]
+    assert len(ref_arrays) == len(our_arrays) > 0
+    for i, (r, o) in enumerate(zip(ref_arrays, our_arrays)):
+        assert tuple(r.shape) == tuple(o.shape), (i, r.shape, o.shape)
+        assert np.array_equal(r, o.numpy()), i
+    assert len(ref_stats) == len(our_stats)
+    for r, o in zip(ref_stats, our_stats):
+        if isinstance(o, tuple):
+            assert np.array_equal(np.asarray(r[0]), o[0].numpy()) and np.array_equal(np.asarray(r[1]), o[1].numpy())
+        else:
+            assert bool(np.asarray(r)) is False and o is False
