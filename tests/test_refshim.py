@@ -171,3 +171,58 @@ def test_positional_loader_places_every_tensor_where_the_reference_does(tmp_path
             assert np.array_equal(np.asarray(r[0]), o[0].numpy()) and np.array_equal(np.asarray(r[1]), o[1].numpy())
         else:
             assert bool(np.asarray(r)) is False and o is False
+
+
+def _raises(fn):
+    try:
+        fn()
+    except Exception as exc:  # noqa: BLE001 - the point is to learn which exception type comes out
+        return type(exc)
+    return None
+
+
+@needs_reference
+def test_error_conventions_match_the_reference_code():
+    """SURVEY.md 8(b) error conventions, derived by provoking the reference's own code (through the shim) and this
+    repo's host code with the same misuse: both must raise, and raise the same exception type."""
+    import eqxvision_b200 as eb
+    from eqxvision_b200 import _trace as T
+
+    sym = T.Sym("chw", (3, 64, 64), T.Input())
+    ours = {
+        "resnet_without_key": lambda: type(eb.models.resnet18()).__call__.__wrapped__(
+            eb.tree_inference(eb.models.resnet18(), True), sym, key=None),
+        "alexnet_without_key": lambda: type(eb.models.alexnet()).__call__.__wrapped__(
+            eb.tree_inference(eb.models.alexnet(), True), T.Sym("chw", (3, 224, 224), T.Input()), key=None),
+        "bad_replace_stride_with_dilation": lambda: eb.models.resnet50(replace_stride_with_dilation=[True]),
+        "empty_efficientnet_setting": lambda: eb.models.EfficientNet([], 0.2),
+        "empty_mobilenet_v2_setting": lambda: eb.models.MobileNetV2(inverted_residual_setting=[]),
+        "empty_convnext_setting": lambda: eb.models.ConvNeXt([]),
+        "shufflenet_wrong_stage_count": lambda: eb.models.ShuffleNetV2([4, 8], [24, 48, 96, 192, 1024]),
+        "invalid_regnet_width": lambda: eb.models.regnet.BlockParams.from_init_params(4, 50, 1.0, 2.0, 8),
+        "load_without_path": lambda: eb.utils.load_torch_weights(eb.models.resnet18(), None),
+        "patch_embed_size_mismatch": lambda: type(eb.layers.PatchEmbed(224, 16, 3, 32)).__call__.__wrapped__(
+            eb.layers.PatchEmbed(224, 16, 3, 32), T.Sym("chw", (3, 200, 224), T.Input())),
+    }
+    with refshim.install() as ev:
+        import equinox as eqx
+        import jax
+
+        img = jax.numpy.zeros((3, 64, 64))
+        theirs = {
+            "resnet_without_key": lambda: eqx.tree_inference(ev.models.resnet18(), True)(img, key=None),
+            "alexnet_without_key": lambda: eqx.tree_inference(ev.models.alexnet(), True)(
+                jax.numpy.zeros((3, 224, 224)), key=None),
+            "bad_replace_stride_with_dilation": lambda: ev.models.resnet50(replace_stride_with_dilation=[True]),
+            "empty_efficientnet_setting": lambda: ev.models.EfficientNet([], 0.2),
+            "empty_mobilenet_v2_setting": lambda: ev.models.MobileNetV2(inverted_residual_setting=[]),
+            "empty_convnext_setting": lambda: ev.models.ConvNeXt([]),
+            "shufflenet_wrong_stage_count": lambda: ev.models.ShuffleNetV2([4, 8], [24, 48, 96, 192, 1024]),
+            "invalid_regnet_width": lambda: ev.models.regnet.BlockParams.from_init_params(4, 50, 1.0, 2.0, 8),
+            "load_without_path": lambda: ev.utils.load_torch_weights(ev.models.resnet18(), None),
+            "patch_embed_size_mismatch": lambda: ev.layers.PatchEmbed(224, 16, 3, 32)(jax.numpy.zeros((3, 200, 224))),
+        }
+        expected = {k: _raises(f) for k, f in theirs.items()}
+    for k, f in ours.items():
+        assert expected[k] is not None, f"the reference does not raise on {k}"
+        assert _raises(f) is expected[k], (k, _raises(f), expected[k])
