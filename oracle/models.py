@@ -710,6 +710,24 @@ def deeplabv3_resnet50(state_dict, x, rates=(12, 24, 36)):
     return aux, out
 
 
+def fcn_resnet50(state_dict, x):
+    """FCN (fcn.py:37-120) over the dilated ResNet-50 backbone, taps layer3 (aux) / layer4: FCNHead (fcn.py:19-34) =
+    conv3x3 (no bias) -> BN -> ReLU -> Dropout(0.1, no-op) -> conv1x1 (bias); both outputs resized bilinearly to the
+    input size; returns (aux, out) as _SimpleSegmentationModel.__call__ does (_utils.py:58)."""
+    s = Stream(state_dict)
+    h, w = x.shape[-2:]
+    stages = resnet_features(s, x, "resnet50", (False, True, True))
+    c3, c4 = stages[2], stages[3]
+    y = _cna(s, c4, 1, 1, act="relu")
+    wc, bc = s.take(), s.take()
+    out = O.resize_bilinear(O.conv_bn_act(y, wc, bc, None), h, w)
+    a = _cna(s, c3, 1, 1, act="relu")
+    wa, ba = s.take(), s.take()
+    aux = O.resize_bilinear(O.conv_bn_act(a, wa, ba, None), h, w)
+    assert s.done()
+    return aux, out
+
+
 # ------------------------------------------------------------------------------------------------
 # Swin Transformer v1 (swin.py)
 # ------------------------------------------------------------------------------------------------

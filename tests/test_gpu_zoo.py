@@ -195,3 +195,25 @@ def test_reference_golden_vectors(device, save_checkpoint):
         assert rel(got, e["expected"]) < e["tol"], (key, rel(got, e["expected"]))
         seen += 1
     assert seen >= 9
+
+
+def test_fcn_resnet50_parity(device, save_checkpoint):
+    """FCN (fcn.py): dilated ResNet-50 taps layer3 / layer4, two FCNHeads, `(aux, out)`; dense per-pixel outputs of an
+    untrained net, hence the DeepLabV3-style bounds (the lowering itself is pinned at 2e-3 on the CPU)"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    sd = ck.torchvision_model("fcn_resnet50", seed=1, calib_hw=64, aux_loss=True).state_dict()
+    net = eb.models.fcn(intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024,
+                        torch_weights=save_checkpoint(sd))
+    net = eb.tree_inference(net, True)
+    x = ck.synthetic_images(2, h=128, w=128, seed=2)
+    aux, out = eb.vmap(net, axis_name="batch")(x, key=keys(2))
+    assert out.shape == aux.shape == (2, 21, 128, 128)
+    aux_r, out_r = om.fcn_resnet50(sd, x)
+    with O.emulate_bf16():
+        aux_e, out_e = om.fcn_resnet50(sd, x)
+    assert rel(out, out_e) < 1e-1 and rel(aux, aux_e) < 8e-2, (rel(out, out_e), rel(aux, aux_e))
+    assert rel(out, out_r) < 2.5e-1 and rel(aux, aux_r) < 2e-1, (rel(out, out_r), rel(aux, aux_r))

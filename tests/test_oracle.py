@@ -350,3 +350,14 @@ def test_oracle_matches_golden_vectors_of_the_reference_code():
             got = _oracle_for(e["arch"])(sd, x, e["arch"])
         assert got.shape == e["expected"].shape, key
         assert torch.allclose(got, e["expected"], atol=1e-4, rtol=1e-4), (key, (got - e["expected"]).abs().max())
+
+
+def test_fcn_oracle_matches_torchvision():
+    """tests/test_models/test_fcn.py of the reference: atol 1e-4 against torchvision's fcn_resnet50 (out, aux)"""
+    tv = ck.torchvision_model("fcn_resnet50", seed=1, calib_hw=64, aux_loss=True)
+    x = ck.synthetic_images(1, h=64, w=64, seed=2)
+    with torch.no_grad():
+        ref = tv(x)
+    aux, out = om.fcn_resnet50(tv.state_dict(), x)
+    assert torch.allclose(out, ref["out"], atol=1e-4, rtol=1e-4), (out - ref["out"]).abs().max()
+    assert torch.allclose(aux, ref["aux"], atol=1e-4, rtol=1e-4), (aux - ref["aux"]).abs().max()

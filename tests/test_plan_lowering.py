@@ -145,3 +145,20 @@ def test_vgg_flatten_permutation_lowering(tmp_path):
     with O.emulate_bf16(activations=False):
         ref = om.vgg(sd, x, "vgg11_bn")
     assert rel(_replay_f32(net, x), ref) < 5e-4
+
+
+def test_fcn_lowering_matches_oracle(tmp_path):
+    """fcn (fcn.py:37-120): dilated ResNet-50 taps, two FCNHeads, (aux, out)"""
+    sd = ck.torchvision_model("fcn_resnet50", seed=1, calib_hw=64, aux_loss=True).state_dict()
+    path = str(tmp_path / "f.pth")
+    torch.save(sd, path)
+    net = eb.models.fcn(intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024, torch_weights=path)
+    net = eb.tree_inference(net, True)
+    x = ck.synthetic_images(1, h=64, w=64, seed=2)
+    aux, out = _replay_f32(net, x)
+    with O.emulate_bf16(activations=False):
+        aux_r, out_r = om.fcn_resnet50(sd, x)
+    assert out.shape == out_r.shape == (1, 21, 64, 64)
+    assert rel(out, out_r) < 2e-3 and rel(aux, aux_r) < 2e-3
+    with pytest.raises(ValueError):                      # fcn.py:92-101: aux head needs exactly two taps
+        eb.models.fcn(intermediate_layers=lambda m: [m.layer4], aux_in_channels=1024)

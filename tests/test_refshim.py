@@ -226,3 +226,15 @@ def test_error_conventions_match_the_reference_code():
     for k, f in ours.items():
         assert expected[k] is not None, f"the reference does not raise on {k}"
         assert _raises(f) is expected[k], (k, _raises(f), expected[k])
+
+
+@needs_reference
+def test_oracle_reproduces_the_reference_fcn(tmp_path):
+    x = ck.synthetic_images(1, h=64, w=64, seed=2)
+    sd = ck.torchvision_model("fcn_resnet50", seed=1, calib_hw=64, aux_loss=True).state_dict()
+    path = str(tmp_path / "f.pth")
+    torch.save(sd, path)
+    aux, out = run_reference(lambda ev, p: ev.models.fcn(
+        intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024, torch_weights=p), x, path)
+    aux_r, out_r = om.fcn_resnet50(sd, x)
+    assert torch.allclose(out, out_r, atol=1e-4, rtol=1e-4) and torch.allclose(aux, aux_r, atol=1e-4, rtol=1e-4)
