@@ -50,7 +50,9 @@ CASES = [  # (reference constructor, oracle function, input hw, torchvision kwar
     ("mobilenet_v3_small", "mobilenet_v3", 64, {}),
     ("mobilenet_v3_large", "mobilenet_v3", 64, {}),
     ("efficientnet_b0", "efficientnet", 64, {}),
+    ("efficientnet_b4", "efficientnet", 64, {}),            # BASELINE.json configs[3]
     ("efficientnet_v2_s", "efficientnet", 64, {}),
+    ("wide_resnet50_2", "resnet", 64, {}),
     ("regnet_y_400mf", "regnet", 64, {}),
     ("regnet_x_400mf", "regnet", 64, {}),
     ("squeezenet1_0", "squeezenet", 96, {}),
@@ -89,6 +91,19 @@ def test_oracle_reproduces_the_reference_vit(tmp_path):
     ref_attn = om.vit(sd, x, heads=3, return_last_attention=True)
     assert attn.numel() == ref_attn.numel()
     assert (attn.reshape(ref_attn.shape) - ref_attn).abs().max() < 1e-5
+
+
+@needs_reference
+def test_oracle_reproduces_the_reference_vit_base(tmp_path):
+    """BASELINE.json configs[2]: the full ViT-B/16 (12 blocks, 12 heads, 768 wide, 1000 classes), one image"""
+    sd = ck.vit_state_dict(embed_dim=768, depth=12, heads=12, num_classes=1000, seed=3)
+    path = str(tmp_path / "vb.pth")
+    torch.save(sd, path)
+    x = ck.synthetic_images(1, seed=2)
+    got = run_reference(lambda ev, p: ev.models.vit_base(num_classes=1000, torch_weights=p), x, path)
+    ref = om.vit(sd, x, heads=12)
+    assert got.shape == ref.shape == (1, 1000)
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
 
 
 @needs_reference
