@@ -366,6 +366,17 @@ def test_convnext_layer_scale_folds_into_the_second_gemm():
         models.ConvNeXt([(96, 192, 3)])
 
 
+def test_unsupported_shapes_fail_at_trace_time_not_at_launch():
+    with pytest.raises(NotImplementedError, match="even split"):        # aux heads pool 14x14 -> 4x4 (googlenet.py:265)
+        trace(eb.tree_inference(models.googlenet(aux_logits=True), True), (3, 224, 224))
+    with pytest.raises(NotImplementedError, match="even split"):        # AlexNet at 127 px: 3x3 -> 6x6
+        trace(eb.tree_inference(models.alexnet(), True), (3, 127, 127))
+    with pytest.raises(NotImplementedError):
+        trace(eb.tree_inference(models.swin_v2_t(), True), (3, 224, 224))
+    with pytest.raises(NotImplementedError):
+        nn.AvgPool2d(3, 2, use_ceil=True)
+
+
 def test_googlenet_loads_torchvision_checkpoint_with_aux_heads(tmp_path):
     """googlenet.py:320-335: the checkpoint carries aux1/aux2, the model is built with them, then aux_logits is cleared"""
     import torchvision
