@@ -50,6 +50,18 @@ def _store(out, y):
     out[..., : y.shape[-1]].copy_(y.to(out.dtype))
 
 
+def _check_operand(t, what):
+    """the alignment rules the C entries enforce on activation views (EQXV_CHECK_ARG in csrc/*.cu): 16-byte aligned
+    base address and row pitch, i.e. multiples of 8 bf16 elements - checked on element offsets so that the rule is the
+    same whether the replay keeps activations in bf16 or in fp32"""
+    if t is None:
+        return
+    assert t.stride(-1) == 1, f"{what}: innermost stride must be 1"
+    assert t.storage_offset() % 8 == 0, f"{what}: view starts at element {t.storage_offset()}, not 16-byte aligned"
+    if t.dim() >= 2:
+        assert t.stride(-2) % 8 == 0, f"{what}: pitch {t.stride(-2)} is not a multiple of 8 channels"
+
+
 def nchw_to_nhwc(x, c_pad, out, **_):
     out.zero_()
     out[..., : x.shape[1]].copy_(x.permute(0, 2, 3, 1).to(out.dtype))
@@ -75,6 +87,10 @@ def conv_stem(xpad, wgt, bias, n, h, w, cout, kh, kw, stride, pad, act, out, **_
 
 def conv2d(x, wgt, bias, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, residual=None, res_after_act=False,
            out=None, out_f32=False, grouped_block64=False, **_):
+    assert cin % 8 == 0, "conv: cin must be a multiple of 8"
+    for t, what in ((x, "conv x"), (out, "conv y"), (residual, "conv residual")):
+        _check_operand(t, what)
+    assert out.stride(2) >= cout and (residual is None or residual.stride(2) >= cout)
     xin = x[..., :cin].float().permute(0, 3, 1, 2)
     if grouped_block64:
         wt = wgt.float().reshape(cout, kh, kw, 64)
@@ -90,18 +106,27 @@ def conv2d(x, wgt, bias, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, resid
 
 
 def gemm(a, wgt, bias, act=0, residual=None, res_after_act=False, out=None, out_f32=False, **_):
+    assert a.shape[1] % 8 == 0 and wgt.shape[1] == a.shape[1], "gemm: k must be a multiple of 8 and match the filter"
+    for t, what in ((a, "gemm a"), (residual, "gemm residual")) + (() if out_f32 else ((out, "gemm out"),)):
+        _check_operand(t, what)
     y = a.float() @ wgt.float().t()
     _store(out, _epilogue(y, bias, act, residual, res_after_act))
 
 
 def dwconv(x, wgt, bias, k, stride, pad, dil, act, out, **_):
     c = x.shape[-1]
+    assert c % 8 == 0 and wgt.shape[1] >= c and bias.numel() >= c, "dwconv: channels / filter pitch"
+    _check_operand(x, "dwconv x")
+    _check_operand(out, "dwconv y")
     wt = wgt.float()[:, :c].t().reshape(c, 1, k, k)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, stride, pad, dil, groups=c).permute(0, 2, 3, 1)
     _store(out, _epilogue(y, bias, act, None, False))
 
 
 def maxpool2d(x, k, stride, pad, out, ceil_mode=False, **_):
+    assert x.shape[-1] % 8 == 0 and 2 * pad <= k, "maxpool: channels must be a multiple of 8, 2*pad <= k"
+    _check_operand(x, "maxpool x")
+    _check_operand(out, "maxpool y")
     y = F.max_pool2d(x.float().permute(0, 3, 1, 2), k, stride, pad, ceil_mode=ceil_mode).permute(0, 2, 3, 1)
     _store(out, y)
 
