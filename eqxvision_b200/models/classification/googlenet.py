@@ -175,7 +175,8 @@ class GoogLeNet(nn.Module):
 def googlenet(torch_weights: str = None, **kwargs: Any) -> GoogLeNet:
     """GoogLeNet ("Going Deeper with Convolutions", arXiv 1409.4842); minimum input 15x15. With `torch_weights` the
     model is built WITH the auxiliary heads so that a torchvision checkpoint loads positionally, then `aux_logits` is
-    switched off unless requested (googlenet.py:320-335)."""
+    switched off unless requested (googlenet.py:320-335). (In the reference `googlenet(torch_weights=..., aux_logits=True)`
+    raises a TypeError because `aux_logits` reaches the constructor twice, googlenet.py:323-325; here it is accepted.)"""
     if torch_weights:
         use_aux = kwargs.get("aux_logits", False)
         kwargs.pop("aux_logits", None)

@@ -463,12 +463,25 @@ def _inception(s: Stream, x):
     return torch.cat([b1, b2, b3, b4], 1)
 
 
-def googlenet(state_dict, x, arch="googlenet"):
-    """GoogLeNet.__call__ with aux_logits=False (googlenet.py:108-177). A checkpoint that carries the auxiliary heads
-    (torchvision saves them; the reference loads them positionally, googlenet.py:322-327) has them skipped here:
-    they sit between inception5b and fc in field order."""
+def _inception_aux(x, p):
+    """InceptionAux.__call__ (googlenet.py:263-279): adaptive pool to 4x4 (equinox's uneven rule on 14x14 maps),
+    BasicConv2d 1x1 -> ravel (C,H,W order) -> fc1 -> relu -> Dropout (no-op) -> fc2"""
+    wc, bn, w1, b1, w2, b2 = p
+    y = O.rnd(O.adaptive_avg_pool2d(x, 4, uneven=True))
+    y = O.conv_bn_act(y, wc, None, bn, act="relu", eps=1e-3).flatten(1)
+    y = O.linear_act(y, w1, b1, act="relu")
+    return O.linear_act(y, w2, b2, round_out=False)
+
+
+def googlenet(state_dict, x, arch="googlenet", aux_logits=False):
+    """GoogLeNet.__call__ (googlenet.py:108-177). A checkpoint that carries the auxiliary heads (torchvision saves
+    them; the reference loads them positionally, googlenet.py:322-327) has them skipped when `aux_logits` is False:
+    they sit between inception5b and fc in field order. With `aux_logits=True` returns (logits, aux2, aux1)
+    (googlenet.py:174-175) - CPU oracle only, the device library does not build the uneven 14x14 -> 4x4 pooling."""
     e = 1e-3
     s = Stream(state_dict)
+    if aux_logits:
+        return _googlenet_with_aux(s, x)
     x = _cna(s, x, 2, 3, act="relu", eps=e)
     x = O.max_pool2d(x, 3, 2, ceil_mode=True)
     x = _cna(s, x, act="relu", eps=e)
@@ -574,6 +587,29 @@ def shufflenet_v2(state_dict, x, arch="shufflenet_v2_x1_0"):
     out = O.linear_act(x, s.take(), s.take(), round_out=False)
     assert s.done()
     return out
+
+
+def _googlenet_with_aux(s: Stream, x):
+    e = 1e-3
+    x = _cna(s, x, 2, 3, act="relu", eps=e)
+    x = O.max_pool2d(x, 3, 2, ceil_mode=True)
+    x = _cna(s, x, act="relu", eps=e)
+    x = _cna(s, x, 1, 1, act="relu", eps=e)
+    x = O.max_pool2d(x, 3, 2, ceil_mode=True)
+    x = _inception(s, _inception(s, x))
+    x = O.max_pool2d(x, 3, 2, ceil_mode=True)
+    x4a = _inception(s, x)
+    x = _inception(s, _inception(s, _inception(s, x4a)))                        # 4b, 4c, 4d
+    x4d = x
+    x = _inception(s, x)
+    x = O.max_pool2d(x, 2, 2, ceil_mode=True)
+    x = _inception(s, _inception(s, x))
+    heads = [(s.take(), s.take_bn(), s.take(), s.take(), s.take(), s.take()) for _ in range(2)]
+    aux1, aux2 = _inception_aux(x4a, heads[0]), _inception_aux(x4d, heads[1])
+    x = O.rnd(O.adaptive_avg_pool2d(x, 1).flatten(1))
+    out = O.linear_act(x, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return out, aux2, aux1
 
 
 # ------------------------------------------------------------------------------------------------

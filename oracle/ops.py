@@ -74,12 +74,26 @@ def avg_pool2d(x, k, stride):
     return F.avg_pool2d(x, _pair(k), _pair(stride))
 
 
-def adaptive_avg_pool2d(x, target):
-    """equinox.nn.AdaptiveAvgPool2d for the even-split case (dim % target == 0): block mean"""
+def adaptive_avg_pool2d(x, target, uneven: bool = False):
+    """equinox.nn.AdaptiveAvgPool2d. Even split (dim % target == 0): block mean. `uneven=True` opts into equinox's
+    rule for the other case - the first `dim % target` blocks have dim // target + 1 elements, the rest dim // target -
+    which is NOT torch's overlapping-window rule; the device library builds neither, so callers
+    must ask for it explicitly (GoogLeNet's auxiliary heads, googlenet.py:265-268)."""
     oh, ow = _pair(target)
     n, c, h, w = x.shape
     if h % oh or w % ow:
-        raise NotImplementedError("uneven adaptive pooling differs between equinox and torch")
+        if not uneven:
+            raise NotImplementedError("uneven adaptive pooling differs between equinox and torch")
+        for axis, t in ((2, oh), (3, ow)):
+            size = x.shape[axis]
+            head, block = size % t, size // t
+            parts = []
+            if head:
+                parts.append(x.narrow(axis, 0, head * (block + 1)).unflatten(axis, (head, block + 1)).mean(axis + 1))
+            parts.append(x.narrow(axis, head * (block + 1), (t - head) * block).unflatten(axis, (t - head, block))
+                         .mean(axis + 1))
+            x = torch.cat(parts, axis)
+        return x
     return x.reshape(n, c, oh, h // oh, ow, w // ow).mean((3, 5))
 
 

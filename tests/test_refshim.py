@@ -253,3 +253,34 @@ def test_oracle_reproduces_the_reference_fcn(tmp_path):
         intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024, torch_weights=p), x, path)
     aux_r, out_r = om.fcn_resnet50(sd, x)
     assert torch.allclose(out, out_r, atol=1e-4, rtol=1e-4) and torch.allclose(aux, aux_r, atol=1e-4, rtol=1e-4)
+
+
+@needs_reference
+def test_oracle_reproduces_the_reference_googlenet_aux_heads(tmp_path):
+    """aux_logits=True: (logits, aux2, aux1) (googlenet.py:174-175); the heads pool 14x14 -> 4x4 with EQUINOX's uneven
+    adaptive rule (2 blocks of 4, then 2 of 3), which differs from torch's overlapping windows. CPU oracle only."""
+    import torchvision
+
+    torch.manual_seed(1)
+    tv = torchvision.models.googlenet(weights=None, aux_logits=True, transform_input=False, init_weights=True)
+    ck._perturb_and_calibrate(tv, 1, (4, 3, 96, 96))
+    sd = tv.state_dict()
+    path = str(tmp_path / "g.pth")
+    torch.save(sd, path)
+    x = ck.synthetic_images(1, seed=2)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # googlenet(torch_weights=..., aux_logits=True) is a TypeError in the reference (googlenet.py:323-325 passes
+        # aux_logits twice): build the class and load explicitly
+        got = run_reference(lambda ev, p: ev.utils.load_torch_weights(ev.models.GoogLeNet(aux_logits=True), p), x, path)
+    ref = om.googlenet(sd, x, aux_logits=True)
+    assert len(got) == len(ref) == 3
+    for g, r in zip(got, ref):
+        assert torch.allclose(g, r, atol=1e-4, rtol=1e-4), (g - r).abs().max()
+    with torch.no_grad():
+        tv.train(False)
+        tv_aux = tv.aux1(tv.inception4a(tv.maxpool3(tv.inception3b(tv.inception3a(tv.maxpool2(tv.conv3(tv.conv2(
+            tv.maxpool1(tv.conv1(x))))))))))
+    assert not torch.allclose(ref[2], tv_aux, atol=1e-3)       # torch's adaptive rule gives different numbers
