@@ -47,6 +47,19 @@ CONV_CASES = [
     (2, 48, 40, 72, 40, 5, 1, 2, 1, 0, False, False),      # 5x5, channels not a multiple of 64
     (3, 56, 56, 256, 256, 3, 1, 1, 1, 0, False, False),    # several K blocks through the A ring
     (2, 30, 23, 64, 96, 3, 1, 1, 1, 1, False, False),      # ragged edges inside the halo tiles
+    # BASELINE configs[4] shapes (DeepLabV3-R50 @512^2: 64x64 maps, deeplabv3.py:38-55,77-135): the dilated taps
+    # overlap the map only PARTIALLY, so the producer's and the issuer's tap-skip predicates must agree tile by tile
+    (1, 64, 64, 2048, 256, 3, 1, 12, 12, 1, False, False),  # ASPP d12
+    (1, 64, 64, 2048, 256, 3, 1, 24, 24, 1, False, False),  # ASPP d24
+    (1, 64, 64, 2048, 256, 3, 1, 36, 36, 1, False, False),  # ASPP d36
+    (2, 64, 64, 256, 256, 3, 1, 2, 2, 1, False, False),     # layer3 conv2, dilation 2 (resnet.py:286-333)
+    (1, 64, 64, 512, 512, 3, 1, 4, 4, 1, False, False),     # layer4 conv2, dilation 4
+    (1, 64, 64, 512, 512, 3, 1, 2, 2, 1, False, False),     # layer4 block 0 conv2: previous dilation
+    (1, 64, 64, 1024, 256, 1, 1, 0, 1, 1, False, False),    # layer3 conv1 on the dilated (stride-8) map
+    (1, 64, 64, 2048, 512, 3, 1, 1, 1, 1, False, False),    # FCNHead 3x3 on 2048 channels (fcn.py:19-34)
+    (1, 64, 64, 1280, 256, 1, 1, 0, 1, 1, False, False),    # ASPP projection over the 5-branch concat
+    (3, 33, 33, 320, 256, 3, 1, 12, 12, 0, False, False),   # odd map: ragged tiles AND partial tap overlap
+    (2, 40, 28, 128, 64, 3, 1, 24, 24, 0, False, False),    # d24 on a map where some taps of some tiles vanish
 ]
 
 

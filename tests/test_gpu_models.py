@@ -287,3 +287,116 @@ def test_golden_vectors(device, save_checkpoint):
         else:
             continue
         assert rel(got, rec["expected"]) < rec["tol"], (name, rel(got, rec["expected"]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json shapes: tile / wave selection (choose_tile, choose_block_n, pair vs single CTA) depends on
+# M = batch x pixels, so the batches the bench times take other kernels than the small batches above.
+# 256 (64, 128) DISTINCT images go through the device; 16 rows spread over the batch are compared with the
+# oracle run on exactly those 16 images.
+# ---------------------------------------------------------------------------------------------------------
+def _spread_rows(batch, k=16):
+    step = batch // k
+    return torch.tensor([i * step + (i * 7) % step for i in range(k)])
+
+
+@pytest.mark.parametrize("arch,batch,tol_emu,tol_f32", [("resnet50", 256, 2.0e-2, 6e-2)])
+def test_resnet50_full_batch_rows_vs_oracle(device, save_checkpoint, arch, batch, tol_emu, tol_f32):
+    """BASELINE configs[1]: ResNet-50, batch 256 (resnet.py:144-162,335-358)"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    sd = ck.torchvision_state_dict(arch, seed=1)
+    net = build(arch, sd, save_checkpoint)
+    x = ck.synthetic_images(batch, seed=21)
+    got = eb.vmap(net, axis_name="batch")(x, key=keys(batch))
+    assert got.shape == (batch, 1000) and torch.isfinite(got).all()
+    idx = _spread_rows(batch)
+    ref = om.resnet(sd, x[idx], arch)
+    with O.emulate_bf16():
+        emu = om.resnet(sd, x[idx], arch)
+    assert rel(got[idx], emu) < tol_emu, ("vs bf16-emulating oracle", rel(got[idx], emu))
+    assert rel(got[idx], ref) < tol_f32, ("vs fp32 oracle", rel(got[idx], ref))
+    # every row individually (a wrong tile would spoil single rows without moving the global norm much)
+    per_row = ((got[idx].cpu() - emu).norm(dim=1) / emu.norm(dim=1)).max().item()
+    assert per_row < 2 * tol_emu, per_row
+    # and the same images in a small batch give the same bits (batch is a pure map, also across tile choices)
+    small = eb.vmap(net, axis_name="batch")(x[idx], key=keys(len(idx)))
+    assert rel(small, got[idx]) < 5e-3
+
+
+def test_vit_base_full_batch_rows_vs_oracle(device, save_checkpoint):
+    """BASELINE configs[2]: ViT-B/16, 64 images per GPU (vit.py:56-76,139-157,261-273)"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    batch = 64
+    sd = ck.vit_state_dict(embed_dim=768, depth=12, heads=12, num_classes=1000, seed=3)
+    net = build("vit_base", sd, save_checkpoint, num_classes=1000)
+    x = ck.synthetic_images(batch, seed=22)
+    got = eb.vmap(net)(x, key=keys(batch))
+    assert got.shape == (batch, 1000) and torch.isfinite(got).all()
+    idx = _spread_rows(batch)
+    ref = om.vit(sd, x[idx], heads=12)
+    with O.emulate_bf16():
+        emu = om.vit(sd, x[idx], heads=12)
+    assert rel(got[idx], emu) < 1.5e-2 and rel(got[idx], ref) < 3e-2, (rel(got[idx], emu), rel(got[idx], ref))
+    per_row = ((got[idx].cpu() - emu).norm(dim=1) / emu.norm(dim=1)).max().item()
+    assert per_row < 3e-2, per_row
+
+
+def test_efficientnet_b4_full_batch_rows_vs_oracle(device, save_checkpoint):
+    """BASELINE configs[3]: EfficientNet-B4, batch 128 (efficientnet.py:101-186,392-403; squeeze.py:51-61)"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    batch = 128
+    sd = ck.torchvision_state_dict("efficientnet_b4", seed=1)
+    net = build("efficientnet_b4", sd, save_checkpoint)
+    x = ck.synthetic_images(batch, seed=23)
+    got = eb.vmap(net, axis_name="batch")(x, key=keys(batch))
+    assert got.shape == (batch, 1000) and torch.isfinite(got).all()
+    idx = _spread_rows(batch)
+    ref = om.efficientnet(sd, x[idx], "efficientnet_b4")
+    with O.emulate_bf16():
+        emu = om.efficientnet(sd, x[idx], "efficientnet_b4")
+    assert rel(got[idx], emu) < 1e-2 and rel(got[idx], ref) < 2e-2, (rel(got[idx], emu), rel(got[idx], ref))
+    per_row = ((got[idx].cpu() - emu).norm(dim=1) / emu.norm(dim=1)).max().item()
+    assert per_row < 2e-2, per_row
+
+
+def test_deeplabv3_512_baseline_shape(device, save_checkpoint):
+    """BASELINE configs[4]: DeepLabV3-ResNet50 on 512x512 inputs (64x64 maps at output stride 8, Cin 2048, ASPP
+    dilations 12/24/36 with PARTIAL tap overlap: deeplabv3.py:38-55,77-135). Batch 4 on the device (the shape the
+    bench times), the oracle checks two of the four images."""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    tv = ck.torchvision_model("deeplabv3_resnet50", seed=1, calib_hw=64, aux_loss=True)
+    sd = tv.state_dict()
+    net = eb.models.deeplabv3(intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024,
+                              torch_weights=save_checkpoint(sd))
+    net = eb.tree_inference(net, True)
+    x = ck.synthetic_images(4, h=512, w=512, seed=24)
+    aux, out = eb.vmap(net, axis_name="batch")(x, key=keys(4))
+    assert out.shape == (4, 21, 512, 512) and aux.shape == (4, 21, 512, 512)
+    assert torch.isfinite(out).all() and torch.isfinite(aux).all()
+    idx = torch.tensor([0, 3])
+    aux_r, out_r = om.deeplabv3_resnet50(sd, x[idx])
+    with O.emulate_bf16():
+        aux_e, out_e = om.deeplabv3_resnet50(sd, x[idx])
+    r = dict(out_e=rel(out[idx], out_e), aux_e=rel(aux[idx], aux_e), out_r=rel(out[idx], out_r),
+             aux_r=rel(aux[idx], aux_r))
+    print("deeplabv3@512 rel-L2:", r)
+    assert r["out_e"] < 8e-2 and r["aux_e"] < 4e-2, r
+    assert r["out_r"] < 2e-1 and r["aux_r"] < 1e-1, r
+    agree = (out[idx].cpu().argmax(1) == out_e.argmax(1)).float().mean().item()
+    assert agree > 0.9, agree
