@@ -3,25 +3,29 @@
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port of the reference
-  torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, weak scaling, no collective
+  torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, weak scaling
 
 Workload at N=1 (BASELINE.json configs[1]): ResNet-50 inference, bf16, batch 256 per GPU, synthetic
-3x224x224 images, seeded synthetic checkpoint loaded through load_torch_weights. ViT-B/16 (64 images
-per GPU = 512 over 8, configs[2]) is measured in the same run and reported under "secondary";
-`--all-configs` adds EfficientNet-B4 (B=128, configs[3]), DeepLabV3-ResNet50 (4x3x512x512, configs[4]) and the
-README's single-image AlexNet forward (configs[0]).
-A "step" is one forward pass over one batch: one CUDA-graph replay (57 kernel launches for R50).
+3x224x224 images, seeded synthetic checkpoint loaded through load_torch_weights. The other four BASELINE
+configs are measured in the same run and reported under "secondary": ViT-B/16 (64 images per GPU = 512 over 8,
+configs[2]; with N > 1 its logits all-gather is inside the timed step), EfficientNet-B4 (B=128, configs[3]),
+DeepLabV3-ResNet50 (4x3x512x512, configs[4]) and the README's single-image AlexNet forward (configs[0]).
+A "step" is one forward pass over one batch: one CUDA-graph replay (56 kernel launches for R50).
 
   value   : inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e     : pinned host fp32 NCHW batch -> H2D -> graph -> D2H of every model output, every step, same
-            events; EQXV_E2E_LANES (default 3) plans are used round-robin so that the copy of step i+1
-            overlaps the kernels of step i, graph launches are FIFO-chained across lanes
-  roofline: tensor-bound models: the tcgen05 implicit-GEMM family (all conv/linear launches of a step),
-            algorithmic FLOPs (8.178 GFLOP/img for R50) over the summed per-launch device
-            time of those launches, against the measured sustained cuBLAS bf16 peak; HBM-bound models
+  e2e     : through the public call `eb.filter_jit(eb.vmap(net, axis_name="batch"))(images, key=keys)` with a PINNED HOST
+            batch every step and a device-to-host copy of every model output every step, timed with CUDA events on
+            torch's stream (which the public call orders its results on). Headline: uint8 HWC pixels in
+            (`transforms.images_u8`: ToTensor + Normalize of the reference's fixture fused on the device);
+            `e2e_f32` is the same with the reference's fp32 NCHW batch (4x the bytes over PCIe).
+  roofline: tensor-bound models: the tcgen05 implicit-GEMM family (all conv/linear launches of a step), algorithmic
+            FLOPs (8.178 GFLOP/img for R50) over that family's share of the graph-replay step (share
+            from per-launch event pairs of an eager replay; eager launches lose the PDL overlap, so their SUM exceeds
+            the step and only the share is used), against the measured sustained cuBLAS bf16 peak; HBM-bound models
             (EfficientNet-B4): whole-step algorithmic bytes against the measured copy bandwidth;
-            `traffic` = ncu DRAM bytes of those launches (profiles/traffic.json)
-  cpu_baseline: the CPU oracle (torch fp32 restatement of the reference, kind "port") on a bounded sample
+            `traffic` = ncu DRAM bytes of the step (profiles/traffic.json, regenerated per round)
+  cpu_baseline: the CPU oracle (torch fp32 restatement of the reference, kind "port") on a bounded sample, timed on
+            rank 0 AFTER the process group is gone (no rank spins on a barrier beside it)
 """
 from __future__ import annotations
 
@@ -58,6 +62,20 @@ MODELS = {
 FLOP_PER_IMG = {k: v["flop"] for k, v in MODELS.items()}
 BYTES_PER_IMG = {k: v["bytes"] for k, v in MODELS.items()}
 PER_GPU_BATCH = {k: v["batch"] for k, v in MODELS.items()}
+
+
+def config_of(name: str, world: int) -> dict:
+    """the `config` object: identical in the B200 arm and in the reference arm (same workload, same batch)"""
+    hw = MODELS[name]["hw"]
+    b = PER_GPU_BATCH[name]
+    return {
+        "workload": f"{name} inference 3x{hw}x{hw}, batch {b} per GPU ({MODELS[name]['config']})",
+        "global_batch": b * world,
+        "parallelism": f"dp{world} (batch sharded, weights replicated)",
+        "l2": "every step's input + activations exceed the 126 MB L2 several times over: no explicit flush between "
+              "timed iterations (AlexNet at batch 1: 122 MB of filters + L2-resident activations, stated in its line)",
+        "checkpoint": "seeded synthetic state_dict via load_torch_weights",
+    }
 
 
 def load_peaks():
@@ -110,6 +128,7 @@ class ClockSampler:
             except Exception:  # noqa: BLE001
                 continue
         sm.sort()
+        # median over the samples taken under load (idle samples sit at the max clock as well on this part)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -144,29 +163,32 @@ def build_model(name: str):
     return eb.tree_inference(model, True), sd
 
 
-def measure(name, model, batch, steps, warmup, dist, rank):
-    """returns dict(ms, e2e_ms, launches, igemm_ms, plan)"""
+def _leaves(out):
+    if out is None:
+        return []
+    if isinstance(out, (list, tuple)):
+        return [t for o in out for t in _leaves(o)]
+    return [out]
+
+
+def measure(name, model, batch, steps, warmup, dist, rank, world, gather=False):
+    """returns dict(ms, e2e_ms, e2e_f32_ms, launches, by_kernel_ms, ...)"""
     import torch
 
     import eqxvision_b200 as eb
-    from eqxvision_b200 import _engine, _lib, ops
+    from eqxvision_b200 import _engine, _lib, ops, parallel
+    from eqxvision_b200 import transforms as tr
 
     hw = MODELS[name]["hw"]
     in_shape = (3, hw, hw)
-    plan = _engine.get_plan(model, "__call__", batch, in_shape, (), {"key": eb.random.PRNGKey(0)})
-    st = _engine.stream_handle()
+    keys = eb.random.split(eb.random.PRNGKey(0), batch)
     g = torch.Generator().manual_seed(100 + rank)
-    host_in = torch.rand((batch,) + in_shape, generator=g).pin_memory()
-
-    def host_mirrors(pl):   # one pinned host buffer per model output (DeepLabV3 returns (aux, out))
-        pairs = []
-        for o, _ in pl.outputs:
-            assert o.is_contiguous()
-            pairs.append((o, torch.empty(tuple(o.shape), dtype=o.dtype).pin_memory()))
-        return pairs
-
-    outs1 = host_mirrors(plan)
-    plan.x_in.copy_(host_in)
+    pixels = torch.randint(0, 256, (batch, hw, hw, 3), generator=g, dtype=torch.uint8)
+    host_u8 = tr.images_u8(pixels).pin_memory()                       # what a data loader hands over
+    host_f32 = host_u8.reference_pipeline().pin_memory()              # the reference's fp32 NCHW input
+    plan = _engine.get_plan(model, "__call__", batch, in_shape, (), {"key": keys})
+    st = plan.stream
+    plan.x_in.copy_(host_f32)
     torch.cuda.synchronize()
 
     def ev():
@@ -179,87 +201,62 @@ def measure(name, model, batch, steps, warmup, dist, rank):
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
+            torch.cuda.synchronize()
 
-    def timed(step_fn):
-        for _ in range(warmup):
-            step_fn()
+    # (1) device-resident inputs: graph replays on the plan's stream
+    for _ in range(warmup):
+        plan.launch(st)
+    barrier()
+    e0, e1 = ev(), ev()
+    _lib.call("eqxv_event_record", e0, st)
+    for _ in range(steps):
+        plan.launch(st)
+    _lib.call("eqxv_event_record", e1, st)
+    _lib.call("eqxv_event_sync", e1)
+    barrier()
+    t = C.c_float()
+    _lib.call("eqxv_event_elapsed_ms", e0, e1, C.byref(t))
+    ms = t.value / steps
+
+    # (2) end to end through the public API: pinned host batch in, every output copied back to pinned host memory
+    fwd = eb.filter_jit(eb.vmap(model, axis_name="batch"))
+    gatherer = [None]
+
+    def e2e(host_batch):
+        probe = _leaves(fwd(host_batch, key=keys))
+        if gather and dist is not None and gatherer[0] is None:
+            gatherer[0] = parallel.LogitsAllGather(probe[0].shape[0], probe[0].shape[1], probe[0].dtype)
+        mirrors = None
+
+        def one_step():
+            nonlocal mirrors
+            outs = _leaves(fwd(host_batch, key=keys))
+            if gatherer[0] is not None:
+                outs = [gatherer[0](outs[0])]                         # [world * B, classes] on every rank
+            if mirrors is None:
+                mirrors = [torch.empty(tuple(o.shape), dtype=o.dtype).pin_memory() for o in outs]
+            for o, h in zip(outs, mirrors):
+                h.copy_(o, non_blocking=True)
+
+        for _ in range(max(warmup, _engine.PIPELINE_LANES + 1)):
+            one_step()
         barrier()
-        e0, e1 = ev(), ev()
-        _lib.call("eqxv_event_record", e0, st)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
         for _ in range(steps):
-            step_fn()
-        _lib.call("eqxv_event_record", e1, st)
-        _lib.call("eqxv_event_sync", e1)
+            one_step()
+        t1.record()
+        t1.synchronize()
         barrier()
-        ms = C.c_float()
-        _lib.call("eqxv_event_elapsed_ms", e0, e1, C.byref(ms))
-        return ms.value / steps
+        return t0.elapsed_time(t1) / steps, sum(h.numel() * h.element_size() for h in mirrors)
 
-    # (1) device-resident inputs
-    ms = timed(lambda: plan.launch(st))
+    e2e_ms, d2h = e2e(host_u8)
+    e2e_f32_ms, _ = e2e(host_f32)
+    if gatherer[0] is not None:
+        gatherer[0].close()
 
-    # (2) end to end through host buffers: every step copies its own pinned fp32 NCHW batch to the
-    # device, replays the graph and copies the logits back. LANES plans (own buffers, own stream) are used
-    # round-robin so that the H2D copy of step i+1 overlaps the kernels of step i (copy engine vs SMs);
-    # graph launches are chained with events across lanes (compute runs FIFO, never two graphs interleaved:
-    # interleaving delays the completion of BOTH graphs and with it the next copies).
-    nbytes_in = host_in.numel() * 4
-    nbytes_out = sum(o.numel() * o.element_size() for o, _ in outs1)
-    n_lanes = int(os.environ.get("EQXV_E2E_LANES", "3"))
-    lanes = [(plan, st, outs1)]
-    for _ in range(n_lanes - 1):
-        pl = _engine.build_plan(model, "__call__", batch, in_shape, (), {"key": eb.random.PRNGKey(0)})
-        sx = C.c_void_p()
-        _lib.call("eqxv_stream_create", C.byref(sx))
-        lanes.append((pl, sx.value, host_mirrors(pl)))
-    counter = [0]
-    graph_done = [None]
-    ev_ring = [ev() for _ in range(8)]
-
-    def e2e_step():
-        pl, s, outs = lanes[counter[0] % n_lanes]
-        counter[0] += 1
-        _lib.call("eqxv_memcpy_h2d_async", pl.x_in.data_ptr(), host_in.data_ptr(), nbytes_in, s)
-        if graph_done[0] is not None:
-            _lib.call("eqxv_stream_wait_event", s, graph_done[0])   # FIFO on the SMs
-        pl.launch(s)
-        e = ev_ring[counter[0] % len(ev_ring)]
-        _lib.call("eqxv_event_record", e, s)
-        graph_done[0] = e
-        for o, ho in outs:
-            _lib.call("eqxv_memcpy_d2h_async", ho.data_ptr(), o.data_ptr(), o.numel() * o.element_size(), s)
-
-    def sync_lanes():
-        for _, s, _ in lanes:
-            _lib.call("eqxv_stream_sync", s)
-
-    def timed_lanes():
-        for _ in range(max(warmup, n_lanes)):
-            e2e_step()
-        sync_lanes()
-        barrier()
-        e0, e1 = ev(), ev()
-        _lib.call("eqxv_event_record", e0, st)
-        for _, s, _ in lanes[1:]:
-            _lib.call("eqxv_stream_wait_event", s, e0)   # every lane starts after e0
-        for _ in range(steps):
-            e2e_step()
-        for _, s, _ in lanes[1:]:                        # e1 is after the last step of EVERY lane
-            j = ev()
-            _lib.call("eqxv_event_record", j, s)
-            _lib.call("eqxv_stream_wait_event", st, j)
-        _lib.call("eqxv_event_record", e1, st)
-        _lib.call("eqxv_event_sync", e1)
-        sync_lanes()
-        barrier()
-        ms_ = C.c_float()
-        _lib.call("eqxv_event_elapsed_ms", e0, e1, C.byref(ms_))
-        return ms_.value / steps
-
-    e2e_ms = timed_lanes()
-    del lanes[1:]
-
-    # (3) per-launch device time of the igemm (conv / linear) launches, eager replay with events
+    # (3) share of each C entry in the step: per-launch event pairs of an eager replay (no PDL overlap, so the SUM
+    # is larger than the graph step; only the shares are used, scaled to the measured step)
     igemm_fns = (ops.conv2d, ops.gemm, ops.conv_stem, ops.conv_stem7x7)
     plan.run_steps(st)
     _lib.call("eqxv_stream_sync", st)
@@ -271,17 +268,22 @@ def measure(name, model, batch, steps, warmup, dist, rank):
         _lib.call("eqxv_event_record", b, st)
         evs.append((fn, a, b))
     _lib.call("eqxv_stream_sync", st)
-    igemm_ms, igemm_n, by_kernel = 0.0, 0, {}
+    eager, igemm_eager, igemm_n, by_kernel = 0.0, 0.0, 0, {}
     for fn, a, b in evs:
-        t = C.c_float()
         _lib.call("eqxv_event_elapsed_ms", a, b, C.byref(t))
         by_kernel[fn.__name__] = by_kernel.get(fn.__name__, 0.0) + t.value
+        eager += t.value
         if fn in igemm_fns:
-            igemm_ms += t.value
+            igemm_eager += t.value
             igemm_n += 1
-    return {"ms": ms, "e2e_ms": e2e_ms, "launches": plan.num_launches, "igemm_ms": igemm_ms,
-            "igemm_launches": igemm_n, "by_kernel_ms": {k: round(v, 4) for k, v in by_kernel.items()},
-            "h2d": nbytes_in, "d2h": nbytes_out, "act_bytes": plan.act_bytes}
+    scale = ms / eager
+    res = {"ms": ms, "e2e_ms": e2e_ms, "e2e_f32_ms": e2e_f32_ms, "launches": plan.num_launches,
+           "igemm_ms": igemm_eager * scale, "igemm_share": igemm_eager / eager, "igemm_launches": igemm_n,
+           "by_kernel_ms": {k: round(v * scale, 4) for k, v in by_kernel.items()}, "eager_sum_ms": eager,
+           "h2d_u8": pixels.numel(), "h2d_f32": host_f32.numel() * 4, "d2h": d2h, "act_bytes": plan.act_bytes,
+           "gathered": gatherer[0] is not None}
+    _engine.clear_plans(model)
+    return res
 
 
 def oracle_forward(name, sd, batch):
@@ -328,7 +330,6 @@ def run_reference_arm(args, rank):
     # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm uses all host cores explicitly
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     name = args.model
-    hw = MODELS[name]["hw"]
     sd = synthetic_state_dict(name)
     sample_batch = MODELS[name]["cpu_batch"]
     fn = oracle_forward(name, sd, sample_batch)
@@ -347,8 +348,7 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": "images/sec", "value": round(v, 2), "unit": "img/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name} inference 3x{hw}x{hw}, batch {PER_GPU_BATCH[name]} per GPU",
-                   "global_batch": PER_GPU_BATCH[name] * args.gpus},
+        "config": config_of(name, args.gpus),
         "cpu_baseline": {"value": round(v, 2), "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "jax/equinox are not installable offline; this arm is the CPU oracle port of the reference",
@@ -364,9 +364,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="resnet50", choices=sorted(MODELS))
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--all-configs", action="store_true",
-                    help="also measure EfficientNet-B4 (B=128), DeepLabV3-R50 (4x3x512x512) and AlexNet (1 image) "
-                         "as secondary lines")
+    ap.add_argument("--all-configs", action="store_true", help="kept for compatibility: all five BASELINE configs "
+                                                               "are measured by default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -401,8 +400,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    m = measure(name, model, batch, args.steps, args.warmup, dist, rank)
+    m = measure(name, model, batch, args.steps, args.warmup, dist, rank, world)
     clocks = sampler.stop() if rank == 0 else None
+    del model
 
     def max_over_ranks(v):
         if dist is None:
@@ -413,22 +413,22 @@ def main():
 
     ms = max_over_ranks(m["ms"])
     e2e_ms = max_over_ranks(m["e2e_ms"])
+    e2e_f32_ms = max_over_ranks(m["e2e_f32_ms"])
     total_imgs = batch * world
-    value = total_imgs / ms * 1e3
-    e2e_value = total_imgs / e2e_ms * 1e3
 
     def roofline_of(nm, mm, step_ms):
         """the model's binding roofline for the dominant kernel family"""
         nb = PER_GPU_BATCH[nm]
         if MODELS[nm]["bound"] == "tensor":
-            tf = FLOP_PER_IMG[nm] * nb / mm["igemm_ms"] / 1e9
+            k_ms = step_ms * mm["igemm_share"]
+            tf = FLOP_PER_IMG[nm] * nb / k_ms / 1e9
             r = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM family (all conv/linear launches of one step: "
                                               "igemm_kernel, pair_kernel, halo_kernel, stem_kernel)",
                  "achieved": round(tf, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                  "frac": round(tf / peaks["tflops_sustained"], 4), "traffic": None,
                  "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
-                 "launches": mm["igemm_launches"], "kernel_ms_per_step": round(mm["igemm_ms"], 4),
-                 "flop_per_image": FLOP_PER_IMG[nm]}
+                 "launches": mm["igemm_launches"], "kernel_ms_per_step": round(k_ms, 4),
+                 "kernel_share_of_step": round(mm["igemm_share"], 4), "flop_per_image": FLOP_PER_IMG[nm]}
         else:
             gbs = BYTES_PER_IMG[nm] * nb / step_ms / 1e6
             what = ("whole step (batch 1: every filter is read once, the classifier GEMMs are weight-bandwidth bound)"
@@ -447,49 +447,56 @@ def main():
                 r["traffic_source"] = t["source"]
         return r
 
+    def e2e_of(mm, nb, a_ms, f_ms):
+        return {"value": round(nb * world / a_ms * 1e3, 1), "unit": "img/s", "ms_per_step": round(a_ms, 4),
+                "h2d_bytes_per_step": mm["h2d_u8"], "d2h_bytes_per_step": mm["d2h"],
+                "api": "eb.filter_jit(eb.vmap(net, axis_name='batch'))(transforms.images_u8(pinned uint8 NHWC), "
+                       "key=keys); every output .copy_() to pinned host memory",
+                "input": "uint8 HWC pixels; ToTensor + Normalize of the reference fixture fused on the device"}, \
+               {"value": round(nb * world / f_ms * 1e3, 1), "unit": "img/s", "ms_per_step": round(f_ms, 4),
+                "h2d_bytes_per_step": mm["h2d_f32"], "d2h_bytes_per_step": mm["d2h"],
+                "input": "the reference's fp32 NCHW batch (pinned host memory), same public call"}
+
     secondary = {}
-    others = []
-    if not args.no_secondary:
-        others.append("vit_base" if name == "resnet50" else "resnet50")
-    if args.all_configs:
-        others += [k for k in ("efficientnet_b4", "deeplabv3_resnet50", "alexnet") if k != name and k not in others]
+    others = [] if args.no_secondary else [k for k in ("vit_base", "resnet50", "efficientnet_b4",
+                                                       "deeplabv3_resnet50", "alexnet") if k != name]
     for other in others:
         om_model, _ = build_model(other)
         ob = PER_GPU_BATCH[other]
-        sm = measure(other, om_model, ob, max(10, args.steps // 2), args.warmup, dist, rank)
+        gathered = other == "vit_base" and world > 1      # configs[2] asks for the gathered logits
+        sm = measure(other, om_model, ob, max(10, args.steps // 2), args.warmup, dist, rank, world, gather=gathered)
         s_ms = max_over_ranks(sm["ms"])
-        s_e2e = max_over_ranks(sm["e2e_ms"])
+        a, f = e2e_of(sm, ob, max_over_ranks(sm["e2e_ms"]), max_over_ranks(sm["e2e_f32_ms"]))
+        if gathered:
+            a["gathered"] = f["gathered"] = True
+            a["collective"] = "one all-gather of the fp32 logits per step inside the timed region (parallel.LogitsAllGather)"
         secondary[other] = {
             "value": round(ob * world / s_ms * 1e3, 1), "unit": "img/s", "ms_per_step": round(s_ms, 4),
-            "per_gpu_batch": ob, "e2e": round(ob * world / s_e2e * 1e3, 1), "config": MODELS[other]["config"],
+            "per_gpu_batch": ob, "e2e": a, "e2e_f32": f, "config": MODELS[other]["config"],
             "step_tflops_per_gpu": round(FLOP_PER_IMG[other] * ob / s_ms / 1e9, 1),
             "step_hbm_gbs_per_gpu": round(BYTES_PER_IMG[other] * ob / s_ms / 1e6, 1),
             "roofline": roofline_of(other, sm, s_ms),
             "by_kernel_ms": sm["by_kernel_ms"], "launches": sm["launches"],
+            "act_bytes": sm["act_bytes"],
         }
         del om_model
         torch.cuda.empty_cache()
 
+    # the process group goes away BEFORE the CPU sample: no rank spins on a barrier next to it
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
         return
 
-    hw = MODELS[name]["hw"]
+    a, f = e2e_of(m, batch, e2e_ms, e2e_f32_ms)
     line = {
-        "metric": "images/sec", "value": round(value, 1), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "metric": "images/sec", "value": round(total_imgs / ms * 1e3, 1), "unit": "img/s", "n_gpus": world,
+        "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {
-            "workload": f"{name} inference 3x{hw}x{hw}, batch {batch} per GPU ({MODELS[name]['config']})",
-            "global_batch": total_imgs, "parallelism": f"dp{world} (batch sharded, weights replicated, no collective)",
-            "l2": f"per-step working set {m['act_bytes'] / 2**30:.1f} GiB of activations + "
-                  f"{m['h2d'] / 2**20:.0f} MiB input >> 126 MB L2 (no explicit flush needed)",
-            "checkpoint": "seeded synthetic state_dict via load_torch_weights",
-        },
-        "e2e": {"value": round(e2e_value, 1), "unit": "img/s", "ms_per_step": round(e2e_ms, 4),
-                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+        "config": config_of(name, world),
+        "e2e": a, "e2e_f32": f,
         "gpu_launches": m["launches"] * args.steps,
         "launches_per_step": m["launches"],
         "roofline": roofline_of(name, m, ms),
@@ -499,6 +506,8 @@ def main():
                      "note": "whole step against the layer-wise algorithmic bytes (SURVEY.md §8(d)): the practical "
                              "ceiling of a layer-by-layer bf16 forward"},
         "by_kernel_ms": m["by_kernel_ms"],
+        "eager_sum_ms": round(m["eager_sum_ms"], 4),
+        "activation_bytes": m["act_bytes"],
         "clocks": clocks,
         "secondary": secondary,
     }
@@ -507,9 +516,6 @@ def main():
         line["cpu_baseline"] = {"value": round(v, 2), "unit": "img/s", "cores": cores, "kind": "port",
                                 "sample": sample}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

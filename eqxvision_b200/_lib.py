@@ -67,8 +67,22 @@ SIGNATURES = {
     "eqxv_resize_bilinear_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_copy2d_async": [_vp, _i64, _vp, _i64, _i64, _i64, _vp],
     "eqxv_window_attention_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
+    "eqxv_swin_v2_qk_normalize_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_patch_merge_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_debug_attention_timeline": [_vp],
+    "eqxv_u8hwc_to_nchw_f32": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_u8hwc_pack_stem_input": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_u8hwc_to_nhwc_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_u8hwc_patchify_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_u8hwc_resize_bilinear": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_p2p_window_bytes": [_i64, C.POINTER(_i64)],
+    "eqxv_p2p_alloc": [C.POINTER(_vp), _i64],
+    "eqxv_p2p_free": [_vp],
+    "eqxv_ipc_get_handle": [_vp, C.c_char_p],
+    "eqxv_ipc_open_handle": [C.c_char_p, C.POINTER(_vp)],
+    "eqxv_ipc_close_handle": [_vp],
+    "eqxv_allgather_push": [_vp, _i64, C.POINTER(_vp), _i32, _i32, _i64, _i64, _vp],
+    "eqxv_p2p_buffer_offset": [_i32, _i64, C.POINTER(_i64)],
     "eqxv_stream_create": [C.POINTER(_vp)],
     "eqxv_stream_destroy": [_vp],
     "eqxv_stream_sync": [_vp],
@@ -84,6 +98,7 @@ SIGNATURES = {
     "eqxv_event_elapsed_ms": [_vp, _vp, C.POINTER(_f32)],
     "eqxv_memcpy_h2d_async": [_vp, _vp, _i64, _vp],
     "eqxv_memcpy_d2h_async": [_vp, _vp, _i64, _vp],
+    "eqxv_memcpy_async": [_vp, _vp, _i64, _vp],
     "eqxv_memset_async": [_vp, C.c_int, _i64, _vp],
 }
 _NON_STATUS = {"eqxv_version": C.c_char_p, "eqxv_last_error": C.c_char_p, "eqxv_sm_count": C.c_int}
@@ -101,6 +116,8 @@ _LAUNCHING = {
     "eqxv_vit_assemble_tokens_bf16", "eqxv_gather_rows_bf16", "eqxv_dwconv_bn_act_bf16", "eqxv_dwconv_tile_bf16", "eqxv_eltwise_bf16",
     "eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32", "eqxv_resize_bilinear_nhwc_bf16", "eqxv_copy2d_async",
     "eqxv_window_attention_bf16", "eqxv_patch_merge_bf16",
+    "eqxv_u8hwc_to_nchw_f32", "eqxv_u8hwc_pack_stem_input", "eqxv_u8hwc_to_nhwc_bf16", "eqxv_u8hwc_patchify_bf16",
+    "eqxv_u8hwc_resize_bilinear", "eqxv_allgather_push", "eqxv_swin_v2_qk_normalize_bf16",
 }
 
 

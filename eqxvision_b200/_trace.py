@@ -184,11 +184,12 @@ class Resize(Expr):  # jax.image.resize(method="bilinear"), _utils.py:52
 
 
 class WindowAttention(Expr):  # swin.py:90-255 between the qkv and proj matmuls
-    __slots__ = ("qkv", "h", "w", "heads", "window", "shift", "bias", "scale")
+    __slots__ = ("qkv", "h", "w", "heads", "window", "shift", "bias", "scale", "cosine_scale")
 
-    def __init__(self, qkv, h, w, heads, window, shift, bias, scale):
+    def __init__(self, qkv, h, w, heads, window, shift, bias, scale, cosine_scale=None):
         self.qkv, self.h, self.w, self.heads = qkv, h, w, heads
         self.window, self.shift, self.bias, self.scale = window, shift, bias, scale
+        self.cosine_scale = cosine_scale   # Swin-V2: per-head exp(min(logit_scale, log 100)); q, k normalised first
 
 
 class PatchMerge(Expr):  # swin.py:23-33: 2x2 strided gather, channels (x0,x1,x2,x3)
@@ -547,7 +548,8 @@ def resize_bilinear(x: Sym, h: int, w: int) -> Sym:
     return Sym("chw", (c, h, w), Resize(x, h, w))
 
 
-def window_attention(qkv: Sym, h: int, w: int, heads: int, window, shift, bias, scale: float) -> Sym:
+def window_attention(qkv: Sym, h: int, w: int, heads: int, window, shift, bias, scale: float,
+                     cosine_scale=None) -> Sym:
     """softmax(q*scale k^T + bias + shift_mask) v per window; qkv is the (H*W, 3C) token matrix in
     spatial order, the result is the (H*W, C) matrix in the same order (swin.py:117-253)."""
     t, c3 = qkv.shape
@@ -556,7 +558,8 @@ def window_attention(qkv: Sym, h: int, w: int, heads: int, window, shift, bias, 
     if h % window[0] != 0 or w % window[1] != 0:
         # the reference has the padding commented out (swin.py:107-112): its reshape raises
         raise ValueError(f"feature map {h}x{w} is not a multiple of the window {tuple(window)}")
-    return Sym("tokens", (t, c3 // 3), WindowAttention(qkv, h, w, heads, tuple(window), tuple(shift), bias, scale))
+    return Sym("tokens", (t, c3 // 3), WindowAttention(qkv, h, w, heads, tuple(window), tuple(shift), bias, scale,
+                                                      cosine_scale))
 
 
 def patch_merge(x: Sym) -> Sym:

@@ -181,11 +181,15 @@ extern "C" int eqxv_event_elapsed_ms(void* start, void* stop, float* ms) {
   return EQXV_OK;
 }
 extern "C" int eqxv_memcpy_h2d_async(void* dst, const void* src, int64_t bytes, void* stream) {
-  EQXV_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  EQXV_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
   return EQXV_OK;
 }
 extern "C" int eqxv_memcpy_d2h_async(void* dst, const void* src, int64_t bytes, void* stream) {
-  EQXV_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  EQXV_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return EQXV_OK;
+}
+extern "C" int eqxv_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  EQXV_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
   return EQXV_OK;
 }
 extern "C" int eqxv_memset_async(void* dst, int value, int64_t bytes, void* stream) {

@@ -106,6 +106,55 @@ __global__ void __launch_bounds__(128) window_attention_kernel(
   }
 }
 
+// Swin-V2 cosine attention as the REFERENCE computes it (swin.py:158-166): q / ||q|| and k / ||k|| with the L2 norm taken
+// over axis 0 of the (num_windows, heads, tokens, d) arrays, i.e. over the WINDOWS of one image for every (head, window
+// token, channel) - not over the channel axis as torchvision does. q is then multiplied by
+// exp(min(logit_scale, log 100)) per head (swin.py:164-166; `scale_q`, evaluated on the host). In place on the q and k
+// column ranges of the spatial-order qkv matrix; one CTA = one (window token, image), one thread = 8 channels.
+__global__ void __launch_bounds__(256) swin_v2_qk_normalize_kernel(__nv_bfloat16* __restrict__ qkv,
+                                                                   const float* __restrict__ scale_q, int H, int W, int C,
+                                                                   int head_dim, int ws, int shift_h, int shift_w) {
+  griddep_wait();
+  griddep_launch();
+  const int ty = blockIdx.x / ws, tx = blockIdx.x % ws;
+  const int img = blockIdx.y;
+  const int nwr = H / ws, nwc = W / ws;
+  const long long ld = 3ll * C;
+  __nv_bfloat16* base = qkv + (long long)img * H * W * ld;
+  for (int v = threadIdx.x; v < 2 * C / 8; v += blockDim.x) {      // q columns [0,C), k columns [C,2C)
+    float ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int wr = 0; wr < nwr; ++wr)
+      for (int wc = 0; wc < nwc; ++wc) {
+        const int sy = (wr * ws + ty + shift_h) % H, sx = (wc * ws + tx + shift_w) % W;
+        const uint4 raw = *reinterpret_cast<const uint4*>(base + ((long long)sy * W + sx) * ld + v * 8);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h2[i]);
+          ss[2 * i] = fmaf(f.x, f.x, ss[2 * i]);
+          ss[2 * i + 1] = fmaf(f.y, f.y, ss[2 * i + 1]);
+        }
+      }
+    const float sq = (v * 8 < C) ? __ldg(scale_q + (v * 8) / head_dim) : 1.f;
+    float inv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) inv[i] = sq / sqrtf(ss[i]);
+    for (int wr = 0; wr < nwr; ++wr)
+      for (int wc = 0; wc < nwc; ++wc) {
+        const int sy = (wr * ws + ty + shift_h) % H, sx = (wc * ws + tx + shift_w) % W;
+        uint4* ptr = reinterpret_cast<uint4*>(base + ((long long)sy * W + sx) * ld + v * 8);
+        uint4 raw = *ptr;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h2[i]);
+          h2[i] = __floats2bfloat162_rn(f.x * inv[2 * i], f.y * inv[2 * i + 1]);
+        }
+        *ptr = raw;
+      }
+  }
+}
+
 // out[n, y2, x2, k*C + c] = x[n, 2*y2 + dy_k, 2*x2 + dx_k, c],  (dy,dx)_k = (0,0),(1,0),(0,1),(1,1)
 // (x0,x1,x2,x3 of swin.py:26-31); H, W even.
 __global__ void patch_merge_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h,
@@ -158,6 +207,21 @@ extern "C" int eqxv_window_attention_bf16(const void* qkv, const float* bias, vo
   dim3 grid((unsigned)((h / window) * (w / window)), (unsigned)n);
   EQXV_CUDA(launch_kernel(window_attention_kernel<32>, dim3(grid), dim3(128), (size_t)(smem), (cudaStream_t)stream, 
       (const __nv_bfloat16*)qkv, bias, (__nv_bfloat16*)out, h, w, heads, window, shift_h, shift_w, scale));
+  EQXV_CUDA(cudaGetLastError());
+  return EQXV_OK;
+}
+
+extern "C" int eqxv_swin_v2_qk_normalize_bf16(void* qkv, const float* scale_q, int32_t n, int32_t h, int32_t w,
+                                              int32_t heads, int32_t head_dim, int32_t window, int32_t shift_h,
+                                              int32_t shift_w, void* stream) {
+  EQXV_CHECK_ARG(qkv && scale_q && n > 0 && h > 0 && w > 0 && heads > 0 && head_dim > 0 && head_dim % 8 == 0,
+                 "swin_v2_qk_normalize: bad arguments");
+  EQXV_CHECK_ARG(window >= 1 && h % window == 0 && w % window == 0 && shift_h >= 0 && shift_h < window && shift_w >= 0 &&
+                     shift_w < window && n <= 65535,
+                 "swin_v2_qk_normalize: the map (%dx%d) must be a multiple of the window (%d)", h, w, window);
+  dim3 grid((unsigned)(window * window), (unsigned)n);
+  EQXV_CUDA(launch_kernel(swin_v2_qk_normalize_kernel, grid, dim3(256), (size_t)0, (cudaStream_t)stream,
+                          (__nv_bfloat16*)qkv, scale_q, h, w, heads * head_dim, head_dim, window, shift_h, shift_w));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }

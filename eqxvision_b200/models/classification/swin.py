@@ -1,4 +1,4 @@
-"""Swin Transformer v1 (reference: models/classification/swin.py, a torchvision port).
+"""Swin Transformer v1 and v2 (reference: models/classification/swin.py, a torchvision port).
 
 Field order follows the reference so that torchvision checkpoints load positionally
 (`relative_position_bias_table`, `relative_position_index`, qkv, proj — the integer index buffer is
@@ -9,21 +9,29 @@ Reference quirks kept on purpose:
   `ravel(relative_coords.sum(-1))` — partly negative indices (numpy wrap-around) until a checkpoint
   replaces them; `define_relative_position_bias_table` draws `truncated_normal(lower=2, upper=2)`.
 * the feature map must be a multiple of the window (padding is commented out, swin.py:107-112).
-* Swin-V2 (cosine attention normalised along axis 0, swin.py:161-163; "pretrained not supported",
-  docs/comparison.md:15) is constructible for API parity but its forward is not on the hot path.
+* Swin-V2 (swin.py:369-522, 583-636): cosine attention whose q / k are normalised along AXIS 0 of the
+  (num_windows, heads, tokens, d) arrays - over the windows of the image, not over d as in torchvision (swin.py:161-163);
+  the continuous position bias MLP's channel-first output is reshaped to (-1, heads) without a transpose (swin.py:496-498),
+  and its relative-position index has the same discarded-stack quirk as v1. All three are reproduced; the reference
+  itself lists v2 pretrained weights as unsupported (docs/comparison.md:15).
 
 Device lowering per block (activations stay channels-last, so every CHW<->HWC transpose of the
 reference is free): LayerNorm -> qkv GEMM(+bias) -> eqxv_window_attention_bf16 (roll, window
 partition, relative-position bias, shift mask, softmax, PV, reverse — all index arithmetic) ->
 proj GEMM(+bias+residual) -> LayerNorm -> fc1 GEMM(+bias+tanh-GELU) -> fc2 GEMM(+bias+residual).
-Patch merging = eqxv_patch_merge_bf16 gather -> LayerNorm(4C) -> GEMM(4C->2C).
+Patch merging = eqxv_patch_merge_bf16 gather -> LayerNorm(4C) -> GEMM(4C->2C)  (v2: GEMM, then LayerNorm(2C)).
+V2 block: qkv GEMM (k bias zeroed) -> eqxv_swin_v2_qk_normalize_bf16 (in place) -> eqxv_window_attention_bf16 with
+scale 1 and bias 16*sigmoid(cpb_mlp(coords)[index]) evaluated on the host (weights only) -> proj GEMM -> LayerNorm
+-> + x (post-norm, swin.py:630-636).
 """
+import math
 import warnings
 from functools import partial
 from typing import Any, Callable, List, Optional
 
 import torch
 
+from ... import _trace as T
 from ... import functional as F
 from ... import nn
 from ... import random as jrandom
@@ -76,8 +84,6 @@ def _shifted_window_attention(x, qkv: Linear2d, proj: Linear2d, relative_positio
                               num_heads: int, shift_size: List[int], attention_dropout: float = 0.0,
                               dropout: float = 0.0, logit_scale=None, key=None):
     """swin.py:90-255 on a (C,H,W) map. Dropout with p == 0 is the identity (swin.py:17-20 divides by 1)."""
-    if logit_scale is not None:
-        raise NotImplementedError("Swin-V2 cosine attention (swin.py:158-166) is not on the hot path")
     if attention_dropout != 0.0 or dropout != 0.0:
         raise NotImplementedError("Swin dropout ignores inference mode in the reference (swin.py:227,233); "
                                   "only p == 0 is supported")
@@ -88,10 +94,23 @@ def _shifted_window_attention(x, qkv: Linear2d, proj: Linear2d, relative_positio
     if window_size[1] >= w:
         shift[1] = 0
     tokens = F.to_tokens(x)                                   # transpose (1,2,0): free in NHWC
-    qkv_t = nn.Linear.__call__(qkv, tokens)                   # swin.py:155-157
     head_dim = c // num_heads
-    out = F.window_attention(qkv_t, h, w, num_heads, window_size, shift, relative_position_bias,
-                             head_dim ** -0.5)                # swin.py:168-231
+    if logit_scale is not None:
+        # Swin-V2 (swin.py:146-166): the k third of the qkv bias is zeroed, q and k are normalised (axis 0 = the windows
+        # of the image) and q scaled by exp(min(logit_scale, log 100)) per head; no d^-1/2
+        bias = qkv.bias
+        if bias is not None:
+            bias = bias.clone()
+            length = bias.numel() // 3
+            bias[length:2 * length] = 0
+        qkv_t = T.linear(tokens, qkv.weight, bias)
+        scale_q = torch.exp(torch.clamp(logit_scale.detach().float().reshape(-1), max=math.log(100.0)))
+        out = F.window_attention(qkv_t, h, w, num_heads, window_size, shift, relative_position_bias, 1.0,
+                                 cosine_scale=scale_q)
+    else:
+        qkv_t = nn.Linear.__call__(qkv, tokens)               # swin.py:155-157
+        out = F.window_attention(qkv_t, h, w, num_heads, window_size, shift, relative_position_bias,
+                                 head_dim ** -0.5)            # swin.py:168-231
     out = nn.Linear.__call__(proj, out)                       # swin.py:232
     return F.to_map(out, h, w)                                # reverse windows / roll / transpose: free
 
@@ -144,11 +163,81 @@ class _ShiftedWindowAttention(nn.Module):
             shift_size=self.shift_size, attention_dropout=self.attention_dropout, dropout=self.dropout, key=key)
 
 
-class _ShiftedWindowAttentionV2(_ShiftedWindowAttention):
-    """Constructible for API parity (swin.py:367-522); the cosine-attention forward is not built."""
+class _ShiftedWindowAttentionV2(nn.Module):
+    """swin.py:369-522"""
+    window_size: List[int]
+    shift_size: List[int]
+    num_heads: int
+    attention_dropout: float
+    dropout: float
+    logit_scale: torch.Tensor
+    relative_position_bias_table: torch.Tensor
+    relative_position_index: torch.Tensor
+    qkv: nn.Linear
+    proj: nn.Linear
+    cpb_mlp: nn.Sequential
+
+    def __init__(self, dim: int, window_size: List[int], shift_size: List[int], num_heads: int,
+                 qkv_bias: bool = True, proj_bias: bool = True, attention_dropout: float = 0.0,
+                 dropout: float = 0.0, *, key=None):
+        if len(window_size) != 2 or len(shift_size) != 2:
+            raise ValueError("window_size and shift_size must be of length 2")
+        keys = jrandom.split(key, 3)
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.num_heads = num_heads
+        self.attention_dropout = attention_dropout
+        self.dropout = dropout
+        self.qkv = Linear2d(dim, dim * 3, use_bias=qkv_bias, key=keys[0])
+        self.proj = Linear2d(dim, dim, use_bias=proj_bias, key=keys[1])
+        self.relative_position_bias_table = self.define_relative_position_bias_table(key=keys[2])
+        self.relative_position_index = self.define_relative_position_index()
+        self.logit_scale = torch.log(10 * torch.ones((num_heads, 1, 1)))
+        # mlp to generate continuous relative position bias (swin.py:413-421); evaluated on the host, weights only
+        self.cpb_mlp = nn.Sequential([
+            nn.Lambda(_chw_of_hwc),
+            Linear2d(2, 512, use_bias=True, key=keys[1]),
+            nn.Lambda(F.relu),
+            Linear2d(512, num_heads, use_bias=False, key=keys[2]),
+            nn.Lambda(F.identity),
+        ])
+        if qkv_bias:                                          # swin.py:422-428
+            length = self.qkv.bias.numel() // 3
+            self.qkv.bias[length:2 * length] = 0
+
+    define_relative_position_index = _ShiftedWindowAttention.define_relative_position_index   # swin.py:430-452
+
+    def define_relative_position_bias_table(self, key):
+        """swin.py:454-481: the log-spaced relative COORDINATE table (2Wh-1, 2Ww-1, 2), input of cpb_mlp"""
+        wh, ww = self.window_size
+        ch = torch.arange(-(wh - 1), wh, dtype=torch.float32)
+        cw = torch.arange(-(ww - 1), ww, dtype=torch.float32)
+        t = torch.stack(torch.meshgrid(ch, cw, indexing="ij")).permute(1, 2, 0)
+        t = torch.stack([t[:, :, 0] / wh - 1, t[:, :, 1] / ww - 1], -1)   # (sic) "/ window - 1", swin.py:468-469
+        t = 8 * t
+        return torch.sign(t) * torch.log2(torch.abs(t) + 1.0) / 3.0
+
+    def get_relative_position_bias(self) -> torch.Tensor:
+        """swin.py:483-504 on the host (parameters only): 16 * sigmoid(cpb_mlp(table).reshape(-1, heads)[index])"""
+        table = self.relative_position_bias_table.detach().float()
+        a, b, _ = table.shape
+        fc1, fc2 = self.cpb_mlp.layers[1], self.cpb_mlp.layers[3]
+        tok = table.reshape(a * b, 2)                          # Linear2d sees the (2, A, B) map as (A*B, 2) rows
+        hid = torch.relu(tok @ fc1.weight.detach().float().t() + fc1.bias.detach().float())
+        out_chw = (hid @ fc2.weight.detach().float().t()).t().contiguous()   # Linear2d returns (heads, A, B)
+        flat = out_chw.reshape(-1, self.num_heads)             # (sic) channel-first data read as (-1, heads)
+        bias = _get_relative_position_bias(flat, self.relative_position_index, self.window_size)
+        return 16 * torch.sigmoid(bias)
 
     def __call__(self, x, *, key=None):
-        raise NotImplementedError("Swin-V2 attention (swin.py:506-522) is outside the round-1 hot path")
+        return _shifted_window_attention(
+            x, self.qkv, self.proj, self.get_relative_position_bias(), self.window_size, self.num_heads,
+            shift_size=self.shift_size, attention_dropout=self.attention_dropout, dropout=self.dropout,
+            logit_scale=self.logit_scale, key=key)
+
+
+def _chw_of_hwc(x, *, key=None):   # Lambda(partial(jnp.transpose, axes=(2, 0, 1))), swin.py:415 (host-side only)
+    return x.permute(2, 0, 1)
 
 
 class _SwinTransformerBlock(nn.Module):
@@ -281,7 +370,7 @@ def swin_b(torch_weights: str = None, **kwargs: Any) -> SwinTransformer:
 
 
 def swin_v2_t(torch_weights: str = None, **kwargs: Any) -> SwinTransformer:
-    """swin.py:874-896 (constructible; forward not on the hot path)"""
+    """swin.py:874-896"""
     return _swin_transformer("swin_v2_t", [4, 4], 96, [2, 2, 6, 2], [3, 6, 12, 24], [8, 8], 0.2, torch_weights,
                              block=_SwinTransformerBlockV2, downsample_layer=_PatchMergingV2, **kwargs)
 

@@ -270,10 +270,76 @@ def window_attention(qkv, bias, *, n, h, w, heads, head_dim, window, shift, scal
     return out
 
 
+def swin_v2_qk_normalize(qkv, scale_q, *, n, h, w, heads, head_dim, window, shift, stream=0):
+    """in place: q, k /= L2 norm over the windows of each image; q *= scale_q[head] (swin.py:158-166)"""
+    _check_cuda(qkv, scale_q)
+    if qkv.stride(0) != 3 * heads * head_dim:
+        raise _lib.EqxvError("swin_v2_qk_normalize expects a dense qkv matrix")
+    call("eqxv_swin_v2_qk_normalize_bf16", ptr(qkv), ptr(scale_q), n, h, w, heads, head_dim, window, shift[0],
+         shift[1], stream)
+    return qkv
+
+
 def patch_merge(x, out=None, stream=0):
     _check_cuda(x, out)
     n, h, w, c = x.shape
     if out is None:
         out = torch.empty((n, h // 2, w // 2, 4 * c), dtype=BF16, device=x.device)
     call("eqxv_patch_merge_bf16", ptr(x), ptr(out), n, h, w, c, x.stride(2), out.stride(2), stream)
+    return out
+
+
+# ---- input edge: uint8 HWC images, ToTensor + Normalize fused (tests/conftest.py:20-41 of the reference) ----------
+def _check_u8(x, lut):
+    _check_cuda(x, lut)
+    if x.dtype != torch.uint8 or x.dim() != 4 or not x.is_contiguous() or x.shape[3] > 4:
+        raise _lib.EqxvError("input edge: expected a contiguous uint8 [N, H, W, C<=4] image batch")
+    if lut.dtype != torch.float32 or tuple(lut.shape) != (x.shape[3], 256) or not lut.is_contiguous():
+        raise _lib.EqxvError("input edge: lut must be fp32 [C, 256]")
+
+
+def u8_to_nchw_f32(x, lut, out=None, stream=0):
+    _check_u8(x, lut)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    call("eqxv_u8hwc_to_nchw_f32", ptr(x), ptr(lut), ptr(out), n, h, w, c, stream)
+    return out
+
+
+def u8_pack_stem_input(x, lut, pad=3, out=None, stream=0):
+    _check_u8(x, lut)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, h + 2 * pad, w + 8, 8), dtype=BF16, device=x.device)
+    call("eqxv_u8hwc_pack_stem_input", ptr(x), ptr(lut), ptr(out), n, h, w, c, pad, stream)
+    return out
+
+
+def u8_to_nhwc(x, lut, out=None, stream=0):
+    _check_u8(x, lut)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, 8), dtype=BF16, device=x.device)
+    call("eqxv_u8hwc_to_nhwc_bf16", ptr(x), ptr(lut), ptr(out), n, h, w, c, stream)
+    return out
+
+
+def u8_patchify(x, lut, p, out=None, stream=0):
+    _check_u8(x, lut)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n * (h // p) * (w // p), c * p * p), dtype=BF16, device=x.device)
+    call("eqxv_u8hwc_patchify_bf16", ptr(x), ptr(lut), ptr(out), n, h, w, c, p, stream)
+    return out
+
+
+def u8_resize_bilinear(x, oh, ow, out=None, stream=0):
+    _check_cuda(x, out)
+    if x.dtype != torch.uint8 or x.dim() != 4 or not x.is_contiguous():
+        raise _lib.EqxvError("u8_resize_bilinear: expected a contiguous uint8 [N, H, W, C] batch")
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
+    call("eqxv_u8hwc_resize_bilinear", ptr(x), ptr(out), n, h, w, c, oh, ow, stream)
     return out

@@ -192,6 +192,13 @@ int eqxv_resize_bilinear_nhwc_bf16(const void* x, void* y, int32_t n, int32_t c,
 int eqxv_window_attention_bf16(const void* qkv, const float* bias, void* out, int32_t n, int32_t h, int32_t w,
                                int32_t heads, int32_t head_dim, int32_t window, int32_t shift_h,
                                int32_t shift_w, float scale, void* stream);
+/* Swin-V2 cosine attention, first half (swin.py:158-166, _ShiftedWindowAttentionV2): q and k of the spatial-order qkv
+ * matrix are divided IN PLACE by their L2 norm over axis 0 of the reference's (num_windows, heads, tokens, d) arrays
+ * - the windows of one image, per (head, window token, channel); the reference's quirk, torchvision normalises over d -
+ * and q is multiplied by scale_q[head] = exp(min(logit_scale, log 100)). Follow with eqxv_window_attention_bf16
+ * (scale = 1, bias = 16 * sigmoid(cpb_mlp(...)), swin.py:494-504). */
+int eqxv_swin_v2_qk_normalize_bf16(void* qkv, const float* scale_q, int32_t n, int32_t h, int32_t w, int32_t heads,
+                                   int32_t head_dim, int32_t window, int32_t shift_h, int32_t shift_w, void* stream);
 /* K16: patch merging gather (swin.py:23-33): [n,h,w,c] -> [n,h/2,w/2,4c] = concat(x[0::2,0::2],
  * x[1::2,0::2], x[0::2,1::2], x[1::2,1::2]) along channels. */
 int eqxv_patch_merge_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t x_pitch,
@@ -201,6 +208,51 @@ int eqxv_debug_attention_timeline(long long* ts);
 /* K13 fallback: strided device-to-device copy (channel slices of a concat buffer) */
 int eqxv_copy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
                       int64_t width_bytes, int64_t rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input edge: the reference's own fixture feeds the models with
+ *   transforms.Compose([Resize(s), ToTensor(), Normalize(mean, std)])(PIL image)   (tests/conftest.py:20-41).
+ * Here the uint8 HWC image is what crosses PCIe; ToTensor + Normalize are fused into the layout kernels of the first
+ * layer. x: uint8 [n, h, w, c] (c <= 4); lut: fp32 [c, 256] with lut[ch][v] = (float(v)/255 - mean[ch]) / std[ch]
+ * evaluated by the caller with the reference's fp32 operations (eqxvision_b200/transforms.py), which makes the device
+ * result bit-identical to Normalize(ToTensor(img)) before the one bf16 rounding.
+ * ------------------------------------------------------------------------------------------- */
+/* -> fp32 NCHW [n, c, h, w]: exactly the tensor the reference pipeline hands to the model */
+int eqxv_u8hwc_to_nchw_f32(const uint8_t* x, const float* lut, float* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                           void* stream);
+/* -> bf16 [n, h+2*pad, w+8, 8], the layout eqxv_conv_stem_bf16 reads (same as eqxv_pack_stem_input) */
+int eqxv_u8hwc_pack_stem_input(const uint8_t* x, const float* lut, void* xpad, int32_t n, int32_t h, int32_t w,
+                               int32_t c, int32_t pad, void* stream);
+/* -> bf16 NHWC [n, h, w, 8] (channels zero-padded to 8), same as eqxv_nchw_f32_to_nhwc_bf16(c_pad = 8) */
+int eqxv_u8hwc_to_nhwc_bf16(const uint8_t* x, const float* lut, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                            void* stream);
+/* -> PatchEmbed rows bf16 [n*gh*gw, c*p*p], K order (c, py, px), same as eqxv_patchify_nchw_f32_bf16 */
+int eqxv_u8hwc_patchify_bf16(const uint8_t* x, const float* lut, void* rows, int32_t n, int32_t h, int32_t w,
+                             int32_t c, int32_t p, void* stream);
+/* transforms.Resize on the uint8 image: bilinear, half-pixel centres, no antialiasing (torchvision's tensor path
+ * F.interpolate(mode="bilinear", align_corners=False) in fp32), rounded half-to-even to uint8. [n,h,w,c] -> [n,oh,ow,c] */
+int eqxv_u8hwc_resize_bilinear(const uint8_t* x, uint8_t* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t oh,
+                               int32_t ow, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * C1: all-gather of the fp32 logits over NVLink peer memory: the only collective of the path,
+ * issued when the caller wants the gathered [B, classes] output of a batch sharded over the GPUs of one box
+ * (resnet.py:356 / vit.py:273 produce [B/N, classes] per rank). One process per GPU; each rank owns a "window"
+ * (flags + two gather buffers) allocated with eqxv_p2p_alloc and mapped into every peer through CUDA IPC.
+ * eqxv_allgather_push copies `bytes` of this rank's rows into slot `rank` of the current buffer of EVERY window with
+ * peer stores, publishes a flag per peer and returns (on the stream) once all `world` slices have landed in its own
+ * window. Buffers alternate per launch (epoch parity): read the result from eqxv_p2p_buffer_offset(launches & 1).
+ * Every rank must issue the same sequence of pushes; consumers of a buffer must be stream-ordered before the next push.
+ * ------------------------------------------------------------------------------------------- */
+int eqxv_p2p_window_bytes(int64_t buf_bytes, int64_t* total);
+int eqxv_p2p_alloc(void** ptr, int64_t bytes);   /* cudaMalloc + zero fill (IPC needs a whole allocation) */
+int eqxv_p2p_free(void* ptr);
+int eqxv_ipc_get_handle(const void* ptr, uint8_t handle[64]);
+int eqxv_ipc_open_handle(const uint8_t handle[64], void** ptr);
+int eqxv_ipc_close_handle(void* ptr);
+int eqxv_allgather_push(const void* src, int64_t bytes, void* const* windows /* host array [world] */, int32_t rank,
+                        int32_t world, int64_t slot_bytes, int64_t buf_bytes, void* stream);
+int eqxv_p2p_buffer_offset(int32_t parity, int64_t buf_bytes, int64_t* offset);
 
 /* ---------------------------------------------------------------------------------------------
  * plumbing: streams, CUDA graphs, events (cudaStream_t / cudaGraphExec_t / cudaEvent_t as void*)
@@ -218,8 +270,11 @@ int eqxv_event_record(void* ev, void* stream);
 int eqxv_event_sync(void* ev);
 int eqxv_stream_wait_event(void* stream, void* ev);
 int eqxv_event_elapsed_ms(void* start, void* stop, float* ms);
+/* h2d / d2h name the usual direction; the copy kind is cudaMemcpyDefault (unified addressing), so device sources work */
 int eqxv_memcpy_h2d_async(void* dst, const void* src, int64_t bytes, void* stream);
 int eqxv_memcpy_d2h_async(void* dst, const void* src, int64_t bytes, void* stream);
+/* direction inferred from the pointers (device-to-device copies of results into caller-owned tensors) */
+int eqxv_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
 int eqxv_memset_async(void* dst, int value, int64_t bytes, void* stream);
 
 #ifdef __cplusplus

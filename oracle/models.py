@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import math
+
 import torch
 
 from . import ops as O
@@ -848,6 +850,104 @@ def swin(state_dict, x, arch="swin_t", eps=1e-5):
             t = O.linear_act(t, rw, None)                                      # swin.py:63
     t = O.rnd(O.layer_norm(t, s.take(), s.take(), eps))                        # swin.py:767
     pooled = O.rnd(t.mean(dim=(1, 2)))                                         # avgpool + ravel
+    logits = O.linear_act(pooled, s.take(), s.take(), round_out=False)
+    assert s.done()
+    return logits
+
+
+# ------------------------------------------------------------------------------------------------
+# Swin Transformer v2 (swin.py:369-522 attention, :583-636 block, :68-87 patch merging)
+# ------------------------------------------------------------------------------------------------
+_SWINS_V2 = {
+    "swin_v2_t": (96, [2, 2, 6, 2], [3, 6, 12, 24], 8),
+    "swin_v2_s": (96, [2, 2, 18, 2], [3, 6, 12, 24], 8),
+    "swin_v2_b": (128, [2, 2, 18, 2], [4, 8, 16, 32], 8),
+}
+
+
+def swin_v2_position_bias(coords_table, index, w1, b1, w2, heads, ws):
+    """_ShiftedWindowAttentionV2.get_relative_position_bias (swin.py:494-504): cpb_mlp = [transpose (2,0,1),
+    Linear2d(2,512), relu, Linear2d(512,heads,no bias), identity transpose] maps the (2Wh-1, 2Ww-1, 2) coordinate table
+    to a CHANNEL-FIRST (heads, 2Wh-1, 2Ww-1) array, which `jnp.reshape(..., (-1, heads))` then reads row-major without
+    moving the head axis last (torchvision's cpb_mlp is channels-last, so its view(-1, heads) is a true transpose-free
+    flatten; the reference's is a scramble and is reproduced as such). 16 * sigmoid(table[index]) -> (heads, N, N)."""
+    a, b, _ = coords_table.shape
+    tok = coords_table.reshape(a * b, 2)
+    hid = O.relu(O.linear(tok, w1, b1))
+    out_chw = O.linear(hid, w2).t().contiguous()               # Linear2d returns (heads, A, B)
+    flat = out_chw.reshape(-1, heads)
+    n = ws * ws
+    bias = flat[index.long()].reshape(n, n, -1).permute(2, 0, 1)
+    return 16 * torch.sigmoid(bias)
+
+
+def swin_attention_v2(x, logit_scale, bias, qkv_w, qkv_b, proj_w, proj_b, heads, ws, shift):
+    """_shifted_window_attention with logit_scale (swin.py:146-166): k bias zeroed, cosine attention whose L2 norms run
+    over AXIS 0 of the (num_windows, heads, tokens, d) arrays of ONE sample (the reference's quirk: torchvision
+    normalises over d), times exp(min(logit_scale, log 100)); then bias, shift mask, softmax, PV, proj as in v1.
+    x: (B,H,W,C) channels-last; returns proj(...) in spatial order."""
+    b, h, w, c = x.shape
+    d = c // heads
+    shift = [0 if ws >= h else shift[0], 0 if ws >= w else shift[1]]
+    if sum(shift) > 0:
+        x = torch.roll(x, shifts=(-shift[0], -shift[1]), dims=(1, 2))
+    nw = (h // ws) * (w // ws)
+    n = ws * ws
+    xw = x.reshape(b, h // ws, ws, w // ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(b * nw, n, c)
+    qb = qkv_b.clone()
+    qb[c:2 * c] = 0                                                            # swin.py:146-153
+    qkv = O.linear_act(xw, qkv_w, qb)
+    qkv = qkv.reshape(b, nw, n, 3, heads, d).permute(3, 0, 1, 4, 2, 5)          # (3, B, nW, heads, N, d)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    scale = torch.exp(torch.clamp(logit_scale.reshape(1, 1, heads, 1, 1), max=math.log(100.0)))
+    qn = O.rnd(q / torch.linalg.norm(q, ord=2, dim=1, keepdim=True) * scale)   # dim 1 = the sample's axis 0 (windows)
+    kn = O.rnd(k / torch.linalg.norm(k, ord=2, dim=1, keepdim=True))
+    logits = qn @ kn.transpose(-1, -2) + bias                                  # (B, nW, heads, N, N)
+    if sum(shift) > 0:
+        logits = logits + swin_shift_mask(h, w, ws, shift)[None, :, None]
+    attn = O.softmax(logits, -1)
+    out = (attn @ v).permute(0, 1, 3, 2, 4).reshape(b * nw, n, c)
+    out = O.rnd(out)
+    out = out.reshape(b, h // ws, w // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h, w, c)
+    if sum(shift) > 0:
+        out = torch.roll(out, shifts=(shift[0], shift[1]), dims=(1, 2))
+    return O.linear_act(out, proj_w, proj_b)
+
+
+def swin_v2(state_dict, x, arch="swin_v2_t", eps=1e-5):
+    """SwinTransformer.__call__ with block=_SwinTransformerBlockV2, downsample_layer=_PatchMergingV2 (swin.py:874-946),
+    torchvision swin_v2 key order: per block norm1, attn.{logit_scale, relative_coords_table, relative_position_index,
+    qkv, proj, cpb_mlp.0.{weight,bias}, cpb_mlp.2.weight}, norm2, mlp.{0,3}; per merge reduction.weight, norm."""
+    dim, depths, heads, ws = _SWINS_V2[arch] if isinstance(arch, str) else arch
+    s = Stream(state_dict)
+    pw, pb = s.take(), s.take()
+    t = O.conv_bn_act(x, pw, pb, None, pw.shape[-1], 0)
+    t = t.permute(0, 2, 3, 1)
+    t = O.rnd(O.layer_norm(t, s.take(), s.take(), eps))
+    for i_stage, depth in enumerate(depths):
+        for i_layer in range(depth):
+            n1w, n1b = s.take(), s.take()
+            logit_scale, table, index = s.take(), s.take(), s.take()
+            qw, qb, ow, ob = s.take(), s.take(), s.take(), s.take()
+            c1w, c1b, c2w = s.take(), s.take(), s.take()
+            n2w, n2b = s.take(), s.take()
+            f1w, f1b, f2w, f2b = s.take(), s.take(), s.take(), s.take()
+            shift = [0, 0] if i_layer % 2 == 0 else [ws // 2, ws // 2]
+            bias = swin_v2_position_bias(table.reshape(2 * ws - 1, 2 * ws - 1, 2).float(), index, c1w, c1b, c2w,
+                                         heads[i_stage], ws)
+            y = swin_attention_v2(t, logit_scale.float(), bias, qw, qb, ow, ob, heads[i_stage], ws, shift)
+            t = O.rnd(t + O.rnd(O.layer_norm(y, n1w, n1b, eps)))               # post-norm, swin.py:632-634
+            y = O.linear_act(t, f1w, f1b, act="gelu")
+            y = O.linear_act(y, f2w, f2b)
+            t = O.rnd(t + O.rnd(O.layer_norm(y, n2w, n2b, eps)))               # swin.py:635
+        if i_stage < len(depths) - 1:
+            rw = s.take()
+            nw_, nb_ = s.take(), s.take()
+            t = torch.cat([t[:, 0::2, 0::2], t[:, 1::2, 0::2], t[:, 0::2, 1::2], t[:, 1::2, 1::2]], -1)
+            t = O.linear_act(t, rw, None)                                      # _PatchMergingV2: reduce, THEN norm
+            t = O.rnd(O.layer_norm(t, nw_, nb_, eps))                          # swin.py:84-86
+    t = O.rnd(O.layer_norm(t, s.take(), s.take(), eps))
+    pooled = O.rnd(t.mean(dim=(1, 2)))
     logits = O.linear_act(pooled, s.take(), s.take(), round_out=False)
     assert s.done()
     return logits

@@ -41,6 +41,27 @@ class Array(np.ndarray):
     def T(self):
         return wrap(np.asarray(self).T)
 
+    @property
+    def at(self):
+        """jax's functional index update `x.at[idx].set(v)` (swin.py:148, 424: zeroing the k third of the qkv bias)"""
+        return _At(self)
+
+
+class _At:
+    def __init__(self, arr):
+        self.arr = arr
+
+    def __getitem__(self, idx):
+        arr = self.arr
+
+        class _Ref:
+            def set(self, value):
+                out = np.array(np.asarray(arr), copy=True)
+                out[_unwrap(idx)] = _unwrap(value)
+                return wrap(out, downcast=False)
+
+        return _Ref()
+
 
 def _unwrap(x):
     if isinstance(x, Array):
@@ -271,10 +292,18 @@ def modules():
     image.resize = resize
     lax = _t.ModuleType("jax.lax")
 
-    def _unsupported(*a, **k):
-        raise NotImplementedError("jax.lax is only used by Swin v2 (swin.py:147-166), which the shim does not cover")
+    def scan(f, init, xs, length=None):
+        """jax.lax.scan as a Python loop (swin.py:147-151, 423-427 use it to zero a bias slice element by element)"""
+        carry, ys = init, []
+        for x in (range(length) if xs is None else xs):
+            carry, y = f(carry, x)
+            ys.append(y)
+        return carry, (wrap(np.stack([np.asarray(y) for y in ys])) if ys and ys[0] is not None else None)
 
-    lax.scan = lax.clamp = _unsupported
+    def clamp(min, x, max):   # noqa: A002  (jax.lax.clamp(min, x, max), called with keywords at swin.py:165)
+        return wrap(np.clip(_unwrap(x), _unwrap(min), _unwrap(max)))
+
+    lax.scan, lax.clamp = scan, clamp
     jax = _t.ModuleType("jax")
     jax.numpy, jax.nn, jax.random, jax.image, jax.lax, jax.tree_util = jnp, nn, random, image, lax, tree_util
     jax.vmap = vmap

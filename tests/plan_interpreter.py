@@ -209,6 +209,23 @@ def patch_merge(x, out, **_):
     _store(out, torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1).float())
 
 
+def swin_v2_qk_normalize(qkv, scale_q, n, h, w, heads, head_dim, window, shift, **_):
+    """include/eqxv_b200.h: in place, q and k divided by their L2 norm over the windows of each image (per head,
+    window token and channel; windows of the map rolled by -shift), q times scale_q[head]"""
+    c = heads * head_dim
+    ws = window
+    t = qkv.float().reshape(n, h, w, 3 * c)
+    t = torch.roll(t, shifts=(-shift[0], -shift[1]), dims=(1, 2))
+    t = t.reshape(n, h // ws, ws, w // ws, ws, 3 * c)
+    qk = t[..., : 2 * c]
+    norm = qk.pow(2).sum(dim=(1, 3), keepdim=True).sqrt()
+    mult = torch.ones(2 * c)
+    mult[:c] = scale_q.float().repeat_interleave(head_dim)
+    t = torch.cat([qk / norm * mult, t[..., 2 * c:]], -1).reshape(n, h, w, 3 * c)
+    t = torch.roll(t, shifts=(shift[0], shift[1]), dims=(1, 2))
+    qkv.copy_(t.reshape(n * h * w, 3 * c).to(qkv.dtype))
+
+
 def window_attention(qkv, bias, n, h, w, heads, head_dim, window, shift, scale, out, **_):
     """include/eqxv_b200.h K16: roll by -shift, partition into window x window tiles, softmax(q*scale k^T + bias
     + shift mask) v per (window, head), reverse the partition and the roll. Region labels are built on the rolled map
@@ -239,10 +256,41 @@ def window_attention(qkv, bias, n, h, w, heads, head_dim, window, shift, scale, 
     _store(out, o.reshape(n * h * w, c))
 
 
-IMPLS = {f.__name__: f for f in (nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
+def _u8_norm(x, lut):
+    """Normalize(ToTensor(pixels)) through the table (include/eqxv_b200.h, input edge): fp32 [n, h, w, c]"""
+    c = x.shape[-1]
+    return torch.stack([lut[ch][x[..., ch].long()] for ch in range(c)], -1)
+
+
+def u8_to_nchw_f32(x, lut, out, **_):
+    out.copy_(_u8_norm(x, lut).permute(0, 3, 1, 2))
+
+
+def u8_pack_stem_input(x, lut, pad, out, **_):
+    n, h, w, c = x.shape
+    out.zero_()
+    out[:, pad:pad + h, pad:pad + w, :c].copy_(_u8_norm(x, lut).to(out.dtype))
+
+
+def u8_to_nhwc(x, lut, out, **_):
+    out.zero_()
+    out[..., : x.shape[-1]].copy_(_u8_norm(x, lut).to(out.dtype))
+
+
+def u8_patchify(x, lut, p, out, **_):
+    patchify(_u8_norm(x, lut).permute(0, 3, 1, 2).contiguous(), p, out)
+
+
+def u8_resize_bilinear(x, oh, ow, out, **_):
+    y = F.interpolate(x.permute(0, 3, 1, 2).float(), size=(oh, ow), mode="bilinear", align_corners=False)
+    out.copy_(y.round().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1))
+
+
+IMPLS = {f.__name__: f for f in (u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
+                                 nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
                                  maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d, patchify,
                                  vit_assemble_tokens, attention, attention_probs, gather_rows, resize_bilinear,
-                                 resize_bilinear_to_nchw, patch_merge, window_attention)}
+                                 resize_bilinear_to_nchw, patch_merge, window_attention, swin_v2_qk_normalize)}
 
 
 def run(net, x, method="__call__", fp32_activations=False, **kw):
@@ -270,17 +318,24 @@ def _run(plan_cls, net, x, method, kw):
     import eqxvision_b200 as eb
     from eqxvision_b200 import _engine as E
     from eqxvision_b200 import _trace as T
+    from eqxvision_b200.transforms import ImagesU8
 
-    plan = plan_cls(torch.device("cpu"), x.shape[0], tuple(x.shape[1:]))
+    if isinstance(x, ImagesU8):    # the uint8 input edge: same lowering, the first layout kernel reads pixels
+        plan = plan_cls(torch.device("cpu"), x.shape[0], tuple(x.shape[1:]),
+                        u8={"mean": x.mean, "std": x.std, "raw_hw": tuple(x.pixels.shape[1:3])})
+        shape, x = tuple(x.shape), x.pixels
+    else:
+        plan = plan_cls(torch.device("cpu"), x.shape[0], tuple(x.shape[1:]))
+        shape = tuple(x.shape)
     fn = getattr(type(net), method)
     fn = getattr(fn, "__wrapped__", fn)
     kw.setdefault("key", eb.random.PRNGKey(0))
-    out = fn(net, T.Sym("chw", tuple(x.shape[1:]), T.Input()), **kw)
+    out = fn(net, T.Sym("chw", shape[1:], T.Input()), **kw)
     syms = []
     plan.out_struct = E._flatten_out(out, syms)
     for s in syms:
         plan.add_output(s)
-    plan.x_in.copy_(x)
+    plan.x_host_target.copy_(x)
     for step, kwargs in plan.steps:
         impl = IMPLS.get(step.__name__)
         if impl is None:

@@ -371,8 +371,10 @@ def test_unsupported_shapes_fail_at_trace_time_not_at_launch():
         trace(eb.tree_inference(models.googlenet(aux_logits=True), True), (3, 224, 224))
     with pytest.raises(NotImplementedError, match="even split"):        # AlexNet at 127 px: 3x3 -> 6x6
         trace(eb.tree_inference(models.alexnet(), True), (3, 127, 127))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="multiple of the window"):     # Swin-V2: window 8 does not tile 224/4 = 56... 7
         trace(eb.tree_inference(models.swin_v2_t(), True), (3, 224, 224))
+    out = trace(eb.tree_inference(models.swin_v2_t(), True), (3, 256, 256))
+    assert out.shape == (1000,)
     with pytest.raises(NotImplementedError):
         nn.AvgPool2d(3, 2, use_ceil=True)
 
@@ -389,3 +391,30 @@ def test_googlenet_loads_torchvision_checkpoint_with_aux_heads(tmp_path):
     assert net.aux_logits is False and net.aux1 is not None
     assert torch.equal(net.fc.weight, tv.fc.weight) and torch.equal(net.aux2.fc2.weight, tv.aux2.fc2.weight)
     assert torch.equal(net.inception5b.branch4.layers[1].conv.weight, tv.inception5b.branch4[1].conv.weight)
+
+
+def test_wide_layers_split_into_column_chunks_at_lowering():
+    """the GEMM stages the shift of all its output channels in 20 KB of shared memory (csrc/igemm.cu), so
+    one launch covers at most ~5000 of them. ConvNeXt-Large's MLP (4 x 1536 = 6144, convnext.py:40-48) and the widest
+    RegNet stage must therefore lower to several launches over column slices - and give the same numbers."""
+    import plan_interpreter as PI
+    from eqxvision_b200 import _engine as E
+    from eqxvision_b200.models.classification.convnext import _CNBlockConfig
+
+    assert E._n_chunks(4096) == [(0, 4096)] and E._n_chunks(6144) == [(0, 3072), (3072, 6144)]
+    assert E._n_chunks(7392) == [(0, 3696), (3696, 7392)] and all(a % 8 == 0 for a, _ in E._n_chunks(7392))
+    # one ConvNeXt-Large stage-4 block (dim 1536 -> MLP width 6144) on a 2x2 map
+    net = eb.tree_inference(models.ConvNeXt([_CNBlockConfig(1536, None, 2)], num_classes=16), True)
+    x = torch.randn(1, 3, 8, 8, generator=torch.Generator().manual_seed(0))
+    got, plan = PI.run(net, x, fp32_activations=True)
+    wide = [kw for fn, kw in plan.steps if fn.__name__ == "gemm" and kw["wgt"].shape[0] == 3072]
+    assert len(wide) == 4 and all(kw["wgt"].shape[0] <= E.MAX_COUT_PER_LAUNCH
+                                  for fn, kw in plan.steps if fn.__name__ in ("gemm", "conv2d"))
+    saved = E.MAX_COUT_PER_LAUNCH
+    try:
+        E.MAX_COUT_PER_LAUNCH = 1 << 20
+        ref, plan1 = PI.run(net, x, fp32_activations=True)
+    finally:
+        E.MAX_COUT_PER_LAUNCH = saved
+    assert len(plan1.steps) == len(plan.steps) - 2
+    assert torch.equal(got, ref)

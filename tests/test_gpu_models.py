@@ -165,6 +165,50 @@ def test_swin_t_parity(device, save_checkpoint):
     assert rel(got, ref) < 3e-2, ("vs fp32 oracle", rel(got, ref))
 
 
+def test_swin_v2_parity(device, tmp_path):
+    """Swin-V2 (swin.py:369-522, 583-636) with the reference's quirks (axis-0 cosine normalisation, cpb_mlp reshape);
+    the oracle is pinned against the reference's own code in tests/test_refshim.py. Three stages at 256 px (every
+    stage has >= 4 windows per image, see tests/test_plan_lowering.py::swin_v2_three_stages for why)."""
+    import sys
+
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_plan_lowering import swin_v2_three_stages
+
+    net, sd, cfg = swin_v2_three_stages(tmp_path, num_classes=1000)
+    x = ck.synthetic_images(3, h=256, w=256, seed=2)
+    got = eb.vmap(net, axis_name="batch")(x, key=keys(3))
+    assert got.shape == (3, 1000) and got.dtype == torch.float32
+    ref = om.swin_v2(sd, x, cfg)
+    with O.emulate_bf16():
+        emu = om.swin_v2(sd, x, cfg)
+    print("swin_v2 (3 stages) rel-L2 vs emulation / fp32:", rel(got, emu), rel(got, ref))
+    assert rel(got, emu) < 2e-2, ("vs bf16-emulating oracle", rel(got, emu))
+    assert rel(got, ref) < 5e-2, ("vs fp32 oracle", rel(got, ref))
+
+
+def test_swin_v2_t_full_model_runs(device, save_checkpoint):
+    """the exported swin_v2_t constructor end to end. Its last stage (one window per image) turns the reference's
+    normalisation into sign(q), so only a loose bound against the oracle is meaningful (see above)."""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+
+    sd = ck.swin_model("swin_v2_t", seed=1).state_dict()
+    with pytest.warns(UserWarning):
+        net = build("swin_v2_t", sd, save_checkpoint)
+    x = ck.synthetic_images(2, h=256, w=256, seed=2)
+    got = eb.vmap(net, axis_name="batch")(x, key=keys(2))
+    assert got.shape == (2, 1000) and torch.isfinite(got).all()
+    r = rel(got, om.swin_v2(sd, x, "swin_v2_t"))
+    print("swin_v2_t full model rel-L2 vs fp32 oracle:", r)
+    assert r < 0.5, r
+
+
 def test_vit_base_parity(device, save_checkpoint):
     import eqxvision_b200 as eb
     from oracle import checkpoints as ck

@@ -135,6 +135,55 @@ def test_oracle_reproduces_the_reference_swin(tmp_path):
 
 
 @needs_reference
+def test_oracle_reproduces_the_reference_swin_v2(tmp_path):
+    """Swin-V2 through the reference's own swin.py (swin.py:369-522, 583-636, 874-896): cosine attention normalised
+    along axis 0, the cpb_mlp reshape, post-norm blocks, _PatchMergingV2; torchvision swin_v2_t checkpoint loaded
+    positionally (logit_scale, relative_coords_table, relative_position_index, qkv, proj, cpb_mlp)."""
+    sd = ck.swin_model("swin_v2_t", seed=1).state_dict()
+    path = str(tmp_path / "s2.pth")
+    torch.save(sd, path)
+    x = ck.synthetic_images(1, h=256, w=256, seed=2)
+    got = run_reference(lambda ev, p: ev.models.swin_v2_t(torch_weights=p), x, path)
+    ref = om.swin_v2(sd, x, "swin_v2_t")
+    assert got.shape == (1, 1000)
+    # In the last stage the 8x8 map is ONE window, so the reference's axis-0 norm runs over a single element and
+    # q / ||q|| is sign(q): discontinuous, which turns fp32 summation-order noise (numpy vs torch matmuls) into
+    # differences of a few 1e-4. The two-stage model below, where every norm runs over >= 4 windows, holds 1e-4.
+    assert torch.allclose(got, ref, atol=2e-3, rtol=2e-3), (got - ref).abs().max()
+    assert ((got - ref).norm() / ref.norm()).item() < 1e-3
+    # and it is NOT torchvision's Swin-V2 (the quirks are real): the stock model disagrees on the same checkpoint
+    tv = ck.swin_model("swin_v2_t", seed=1)
+    with torch.no_grad():
+        assert (tv(x) - ref).abs().max() > 1e-2
+
+
+@needs_reference
+def test_oracle_reproduces_the_reference_swin_v2_two_stages_at_1e_4(tmp_path):
+    """the same code path with >= 4 windows per image in every stage (no sign() degeneracy): the reference's own
+    tolerance atol=1e-4"""
+    from torchvision.models.swin_transformer import PatchMergingV2, SwinTransformerBlockV2
+
+    cfg = dict(patch_size=[4, 4], embed_dim=96, depths=[2, 2], num_heads=[3, 6], window_size=[8, 8],
+               stochastic_depth_prob=0.0, num_classes=10, block=SwinTransformerBlockV2, downsample_layer=PatchMergingV2)
+    sd = ck.swin_model(cfg, seed=2).state_dict()
+    path = str(tmp_path / "s2s.pth")
+    torch.save(sd, path)
+    x = ck.synthetic_images(2, h=128, w=128, seed=3)
+
+    def build(ev, p):
+        sw = ev.models.classification.swin
+        net = ev.models.SwinTransformer(patch_size=[4, 4], embed_dim=96, depths=[2, 2], num_heads=[3, 6],
+                                        window_size=[8, 8], stochastic_depth_prob=0.0, num_classes=10,
+                                        block=sw._SwinTransformerBlockV2, downsample_layer=sw._PatchMergingV2)
+        return ev.utils.load_torch_weights(net, torch_weights=p)
+
+    got = run_reference(build, x, path)
+    ref = om.swin_v2(sd, x, (96, [2, 2], [3, 6], 8))
+    assert got.shape == (2, 10)
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()
+
+
+@needs_reference
 def test_oracle_reproduces_the_reference_segmentation(tmp_path):
     x = ck.synthetic_images(1, h=64, w=64, seed=2)
     sd = ck.torchvision_model("deeplabv3_resnet50", seed=1, calib_hw=64, aux_loss=True).state_dict()

@@ -143,7 +143,10 @@ def swin_model(arch: str = "swin_t", seed: int = 0, tanh_gelu: bool = True) -> t
     import torchvision
 
     torch.manual_seed(seed)
-    m = getattr(torchvision.models, arch)(weights=None).eval()
+    if isinstance(arch, dict):   # a custom (small) configuration: kwargs of torchvision's SwinTransformer
+        m = torchvision.models.swin_transformer.SwinTransformer(**arch).eval()
+    else:
+        m = getattr(torchvision.models, arch)(weights=None).eval()
     g = torch.Generator().manual_seed(seed + 1000)
     with torch.no_grad():
         for n, p in m.named_parameters():
@@ -153,6 +156,8 @@ def swin_model(arch: str = "swin_t", seed: int = 0, tanh_gelu: bool = True) -> t
                 p.copy_(0.1 * torch.randn(p.shape, generator=g))
             elif "relative_position_bias_table" in n:
                 p.copy_(0.5 * torch.randn(p.shape, generator=g))
+            elif n.endswith("logit_scale"):     # Swin-V2: some heads above the log(100) clamp, some below
+                p.copy_(p + 2.5 * torch.rand(p.shape, generator=g))
     if tanh_gelu:
         for mod in m.modules():
             if isinstance(mod, torchvision.ops.misc.MLP):
