@@ -18,10 +18,11 @@ A "step" is one forward pass over one batch: one CUDA-graph replay (56 kernel la
             torch's stream (which the public call orders its results on). Headline: uint8 HWC pixels in
             (`transforms.images_u8`: ToTensor + Normalize of the reference's fixture fused on the device);
             `e2e_f32` is the same with the reference's fp32 NCHW batch (4x the bytes over PCIe).
-  roofline: tensor-bound models: the tcgen05 implicit-GEMM family (all conv/linear launches of a step), algorithmic
-            FLOPs (8.178 GFLOP/img for R50) over that family's share of the graph-replay step (share
-            from per-launch event pairs of an eager replay; eager launches lose the PDL overlap, so their SUM exceeds
-            the step and only the share is used), against the measured sustained cuBLAS bf16 peak; HBM-bound models
+  roofline: tensor-bound models: algorithmic FLOPs (8.178 GFLOP/img for R50) over the WHOLE graph-replay
+            step (the tcgen05 implicit-GEMM family is the dominant kernel and is charged with the rest of the step too),
+            against the measured sustained cuBLAS bf16 peak; `by_kernel_ms` splits the step by C entry (shares from
+            per-launch event pairs of an eager replay, scaled to the step: eager launches lose the PDL overlap, so their
+            SUM exceeds the step and only the shares are used); HBM-bound models
             (EfficientNet-B4): whole-step algorithmic bytes against the measured copy bandwidth;
             `traffic` = ncu DRAM bytes of the step (profiles/traffic.json, regenerated per round)
   cpu_baseline: the CPU oracle (torch fp32 restatement of the reference, kind "port") on a bounded sample, timed on
@@ -131,6 +132,31 @@ class ClockSampler:
         # median over the samples taken under load (idle samples sit at the max clock as well on this part)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """pin this rank's threads to the host NUMA node its GPU hangs off, BEFORE any pinned buffer is allocated (first
+    touch places the pages): eight ranks pulling pinned pages through one remote node halved the per-GPU H2D rate in
+    round 1. Best effort; returns a short description for the JSON line."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = "0000:" + bus.split(":", 1)[1]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"numa: rank bound to node {node} ({len(allowed)} cpus)"
+        return f"numa: node {node} has no allowed cpus"
+    except Exception as e:  # noqa: BLE001
+        return f"numa: not bound ({type(e).__name__})"
 
 
 def synthetic_state_dict(name: str):
@@ -309,6 +335,10 @@ def cpu_port(name, sd, batch, iters):
     """bounded CPU sample; returns (img/s, cores, sample)"""
     import torch
 
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))   # undo the NUMA binding of the GPU arm: all host cores
+    except OSError:
+        pass
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     fn = oracle_forward(name, sd, batch)
     with torch.no_grad():
@@ -384,6 +414,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -420,15 +451,17 @@ def main():
         """the model's binding roofline for the dominant kernel family"""
         nb = PER_GPU_BATCH[nm]
         if MODELS[nm]["bound"] == "tensor":
-            k_ms = step_ms * mm["igemm_share"]
-            tf = FLOP_PER_IMG[nm] * nb / k_ms / 1e9
-            r = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM family (all conv/linear launches of one step: "
-                                              "igemm_kernel, pair_kernel, halo_kernel, stem_kernel)",
+            # the WHOLE graph-replay step is the denominator (the conv/linear family is the dominant kernel and the rest
+            # of the step is charged to it): a per-kernel time cannot exceed the step it is part of
+            tf = FLOP_PER_IMG[nm] * nb / step_ms / 1e9
+            r = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM family (igemm_kernel, pair_kernel, halo_kernel, "
+                                              "stem_kernel) charged with the whole step",
                  "achieved": round(tf, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                  "frac": round(tf / peaks["tflops_sustained"], 4), "traffic": None,
                  "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
-                 "launches": mm["igemm_launches"], "kernel_ms_per_step": round(k_ms, 4),
-                 "kernel_share_of_step": round(mm["igemm_share"], 4), "flop_per_image": FLOP_PER_IMG[nm]}
+                 "launches": mm["igemm_launches"], "kernel_ms_per_step": round(step_ms, 4),
+                 "family_share_of_eager_launch_time": round(mm["igemm_share"], 4),
+                 "flop_per_image": FLOP_PER_IMG[nm]}
         else:
             gbs = BYTES_PER_IMG[nm] * nb / step_ms / 1e6
             what = ("whole step (batch 1: every filter is read once, the classifier GEMMs are weight-bandwidth bound)"
@@ -509,6 +542,7 @@ def main():
         "eager_sum_ms": round(m["eager_sum_ms"], 4),
         "activation_bytes": m["act_bytes"],
         "clocks": clocks,
+        "host": numa,
         "secondary": secondary,
     }
     if not args.no_cpu_baseline:

@@ -86,6 +86,8 @@ class Plan:
         self.memo: Dict[int, Buf] = {}
         self.keep: List[Any] = []             # keeps traced exprs alive (ids are memo keys)
         self.u8 = u8
+        self._arena_candidates: Dict[int, torch.Tensor] = {}
+        self.arena = None
         self.stream: Optional[int] = None     # lane stream (created by build_plan on a CUDA device)
         self.done = None                      # event: the lane's last graph launch has finished
         self.out_ready = None                 # event: the lane's last outputs have been copied out
@@ -120,7 +122,113 @@ class Plan:
         pitch = _round8(c)
         t = torch.zeros((rows, pitch), dtype=dtype, device=self.device)
         self.act_bytes += t.numel() * t.element_size()
+        if pitch == c:
+            self.arena_ok(t)   # every column is rewritten by the producer on each replay: the memory can be shared
         return Buf(t, c, self.n, tuple(geom))
+
+    def arena_ok(self, t: torch.Tensor) -> torch.Tensor:
+        """mark a buffer as fully overwritten by its producer(s) on every replay (no zero-filled pad columns or concat
+        slots to preserve): `plan_memory` may then place it in the shared arena"""
+        self._arena_candidates[t.untyped_storage().data_ptr()] = t
+        return t
+
+    def arena_pin(self, t: torch.Tensor) -> None:
+        """keep a buffer out of the arena after all (several producers fill disjoint slices over time)"""
+        self._arena_candidates.pop(t.untyped_storage().data_ptr(), None)
+
+    def plan_memory(self, align: int = 1024) -> None:
+        """Liveness-based activation arena. Every shareable buffer lives from the first step that touches it to the last
+        (outputs: to the end of the replay); buffers whose lifetimes do not overlap share addresses inside ONE
+        allocation (first-fit over a free list, in order of first use). Steps, outputs and views are then re-pointed
+        into the arena and the individual allocations are released. Ordering between consecutive launches is what makes
+        this safe: every kernel of the library waits for its predecessor's completion (griddepcontrol.wait) before it
+        touches activation memory. ResNet-50 at batch 256: 5.4 GiB -> ~1 GiB."""
+        cands = self._arena_candidates
+        if not cands or os.environ.get("EQXV_NO_ARENA") == "1":
+            return
+        first: Dict[int, int] = {}
+        last: Dict[int, int] = {}
+
+        def tensors_of(kw):
+            for v in kw.values():
+                if isinstance(v, torch.Tensor):
+                    yield v
+
+        for i, (_, kw) in enumerate(self.steps):
+            for t in tensors_of(kw):
+                p_ = t.untyped_storage().data_ptr()
+                if p_ in cands:
+                    first.setdefault(p_, i)
+                    last[p_] = i
+        end = len(self.steps)
+        for o, _ in self.outputs:
+            p_ = o.untyped_storage().data_ptr()
+            if p_ in cands and p_ in first:
+                last[p_] = end
+        order = sorted(first, key=lambda p_: (first[p_], -cands[p_].untyped_storage().nbytes()))
+        live: List[Tuple[int, int, int]] = []      # (last step, offset, size) of placed buffers still alive
+        free: List[Tuple[int, int]] = []           # (offset, size) holes below `top`
+        top = peak = 0
+        offset: Dict[int, int] = {}
+        for p_ in order:
+            now = first[p_]
+            still = []
+            for l_, off, size in live:
+                if l_ < now:
+                    free.append((off, size))
+                else:
+                    still.append((l_, off, size))
+            live = still
+            free.sort()
+            merged: List[Tuple[int, int]] = []
+            for off, size in free:
+                if merged and merged[-1][0] + merged[-1][1] == off:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + size)
+                else:
+                    merged.append((off, size))
+            if merged and merged[-1][0] + merged[-1][1] == top:   # a hole at the top shrinks the arena front
+                top = merged.pop()[0]
+            free = merged
+            need = -(-cands[p_].untyped_storage().nbytes() // align) * align
+            best = None
+            for j, (off, size) in enumerate(free):
+                if size >= need and (best is None or size < free[best][1]):
+                    best = j
+            if best is not None:
+                off, size = free.pop(best)
+                if size > need:
+                    free.append((off + need, size - need))
+            else:
+                off = top
+                top += need
+            offset[p_] = off
+            peak = max(peak, off + need)
+            live.append((last[p_], off, need))
+        total = peak
+        arena = torch.empty(max(total, align), dtype=torch.uint8, device=self.device)
+        ast = arena.untyped_storage()
+
+        def remap(t):
+            if not isinstance(t, torch.Tensor):
+                return t
+            off = offset.get(t.untyped_storage().data_ptr())
+            if off is None:
+                return t
+            es = t.element_size()
+            return torch.empty(0, dtype=t.dtype, device=t.device).set_(ast, off // es + t.storage_offset(), t.shape,
+                                                                       t.stride())
+
+        self.steps = [(fn, {k: remap(v) for k, v in kw.items()}) for fn, kw in self.steps]
+        self.outputs = [(remap(o), shp) for o, shp in self.outputs]
+        shared = sum(cands[p_].untyped_storage().nbytes() for p_ in offset)
+        self.act_bytes_unshared = self.act_bytes
+        self.act_bytes = self.act_bytes - shared + total
+        self.arena = arena
+        self._arena_candidates = {}
+        self.memo.clear()
+        self._input_nhwc.clear()
+        self._input_stem.clear()
+        self._concat_groups.clear()
 
     def const(self, t: torch.Tensor) -> torch.Tensor:
         d = t.to(self.device).contiguous()
@@ -228,7 +336,9 @@ class Plan:
                 # first-layer conv on the raw image (resnet.py:243-251, vgg.py:137, efficientnet.py:327):
                 # padded NHWC8 image + one GEMM K-block per filter row (eqxv_conv_stem_bf16)
                 if ph not in self._input_stem:
-                    xp = torch.zeros((self.n, h + 2 * ph, wd + 8, 8), dtype=BF16, device=self.device)
+                    # the pack kernels write the zero border too: the whole buffer is rewritten every replay
+                    xp = self.arena_ok(torch.zeros((self.n, h + 2 * ph, wd + 8, 8), dtype=BF16, device=self.device))
+                    self.act_bytes += xp.numel() * 2
                     if self.u8 is not None:
                         self.step(ops.u8_pack_stem_input, x=self.x_in, lut=self.lut, pad=ph, out=xp)
                     else:
@@ -370,7 +480,7 @@ class Plan:
         w_f, b_f = _pack.fold_bn(ce.weight, ce.bias, ce.bn)
         act, _ = self._epilogue(ce)
         k = cin * p * p
-        rows = torch.empty((self.n * np_, k), dtype=BF16, device=self.device)
+        rows = self.arena_ok(torch.empty((self.n * np_, k), dtype=BF16, device=self.device))
         self.act_bytes += rows.numel() * 2
         if self.u8 is not None:
             self.step(ops.u8_patchify, x=self.x_in, lut=self.lut, p=p, out=rows)
@@ -809,6 +919,7 @@ def build_plan(module, method: str, batch: int, in_shape: Tuple[int, ...], args=
         plan.add_output(s)
     plan.memo.clear()
     plan.keep.clear()
+    plan.plan_memory()
     return _arm_lane(plan, ctx.stream if stream is None else stream, use_graph)
 
 

@@ -293,7 +293,7 @@ IMPLS = {f.__name__: f for f in (u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc,
                                  resize_bilinear_to_nchw, patch_merge, window_attention, swin_v2_qk_normalize)}
 
 
-def run(net, x, method="__call__", fp32_activations=False, **kw):
+def run(net, x, method="__call__", fp32_activations=False, arena=False, **kw):
     """lower `net` for the batch `x` on a CPU-device plan and replay the recorded steps with the torch stand-ins.
     `fp32_activations`: allocate every activation buffer in fp32 (filters stay bf16 as packed), which removes the
     bf16 rounding noise from the comparison and leaves a sharp check of the lowering itself."""
@@ -309,12 +309,12 @@ def run(net, x, method="__call__", fp32_activations=False, **kw):
     if fp32_activations:
         E.BF16 = torch.float32
     try:
-        return _run(_F32Plan if fp32_activations else E.Plan, net, x, method, kw)
+        return _run(_F32Plan if fp32_activations else E.Plan, net, x, method, kw, arena)
     finally:
         E.BF16 = saved
 
 
-def _run(plan_cls, net, x, method, kw):
+def _run(plan_cls, net, x, method, kw, arena=False):
     import eqxvision_b200 as eb
     from eqxvision_b200 import _engine as E
     from eqxvision_b200 import _trace as T
@@ -335,6 +335,10 @@ def _run(plan_cls, net, x, method, kw):
     plan.out_struct = E._flatten_out(out, syms)
     for s in syms:
         plan.add_output(s)
+    if arena:   # the liveness-based activation arena of the engine (Plan.plan_memory), poisoned first
+        plan.plan_memory()
+        if plan.arena is not None:
+            plan.arena.fill_(0x7f)
     plan.x_host_target.copy_(x)
     for step, kwargs in plan.steps:
         impl = IMPLS.get(step.__name__)

@@ -192,3 +192,40 @@ def test_fcn_lowering_matches_oracle(tmp_path):
     assert rel(out, out_r) < 2e-3 and rel(aux, aux_r) < 2e-3
     with pytest.raises(ValueError):                      # fcn.py:92-101: aux head needs exactly two taps
         eb.models.fcn(intermediate_layers=lambda m: [m.layer4], aux_in_channels=1024)
+
+
+@pytest.mark.parametrize("arch,hw,shrink", [("resnet50", 64, 0.45), ("efficientnet_b0", 64, 0.6), ("densenet121", 64, 1.0),
+                                            ("mobilenet_v3_small", 64, 0.8), ("shufflenet_v2_x1_0", 64, 1.0)])
+def test_activation_arena_gives_the_same_bits_in_less_memory(tmp_path, arch, hw, shrink):
+    """Plan.plan_memory: buffers with disjoint lifetimes share one arena. The replay on a POISONED arena
+    must give exactly the bits of the replay on private buffers (a buffer reused too early, or one that relied on its
+    zero fill, would show), and the footprint must drop."""
+    sd = ck.torchvision_state_dict(arch, seed=1)
+    path = str(tmp_path / "m.pth")
+    torch.save(sd, path)
+    net = eb.tree_inference(getattr(eb.models, arch)(torch_weights=path), True)
+    x = ck.synthetic_images(2, h=hw, w=hw, seed=2)
+    ref, plan0 = PI.run(net, x)
+    got, plan1 = PI.run(net, x, arena=True)
+    assert torch.equal(got, ref)
+    assert plan1.act_bytes <= shrink * plan0.act_bytes, (plan1.act_bytes, plan0.act_bytes)
+
+
+def test_activation_arena_vit_and_segmentation(tmp_path):
+    sd = ck.vit_state_dict(embed_dim=192, depth=3, heads=3, num_classes=10, seed=3)
+    path = str(tmp_path / "v.pth")
+    torch.save(sd, path)
+    net = eb.tree_inference(eb.models.vit_tiny(depth=3, num_classes=10, torch_weights=path), True)
+    x = ck.synthetic_images(2, seed=4)
+    ref, plan0 = PI.run(net, x)
+    got, plan1 = PI.run(net, x, arena=True)
+    assert torch.equal(got, ref) and plan1.act_bytes < 0.5 * plan0.act_bytes
+    tv = ck.torchvision_model("deeplabv3_resnet50", seed=1, calib_hw=64, aux_loss=True)
+    path = str(tmp_path / "d.pth")
+    torch.save(tv.state_dict(), path)
+    net = eb.tree_inference(eb.models.deeplabv3(intermediate_layers=lambda m: [m.layer3, m.layer4], aux_in_channels=1024,
+                                                torch_weights=path), True)
+    x = ck.synthetic_images(1, h=64, w=64, seed=2)
+    (aux0, out0), plan0 = PI.run(net, x)
+    (aux1, out1), plan1 = PI.run(net, x, arena=True)
+    assert torch.equal(aux0, aux1) and torch.equal(out0, out1) and plan1.act_bytes < plan0.act_bytes
