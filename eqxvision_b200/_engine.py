@@ -87,6 +87,7 @@ class Plan:
         self.keep: List[Any] = []             # keeps traced exprs alive (ids are memo keys)
         self.u8 = u8
         self._arena_candidates: Dict[int, torch.Tensor] = {}
+        self._pool_requests: Dict[int, Buf] = {}   # id of a depthwise Conv expr -> pooled Buf: squeeze fused into that conv
         self.arena = None
         self.stream: Optional[int] = None     # lane stream (created by build_plan on a CUDA device)
         self.done = None                      # event: the lane's last graph launch has finished
@@ -414,9 +415,28 @@ class Plan:
         bias_d = self.const(bias)
         ho, wo = sym.shape[1:]
         out = dst if dst is not None else self.alloc(self.n * ho * wo, c, (ho, wo))
+        if id(e) in self._pool_requests and self._dw_pool_fusable(e, act):
+            # SqueezeExcitation right behind the depthwise conv (efficientnet.py:138-160): the squeeze (squeeze.py:52)
+            # comes out of the same kernel, no pass over the expanded tensor just to average it
+            pooled = self._pool_requests.pop(id(e))
+            need = ops.dwconv_pool_workspace_bytes(self.n, h, wd, cp, k, sh, ph) if self.device.type == "cuda" else 0
+            ws = torch.zeros(max(need, 16), dtype=torch.uint8, device=self.device) if need else None
+            self.step(ops.dwconv_pool, x=xb.map(h, wd, cp), wgt=wp, bias=bias_d, k=k, stride=sh, pad=ph, act=act,
+                      out=out.map(ho, wo, cp), pooled=pooled.rows(cp), workspace=ws)
+            return out
         self.step(ops.dwconv, x=xb.map(h, wd, cp), wgt=wp, bias=bias_d, k=k, stride=sh, pad=ph, dil=dh, act=act,
                   out=out.map(ho, wo, cp))
         return out
+
+    @staticmethod
+    def _dw_pool_fusable(e: "T.Conv", act: Optional[int] = None) -> bool:
+        k = e.weight.shape[2]
+        ok = (e.groups == e.weight.shape[0] and e.weight.shape[1] == 1 and e.groups > 1 and e.res is None
+              and k == e.weight.shape[3] and k in (3, 5) and e.stride in ((1, 1), (2, 2)) and e.dilation == (1, 1)
+              and e.padding[0] == e.padding[1] and e.weight.shape[0] % 8 == 0)
+        if act is not None:
+            ok = ok and act in (_lib.ACT_NONE, _lib.ACT_RELU, _lib.ACT_SILU, _lib.ACT_HARDSWISH)
+        return ok
 
     # ---- linear ------------------------------------------------------------------------------
     def _emit_Linear(self, sym, e: T.Linear, out_f32=False):
@@ -510,8 +530,17 @@ class Plan:
         return out
 
     def _emit_AdaptiveAvgPool(self, sym, e: T.AdaptiveAvgPool):
-        xb = self.emit(e.x)
         c, h, w = e.x.shape
+        xe = e.x.expr
+        if (e.oh, e.ow) == (1, 1) and isinstance(xe, T.Conv) and id(xe) not in self.memo and self._dw_pool_fusable(xe):
+            pooled = self.alloc(self.n, c, (1, 1))
+            self._pool_requests[id(xe)] = pooled  # (emission recurses: several requests can be open at once)
+            self.emit(e.x)
+            if self._pool_requests.pop(id(xe), None) is None:   # taken: the depthwise kernel writes the squeeze as well
+                return pooled
+            self.step(ops.adaptive_avgpool, x=self.memo[id(xe)].map(h, w), oh=1, ow=1, out=pooled.map(1, 1))
+            return pooled
+        xb = self.emit(e.x)
         out = self.alloc(self.n * e.oh * e.ow, c, (e.oh, e.ow))
         self.step(ops.adaptive_avgpool, x=xb.map(h, w), oh=e.oh, ow=e.ow, out=out.map(e.oh, e.ow))
         return out
@@ -622,7 +651,8 @@ class Plan:
 
     def _emit_ChannelScale(self, sym, e: T.ChannelScale):
         """x * s with one gate per (image, channel): the SqueezeExcitation output (squeeze.py:61)"""
-        xb, sb = self.emit(e.x), self.emit(e.s)
+        sb = self.emit(e.s)      # the gate first: its squeeze may ride in the kernel that produces x (depthwise + pool)
+        xb = self.emit(e.x)
         c, h, w = e.x.shape
         out = self._like(xb, sym)
         self.step(ops.eltwise, x=xb.rows(), gate=sb.rows(xb.cpad), rows_per_image=h * w, out=out.rows())

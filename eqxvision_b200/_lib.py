@@ -61,6 +61,9 @@ SIGNATURES = {
     "eqxv_vit_assemble_tokens_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "eqxv_gather_rows_bf16": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
     "eqxv_dwconv_bn_act_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_dwconv_pool_workspace_bytes": [_i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_i64)],
+    "eqxv_dwconv_bn_act_pool_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                     _i32, _i32, _i32, _vp],
     "eqxv_dwconv_tile_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_eltwise_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -117,7 +120,7 @@ _LAUNCHING = {
     "eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32", "eqxv_resize_bilinear_nhwc_bf16", "eqxv_copy2d_async",
     "eqxv_window_attention_bf16", "eqxv_patch_merge_bf16",
     "eqxv_u8hwc_to_nchw_f32", "eqxv_u8hwc_pack_stem_input", "eqxv_u8hwc_to_nhwc_bf16", "eqxv_u8hwc_patchify_bf16",
-    "eqxv_u8hwc_resize_bilinear", "eqxv_allgather_push", "eqxv_swin_v2_qk_normalize_bf16",
+    "eqxv_u8hwc_resize_bilinear", "eqxv_allgather_push", "eqxv_swin_v2_qk_normalize_bf16", "eqxv_dwconv_bn_act_pool_bf16",
 }
 
 

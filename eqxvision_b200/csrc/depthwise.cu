@@ -10,6 +10,12 @@
 
 namespace eqxv {
 
+// dwconv_img.cu
+bool dwconv_img_supported(int k, int stride, int dil, int act, int c, int x_pitch, int y_pitch, int w_pitch);
+int dwconv_img_launch(const void* x, const float* wgt, const float* bias, void* y, void* pooled, void* workspace,
+                      long long workspace_bytes, int n, int h, int w, int c, int k, int stride, int pad, int x_pitch,
+                      int y_pitch, int w_pitch, int pool_pitch, int act, cudaStream_t stream);
+
 constexpr int kDwThreads = 256;
 
 // Grid-stride loop over `total` work items with a 32-bit index whenever it fits: the index decomposition
@@ -50,7 +56,12 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 __device__ __forceinline__ float act_rt(float v, int act) {
   switch (act) {
     case EQXV_ACT_RELU: return fmaxf(v, 0.f);
-    case EQXV_ACT_SILU: return __fdividef(v, 1.f + __expf(-v));
+    case EQXV_ACT_SILU: {   // h + h * tanh(h), h = x / 2: one special-function op (see igemm.cu apply_act)
+      const float h = 0.5f * v;
+      float th;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+      return fmaf(h, th, h);
+    }
     case EQXV_ACT_GELU_TANH: {
       const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
       float th;
@@ -58,7 +69,11 @@ __device__ __forceinline__ float act_rt(float v, int act) {
       return 0.5f * v * (1.f + th);
     }
     case EQXV_ACT_HARDSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    case EQXV_ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-v));
+    case EQXV_ACT_SIGMOID: {
+      float th;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * v));
+      return fmaf(0.5f, th, 0.5f);
+    }
     case EQXV_ACT_HARDSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
     case EQXV_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
     default: return v;
@@ -547,6 +562,14 @@ static int dwconv_impl(const void* x, const float* wgt, const float* bias, void*
   if (force_tile) {
     set_error("dwconv: the shared-memory stencil kernel needs k in {3,5}, dilation 1, 16-byte aligned operands");
     return EQXV_ERR_UNSUPPORTED;
+  }
+  {
+    // production path: packed-FMA per-image kernel (dwconv_img.cu); EQXV_DWIMG=0 falls back to the strip kernels (A/B)
+    static const bool use_img = !(getenv("EQXV_DWIMG") && getenv("EQXV_DWIMG")[0] == '0');
+    const bool aligned = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)wgt | (uintptr_t)bias) & 15) == 0) && n <= 65535;
+    if (use_img && aligned && dwconv_img_supported(k, stride, dil, act, c, x_pitch, y_pitch, w_pitch))
+      return dwconv_img_launch(x, wgt, bias, y, nullptr, nullptr, 0, n, h, w, c, k, stride, pad, x_pitch, y_pitch,
+                               w_pitch, 0, act, st);
   }
 #define EQXV_DWS(K, S, TW)                                                                          \
   EQXV_CUDA(launch_kernel(dwconv_strip_kernel<K, S, TW>,                                            \

@@ -222,6 +222,31 @@ def dwconv(x, wgt, bias, *, k, stride=1, pad=0, dil=1, act=0, out=None, tile=Fal
     return out
 
 
+def dwconv_pool_workspace_bytes(n, h, w, c, k, stride, pad) -> int:
+    b = C.c_int64()
+    call("eqxv_dwconv_pool_workspace_bytes", n, h, w, c, k, stride, pad, C.byref(b))
+    return b.value
+
+
+def dwconv_pool(x, wgt, bias, *, k, stride=1, pad=0, act=0, out=None, pooled=None, workspace=None, stream=0):
+    """depthwise conv + BN + act AND the SE squeeze: pooled[n, c] = mean over the output map (eqxv_dwconv_bn_act_pool_bf16).
+    `workspace`: zero-initialised uint8 tensor of dwconv_pool_workspace_bytes(...) bytes (left zeroed by the kernel)."""
+    _check_cuda(x, wgt, bias, out, pooled, workspace)
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, k, stride, pad, 1), conv_out_size(w, k, stride, pad, 1)
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    if pooled is None:
+        pooled = torch.empty((n, c), dtype=BF16, device=x.device)
+    need = dwconv_pool_workspace_bytes(n, h, w, c, k, stride, pad)
+    if workspace is None and need:
+        workspace = torch.zeros(need, dtype=torch.uint8, device=x.device)
+    call("eqxv_dwconv_bn_act_pool_bf16", ptr(x), ptr(wgt), ptr(bias), ptr(out), ptr(pooled), ptr(workspace),
+         0 if workspace is None else workspace.numel(), n, h, w, c, k, stride, pad, x.stride(2), out.stride(2),
+         wgt.stride(0), pooled.stride(0), act, stream)
+    return out, pooled
+
+
 def eltwise(x, *, scale=None, shift=None, other=None, gate=None, rows_per_image=1, act=0, out=None, stream=0):
     """rows x c: out = act(x*scale + shift + other) * gate[row // rows_per_image]"""
     _check_cuda(x, scale, shift, other, gate, out)

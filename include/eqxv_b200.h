@@ -165,6 +165,19 @@ int eqxv_dwconv_bn_act_bf16(const void* x, const float* wgt, const float* bias, 
                             int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad,
                             int32_t dil, int32_t x_pitch, int32_t y_pitch, int32_t w_pitch, int32_t act,
                             void* stream);
+/* K3 + K11: the same depthwise convolution with the SqueezeExcitation squeeze fused in (layers/squeeze.py:52 `avgpool(x)`
+ * on the output of the depthwise ConvNormActivation, efficientnet.py:138-160, mobilenetv3.py:88-112): besides y the kernel
+ * writes pooled[n, c] = mean over the output map of the bf16-rounded activation, so no separate pass re-reads the widest
+ * tensor of the block. One thread block works on ONE image; per-block partial sums go to `workspace` and the last block of
+ * an image (integer ticket) adds them in a fixed order: bitwise reproducible, independent of the batch composition.
+ * k in {3,5}, stride 1/2, dilation 1, act in {none, relu, silu, hard-swish}. `workspace`: zero-initialised once by the
+ * caller (the kernel leaves it zeroed), eqxv_dwconv_pool_workspace_bytes() bytes (0 = not needed). */
+int eqxv_dwconv_pool_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad,
+                                     int64_t* bytes);
+int eqxv_dwconv_bn_act_pool_bf16(const void* x, const float* wgt, const float* bias, void* y, void* pooled,
+                                 void* workspace, int64_t workspace_bytes, int32_t n, int32_t h, int32_t w, int32_t c,
+                                 int32_t k, int32_t stride, int32_t pad, int32_t x_pitch, int32_t y_pitch,
+                                 int32_t w_pitch, int32_t pool_pitch, int32_t act, void* stream);
 /* Same contract, forced through the shared-memory stencil kernel (TMA-staged halo tile of a 64-channel block,
  * sliding accumulator window; k in {3,5}, dilation 1). eqxv_dwconv_bn_act_bf16 picks it when EQXV_DWTILE=1. */
 int eqxv_dwconv_tile_bf16(const void* x, const float* wgt, const float* bias, void* y, int32_t n, int32_t h,

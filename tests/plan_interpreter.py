@@ -123,6 +123,13 @@ def dwconv(x, wgt, bias, k, stride, pad, dil, act, out, **_):
     _store(out, _epilogue(y, bias, act, None, False))
 
 
+def dwconv_pool(x, wgt, bias, k, stride, pad, act, out, pooled, workspace=None, **_):
+    """include/eqxv_b200.h K3 + K11: the depthwise conv and, from the same kernel, the mean of its (stored) output"""
+    dwconv(x, wgt, bias, k, stride, pad, 1, act, out)
+    c = x.shape[-1]
+    pooled[..., :c].copy_(out[..., :c].float().mean((1, 2)).to(pooled.dtype))
+
+
 def maxpool2d(x, k, stride, pad, out, ceil_mode=False, **_):
     assert x.shape[-1] % 8 == 0 and 2 * pad <= k, "maxpool: channels must be a multiple of 8, 2*pad <= k"
     _check_operand(x, "maxpool x")
@@ -286,7 +293,7 @@ def u8_resize_bilinear(x, oh, ow, out, **_):
     out.copy_(y.round().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1))
 
 
-IMPLS = {f.__name__: f for f in (u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
+IMPLS = {f.__name__: f for f in (dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
                                  nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
                                  maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d, patchify,
                                  vit_assemble_tokens, attention, attention_probs, gather_rows, resize_bilinear,

@@ -412,3 +412,36 @@ def test_patch_merge_is_bit_exact(device):
     got = ops.patch_merge(x.to(device)).cpu()
     ref = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)  # swin.py:26-31
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("c,hw,k,stride,act,n", [(48, 112, 3, 1, 2, 3), (144, 112, 3, 2, 2, 2), (336, 28, 5, 1, 2, 3),
+                                                 (192, 56, 5, 2, 4, 2), (960, 14, 5, 1, 4, 5), (1632, 7, 5, 1, 2, 4),
+                                                 (2688, 7, 3, 1, 2, 3), (72, 17, 3, 1, 1, 2), (40, 9, 5, 2, 0, 3),
+                                                 (8, 5, 3, 1, 2, 1), (672, 14, 5, 2, 2, 130)])
+def test_depthwise_with_fused_squeeze(device, c, hw, k, stride, act, n):
+    """eqxv_dwconv_bn_act_pool_bf16: the depthwise output AND the SqueezeExcitation squeeze (squeeze.py:52) from one kernel.
+    y against torch's grouped conv; pooled against the mean of the kernel's own stored output (that is what the next layer
+    reads); bitwise reproducible and independent of where an image sits in the batch."""
+    from eqxvision_b200 import _pack, ops
+
+    pad = (k - 1) // 2
+    x = rb(device, n, hw, hw, c, seed=1)
+    g = torch.Generator().manual_seed(2)
+    wt = torch.randn(c, 1, k, k, generator=g) * (k * k) ** -0.5
+    bias = torch.randn(c, generator=g)
+    wp, bd = _pack.pack_depthwise_weight(wt, c).to(device), bias.to(device)
+    y, pooled = ops.dwconv_pool(x, wp, bd, k=k, stride=stride, pad=pad, act=act)
+    ref = ACTS[act](F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(device), bd, stride=stride, padding=pad, groups=c))
+    assert rel_l2(y, ref.permute(0, 2, 3, 1)) < TOL_BF16
+    want = y.float().mean((1, 2))
+    assert pooled.shape == (n, c)
+    assert (pooled.float() - want).abs().max().item() <= 2 ** -7 * want.abs().max().item() + 1e-6
+    assert rel_l2(pooled, want) < 3e-3
+    y2, pooled2 = ops.dwconv_pool(x, wp, bd, k=k, stride=stride, pad=pad, act=act)
+    assert torch.equal(y, y2) and torch.equal(pooled, pooled2)
+    if n > 1:
+        perm = torch.randperm(n, generator=torch.Generator().manual_seed(3)).to(device)
+        y3, pooled3 = ops.dwconv_pool(x[perm].contiguous(), wp, bd, k=k, stride=stride, pad=pad, act=act)
+        assert torch.equal(y3, y[perm]) and torch.equal(pooled3, pooled[perm])
+    # and the plain entry (no squeeze) takes the same kernel: identical y
+    assert torch.equal(ops.dwconv(x, wp, bd, k=k, stride=stride, pad=pad, act=act), y)
