@@ -39,10 +39,11 @@ def _round8(v: int) -> int:
 MAX_COUT_PER_LAUNCH = 4096
 
 
-def _n_chunks(cout: int):
-    if cout <= MAX_COUT_PER_LAUNCH:
+def _n_chunks(cout: int, limit: Optional[int] = None):
+    limit = MAX_COUT_PER_LAUNCH if limit is None else limit
+    if cout <= limit:
         return [(0, cout)]
-    k = -(-cout // MAX_COUT_PER_LAUNCH)
+    k = -(-cout // limit)
     per = _round8(-(-cout // k))
     return [(n0, min(cout, n0 + per)) for n0 in range(0, cout, per)]
 
@@ -87,6 +88,8 @@ class Plan:
         self.keep: List[Any] = []             # keeps traced exprs alive (ids are memo keys)
         self.u8 = u8
         self._arena_candidates: Dict[int, torch.Tensor] = {}
+        self._ln_producers: Dict[int, int] = {}     # id of a Linear expr -> index of its plain residual-GEMM step
+        self._ln_stats: Dict[int, torch.Tensor] = {}  # id of that expr -> row statistics its patched step writes
         self._pool_requests: Dict[int, Buf] = {}   # id of a depthwise Conv expr -> pooled Buf: squeeze fused into that conv
         self.arena = None
         self.stream: Optional[int] = None     # lane stream (created by build_plan on a CUDA device)
@@ -439,11 +442,53 @@ class Plan:
         return ok
 
     # ---- linear ------------------------------------------------------------------------------
+    # The LayerNorm between two GEMMs (vit.py:149,154) is folded into them: the producer's epilogue emits row statistics,
+    # the consumer applies mean / rstd to its accumulators (include/eqxv_b200.h, K5 + K7). EQXV_NO_LN_FOLD=1: A/B switch.
+    LN_FOLD = os.environ.get("EQXV_NO_LN_FOLD") != "1"
+    LN_MAX_COUT = 3328    # the consumer stages bias AND filter column sums (28 KB area: csrc/igemm.cu)
+
+    def _emit_linear_ln(self, sym, e: T.Linear, ln: "T.LayerNormE", act: int) -> Optional[Buf]:
+        """Linear(LayerNorm(x)) with x produced by a residual GEMM of this plan: no LayerNorm kernel, no LayerNorm
+        output in HBM. Returns None when the pattern does not apply (the caller lowers the two ops separately)."""
+        out_f, in_f = e.weight.shape
+        pkey = id(ln.x.expr)
+        xb = self.emit(ln.x)
+        idx = self._ln_producers.get(pkey)
+        if idx is None or xb.pitch != in_f or in_f % 8 != 0:
+            return None
+        rows = xb.t.shape[0]
+        stats = self._ln_stats.get(pkey)
+        if stats is None:
+            stats = self.arena_ok(torch.zeros((rows, (in_f + 63) // 64, 2), dtype=torch.float32, device=self.device))
+            self.act_bytes += stats.numel() * 4
+            self._ln_stats[pkey] = stats
+            fn, kw = self.steps[idx]
+            assert fn is ops.gemm
+            self.steps[idx] = (ops.gemm_rowstats, dict(kw, stats=stats))
+        gamma, beta = ln.weight.detach().double(), ln.bias.detach().double()
+        w64 = e.weight.detach().double()
+        wp = _pack.pack_linear_weight((w64 * gamma[None, :]).float(), in_f)       # [out_f, in_f] bf16, gamma folded
+        wsum = wp.float().sum(1)                                                  # of the ROUNDED filter the MMA sees
+        bias = (w64 @ beta + (e.bias.detach().double().reshape(-1) if e.bias is not None else 0.0)).float()
+        wp_d, wsum_d, bias_d = self.const(wp), self.const(wsum), self.const(bias)
+        geom = (sym.shape[0],) if sym.kind == "tokens" else ()
+        out = self.alloc(rows, out_f, geom)
+        o2d = out.rows()
+        for n0, n1 in _n_chunks(out_f, self.LN_MAX_COUT):
+            self.step(ops.gemm_ln, a=xb.rows(in_f), wgt=wp_d[n0:n1], bias=bias_d[n0:n1], wsum=wsum_d[n0:n1], stats=stats,
+                      eps=float(ln.eps), act=act, out=o2d if (n0, n1) == (0, out_f) else o2d[:, n0:n1])
+        return out
+
     def _emit_Linear(self, sym, e: T.Linear, out_f32=False):
         out_f, in_f = e.weight.shape
         act, res_after = self._epilogue(e)
         w = e.weight.detach().float()
         xsym = e.x
+        if (self.LN_FOLD and isinstance(xsym.expr, T.LayerNormE) and not out_f32 and e.res is None
+                and act in (_lib.ACT_NONE, _lib.ACT_GELU_TANH) and id(xsym.expr) not in self.memo):
+            folded = self._emit_linear_ln(sym, e, xsym.expr, act)
+            if folded is not None:
+                return folded
         if isinstance(xsym.expr, T.Ravel) and xsym.expr.x.shape[1] * xsym.expr.x.shape[2] > 1:
             # flatten of a (C,H,W) map is in C,H,W order (jnp.ravel, vgg.py:116); the buffer is H,W,C
             src = xsym.expr.x
@@ -466,10 +511,14 @@ class Plan:
         geom = (sym.shape[0],) if sym.kind == "tokens" else ()
         out = self.alloc(rows, out_f, geom, dtype=torch.float32 if out_f32 else BF16)
         o2d, r2d = out.rows(out_f if out_f32 else None), None if res is None else res.rows()
-        for n0, n1 in _n_chunks(out_f):
+        chunks = _n_chunks(out_f)
+        for n0, n1 in chunks:
             self.step(ops.gemm, a=a, wgt=wp[n0:n1], bias=None if bias_d is None else bias_d[n0:n1], act=act,
                       residual=None if r2d is None else r2d[:, n0:n1], res_after_act=res_after,
                       out=o2d[:, n0:n1] if (n0, n1) != (0, out_f) else o2d, out_f32=out_f32)
+        if (len(chunks) == 1 and res is not None and act == _lib.ACT_NONE and not res_after and not out_f32
+                and bias_d is not None and out.pitch == out_f):
+            self._ln_producers[id(sym.expr)] = len(self.steps) - 1   # may later emit row statistics for a LayerNorm
         return out
 
     # ---- shape-only nodes --------------------------------------------------------------------

@@ -47,6 +47,8 @@ SIGNATURES = {
     "eqxv_init": [C.c_int],
     "eqxv_conv2d_igemm_bf16": [C.POINTER(ConvDesc), _vp],
     "eqxv_gemm_bias_act_res_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_gemm_res_rowstats_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp],
+    "eqxv_gemm_ln_act_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _i64, _i64, _i32, _i32, _i32, _vp],
     "eqxv_conv_stem_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_pack_stem_input": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -120,7 +122,8 @@ _LAUNCHING = {
     "eqxv_resize_bilinear_nhwc_bf16_to_nchw_f32", "eqxv_resize_bilinear_nhwc_bf16", "eqxv_copy2d_async",
     "eqxv_window_attention_bf16", "eqxv_patch_merge_bf16",
     "eqxv_u8hwc_to_nchw_f32", "eqxv_u8hwc_pack_stem_input", "eqxv_u8hwc_to_nhwc_bf16", "eqxv_u8hwc_patchify_bf16",
-    "eqxv_u8hwc_resize_bilinear", "eqxv_allgather_push", "eqxv_swin_v2_qk_normalize_bf16", "eqxv_dwconv_bn_act_pool_bf16",
+    "eqxv_u8hwc_resize_bilinear", "eqxv_allgather_push", "eqxv_swin_v2_qk_normalize_bf16", "eqxv_dwconv_bn_act_pool_bf16", "eqxv_gemm_res_rowstats_bf16",
+    "eqxv_gemm_ln_act_bf16",
 }
 
 

@@ -50,6 +50,15 @@ struct alignas(64) IgemmParams {
   int epi_sub;      // epilogue warps per TMEM lane quadrant (1 or 2): blockDim = 64 + 128 * epi_sub
   // shared-memory carve-up (byte offsets from the 1024-aligned base)
   int off_out, off_res, off_bias, off_bars;
+  // LayerNorm folded into the GEMMs on either side of it (flat GEMMs only, kLN template parameter):
+  //   kLN == 2 (producer, y = a w^T + bias + residual): besides y, (sum, sum of squares) of every stored row over each
+  //             64-column chunk go to ln_stats[row][chunk]
+  //   kLN == 1 (consumer of LayerNorm(x) with gamma folded into w and beta into bias): y = act(rstd[row] * (acc -
+  //             mean[row] * wsum[col]) + bias[col]); mean / rstd from the producer's ln_stats
+  float2* ln_stats;
+  const float* ln_wsum;
+  int ln_slots, ln_rows, off_wsum;
+  float ln_inv_d, ln_eps;
   // first-layer (halo) kernel only
   int h_stride, h_planes, h_px, h_rows, h_plane_pitch, h_stage_bytes, h_ksteps, h_off_b;
   const void* h_src;  // padded NHWC8 image [n, in_h, in_w, 8]
@@ -185,11 +194,56 @@ __device__ __forceinline__ uint4 epilogue8(const float* v, const float* bias_sme
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// LayerNorm-consumer variant (kLN == 1): x = rstd * acc + (bias - mean * rstd * wsum), activation, round.
+// All arithmetic on packed fp32 pairs (fma/mul.f32x2): the fc1 epilogue (LayerNorm + tanh-GELU on 128 x 256 outputs per
+// tile and CTA, four warps) is as long as its mainloop, so its instruction count is what bounds the layer.
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+template <int kAct>
+__device__ __forceinline__ uint4 epilogue8_ln(const float* v, const float* bias_smem, const float* wsum_smem,
+                                              const float rstd, const float nmr) {
+  const float4 b0 = *reinterpret_cast<const float4*>(bias_smem), b1 = *reinterpret_cast<const float4*>(bias_smem + 4);
+  const float4 s0 = *reinterpret_cast<const float4*>(wsum_smem), s1 = *reinterpret_cast<const float4*>(wsum_smem + 4);
+  const uint64_t bb[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y), f2_pack(b1.z, b1.w)};
+  const uint64_t ss[4] = {f2_pack(s0.x, s0.y), f2_pack(s0.z, s0.w), f2_pack(s1.x, s1.y), f2_pack(s1.z, s1.w)};
+  const uint64_t rstd2 = f2_pack(rstd, rstd), nmr2 = f2_pack(nmr, nmr);
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint64_t x = f2_fma(f2_pack(v[2 * q], v[2 * q + 1]), rstd2, f2_fma(nmr2, ss[q], bb[q]));
+    if constexpr (kAct == EQXV_ACT_GELU_TANH) {
+      // 0.5 x (1 + tanh(0.79788 x (1 + 0.044715 x^2)))  =  h + h * tanh(u),  h = x / 2
+      const uint64_t inner = f2_fma(f2_mul(x, x), f2_pack(0.044715f, 0.044715f), f2_pack(1.f, 1.f));
+      const uint64_t u = f2_mul(f2_mul(x, f2_pack(0.7978845608028654f, 0.7978845608028654f)), inner);
+      float u0, u1, t0, t1;
+      f2_unpack(u, u0, u1);
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+      const uint64_t h = f2_mul(x, f2_pack(0.5f, 0.5f));
+      x = f2_fma(h, f2_pack(t0, t1), h);
+    } else if constexpr (kAct != EQXV_ACT_NONE) {
+      float x0, x1;
+      f2_unpack(x, x0, x1);
+      x = f2_pack(apply_act<kAct>(x0), apply_act<kAct>(x1));
+    }
+    o[q] = f2_to_bf2(x);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // ============================== epilogue, four warps (epi_sub == 1) ==============================
 // One warp per TMEM lane quadrant, tile-major loop, double-buffered staging slab per warp. Used where the
 // K loop hides the epilogue (first layer, halo kernel, deep-K residual GEMMs): it is measurably leaner per
 // chunk than the generic two-warps-per-quadrant loop below (first layer 183 vs 205 us on B200).
-template <bool kOutF32, int kAct, int kRes, bool kPair = false>
+template <bool kOutF32, int kAct, int kRes, bool kPair = false, int kLN = 0>
 __device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
                                                const uint32_t tmem_base, const int warp, const int lane) {
   const int S = p.stages;
@@ -240,6 +294,25 @@ __device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const ui
     uint32_t acc_phase = 0;
     for (int tile = t_first; tile < p.num_tiles; tile += t_stride) {
       const TileCoord t = decode_tile<kPair>(p, tile);
+      // LayerNorm folding (flat GEMMs: the tile is 128 consecutive rows, this thread owns row t.w0 + so + lane)
+      // (the phantom m-tile of an odd pair decodes to n0 = 1, w0 = 0: its rows must not be mistaken for rows 0..127)
+      const int ln_row = (t.n0 == 0 && t.h0 == 0) ? t.w0 + so + lane : p.ln_rows;
+      float ln_rstd = 1.f, ln_nmr = 0.f;
+      if constexpr (kLN == 1) {
+        // statistics of this row, written by the producing GEMM's epilogue: loaded before the accumulator wait
+        float sum = 0.f, sq = 0.f;
+        if (ln_row < p.ln_rows) {
+          const float2* st = p.ln_stats + (long long)ln_row * p.ln_slots;
+          for (int i = 0; i < p.ln_slots; ++i) {
+            const float2 a = __ldg(st + i);
+            sum += a.x;
+            sq += a.y;
+          }
+        }
+        const float mean = sum * p.ln_inv_d;
+        ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_d - mean * mean, 0.f) + p.ln_eps);
+        ln_nmr = -mean * ln_rstd;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.acc_stride);
@@ -278,7 +351,33 @@ __device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const ui
           for (int j = 0; j < 8; ++j) {
             uint4 rv = make_uint4(0u, 0u, 0u, 0u);
             if constexpr (has_res) rv = *reinterpret_cast<const uint4*>(res_row + sw128_off(lane, j));
-            packed[j] = epilogue8<kAct, kRes>(&v[j * 8], bias_c + j * 8, rv);
+            if constexpr (kLN == 1) {
+              const float* wsum_c = reinterpret_cast<const float*>(gbase + p.off_wsum) + t.ncol0 + c * CH;
+              packed[j] = epilogue8_ln<kAct>(&v[j * 8], bias_c + j * 8, wsum_c + j * 8, ln_rstd, ln_nmr);
+            } else {
+              packed[j] = epilogue8<kAct, kRes>(&v[j * 8], bias_c + j * 8, rv);
+            }
+          }
+          if constexpr (kLN == 2) {
+            // row statistics of what is STORED (the bf16-rounded values the LayerNorm would have read back)
+            uint64_t sum2 = 0ull, sq2 = 0ull;   // packed pairs: (even columns, odd columns)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t wv[4] = {packed[j].x, packed[j].y, packed[j].z, packed[j].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint64_t f = bf2_to_f2(wv[q]);
+                sum2 = f2_add(sum2, f);
+                sq2 = f2_fma(f, f, sq2);
+              }
+            }
+            float s_lo, s_hi, q_lo, q_hi;
+            f2_unpack(sum2, s_lo, s_hi);
+            f2_unpack(sq2, q_lo, q_hi);
+            const float sum = s_lo + s_hi, sq = q_lo + q_hi;
+            const int col0 = t.ncol0 + c * CH;
+            if (ln_row < p.ln_rows && col0 < p.cout)
+              p.ln_stats[(long long)ln_row * p.ln_slots + (col0 >> 6)] = make_float2(sum, sq);
           }
           if (lane == 0) tma_store_wait_read<1>();  // this warp's store that last used out[buf] is done
           __syncwarp();
@@ -325,11 +424,11 @@ __device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const ui
 // pipe, bounded every shallow-K layer. Two warps per sub-partition hide each other's latencies.
 // Every warp owns its slab privately: its own staging buffer, its own TMA stores / residual loads
 // (issued by an elected lane) and its own mbarriers; there is no CTA-wide barrier on this path.
-template <bool kOutF32, int kAct, int kRes, bool kPair = false>
+template <bool kOutF32, int kAct, int kRes, bool kPair = false, int kLN = 0>
 __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
                                                const uint32_t tmem_base, const int warp, const int lane) {
-  if (p.epi_sub == 1) {   // CTA-uniform
-    epilogue_warps_x4<kOutF32, kAct, kRes, kPair>(p, base, gbase, tmem_base, warp, lane);
+  if (p.epi_sub == 1 || kLN != 0) {   // CTA-uniform (LayerNorm folding exists in the four-warp epilogue only)
+    epilogue_warps_x4<kOutF32, kAct, kRes, kPair, kLN>(p, base, gbase, tmem_base, warp, lane);
     return;
   }
   const int S = p.stages;
@@ -472,7 +571,7 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
 // kRes: 0 = no residual, 1 = act(acc + bias + res), 2 = act(acc + bias) + res. Compile-time so that the
 // unrolled epilogue is straight-line code (a runtime flag doubled its instruction count and made the
 // epilogue warps issue-bound on the HBM-bound layers: profiles/r01_layers_v4).
-template <bool kOutF32, int kAct, int kRes>
+template <bool kOutF32, int kAct, int kRes, int kLN = 0>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -515,6 +614,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const int ncols_pad = p.n_tiles * p.block_n + 64;
     for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x)
       sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
+    if (kLN == 1) {   // column sums of the gamma-folded filter, next to the bias
+      float* sw = reinterpret_cast<float*>(gbase + p.off_wsum);
+      for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x) sw[i] = i < p.cout ? __ldg(p.ln_wsum + i) : 0.f;
+    }
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -621,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
     __syncwarp();
   } else {
-    epilogue_warps<kOutF32, kAct, kRes>(p, base, gbase, tmem_base, warp, lane);
+    epilogue_warps<kOutF32, kAct, kRes, false, kLN>(p, base, gbase, tmem_base, warp, lane);
   }
 
   // ---- teardown ----
@@ -645,7 +748,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 // Protocol: full[s] lives in the leader (both producers' TMA bytes are credited to it), the MMA
 // commits are multicast to empty[s] / tfull[a] of both CTAs, both epilogues arrive on the leader's
 // tempty[a]. The epilogue itself is the single-CTA one (each CTA drains its own 128 TMEM lanes).
-template <int kAct, int kRes>
+template <int kAct, int kRes, int kLN = 0>
 __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -688,6 +791,10 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
     const int ncols_pad = p.n_tiles * p.block_n + 64;
     for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x)
       sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
+    if (kLN == 1) {   // column sums of the gamma-folded filter, next to the bias
+      float* sw = reinterpret_cast<float*>(gbase + p.off_wsum);
+      for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x) sw[i] = i < p.cout ? __ldg(p.ln_wsum + i) : 0.f;
+    }
   }
   if (warp == 1) {
     tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
@@ -773,7 +880,7 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
     }
     __syncwarp();
   } else {
-    epilogue_warps<false, kAct, kRes, true>(p, base, gbase, tmem_base, warp, lane);
+    epilogue_warps<false, kAct, kRes, true, kLN>(p, base, gbase, tmem_base, warp, lane);
   }
 
   // ---- teardown: neither CTA may leave while its peer can still touch its smem / TMEM / barriers ----
@@ -786,10 +893,10 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
   }
 }
 
-template <int kAct, int kRes>
+template <int kAct, int kRes, int kLN = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     pair_kernel(const __grid_constant__ IgemmParams p) {
-  pair_kernel_body<kAct, kRes>(p);
+  pair_kernel_body<kAct, kRes, kLN>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1248,6 +1355,12 @@ struct IgemmProblem {
   int kchunks, cin_pack;
   int act, flags;
   int grouped;
+  // LayerNorm folding (flat GEMMs): 0 none, 1 consumer, 2 producer (see IgemmParams)
+  int ln_mode;
+  float2* ln_stats;
+  const float* ln_wsum;
+  int ln_slots;
+  float ln_inv_d, ln_eps;
 };
 
 static void choose_tile(int n, int ho, int wo, int& tw, int& th, int& tn) {
@@ -1353,6 +1466,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
     if (bn >= 64 && bn <= 256 && bn % 64 == 0 && bn < q.cout && !(pair && bn >= 2 * q.cout)) block_n = bn;
   }
   if (q.grouped) block_n = 64;   // one n-tile = one 64-channel block of the block-diagonal filter
+  if (q.ln_mode == 2 && block_n % 64 != 0) block_n = std::min(256, ceil_div(block_n, 64) * 64);   // 64-column stat chunks
   p.grouped = q.grouped;
   p.block_n = block_n;
   p.acc_stride = ceil_div(block_n, 32) * 32;
@@ -1379,14 +1493,27 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
 
   // shared memory carve-up
   const int stage_bytes = kABytes + (pair ? block_n * 64 : block_n * 128);
-  const int bias_bytes = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
-  EQXV_CHECK_ARG(bias_bytes <= 20 * 1024, "igemm: cout %d too large for the bias staging area", q.cout);
+  const int bias_one = ceil_div((p.n_tiles * block_n + 64) * 4, 1024) * 1024;
+  const int bias_bytes = bias_one * (q.ln_mode == 1 ? 2 : 1);   // consumer: + the filter's column sums
+  EQXV_CHECK_ARG(bias_bytes <= (q.ln_mode == 1 ? 28 : 20) * 1024, "igemm: cout %d too large for the bias staging area",
+                 q.cout);
+  p.ln_stats = q.ln_stats, p.ln_wsum = q.ln_wsum, p.ln_slots = q.ln_slots, p.ln_rows = q.out_w;
+  p.ln_inv_d = q.ln_inv_d, p.ln_eps = q.ln_eps;
+  if (q.ln_mode != 0) {
+    EQXV_CHECK_ARG(q.tw == 128 && q.th == 1 && q.tn == 1 && q.kh == 1 && q.kw == 1 && !out_f32 && !q.grouped,
+                   "igemm: LayerNorm folding needs a flat bf16 GEMM");
+    EQXV_CHECK_ARG(q.ln_mode == 1 ? (q.res == nullptr && (q.act == EQXV_ACT_NONE || q.act == EQXV_ACT_GELU_TANH))
+                                  : (q.res != nullptr && q.act == EQXV_ACT_NONE &&
+                                     !(q.flags & EQXV_FLAG_RES_AFTER_ACT)),
+                   "igemm: LayerNorm folding: consumer = no residual, act none/gelu; producer = residual, no act");
+  }
   // epilogue warps per TMEM lane quadrant; every warp owns 2 residual slabs, the 8 staging slabs are shared out
   const int forced_sub = env_int("EQXV_EPI_SUB");
   // Two warps per quadrant where the epilogue bounds the tile (shallow K, <= 4 K blocks: ResNet c3 / downsample
   // layers went from 78 % to 99 % of their HBM roofline); one where the K loop hides it: the leaner tile-major
   // loop wins there by 2-7 % with or without a residual (tools/sweep_igemm.py, profiles/r01_sweep_igemm_v18.txt).
   p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : (kblocks <= 4 ? 2 : 1);
+  if (q.ln_mode != 0) p.epi_sub = 1;   // the folding lives in the four-warp epilogue
   const int fixed = 2 * kStageBuf + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
   int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
   stages = std::min(stages, 8);
@@ -1395,6 +1522,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   p.off_out = stages * stage_bytes;
   p.off_res = p.off_out + 2 * kStageBuf;
   p.off_bias = p.off_res + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0);
+  p.off_wsum = p.off_bias + bias_one;
   p.off_bars = p.off_bias + bias_bytes;
   const int smem_bytes = p.off_bars + 512 + 1024;
 
@@ -1441,15 +1569,28 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   const int res_mode = q.res ? (p.res_after_act ? 2 : 1) : 0;
   if (pair) {
     const int clusters = std::min(p.num_tiles, device_sm_count() / 2);
-    EQXV_CUDA(launch_kernel(pair_table(q.act, res_mode), dim3(2 * clusters), dim3(64 + 128 * p.epi_sub), (size_t)(smem_bytes), stream, p));
+    KernelFn pfn = pair_table(q.act, res_mode);
+    if (q.ln_mode == 1) pfn = q.act == EQXV_ACT_NONE ? pair_kernel<0, 0, 1> : pair_kernel<EQXV_ACT_GELU_TANH, 0, 1>;
+    if (q.ln_mode == 2) pfn = pair_kernel<0, 1, 2>;
+    EQXV_CUDA(launch_kernel(pfn, dim3(2 * clusters), dim3(64 + 128 * p.epi_sub), (size_t)(smem_bytes), stream, p));
     EQXV_CUDA(cudaGetLastError());
     return EQXV_OK;
   }
   const int grid = std::min(p.num_tiles, device_sm_count());
-  const KernelFn fn = out_f32 ? kernel_table().f32[q.act] : kernel_table().bf16[res_mode][q.act];
+  KernelFn fn = out_f32 ? kernel_table().f32[q.act] : kernel_table().bf16[res_mode][q.act];
+  if (q.ln_mode == 1)
+    fn = q.act == EQXV_ACT_NONE ? igemm_kernel<false, 0, 0, 1> : igemm_kernel<false, EQXV_ACT_GELU_TANH, 0, 1>;
+  if (q.ln_mode == 2) fn = igemm_kernel<false, 0, 1, 2>;
   EQXV_CUDA(launch_kernel(fn, dim3(grid), dim3(64 + 128 * p.epi_sub), (size_t)(smem_bytes), stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
+}
+
+static KernelFn ln_kernels(int i) {
+  static const KernelFn t[6] = {pair_kernel<0, 0, 1>, pair_kernel<EQXV_ACT_GELU_TANH, 0, 1>, pair_kernel<0, 1, 2>,
+                                igemm_kernel<false, 0, 0, 1>, igemm_kernel<false, EQXV_ACT_GELU_TANH, 0, 1>,
+                                igemm_kernel<false, 0, 1, 2>};
+  return t[i];
 }
 
 // halo kernel instantiations: the activations that follow large-map 3x3 convolutions
@@ -1468,6 +1609,8 @@ static StemFn stem_table(int act) {
 }
 
 int igemm_init() {
+  for (int i = 0; i < 6; ++i)
+    EQXV_CUDA(cudaFuncSetAttribute(ln_kernels(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < kNumActs; ++a)
     EQXV_CUDA(cudaFuncSetAttribute(stem_table(a), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < 3; ++a)
@@ -1618,7 +1761,18 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
 
 using namespace eqxv;
 
-extern "C" int eqxv_conv2d_igemm_bf16(const eqxv_conv_desc* d, void* stream) {
+struct LnFold {
+  int mode;   // 1 consumer, 2 producer
+  float2* stats;
+  const float* wsum;
+  int slots;
+  float inv_d, eps;
+};
+static int conv_impl(const eqxv_conv_desc* d, const LnFold* ln, void* stream);
+
+extern "C" int eqxv_conv2d_igemm_bf16(const eqxv_conv_desc* d, void* stream) { return conv_impl(d, nullptr, stream); }
+
+static int conv_impl(const eqxv_conv_desc* d, const LnFold* ln, void* stream) {
   EQXV_CHECK_ARG(d != nullptr, "conv: null descriptor");
   EQXV_CHECK_ARG(d->x && d->wgt && d->y, "conv: null tensor pointer");
   EQXV_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0, "conv: bad shape");
@@ -1643,9 +1797,13 @@ extern "C" int eqxv_conv2d_igemm_bf16(const eqxv_conv_desc* d, void* stream) {
   if (grouped)
     EQXV_CHECK_ARG(d->cin == d->cout && d->cin % 64 == 0 && !f32,
                    "conv: GROUPED_BLOCK64 needs cin == cout, a multiple of 64, bf16 output");
-  if (!grouped && halo_eligible(d, ho, wo)) return launch_halo(d, ho, wo, (cudaStream_t)stream);
+  if (!grouped && !ln && halo_eligible(d, ho, wo)) return launch_halo(d, ho, wo, (cudaStream_t)stream);
 
   IgemmProblem q{};
+  if (ln) {
+    q.ln_mode = ln->mode, q.ln_stats = ln->stats, q.ln_wsum = ln->wsum, q.ln_slots = ln->slots;
+    q.ln_inv_d = ln->inv_d, q.ln_eps = ln->eps;
+  }
   q.grouped = grouped ? 1 : 0;
   q.wgt = d->wgt;
   q.ktot = d->kh * d->kw * (grouped ? 64 : d->cin);
@@ -1716,6 +1874,39 @@ extern "C" int eqxv_gemm_bias_act_res_bf16(const void* a, int64_t lda, const voi
   return eqxv_conv2d_igemm_bf16(&d, stream);
 }
 
+static void gemm_desc(eqxv_conv_desc& d, const void* a, int64_t lda, const void* w, const float* bias,
+                      const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t m, int32_t n, int32_t k,
+                      int32_t act) {
+  d.x = a, d.wgt = w, d.bias = bias, d.residual = residual, d.y = out;
+  d.n = 1, d.h = 1, d.w = (int32_t)m, d.cin = k, d.cout = n;
+  d.kh = d.kw = 1, d.stride = 1, d.pad = 0, d.dil = 1;
+  d.x_pitch = (int32_t)lda, d.y_pitch = (int32_t)ldo, d.res_pitch = (int32_t)ldr;
+  d.act = act, d.flags = 0;
+}
+
+extern "C" int eqxv_gemm_res_rowstats_bf16(const void* a, int64_t lda, const void* w, const float* bias,
+                                           const void* residual, int64_t ldr, void* out, int64_t ldo,
+                                           float* row_stats, int64_t m, int32_t n, int32_t k, void* stream) {
+  EQXV_CHECK_ARG(m > 0 && m < (1ll << 31) && n > 0 && k > 0 && k % 8 == 0, "gemm_res_rowstats: bad shape");
+  EQXV_CHECK_ARG(residual && row_stats && ((uintptr_t)row_stats & 7) == 0, "gemm_res_rowstats: residual and row_stats are required");
+  eqxv_conv_desc d{};
+  gemm_desc(d, a, lda, w, bias, residual, ldr, out, ldo, m, n, k, EQXV_ACT_NONE);
+  LnFold ln{2, reinterpret_cast<float2*>(row_stats), nullptr, (n + 63) / 64, 0.f, 0.f};
+  return conv_impl(&d, &ln, stream);
+}
+
+extern "C" int eqxv_gemm_ln_act_bf16(const void* a, int64_t lda, const void* w, const float* bias, const float* wsum,
+                                     const float* row_stats, int32_t slots, float eps, void* out, int64_t ldo,
+                                     int64_t m, int32_t n, int32_t k, int32_t act, void* stream) {
+  EQXV_CHECK_ARG(m > 0 && m < (1ll << 31) && n > 0 && k > 0 && k % 8 == 0, "gemm_ln_act: bad shape");
+  EQXV_CHECK_ARG(bias && wsum && row_stats && slots == (k + 63) / 64,
+                 "gemm_ln_act: bias, wsum and row_stats[m][ceil(k/64)] are required (slots %d, k %d)", slots, k);
+  eqxv_conv_desc d{};
+  gemm_desc(d, a, lda, w, bias, nullptr, 0, out, ldo, m, n, k, act);
+  LnFold ln{1, reinterpret_cast<float2*>(const_cast<float*>(row_stats)), wsum, slots, 1.f / (float)k, eps};
+  return conv_impl(&d, &ln, stream);
+}
+
 extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n,
                                    int32_t h, int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride,
                                    int32_t pad, int32_t y_pitch, int32_t act, void* stream) {
@@ -1769,7 +1960,7 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
     static const int stem_sub = getenv("EQXV_STEM_SUB") ? atoi(getenv("EQXV_STEM_SUB")) : 0;
     p.epi_sub = stem_sub == 1 ? 1 : 2;
     p.off_bias = p.off_res;
-    p.off_bars = p.off_bias + bias_bytes;
+  p.off_bars = p.off_bias + bias_bytes;
     const int smem_bytes = p.off_bars + 256 + 1024;
 
     p.h_src = xpad;

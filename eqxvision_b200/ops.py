@@ -64,6 +64,38 @@ def gemm(a, wgt, bias, *, act=0, residual=None, out=None, out_f32=False, res_aft
     return out
 
 
+def gemm_rowstats(a, wgt, bias, *, residual, stats, out=None, act=0, res_after_act=False, out_f32=False, stream=0):
+    """out = a @ wgt^T + bias + residual, and stats[m, ceil(n/64), 2] = (sum, sum of squares) of every stored row per
+    64-column chunk: the producer half of a LayerNorm folded into its neighbours (eqxv_gemm_res_rowstats_bf16)"""
+    _check_cuda(a, wgt, bias, residual, out, stats)
+    if act != 0 or res_after_act or out_f32 or residual is None:
+        raise _lib.EqxvError("gemm_rowstats: plain bf16 GEMM + bias + residual only")
+    m, k = a.shape
+    n = wgt.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=BF16, device=a.device)
+    if stats.dtype != torch.float32 or tuple(stats.shape) != (m, (n + 63) // 64, 2) or not stats.is_contiguous():
+        raise _lib.EqxvError("gemm_rowstats: stats must be a contiguous fp32 [m, ceil(n/64), 2] tensor")
+    call("eqxv_gemm_res_rowstats_bf16", ptr(a), a.stride(0), ptr(wgt), ptr(bias), ptr(residual), residual.stride(0),
+         ptr(out), out.stride(0), ptr(stats), m, n, k, stream)
+    return out
+
+
+def gemm_ln(a, wgt, bias, wsum, stats, eps, *, act=0, out=None, stream=0):
+    """out = act(LayerNorm(a) @ W^T + b) without materialising the LayerNorm: wgt = W * gamma, bias = b + W @ beta,
+    wsum = row sums of wgt, stats from gemm_rowstats of the GEMM that produced `a` (eqxv_gemm_ln_act_bf16)"""
+    _check_cuda(a, wgt, bias, wsum, stats, out)
+    m, k = a.shape
+    n = wgt.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=BF16, device=a.device)
+    if stats.dtype != torch.float32 or tuple(stats.shape) != (m, (k + 63) // 64, 2) or not stats.is_contiguous():
+        raise _lib.EqxvError("gemm_ln: stats must be a contiguous fp32 [m, ceil(k/64), 2] tensor")
+    call("eqxv_gemm_ln_act_bf16", ptr(a), a.stride(0), ptr(wgt), ptr(bias), ptr(wsum), ptr(stats), stats.shape[1],
+         float(eps), ptr(out), out.stride(0), m, n, k, act, stream)
+    return out
+
+
 def pack_stem_input(x_nchw, pad=3, out=None, stream=0):
     _check_cuda(x_nchw, out)
     n, c, h, w = x_nchw.shape

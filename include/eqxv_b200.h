@@ -94,6 +94,22 @@ int eqxv_gemm_bias_act_res_bf16(const void* a, int64_t lda, const void* w, const
                                 const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t m,
                                 int32_t n, int32_t k, int32_t act, int32_t flags, void* stream);
 
+/* K5 + K7 fused: the LayerNorm between two GEMMs never touches HBM (vit.py:149,154: `x + attn(norm1(x))`,
+ * `x + mlp(norm2(x))`; mlps.py:61-65). The GEMM that PRODUCES the LayerNorm input (attention projection / fc2 with
+ * the residual add in its epilogue) also writes, per row and 64-column chunk, (sum, sum of squares) of the values it
+ * stores: row_stats is fp32 [m][ceil(n/64)][2]. */
+int eqxv_gemm_res_rowstats_bf16(const void* a, int64_t lda, const void* w, const float* bias, const void* residual,
+                                int64_t ldr, void* out, int64_t ldo, float* row_stats, int64_t m, int32_t n, int32_t k,
+                                void* stream);
+/* ... and the GEMM that CONSUMES LayerNorm(x) reads x itself: with w' = w * gamma (per input column, packed by the
+ * caller), bias' = bias + w @ beta and wsum[j] = sum_k w'[j, k],
+ *   out[i, j] = act( rstd_i * (x_i . w'_j - mean_i * wsum[j]) + bias'[j] ),
+ * mean_i / rstd_i from the producer's row_stats (slots = ceil(k/64) chunks per row; biased variance, eps as
+ * equinox.nn.LayerNorm). act: none or tanh-GELU. */
+int eqxv_gemm_ln_act_bf16(const void* a, int64_t lda, const void* w, const float* bias, const float* wsum,
+                          const float* row_stats, int32_t slots, float eps, void* out, int64_t ldo, int64_t m, int32_t n,
+                          int32_t k, int32_t act, void* stream);
+
 /* First-layer ("stem") convolution on the raw image, cin <= 8: resnet.py:243-251 (7x7 s2 p3),
  * vgg.py:137 (3x3 s1 p1), efficientnet.py:327-337 / mobilenetv3.py:196-206 (3x3 s2 p1), densenet.py:175.
  * Input is the padded 8-channel image written by eqxv_pack_stem_input; weights are [cout, kh, 8, 8] bf16

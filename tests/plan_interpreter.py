@@ -113,6 +113,28 @@ def gemm(a, wgt, bias, act=0, residual=None, res_after_act=False, out=None, out_
     _store(out, _epilogue(y, bias, act, residual, res_after_act))
 
 
+def gemm_rowstats(a, wgt, bias, residual, stats, out, **_):
+    """include/eqxv_b200.h K5 + K7, producer: the GEMM, plus (sum, sum of squares) of each STORED row per 64-column chunk"""
+    gemm(a, wgt, bias, 0, residual, False, out)
+    n = wgt.shape[0]
+    y = out[:, :n].float()
+    for c in range(stats.shape[1]):
+        blk = y[:, 64 * c:64 * c + 64]
+        stats[:, c, 0] = blk.sum(1)
+        stats[:, c, 1] = (blk * blk).sum(1)
+
+
+def gemm_ln(a, wgt, bias, wsum, stats, eps, act, out, **_):
+    """consumer: act(rstd * (a @ w'^T - mean * wsum) + bias') with mean / rstd from the producer's statistics"""
+    k = a.shape[1]
+    mean = stats[:, :, 0].sum(1) / k
+    var = (stats[:, :, 1].sum(1) / k - mean * mean).clamp_min(0)
+    rstd = torch.rsqrt(var + eps)
+    acc = a.float() @ wgt.float().t()
+    y = rstd[:, None] * (acc - mean[:, None] * wsum.float()[None, :]) + bias.float()[None, :]
+    _store(out, _act(y, act))
+
+
 def dwconv(x, wgt, bias, k, stride, pad, dil, act, out, **_):
     c = x.shape[-1]
     assert c % 8 == 0 and wgt.shape[1] >= c and bias.numel() >= c, "dwconv: channels / filter pitch"
@@ -293,7 +315,7 @@ def u8_resize_bilinear(x, oh, ow, out, **_):
     out.copy_(y.round().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1))
 
 
-IMPLS = {f.__name__: f for f in (dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
+IMPLS = {f.__name__: f for f in (gemm_rowstats, gemm_ln, dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
                                  nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
                                  maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d, patchify,
                                  vit_assemble_tokens, attention, attention_probs, gather_rows, resize_bilinear,

@@ -445,3 +445,36 @@ def test_depthwise_with_fused_squeeze(device, c, hw, k, stride, act, n):
         assert torch.equal(y3, y[perm]) and torch.equal(pooled3, pooled[perm])
     # and the plain entry (no squeeze) takes the same kernel: identical y
     assert torch.equal(ops.dwconv(x, wp, bd, k=k, stride=stride, pad=pad, act=act), y)
+
+
+@pytest.mark.parametrize("m,d,n,act", [(12608, 768, 2048, 0), (12608, 768, 1536, 3), (300, 192, 576, 0), (197, 384, 1536, 3),
+                                      (1000, 96, 288, 0)])
+def test_layernorm_folded_into_its_neighbour_gemms(device, m, d, n, act):
+    """eqxv_gemm_res_rowstats_bf16 -> eqxv_gemm_ln_act_bf16 (vit.py:149,154, mlps.py:61-65): the first GEMM adds the
+    residual and emits row statistics, the second applies LayerNorm to x on the fly. Reference: torch's layer_norm on
+    the stored x followed by the linear layer, fp32."""
+    from eqxvision_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    a0 = rb(device, m, d, seed=1)
+    w0 = rb(device, d, d, scale=d ** -0.5, seed=2)
+    b0 = torch.randn(d, generator=g).to(device)
+    res = rb(device, m, d, seed=3) * 3 + 1.5                     # rows with a mean well away from zero
+    stats = torch.zeros(m, (d + 63) // 64, 2, device=device)
+    x = ops.gemm_rowstats(a0, w0, b0, residual=res, stats=stats)
+    ref_x = a0.float() @ w0.float().t() + b0 + res.float()
+    assert rel_l2(x, ref_x) < TOL_BF16
+    xs = x.float()
+    want = torch.stack([xs.reshape(m, -1, 64).sum(2) if d % 64 == 0 else
+                        torch.stack([xs[:, c:c + 64].sum(1) for c in range(0, d, 64)], 1),
+                        (xs * xs).reshape(m, -1, 64).sum(2) if d % 64 == 0 else
+                        torch.stack([(xs[:, c:c + 64] ** 2).sum(1) for c in range(0, d, 64)], 1)], 2)
+    assert torch.allclose(stats, want, rtol=1e-5, atol=1e-3)
+    gamma = (1 + 0.2 * torch.randn(d, generator=g)).to(device)
+    beta = (0.3 * torch.randn(d, generator=g)).to(device)
+    w1 = (torch.randn(n, d, generator=g) * d ** -0.5).to(device)
+    b1 = torch.randn(n, generator=g).to(device)
+    wf = (w1 * gamma[None, :]).to(torch.bfloat16)
+    y = ops.gemm_ln(x, wf, (b1.double() + w1.double() @ beta.double()).float(), wf.float().sum(1), stats, 1e-5, act=act)
+    ref = ACTS[act](F.layer_norm(xs, (d,), gamma, beta, 1e-5) @ w1.t() + b1)
+    assert rel_l2(y, ref) < 6e-3     # two bf16 roundings (filter w*gamma, output) against an fp32 reference
