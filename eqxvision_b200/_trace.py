@@ -429,11 +429,10 @@ def adaptive_avg_pool2d(x: Sym, target) -> Sym:
     c, h, w = x.shape
     if (oh, ow) == (h, w):
         return x
-    if h % oh or w % ow:
-        # equinox splits an uneven axis into `dim % t` leading blocks of dim // t + 1 and the rest of dim // t, torch
-        # uses overlapping windows; the device kernel builds neither: fail at trace time, not at launch
-        raise NotImplementedError(f"adaptive average pooling {h}x{w} -> {oh}x{ow} is not an even split "
-                                  "(GoogLeNet's auxiliary heads, AlexNet / VGG away from 224x224)")
+    if (h % oh or w % ow) and (oh > h or ow > w):
+        # equinox splits an uneven axis into `dim % t` leading blocks of dim // t + 1 and the rest of dim // t (the
+        # device kernel follows that rule); a target larger than the map would need empty blocks
+        raise NotImplementedError(f"adaptive average pooling {h}x{w} -> {oh}x{ow}: target larger than the map")
     return Sym("chw", (c, oh, ow), AdaptiveAvgPool(x, oh, ow))
 
 

@@ -300,13 +300,28 @@ __device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const ui
       float ln_rstd = 1.f, ln_nmr = 0.f;
       if constexpr (kLN == 1) {
         // statistics of this row, written by the producing GEMM's epilogue: loaded before the accumulator wait
+        // (all loads of the row are issued back to back - one L2 latency, not one per slot: with a runtime-bound loop
+        // the twelve dependent-looking loads of a ViT-B row cost ~8000 cycles at the head of every tile's epilogue)
         float sum = 0.f, sq = 0.f;
         if (ln_row < p.ln_rows) {
           const float2* st = p.ln_stats + (long long)ln_row * p.ln_slots;
-          for (int i = 0; i < p.ln_slots; ++i) {
-            const float2 a = __ldg(st + i);
-            sum += a.x;
-            sq += a.y;
+          if ((p.ln_slots & 1) == 0 && p.ln_slots <= 32) {
+            const float4* st4 = reinterpret_cast<const float4*>(st);   // rows of an even slot count are 16-byte aligned
+            const int n4 = p.ln_slots >> 1;
+            float4 a[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = i < n4 ? __ldg(st4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              sum += a[i].x + a[i].z;
+              sq += a[i].y + a[i].w;
+            }
+          } else {
+            for (int i = 0; i < p.ln_slots; ++i) {
+              const float2 a = __ldg(st + i);
+              sum += a.x;
+              sq += a.y;
+            }
           }
         }
         const float mean = sum * p.ln_inv_d;

@@ -730,13 +730,62 @@ extern "C" int eqxv_avgpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32
                      (cudaStream_t)stream);
 }
 
+// equinox.nn.AdaptiveAvgPool2d on an axis that does not divide evenly (GoogLeNet's auxiliary heads pool 14x14 -> 4x4,
+// googlenet.py:265-268; AlexNet / VGG away from 224 px): Equinox splits the axis into `t` consecutive blocks, the first
+// dim % t of them one element longer (dim // t + 1), the rest dim // t - NOT torch's overlapping windows.
+__device__ __forceinline__ void eqx_block(int i, int dim, int t, int& start, int& len) {
+  const int head = dim % t, block = dim / t;
+  if (i < head) {
+    start = i * (block + 1), len = block + 1;
+  } else {
+    start = head * (block + 1) + (i - head) * block, len = block;
+  }
+}
+__global__ void adaptive_avgpool_uneven_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n,
+                                               int h, int w, int c, int oh, int ow, int xp, int yp) {
+  griddep_wait();
+  griddep_launch();
+  const int groups = c / 8;
+  const long long total = (long long)n * oh * ow * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long t = i / groups;
+    const int ox = (int)(t % ow);
+    t /= ow;
+    const int oy = (int)(t % oh);
+    const int img = (int)(t / oh);
+    int y0, hy, x0, wx;
+    eqx_block(oy, h, oh, y0, hy);
+    eqx_block(ox, w, ow, x0, wx);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = y0; r < y0 + hy; ++r)
+      for (int q = x0; q < x0 + wx; ++q) {
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)img * h + r) * w + q) * xp + g * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    const float inv = 1.f / (float)(hy * wx);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    *reinterpret_cast<bf16x8*>(y + (((long long)img * oh + oy) * ow + ox) * yp + g * 8) = pack8(acc);
+  }
+}
+
 extern "C" int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w,
                                                int32_t c, int32_t oh, int32_t ow, int32_t x_pitch,
                                                int32_t y_pitch, void* stream) {
   EQXV_CHECK_ARG(oh >= 1 && ow >= 1, "adaptive_avgpool: bad output size");
   if (h % oh != 0 || w % ow != 0) {
-    set_error("adaptive_avgpool: %dx%d -> %dx%d is not an even split (unsupported)", h, w, oh, ow);
-    return EQXV_ERR_UNSUPPORTED;
+    EQXV_CHECK_ARG(x && y && n > 0 && c > 0 && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 && x_pitch >= c &&
+                       y_pitch >= c && oh <= h && ow <= w,
+                   "adaptive_avgpool: bad arguments (uneven split needs oh <= h, ow <= w, channels a multiple of 8)");
+    const long long total = (long long)n * oh * ow * (c / 8);
+    EQXV_CUDA(launch_kernel(adaptive_avgpool_uneven_kernel, dim3(grid_for(total)), dim3(kPwThreads), (size_t)0,
+                            (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, h, w, c, oh, ow, x_pitch,
+                            y_pitch));
+    EQXV_LAUNCH_CHECK();
+    return EQXV_OK;
   }
   if (oh == 1 && ow == 1 && h * w >= 32) {
     EQXV_CHECK_ARG(x && y && n > 0 && c > 0 && c % 8 == 0 && x_pitch % 8 == 0 && y_pitch % 8 == 0 &&

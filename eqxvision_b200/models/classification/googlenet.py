@@ -5,9 +5,10 @@ BasicConv2d = conv (no bias) -> BatchNorm(eps 1e-3) -> ReLU. _Inception = channe
 max-pool 3x3/1 p1 -> 1x1. Stage pools are 3x3/2 (2x2/2 before inception5) with `use_ceil=True`.
 Device lowering: every branch's last convolution stores straight into its channel slice of the block's output buffer
 (no concat pass); BN + ReLU are GEMM epilogues.
-The auxiliary classifiers (`aux_logits=True`) pool 14x14 maps adaptively to 4x4, an uneven split that the device
-library does not build (equinox and torch disagree on it): constructing them works, so that
-torchvision checkpoints load positionally the way the reference loads them (googlenet.py:322-327), calling them raises.
+The auxiliary classifiers (`aux_logits=True`) pool 14x14 maps adaptively to 4x4: an uneven split, which Equinox cuts
+into consecutive blocks of 4, 4, 3, 3 (torch would use overlapping windows) - the device kernel follows
+Equinox (`eqxv_adaptive_avgpool_nhwc_bf16`), and the model returns `(logits, aux2, aux1)` like the reference
+(googlenet.py:174-175).
 """
 import copy
 import warnings

@@ -143,8 +143,10 @@ int eqxv_maxpool2d_ceil_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, 
 /* K10: equinox.nn.AvgPool2d(k, stride) (densenet.py:128) */
 int eqxv_avgpool2d_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
                              int32_t k, int32_t stride, int32_t x_pitch, int32_t y_pitch, void* stream);
-/* K10: AdaptiveAvgPool2d((oh, ow)) with h % oh == 0 and w % ow == 0 (block mean), resnet.py:283,
- * vgg.py:90; (1,1) is the global pool that feeds the classifier. */
+/* K10: AdaptiveAvgPool2d((oh, ow)), resnet.py:283, vgg.py:90; (1,1) is the global pool that feeds the classifier.
+ * h % oh == 0 and w % ow == 0: block mean. Otherwise EQUINOX's rule (not torch's overlapping windows): the axis is cut
+ * into consecutive blocks, the first dim % t of them dim // t + 1 long, the rest dim // t (GoogLeNet's auxiliary heads,
+ * googlenet.py:265-268: 14x14 -> 4x4; AlexNet / VGG on inputs other than 224 px). */
 int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t w,
                                     int32_t c, int32_t oh, int32_t ow, int32_t x_pitch,
                                     int32_t y_pitch, void* stream);

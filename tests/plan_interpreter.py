@@ -166,6 +166,14 @@ def avgpool2d(x, k, stride, out, **_):
 
 def adaptive_avgpool(x, oh, ow, out, **_):
     n, h, w, c = x.shape
+    if h % oh or w % ow:   # Equinox's uneven rule (include/eqxv_b200.h K10): leading blocks one element longer
+        def blocks(dim, t):
+            head, blk = dim % t, dim // t
+            return [(i * (blk + 1), blk + 1) if i < head else (head * (blk + 1) + (i - head) * blk, blk) for i in range(t)]
+        y = torch.stack([torch.stack([x[:, y0:y0 + hy, x0:x0 + wx].float().mean((1, 2)) for x0, wx in blocks(w, ow)], 1)
+                         for y0, hy in blocks(h, oh)], 1)
+        _store(out, y)
+        return
     y = x.float().reshape(n, oh, h // oh, ow, w // ow, c).mean((2, 4))
     _store(out, y)
 

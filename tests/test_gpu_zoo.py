@@ -149,6 +149,27 @@ def test_zoo_parity(device, save_checkpoint, arch, fn, hw, batch, tol_emu, tol_f
     assert rel(got, ref) < tol_f32, ("vs fp32 oracle", rel(got, ref))
 
 
+def test_googlenet_with_auxiliary_heads(device, save_checkpoint):
+    """GoogLeNet(aux_logits=True) -> (logits, aux2, aux1) (googlenet.py:157-175): the auxiliary heads' 14x14 -> 4x4 pooling
+    follows Equinox's uneven rule on the device (oracle pinned against the reference's own code, tests/test_refshim.py)"""
+    import eqxvision_b200 as eb
+    from oracle import checkpoints as ck
+    from oracle import models as om
+    from oracle import ops as O
+
+    kw = {"aux_logits": True, "transform_input": False, "init_weights": True}
+    sd = ck.torchvision_state_dict("googlenet", seed=1, **kw)
+    net = eb.tree_inference(eb.models.googlenet(torch_weights=save_checkpoint(sd, "g.pth"), aux_logits=True), True)
+    x = ck.synthetic_images(3, seed=2)
+    out, aux2, aux1 = eb.vmap(net, axis_name="batch")(x, key=keys(3))
+    with O.emulate_bf16():
+        e0, e2, e1 = om.googlenet(sd, x, "googlenet", aux_logits=True)
+    r0, r2, r1 = om.googlenet(sd, x, "googlenet", aux_logits=True)
+    for got, emu, ref in ((out, e0, r0), (aux2, e2, r2), (aux1, e1, r1)):
+        assert got.shape == (3, 1000)
+        assert rel(got, emu) < 1.5e-2 and rel(got, ref) < 4e-2, (rel(got, emu), rel(got, ref))
+
+
 def test_alexnet_readme_example_single_image(device, save_checkpoint):
     """BASELINE config 0 / README.md:37-46: `filter_jit(vmap(net, axis_name="batch"))(images, key=keys)` on a
     1x3x224x224 batch, and `.features` as the reference's own test reaches it (tests/test_models/test_alexnet.py:23)"""

@@ -56,6 +56,25 @@ def test_lowered_plan_matches_emulating_oracle(tmp_path, arch, fn, hw, kw):
         assert rel(got16, emu16) < 1e-2, rel(got16, emu16)
 
 
+def test_googlenet_auxiliary_heads_lower_with_equinox_uneven_pooling(tmp_path):
+    """GoogLeNet(aux_logits=True) returns (logits, aux2, aux1) (googlenet.py:174-175); its auxiliary heads pool 14x14 maps
+    to 4x4 with EQUINOX's uneven rule (blocks of 4, 4, 3, 3 - not torch's overlapping windows), then flatten in (C, H, W)
+    order into fc1. Also AlexNet away from 224 px (6x6 target on a 3x3... map is refused, 13x13 -> 6x6 is not)."""
+    kw = {"aux_logits": True, "transform_input": False, "init_weights": True}
+    sd = ck.torchvision_state_dict("googlenet", seed=1, calib_hw=96, **kw)
+    path = str(tmp_path / "g.pth")
+    torch.save(sd, path)
+    net = eb.tree_inference(eb.models.googlenet(torch_weights=path, aux_logits=True), True)
+    x = ck.synthetic_images(2, h=224, w=224, seed=2)
+    (out, aux2, aux1), plan = PI.run(net, x, fp32_activations=True)
+    with O.emulate_bf16(activations=False):
+        ref, r2, r1 = om.googlenet(sd, x, "googlenet", aux_logits=True)
+    assert out.shape == aux1.shape == aux2.shape == (2, 1000)
+    assert rel(out, ref) < 5e-4 and rel(aux1, r1) < 5e-4 and rel(aux2, r2) < 5e-4, (rel(out, ref), rel(aux1, r1), rel(aux2, r2))
+    pools = [kw_ for fn, kw_ in plan.steps if fn.__name__ == "adaptive_avgpool" and kw_["oh"] == 4]
+    assert len(pools) == 2 and all(tuple(kw_["x"].shape[1:3]) == (14, 14) for kw_ in pools)
+
+
 def test_channel_views_compose_and_fold_into_dense_convs():
     from eqxvision_b200 import _trace as T
 
