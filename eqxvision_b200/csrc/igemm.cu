@@ -239,6 +239,39 @@ __device__ __forceinline__ uint4 epilogue8_ln(const float* v, const float* bias_
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// Per-column fp32 vector (folded-BN shift / bias, filter column sums) -> shared memory, zero beyond `count`, once per
+// CTA. Every thread issues up to four 16-byte loads BEFORE it stores anything: the persistent CTAs of the next kernel
+// only become resident when the previous kernel's CTAs exit, so this prologue is NOT hidden by PDL, and the scalar loop
+// it replaces paid one dependent L2 round trip per 288 columns (ncu on ViT-B/16 fc1, N = 3072, bias + column sums:
+// 21 % of the kernel's stall samples sat on these two loops, profiles/r02_ncu_pair_vit.txt).
+__device__ __forceinline__ void stage_columns(float* dst, const float* __restrict__ src, int count, int ncols_pad) {
+  const int n4 = ncols_pad >> 2;   // ncols_pad is a multiple of 16
+  const bool vec = src != nullptr && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  for (int base = 0; base < n4; base += 4 * (int)blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = (base + (int)threadIdx.x + k * (int)blockDim.x) * 4;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src != nullptr && c < count) {
+        if (vec && c + 3 < count) {
+          v[k] = __ldg(reinterpret_cast<const float4*>(src + c));
+        } else {
+          v[k].x = __ldg(src + c);
+          if (c + 1 < count) v[k].y = __ldg(src + c + 1);
+          if (c + 2 < count) v[k].z = __ldg(src + c + 2);
+          if (c + 3 < count) v[k].w = __ldg(src + c + 3);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i4 = base + (int)threadIdx.x + k * (int)blockDim.x;
+      if (i4 < n4) reinterpret_cast<float4*>(dst)[i4] = v[k];
+    }
+  }
+}
+
 // ============================== epilogue, four warps (epi_sub == 1) ==============================
 // One warp per TMEM lane quadrant, tile-major loop, double-buffered staging slab per warp. Used where the
 // K loop hides the epilogue (first layer, halo kernel, deep-K residual GEMMs): it is measurably leaner per
@@ -625,14 +658,10 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   }
   // folded-BN shift / bias for every output column, once per CTA (zero beyond cout)
   {
-    float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
     const int ncols_pad = p.n_tiles * p.block_n + 64;
-    for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x)
-      sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
-    if (kLN == 1) {   // column sums of the gamma-folded filter, next to the bias
-      float* sw = reinterpret_cast<float*>(gbase + p.off_wsum);
-      for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x) sw[i] = i < p.cout ? __ldg(p.ln_wsum + i) : 0.f;
-    }
+    stage_columns(reinterpret_cast<float*>(gbase + p.off_bias), p.bias, p.cout, ncols_pad);
+    if (kLN == 1)   // column sums of the gamma-folded filter, next to the bias
+      stage_columns(reinterpret_cast<float*>(gbase + p.off_wsum), p.ln_wsum, p.cout, ncols_pad);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -802,14 +831,10 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
     mbar_fence_init();
   }
   {
-    float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
     const int ncols_pad = p.n_tiles * p.block_n + 64;
-    for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x)
-      sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
-    if (kLN == 1) {   // column sums of the gamma-folded filter, next to the bias
-      float* sw = reinterpret_cast<float*>(gbase + p.off_wsum);
-      for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x) sw[i] = i < p.cout ? __ldg(p.ln_wsum + i) : 0.f;
-    }
+    stage_columns(reinterpret_cast<float*>(gbase + p.off_bias), p.bias, p.cout, ncols_pad);
+    if (kLN == 1)   // column sums of the gamma-folded filter, next to the bias
+      stage_columns(reinterpret_cast<float*>(gbase + p.off_wsum), p.ln_wsum, p.cout, ncols_pad);
   }
   if (warp == 1) {
     tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
@@ -1175,10 +1200,8 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
     mbar_fence_init();
   }
   {
-    float* sb = reinterpret_cast<float*>(gbase + p.off_bias);
     const int ncols_pad = p.n_tiles * p.block_n + 64;
-    for (int i = threadIdx.x; i < ncols_pad; i += blockDim.x)
-      sb[i] = (p.bias != nullptr && i < p.cout) ? __ldg(p.bias + i) : 0.f;
+    stage_columns(reinterpret_cast<float*>(gbase + p.off_bias), p.bias, p.cout, ncols_pad);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
