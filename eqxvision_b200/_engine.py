@@ -334,6 +334,19 @@ class Plan:
         else:
             out = self.alloc(self.n * ho * wo, cout, (ho, wo), dtype=torch.float32 if out_f32 else BF16)
 
+        if (self.GATE_FUSE and isinstance(xin.expr, T.ChannelScale) and id(xin.expr) not in self.memo and kh == kw == 1
+                and sh == 1 and ph == 0 and act == _lib.ACT_NONE and not res_after and not out_f32 and bias_d is not None
+                and cout <= MAX_COUT_PER_LAUNCH):
+            # SqueezeExcitation gate feeding the projection (efficientnet.py:161-170): applied to the GEMM's A operand
+            # in shared memory (eqxv_gemm_gated_bf16) instead of a pass that reads and rewrites the expanded tensor
+            ce = xin.expr
+            sb = self.emit(ce.s)          # gate first: its squeeze may ride in the depthwise kernel
+            xb = self.emit(ce.x)
+            if xb.pitch == c_in and c_in % 8 == 0 and sb.pitch >= c_in:
+                wp = self.const(_pack.pack_conv_weight(w, c_in))
+                self.step(ops.gemm_gated, a=xb.rows(c_in), gate=sb.rows(sb.pitch), wgt=wp, bias=bias_d,
+                          rows_per_image=h * wd, residual=None if res is None else res.rows(), out=out.rows())
+                return out
         if isinstance(xin.expr, T.Input):
             if c_in <= 8 and kh <= 8 and kw <= 8 and sh in (1, 2, 4) and dh == 1 and 2 * ph <= kw \
                     and res is None and not out_f32 and dst is None:
@@ -445,6 +458,7 @@ class Plan:
     # The LayerNorm between two GEMMs (vit.py:149,154) is folded into them: the producer's epilogue emits row statistics,
     # the consumer applies mean / rstd to its accumulators (include/eqxv_b200.h, K5 + K7). EQXV_NO_LN_FOLD=1: A/B switch.
     LN_FOLD = os.environ.get("EQXV_NO_LN_FOLD") != "1"
+    GATE_FUSE = os.environ.get("EQXV_NO_GATE_FUSE") != "1"   # SE gate inside the projection GEMM (A/B switch)
     LN_MAX_COUT = 3328    # the consumer stages bias AND filter column sums (28 KB area: csrc/igemm.cu)
 
     def _emit_linear_ln(self, sym, e: T.Linear, ln: "T.LayerNormE", act: int) -> Optional[Buf]:

@@ -49,6 +49,7 @@ SIGNATURES = {
     "eqxv_gemm_bias_act_res_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
     "eqxv_gemm_res_rowstats_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp],
     "eqxv_gemm_ln_act_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _i64, _i64, _i32, _i32, _i32, _vp],
+    "eqxv_gemm_gated_bf16": [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp],
     "eqxv_conv_stem_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_pack_stem_input": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -123,7 +124,7 @@ _LAUNCHING = {
     "eqxv_window_attention_bf16", "eqxv_patch_merge_bf16",
     "eqxv_u8hwc_to_nchw_f32", "eqxv_u8hwc_pack_stem_input", "eqxv_u8hwc_to_nhwc_bf16", "eqxv_u8hwc_patchify_bf16",
     "eqxv_u8hwc_resize_bilinear", "eqxv_allgather_push", "eqxv_swin_v2_qk_normalize_bf16", "eqxv_dwconv_bn_act_pool_bf16", "eqxv_gemm_res_rowstats_bf16",
-    "eqxv_gemm_ln_act_bf16",
+    "eqxv_gemm_ln_act_bf16", "eqxv_gemm_gated_bf16",
 }
 
 

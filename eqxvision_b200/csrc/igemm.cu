@@ -59,6 +59,9 @@ struct alignas(64) IgemmParams {
   const float* ln_wsum;
   int ln_slots, ln_rows, off_wsum;
   float ln_inv_d, ln_eps;
+  // SqueezeExcitation gate applied to the A operand (kGate kernels, flat GEMMs): A[row, k] *= gate[row / gate_rpi, k]
+  const __nv_bfloat16* gate;
+  int gate_pitch, gate_rpi, gate_cols;
   // first-layer (halo) kernel only
   int h_stride, h_planes, h_px, h_rows, h_plane_pitch, h_stage_bytes, h_ksteps, h_off_b;
   const void* h_src;  // padded NHWC8 image [n, in_h, in_w, 8]
@@ -619,7 +622,7 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
 // kRes: 0 = no residual, 1 = act(acc + bias + res), 2 = act(acc + bias) + res. Compile-time so that the
 // unrolled epilogue is straight-line code (a runtime flag doubled its instruction count and made the
 // epilogue warps issue-bound on the HBM-bound layers: profiles/r01_layers_v4).
-template <bool kOutF32, int kAct, int kRes, int kLN = 0>
+template <bool kOutF32, int kAct, int kRes, int kLN = 0, bool kGate = false>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -654,6 +657,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       mbar_init(tempty_bar(a), 128u * (uint32_t)p.epi_sub);
     }
     for (int b = 0; b < 16; ++b) mbar_init(bars + 8u * (48 + b), 1);   // residual ring (epilogue_warps)
+    if (kGate)
+      for (int b = 0; b < S; ++b) mbar_init(bars + 8u * (32 + b), 128);   // xf[stage]: the 128 gate threads
     mbar_fence_init();
   }
   // folded-BN shift / bias for every output column, once per CTA (zero beyond cout)
@@ -709,6 +714,57 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       }
     }
     __syncwarp();
+  } else if (kGate && warp >= 6) {
+    // ============================== SE gate on the A operand (warps 6..9, kGate kernels) ==============================
+    // SqueezeExcitation `x * scale` (layers/squeeze.py:61) feeding the project convolution (efficientnet.py:161-170):
+    // instead of a separate pass that reads and rewrites the expanded tensor, these four warps scale every staged A
+    // tile IN SHARED MEMORY - thread = one row of the tile; 16-byte chunk j of row r of the 128B-swizzled tile sits at
+    // r*128 + ((j ^ (r & 7)) << 4); bf16 x bf16 products rounded to bf16 with HMUL2, exactly what the separate pass
+    // stored - make the writes visible to the async proxy and arrive on xf[stage], which the MMA issuer waits for in
+    // place of full[stage]. Flat GEMMs (1x1 convolutions) only; the epilogue runs on four warps (epi_sub == 1).
+    const int r = (warp - 6) * 32 + lane;
+    const uint32_t xor7 = (uint32_t)(r & 7);
+    uint32_t fb = full_bar(0);
+    const uint32_t fb0 = fb;
+    uint32_t xb = bars + 8u * 32u;
+    const uint32_t xb0 = xb;
+    uint32_t phase = 0;
+    uint8_t* rowp = gbase + r * 128;
+    uint8_t* const row0 = rowp;
+    int sidx = 0;
+    const int kchunks = p.kchunks;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int row = min(t.w0 + r, p.ln_rows - 1);   // rows past the end: zero-filled A, any gate will do
+      const __nv_bfloat16* grow = p.gate + (long long)(row / p.gate_rpi) * p.gate_pitch;
+      for (int i = 0; i < kchunks; ++i) {
+        const int k0 = i * kBlockK;
+        uint4 g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)   // the gate does not depend on the tile data: in flight during the barrier wait
+          g[j] = (k0 + j * 8 < p.gate_cols) ? __ldg(reinterpret_cast<const uint4*>(grow + k0 + j * 8))
+                                            : make_uint4(0u, 0u, 0u, 0u);
+        mbar_wait(fb, phase);
+        uint4 a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = *reinterpret_cast<const uint4*>(rowp + (((uint32_t)j ^ xor7) << 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a[j]);
+          const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g[j]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a2[e] = __hmul2(a2[e], g2[e]);
+          *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ xor7) << 4)) = a[j];
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        mbar_arrive(xb);
+        fb += 8, xb += 8, rowp += stage_bytes;
+        if (++sidx == S) {
+          sidx = 0, fb = fb0, xb = xb0, rowp = row0;
+          phase ^= 1u;
+        }
+      }
+    }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     // ONE thread runs the whole role. Per 64-deep K block it needs: a barrier wait, 4 UTCHMMA, a
@@ -725,7 +781,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const uint32_t a_end = a_lo0 + (uint32_t)S * step;
       const uint32_t b_off = kABytes >> 4;
       uint32_t a_lo = a_lo0;
-      uint32_t fb = full_bar(0), eb = empty_bar(0);
+      uint32_t fb = kGate ? bars + 8u * 32u : full_bar(0), eb = empty_bar(0);
       const uint32_t fb0 = fb, eb0 = eb;
       uint32_t phase = 0;
       int acc = 0;
@@ -751,7 +807,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         uint32_t accumulate = 0;
         for (int i = 0; i < nk; ++i) {
-          mbar_wait(fb, phase);
+          mbar_wait(fb, phase);      // kGate: xf[stage], raised by the gate warps once the A tile is scaled
           tc_fence_after();
           umma_bf16_kblock64(d_tmem, a_lo, a_lo + b_off, desc_hi, desc_hi, idesc, accumulate, eb);
           accumulate = 1;
@@ -1399,6 +1455,9 @@ struct IgemmProblem {
   const float* ln_wsum;
   int ln_slots;
   float ln_inv_d, ln_eps;
+  // SE gate on the A operand (flat GEMMs)
+  const void* gate;
+  int gate_pitch, gate_rpi;
 };
 
 static void choose_tile(int n, int ho, int wo, int& tw, int& th, int& tn) {
@@ -1492,7 +1551,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   const int kblocks = q.kh * q.kw * q.kchunks;
   // CTA pairs pay off when the K loop (not HBM or the epilogue) dominates: deep K, wide N, enough tiles
   const bool pair_ok = !out_f32 && q.cout >= 128 && m_tiles >= 2 && q.dil_h == 1 && !q.grouped;
-  const bool pair = pair_ok && !env_int("EQXV_NO_PAIR") && (kblocks >= 4 || env_int("EQXV_FORCE_PAIR"));
+  const bool pair = pair_ok && !q.gate && !env_int("EQXV_NO_PAIR") && (kblocks >= 4 || env_int("EQXV_FORCE_PAIR"));
   int block_n;
   if (pair) {
     block_n = choose_block_n_pair(q.cout, (m_tiles + 1) / 2, kblocks, device_sm_count() / 2);
@@ -1537,6 +1596,14 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
                  q.cout);
   p.ln_stats = q.ln_stats, p.ln_wsum = q.ln_wsum, p.ln_slots = q.ln_slots, p.ln_rows = q.out_w;
   p.ln_inv_d = q.ln_inv_d, p.ln_eps = q.ln_eps;
+  if (q.gate) {
+    EQXV_CHECK_ARG(q.tw == 128 && q.th == 1 && q.tn == 1 && q.kh == 1 && q.kw == 1 && !out_f32 && !q.grouped &&
+                       q.ln_mode == 0 && q.act == EQXV_ACT_NONE && !(q.flags & EQXV_FLAG_RES_AFTER_ACT),
+                   "igemm: the gated A operand needs a flat bf16 GEMM without activation");
+    p.gate = static_cast<const __nv_bfloat16*>(q.gate), p.gate_pitch = q.gate_pitch, p.gate_rpi = q.gate_rpi;
+    p.gate_cols = q.cin_pack;
+    p.ln_rows = q.out_w;
+  }
   if (q.ln_mode != 0) {
     EQXV_CHECK_ARG(q.tw == 128 && q.th == 1 && q.tn == 1 && q.kh == 1 && q.kw == 1 && !out_f32 && !q.grouped,
                    "igemm: LayerNorm folding needs a flat bf16 GEMM");
@@ -1552,6 +1619,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   // loop wins there by 2-7 % with or without a residual (tools/sweep_igemm.py, profiles/r01_sweep_igemm_v18.txt).
   p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : (kblocks <= 4 ? 2 : 1);
   if (q.ln_mode != 0) p.epi_sub = 1;   // the folding lives in the four-warp epilogue
+  if (q.gate) p.epi_sub = 1;           // warps 6..9 scale the A tiles
   const int fixed = 2 * kStageBuf + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
   int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
   stages = std::min(stages, 8);
@@ -1619,15 +1687,17 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   if (q.ln_mode == 1)
     fn = q.act == EQXV_ACT_NONE ? igemm_kernel<false, 0, 0, 1> : igemm_kernel<false, EQXV_ACT_GELU_TANH, 0, 1>;
   if (q.ln_mode == 2) fn = igemm_kernel<false, 0, 1, 2>;
-  EQXV_CUDA(launch_kernel(fn, dim3(grid), dim3(64 + 128 * p.epi_sub), (size_t)(smem_bytes), stream, p));
+  if (q.gate) fn = q.res ? igemm_kernel<false, 0, 1, 0, true> : igemm_kernel<false, 0, 0, 0, true>;
+  EQXV_CUDA(launch_kernel(fn, dim3(grid), dim3(64 + 128 * p.epi_sub + (q.gate ? 128 : 0)), (size_t)(smem_bytes), stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
 
 static KernelFn ln_kernels(int i) {
-  static const KernelFn t[6] = {pair_kernel<0, 0, 1>, pair_kernel<EQXV_ACT_GELU_TANH, 0, 1>, pair_kernel<0, 1, 2>,
+  static const KernelFn t[8] = {pair_kernel<0, 0, 1>, pair_kernel<EQXV_ACT_GELU_TANH, 0, 1>, pair_kernel<0, 1, 2>,
                                 igemm_kernel<false, 0, 0, 1>, igemm_kernel<false, EQXV_ACT_GELU_TANH, 0, 1>,
-                                igemm_kernel<false, 0, 1, 2>};
+                                igemm_kernel<false, 0, 1, 2>, igemm_kernel<false, 0, 0, 0, true>,
+                                igemm_kernel<false, 0, 1, 0, true>};
   return t[i];
 }
 
@@ -1647,7 +1717,7 @@ static StemFn stem_table(int act) {
 }
 
 int igemm_init() {
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 8; ++i)
     EQXV_CUDA(cudaFuncSetAttribute(ln_kernels(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < kNumActs; ++a)
     EQXV_CUDA(cudaFuncSetAttribute(stem_table(a), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -1800,11 +1870,13 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
 using namespace eqxv;
 
 struct LnFold {
-  int mode;   // 1 consumer, 2 producer
+  int mode;   // 1 LayerNorm consumer, 2 LayerNorm producer, 0 with `gate`: SE gate on the A operand
   float2* stats;
   const float* wsum;
   int slots;
   float inv_d, eps;
+  const void* gate = nullptr;
+  int gate_pitch = 0, gate_rpi = 0;
 };
 static int conv_impl(const eqxv_conv_desc* d, const LnFold* ln, void* stream);
 
@@ -1841,6 +1913,7 @@ static int conv_impl(const eqxv_conv_desc* d, const LnFold* ln, void* stream) {
   if (ln) {
     q.ln_mode = ln->mode, q.ln_stats = ln->stats, q.ln_wsum = ln->wsum, q.ln_slots = ln->slots;
     q.ln_inv_d = ln->inv_d, q.ln_eps = ln->eps;
+    q.gate = ln->gate, q.gate_pitch = ln->gate_pitch, q.gate_rpi = ln->gate_rpi;
   }
   q.grouped = grouped ? 1 : 0;
   q.wgt = d->wgt;
@@ -1942,6 +2015,18 @@ extern "C" int eqxv_gemm_ln_act_bf16(const void* a, int64_t lda, const void* w, 
   eqxv_conv_desc d{};
   gemm_desc(d, a, lda, w, bias, nullptr, 0, out, ldo, m, n, k, act);
   LnFold ln{1, reinterpret_cast<float2*>(const_cast<float*>(row_stats)), wsum, slots, 1.f / (float)k, eps};
+  return conv_impl(&d, &ln, stream);
+}
+
+extern "C" int eqxv_gemm_gated_bf16(const void* a, int64_t lda, const void* gate, int64_t ldg, int32_t rows_per_image,
+                                    const void* w, const float* bias, const void* residual, int64_t ldr, void* out,
+                                    int64_t ldo, int64_t m, int32_t n, int32_t k, void* stream) {
+  EQXV_CHECK_ARG(m > 0 && m < (1ll << 31) && n > 0 && k > 0 && k % 8 == 0, "gemm_gated: bad shape");
+  EQXV_CHECK_ARG(gate && rows_per_image > 0 && ldg >= k && ldg % 8 == 0 && ((uintptr_t)gate & 15) == 0,
+                 "gemm_gated: gate must be a 16-byte aligned bf16 [images, >= k] matrix");
+  eqxv_conv_desc d{};
+  gemm_desc(d, a, lda, w, bias, residual, ldr, out, ldo, m, n, k, EQXV_ACT_NONE);
+  LnFold ln{0, nullptr, nullptr, 0, 0.f, 0.f, gate, (int)ldg, rows_per_image};
   return conv_impl(&d, &ln, stream);
 }
 

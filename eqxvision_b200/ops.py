@@ -96,6 +96,19 @@ def gemm_ln(a, wgt, bias, wsum, stats, eps, *, act=0, out=None, stream=0):
     return out
 
 
+def gemm_gated(a, gate, wgt, bias, *, rows_per_image, residual=None, out=None, stream=0):
+    """out = (a * gate[row // rows_per_image]) @ wgt^T + bias (+ residual): the SE gate applied to the A operand inside
+    the projection GEMM (eqxv_gemm_gated_bf16); a [m, k], gate [images, >= k] bf16"""
+    _check_cuda(a, gate, wgt, bias, residual, out)
+    m, k = a.shape
+    n = wgt.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=BF16, device=a.device)
+    call("eqxv_gemm_gated_bf16", ptr(a), a.stride(0), ptr(gate), gate.stride(0), rows_per_image, ptr(wgt), ptr(bias),
+         ptr(residual), residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), m, n, k, stream)
+    return out
+
+
 def pack_stem_input(x_nchw, pad=3, out=None, stream=0):
     _check_cuda(x_nchw, out)
     n, c, h, w = x_nchw.shape

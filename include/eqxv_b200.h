@@ -110,6 +110,14 @@ int eqxv_gemm_ln_act_bf16(const void* a, int64_t lda, const void* w, const float
                           const float* row_stats, int32_t slots, float eps, void* out, int64_t ldo, int64_t m, int32_t n,
                           int32_t k, int32_t act, void* stream);
 
+/* K5 + K11 fused: SqueezeExcitation's `x * scale` (layers/squeeze.py:61) applied to the A operand of the projection that
+ * consumes it (efficientnet.py:161-170, mobilenetv3.py:113-121): out = (a * gate[row / rows_per_image]) @ w^T + bias
+ * (+ residual). The staged A tile is scaled in shared memory before the MMA (bf16 x bf16 rounded to bf16, exactly what
+ * the separate gate pass stored), so the expanded tensor is read ONCE and never rewritten. gate: bf16 [images, ldg]. */
+int eqxv_gemm_gated_bf16(const void* a, int64_t lda, const void* gate, int64_t ldg, int32_t rows_per_image, const void* w,
+                         const float* bias, const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t m,
+                         int32_t n, int32_t k, void* stream);
+
 /* First-layer ("stem") convolution on the raw image, cin <= 8: resnet.py:243-251 (7x7 s2 p3),
  * vgg.py:137 (3x3 s1 p1), efficientnet.py:327-337 / mobilenetv3.py:196-206 (3x3 s2 p1), densenet.py:175.
  * Input is the padded 8-channel image written by eqxv_pack_stem_input; weights are [cout, kh, 8, 8] bf16

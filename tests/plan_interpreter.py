@@ -135,6 +135,15 @@ def gemm_ln(a, wgt, bias, wsum, stats, eps, act, out, **_):
     _store(out, _act(y, act))
 
 
+def gemm_gated(a, gate, wgt, bias, rows_per_image, residual=None, out=None, **_):
+    """include/eqxv_b200.h K5 + K11: the SE gate multiplies the A operand (product rounded to the activation dtype, as
+    the separate gate pass did), then the plain GEMM + bias (+ residual)"""
+    k = a.shape[1]
+    g = gate[:, :k].float().repeat_interleave(rows_per_image, 0)
+    ag = (a.float() * g).to(a.dtype)
+    gemm(ag, wgt, bias, 0, residual, False, out)
+
+
 def dwconv(x, wgt, bias, k, stride, pad, dil, act, out, **_):
     c = x.shape[-1]
     assert c % 8 == 0 and wgt.shape[1] >= c and bias.numel() >= c, "dwconv: channels / filter pitch"
@@ -323,7 +332,7 @@ def u8_resize_bilinear(x, oh, ow, out, **_):
     out.copy_(y.round().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1))
 
 
-IMPLS = {f.__name__: f for f in (gemm_rowstats, gemm_ln, dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
+IMPLS = {f.__name__: f for f in (gemm_gated, gemm_rowstats, gemm_ln, dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
                                  nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
                                  maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d, patchify,
                                  vit_assemble_tokens, attention, attention_probs, gather_rows, resize_bilinear,

@@ -478,3 +478,28 @@ def test_layernorm_folded_into_its_neighbour_gemms(device, m, d, n, act):
     y = ops.gemm_ln(x, wf, (b1.double() + w1.double() @ beta.double()).float(), wf.float().sum(1), stats, 1e-5, act=act)
     ref = ACTS[act](F.layer_norm(xs, (d,), gamma, beta, 1e-5) @ w1.t() + b1)
     assert rel_l2(y, ref) < 6e-3     # two bf16 roundings (filter w*gamma, output) against an fp32 reference
+
+
+@pytest.mark.parametrize("n_img,hw,k,n,res", [(3, 49, 2688, 448, False), (5, 196, 672, 112, True), (2, 3136, 192, 32, True),
+                                              (4, 12544, 48, 24, False), (7, 49, 1632, 272, True), (3, 100, 40, 24, False)])
+def test_gemm_with_se_gate_on_the_a_operand(device, n_img, hw, k, n, res):
+    """eqxv_gemm_gated_bf16: out = (a * gate[image]) @ w^T + bias (+ residual) (squeeze.py:61 + efficientnet.py:161-170).
+    Must equal the two-kernel path (eltwise gate, then GEMM) BITWISE: the in-smem product is rounded to bf16 exactly as
+    the gate pass stored it."""
+    from eqxvision_b200 import ops
+
+    m = n_img * hw
+    a = rb(device, m, k, seed=1)
+    gate = torch.sigmoid(rb(device, n_img, k, seed=2).float()).to(torch.bfloat16)
+    wt = rb(device, n, k, scale=k ** -0.5, seed=3)
+    bias = torch.randn(n, generator=torch.Generator().manual_seed(4)).to(device)
+    r = rb(device, m, n, seed=5) if res else None
+    got = ops.gemm_gated(a, gate, wt, bias, rows_per_image=hw, residual=r)
+    gated = ops.eltwise(a, gate=gate, rows_per_image=hw)
+    want = ops.gemm(gated, wt, bias, residual=r)
+    torch.cuda.synchronize()
+    ref = (a.float() * gate.float().repeat_interleave(hw, 0)).to(torch.bfloat16).float() @ wt.float().t() + bias
+    if res:
+        ref = ref + r.float()
+    assert rel_l2(got, ref) < TOL_BF16
+    assert rel_l2(got, want) < 1e-3     # (tile shapes may differ between the pair and single-CTA kernels: not bitwise)

@@ -74,8 +74,21 @@ VIT = [("qkv 768->2304", lambda: gemm_case(M, 2304, 768, 0, False), 12),
        ("fc1 768->3072 gelu", lambda: gemm_case(M, 3072, 768, 3, False), 12),
        ("fc2 3072->768 +res", lambda: gemm_case(M, 768, 3072, 0, True), 12)]
 
+MB = 128 * 112 * 112
+B4 = [("b4 s1 proj 48->24 @112", lambda: gemm_case(MB, 24, 48, 0, False), 1),
+      ("b4 s1 proj 24->24 @112 +res", lambda: gemm_case(MB, 24, 24, 0, True), 1),
+      ("b4 s2 expand 24->144 silu", lambda: gemm_case(MB, 144, 24, 2, False), 1),
+      ("b4 s2 proj 144->32 @56", lambda: gemm_case(MB // 4, 32, 144, 0, False), 1),
+      ("b4 s2 expand 32->192 silu", lambda: gemm_case(MB // 4, 192, 32, 2, False), 3),
+      ("b4 s2 proj 192->32 @56 +res", lambda: gemm_case(MB // 4, 32, 192, 0, True), 3),
+      ("b4 s3 expand 56->336 silu", lambda: gemm_case(MB // 16, 336, 56, 2, False), 3),
+      ("b4 s4 expand 112->672 silu", lambda: gemm_case(MB // 64, 672, 112, 2, False), 5),
+      ("b4 s5 expand 160->960 silu", lambda: gemm_case(MB // 64, 960, 160, 2, False), 5),
+      ("b4 s6 expand 272->1632 silu", lambda: gemm_case(MB // 256, 1632, 272, 2, False), 7)]
+
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-cases = (RESNET if which in ("resnet", "all") else []) + (VIT if which in ("vit", "all") else [])
+cases = (RESNET if which in ("resnet", "all") else []) + (VIT if which in ("vit", "all") else []) + \
+    (B4 if which in ("b4", "all") else [])
 gain = 0.0
 for name, make, count in cases:
     fn = make()
