@@ -59,6 +59,13 @@ struct alignas(64) IgemmParams {
   const float* ln_wsum;
   int ln_slots, ln_rows, off_wsum;
   float ln_inv_d, ln_eps;
+  // Direct epilogue (flat bf16 GEMMs with few K blocks and <= 32 output channels): every thread stores its row's 16-byte
+  // vectors straight to global memory and reads the residual the same way - no staging slab, no proxy fence, no TMA
+  // store / load per 32-row slab (see launch_igemm for where it wins and where it loses).
+  int direct_out;
+  __nv_bfloat16* y_ptr;
+  const __nv_bfloat16* res_ptr;
+  int y_pitch, res_pitch;
   // SqueezeExcitation gate applied to the A operand (kGate kernels, flat GEMMs): A[row, k] *= gate[row / gate_rpi, k]
   const __nv_bfloat16* gate;
   int gate_pitch, gate_rpi, gate_cols;
@@ -321,7 +328,8 @@ __device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const ui
     };
 
     uint32_t g = 0;
-    if (has_res && lane == 0) {
+    const bool tma_res = has_res && !(kLN == 0 && !kOutF32 && p.direct_out);
+    if (tma_res && lane == 0) {
       issue_res(0);
       issue_res(1);
     }
@@ -394,6 +402,25 @@ __device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const ui
         }
         const float* bias_c = s_bias + t.ncol0 + c * CH;
         uint8_t* out_row = out_g + buf * kStageBuf;
+        if constexpr (!kOutF32 && kLN == 0) {
+          if (p.direct_out) {   // CTA-uniform
+            const int col0 = t.ncol0 + c * CH;
+            if (ln_row < p.ln_rows) {
+              __nv_bfloat16* orow = p.y_ptr + (long long)ln_row * p.y_pitch + col0;
+              const __nv_bfloat16* rrow = has_res ? p.res_ptr + (long long)ln_row * p.res_pitch + col0 : nullptr;
+              uint4 rv[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                rv[j] = (has_res && col0 + j * 8 < p.cout) ? __ldg(reinterpret_cast<const uint4*>(rrow + j * 8))
+                                                           : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (col0 + j * 8 < p.cout)
+                  *reinterpret_cast<uint4*>(orow + j * 8) = epilogue8<kAct, kRes>(&v[j * 8], bias_c + j * 8, rv[j]);
+            }
+            continue;
+          }
+        }
         if constexpr (!kOutF32) {
           uint4 packed[8];
           if (has_res) mbar_wait(rbar(buf), rphase);
@@ -451,7 +478,7 @@ __device__ __forceinline__ void epilogue_warps_x4(const IgemmParams& p, const ui
           tma_store_4d(&p.tmC, out_u32 + buf * kStageBuf, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off,
                        t.n0 + n_off);
           tma_store_commit();
-          if (has_res) issue_res(g + 2);
+          if (tma_res) issue_res(g + 2);
         }
         __syncwarp();
       }
@@ -527,7 +554,8 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
     }
   };
 
-  if (has_res && lane == 0) {
+  const bool tma_res = has_res && !(!kOutF32 && p.direct_out);
+  if (tma_res && lane == 0) {
     issue_res(0);
     issue_res(1);
   }
@@ -574,6 +602,31 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
     const float* bias_c = s_bias + t.ncol0 + c * CH;
     uint8_t* out_row = out_g + ob * kSlab;
     if constexpr (!kOutF32) {
+      if (p.direct_out) {   // CTA-uniform: see IgemmParams::direct_out
+        const int col0 = t.ncol0 + c * CH;
+        const int row = (t.n0 == 0 && t.h0 == 0) ? t.w0 + so + lane : p.ln_rows;
+        if (row < p.ln_rows) {
+          __nv_bfloat16* orow = p.y_ptr + (long long)row * p.y_pitch + col0;
+          const __nv_bfloat16* rrow = has_res ? p.res_ptr + (long long)row * p.res_pitch + col0 : nullptr;
+          uint4 rv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            rv[j] = (has_res && col0 + j * 8 < p.cout) ? __ldg(reinterpret_cast<const uint4*>(rrow + j * 8))
+                                                       : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (col0 + j * 8 < p.cout)
+              *reinterpret_cast<uint4*>(orow + j * 8) = epilogue8<kAct, kRes>(&v[j * 8], bias_c + j * 8, rv[j]);
+        }
+        c += nsub;
+        while (c >= cpt) {
+          c -= cpt;
+          ++ti;
+        }
+        continue;
+      }
+    }
+    if constexpr (!kOutF32) {
       uint4 packed[8];
       if (has_res) mbar_wait(rbar(rb), rphase);
       const uint8_t* res_row = res_g + rb * kSlab;
@@ -606,7 +659,7 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
     if (lane == 0) {
       tma_store_4d(&p.tmC, out_u32 + ob * kSlab, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off, t.n0 + n_off);
       tma_store_commit();
-      if (has_res) issue_res(l + 2);
+      if (tma_res) issue_res(l + 2);
     }
     __syncwarp();
     c += nsub;
@@ -1596,6 +1649,20 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
                  q.cout);
   p.ln_stats = q.ln_stats, p.ln_wsum = q.ln_wsum, p.ln_slots = q.ln_slots, p.ln_rows = q.out_w;
   p.ln_inv_d = q.ln_inv_d, p.ln_eps = q.ln_eps;
+  // direct epilogue: flat bf16 GEMMs whose K loop is too short to hide per-slab TMA operations
+  {
+    static const int direct_env = getenv("EQXV_DIRECT_OUT") ? atoi(getenv("EQXV_DIRECT_OUT")) : -1;
+    const bool flat = q.tw == 128 && q.th == 1 && q.tn == 1 && q.kh == 1 && q.kw == 1 && !q.grouped;
+    const bool ok = flat && !out_f32 && q.ln_mode == 0 && q.cout % 8 == 0 && q.y_pitch % 8 == 0 &&
+                    (!q.res || q.res_pitch % 8 == 0);
+    // Only where a warp's 32 rows are one contiguous run in memory (cout <= 32: <= 64 bytes per row): measured on B200,
+    // wider rows turn every 16-byte store of a warp into 32 scattered sectors and the direct path LOSES to the TMA slab
+    // (ResNet-50 layer1 c1/c3, K = 64: 3.33 -> 4.13 ms per step; EfficientNet 24 -> 144: 303 -> 389 us), while the
+    // 24-channel projections gain (192 -> 159 us, 107 -> 97 us; what remains there is the TMA fetching 48-byte rows).
+    p.direct_out = ok && (direct_env >= 0 ? direct_env != 0 : (kblocks <= 3 && q.cout <= 32)) ? 1 : 0;
+    p.y_ptr = static_cast<__nv_bfloat16*>(q.y), p.res_ptr = static_cast<const __nv_bfloat16*>(q.res);
+    p.y_pitch = q.y_pitch, p.res_pitch = q.res_pitch;
+  }
   if (q.gate) {
     EQXV_CHECK_ARG(q.tw == 128 && q.th == 1 && q.tn == 1 && q.kh == 1 && q.kw == 1 && !out_f32 && !q.grouped &&
                        q.ln_mode == 0 && q.act == EQXV_ACT_NONE && !(q.flags & EQXV_FLAG_RES_AFTER_ACT),
