@@ -7,7 +7,9 @@
 
 namespace eqxv {
 
-// One CTA = one (window, image); loops over the heads. qkv rows are in SPATIAL order
+// One CTA = one (window, image, head group): blockIdx.z picks a contiguous slice of the heads (one head per CTA when the
+// grid would otherwise be small: the last Swin stage has ONE window per image and 24 heads - looping over them inside
+// 64 CTAs left most of the 148 SMs idle: 660 us per launch at batch 64). qkv rows are in SPATIAL order
 // (row = (img*H + y)*W + x), columns ordered (3, heads, head_dim) as produced by reshape(..,3,heads,d)
 // (swin.py:166-171). A window token (i) of window (wr, wc) sits at rolled position
 // (wr*ws + i/ws, wc*ws + i%ws), i.e. at source pixel ((r + shift) % H, (c + shift) % W) (jnp.roll by
@@ -43,7 +45,9 @@ __global__ void __launch_bounds__(128) window_attention_kernel(
   }
   __syncthreads();
   const long long img_row0 = (long long)img * H * W;
-  for (int h = 0; h < heads; ++h) {
+  const int hpb = (heads + gridDim.z - 1) / gridDim.z;       // heads per CTA
+  const int h_begin = blockIdx.z * hpb, h_end = min(heads, h_begin + hpb);
+  for (int h = h_begin; h < h_end; ++h) {
     // ---- load q, k, v of this head (bf16 -> fp32 smem) ----
     for (int e = tid; e < T * (HD / 2); e += blockDim.x) {
       const int i = e / (HD / 2), d2 = e % (HD / 2);
@@ -204,7 +208,12 @@ extern "C" int eqxv_window_attention_bf16(const void* qkv, const float* bias, vo
     EQXV_CUDA(cudaFuncSetAttribute(window_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     attr = true;
   }
-  dim3 grid((unsigned)((h / window) * (w / window)), (unsigned)n);
+  // split the heads over blockIdx.z until the grid fills the machine a few times over
+  const long long wn = (long long)(h / window) * (w / window) * n;
+  int zsplit = 1;
+  while (zsplit < heads && wn * zsplit < 8ll * device_sm_count()) ++zsplit;
+  while (heads % zsplit != 0) ++zsplit;
+  dim3 grid((unsigned)((h / window) * (w / window)), (unsigned)n, (unsigned)zsplit);
   EQXV_CUDA(launch_kernel(window_attention_kernel<32>, dim3(grid), dim3(128), (size_t)(smem), (cudaStream_t)stream, 
       (const __nv_bfloat16*)qkv, bias, (__nv_bfloat16*)out, h, w, heads, window, shift_h, shift_w, scale));
   EQXV_CUDA(cudaGetLastError());
