@@ -48,6 +48,7 @@ struct alignas(64) IgemmParams {
   int b_resident;   // halo kernel: the whole packed filter stays in the B ring (loaded once per CTA)
   int grouped;      // 1: block-diagonal grouped conv, the A channel offset follows the n-tile (block_n == 64)
   int epi_sub;      // epilogue warps per TMEM lane quadrant (1 or 2): blockDim = 64 + 128 * epi_sub
+  int epi_obufs;    // output staging slabs per epilogue warp (eight-warp epilogue: 1, or 2 where shared memory allows)
   // shared-memory carve-up (byte offsets from the 1024-aligned base)
   int off_out, off_res, off_bias, off_bars;
   // LayerNorm folded into the GEMMs on either side of it (flat GEMMs only, kLN template parameter):
@@ -527,7 +528,7 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
   const int so = quad * 32;
   const int w_off = so % p.tw, h_off = (so / p.tw) % p.th, n_off = so / (p.tw * p.th);
   constexpr uint32_t kSlab = 32 * 128;  // 4 KiB: 32 rows x 128 B
-  const uint32_t obufs = 2u / (uint32_t)nsub;                       // staging buffers of this warp (8 slabs in all)
+  const uint32_t obufs = p.epi_obufs > 0 ? (uint32_t)p.epi_obufs : 2u / (uint32_t)nsub;   // staging slabs of this warp
   const uint32_t out_u32 = base + p.off_out + (uint32_t)wid * obufs * kSlab;
   uint8_t* out_g = gbase + p.off_out + (uint32_t)wid * obufs * kSlab;
   const uint32_t res_u32 = base + p.off_res + (uint32_t)wid * 2u * kSlab;   // residual ring: 2 slabs per warp
@@ -1687,13 +1688,28 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : (kblocks <= 4 ? 2 : 1);
   if (q.ln_mode != 0) p.epi_sub = 1;   // the folding lives in the four-warp epilogue
   if (q.gate) p.epi_sub = 1;           // warps 6..9 scale the A tiles
-  const int fixed = 2 * kStageBuf + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
+  // eight-warp epilogue: ONE staging slab per warp means every chunk waits until the TMA store of the previous chunk
+  // has finished reading it; with a second slab (32 KiB more, one pipeline stage less) the store of chunk l overlaps the
+  // math of chunk l+1. Worth it where the epilogue bounds the layer and the K loop is short (ResNet c3 layers).
+  static const int obuf_env = getenv("EQXV_EPI_OBUFS") ? atoi(getenv("EQXV_EPI_OBUFS")) : 0;
+  int out_bytes = 2 * kStageBuf;
+  p.epi_obufs = 0;
+  // Measured on ResNet-50 (A/B in one call, 3.457 vs 3.43 ms per step): no gain - the c3 layers are not waiting on
+  // their staging slab - so the second slab stays opt-in (EQXV_EPI_OBUFS=2).
+  if (p.epi_sub == 2 && obuf_env == 2) {
+    const int fixed2 = 4 * kStageBuf + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
+    if ((kMaxSmem - 1024 - fixed2) / stage_bytes >= 3) {
+      out_bytes = 4 * kStageBuf;
+      p.epi_obufs = 2;
+    }
+  }
+  const int fixed = out_bytes + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
   int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
   stages = std::min(stages, 8);
   EQXV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for block_n=%d", block_n);
   p.stages = stages;
   p.off_out = stages * stage_bytes;
-  p.off_res = p.off_out + 2 * kStageBuf;
+  p.off_res = p.off_out + out_bytes;
   p.off_bias = p.off_res + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0);
   p.off_wsum = p.off_bias + bias_one;
   p.off_bars = p.off_bias + bias_bytes;

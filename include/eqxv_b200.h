@@ -228,6 +228,9 @@ int eqxv_resize_bilinear_nhwc_bf16(const void* x, void* y, int32_t n, int32_t c,
  * arithmetic. qkv: [n*h*w, 3*heads*32] in spatial row order, columns (3, heads, 32); bias: fp32
  * [heads, window^2, window^2] = relative_position_bias_table[relative_position_index] (swin.py:46-57);
  * out: [n*h*w, heads*32]. */
+/* Implementation: tcgen05 - two windows x one head form one 128-row MMA tile (q k^T: M=128, N=128, K=32; p v: M=128, N=32,
+ * K=128) on operand tiles the CTA gathers into 128B-swizzled shared memory itself; softmax one thread per row.
+ * EQXV_WATTN_TC=0 selects the CUDA-core kernel (A/B reference). */
 int eqxv_window_attention_bf16(const void* qkv, const float* bias, void* out, int32_t n, int32_t h, int32_t w,
                                int32_t heads, int32_t head_dim, int32_t window, int32_t shift_h,
                                int32_t shift_w, float scale, void* stream);

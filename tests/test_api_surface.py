@@ -316,7 +316,9 @@ def test_regnet_block_params_and_lowering():
         BlockParams.from_init_params(depth=4, w_0=50, w_a=1.0, w_m=2.0, group_width=8)   # w_0 % 8 != 0
     out, plan, steps = lower(eb.tree_inference(models.regnet_y_400mf(), True))
     assert out.shape == (1000,)
-    assert steps["conv2d"] == 16 * 3 + 4 + 16 * 2 and steps["eltwise"] == 16     # 3 convs/block, 4 proj, SE fc1/fc2
+    # 3 convs/block, 4 proj, SE fc1/fc2; in the first block of each stage the SE gate rides in the conv that follows
+    # it (no activation on that conv: the shortcut add sits in the projection's epilogue) -> eqxv_gemm_gated_bf16
+    assert steps["conv2d"] == 16 * 3 + 4 + 16 * 2 - 4 and steps["gemm_gated"] == 4 and steps["eltwise"] == 12
 
 
 def test_grouped_weight_dense_expansion():
