@@ -40,12 +40,24 @@ class ConvDesc(C.Structure):
     ]
 
 
+class Bottleneck64Desc(C.Structure):
+    _fields_ = [
+        ("t1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("residual", C.c_void_p), ("x0", C.c_void_p), ("y", C.c_void_p), ("w1n", C.c_void_p), ("b1n", C.c_void_p),
+        ("next", C.c_void_p),
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("t1_pitch", C.c_int32), ("res_pitch", C.c_int32), ("x0_pitch", C.c_int32), ("y_pitch", C.c_int32),
+        ("next_pitch", C.c_int32),
+    ]
+
+
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> argtypes; every function returns int status unless listed in _NON_STATUS
 SIGNATURES = {
     "eqxv_init": [C.c_int],
     "eqxv_conv2d_igemm_bf16": [C.POINTER(ConvDesc), _vp],
+    "eqxv_bottleneck64_fused_bf16": [C.POINTER(Bottleneck64Desc), _vp],
     "eqxv_gemm_bias_act_res_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
     "eqxv_gemm_res_rowstats_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp],
     "eqxv_gemm_ln_act_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _i64, _i64, _i32, _i32, _i32, _vp],
@@ -115,7 +127,7 @@ _initialised_device = None
 launch_count = 0  # number of kernel-launching C-ABI calls made by this process (bench bookkeeping)
 
 _LAUNCHING = {
-    "eqxv_conv2d_igemm_bf16", "eqxv_gemm_bias_act_res_bf16", "eqxv_conv_stem_bf16",
+    "eqxv_conv2d_igemm_bf16", "eqxv_bottleneck64_fused_bf16", "eqxv_gemm_bias_act_res_bf16", "eqxv_conv_stem_bf16",
     "eqxv_pack_stem_input", "eqxv_nchw_f32_to_nhwc_bf16", "eqxv_nhwc_bf16_to_nchw_f32",
     "eqxv_maxpool2d_nhwc_bf16", "eqxv_maxpool2d_ceil_nhwc_bf16", "eqxv_avgpool2d_nhwc_bf16", "eqxv_adaptive_avgpool_nhwc_bf16",
     "eqxv_layernorm_bf16", "eqxv_attention_fwd_bf16", "eqxv_patchify_nchw_f32_bf16",

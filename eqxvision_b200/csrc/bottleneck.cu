@@ -1,0 +1,467 @@
+// ResNet bottleneck (64-channel trunk, stride 1) as ONE kernel on a CTA pair: resnet.py:144-162 composed over
+// resnet.py:288-296 (layer1 of ResNet-50/101/152).
+//
+//   t1  --3x3 conv + BN + ReLU-->  t2  --1x1 conv + BN (+ identity | + downsample(x0)) + ReLU-->  y
+//                                                        y  --next block's 1x1 conv + BN + ReLU-->  t1'
+//
+// Layer by layer these tensors cross HBM seven times per block (t2 written + read, y written, read as the next block's
+// c1 input and again as its residual, the 256-channel downsample output written + read); at batch 256 that is 1.1 ms of
+// a 3.4 ms ResNet-50 step, every layer already at its own HBM roofline (profiles/r01_layer_roofline_v20.txt). Here t2
+// never leaves the SM, y is written once and consumed in place by the next block's c1, and the downsample of the first
+// block is two more K blocks of the c3 accumulation.
+//
+// One CTA pair (cta_group::2, one TPC) owns two 8 x 16 pixel tiles; the three filters stay resident, split between the
+// two CTAs along N (each CTA holds HALF of every filter: 36 + 16..32 + 16 KiB), which is what makes them fit next to
+// the tiles. Per tile and CTA:
+//   c2   9 taps x 4 UMMA (M 256, N 64, K 16) on ONE halo tile of t1 (10 x 18 pixels x 64 ch, a single 4-D TMA box; tap
+//        (r, s) is the same 128B-swizzled tile through a descriptor shifted by r*10 + s rows, SBO = one halo row)
+//        -> D2 (TMEM, 64 columns)
+//   e2   epilogue warps: D2 + b2 -> ReLU -> bf16 -> the A operand of c3, written over the consumed halo tile
+//   c3   4 UMMA (N 256) [+ 4 more on the x0 tile with the downsample filter] -> D3 (256 columns)
+//   e3   D3 + b3 (+ residual, TMA-prefetched INTO the output tile) -> ReLU -> bf16 -> output tile (4 x [128 x 64] SW128
+//        chunks) -> TMA store of y; the same tile is the A operand of
+//   c1'  16 UMMA (N 64, K 256) -> D1 (64 columns)
+//   e4   D1 + b1' -> ReLU -> bf16 -> t1' (16-byte global stores, 128 contiguous bytes per thread)
+// The issuer runs c2 of tile i+1 behind c3 of tile i, so the tensor pipe works through e3.
+// Hand-offs: TMA -> issuer and issuer -> epilogue by mbarrier (tcgen05.commit multicast to both CTAs); epilogue ->
+// issuer (operand tiles written with st.shared in BOTH CTAs, each consumed by its own SM's tensor core under the leader's
+// MMAs) by fence.proxy.async + a plain arrive on the leader's barrier. (An arrive.release.cluster here compiles to
+// MEMBAR.ALL + ERRBAR per thread and cost 19 % of the kernel's stall samples, profiles/r02_ncu_bneck_v1.txt; the data
+// never crosses SMs, only the notification does.)
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+#include "ptx.cuh"
+#include "epilogue.cuh"
+
+namespace eqxv {
+
+constexpr int kBnThreads = 320;                          // warp 0 TMA, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int kHaloW = 10, kHaloH = 18;                  // halo of an 8 x 16 tile under a 3x3 filter
+constexpr uint32_t kT1Bytes = kHaloW * kHaloH * 128;     // 23040
+constexpr uint32_t kT1Slot = 23552;                      // rounded up to 1 KiB (swizzle atoms stay aligned)
+constexpr uint32_t kTile = 16384;                        // 128 rows x 128 B
+constexpr uint32_t kW2Tap = 32 * 128;                    // this CTA's half (32 of 64 filter rows) of one tap
+constexpr int kBnMaxSmem = 232448;
+
+struct alignas(64) BneckParams {
+  CUtensorMap tmT1, tmX0, tmW2, tmW3, tmW1, tmY, tmR;
+  const float *b2, *b3, *b1n;
+  __nv_bfloat16* next_out;
+  int next_pitch;
+  int tiles_w, tiles_h, num_mtiles, num_pairs;
+  int n, h, w;
+  int w3_chunks;   // 1, or 2 with the downsample filter concatenated along K
+  uint32_t off_w3, off_w1, off_t1, off_x0, off_y, off_bias, off_bars;
+};
+
+struct BnTile {
+  int w0, h0, n0;
+};
+__device__ __forceinline__ BnTile bn_decode(const BneckParams& p, int m) {
+  BnTile t;
+  t.w0 = (m % p.tiles_w) * 8;
+  m /= p.tiles_w;
+  t.h0 = (m % p.tiles_h) * 16;
+  t.n0 = m / p.tiles_h;   // >= p.n for the phantom tile of an odd count: TMA zero-fills / clips, direct stores check
+  return t;
+}
+
+// barrier slots (8 bytes each from off_bars)
+enum : uint32_t {
+  kBarW = 0, kBarT1Full = 1, kBarT1Empty = 3, kBarX0Full = 5, kBarX0Empty = 6, kBarD2Full = 7, kBarA3Full = 8,
+  kBarD3Full = 9, kBarYFull = 10, kBarD1Full = 11, kBarTmemSlot = 12, kBarRes = 16   // + (warp - 2) * 2 + k
+};
+
+template <bool kDown, bool kNext>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
+    bneck_kernel(const __grid_constant__ BneckParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = blockIdx.x & 1u;   // == %cluster_ctarank for a (2,1,1) cluster
+  const uint32_t bars = base + p.off_bars;
+  auto bar = [&](uint32_t i) { return bars + 8u * i; };
+  const uint32_t w2_s = base, w3_s = base + p.off_w3, w1_s = base + p.off_w1, t1_s = base + p.off_t1,
+                 x0_s = base + p.off_x0, y_s = base + p.off_y;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * kBarTmemSlot);
+  float* s_bias = reinterpret_cast<float*>(gbase + p.off_bias);   // [b2 64][b3 256][b1' 64]
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmT1);
+    tma_prefetch_desc(&p.tmW2);
+    tma_prefetch_desc(&p.tmW3);
+    tma_prefetch_desc(&p.tmY);
+    if (kDown) tma_prefetch_desc(&p.tmX0); else tma_prefetch_desc(&p.tmR);
+    if (kNext) tma_prefetch_desc(&p.tmW1);
+    mbar_init(bar(kBarW), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(kBarT1Full + s), 1);    // leader: its producer's arrive.expect_tx (both CTAs' bytes)
+      mbar_init(bar(kBarT1Empty + s), 1);   // one multicast commit per use
+    }
+    mbar_init(bar(kBarX0Full), 1);
+    mbar_init(bar(kBarX0Empty), 1);
+    mbar_init(bar(kBarD2Full), 1);
+    mbar_init(bar(kBarA3Full), 512);        // leader: the 2 x 256 epilogue threads of the pair
+    mbar_init(bar(kBarD3Full), 1);
+    mbar_init(bar(kBarYFull), 512);
+    mbar_init(bar(kBarD1Full), 1);
+    for (int b = 0; b < 16; ++b) mbar_init(bar(kBarRes + b), 1);
+    mbar_fence_init();
+    // The filters are constants of the plan (not written by the preceding kernel): fetched before the PDL wait.
+    const uint32_t wbytes = 9u * kW2Tap + (uint32_t)p.w3_chunks * kTile + (kNext ? 4u * kW2Tap : 0u);
+    mbar_expect_tx(bar(kBarW), wbytes);
+    for (int tap = 0; tap < 9; ++tap) tma_load_2d(w2_s + tap * kW2Tap, &p.tmW2, bar(kBarW), tap * 64, (int)rank * 32);
+    for (int k = 0; k < p.w3_chunks; ++k) tma_load_2d(w3_s + k * kTile, &p.tmW3, bar(kBarW), k * 64, (int)rank * 128);
+    if (kNext)
+      for (int k = 0; k < 4; ++k) tma_load_2d(w1_s + k * kW2Tap, &p.tmW1, bar(kBarW), k * 64, (int)rank * 32);
+  }
+  for (int i = threadIdx.x; i < 384; i += blockDim.x) {
+    float v = 0.f;
+    if (i < 64) v = __ldg(p.b2 + i);
+    else if (i < 320) v = __ldg(p.b3 + (i - 64));
+    else if (kNext) v = __ldg(p.b1n + (i - 320));
+    s_bias[i] = v;
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(bar(kBarTmemSlot), 512u);
+    tmem_relinquish_pair();
+  }
+  griddep_wait();     // PDL: everything above overlapped the previous kernel's tail
+  tc_fence_before();
+  __syncthreads();
+  griddep_launch();
+  mbar_wait(bar(kBarW), 0u);   // this CTA's filter halves have landed
+  cluster_sync_all();          // ... and the peer's; its barriers are initialised before anything is signalled remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const uint32_t d2_t = tmem_base, d1_t = tmem_base + 64u, d3_t = tmem_base + 256u;
+  const int p_first = (int)(blockIdx.x >> 1), p_stride = (int)(gridDim.x >> 1);
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs, one thread) ==============================
+    if (elect_one()) {
+      int slot = 0;
+      uint32_t ph = 0, xph = 0;
+      for (int pi = p_first; pi < p.num_pairs; pi += p_stride) {
+        const BnTile t = bn_decode(p, 2 * pi + (int)rank);
+        mbar_wait(bar(kBarT1Empty + slot), ph ^ 1u);
+        if (rank == 0) mbar_expect_tx(bar(kBarT1Full + slot), 2u * kT1Bytes);   // both CTAs' bytes land on this barrier
+        tma_load_4d_pair(t1_s + slot * kT1Slot, &p.tmT1, bar(kBarT1Full + slot), 0, t.w0 - 1, t.h0 - 1, t.n0);
+        if (kDown) {
+          mbar_wait(bar(kBarX0Empty), xph ^ 1u);
+          if (rank == 0) mbar_expect_tx(bar(kBarX0Full), 2u * kTile);
+          tma_load_4d_pair(x0_s, &p.tmX0, bar(kBarX0Full), 0, t.w0, t.h0, t.n0);
+          xph ^= 1u;
+        }
+        if (++slot == 2) {
+          slot = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer (leader CTA, one thread) ==============================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc64 = umma_idesc_bf16_m256(64u), idesc256 = umma_idesc_bf16_m256(256u);
+      const uint32_t k_hi = (uint32_t)(umma_desc_sw128(0) >> 32);   // plain 128B-swizzled K-major tile
+      // halo view: 8-row groups strided by one halo row (SBO = 10 x 128 B), see halo_kernel in igemm.cu
+      const uint32_t halo_hi = ((uint32_t)(kHaloW * 128) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t lbo = 1u << 16;
+      auto lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | lbo; };
+      const uint32_t w2_lo = lo(w2_s), w3_lo = lo(w3_s), w1_lo = lo(w1_s), x0_lo = lo(x0_s), y_lo = lo(y_s);
+      auto issue_c2 = [&](int slot) {
+        const uint32_t a0 = lo(t1_s + (uint32_t)slot * kT1Slot);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            umma_bf16_kblock64_pair_nc(d2_t, a0 + (uint32_t)(r * kHaloW + s) * 8u,
+                                       w2_lo + (uint32_t)(r * 3 + s) * (kW2Tap >> 4), halo_hi, k_hi, idesc64,
+                                       (r | s) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit_pair(bar(kBarD2Full));
+      };
+      int slot = 0;
+      uint32_t tph = 0;                 // parity of the once-per-tile barriers
+      uint32_t fph[2] = {0u, 0u};       // parity of t1full[slot]
+      bool first = true;
+      for (int pi = p_first; pi < p.num_pairs; pi += p_stride) {
+        if (first) {
+          mbar_wait(bar(kBarT1Full + 0), fph[0]);
+          fph[0] ^= 1u;
+          tc_fence_after();
+          issue_c2(0);
+          first = false;
+        }
+        // c3 (+ downsample): A = the bf16 tile the epilogue wrote over the consumed halo tile
+        mbar_wait(bar(kBarA3Full), tph);
+        if (kDown) mbar_wait(bar(kBarX0Full), tph);
+        tc_fence_after();
+        umma_bf16_kblock64_pair_nc(d3_t, lo(t1_s + (uint32_t)slot * kT1Slot), w3_lo, k_hi, k_hi, idesc256, 0u);
+        if (kDown) umma_bf16_kblock64_pair_nc(d3_t, x0_lo, w3_lo + (kTile >> 4), k_hi, k_hi, idesc256, 1u);
+        umma_commit_pair(bar(kBarT1Empty + slot));
+        if (kDown) umma_commit_pair(bar(kBarX0Empty));
+        umma_commit_pair(bar(kBarD3Full));
+        // c2 of the next tile runs while the epilogue warps work through D3
+        if (pi + p_stride < p.num_pairs) {
+          const int ns = slot ^ 1;
+          mbar_wait(bar(kBarT1Full + ns), fph[ns]);
+          fph[ns] ^= 1u;
+          tc_fence_after();
+          issue_c2(ns);
+        }
+        if (kNext) {
+          // next block's c1: A = the finished output tile (4 K chunks), still in shared memory
+          mbar_wait(bar(kBarYFull), tph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_kblock64_pair_nc(d1_t, y_lo + (uint32_t)k * (kTile >> 4), w1_lo + (uint32_t)k * (kW2Tap >> 4), k_hi,
+                                       k_hi, idesc64, k != 0 ? 1u : 0u);
+          umma_commit_pair(bar(kBarD1Full));
+        }
+        slot ^= 1;
+        tph ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== epilogue (warps 2..9, both CTAs) ==============================
+    // Two warps per TMEM lane quadrant: `sub` picks the column half (e2, e4) / the 64-column chunks {sub, sub + 2} (e3).
+    // Thread <-> accumulator row r = 32 q + lane <-> pixel (h0 + r / 8, w0 + r % 8).
+    const int q = warp & 3, sub = (warp - 2) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int r = q * 32 + lane;
+    const int h_loc = r >> 3, w_loc = r & 7;
+    auto rbar = [&](int k) { return bar(kBarRes + (uint32_t)(warp - 2) * 2u + (uint32_t)k); };
+    auto slab_off = [&](int k) { return (uint32_t)(sub + 2 * k) * kTile + (uint32_t)q * 4096u; };   // 32 rows x 128 B
+    auto issue_res = [&](const BnTile& t) {   // ONE lane: this warp's two residual slabs, straight into the output tile
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        mbar_expect_tx(rbar(k), 4096u);
+        tma_load_4d(y_s + slab_off(k), &p.tmR, rbar(k), (sub + 2 * k) * 64, t.w0, t.h0 + 4 * q, t.n0);
+      }
+    };
+    uint32_t tph = 0;
+    int slot = 0;
+    if (!kDown && lane == 0 && p_first < p.num_pairs) issue_res(bn_decode(p, 2 * p_first + (int)rank));
+    __syncwarp();
+    for (int pi = p_first; pi < p.num_pairs; pi += p_stride) {
+      const BnTile t = bn_decode(p, 2 * pi + (int)rank);
+      // ---------------- e2: D2 -> A operand of c3 ----------------
+      mbar_wait(bar(kBarD2Full), tph);
+      tc_fence_after();
+      {
+        float v[32];
+        tmem_ld_x16(d2_t + lane_base + (uint32_t)(32 * sub), &v[0]);
+        tmem_ld_x16(d2_t + lane_base + (uint32_t)(32 * sub + 16), &v[16]);
+        tmem_ld_wait();
+        tc_fence_before();
+        uint8_t* a3 = gbase + p.off_t1 + (uint32_t)slot * kT1Slot;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 o = epilogue8<EQXV_ACT_RELU, 0>(&v[8 * j], s_bias + 32 * sub + 8 * j, make_uint4(0u, 0u, 0u, 0u));
+          *reinterpret_cast<uint4*>(a3 + sw128_off((uint32_t)r, (uint32_t)(4 * sub + j))) = o;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive_leader(bar(kBarA3Full));
+      }
+      // ---------------- e3: D3 (+ residual) -> y ----------------
+      mbar_wait(bar(kBarD3Full), tph);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int c = sub + 2 * k;
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmem_ld_x16(d3_t + lane_base + (uint32_t)(64 * c + 16 * j), &v[16 * j]);
+        tmem_ld_wait();
+        if (k == 1) tc_fence_before();
+        uint8_t* slab = gbase + p.off_y + slab_off(k);
+        if (!kDown) mbar_wait(rbar(k), tph);   // the residual slab has landed
+        uint4 packed[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+          if (!kDown) rv = *reinterpret_cast<const uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)j));
+          packed[j] = epilogue8<EQXV_ACT_RELU, kDown ? 0 : 1>(&v[8 * j], s_bias + 64 + 64 * c + 8 * j, rv);
+        }
+        if (kDown) {
+          // no residual load orders this: the TMA store that last read the slab must be done before it is rewritten
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)j)) = packed[j];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&p.tmY, y_s + slab_off(k), c * 64, t.w0, t.h0 + 4 * q, t.n0);
+          tma_store_commit();
+        }
+        __syncwarp();
+      }
+      if (kNext) mbar_arrive_leader(bar(kBarYFull));
+      // ---------------- e4: D1 -> t1' of the next block; residual prefetch for the next tile ----------------
+      float v1[32];
+      if (kNext) {
+        mbar_wait(bar(kBarD1Full), tph);   // c1' has consumed the output tile
+        tc_fence_after();
+        tmem_ld_x16(d1_t + lane_base + (uint32_t)(32 * sub), &v1[0]);
+        tmem_ld_x16(d1_t + lane_base + (uint32_t)(32 * sub + 16), &v1[16]);
+      }
+      if (!kDown && pi + p_stride < p.num_pairs) {
+        if (lane == 0) {
+          tma_store_wait_read<0>();   // this warp's stores have read their slabs
+          issue_res(bn_decode(p, 2 * (pi + p_stride) + (int)rank));
+        }
+        __syncwarp();
+      }
+      if (kNext) {
+        tmem_ld_wait();
+        tc_fence_before();
+        const int hh = t.h0 + h_loc, ww = t.w0 + w_loc;
+        if (t.n0 < p.n && hh < p.h && ww < p.w) {
+          __nv_bfloat16* orow = p.next_out + (((long long)t.n0 * p.h + hh) * p.w + ww) * p.next_pitch + 32 * sub;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(orow + 8 * j) =
+                epilogue8<EQXV_ACT_RELU, 0>(&v1[8 * j], s_bias + 320 + 32 * sub + 8 * j, make_uint4(0u, 0u, 0u, 0u));
+        }
+      }
+      slot ^= 1;
+      tph ^= 1u;
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
+  }
+
+  // ---- teardown: neither CTA may leave while its peer can still touch its smem / TMEM / barriers ----
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512u);
+  }
+}
+
+using BneckFn = void (*)(const BneckParams);
+static BneckFn bneck_table(bool down, bool next) {
+  static const BneckFn t[2][2] = {{bneck_kernel<false, false>, bneck_kernel<false, true>},
+                                  {bneck_kernel<true, false>, bneck_kernel<true, true>}};
+  return t[down ? 1 : 0][next ? 1 : 0];
+}
+
+int bottleneck_init() {
+  for (int d = 0; d < 2; ++d)
+    for (int n = 0; n < 2; ++n)
+      EQXV_CUDA(cudaFuncSetAttribute(bneck_table(d, n), cudaFuncAttributeMaxDynamicSharedMemorySize, kBnMaxSmem));
+  return EQXV_OK;
+}
+
+static int map4d(CUtensorMap* m, const void* ptr, int c, int w, int h, int n, int pitch, int bw, int bh) {
+  TmapSpec s{};
+  s.base = const_cast<void*>(ptr);
+  s.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  s.rank = 4;
+  s.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+  s.dims[0] = (uint64_t)c, s.dims[1] = (uint64_t)w, s.dims[2] = (uint64_t)h, s.dims[3] = (uint64_t)n;
+  s.strides_bytes[0] = (uint64_t)pitch * 2;
+  s.strides_bytes[1] = s.strides_bytes[0] * (uint64_t)w;
+  s.strides_bytes[2] = s.strides_bytes[1] * (uint64_t)h;
+  s.box[0] = 64, s.box[1] = (uint32_t)bw, s.box[2] = (uint32_t)bh, s.box[3] = 1;
+  s.estride[0] = s.estride[1] = s.estride[2] = s.estride[3] = 1;
+  return encode_tmap(m, s);
+}
+static int map2d(CUtensorMap* m, const void* ptr, int k, int rows, int box_rows) {
+  TmapSpec s{};
+  s.base = const_cast<void*>(ptr);
+  s.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  s.rank = 2;
+  s.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
+  s.dims[0] = (uint64_t)k, s.dims[1] = (uint64_t)rows;
+  s.strides_bytes[0] = (uint64_t)k * 2;
+  s.box[0] = 64, s.box[1] = (uint32_t)box_rows;
+  s.estride[0] = s.estride[1] = 1;
+  return encode_tmap(m, s);
+}
+
+}  // namespace eqxv
+
+using namespace eqxv;
+
+extern "C" int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, void* stream) {
+  EQXV_CHECK_ARG(d != nullptr, "bottleneck: null descriptor");
+  EQXV_CHECK_ARG(d->t1 && d->w2 && d->b2 && d->w3 && d->b3 && d->y, "bottleneck: null tensor pointer");
+  EQXV_CHECK_ARG((d->residual != nullptr) != (d->x0 != nullptr),
+                 "bottleneck: exactly one of residual (identity shortcut) / x0 (downsample input) must be given");
+  EQXV_CHECK_ARG((d->w1n != nullptr) == (d->next != nullptr) && (d->w1n != nullptr) == (d->b1n != nullptr),
+                 "bottleneck: w1n, b1n and next go together");
+  EQXV_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0, "bottleneck: bad shape");
+  const bool down = d->x0 != nullptr, next = d->next != nullptr;
+  auto ok_ptr = [](const void* p_) { return ((uintptr_t)p_ & 15) == 0; };
+  EQXV_CHECK_ARG(ok_ptr(d->t1) && ok_ptr(d->w2) && ok_ptr(d->w3) && ok_ptr(d->y) && ok_ptr(d->residual) &&
+                     ok_ptr(d->x0) && ok_ptr(d->w1n) && ok_ptr(d->next),
+                 "bottleneck: pointers must be 16-byte aligned");
+  EQXV_CHECK_ARG(d->t1_pitch >= 64 && d->t1_pitch % 8 == 0 && d->y_pitch >= 256 && d->y_pitch % 8 == 0,
+                 "bottleneck: bad t1 / y pitch");
+  if (down) EQXV_CHECK_ARG(d->x0_pitch >= 64 && d->x0_pitch % 8 == 0, "bottleneck: bad x0 pitch");
+  else EQXV_CHECK_ARG(d->res_pitch >= 256 && d->res_pitch % 8 == 0, "bottleneck: bad residual pitch");
+  if (next) EQXV_CHECK_ARG(d->next_pitch >= 64 && d->next_pitch % 8 == 0, "bottleneck: bad next pitch");
+
+  BneckParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = d->n, p.h = d->h, p.w = d->w;
+  p.tiles_w = ceil_div(d->w, 8), p.tiles_h = ceil_div(d->h, 16);
+  const long long mt = (long long)p.tiles_w * p.tiles_h * d->n;
+  EQXV_CHECK_ARG(mt < (1ll << 30), "bottleneck: too many tiles");
+  p.num_mtiles = (int)mt;
+  p.num_pairs = (int)((mt + 1) / 2);
+  p.b2 = d->b2, p.b3 = d->b3, p.b1n = d->b1n;
+  p.next_out = static_cast<__nv_bfloat16*>(d->next), p.next_pitch = d->next_pitch;
+  p.w3_chunks = down ? 2 : 1;
+  uint32_t off = 9u * kW2Tap;
+  p.off_w3 = off, off += (uint32_t)p.w3_chunks * kTile;
+  p.off_w1 = off, off += next ? 4u * kW2Tap : 0u;
+  p.off_t1 = off, off += 2u * kT1Slot;
+  p.off_x0 = off, off += down ? kTile : 0u;
+  p.off_y = off, off += 4u * kTile;
+  p.off_bias = off, off += 2048u;
+  p.off_bars = off, off += 512u;
+  const size_t smem_bytes = (size_t)off + 1024;
+  EQXV_CHECK_ARG(smem_bytes <= (size_t)kBnMaxSmem, "bottleneck: shared memory budget exceeded (%zu)", smem_bytes);
+
+  int rc = map4d(&p.tmT1, d->t1, 64, d->w, d->h, d->n, d->t1_pitch, kHaloW, kHaloH);
+  if (rc) return rc;
+  if (down) {
+    rc = map4d(&p.tmX0, d->x0, 64, d->w, d->h, d->n, d->x0_pitch, 8, 16);
+    if (rc) return rc;
+  } else {
+    rc = map4d(&p.tmR, d->residual, 256, d->w, d->h, d->n, d->res_pitch, 8, 4);
+    if (rc) return rc;
+  }
+  rc = map4d(&p.tmY, d->y, 256, d->w, d->h, d->n, d->y_pitch, 8, 4);
+  if (rc) return rc;
+  rc = map2d(&p.tmW2, d->w2, 9 * 64, 64, 32);
+  if (rc) return rc;
+  rc = map2d(&p.tmW3, d->w3, down ? 128 : 64, 256, 128);
+  if (rc) return rc;
+  if (next) {
+    rc = map2d(&p.tmW1, d->w1n, 256, 64, 32);
+    if (rc) return rc;
+  }
+  const int clusters = std::min(p.num_pairs, device_sm_count() / 2);
+  EQXV_CUDA(launch_kernel(bneck_table(down, next), dim3(2 * clusters), dim3(kBnThreads), smem_bytes,
+                          (cudaStream_t)stream, p));
+  EQXV_CUDA(cudaGetLastError());
+  return EQXV_OK;
+}

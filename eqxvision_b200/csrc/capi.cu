@@ -69,6 +69,7 @@ int encode_tmap(CUtensorMap* out, const TmapSpec& s) {
 
 int igemm_init();
 int attention_init();
+int bottleneck_init();
 
 }  // namespace eqxv
 
@@ -109,6 +110,8 @@ extern "C" int eqxv_init(int device) {
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
   int rc = igemm_init();
+  if (rc) return rc;
+  rc = bottleneck_init();
   if (rc) return rc;
   rc = attention_init();
   if (rc) return rc;

@@ -435,6 +435,73 @@ __device__ __forceinline__ void umma_bf16_kblock64_pair(uint32_t tmem_d, uint32_
       "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(commit_bar)
       : "memory");
 }
+// Same four pair MMAs without the commit (operands that stay resident / are released by a later commit).
+__device__ __forceinline__ void umma_bf16_kblock64_pair_nc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                           uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 a1, b1;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "setp.eq.b32 p, 0, 0;\n"
+      "add.u32 a1, %1, 2;\n"
+      "add.u32 b1, %2, 2;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "add.u32 a1, %1, 4;\n"
+      "add.u32 b1, %2, 4;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "add.u32 a1, %1, 6;\n"
+      "add.u32 b1, %2, 6;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Shared-memory DATA handed from the threads of either CTA of a pair to the leader's MMA issuer (an operand tile written
+// with st.shared, then read by tcgen05.mma.cta_group::2 in the writer's own SM): the writer fences its generic-proxy
+// writes for the async proxy and arrives with release semantics at cluster scope on the LEADER's barrier; the issuer
+// waits with acquire semantics at cluster scope.
+__device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (((++spins) & 0x3ff) == 0 && (clock64() - t0) > 8000000000LL) {
+      printf("eqxv: mbarrier watchdog (cluster): block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait_cluster(bar, parity)) mbar_wait_cluster_slow(bar, parity);
+}
 // kind::f16 instruction descriptor for the 256-row pair MMA
 __host__ __device__ inline uint32_t umma_idesc_bf16_m256(uint32_t n) {
   uint32_t d = 0;

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, call, ptr
+from ._lib import Bottleneck64Desc, ConvDesc, call, ptr
 
 BF16 = torch.bfloat16
 
@@ -48,6 +48,29 @@ def conv2d(x, wgt, bias, *, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, re
         (_lib.FLAG_GROUPED_BLOCK64 if grouped_block64 else 0)
     call("eqxv_conv2d_igemm_bf16", C.byref(d), stream)
     return out
+
+
+def bottleneck64(t1, w2, b2, w3, b3, *, residual=None, x0=None, out=None, w1n=None, b1n=None, next_out=None, stream=0):
+    """One ResNet bottleneck with a 64-channel trunk behind its first 1x1 convolution (eqxv_bottleneck64_fused_bf16):
+    out = relu(conv1x1(relu(conv3x3(t1))) + residual)  or, with x0, relu([t2 | x0] @ [w3 | wd]^T + b3);
+    next_out = relu(conv1x1(out; w1n) + b1n) when w1n is given. t1 / x0 / next_out: [N,H,W,64], residual / out: [N,H,W,256]."""
+    _check_cuda(t1, w2, b2, w3, b3, residual, x0, out, w1n, b1n, next_out)
+    n, h, w, _ = t1.shape
+    if out is None:
+        out = torch.empty((n, h, w, 256), dtype=BF16, device=t1.device)
+    if w1n is not None and next_out is None:
+        next_out = torch.empty((n, h, w, 64), dtype=BF16, device=t1.device)
+    d = Bottleneck64Desc()
+    d.t1, d.w2, d.b2, d.w3, d.b3 = ptr(t1), ptr(w2), ptr(b2), ptr(w3), ptr(b3)
+    d.residual, d.x0, d.y = ptr(residual), ptr(x0), ptr(out)
+    d.w1n, d.b1n, d.next = ptr(w1n), ptr(b1n), ptr(next_out)
+    d.n, d.h, d.w = n, h, w
+    d.t1_pitch, d.y_pitch = t1.stride(2), out.stride(2)
+    d.res_pitch = residual.stride(2) if residual is not None else 0
+    d.x0_pitch = x0.stride(2) if x0 is not None else 0
+    d.next_pitch = next_out.stride(2) if next_out is not None else 0
+    call("eqxv_bottleneck64_fused_bf16", C.byref(d), stream)
+    return out if next_out is None else (out, next_out)
 
 
 def gemm(a, wgt, bias, *, act=0, residual=None, out=None, out_f32=False, res_after_act=False, stream=0):

@@ -118,6 +118,35 @@ int eqxv_gemm_gated_bf16(const void* a, int64_t lda, const void* gate, int64_t l
                          const float* bias, const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t m,
                          int32_t n, int32_t k, void* stream);
 
+/* K1 + K2 + K4 fused across layer boundaries: one whole ResNet bottleneck with a 64-channel trunk (resnet.py:144-162
+ * as instantiated by resnet.py:288-296: layer1 of ResNet-50/101/152), minus its first 1x1 convolution, plus - optionally -
+ * the first 1x1 convolution of the block that follows:
+ *     t2   = relu(conv3x3(t1; w2) + b2)                                 64 -> 64, stride 1, pad 1   (never stored)
+ *     y    = relu(conv1x1(t2; w3) + b3 + residual)                      64 -> 256                   identity shortcut
+ *          | relu([t2 | x0] @ [w3 | wd]^T + (b3 + bd))                                              downsample shortcut
+ *     next = relu(conv1x1(y; w1n) + b1n)                                256 -> 64                   (optional)
+ * BatchNorm folded into w / b by the caller as for eqxv_conv2d_igemm_bf16. All tensors NHWC bf16; biases fp32.
+ * Exactly one of `residual` (256 channels) / `x0` (the 64-channel input of the block's downsample convolution, w3 then
+ * holds [w3 | wd] along K: [256, 128], b3 = b3 + bd) must be given. Rounding points are those of the layer-by-layer
+ * path (t2, y and next are rounded to bf16 where that path stored them), so results agree with it to accumulation
+ * order. One CTA pair per two 8 x 16 pixel tiles, filters resident in shared memory (csrc/bottleneck.cu). */
+typedef struct eqxv_bottleneck64_desc {
+  const void* t1;       /* bf16 [n, h, w, t1_pitch], 64 channels: output of the block's first 1x1 convolution */
+  const void* w2;       /* bf16 [64, 9*64] (tap-major K, as eqxv_conv2d_igemm_bf16) */
+  const float* b2;      /* fp32 [64] */
+  const void* w3;       /* bf16 [256, 64], or [256, 128] = [w3 | wd] with x0 */
+  const float* b3;      /* fp32 [256] */
+  const void* residual; /* bf16 [n, h, w, res_pitch], 256 channels, or NULL */
+  const void* x0;       /* bf16 [n, h, w, x0_pitch], 64 channels, or NULL */
+  void* y;              /* bf16 [n, h, w, y_pitch], 256 channels */
+  const void* w1n;      /* bf16 [64, 256] or NULL */
+  const float* b1n;     /* fp32 [64] or NULL */
+  void* next;           /* bf16 [n, h, w, next_pitch], 64 channels, or NULL */
+  int32_t n, h, w;
+  int32_t t1_pitch, res_pitch, x0_pitch, y_pitch, next_pitch;
+} eqxv_bottleneck64_desc;
+int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, void* stream);
+
 /* First-layer ("stem") convolution on the raw image, cin <= 8: resnet.py:243-251 (7x7 s2 p3),
  * vgg.py:137 (3x3 s1 p1), efficientnet.py:327-337 / mobilenetv3.py:196-206 (3x3 s2 p1), densenet.py:175.
  * Input is the padded 8-channel image written by eqxv_pack_stem_input; weights are [cout, kh, 8, 8] bf16

@@ -503,3 +503,52 @@ def test_gemm_with_se_gate_on_the_a_operand(device, n_img, hw, k, n, res):
         ref = ref + r.float()
     assert rel_l2(got, ref) < TOL_BF16
     assert rel_l2(got, want) < 1e-3     # (tile shapes may differ between the pair and single-CTA kernels: not bitwise)
+
+
+# n, h, w, downsample shortcut, fused next conv1
+BOTTLENECK_CASES = [(2, 56, 56, False, False), (3, 56, 56, False, True), (2, 56, 56, True, True), (1, 56, 56, True, False),
+                    (3, 24, 40, False, True),      # odd tile count: the pair's phantom tile
+                    (2, 30, 23, True, True),       # ragged edges in both directions
+                    (37, 56, 56, False, True)]     # more pairs than clusters: several tiles per CTA, slot / phase wrap
+
+
+@pytest.mark.parametrize("case", BOTTLENECK_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_bottleneck64_fused(device, case):
+    """eqxv_bottleneck64_fused_bf16 (resnet.py:144-162 on the 64-channel trunk of layer1): against the layer-by-layer
+    kernels of the same library (same rounding points: must agree to accumulation order) and against torch fp32."""
+    from eqxvision_b200 import ops
+
+    n, h, w, down, nxt = case
+    t1 = rb(device, n, h, w, 64, seed=1)
+    w2 = rb(device, 64, 3, 3, 64, scale=576 ** -0.5, seed=2)
+    w3 = rb(device, 256, 64, scale=64 ** -0.5, seed=3)
+    g = torch.Generator().manual_seed(4)
+    b2, b3, b1n, bd = (torch.randn(c, generator=g).to(device) * 0.5 for c in (64, 256, 64, 256))
+    res = rb(device, n, h, w, 256, seed=5) if not down else None
+    x0 = rb(device, n, h, w, 64, seed=6) if down else None
+    wd = rb(device, 256, 64, scale=64 ** -0.5, seed=7)
+    w1n = rb(device, 64, 256, scale=256 ** -0.5, seed=8) if nxt else None
+    w3cat = torch.cat([w3, wd], dim=1).contiguous() if down else w3
+    b3cat = b3 + bd if down else b3
+    got = ops.bottleneck64(t1, w2.reshape(64, -1), b2, w3cat, b3cat, residual=res, x0=x0, w1n=w1n,
+                           b1n=b1n if nxt else None)
+    y, nx = got if nxt else (got, None)
+    # layer by layer, same library
+    t2 = ops.conv2d(t1, w2.reshape(64, -1), b2, cin=64, cout=64, kh=3, kw=3, pad=1, act=1)
+    # torch fp32 on the bf16-rounded intermediates
+    t2_ref = F.relu(F.conv2d(t1.float().permute(0, 3, 1, 2), w2.float().permute(0, 3, 1, 2), b2, padding=1))
+    t2r = t2_ref.permute(0, 2, 3, 1).to(torch.bfloat16).float()
+    assert rel_l2(t2, t2r) < TOL_BF16
+    if down:
+        yr = F.relu(t2r @ w3.float().t() + x0.float() @ wd.float().t() + b3cat)
+    else:
+        yr = F.relu(t2r @ w3.float().t() + b3 + res.float())
+    assert rel_l2(y, yr) < TOL_BF16
+    if not down:
+        y_layer = ops.conv2d(t2, w3, b3, cin=64, cout=256, kh=1, kw=1, act=1, residual=res)
+        assert rel_l2(y, y_layer) < 1e-3
+    if nxt:
+        nr = F.relu(y.float() @ w1n.float().t() + b1n)      # on the kernel's own (bf16) y: isolates the last GEMM
+        assert rel_l2(nx, nr) < TOL_BF16
+        n_layer = ops.conv2d(y, w1n, b1n, cin=256, cout=64, kh=1, kw=1, act=1)
+        assert rel_l2(nx, n_layer) < 1e-3
