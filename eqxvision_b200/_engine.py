@@ -313,6 +313,11 @@ class Plan:
         cout, cin_g, kh, kw = e.weight.shape
         (sh, sw), (ph, pw), (dh, dw) = e.stride, e.padding, e.dilation
         ho, wo = sym.shape[1:]
+        if dst is None and not out_f32 and self.BNECK_FUSE:
+            # before the shortcut operand is lowered: the fused kernel wants to lower the trunk first (see there)
+            fused = self._emit_bottleneck64(sym, e)
+            if fused is not None:
+                return fused
         w, b = _pack.fold_bn(e.weight, e.bias, e.bn)
         act, res_after = self._epilogue(e)
         res = self.emit(e.res) if e.res is not None else None
@@ -377,6 +382,82 @@ class Plan:
                       cin=cin_eff, cout=n1 - n0, kh=kh, kw=kw, stride=sh, pad=ph, dil=dh, act=act,
                       residual=None if rmap is None else rmap[..., n0:n1], res_after_act=res_after,
                       out=omap if whole else omap[..., n0:n1], out_f32=out_f32)
+        return out
+
+    # ---- fused ResNet bottleneck (64-channel trunk) ---------------------------------------------
+    BNECK_FUSE = os.environ.get("EQXV_NO_BNECK") != "1"
+
+    def _plain_conv(self, e, cin, cout, k, pad, act_name, res: bool) -> bool:
+        """e is a dense stride-1 undilated k x k convolution cin -> cout with exactly this epilogue and a bias"""
+        if not isinstance(e, T.Conv) or e.groups != 1 or tuple(e.weight.shape) != (cout, cin, k, k):
+            return False
+        if e.stride != (1, 1) or e.padding != (pad, pad) or e.dilation != (1, 1) or (e.bn is None and e.bias is None):
+            return False
+        if res:
+            return e.res is not None and e.act1 is None and e.act2 == act_name
+        return e.res is None and e.act2 is None and e.act1 == act_name
+
+    def _bottleneck64_match(self, e):
+        """e = the closing 1x1 convolution (64 -> 256, + shortcut, ReLU) of a bottleneck whose 3x3 is 64 -> 64, stride 1
+        (resnet.py:144-162 in layer1 of ResNet-50/101/152) and has not been lowered yet"""
+        if id(e) in self.memo or not self._plain_conv(e, 64, 256, 1, 0, "relu", True):
+            return None
+        c2 = e.x.expr
+        if id(c2) in self.memo or not self._plain_conv(c2, 64, 64, 3, 1, "relu", False):
+            return None
+        if e.res.shape != (256,) + tuple(e.x.shape[1:]) or isinstance(c2.x.expr, T.Input):
+            return None
+        down = e.res.expr
+        if id(down) in self.memo or not self._plain_conv(down, 64, 256, 1, 0, None, False) or \
+                isinstance(down.x.expr, T.Input):
+            down = None
+        return c2, down
+
+    def _emit_bottleneck64(self, sym, e: T.Conv) -> Optional[Buf]:
+        """Lowers a matched bottleneck onto eqxv_bottleneck64_fused_bf16. Called for the block's closing convolution
+        (returns y) or for the NEXT block's opening 1x1 (256 -> 64, ReLU) whose input is such a block: then one launch
+        produces both y (memoised for the shortcut / any other consumer) and that convolution's output."""
+        nxt = None
+        ysym = sym
+        if self._plain_conv(e, 256, 64, 1, 0, "relu", False) and self._bottleneck64_match(e.x.expr) is not None:
+            nxt, ysym = e, e.x
+        m = self._bottleneck64_match(ysym.expr)
+        if m is None:
+            return None
+        c3 = ysym.expr
+        c2, down = m
+        _, h, wd = ysym.shape
+        t1 = self.emit(c2.x)          # first: it may itself be the fused tail of the previous block (which memoises y)
+        if t1.pitch != 64:
+            return None
+        w2, b2 = _pack.fold_bn(c2.weight, c2.bias, c2.bn)
+        w3, b3 = _pack.fold_bn(c3.weight, c3.bias, c3.bn)
+        w3p = _pack.pack_conv_weight(w3, 64)
+        res = x0 = None
+        if down is not None:
+            x0 = self.emit(down.x)
+            wdn, bdn = _pack.fold_bn(down.weight, down.bias, down.bn)
+            w3p = torch.cat([w3p, _pack.pack_conv_weight(wdn, 64)], dim=1).contiguous()
+            b3 = b3 + bdn
+            if x0.pitch != 64:
+                return None
+        else:
+            res = self.emit(c3.res)
+            if res.pitch != 256:
+                return None
+        y = self.alloc(self.n * h * wd, 256, (h, wd))
+        kw = dict(t1=t1.map(h, wd), w2=self.const(_pack.pack_conv_weight(w2, 64)), b2=self.const(b2), w3=self.const(w3p),
+                  b3=self.const(b3), residual=None if res is None else res.map(h, wd),
+                  x0=None if x0 is None else x0.map(h, wd), out=y.map(h, wd))
+        out = y
+        if nxt is not None:
+            w1, b1 = _pack.fold_bn(nxt.weight, nxt.bias, nxt.bn)
+            out = self.alloc(self.n * h * wd, 64, (h, wd))
+            kw.update(w1n=self.const(_pack.pack_conv_weight(w1, 256)), b1n=self.const(b1), next_out=out.map(h, wd))
+            self.keep.append(c3)
+            self.memo[id(c3)] = y
+        self.keep.append(c2)
+        self.step(ops.bottleneck64, **kw)
         return out
 
     def _emit_grouped(self, sym, e, w, b, act, res_after, res, dst, out_f32):

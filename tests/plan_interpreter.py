@@ -105,6 +105,23 @@ def conv2d(x, wgt, bias, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, resid
     _store(out, _epilogue(y.permute(0, 2, 3, 1), bias, act, residual, res_after_act))
 
 
+def bottleneck64(t1, w2, b2, w3, b3, residual=None, x0=None, out=None, w1n=None, b1n=None, next_out=None, **_):
+    """include/eqxv_b200.h, eqxv_bottleneck64_fused_bf16: conv3x3 -> conv1x1 + shortcut -> (next block's conv1x1), with the
+    layer-by-layer path's rounding points (t2, y, next stored in the activation dtype)"""
+    assert (residual is None) != (x0 is None) and (w1n is None) == (next_out is None)
+    for t, what in ((t1, "bneck t1"), (residual, "bneck residual"), (x0, "bneck x0"), (out, "bneck y"), (next_out, "bneck next")):
+        _check_operand(t, what)
+    assert w2.shape == (64, 576) and w3.shape == (256, 128 if x0 is not None else 64) and out.shape[-1] >= 256
+    t2 = torch.empty(t1.shape[:3] + (64,), dtype=out.dtype)
+    conv2d(t1, w2, b2, 64, 64, 3, 3, 1, 1, 1, 1, None, False, t2)
+    a = t2 if x0 is None else torch.cat([t2, x0[..., :64].to(t2.dtype)], dim=-1)
+    y = a.float() @ w3.float().t()
+    _store(out, _epilogue(y, b3, 1, residual, False))
+    if w1n is not None:
+        assert w1n.shape == (64, 256)
+        _store(next_out, _epilogue(out[..., :256].float() @ w1n.float().t(), b1n, 1, None, False))
+
+
 def gemm(a, wgt, bias, act=0, residual=None, res_after_act=False, out=None, out_f32=False, **_):
     assert a.shape[1] % 8 == 0 and wgt.shape[1] == a.shape[1], "gemm: k must be a multiple of 8 and match the filter"
     for t, what in ((a, "gemm a"), (residual, "gemm residual")) + (() if out_f32 else ((out, "gemm out"),)):
@@ -332,7 +349,7 @@ def u8_resize_bilinear(x, oh, ow, out, **_):
     out.copy_(y.round().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1))
 
 
-IMPLS = {f.__name__: f for f in (gemm_gated, gemm_rowstats, gemm_ln, dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
+IMPLS = {f.__name__: f for f in (bottleneck64, gemm_gated, gemm_rowstats, gemm_ln, dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
                                  nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
                                  maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d, patchify,
                                  vit_assemble_tokens, attention, attention_probs, gather_rows, resize_bilinear,

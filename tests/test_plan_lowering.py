@@ -20,6 +20,7 @@ def rel(a, b):
 CASES = [  # (ctor, oracle fn, input hw, torchvision kwargs)
     ("alexnet", "alexnet", 224, {}),
     ("resnet18", "resnet", 64, {}),
+    ("resnet50", "resnet", 64, {}),                        # layer1 on the fused bottleneck entry
     ("mobilenet_v2", "mobilenet_v2", 64, {}),
     ("regnet_y_400mf", "regnet", 64, {}),
     ("squeezenet1_1", "squeezenet", 64, {}),
@@ -48,12 +49,21 @@ def test_lowered_plan_matches_emulating_oracle(tmp_path, arch, fn, hw, kw):
         emu = getattr(om, fn)(sd, x, arch)
     assert got.shape == emu.shape
     assert rel(got, emu) < 5e-4, rel(got, emu)   # a packing or layout mistake gives O(1)
-    if arch in ("alexnet", "resnet18", "mobilenet_v2"):
+    if arch == "resnet50":
+        # layer1 (resnet.py:288-296): block 0 with its downsample and block 1 each carry the NEXT block's opening 1x1;
+        # block 2 ends the chain (layer2's opening conv is 256 -> 128). 53 convolutions - 1 (stem entry) - (2 + downsample
+        # + next) - (2 + next) - 2 inside the three fused launches = 43 plain launches
+        fused = [kw_ for f_, kw_ in plan.steps if f_.__name__ == "bottleneck64"]
+        assert [(kw_["x0"] is not None, kw_.get("w1n") is not None) for kw_ in fused] == [(True, True), (False, True), (False, False)]
+        assert sum(f_.__name__ == "conv2d" for f_, _ in plan.steps) == 43
+    if arch in ("alexnet", "resnet18", "resnet50", "mobilenet_v2"):
         # and the bf16 replay against the fully emulating oracle (rounding positions), at bf16 noise level
         got16, _ = PI.run(net, x)
         with O.emulate_bf16():
             emu16 = getattr(om, fn)(sd, x, arch)
-        assert rel(got16, emu16) < 1e-2, rel(got16, emu16)
+        # resnet50: 50 layers of bf16 noise (1.5e-2 layer by layer), and the fused first block keeps its downsample
+        # branch in the fp32 accumulator where the oracle rounds it to bf16 once more (3e-2: one rounding FEWER)
+        assert rel(got16, emu16) < (5e-2 if arch == "resnet50" else 1e-2), rel(got16, emu16)
 
 
 def test_googlenet_auxiliary_heads_lower_with_equinox_uneven_pooling(tmp_path):
