@@ -37,7 +37,7 @@
 
 namespace eqxv {
 
-constexpr int kBnThreads = 320;                          // warp 0 TMA, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int kBnThreads = 576;                          // warp 0 TMA loads, warp 1 MMA issuer, warps 2..17 epilogue
 constexpr int kHaloW = 10, kHaloH = 18;                  // halo of an 8 x 16 tile under a 3x3 filter
 constexpr uint32_t kT1Bytes = kHaloW * kHaloH * 128;     // 23040
 constexpr uint32_t kT1Slot = 23552;                      // rounded up to 1 KiB (swizzle atoms stay aligned)
@@ -54,6 +54,7 @@ struct alignas(64) BneckParams {
   int n, h, w;
   int w3_chunks;   // 1, or 2 with the downsample filter concatenated along K
   uint32_t off_w3, off_w1, off_t1, off_x0, off_y, off_bias, off_bars;
+  long long* dbg;   // eqxv_debug_bottleneck_timeline: clock64 stamps of CTA 0 (tools/bneck_timeline.py), normally null
 };
 
 struct BnTile {
@@ -68,11 +69,24 @@ __device__ __forceinline__ BnTile bn_decode(const BneckParams& p, int m) {
   return t;
 }
 
+#define BN_STAMP(it, ev)                                                              \
+  do {                                                                                \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (it) < 16) p.dbg[(it) * 16 + (ev)] = clock64(); \
+  } while (0)
+
 // barrier slots (8 bytes each from off_bars)
 enum : uint32_t {
   kBarW = 0, kBarT1Full = 1, kBarT1Empty = 3, kBarX0Full = 5, kBarX0Empty = 6, kBarD2Full = 7, kBarA3Full = 8,
-  kBarD3Full = 9, kBarYFull = 10, kBarD1Full = 11, kBarTmemSlot = 12, kBarRes = 16   // + (warp - 2) * 2 + k
+  kBarD3Full = 9, kBarYFull = 10, kBarD1Full = 11, kBarTmemSlot = 12, kBarRes = 16   // + (warp - 2)
 };
+
+// 32 lanes x 32 contiguous bytes each: one full sector per thread in ONE instruction (16-byte stores leave half-written
+// sectors in flight and double the L2 write transactions of a pattern where every lane hits a different 128-byte line)
+__device__ __forceinline__ void st_global_32B(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 
 template <bool kDown, bool kNext>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
@@ -106,9 +120,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
     mbar_init(bar(kBarX0Full), 1);
     mbar_init(bar(kBarX0Empty), 1);
     mbar_init(bar(kBarD2Full), 1);
-    mbar_init(bar(kBarA3Full), 512);        // leader: the 2 x 256 epilogue threads of the pair
+    mbar_init(bar(kBarA3Full), 32);         // leader: the 2 x 16 epilogue warps of the pair
     mbar_init(bar(kBarD3Full), 1);
-    mbar_init(bar(kBarYFull), 512);
+    mbar_init(bar(kBarYFull), 32);
     mbar_init(bar(kBarD1Full), 1);
     for (int b = 0; b < 16; ++b) mbar_init(bar(kBarRes + b), 1);
     mbar_fence_init();
@@ -139,7 +153,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
   cluster_sync_all();          // ... and the peer's; its barriers are initialised before anything is signalled remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
-  const uint32_t d2_t = tmem_base, d1_t = tmem_base + 64u, d3_t = tmem_base + 256u;
+  // TMEM columns: D2 [0, 64), D1 [64, 128), Y (bf16 pairs, A operand of c1') [128, 256), D3 [256, 512)
+  const uint32_t d2_t = tmem_base, d1_t = tmem_base + 64u, y_t = tmem_base + 128u, d3_t = tmem_base + 256u;
   const int p_first = (int)(blockIdx.x >> 1), p_stride = (int)(gridDim.x >> 1);
 
   if (warp == 0) {
@@ -174,7 +189,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
       const uint32_t halo_hi = ((uint32_t)(kHaloW * 128) >> 4) | (1u << 14) | (2u << 29);
       const uint32_t lbo = 1u << 16;
       auto lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | lbo; };
-      const uint32_t w2_lo = lo(w2_s), w3_lo = lo(w3_s), w1_lo = lo(w1_s), x0_lo = lo(x0_s), y_lo = lo(y_s);
+      const uint32_t w2_lo = lo(w2_s), w3_lo = lo(w3_s), w1_lo = lo(w1_s), x0_lo = lo(x0_s);
       auto issue_c2 = [&](int slot) {
         const uint32_t a0 = lo(t1_s + (uint32_t)slot * kT1Slot);
 #pragma unroll
@@ -191,24 +206,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
       int slot = 0;
       uint32_t tph = 0;                 // parity of the once-per-tile barriers
       uint32_t fph[2] = {0u, 0u};       // parity of t1full[slot]
-      bool first = true;
-      for (int pi = p_first; pi < p.num_pairs; pi += p_stride) {
-        if (first) {
+      int it = 0;
+      for (int pi = p_first; pi < p.num_pairs; pi += p_stride, ++it) {
+        if (it == 0) {
           mbar_wait(bar(kBarT1Full + 0), fph[0]);
           fph[0] ^= 1u;
           tc_fence_after();
           issue_c2(0);
-          first = false;
         }
         // c3 (+ downsample): A = the bf16 tile the epilogue wrote over the consumed halo tile
         mbar_wait(bar(kBarA3Full), tph);
         if (kDown) mbar_wait(bar(kBarX0Full), tph);
         tc_fence_after();
+        BN_STAMP(it, 0);
         umma_bf16_kblock64_pair_nc(d3_t, lo(t1_s + (uint32_t)slot * kT1Slot), w3_lo, k_hi, k_hi, idesc256, 0u);
         if (kDown) umma_bf16_kblock64_pair_nc(d3_t, x0_lo, w3_lo + (kTile >> 4), k_hi, k_hi, idesc256, 1u);
         umma_commit_pair(bar(kBarT1Empty + slot));
         if (kDown) umma_commit_pair(bar(kBarX0Empty));
         umma_commit_pair(bar(kBarD3Full));
+        BN_STAMP(it, 1);
         // c2 of the next tile runs while the epilogue warps work through D3
         if (pi + p_stride < p.num_pairs) {
           const int ns = slot ^ 1;
@@ -217,15 +233,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
           tc_fence_after();
           issue_c2(ns);
         }
+        BN_STAMP(it, 2);
         if (kNext) {
-          // next block's c1: A = the finished output tile (4 K chunks), still in shared memory
+          // next block's c1: A = the finished output tile as bf16 pairs in TENSOR MEMORY (the epilogue wrote it there next
+          // to the staging slab of the TMA store), so the slab is free for the next tile's residual as soon as the store
+          // has read it - with A in shared memory every tile waited for c1' AND a TMA round trip before its e3.
           mbar_wait(bar(kBarYFull), tph);
           tc_fence_after();
+          BN_STAMP(it, 3);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_kblock64_pair_nc(d1_t, y_lo + (uint32_t)k * (kTile >> 4), w1_lo + (uint32_t)k * (kW2Tap >> 4), k_hi,
-                                       k_hi, idesc64, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 16; ++k)
+            umma_bf16_ts_pair(d1_t, y_t + (uint32_t)(8 * k), w1_lo + (uint32_t)(k >> 2) * (kW2Tap >> 4) + (uint32_t)(k & 3) * 2u,
+                              k_hi, idesc64, k != 0 ? 1u : 0u);
           umma_commit_pair(bar(kBarD1Full));
+          BN_STAMP(it, 4);
         }
         slot ^= 1;
         tph ^= 1u;
@@ -233,110 +254,133 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
     }
     __syncwarp();
   } else {
-    // ============================== epilogue (warps 2..9, both CTAs) ==============================
-    // Two warps per TMEM lane quadrant: `sub` picks the column half (e2, e4) / the 64-column chunks {sub, sub + 2} (e3).
-    // Thread <-> accumulator row r = 32 q + lane <-> pixel (h0 + r / 8, w0 + r % 8).
+    // ============================== epilogue (warps 2..17, both CTAs) ==============================
+    // Four warps per TMEM lane quadrant: `sub` picks 16 of the 64 columns (e2, e4) / ONE 64-column chunk (e3).
+    // Thread <-> accumulator row r = 32 q + lane <-> pixel (h0 + r / 8, w0 + r % 8). Every warp is autonomous: it owns
+    // the 4 KiB slab (its 32 rows x its chunk) of the output tile - residual load, in-place arithmetic, TMA store - and
+    // its own mbarrier; there is no CTA-wide synchronisation on this path.
+    // Order per tile: e3(i), e2(i+1), residual load(i+1), e4(i): the issuer's c3(i+1) / c1'(i) run behind e2 / e4.
     const int q = warp & 3, sub = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int r = q * 32 + lane;
     const int h_loc = r >> 3, w_loc = r & 7;
-    auto rbar = [&](int k) { return bar(kBarRes + (uint32_t)(warp - 2) * 2u + (uint32_t)k); };
-    auto slab_off = [&](int k) { return (uint32_t)(sub + 2 * k) * kTile + (uint32_t)q * 4096u; };   // 32 rows x 128 B
-    auto issue_res = [&](const BnTile& t) {   // ONE lane: this warp's two residual slabs, straight into the output tile
+    const uint32_t rbar = bar(kBarRes + (uint32_t)(warp - 2));
+    const uint32_t slab_off = (uint32_t)sub * kTile + (uint32_t)q * 4096u;   // 32 rows x 128 B of chunk `sub`
+    uint8_t* const slab = gbase + p.off_y + slab_off;
+    const float* const bias3 = s_bias + 64 + 64 * sub;
+    auto e2 = [&](int slot, uint32_t ph) {   // D2 -> 16 columns of the A operand of c3, over the consumed halo tile
+      mbar_wait(bar(kBarD2Full), ph);
+      tc_fence_after();
+      float v[16];
+      tmem_ld_x16(d2_t + lane_base + (uint32_t)(16 * sub), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      uint8_t* a3 = gbase + p.off_t1 + (uint32_t)slot * kT1Slot;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        mbar_expect_tx(rbar(k), 4096u);
-        tma_load_4d(y_s + slab_off(k), &p.tmR, rbar(k), (sub + 2 * k) * 64, t.w0, t.h0 + 4 * q, t.n0);
-      }
+      for (int j = 0; j < 2; ++j)
+        *reinterpret_cast<uint4*>(a3 + sw128_off((uint32_t)r, (uint32_t)(2 * sub + j))) =
+            epilogue8<EQXV_ACT_RELU, 0>(&v[8 * j], s_bias + 16 * sub + 8 * j, make_uint4(0u, 0u, 0u, 0u));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar(kBarA3Full));
+    };
+    auto issue_res = [&](const BnTile& t) {   // ONE lane
+      mbar_expect_tx(rbar, 4096u);
+      tma_load_4d(y_s + slab_off, &p.tmR, rbar, sub * 64, t.w0, t.h0 + 4 * q, t.n0);
     };
     uint32_t tph = 0;
-    int slot = 0;
-    if (!kDown && lane == 0 && p_first < p.num_pairs) issue_res(bn_decode(p, 2 * p_first + (int)rank));
-    __syncwarp();
-    for (int pi = p_first; pi < p.num_pairs; pi += p_stride) {
-      const BnTile t = bn_decode(p, 2 * pi + (int)rank);
-      // ---------------- e2: D2 -> A operand of c3 ----------------
-      mbar_wait(bar(kBarD2Full), tph);
-      tc_fence_after();
-      {
-        float v[32];
-        tmem_ld_x16(d2_t + lane_base + (uint32_t)(32 * sub), &v[0]);
-        tmem_ld_x16(d2_t + lane_base + (uint32_t)(32 * sub + 16), &v[16]);
-        tmem_ld_wait();
-        tc_fence_before();
-        uint8_t* a3 = gbase + p.off_t1 + (uint32_t)slot * kT1Slot;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 o = epilogue8<EQXV_ACT_RELU, 0>(&v[8 * j], s_bias + 32 * sub + 8 * j, make_uint4(0u, 0u, 0u, 0u));
-          *reinterpret_cast<uint4*>(a3 + sw128_off((uint32_t)r, (uint32_t)(4 * sub + j))) = o;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive_leader(bar(kBarA3Full));
+    int slot = 0, it = 0;
+    const bool stamp = warp == 2 && lane == 0;
+    BnTile t = bn_decode(p, 2 * p_first + (int)rank), tnext = t;
+    if (p_first < p.num_pairs) {
+      if (!kDown && lane == 0) issue_res(t);
+      __syncwarp();
+      e2(0, 0u);
+    }
+    for (int pi = p_first; pi < p.num_pairs; pi += p_stride, ++it) {
+      const bool more = pi + p_stride < p.num_pairs;
+      if (more) {
+        tnext = bn_decode(p, 2 * (pi + p_stride) + (int)rank);
+        // the next tile's residual slab on its way from HBM to L2 while this tile is worked on
+        if (!kDown && lane == 0) tma_prefetch_l2_4d(&p.tmR, sub * 64, tnext.w0, tnext.h0 + 4 * q, tnext.n0);
       }
-      // ---------------- e3: D3 (+ residual) -> y ----------------
+      // ---------------- e3: D3 (+ residual, in place) -> y ----------------
       mbar_wait(bar(kBarD3Full), tph);
       tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int c = sub + 2 * k;
-        float v[64];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tmem_ld_x16(d3_t + lane_base + (uint32_t)(64 * c + 16 * j), &v[16 * j]);
-        tmem_ld_wait();
-        if (k == 1) tc_fence_before();
-        uint8_t* slab = gbase + p.off_y + slab_off(k);
-        if (!kDown) mbar_wait(rbar(k), tph);   // the residual slab has landed
-        uint4 packed[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-          if (!kDown) rv = *reinterpret_cast<const uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)j));
-          packed[j] = epilogue8<EQXV_ACT_RELU, kDown ? 0 : 1>(&v[8 * j], s_bias + 64 + 64 * c + 8 * j, rv);
-        }
-        if (kDown) {
+      if (stamp) BN_STAMP(it, 5);
+      {
+        // four steps of 16 columns, the next step's TMEM load in flight behind the current step's arithmetic
+        float va[16], vb[16];
+        tmem_ld_x16(d3_t + lane_base + (uint32_t)(64 * sub), va);
+        if (!kDown) {
+          mbar_wait(rbar, tph);   // the residual slab has landed
+        } else {
           // no residual load orders this: the TMA store that last read the slab must be done before it is rewritten
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
         }
+        if (stamp) BN_STAMP(it, 6);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)j)) = packed[j];
+        for (int st = 0; st < 4; ++st) {
+          float* cur = (st & 1) ? vb : va;
+          float* nxt = (st & 1) ? va : vb;
+          uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+          if (!kDown) {
+            r0 = *reinterpret_cast<const uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)(2 * st)));
+            r1 = *reinterpret_cast<const uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)(2 * st + 1)));
+          }
+          tmem_ld_wait();
+          if (st < 3) tmem_ld_x16(d3_t + lane_base + (uint32_t)(64 * sub + 16 * (st + 1)), nxt);
+          uint4 o[2];
+          o[0] = epilogue8<EQXV_ACT_RELU, kDown ? 0 : 1>(&cur[0], bias3 + 16 * st, r0);
+          o[1] = epilogue8<EQXV_ACT_RELU, kDown ? 0 : 1>(&cur[8], bias3 + 16 * st + 8, r1);
+          *reinterpret_cast<uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)(2 * st))) = o[0];
+          *reinterpret_cast<uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)(2 * st + 1))) = o[1];
+          // ... and, as bf16 pairs, into the A operand of c1' (row = lane, K = 64 sub + 16 st .. + 15)
+          if (kNext) tmem_st_x8(y_t + lane_base + (uint32_t)(32 * sub + 8 * st), reinterpret_cast<const uint32_t*>(o));
+        }
+        if (kNext) tmem_st_wait();
+        tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&p.tmY, y_s + slab_off(k), c * 64, t.w0, t.h0 + 4 * q, t.n0);
+          tma_store_4d(&p.tmY, y_s + slab_off, sub * 64, t.w0, t.h0 + 4 * q, t.n0);
           tma_store_commit();
+          if (kNext) mbar_arrive_leader(bar(kBarYFull));
         }
         __syncwarp();
       }
-      if (kNext) mbar_arrive_leader(bar(kBarYFull));
-      // ---------------- e4: D1 -> t1' of the next block; residual prefetch for the next tile ----------------
-      float v1[32];
-      if (kNext) {
-        mbar_wait(bar(kBarD1Full), tph);   // c1' has consumed the output tile
-        tc_fence_after();
-        tmem_ld_x16(d1_t + lane_base + (uint32_t)(32 * sub), &v1[0]);
-        tmem_ld_x16(d1_t + lane_base + (uint32_t)(32 * sub + 16), &v1[16]);
-      }
-      if (!kDown && pi + p_stride < p.num_pairs) {
+      if (stamp) BN_STAMP(it, 7);
+      // ---------------- e2 of the next tile (its c2 ran behind this tile's c3) ----------------
+      if (more) e2(slot ^ 1, tph ^ 1u);
+      if (stamp) BN_STAMP(it, 8);
+      // ---------------- the next tile's residual into the slab this warp's store has just read ----------------
+      if (!kDown && more) {
         if (lane == 0) {
-          tma_store_wait_read<0>();   // this warp's stores have read their slabs
-          issue_res(bn_decode(p, 2 * (pi + p_stride) + (int)rank));
+          tma_store_wait_read<0>();
+          issue_res(tnext);
         }
         __syncwarp();
       }
+      if (stamp) BN_STAMP(it, 9);
+      // ---------------- e4: D1 -> this thread's 16 channels of t1' ----------------
       if (kNext) {
+        mbar_wait(bar(kBarD1Full), tph);
+        tc_fence_after();
+        float v[16];
+        tmem_ld_x16(d1_t + lane_base + (uint32_t)(16 * sub), v);
         tmem_ld_wait();
         tc_fence_before();
         const int hh = t.h0 + h_loc, ww = t.w0 + w_loc;
         if (t.n0 < p.n && hh < p.h && ww < p.w) {
-          __nv_bfloat16* orow = p.next_out + (((long long)t.n0 * p.h + hh) * p.w + ww) * p.next_pitch + 32 * sub;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(orow + 8 * j) =
-                epilogue8<EQXV_ACT_RELU, 0>(&v1[8 * j], s_bias + 320 + 32 * sub + 8 * j, make_uint4(0u, 0u, 0u, 0u));
+          __nv_bfloat16* orow = p.next_out + (((long long)t.n0 * p.h + hh) * p.w + ww) * p.next_pitch + 16 * sub;
+          const uint4 o0 = epilogue8<EQXV_ACT_RELU, 0>(&v[0], s_bias + 320 + 16 * sub, make_uint4(0u, 0u, 0u, 0u));
+          const uint4 o1 = epilogue8<EQXV_ACT_RELU, 0>(&v[8], s_bias + 320 + 16 * sub + 8, make_uint4(0u, 0u, 0u, 0u));
+          st_global_32B(orow, o0, o1);
         }
       }
+      if (stamp) BN_STAMP(it, 10);
+      t = tnext;
       slot ^= 1;
       tph ^= 1u;
     }
@@ -354,6 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
   }
 }
 
+static long long* g_bn_dbg = nullptr;
 using BneckFn = void (*)(const BneckParams);
 static BneckFn bneck_table(bool down, bool next) {
   static const BneckFn t[2][2] = {{bneck_kernel<false, false>, bneck_kernel<false, true>},
@@ -399,6 +444,11 @@ static int map2d(CUtensorMap* m, const void* ptr, int k, int rows, int box_rows)
 
 using namespace eqxv;
 
+extern "C" int eqxv_debug_bottleneck_timeline(long long* ts) {
+  g_bn_dbg = ts;
+  return EQXV_OK;
+}
+
 extern "C" int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, void* stream) {
   EQXV_CHECK_ARG(d != nullptr, "bottleneck: null descriptor");
   EQXV_CHECK_ARG(d->t1 && d->w2 && d->b2 && d->w3 && d->b3 && d->y, "bottleneck: null tensor pointer");
@@ -416,7 +466,8 @@ extern "C" int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, voi
                  "bottleneck: bad t1 / y pitch");
   if (down) EQXV_CHECK_ARG(d->x0_pitch >= 64 && d->x0_pitch % 8 == 0, "bottleneck: bad x0 pitch");
   else EQXV_CHECK_ARG(d->res_pitch >= 256 && d->res_pitch % 8 == 0, "bottleneck: bad residual pitch");
-  if (next) EQXV_CHECK_ARG(d->next_pitch >= 64 && d->next_pitch % 8 == 0, "bottleneck: bad next pitch");
+  if (next) EQXV_CHECK_ARG(d->next_pitch >= 64 && d->next_pitch % 16 == 0 && ((uintptr_t)d->next & 31) == 0,
+                           "bottleneck: next is written with 32-byte stores: pitch %% 16 == 0, 32-byte aligned base");
 
   BneckParams p;
   memset(&p, 0, sizeof(p));
@@ -429,6 +480,7 @@ extern "C" int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, voi
   p.b2 = d->b2, p.b3 = d->b3, p.b1n = d->b1n;
   p.next_out = static_cast<__nv_bfloat16*>(d->next), p.next_pitch = d->next_pitch;
   p.w3_chunks = down ? 2 : 1;
+  p.dbg = g_bn_dbg;
   uint32_t off = 9u * kW2Tap;
   p.off_w3 = off, off += (uint32_t)p.w3_chunks * kTile;
   p.off_w1 = off, off += next ? 4u * kW2Tap : 0u;

@@ -106,6 +106,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// L2 prefetch of a 4-D box (no shared-memory destination, no barrier): a later TMA load of the same box hits L2
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1,
                                              int c2, int c3) {
   asm volatile(
@@ -501,6 +507,20 @@ static __device__ __noinline__ void mbar_wait_cluster_slow(uint32_t bar, uint32_
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   if (!mbar_try_wait_cluster(bar, parity)) mbar_wait_cluster_slow(bar, parity);
+}
+// pair flavour of umma_bf16_ts: D[tmem] (+)= A[tmem] * B[smem] over both CTAs (each CTA's 128 A rows in its own TMEM)
+__device__ __forceinline__ void umma_bf16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // kind::f16 instruction descriptor for the 256-row pair MMA
 __host__ __device__ inline uint32_t umma_idesc_bf16_m256(uint32_t n) {
