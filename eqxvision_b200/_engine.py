@@ -320,6 +320,10 @@ class Plan:
                 return fused
         w, b = _pack.fold_bn(e.weight, e.bias, e.bn)
         act, res_after = self._epilogue(e)
+        if e.res is not None and self.BNECK_FUSE and isinstance(e.x.expr, T.Conv) and e.groups == 1:
+            # trunk before shortcut: the trunk's first convolution may come out of the launch that produces the shortcut
+            # tensor (fused bottleneck + next 1x1); lowering the shortcut first would emit that block without it
+            self.emit(e.x)
         res = self.emit(e.res) if e.res is not None else None
         xin = e.x
         c_in, h, wd = xin.shape
@@ -415,12 +419,16 @@ class Plan:
 
     def _emit_bottleneck64(self, sym, e: T.Conv) -> Optional[Buf]:
         """Lowers a matched bottleneck onto eqxv_bottleneck64_fused_bf16. Called for the block's closing convolution
-        (returns y) or for the NEXT block's opening 1x1 (256 -> 64, ReLU) whose input is such a block: then one launch
+        (returns y) or for the NEXT block's opening 1x1 (256 -> 64 | 128, ReLU) whose input is such a block: then one launch
         produces both y (memoised for the shortcut / any other consumer) and that convolution's output."""
         nxt = None
         ysym = sym
-        if self._plain_conv(e, 256, 64, 1, 0, "relu", False) and self._bottleneck64_match(e.x.expr) is not None:
-            nxt, ysym = e, e.x
+        if self._plain_conv(e, 256, 64, 1, 0, "relu", False) or self._plain_conv(e, 256, 128, 1, 0, "relu", False):
+            # 64: the next block of the stage; 128: the first block of the next stage (not together with a downsample
+            # shortcut: the two 32 KiB filters do not fit side by side - a one-block stage, which ResNet does not have)
+            pm = self._bottleneck64_match(e.x.expr)
+            if pm is not None and not (e.weight.shape[0] == 128 and pm[1] is not None):
+                nxt, ysym = e, e.x
         m = self._bottleneck64_match(ysym.expr)
         if m is None:
             return None
@@ -452,7 +460,7 @@ class Plan:
         out = y
         if nxt is not None:
             w1, b1 = _pack.fold_bn(nxt.weight, nxt.bias, nxt.bn)
-            out = self.alloc(self.n * h * wd, 64, (h, wd))
+            out = self.alloc(self.n * h * wd, nxt.weight.shape[0], (h, wd))
             kw.update(w1n=self.const(_pack.pack_conv_weight(w1, 256)), b1n=self.const(b1), next_out=out.map(h, wd))
             self.keep.append(c3)
             self.memo[id(c3)] = y

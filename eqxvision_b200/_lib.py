@@ -47,7 +47,7 @@ class Bottleneck64Desc(C.Structure):
         ("next", C.c_void_p),
         ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
         ("t1_pitch", C.c_int32), ("res_pitch", C.c_int32), ("x0_pitch", C.c_int32), ("y_pitch", C.c_int32),
-        ("next_pitch", C.c_int32),
+        ("next_pitch", C.c_int32), ("next_channels", C.c_int32),
     ]
 
 

@@ -88,9 +88,11 @@ __device__ __forceinline__ void st_global_32B(void* ptr, const uint4& a, const u
                : "memory");
 }
 
-template <bool kDown, bool kNext>
+template <bool kDown, int kNextN>   // kNextN: output channels of the fused next 1x1 convolution (0 = none, 64, 128)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
     bneck_kernel(const __grid_constant__ BneckParams p) {
+  constexpr bool kNext = kNextN != 0;
+  constexpr uint32_t kW1Chunk = (uint32_t)(kNextN / 2) * 128u;   // this CTA's half of one 64-deep K chunk of w1'
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -103,7 +105,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
   const uint32_t w2_s = base, w3_s = base + p.off_w3, w1_s = base + p.off_w1, t1_s = base + p.off_t1,
                  x0_s = base + p.off_x0, y_s = base + p.off_y;
   volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbase + p.off_bars + 8 * kBarTmemSlot);
-  float* s_bias = reinterpret_cast<float*>(gbase + p.off_bias);   // [b2 64][b3 256][b1' 64]
+  float* s_bias = reinterpret_cast<float*>(gbase + p.off_bias);   // [b2 64][b3 256][b1' kNextN]
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmT1);
@@ -127,18 +129,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
     for (int b = 0; b < 16; ++b) mbar_init(bar(kBarRes + b), 1);
     mbar_fence_init();
     // The filters are constants of the plan (not written by the preceding kernel): fetched before the PDL wait.
-    const uint32_t wbytes = 9u * kW2Tap + (uint32_t)p.w3_chunks * kTile + (kNext ? 4u * kW2Tap : 0u);
+    const uint32_t wbytes = 9u * kW2Tap + (uint32_t)p.w3_chunks * kTile + 4u * kW1Chunk;
     mbar_expect_tx(bar(kBarW), wbytes);
     for (int tap = 0; tap < 9; ++tap) tma_load_2d(w2_s + tap * kW2Tap, &p.tmW2, bar(kBarW), tap * 64, (int)rank * 32);
     for (int k = 0; k < p.w3_chunks; ++k) tma_load_2d(w3_s + k * kTile, &p.tmW3, bar(kBarW), k * 64, (int)rank * 128);
     if (kNext)
-      for (int k = 0; k < 4; ++k) tma_load_2d(w1_s + k * kW2Tap, &p.tmW1, bar(kBarW), k * 64, (int)rank * 32);
+      for (int k = 0; k < 4; ++k) tma_load_2d(w1_s + k * kW1Chunk, &p.tmW1, bar(kBarW), k * 64, (int)rank * (kNextN / 2));
   }
-  for (int i = threadIdx.x; i < 384; i += blockDim.x) {
-    float v = 0.f;
+  for (int i = threadIdx.x; i < 320 + kNextN; i += blockDim.x) {
+    float v;
     if (i < 64) v = __ldg(p.b2 + i);
     else if (i < 320) v = __ldg(p.b3 + (i - 64));
-    else if (kNext) v = __ldg(p.b1n + (i - 320));
+    else v = __ldg(p.b1n + (i - 320));
     s_bias[i] = v;
   }
   if (warp == 1) {
@@ -153,8 +155,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
   cluster_sync_all();          // ... and the peer's; its barriers are initialised before anything is signalled remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
-  // TMEM columns: D2 [0, 64), D1 [64, 128), Y (bf16 pairs, A operand of c1') [128, 256), D3 [256, 512)
-  const uint32_t d2_t = tmem_base, d1_t = tmem_base + 64u, y_t = tmem_base + 128u, d3_t = tmem_base + 256u;
+  // TMEM columns: D2 [0, 64), D1 [64, 64 + kNextN), D3 [256, 512). Y - the finished output tile as bf16 pairs, A operand of
+  // c1' - is written IN PLACE over the D3 columns the same thread has just drained: chunk c (64 fp32 columns) leaves 32
+  // packed columns at D3 + 64 c. c3 of the next tile overwrites them only after c1' (MMAs execute in issue order).
+  const uint32_t d2_t = tmem_base, d1_t = tmem_base + 64u, d3_t = tmem_base + 256u;
   const int p_first = (int)(blockIdx.x >> 1), p_stride = (int)(gridDim.x >> 1);
 
   if (warp == 0) {
@@ -241,10 +245,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
           mbar_wait(bar(kBarYFull), tph);
           tc_fence_after();
           BN_STAMP(it, 3);
+          const uint32_t idesc_n = umma_idesc_bf16_m256((uint32_t)kNextN);
 #pragma unroll
           for (int k = 0; k < 16; ++k)
-            umma_bf16_ts_pair(d1_t, y_t + (uint32_t)(8 * k), w1_lo + (uint32_t)(k >> 2) * (kW2Tap >> 4) + (uint32_t)(k & 3) * 2u,
-                              k_hi, idesc64, k != 0 ? 1u : 0u);
+            umma_bf16_ts_pair(d1_t, d3_t + (uint32_t)(64 * (k >> 2) + 8 * (k & 3)),
+                              w1_lo + (uint32_t)(k >> 2) * (kW1Chunk >> 4) + (uint32_t)(k & 3) * 2u, k_hi, idesc_n,
+                              k != 0 ? 1u : 0u);
           umma_commit_pair(bar(kBarD1Full));
           BN_STAMP(it, 4);
         }
@@ -337,7 +343,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
           *reinterpret_cast<uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)(2 * st))) = o[0];
           *reinterpret_cast<uint4*>(slab + sw128_off((uint32_t)lane, (uint32_t)(2 * st + 1))) = o[1];
           // ... and, as bf16 pairs, into the A operand of c1' (row = lane, K = 64 sub + 16 st .. + 15)
-          if (kNext) tmem_st_x8(y_t + lane_base + (uint32_t)(32 * sub + 8 * st), reinterpret_cast<const uint32_t*>(o));
+          if (kNext) tmem_st_x8(d3_t + lane_base + (uint32_t)(64 * sub + 8 * st), reinterpret_cast<const uint32_t*>(o));
         }
         if (kNext) tmem_st_wait();
         tc_fence_before();
@@ -363,20 +369,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
         __syncwarp();
       }
       if (stamp) BN_STAMP(it, 9);
-      // ---------------- e4: D1 -> this thread's 16 channels of t1' ----------------
-      if (kNext) {
+      // ---------------- e4: D1 -> this thread's kNextN / 4 channels of t1' ----------------
+      if constexpr (kNext) {
+        constexpr int kCols = kNextN / 4;   // 16 or 32
         mbar_wait(bar(kBarD1Full), tph);
         tc_fence_after();
-        float v[16];
-        tmem_ld_x16(d1_t + lane_base + (uint32_t)(16 * sub), v);
+        float v[kCols];
+#pragma unroll
+        for (int g = 0; g < kCols / 16; ++g) tmem_ld_x16(d1_t + lane_base + (uint32_t)(kCols * sub + 16 * g), &v[16 * g]);
         tmem_ld_wait();
         tc_fence_before();
         const int hh = t.h0 + h_loc, ww = t.w0 + w_loc;
         if (t.n0 < p.n && hh < p.h && ww < p.w) {
-          __nv_bfloat16* orow = p.next_out + (((long long)t.n0 * p.h + hh) * p.w + ww) * p.next_pitch + 16 * sub;
-          const uint4 o0 = epilogue8<EQXV_ACT_RELU, 0>(&v[0], s_bias + 320 + 16 * sub, make_uint4(0u, 0u, 0u, 0u));
-          const uint4 o1 = epilogue8<EQXV_ACT_RELU, 0>(&v[8], s_bias + 320 + 16 * sub + 8, make_uint4(0u, 0u, 0u, 0u));
-          st_global_32B(orow, o0, o1);
+          __nv_bfloat16* orow = p.next_out + (((long long)t.n0 * p.h + hh) * p.w + ww) * p.next_pitch + kCols * sub;
+          const float* bn = s_bias + 320 + kCols * sub;
+#pragma unroll
+          for (int g = 0; g < kCols / 16; ++g) {
+            const uint4 o0 = epilogue8<EQXV_ACT_RELU, 0>(&v[16 * g], bn + 16 * g, make_uint4(0u, 0u, 0u, 0u));
+            const uint4 o1 = epilogue8<EQXV_ACT_RELU, 0>(&v[16 * g + 8], bn + 16 * g + 8, make_uint4(0u, 0u, 0u, 0u));
+            st_global_32B(orow + 16 * g, o0, o1);
+          }
         }
       }
       if (stamp) BN_STAMP(it, 10);
@@ -400,16 +412,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
 
 static long long* g_bn_dbg = nullptr;
 using BneckFn = void (*)(const BneckParams);
-static BneckFn bneck_table(bool down, bool next) {
-  static const BneckFn t[2][2] = {{bneck_kernel<false, false>, bneck_kernel<false, true>},
-                                  {bneck_kernel<true, false>, bneck_kernel<true, true>}};
-  return t[down ? 1 : 0][next ? 1 : 0];
+static BneckFn bneck_table(bool down, int next_n) {
+  static const BneckFn t[2][3] = {{bneck_kernel<false, 0>, bneck_kernel<false, 64>, bneck_kernel<false, 128>},
+                                  {bneck_kernel<true, 0>, bneck_kernel<true, 64>, bneck_kernel<true, 128>}};
+  return t[down ? 1 : 0][next_n / 64];
 }
 
 int bottleneck_init() {
   for (int d = 0; d < 2; ++d)
-    for (int n = 0; n < 2; ++n)
-      EQXV_CUDA(cudaFuncSetAttribute(bneck_table(d, n), cudaFuncAttributeMaxDynamicSharedMemorySize, kBnMaxSmem));
+    for (int n = 0; n <= 128; n += 64)
+      EQXV_CUDA(cudaFuncSetAttribute(bneck_table(d != 0, n), cudaFuncAttributeMaxDynamicSharedMemorySize, kBnMaxSmem));
   return EQXV_OK;
 }
 
@@ -458,6 +470,9 @@ extern "C" int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, voi
                  "bottleneck: w1n, b1n and next go together");
   EQXV_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0, "bottleneck: bad shape");
   const bool down = d->x0 != nullptr, next = d->next != nullptr;
+  const int next_n = next ? d->next_channels : 0;
+  EQXV_CHECK_ARG(!next || next_n == 64 || next_n == 128, "bottleneck: the fused next convolution has 64 or 128 outputs, not %d",
+                 next_n);
   auto ok_ptr = [](const void* p_) { return ((uintptr_t)p_ & 15) == 0; };
   EQXV_CHECK_ARG(ok_ptr(d->t1) && ok_ptr(d->w2) && ok_ptr(d->w3) && ok_ptr(d->y) && ok_ptr(d->residual) &&
                      ok_ptr(d->x0) && ok_ptr(d->w1n) && ok_ptr(d->next),
@@ -466,7 +481,7 @@ extern "C" int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, voi
                  "bottleneck: bad t1 / y pitch");
   if (down) EQXV_CHECK_ARG(d->x0_pitch >= 64 && d->x0_pitch % 8 == 0, "bottleneck: bad x0 pitch");
   else EQXV_CHECK_ARG(d->res_pitch >= 256 && d->res_pitch % 8 == 0, "bottleneck: bad residual pitch");
-  if (next) EQXV_CHECK_ARG(d->next_pitch >= 64 && d->next_pitch % 16 == 0 && ((uintptr_t)d->next & 31) == 0,
+  if (next) EQXV_CHECK_ARG(d->next_pitch >= next_n && d->next_pitch % 16 == 0 && ((uintptr_t)d->next & 31) == 0,
                            "bottleneck: next is written with 32-byte stores: pitch %% 16 == 0, 32-byte aligned base");
 
   BneckParams p;
@@ -483,7 +498,7 @@ extern "C" int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, voi
   p.dbg = g_bn_dbg;
   uint32_t off = 9u * kW2Tap;
   p.off_w3 = off, off += (uint32_t)p.w3_chunks * kTile;
-  p.off_w1 = off, off += next ? 4u * kW2Tap : 0u;
+  p.off_w1 = off, off += 4u * (uint32_t)(next_n / 2) * 128u;
   p.off_t1 = off, off += 2u * kT1Slot;
   p.off_x0 = off, off += down ? kTile : 0u;
   p.off_y = off, off += 4u * kTile;
@@ -508,11 +523,11 @@ extern "C" int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, voi
   rc = map2d(&p.tmW3, d->w3, down ? 128 : 64, 256, 128);
   if (rc) return rc;
   if (next) {
-    rc = map2d(&p.tmW1, d->w1n, 256, 64, 32);
+    rc = map2d(&p.tmW1, d->w1n, 256, next_n, next_n / 2);
     if (rc) return rc;
   }
   const int clusters = std::min(p.num_pairs, device_sm_count() / 2);
-  EQXV_CUDA(launch_kernel(bneck_table(down, next), dim3(2 * clusters), dim3(kBnThreads), smem_bytes,
+  EQXV_CUDA(launch_kernel(bneck_table(down, next_n), dim3(2 * clusters), dim3(kBnThreads), smem_bytes,
                           (cudaStream_t)stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;

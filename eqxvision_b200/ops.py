@@ -59,7 +59,7 @@ def bottleneck64(t1, w2, b2, w3, b3, *, residual=None, x0=None, out=None, w1n=No
     if out is None:
         out = torch.empty((n, h, w, 256), dtype=BF16, device=t1.device)
     if w1n is not None and next_out is None:
-        next_out = torch.empty((n, h, w, 64), dtype=BF16, device=t1.device)
+        next_out = torch.empty((n, h, w, w1n.shape[0]), dtype=BF16, device=t1.device)
     d = Bottleneck64Desc()
     d.t1, d.w2, d.b2, d.w3, d.b3 = ptr(t1), ptr(w2), ptr(b2), ptr(w3), ptr(b3)
     d.residual, d.x0, d.y = ptr(residual), ptr(x0), ptr(out)
@@ -69,6 +69,7 @@ def bottleneck64(t1, w2, b2, w3, b3, *, residual=None, x0=None, out=None, w1n=No
     d.res_pitch = residual.stride(2) if residual is not None else 0
     d.x0_pitch = x0.stride(2) if x0 is not None else 0
     d.next_pitch = next_out.stride(2) if next_out is not None else 0
+    d.next_channels = w1n.shape[0] if w1n is not None else 0
     call("eqxv_bottleneck64_fused_bf16", C.byref(d), stream)
     return out if next_out is None else (out, next_out)
 

@@ -124,7 +124,7 @@ int eqxv_gemm_gated_bf16(const void* a, int64_t lda, const void* gate, int64_t l
  *     t2   = relu(conv3x3(t1; w2) + b2)                                 64 -> 64, stride 1, pad 1   (never stored)
  *     y    = relu(conv1x1(t2; w3) + b3 + residual)                      64 -> 256                   identity shortcut
  *          | relu([t2 | x0] @ [w3 | wd]^T + (b3 + bd))                                              downsample shortcut
- *     next = relu(conv1x1(y; w1n) + b1n)                                256 -> 64                   (optional)
+ *     next = relu(conv1x1(y; w1n) + b1n)                                256 -> 64 | 128             (optional)
  * BatchNorm folded into w / b by the caller as for eqxv_conv2d_igemm_bf16. All tensors NHWC bf16; biases fp32.
  * Exactly one of `residual` (256 channels) / `x0` (the 64-channel input of the block's downsample convolution, w3 then
  * holds [w3 | wd] along K: [256, 128], b3 = b3 + bd) must be given. Rounding points are those of the layer-by-layer
@@ -139,11 +139,12 @@ typedef struct eqxv_bottleneck64_desc {
   const void* residual; /* bf16 [n, h, w, res_pitch], 256 channels, or NULL */
   const void* x0;       /* bf16 [n, h, w, x0_pitch], 64 channels, or NULL */
   void* y;              /* bf16 [n, h, w, y_pitch], 256 channels */
-  const void* w1n;      /* bf16 [64, 256] or NULL */
-  const float* b1n;     /* fp32 [64] or NULL */
-  void* next;           /* bf16 [n, h, w, next_pitch], 64 channels, or NULL */
+  const void* w1n;      /* bf16 [next_channels, 256] or NULL */
+  const float* b1n;     /* fp32 [next_channels] or NULL */
+  void* next;           /* bf16 [n, h, w, next_pitch], next_channels channels, or NULL */
   int32_t n, h, w;
   int32_t t1_pitch, res_pitch, x0_pitch, y_pitch, next_pitch;
+  int32_t next_channels; /* 64 (the next block of the same stage) or 128 (first block of the next stage); 0 without next */
 } eqxv_bottleneck64_desc;
 int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, void* stream);
 

@@ -118,7 +118,7 @@ def bottleneck64(t1, w2, b2, w3, b3, residual=None, x0=None, out=None, w1n=None,
     y = a.float() @ w3.float().t()
     _store(out, _epilogue(y, b3, 1, residual, False))
     if w1n is not None:
-        assert w1n.shape == (64, 256)
+        assert w1n.shape in ((64, 256), (128, 256)) and next_out.shape[-1] >= w1n.shape[0]
         _store(next_out, _epilogue(out[..., :256].float() @ w1n.float().t(), b1n, 1, None, False))
 
 

@@ -505,11 +505,13 @@ def test_gemm_with_se_gate_on_the_a_operand(device, n_img, hw, k, n, res):
     assert rel_l2(got, want) < 1e-3     # (tile shapes may differ between the pair and single-CTA kernels: not bitwise)
 
 
-# n, h, w, downsample shortcut, fused next conv1
-BOTTLENECK_CASES = [(2, 56, 56, False, False), (3, 56, 56, False, True), (2, 56, 56, True, True), (1, 56, 56, True, False),
-                    (3, 24, 40, False, True),      # odd tile count: the pair's phantom tile
-                    (2, 30, 23, True, True),       # ragged edges in both directions
-                    (37, 56, 56, False, True)]     # more pairs than clusters: several tiles per CTA, slot / phase wrap
+# n, h, w, downsample shortcut, output channels of the fused next conv1 (0: none)
+BOTTLENECK_CASES = [(2, 56, 56, False, 0), (3, 56, 56, False, 64), (2, 56, 56, True, 64), (1, 56, 56, True, 0),
+                    (3, 24, 40, False, 64),     # odd tile count: the pair's phantom tile
+                    (2, 30, 23, True, 64),      # ragged edges in both directions
+                    (37, 56, 56, False, 64),    # more pairs than clusters: several tiles per CTA, slot / phase wrap
+                    (35, 56, 56, False, 128),   # last block of the stage + the next stage's 256 -> 128 (resnet.py:290-297)
+                    (40, 56, 56, True, 64), (36, 56, 56, False, 0)]
 
 
 @pytest.mark.parametrize("case", BOTTLENECK_CASES, ids=lambda c: "x".join(map(str, c)))
@@ -523,11 +525,11 @@ def test_bottleneck64_fused(device, case):
     w2 = rb(device, 64, 3, 3, 64, scale=576 ** -0.5, seed=2)
     w3 = rb(device, 256, 64, scale=64 ** -0.5, seed=3)
     g = torch.Generator().manual_seed(4)
-    b2, b3, b1n, bd = (torch.randn(c, generator=g).to(device) * 0.5 for c in (64, 256, 64, 256))
+    b2, b3, b1n, bd = (torch.randn(c, generator=g).to(device) * 0.5 for c in (64, 256, max(nxt, 8), 256))
     res = rb(device, n, h, w, 256, seed=5) if not down else None
     x0 = rb(device, n, h, w, 64, seed=6) if down else None
     wd = rb(device, 256, 64, scale=64 ** -0.5, seed=7)
-    w1n = rb(device, 64, 256, scale=256 ** -0.5, seed=8) if nxt else None
+    w1n = rb(device, nxt, 256, scale=256 ** -0.5, seed=8) if nxt else None
     w3cat = torch.cat([w3, wd], dim=1).contiguous() if down else w3
     b3cat = b3 + bd if down else b3
     got = ops.bottleneck64(t1, w2.reshape(64, -1), b2, w3cat, b3cat, residual=res, x0=x0, w1n=w1n,
@@ -550,5 +552,18 @@ def test_bottleneck64_fused(device, case):
     if nxt:
         nr = F.relu(y.float() @ w1n.float().t() + b1n)      # on the kernel's own (bf16) y: isolates the last GEMM
         assert rel_l2(nx, nr) < TOL_BF16
-        n_layer = ops.conv2d(y, w1n, b1n, cin=256, cout=64, kh=1, kw=1, act=1)
+        n_layer = ops.conv2d(y, w1n, b1n, cin=256, cout=nxt, kh=1, kw=1, act=1)
         assert rel_l2(nx, n_layer) < 1e-3
+
+
+def test_bottleneck64_refuses_what_does_not_fit(device):
+    """downsample shortcut + a 128-wide next convolution needs 235 KB of shared memory (never occurs in ResNet: block 0
+    of a stage is not its last block): the entry fails loudly instead of launching"""
+    from eqxvision_b200 import _lib, ops
+
+    t1, x0 = rb(device, 1, 16, 16, 64), rb(device, 1, 16, 16, 64)
+    b = torch.zeros(256, device=device)
+    with pytest.raises(_lib.EqxvError, match="shared memory"):
+        ops.bottleneck64(t1, rb(device, 64, 576), b[:64], rb(device, 256, 128), b, x0=x0, w1n=rb(device, 128, 256), b1n=b[:128])
+    with pytest.raises(_lib.EqxvError, match="exactly one"):
+        ops.bottleneck64(t1, rb(device, 64, 576), b[:64], rb(device, 256, 64), b)

@@ -68,3 +68,10 @@ timed("fused identity", lambda: ops.bottleneck64(t1, w2, b2, w3, b3, residual=re
 timed("layer by layer: down + c2 + c3(+res) + next c1", layer_down)
 timed("fused downsample + next", lambda: ops.bottleneck64(t1, w2, b2, w3cat, b3, x0=x0, out=y, w1n=w1n, b1n=b1n, next_out=nx))
 timed("fused downsample", lambda: ops.bottleneck64(t1, w2, b2, w3cat, b3, x0=x0, out=y))
+w1n128 = rnd(128, 256, scale=1 / 16)
+b1n128 = torch.randn(128, device=dev) * 0.1
+nx128 = torch.empty(B, H, W, 128, device=dev, dtype=bf)
+timed("layer by layer: c2 + c3(+res) + next c1 (128)", lambda: (ops.conv2d(t1, w2, b2, cin=64, cout=64, kh=3, kw=3, pad=1, act=1, out=t2),
+                                                                 ops.conv2d(t2, w3, b3, cin=64, cout=256, kh=1, kw=1, act=1, residual=res, out=y),
+                                                                 ops.conv2d(y, w1n128, b1n128, cin=256, cout=128, kh=1, kw=1, act=1, out=nx128)))
+timed("fused identity + next (128)", lambda: ops.bottleneck64(t1, w2, b2, w3, b3, residual=res, out=y, w1n=w1n128, b1n=b1n128, next_out=nx128))
