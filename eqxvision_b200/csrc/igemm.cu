@@ -71,6 +71,12 @@ struct alignas(64) IgemmParams {
   // SqueezeExcitation gate applied to the A operand (kGate kernels, flat GEMMs): A[row, k] *= gate[row / gate_rpi, k]
   const __nv_bfloat16* gate;
   int gate_pitch, gate_rpi, gate_cols;
+  // Narrow-K A operand (kEpi16 kernels, flat GEMMs with ONE K block and k < 64): a TMA box that reaches past the tensor's
+  // inner extent is served at a fraction of the normal rate (measured: [1.6 M x 24] -> 144 columns runs at 1.3 TB/s,
+  // the same rows padded to 64 columns at 5.9 TB/s), so warp 0 gathers the rows with 16-byte cp.async instead.
+  const __nv_bfloat16* ga_ptr;
+  const __nv_bfloat16* gb_ptr;   // the filter [cout, gb_pitch]: gathered ONCE per CTA into a resident slab at off_bres
+  int ga_on, ga_pitch, ga_rows, ga_k16, gb_pitch, off_bres;
   // first-layer (halo) kernel only
   int h_stride, h_planes, h_px, h_rows, h_plane_pitch, h_stage_bytes, h_ksteps, h_off_b;
   const void* h_src;  // padded NHWC8 image [n, in_h, in_w, 8]
@@ -490,11 +496,103 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
   __syncwarp();
 }
 
+// ============================== epilogue, sixteen warps (epi_sub == 4) ==============================
+// Shallow-K layers without a residual whose tile is ALL epilogue (EfficientNet / MobileNet 1x1 expansions: one K block,
+// 128 x N outputs through an activation; ncu on EfficientNet-B4's 24 -> 144 @112^2: 1.6 TB/s of output with eight warps,
+// issue slots 20 % busy - a latency chain per chunk with two warps per SM sub-partition to hide it). Four warps per
+// TMEM lane quadrant take every fourth 64-column chunk; the chunk goes through in four 16-column steps with the next
+// step's tcgen05.ld in flight (the fused bottleneck kernel's e3, csrc/bottleneck.cu): ~60 live registers, which is what
+// lets 18 warps share the register file. One staging slab per warp, bf16 output, no residual, no LayerNorm folding.
+constexpr int kThreads16 = 64 + 32 * 16;
+template <int kAct>
+__device__ __forceinline__ void epilogue_warps16(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
+                                                 const uint32_t tmem_base, const int warp, const int lane) {
+  const int S = p.stages;
+  const int t_first = (int)blockIdx.x, t_stride = (int)gridDim.x;
+  const uint32_t bars = base + p.off_bars;
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  constexpr int CH = 64;
+  constexpr int nsub = 4;
+  const int quad = warp & 3;
+  const int sub = (warp - 2) >> 2;
+  const int wid = quad * nsub + sub;
+  const int cpt = (p.block_n + CH - 1) / CH;
+  const float* s_bias = reinterpret_cast<const float*>(gbase + p.off_bias);
+  const int so = quad * 32;
+  const int w_off = so % p.tw, h_off = (so / p.tw) % p.th, n_off = so / (p.tw * p.th);
+  constexpr uint32_t kSlab = 32 * 128;
+  const uint32_t out_u32 = base + p.off_out + (uint32_t)wid * kSlab;
+  uint8_t* out_row = gbase + p.off_out + (uint32_t)wid * kSlab;
+  auto release_acc = [&](int ti) {
+    tc_fence_before();
+    mbar_arrive(tempty_bar(ti & 1));
+  };
+  int cur_ti = -1;
+  int ti = sub / cpt, c = sub - ti * cpt;
+  int dec_ti = -1;
+  TileCoord t{};
+  for (;;) {
+    if (ti != dec_ti) {
+      t = decode_tile<false>(p, t_first + ti * t_stride);
+      dec_ti = ti;
+    }
+    bool done = false;
+    while (cur_ti < ti) {
+      ++cur_ti;
+      if ((long long)t_first + (long long)cur_ti * t_stride >= p.num_tiles) {
+        done = true;
+        break;
+      }
+      mbar_wait(tfull_bar(cur_ti & 1), (uint32_t)((cur_ti >> 1) & 1));
+      tc_fence_after();
+      if (cur_ti < ti) release_acc(cur_ti);
+    }
+    if (done) break;
+    const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ti & 1) * p.acc_stride) + (uint32_t)(c * CH);
+    const int ncols = min(CH, p.block_n - c * CH);   // multiple of 16
+    const float* bias_c = s_bias + t.ncol0 + c * CH;
+    float va[16], vb[16];
+    tmem_ld_x16(t_acc, va);
+    if (lane == 0) tma_store_wait_read<0>();   // the store that last used this warp's slab has read it
+    __syncwarp();
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      float* cur = (st & 1) ? vb : va;
+      float* nxt = (st & 1) ? va : vb;
+      uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
+      if (st * 16 < ncols) {   // warp-uniform
+        tmem_ld_wait();
+        if (st < 3 && (st + 1) * 16 < ncols) tmem_ld_x16(t_acc + (uint32_t)(16 * (st + 1)), nxt);
+        o0 = epilogue8<kAct, 0>(&cur[0], bias_c + 16 * st, make_uint4(0u, 0u, 0u, 0u));
+        o1 = epilogue8<kAct, 0>(&cur[8], bias_c + 16 * st + 8, make_uint4(0u, 0u, 0u, 0u));
+      }
+      *reinterpret_cast<uint4*>(out_row + sw128_off(lane, 2 * st)) = o0;
+      *reinterpret_cast<uint4*>(out_row + sw128_off(lane, 2 * st + 1)) = o1;
+    }
+    if (c + nsub >= cpt) release_acc(ti);   // this warp's last chunk of the tile
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(&p.tmC, out_u32, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off, t.n0 + n_off);
+      tma_store_commit();
+    }
+    __syncwarp();
+    c += nsub;
+    while (c >= cpt) {
+      c -= cpt;
+      ++ti;
+    }
+  }
+  if (lane == 0) tma_store_wait_all();
+  __syncwarp();
+}
+
 // kRes: 0 = no residual, 1 = act(acc + bias + res), 2 = act(acc + bias) + res. Compile-time so that the
 // unrolled epilogue is straight-line code (a runtime flag doubled its instruction count and made the
 // epilogue warps issue-bound on the HBM-bound layers: profiles/r01_layers_v4).
-template <bool kOutF32, int kAct, int kRes, int kLN = 0, bool kGate = false>
-__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+template <bool kOutF32, int kAct, int kRes, int kLN = 0, bool kGate = false, bool kEpi16 = false>
+__global__ void __launch_bounds__(kEpi16 ? kThreads16 : kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -503,7 +601,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = p.stages;
-  const uint32_t stage_bytes = kABytes + p.block_n * 128;
+  const bool gather = kEpi16 && p.ga_on;   // narrow-K layers: A gathered by warp 0, filter resident (IgemmParams::ga_*)
+  const uint32_t stage_bytes = gather ? (uint32_t)kABytes : (uint32_t)(kABytes + p.block_n * 128);
 
   const uint32_t bars = base + p.off_bars;
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -520,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     tma_prefetch_desc(&p.tmC);
     if (p.has_res) tma_prefetch_desc(&p.tmR);
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), gather ? 32u : 1u);   // gathered A: + the 32 lanes of warp 0
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -551,7 +650,65 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   const uint32_t tmem_base = *tmem_slot_g;
 
 
-  if (warp == 0) {
+  if (gather && warp == 0) {
+    // ============================== gathering producer (narrow K, see IgemmParams::ga_*) ==============================
+    // lane <-> rows lane, lane + 32, ... of a 128-row tile; chunk j of row r sits at r*128 + ((j ^ (r & 7)) << 4) (the
+    // layout a SWIZZLE_128B TMA box would have written). The chunks beyond K are zeroed once per stage and never touched
+    // again. The filter (<= 256 rows of k < 64) is gathered the same way ONCE, before the first tile is signalled.
+    const int k16 = p.ga_k16;
+    const uint32_t zero_chunks = (uint32_t)(8 - k16);
+    const uint32_t rows_total = (uint32_t)S * 128u + (uint32_t)p.block_n;   // A stages (16 KiB each), then the filter slab
+    for (uint32_t idx = (uint32_t)lane; idx < rows_total * zero_chunks; idx += 32u) {
+      const uint32_t rr = idx / zero_chunks, j = (uint32_t)k16 + idx % zero_chunks;
+      uint8_t* rowp = rr < (uint32_t)S * 128u ? gbase + rr * 128u : gbase + p.off_bres + (rr - (uint32_t)S * 128u) * 128u;
+      const uint32_t r = rr < (uint32_t)S * 128u ? (rr & 127u) : rr - (uint32_t)S * 128u;
+      *reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7u)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int r = lane; r < p.block_n; r += 32) {
+      const bool ok = r < p.cout;
+      const __nv_bfloat16* src = p.gb_ptr + (long long)(ok ? r : 0) * p.gb_pitch;
+      const uint32_t drow = base + (uint32_t)p.off_bres + (uint32_t)r * 128u;
+      for (int j = 0; j < k16; ++j) cp_async_16(drow + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4), src + 8 * j, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    constexpr int kLookahead = 3;   // tiles in flight (cp.async groups)
+    int stage = 0, cstage = 0, pending = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t dst = base + (uint32_t)stage * stage_bytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = lane + 32 * i;
+        const int gr = t.w0 + r;
+        const bool ok = gr < p.ga_rows;
+        const __nv_bfloat16* src = p.ga_ptr + (long long)(ok ? gr : 0) * p.ga_pitch;
+        const uint32_t drow = dst + (uint32_t)r * 128u;
+        for (int j = 0; j < k16; ++j) cp_async_16(drow + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4), src + 8 * j, ok);
+      }
+      cp_async_commit();
+      if (++pending == kLookahead) {
+        cp_async_wait<kLookahead - 1>();
+        fence_proxy_async_smem();
+        mbar_arrive(full_bar(cstage));
+        if (++cstage == S) cstage = 0;
+        --pending;
+      }
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (; pending > 0; --pending) {
+      mbar_arrive(full_bar(cstage));
+      if (++cstage == S) cstage = 0;
+    }
+  } else if (warp == 0) {
     // ============================== TMA producer ==============================
     // One elected thread runs the whole role (same reasoning as the MMA issuer below): per K block a
     // barrier wait, an expect_tx and two bulk-tensor loads; ring addresses advance incrementally.
@@ -651,6 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const uint32_t a_lo0 = ((base & 0x3FFFF) >> 4) | lbo;
       const uint32_t a_end = a_lo0 + (uint32_t)S * step;
       const uint32_t b_off = kABytes >> 4;
+      const uint32_t bres_lo = (((base + (uint32_t)p.off_bres) & 0x3FFFF) >> 4) | lbo;   // resident filter (gather mode)
       uint32_t a_lo = a_lo0;
       uint32_t fb = kGate ? bars + 8u * 32u : full_bar(0), eb = empty_bar(0);
       const uint32_t fb0 = fb, eb0 = eb;
@@ -680,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         for (int i = 0; i < nk; ++i) {
           mbar_wait(fb, phase);      // kGate: xf[stage], raised by the gate warps once the A tile is scaled
           tc_fence_after();
-          umma_bf16_kblock64(d_tmem, a_lo, a_lo + b_off, desc_hi, desc_hi, idesc, accumulate, eb);
+          umma_bf16_kblock64(d_tmem, a_lo, gather ? bres_lo : a_lo + b_off, desc_hi, desc_hi, idesc, accumulate, eb);
           accumulate = 1;
           a_lo += step, fb += 8, eb += 8;
           if (a_lo == a_end) {
@@ -695,7 +853,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
     __syncwarp();
   } else {
-    epilogue_warps<kOutF32, kAct, kRes, false, kLN>(p, base, gbase, tmem_base, warp, lane);
+    if constexpr (kEpi16) {
+      epilogue_warps16<kAct>(p, base, gbase, tmem_base, warp, lane);
+    } else {
+      epilogue_warps<kOutF32, kAct, kRes, false, kLN>(p, base, gbase, tmem_base, warp, lane);
+    }
   }
 
   // ---- teardown ----
@@ -1412,6 +1574,15 @@ static int choose_block_n_pair(int cout, long long pair_m_tiles, int kblocks, in
   return best_bn;
 }
 
+static KernelFn epi16_table(int act) {
+  static const KernelFn t[kNumActs] = {
+      igemm_kernel<false, 0, 0, 0, false, true>, igemm_kernel<false, 1, 0, 0, false, true>,
+      igemm_kernel<false, 2, 0, 0, false, true>, igemm_kernel<false, 3, 0, 0, false, true>,
+      igemm_kernel<false, 4, 0, 0, false, true>, igemm_kernel<false, 5, 0, 0, false, true>,
+      igemm_kernel<false, 6, 0, 0, false, true>, igemm_kernel<false, 7, 0, 0, false, true>};
+  return t[act];
+}
+
 static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -1505,11 +1676,35 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   p.epi_sub = (forced_sub == 1 || forced_sub == 2) ? forced_sub : (kblocks <= 4 ? 2 : 1);
   if (q.ln_mode != 0) p.epi_sub = 1;   // the folding lives in the four-warp epilogue
   if (q.gate) p.epi_sub = 1;           // warps 6..9 scale the A tiles
+  // sixteen warps where the tile is all epilogue: one or two K blocks, no residual, enough 64-column chunks per CTA
+  // for the extra warps to matter (see epilogue_warps16). EQXV_EPI_SUB=4 forces it where it is legal, =1/2 disables it.
+  bool epi16 = false;
+  {
+    const bool legal = !pair && !out_f32 && !q.res && q.ln_mode == 0 && !q.gate && !p.direct_out && !q.grouped &&
+                       block_n % 16 == 0;
+    const long long chunks = num_tiles * ceil_div(block_n, 64);
+    if (legal && (forced_sub == 4 || (forced_sub == 0 && kblocks <= 2 && chunks >= 8ll * device_sm_count()))) {
+      epi16 = true;
+      p.epi_sub = 4;
+    }
+  }
   // eight-warp epilogue: ONE staging slab per warp means every chunk waits until the TMA store of the previous chunk
   // has finished reading it; with a second slab (32 KiB more, one pipeline stage less) the store of chunk l overlaps the
   // math of chunk l+1. Worth it where the epilogue bounds the layer and the K loop is short (ResNet c3 layers).
   static const int obuf_env = getenv("EQXV_EPI_OBUFS") ? atoi(getenv("EQXV_EPI_OBUFS")) : 0;
-  int out_bytes = 2 * kStageBuf;
+  {
+    static const bool no_gather = getenv("EQXV_NO_GATHER_A") != nullptr;
+    const bool flat = q.tw == 128 && q.th == 1 && q.tn == 1 && q.kh == 1 && q.kw == 1;
+    const long long a_pitch = (long long)(q.a.strides_bytes[0] / 2);
+    if (epi16 && flat && q.kchunks == 1 && q.cin_pack < 64 && q.cin_pack % 8 == 0 && a_pitch % 8 == 0 && !no_gather &&
+        p.n_tiles == 1 && q.ktot % 8 == 0) {
+      p.ga_on = 1;
+      p.ga_ptr = static_cast<const __nv_bfloat16*>(q.a.base);
+      p.gb_ptr = static_cast<const __nv_bfloat16*>(q.wgt);
+      p.ga_pitch = (int)a_pitch, p.ga_rows = q.out_w, p.ga_k16 = q.cin_pack / 8, p.gb_pitch = q.ktot;
+    }
+  }
+  int out_bytes = epi16 ? 4 * kStageBuf : 2 * kStageBuf;   // sixteen warps: one 4 KiB slab each
   p.epi_obufs = 0;
   // Measured on ResNet-50 (A/B in one call, 3.457 vs 3.43 ms per step): no gain - the c3 layers are not waiting on
   // their staging slab - so the second slab stays opt-in (EQXV_EPI_OBUFS=2).
@@ -1520,12 +1715,16 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
       p.epi_obufs = 2;
     }
   }
-  const int fixed = out_bytes + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512;
-  int stages = (kMaxSmem - 1024 - fixed) / stage_bytes;
+  const int bres_bytes = p.ga_on ? ceil_div(block_n * 128, 1024) * 1024 : 0;   // resident filter slab (gather mode)
+  const int ring_stage = p.ga_on ? kABytes : stage_bytes;
+  const int fixed = out_bytes + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512 + bres_bytes;
+  int stages = (kMaxSmem - 1024 - fixed) / ring_stage;
   stages = std::min(stages, 8);
   EQXV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for block_n=%d", block_n);
+  EQXV_CHECK_ARG(!p.ga_on || stages >= 4, "igemm: internal: gather mode needs four stages");
   p.stages = stages;
-  p.off_out = stages * stage_bytes;
+  p.off_bres = stages * ring_stage;
+  p.off_out = p.off_bres + bres_bytes;
   p.off_res = p.off_out + out_bytes;
   p.off_bias = p.off_res + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0);
   p.off_wsum = p.off_bias + bias_one;
@@ -1588,6 +1787,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
     fn = q.act == EQXV_ACT_NONE ? igemm_kernel<false, 0, 0, 1> : igemm_kernel<false, EQXV_ACT_GELU_TANH, 0, 1>;
   if (q.ln_mode == 2) fn = igemm_kernel<false, 0, 1, 2>;
   if (q.gate) fn = q.res ? igemm_kernel<false, 0, 1, 0, true> : igemm_kernel<false, 0, 0, 0, true>;
+  if (epi16) fn = epi16_table(q.act);
   EQXV_CUDA(launch_kernel(fn, dim3(grid), dim3(64 + 128 * p.epi_sub + (q.gate ? 128 : 0)), (size_t)(smem_bytes), stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
@@ -1617,6 +1817,8 @@ static StemFn stem_table(int act) {
 }
 
 int igemm_init() {
+  for (int a = 0; a < kNumActs; ++a)
+    EQXV_CUDA(cudaFuncSetAttribute(epi16_table(a), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int i = 0; i < 8; ++i)
     EQXV_CUDA(cudaFuncSetAttribute(ln_kernels(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < kNumActs; ++a)

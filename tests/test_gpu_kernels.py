@@ -119,6 +119,9 @@ GEMM_CASES = [
     (12608, 2304, 768, 0, False, False), (12608, 768, 3072, 0, True, False), (12608, 3072, 768, 3, False, False),
     (256, 1000, 2048, 0, False, True), (300, 272, 1632, 0, False, False), (512, 24, 144, 2, False, False),
     (512, 64, 24, 1, False, False), (7, 448, 8, 5, False, False), (130, 2688, 112, 6, False, False),
+    # all-epilogue tiles (one K block, no residual, many chunks): the sixteen-warp epilogue (igemm.cu epilogue_warps16)
+    (200704, 144, 24, 2, False, False), (100352, 192, 32, 2, False, False), (50176, 336, 56, 2, False, False),
+    (160000, 64, 64, 1, False, False), (70000, 272, 128, 4, False, False),
 ]
 
 
