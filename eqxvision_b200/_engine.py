@@ -300,6 +300,19 @@ class Plan:
             self._input_nhwc[c_pad] = buf
         return self._input_nhwc[c_pad]
 
+    def _stem_input(self, ph: int, h: int, wd: int) -> torch.Tensor:
+        """the padded NHWC8 image the first-layer kernels read (eqxv_pack_stem_input / its uint8 twin), once per padding"""
+        if ph not in self._input_stem:
+            # the pack kernels write the zero border too: the whole buffer is rewritten every replay
+            xp = self.arena_ok(torch.zeros((self.n, h + 2 * ph, wd + 8, 8), dtype=BF16, device=self.device))
+            self.act_bytes += xp.numel() * 2
+            if self.u8 is not None:
+                self.step(ops.u8_pack_stem_input, x=self.x_in, lut=self.lut, pad=ph, out=xp)
+            else:
+                self.step(ops.pack_stem_input, x_nchw=self.x_in, pad=ph, out=xp)
+            self._input_stem[ph] = xp
+        return self._input_stem[ph]
+
     # ---- conv --------------------------------------------------------------------------------
     @staticmethod
     def _epilogue(e) -> Tuple[int, bool]:
@@ -352,44 +365,40 @@ class Plan:
             sb = self.emit(ce.s)          # gate first: its squeeze may ride in the depthwise kernel
             xb = self.emit(ce.x)
             if xb.pitch == c_in and c_in % 8 == 0 and sb.pitch >= c_in:
-                wp = self.const(_pack.pack_conv_weight(w, c_in))
+                tail = self.TAIL_SHIFT and _pack.tail_shift_applies(c_in)
+                wp = self.const(_pack.pack_conv_weight(w, c_in, tail_shift=tail))
                 self.step(ops.gemm_gated, a=xb.rows(c_in), gate=sb.rows(sb.pitch), wgt=wp, bias=bias_d,
-                          rows_per_image=h * wd, residual=None if res is None else res.rows(), out=out.rows())
+                          rows_per_image=h * wd, residual=None if res is None else res.rows(), out=out.rows(),
+                          k_tail_shift=tail)
                 return out
         if isinstance(xin.expr, T.Input):
             if c_in <= 8 and kh <= 8 and kw <= 8 and sh in (1, 2, 4) and dh == 1 and 2 * ph <= kw \
                     and res is None and not out_f32 and dst is None:
                 # first-layer conv on the raw image (resnet.py:243-251, vgg.py:137, efficientnet.py:327):
                 # padded NHWC8 image + one GEMM K-block per filter row (eqxv_conv_stem_bf16)
-                if ph not in self._input_stem:
-                    # the pack kernels write the zero border too: the whole buffer is rewritten every replay
-                    xp = self.arena_ok(torch.zeros((self.n, h + 2 * ph, wd + 8, 8), dtype=BF16, device=self.device))
-                    self.act_bytes += xp.numel() * 2
-                    if self.u8 is not None:
-                        self.step(ops.u8_pack_stem_input, x=self.x_in, lut=self.lut, pad=ph, out=xp)
-                    else:
-                        self.step(ops.pack_stem_input, x_nchw=self.x_in, pad=ph, out=xp)
-                    self._input_stem[ph] = xp
                 wp = self.const(_pack.pack_stem_weight(w))
-                self.step(ops.conv_stem, xpad=self._input_stem[ph], wgt=wp, bias=bias_d, n=self.n, h=h, w=wd,
+                self.step(ops.conv_stem, xpad=self._stem_input(ph, h, wd), wgt=wp, bias=bias_d, n=self.n, h=h, w=wd,
                           cout=cout, kh=kh, kw=kw, stride=sh, pad=ph, act=act, out=out.map(ho, wo))
                 return out
             xb = self.input_nhwc(_round8(c_in))
         else:
             xb = self.emit(xin)
         cin_eff = xb.cpad
-        wp = self.const(_pack.pack_conv_weight(w, cin_eff))
+        # every K chunk inside the tensor (EQXV_FLAG_K_TAIL_SHIFT): partially out-of-bounds TMA boxes are slow
+        tail = self.TAIL_SHIFT and _pack.tail_shift_applies(cin_eff)
+        wp = self.const(_pack.pack_conv_weight(w, cin_eff, tail_shift=tail))
         omap, rmap = out.map(ho, wo, cout if out_f32 else None), None if res is None else res.map(ho, wo)
         for n0, n1 in _n_chunks(cout):
             whole = (n0, n1) == (0, cout)
             self.step(ops.conv2d, x=xb.map(h, wd, cin_eff), wgt=wp[n0:n1], bias=None if bias_d is None else bias_d[n0:n1],
                       cin=cin_eff, cout=n1 - n0, kh=kh, kw=kw, stride=sh, pad=ph, dil=dh, act=act,
                       residual=None if rmap is None else rmap[..., n0:n1], res_after_act=res_after,
-                      out=omap if whole else omap[..., n0:n1], out_f32=out_f32)
+                      out=omap if whole else omap[..., n0:n1], out_f32=out_f32, k_tail_shift=tail)
         return out
 
     # ---- fused ResNet bottleneck (64-channel trunk) ---------------------------------------------
     BNECK_FUSE = os.environ.get("EQXV_NO_BNECK") != "1"
+    TAIL_SHIFT = os.environ.get("EQXV_NO_TAIL_SHIFT") != "1"   # in-bounds last K chunk (A/B switch)
 
     def _plain_conv(self, e, cin, cout, k, pad, act_name, res: bool) -> bool:
         """e is a dense stride-1 undilated k x k convolution cin -> cout with exactly this epilogue and a bias"""
@@ -669,7 +678,40 @@ class Plan:
         return Buf(src.t, src.c, self.n, (e.h, e.w))
 
     # ---- pooling -----------------------------------------------------------------------------
+    # Measured on B200 (tools/bench_tail.py, batch 256): stem 174 us + max-pool 118 us separately, 401 us fused - the 192
+    # red.global.max (bf16 x 8) per tile that combine the pooled pixels on tile borders cost more than the 822 MB of
+    # traffic the fusion removes. The kernel stays (bit-exact, tested) but the lowering uses it only on request.
+    STEM_POOL_FUSE = os.environ.get("EQXV_STEM_POOL") == "1"
+
+    def _emit_stem_maxpool(self, sym, e: T.Pool) -> Optional[Buf]:
+        """conv1 -> bn1 -> relu -> maxpool 3x3 / 2 / 1 (resnet.py:243-253) in ONE kernel: the convolution's output is
+        never materialised. Applies to a first-layer convolution with 64 filters whose output tiles into 16 x 8 blocks."""
+        ce = e.x.expr
+        if not (self.STEM_POOL_FUSE and e.mode == "max" and (e.k, e.stride, e.pad) == (3, 2, 1) and not e.ceil):
+            return None
+        if not (isinstance(ce, T.Conv) and id(ce) not in self.memo and isinstance(ce.x.expr, T.Input) and ce.groups == 1):
+            return None
+        cout, cin, kh, kw = ce.weight.shape
+        (sh, sw), (ph, pw), (dh, dw) = ce.stride, ce.padding, ce.dilation
+        _, hc, wc = e.x.shape
+        if not (cout == 64 and cin <= 8 and kh <= 8 and kw <= 8 and sh == sw and sh in (1, 2, 4) and ph == pw and dh == dw == 1
+                and 2 * ph <= kw and ce.res is None and ce.act1 == "relu" and ce.act2 is None and hc % 16 == 0 and wc % 8 == 0):
+            return None
+        w, b = _pack.fold_bn(ce.weight, ce.bias, ce.bn)
+        if b is None:
+            return None
+        _, h, wd = ce.x.shape
+        ho, wo = sym.shape[1:]
+        out = self.alloc(self.n * ho * wo, cout, (ho, wo))
+        self.step(ops.conv_stem_maxpool, xpad=self._stem_input(ph, h, wd), wgt=self.const(_pack.pack_stem_weight(w)),
+                  bias=self.const(b), n=self.n, h=h, w=wd, cout=cout, kh=kh, kw=kw, stride=sh, pad=ph, out=out.map(ho, wo))
+        return out
+
     def _emit_Pool(self, sym, e: T.Pool, dst: Optional[Buf] = None):
+        if dst is None:
+            fused = self._emit_stem_maxpool(sym, e)
+            if fused is not None:
+                return fused
         xb = self.emit(e.x)
         c, h, w = e.x.shape
         ho, wo = sym.shape[1:]

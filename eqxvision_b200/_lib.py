@@ -17,6 +17,7 @@ ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU_TANH, ACT_HARDSWISH, ACT_SIGMOID, ACT_HAR
 FLAG_OUT_F32 = 1
 FLAG_RES_AFTER_ACT = 2
 FLAG_GROUPED_BLOCK64 = 4
+FLAG_K_TAIL_SHIFT = 8
 
 ACT_BY_NAME = {
     None: ACT_NONE, "none": ACT_NONE, "identity": ACT_NONE, "relu": ACT_RELU, "silu": ACT_SILU,
@@ -61,8 +62,9 @@ SIGNATURES = {
     "eqxv_gemm_bias_act_res_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp],
     "eqxv_gemm_res_rowstats_bf16": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp],
     "eqxv_gemm_ln_act_bf16": [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _i64, _i64, _i32, _i32, _i32, _vp],
-    "eqxv_gemm_gated_bf16": [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp],
+    "eqxv_gemm_gated_bf16": [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp],
     "eqxv_conv_stem_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_conv_stem_maxpool_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_pack_stem_input": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -128,7 +130,7 @@ _initialised_device = None
 launch_count = 0  # number of kernel-launching C-ABI calls made by this process (bench bookkeeping)
 
 _LAUNCHING = {
-    "eqxv_conv2d_igemm_bf16", "eqxv_bottleneck64_fused_bf16", "eqxv_gemm_bias_act_res_bf16", "eqxv_conv_stem_bf16",
+    "eqxv_conv2d_igemm_bf16", "eqxv_bottleneck64_fused_bf16", "eqxv_conv_stem_maxpool_bf16", "eqxv_gemm_bias_act_res_bf16", "eqxv_conv_stem_bf16",
     "eqxv_pack_stem_input", "eqxv_nchw_f32_to_nhwc_bf16", "eqxv_nhwc_bf16_to_nchw_f32",
     "eqxv_maxpool2d_nhwc_bf16", "eqxv_maxpool2d_ceil_nhwc_bf16", "eqxv_avgpool2d_nhwc_bf16", "eqxv_adaptive_avgpool_nhwc_bf16",
     "eqxv_layernorm_bf16", "eqxv_attention_fwd_bf16", "eqxv_patchify_nchw_f32_bf16",

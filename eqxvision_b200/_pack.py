@@ -31,15 +31,41 @@ def fold_bn(weight: torch.Tensor, bias: Optional[torch.Tensor], bn) -> Tuple[tor
     return w.float(), (None if b is None else b.float())
 
 
-def pack_conv_weight(w_oihw: torch.Tensor, cin_pad: int) -> torch.Tensor:
-    """OIHW fp32 -> [O, kh*kw*cin_pad] bf16 (zero-padded input channels)"""
+def tail_shift_applies(cin_pad: int) -> bool:
+    """EQXV_FLAG_K_TAIL_SHIFT (include/eqxv_b200.h) is defined for dense filters with cin > 64, cin % 64 != 0"""
+    return cin_pad > 64 and cin_pad % 64 != 0
+
+
+def pack_conv_weight(w_oihw: torch.Tensor, cin_pad: int, tail_shift: bool = False) -> torch.Tensor:
+    """OIHW fp32 -> [O, kh*kw*cin_pad] bf16 (zero-padded input channels).
+    tail_shift (EQXV_FLAG_K_TAIL_SHIFT): [O, kh*kw*64*kc], kc = ceil(cin_pad / 64); per tap the last 64-wide chunk holds
+    channels [cin_pad - 64, cin_pad) - the chunk the kernel then fetches, entirely inside the tensor - with the columns
+    that repeat the previous chunk zeroed, so every product is still counted exactly once."""
     o, i, kh, kw = w_oihw.shape
     w = w_oihw.permute(0, 2, 3, 1).contiguous()  # O, kh, kw, I
     if cin_pad != i:
         wp = torch.zeros(o, kh, kw, cin_pad, dtype=w.dtype)
         wp[..., :i] = w
         w = wp
+    if tail_shift:
+        assert tail_shift_applies(cin_pad)
+        kc = -(-cin_pad // 64)
+        head = 64 * (kc - 1)
+        off = 64 * kc - cin_pad                      # columns of the last chunk that overlap the previous one
+        ws = torch.zeros(o, kh, kw, 64 * kc, dtype=w.dtype)
+        ws[..., :head] = w[..., :head]
+        ws[..., head + off:] = w[..., head:]
+        return ws.reshape(o, kh * kw * 64 * kc).to(torch.bfloat16).contiguous()
     return w.reshape(o, kh * kw * cin_pad).to(torch.bfloat16).contiguous()
+
+
+def unshift_tail(wp: torch.Tensor, taps: int, cin_pad: int) -> torch.Tensor:
+    """inverse of pack_conv_weight(tail_shift=True) on the packed matrix: [O, taps*64*kc] -> [O, taps*cin_pad]"""
+    o = wp.shape[0]
+    kc = -(-cin_pad // 64)
+    head, off = 64 * (kc - 1), 64 * kc - cin_pad
+    ws = wp.reshape(o, taps, 64 * kc)
+    return torch.cat([ws[..., :head], ws[..., head + off:]], dim=-1).reshape(o, taps * cin_pad).contiguous()
 
 
 def pack_grouped_weight(w: torch.Tensor, groups: int) -> torch.Tensor:

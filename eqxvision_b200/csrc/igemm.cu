@@ -42,6 +42,7 @@ struct alignas(64) IgemmParams {
   int kh, kw, dil_h, dil_w, pad_h, pad_w, mul_h, mul_w;
   int in_h, in_w;   // extent of A dims 2 / 1 (tap skipping)
   int kchunks;      // ceil(cin / 64)
+  int a_tail;       // EQXV_FLAG_K_TAIL_SHIFT: channel coordinate of the LAST K chunk's A box (cin - 64), else -1
   int cin_pack;     // K offset between consecutive taps in B
   int cout;
   int act, res_after_act, has_res;
@@ -77,6 +78,9 @@ struct alignas(64) IgemmParams {
   const __nv_bfloat16* ga_ptr;
   const __nv_bfloat16* gb_ptr;   // the filter [cout, gb_pitch]: gathered ONCE per CTA into a resident slab at off_bres
   int ga_on, ga_pitch, ga_rows, ga_k16, gb_pitch, off_bres;
+  // first-layer kernel with the 3x3 / stride 2 / pad 1 max-pool in its epilogue (stem_pool_epilogue)
+  __nv_bfloat16* pool_y;
+  int pool_h, pool_w, pool_pitch;
   // first-layer (halo) kernel only
   int h_stride, h_planes, h_px, h_rows, h_plane_pitch, h_stage_bytes, h_ksteps, h_off_b;
   const void* h_src;  // padded NHWC8 image [n, in_h, in_w, 8]
@@ -729,7 +733,8 @@ __global__ void __launch_bounds__(kEpi16 ? kThreads16 : kThreads, 1) igemm_kerne
             for (int c = 0; c < kchunks; ++c, kb += kBlockK) {
               mbar_wait(eb, phase ^ 1u);
               mbar_expect_tx(fb, stage_bytes);
-              tma_load_4d(dst, &p.tmA, fb, c * kBlockK + (p.grouped ? t.ncol0 : 0), wc, hc, t.n0);
+              const int ac = (c == kchunks - 1 && p.a_tail >= 0) ? p.a_tail : c * kBlockK;   // K_TAIL_SHIFT: in-bounds box
+              tma_load_4d(dst, &p.tmA, fb, ac + (p.grouped ? t.ncol0 : 0), wc, hc, t.n0);
               tma_load_2d(dst + kABytes, &p.tmB, fb, kb, t.ncol0);
               dst += stage_bytes, fb += 8, eb += 8;
               if (dst == dst_end) {
@@ -766,7 +771,7 @@ __global__ void __launch_bounds__(kEpi16 ? kThreads16 : kThreads, 1) igemm_kerne
       const int row = min(t.w0 + r, p.ln_rows - 1);   // rows past the end: zero-filled A, any gate will do
       const __nv_bfloat16* grow = p.gate + (long long)(row / p.gate_rpi) * p.gate_pitch;
       for (int i = 0; i < kchunks; ++i) {
-        const int k0 = i * kBlockK;
+        const int k0 = (i == kchunks - 1 && p.a_tail >= 0) ? p.a_tail : i * kBlockK;
         uint4 g[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)   // the gate does not depend on the tile data: in flight during the barrier wait
@@ -956,7 +961,7 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
             for (int c = 0; c < kchunks; ++c, kb += kBlockK) {
               mbar_wait(eb, phase ^ 1u);
               if (rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);   // both CTAs' bytes land on this barrier
-              tma_load_4d_pair(dst, &p.tmA, fb, c * kBlockK, wc, hc, t.n0);
+              tma_load_4d_pair(dst, &p.tmA, fb, (c == kchunks - 1 && p.a_tail >= 0) ? p.a_tail : c * kBlockK, wc, hc, t.n0);
               tma_load_2d_pair(dst + kABytes, &p.tmB, fb, kb, t.ncol0 + nrow);
               dst += stage_bytes, fb += 8, eb += 8;
               if (dst == dst_end) {
@@ -1114,7 +1119,98 @@ __device__ __forceinline__ void stem_gather(const IgemmParams& p, const uint32_t
   }
 }
 
-template <int kAct>
+// First-layer epilogue with the max-pool that follows it (resnet.py:243-253: conv1 -> bn1 -> relu -> maxpool 3x3 / 2 / 1):
+// the 411 MB conv1 output of a 256-image batch is neither written nor read back. The four warps that drain a tile
+// (8 columns x 16 rows of conv outputs) stage it in shared memory, then the same 128 threads reduce the 3x3 windows:
+// pooled pixel (ph, pw) needs conv rows 2ph-1..2ph+1 and columns 2pw-1..2pw+1, so with tile origins at multiples of
+// (16, 8) the pooled pixels 1..7 x 1..3 of a tile are complete inside it (plain 16-byte stores), the first / last
+// pooled row and column (ph % 8 == 0, pw % 4 == 0) collect contributions from two or four tiles: those go through
+// red.global.max (bf16 x 8 per instruction) on memory the host entry zeroed - exact and order-independent because
+// ReLU outputs are >= 0 (0 is the identity of max on them; the pool's own padding is -inf, i.e. "skip the tap").
+// Requires conv output extents that are multiples of (16, 8), cout == 64, ReLU: the entry checks.
+__device__ __forceinline__ uint4 bf16x8_max(const uint4 a, const uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+__device__ __forceinline__ void red_max_bf16x8(void* ptr, const uint4 v) {
+  asm volatile("red.global.max.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stem_pool_epilogue(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
+                                                   const uint32_t tmem_base, const int warp, const int lane) {
+  const int S = p.stages;
+  const int t_first = (int)blockIdx.x, t_stride = (int)gridDim.x;
+  const uint32_t bars = base + p.off_bars;
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  const int quad = warp & 3;
+  const int sub = ((warp - 2) >> 2) & 1;        // two groups of four warps take alternate tiles
+  const int r = quad * 32 + lane;               // accumulator row = conv pixel (r / 8, r % 8) of the tile
+  uint8_t* tb = gbase + p.off_out + (uint32_t)sub * kStageBuf;   // this group's tile: 128 rows x 128 B, XOR-swizzled
+  const float* s_bias = reinterpret_cast<const float*>(gbase + p.off_bias);
+  const uint32_t bar_id = 1u + (uint32_t)sub;
+  for (int ti = 0;; ++ti) {
+    const long long tile = (long long)t_first + (long long)ti * t_stride;
+    if (tile >= p.num_tiles) break;
+    mbar_wait(tfull_bar(ti & 1), (uint32_t)((ti >> 1) & 1));
+    tc_fence_after();
+    if ((ti & 1) != sub) {   // the other group's tile: hand the accumulator back at once (both groups arrive)
+      tc_fence_before();
+      mbar_arrive(tempty_bar(ti & 1));
+      continue;
+    }
+    const TileCoord t = decode_tile<false>(p, (int)tile);
+    const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ti & 1) * p.acc_stride);
+    named_bar_sync(bar_id, 128);   // the group's pooling reads of its previous tile are done
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float v[32];
+      tmem_ld_x16(t_acc + (uint32_t)(32 * hf), &v[0]);
+      tmem_ld_x16(t_acc + (uint32_t)(32 * hf + 16), &v[16]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(tb + sw128_off((uint32_t)r, (uint32_t)(4 * hf + j))) =
+            epilogue8<EQXV_ACT_RELU, 0>(&v[8 * j], s_bias + 32 * hf + 8 * j, make_uint4(0u, 0u, 0u, 0u));
+    }
+    tc_fence_before();
+    mbar_arrive(tempty_bar(ti & 1));
+    named_bar_sync(bar_id, 128);   // the tile is complete in shared memory
+    const int ph0 = t.h0 >> 1, pw0 = t.w0 >> 1;
+    for (int it = r; it < 45 * 8; it += 128) {
+      const int j = it & 7, pix = it >> 3;
+      const int phi = pix / 5, pwi = pix - phi * 5;
+      const int ph = ph0 + phi, pw = pw0 + pwi;
+      if (ph >= p.pool_h || pw >= p.pool_w) continue;
+      uint4 m = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int dr = -1; dr <= 1; ++dr) {
+        const int hr = 2 * phi + dr;
+        if (hr < 0 || hr > 15) continue;
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc) {
+          const int wc = 2 * pwi + dc;
+          if (wc < 0 || wc > 7) continue;
+          const uint32_t rr = (uint32_t)(hr * 8 + wc);
+          m = bf16x8_max(m, *reinterpret_cast<const uint4*>(tb + sw128_off(rr, (uint32_t)j)));
+        }
+      }
+      __nv_bfloat16* dst = p.pool_y + (((long long)t.n0 * p.pool_h + ph) * p.pool_w + pw) * p.pool_pitch + 8 * j;
+      if (phi >= 1 && phi <= 7 && pwi >= 1 && pwi <= 3) {
+        *reinterpret_cast<uint4*>(dst) = m;
+      } else {
+        red_max_bf16x8(dst, m);
+      }
+    }
+  }
+}
+
+template <int kAct, bool kPool = false>
 __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -1134,7 +1230,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmB);
-    tma_prefetch_desc(&p.tmC);
+    if (!kPool) tma_prefetch_desc(&p.tmC);
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 32 * kStemProducers);  // every producer lane arrives once its copies landed
       mbar_init(empty_bar(s), 1);
@@ -1223,7 +1319,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     }
     __syncwarp();
   } else if (warp < 2 + 4 * p.epi_sub) {
-    epilogue_warps<false, kAct, 0>(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
+    if constexpr (kPool) {
+      stem_pool_epilogue(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
+    } else {
+      epilogue_warps<false, kAct, 0>(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
+    }
   } else {
     stem_gather(p, base, warp - (1 + 4 * p.epi_sub));  // producer warps 1..3
   }
@@ -1320,7 +1420,8 @@ __global__ void __launch_bounds__(kThreads, 1) halo_kernel(const __grid_constant
         for (int c = 0; c < kchunks; ++c) {
           mbar_wait(aempty_bar(sa), pa ^ 1u);
           mbar_expect_tx(afull_bar(sa), a_bytes);
-          tma_load_4d(a_smem + sa * p.h_stage_bytes, &p.tmA, afull_bar(sa), c * kBlockK, t.w0 - p.pad_w,
+          tma_load_4d(a_smem + sa * p.h_stage_bytes, &p.tmA, afull_bar(sa),
+                      (c == kchunks - 1 && p.a_tail >= 0) ? p.a_tail : c * kBlockK, t.w0 - p.pad_w,
                       t.h0 - p.pad_h, t.n0);
           if (++sa == SA) {
             sa = 0;
@@ -1480,6 +1581,8 @@ struct IgemmProblem {
   int kh, kw, dil_h, dil_w, pad_h, pad_w, mul_h, mul_w;
   int in_h, in_w;
   int kchunks, cin_pack;
+  int cin;      // logical input channels (gate extent)
+  int a_tail;   // see IgemmParams
   int act, flags;
   int grouped;
   // LayerNorm folding (flat GEMMs): 0 none, 1 consumer, 2 producer (see IgemmParams)
@@ -1624,6 +1727,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   p.pad_h = q.pad_h, p.pad_w = q.pad_w, p.mul_h = q.mul_h, p.mul_w = q.mul_w;
   p.in_h = q.in_h, p.in_w = q.in_w;
   p.kchunks = q.kchunks, p.cin_pack = q.cin_pack;
+  p.a_tail = q.a_tail;
   p.cout = q.cout;
   p.act = q.act;
   p.res_after_act = (q.flags & EQXV_FLAG_RES_AFTER_ACT) ? 1 : 0;
@@ -1657,7 +1761,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
                        q.ln_mode == 0 && q.act == EQXV_ACT_NONE && !(q.flags & EQXV_FLAG_RES_AFTER_ACT),
                    "igemm: the gated A operand needs a flat bf16 GEMM without activation");
     p.gate = static_cast<const __nv_bfloat16*>(q.gate), p.gate_pitch = q.gate_pitch, p.gate_rpi = q.gate_rpi;
-    p.gate_cols = q.cin_pack;
+    p.gate_cols = q.cin;
     p.ln_rows = q.out_w;
   }
   if (q.ln_mode != 0) {
@@ -1823,6 +1927,7 @@ int igemm_init() {
     EQXV_CUDA(cudaFuncSetAttribute(ln_kernels(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < kNumActs; ++a)
     EQXV_CUDA(cudaFuncSetAttribute(stem_table(a), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  EQXV_CUDA(cudaFuncSetAttribute(stem_kernel<EQXV_ACT_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < 3; ++a)
     for (int r = 0; r < 3; ++r)
       EQXV_CUDA(cudaFuncSetAttribute(halo_table(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -1871,7 +1976,10 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
   p.kh = d->kh, p.kw = d->kw, p.dil_h = p.dil_w = d->dil, p.pad_h = p.pad_w = d->pad;
   p.mul_h = p.mul_w = 1;
   p.in_h = d->h, p.in_w = d->w;
-  p.kchunks = kchunks, p.cin_pack = d->cin;
+  const bool tail = (d->flags & EQXV_FLAG_K_TAIL_SHIFT) != 0;
+  const int cin_pack = tail ? kchunks * kBlockK : d->cin;
+  p.kchunks = kchunks, p.cin_pack = cin_pack;
+  p.a_tail = tail ? d->cin - kBlockK : -1;
   p.cout = d->cout, p.act = d->act, p.bias = d->bias;
   p.res_after_act = (d->flags & EQXV_FLAG_RES_AFTER_ACT) ? 1 : 0;
   p.has_res = d->residual ? 1 : 0;
@@ -1932,7 +2040,7 @@ static int launch_halo(const eqxv_conv_desc* d, int ho, int wo, cudaStream_t str
   b.base = const_cast<void*>(d->wgt);
   b.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   b.rank = 2;
-  const int ktot = d->kh * d->kw * d->cin;
+  const int ktot = d->kh * d->kw * cin_pack;
   b.dims[0] = (uint64_t)ktot, b.dims[1] = (uint64_t)d->cout;
   b.strides_bytes[0] = (uint64_t)ktot * 2;
   b.box[0] = kBlockK, b.box[1] = (uint32_t)block_n;
@@ -2009,6 +2117,10 @@ static int conv_impl(const eqxv_conv_desc* d, const LnFold* ln, void* stream) {
   if (grouped)
     EQXV_CHECK_ARG(d->cin == d->cout && d->cin % 64 == 0 && !f32,
                    "conv: GROUPED_BLOCK64 needs cin == cout, a multiple of 64, bf16 output");
+  const bool tail = (d->flags & EQXV_FLAG_K_TAIL_SHIFT) != 0;
+  if (tail)
+    EQXV_CHECK_ARG(!grouped && d->cin > kBlockK && d->cin % kBlockK != 0,
+                   "conv: K_TAIL_SHIFT needs a dense filter with cin > 64, cin %% 64 != 0 (cin = %d)", d->cin);
   if (!grouped && !ln && halo_eligible(d, ho, wo)) return launch_halo(d, ho, wo, (cudaStream_t)stream);
 
   IgemmProblem q{};
@@ -2019,7 +2131,10 @@ static int conv_impl(const eqxv_conv_desc* d, const LnFold* ln, void* stream) {
   }
   q.grouped = grouped ? 1 : 0;
   q.wgt = d->wgt;
-  q.ktot = d->kh * d->kw * (grouped ? 64 : d->cin);
+  const int cin_pack = grouped ? 64 : (tail ? ceil_div(d->cin, kBlockK) * kBlockK : d->cin);
+  q.ktot = d->kh * d->kw * cin_pack;
+  q.cin = d->cin;
+  q.a_tail = tail ? d->cin - kBlockK : -1;
   q.bias = d->bias;
   q.y = d->y;
   q.res = d->residual;
@@ -2029,7 +2144,7 @@ static int conv_impl(const eqxv_conv_desc* d, const LnFold* ln, void* stream) {
   q.act = d->act;
   q.flags = d->flags;
   q.kchunks = grouped ? 1 : ceil_div(d->cin, kBlockK);
-  q.cin_pack = grouped ? 64 : d->cin;
+  q.cin_pack = cin_pack;
   q.a.base = const_cast<void*>(d->x);
   q.a.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   q.a.rank = 4;
@@ -2122,19 +2237,37 @@ extern "C" int eqxv_gemm_ln_act_bf16(const void* a, int64_t lda, const void* w, 
 
 extern "C" int eqxv_gemm_gated_bf16(const void* a, int64_t lda, const void* gate, int64_t ldg, int32_t rows_per_image,
                                     const void* w, const float* bias, const void* residual, int64_t ldr, void* out,
-                                    int64_t ldo, int64_t m, int32_t n, int32_t k, void* stream) {
+                                    int64_t ldo, int64_t m, int32_t n, int32_t k, int32_t flags, void* stream) {
   EQXV_CHECK_ARG(m > 0 && m < (1ll << 31) && n > 0 && k > 0 && k % 8 == 0, "gemm_gated: bad shape");
+  EQXV_CHECK_ARG((flags & ~EQXV_FLAG_K_TAIL_SHIFT) == 0, "gemm_gated: only EQXV_FLAG_K_TAIL_SHIFT is accepted");
   EQXV_CHECK_ARG(gate && rows_per_image > 0 && ldg >= k && ldg % 8 == 0 && ((uintptr_t)gate & 15) == 0,
                  "gemm_gated: gate must be a 16-byte aligned bf16 [images, >= k] matrix");
   eqxv_conv_desc d{};
   gemm_desc(d, a, lda, w, bias, residual, ldr, out, ldo, m, n, k, EQXV_ACT_NONE);
+  d.flags = flags;
   LnFold ln{0, nullptr, nullptr, 0, 0.f, 0.f, gate, (int)ldg, rows_per_image};
   return conv_impl(&d, &ln, stream);
 }
 
+static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n, int32_t h, int32_t w,
+                          int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t y_pitch, int32_t act,
+                          bool pool, void* stream);
+
 extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n,
                                    int32_t h, int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride,
                                    int32_t pad, int32_t y_pitch, int32_t act, void* stream) {
+  return conv_stem_impl(xpad, wgt, bias, y, n, h, w, cout, kh, kw, stride, pad, y_pitch, act, false, stream);
+}
+
+extern "C" int eqxv_conv_stem_maxpool_bf16(const void* xpad, const void* wgt, const float* bias, void* y_pooled, int32_t n,
+                                           int32_t h, int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride,
+                                           int32_t pad, int32_t y_pitch, void* stream) {
+  return conv_stem_impl(xpad, wgt, bias, y_pooled, n, h, w, cout, kh, kw, stride, pad, y_pitch, EQXV_ACT_RELU, true, stream);
+}
+
+static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n, int32_t h, int32_t w,
+                          int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t y_pitch, int32_t act,
+                          bool pool, void* stream) {
   EQXV_CHECK_ARG(xpad && wgt && y, "stem: null pointer");
   EQXV_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0, "stem: bad shape");
   EQXV_CHECK_ARG(kh >= 1 && kh <= 8 && kw >= 1 && kw <= 8 && stride >= 1 && stride <= 4 && pad >= 0 &&
@@ -2145,6 +2278,10 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
   EQXV_CHECK_ARG(ho > 0 && wo > 0, "stem: empty output");
   const int hp = h + 2 * pad, wp = w + 8;  // layout written by eqxv_pack_stem_input
   EQXV_CHECK_ARG(act >= 0 && act < kNumActs, "stem: unknown activation %d", act);
+  if (pool)
+    EQXV_CHECK_ARG(cout == 64 && ho % 16 == 0 && wo % 8 == 0 && (stride == 1 || stride == 2 || stride == 4) && y_pitch % 8 == 0 &&
+                       ((uintptr_t)y & 15) == 0,
+                   "stem+maxpool: needs cout == 64 and a conv output of (16 a) x (8 b) pixels (got %d x %d x %d)", cout, ho, wo);
   if (cout <= 256 && (stride == 1 || stride == 2 || stride == 4)) {
     // ---- halo kernel: one staged image tile serves every filter tap ----
     IgemmParams p;
@@ -2183,7 +2320,7 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
     // ~2000-cycle chain per tile bounded the kernel (188 us against 98 us of HBM traffic); two warps per
     // quadrant take alternate tiles.
     static const int stem_sub = getenv("EQXV_STEM_SUB") ? atoi(getenv("EQXV_STEM_SUB")) : 0;
-    p.epi_sub = stem_sub == 1 ? 1 : 2;
+    p.epi_sub = (stem_sub == 1 && !pool) ? 1 : 2;   // the pooling epilogue is written for two groups of four warps
     p.off_bias = p.off_res;
   p.off_bars = p.off_bias + bias_bytes;
     const int smem_bytes = p.off_bars + 256 + 1024;
@@ -2203,6 +2340,21 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
     b.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
     rc = encode_tmap(&p.tmB, b);
     if (rc) return rc;
+    if (pool) {
+      // pooled rows ph % 8 == 0 and columns pw % 4 == 0 collect red.max contributions from several tiles: zero them
+      // (ReLU outputs are >= 0); everything else is written exactly once with plain stores
+      const int ph = ho / 2, pw = wo / 2;
+      p.pool_y = static_cast<__nv_bfloat16*>(y), p.pool_h = ph, p.pool_w = pw, p.pool_pitch = y_pitch;
+      const size_t px = (size_t)y_pitch * 2;
+      EQXV_CUDA(cudaMemset2DAsync(y, 8 * pw * px, 0, pw * px, (size_t)n * ph / 8, (cudaStream_t)stream));
+      EQXV_CUDA(cudaMemset2DAsync(y, 4 * px, 0, (size_t)cout * 2, (size_t)n * ph * pw / 4, (cudaStream_t)stream));
+      const int grid = std::min(p.num_tiles, device_sm_count());
+      EQXV_CUDA(launch_kernel(stem_kernel<EQXV_ACT_RELU, true>, dim3(grid),
+                              dim3(64 + 128 * p.epi_sub + 32 * (kStemProducers - 1)), (size_t)(smem_bytes),
+                              (cudaStream_t)stream, p));
+      EQXV_CUDA(cudaGetLastError());
+      return EQXV_OK;
+    }
     TmapSpec c{};
     c.base = y;
     c.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -2221,6 +2373,7 @@ extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const floa
     EQXV_CUDA(cudaGetLastError());
     return EQXV_OK;
   }
+  EQXV_CHECK_ARG(!pool, "stem+maxpool: unsupported geometry");
   IgemmProblem q{};
   q.wgt = wgt;
   q.ktot = kh * 64;

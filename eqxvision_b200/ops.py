@@ -27,9 +27,10 @@ def conv_out_size(h, k, stride, pad, dil):
 
 
 def conv2d(x, wgt, bias, *, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, residual=None,
-           res_after_act=False, out=None, out_f32=False, grouped_block64=False, stream=0):
+           res_after_act=False, out=None, out_f32=False, grouped_block64=False, k_tail_shift=False, stream=0):
     """x: [N,H,W,x_pitch] bf16 view (last-dim stride 1); wgt: [cout, kh*kw*cin] bf16; bias fp32 [cout].
-    grouped_block64: block-diagonal grouped convolution, wgt [cout, kh*kw*64] (_pack.pack_grouped_weight)."""
+    grouped_block64: block-diagonal grouped convolution, wgt [cout, kh*kw*64] (_pack.pack_grouped_weight).
+    k_tail_shift: wgt packed by _pack.pack_conv_weight(tail_shift=True) (EQXV_FLAG_K_TAIL_SHIFT)."""
     _check_cuda(x, wgt, bias, residual, out)
     n, h, w, _ = x.shape
     x_pitch = x.stride(2)
@@ -45,7 +46,7 @@ def conv2d(x, wgt, bias, *, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, re
     d.res_pitch = residual.stride(2) if residual is not None else 0
     d.act = act
     d.flags = (_lib.FLAG_OUT_F32 if out_f32 else 0) | (_lib.FLAG_RES_AFTER_ACT if res_after_act else 0) | \
-        (_lib.FLAG_GROUPED_BLOCK64 if grouped_block64 else 0)
+        (_lib.FLAG_GROUPED_BLOCK64 if grouped_block64 else 0) | (_lib.FLAG_K_TAIL_SHIFT if k_tail_shift else 0)
     call("eqxv_conv2d_igemm_bf16", C.byref(d), stream)
     return out
 
@@ -120,7 +121,7 @@ def gemm_ln(a, wgt, bias, wsum, stats, eps, *, act=0, out=None, stream=0):
     return out
 
 
-def gemm_gated(a, gate, wgt, bias, *, rows_per_image, residual=None, out=None, stream=0):
+def gemm_gated(a, gate, wgt, bias, *, rows_per_image, residual=None, out=None, k_tail_shift=False, stream=0):
     """out = (a * gate[row // rows_per_image]) @ wgt^T + bias (+ residual): the SE gate applied to the A operand inside
     the projection GEMM (eqxv_gemm_gated_bf16); a [m, k], gate [images, >= k] bf16"""
     _check_cuda(a, gate, wgt, bias, residual, out)
@@ -129,7 +130,8 @@ def gemm_gated(a, gate, wgt, bias, *, rows_per_image, residual=None, out=None, s
     if out is None:
         out = torch.empty((m, n), dtype=BF16, device=a.device)
     call("eqxv_gemm_gated_bf16", ptr(a), a.stride(0), ptr(gate), gate.stride(0), rows_per_image, ptr(wgt), ptr(bias),
-         ptr(residual), residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), m, n, k, stream)
+         ptr(residual), residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), m, n, k,
+         _lib.FLAG_K_TAIL_SHIFT if k_tail_shift else 0, stream)
     return out
 
 
@@ -150,6 +152,18 @@ def conv_stem(xpad, wgt, bias, *, n, h, w, cout, kh=7, kw=7, stride=2, pad=3, ac
         out = torch.empty((n, ho, wo, cout), dtype=BF16, device=xpad.device)
     call("eqxv_conv_stem_bf16", ptr(xpad), ptr(wgt), ptr(bias), ptr(out), n, h, w, cout, kh, kw, stride, pad,
          out.stride(2), act, stream)
+    return out
+
+
+def conv_stem_maxpool(xpad, wgt, bias, *, n, h, w, cout, kh=7, kw=7, stride=2, pad=3, out=None, stream=0):
+    """first-layer convolution + ReLU + max-pool 3x3 / 2 / 1 in one kernel (eqxv_conv_stem_maxpool_bf16); out:
+    [n, ho/2, wo/2, cout] with ho, wo the convolution's output extents"""
+    _check_cuda(xpad, wgt, bias, out)
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho // 2, wo // 2, cout), dtype=BF16, device=xpad.device)
+    call("eqxv_conv_stem_maxpool_bf16", ptr(xpad), ptr(wgt), ptr(bias), ptr(out), n, h, w, cout, kh, kw, stride, pad,
+         out.stride(2), stream)
     return out
 
 

@@ -53,7 +53,14 @@ enum {
   /* grouped convolution (equinox.nn.Conv2d(groups=G), resnet.py:19-23,83: ResNeXt) stored block-diagonally:
    * output channels [64b, 64b+64) read only input channels [64b, 64b+64); wgt is [cout, kh*kw*64]
    * (zero outside a group's own channels). Requires cin == cout, cin % 64 == 0, 64 % (cin/G) == 0. */
-  EQXV_FLAG_GROUPED_BLOCK64 = 4
+  EQXV_FLAG_GROUPED_BLOCK64 = 4,
+  /* Dense filters with cin > 64 and cin % 64 != 0: a TMA box that reaches past the tensor's inner extent is served at
+   * a fraction of the normal rate (measured on B200: the same rows run 2-3.6x faster when every box is in bounds), so
+   * the LAST 64-wide K chunk of the activation is fetched from channels [cin - 64, cin) instead of [64 (kc-1), 64 kc).
+   * wgt is then [cout, kh*kw * 64 kc] (kc = ceil(cin / 64)): per tap, chunks 0 .. kc-2 as usual, the last chunk holds
+   * the filter of channels [cin - 64, cin) with the 64 kc - cin columns that repeat the previous chunk set to ZERO
+   * (eqxvision_b200/_pack.py: pack_conv_weight(tail_shift=True)). Results are unchanged. */
+  EQXV_FLAG_K_TAIL_SHIFT = 8
 };
 
 const char* eqxv_version(void);
@@ -116,7 +123,7 @@ int eqxv_gemm_ln_act_bf16(const void* a, int64_t lda, const void* w, const float
  * the separate gate pass stored), so the expanded tensor is read ONCE and never rewritten. gate: bf16 [images, ldg]. */
 int eqxv_gemm_gated_bf16(const void* a, int64_t lda, const void* gate, int64_t ldg, int32_t rows_per_image, const void* w,
                          const float* bias, const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t m,
-                         int32_t n, int32_t k, void* stream);
+                         int32_t n, int32_t k, int32_t flags /* 0 or EQXV_FLAG_K_TAIL_SHIFT */, void* stream);
 
 /* K1 + K2 + K4 fused across layer boundaries: one whole ResNet bottleneck with a 64-channel trunk (resnet.py:144-162
  * as instantiated by resnet.py:288-296: layer1 of ResNet-50/101/152), minus its first 1x1 convolution, plus - optionally -
@@ -156,6 +163,14 @@ int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, void* stream);
 int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n, int32_t h,
                         int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
                         int32_t y_pitch, int32_t act, void* stream);
+/* ... with the max-pool that follows it in the ResNet stem (resnet.py:243-253: conv1 -> bn1 -> relu -> maxpool 3x3 /
+ * stride 2 / pad 1) in the kernel's epilogue: y_pooled is bf16 [n, ho/2, wo/2, y_pitch]; the conv output itself (411 MB
+ * for a 256-image batch) is never written. ReLU is implied (0 is then the identity of max, which is what lets the pooled
+ * pixels on tile borders be combined with red.global.max). Needs cout == 64 and conv output extents ho % 16 == 0,
+ * wo % 8 == 0; anything else fails with EQXV_ERR_INVALID_ARGUMENT (use the two separate entries). */
+int eqxv_conv_stem_maxpool_bf16(const void* xpad, const void* wgt, const float* bias, void* y_pooled, int32_t n, int32_t h,
+                                int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
+                                int32_t y_pitch, void* stream);
 /* fp32 NCHW [n,c<=8,h,w] (the reference's input layout, README.md:45) -> bf16 [n, h+2*pad, w+8, 8]:
  * the image sits at rows pad..h+pad-1, columns pad..w+pad-1; border and channels >= c are zero. */
 int eqxv_pack_stem_input(const float* x_nchw, void* xpad, int32_t n, int32_t c, int32_t h, int32_t w,

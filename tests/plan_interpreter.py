@@ -85,9 +85,26 @@ def conv_stem(xpad, wgt, bias, n, h, w, cout, kh, kw, stride, pad, act, out, **_
     _store(out, _epilogue(y, bias, act, None, False))
 
 
+def conv_stem_maxpool(xpad, wgt, bias, n, h, w, cout, kh, kw, stride, pad, out, **_):
+    """include/eqxv_b200.h eqxv_conv_stem_maxpool_bf16: the stem convolution + ReLU (rounded to the activation dtype, as the
+    separate entry stored it), then max-pool 3x3 / 2 / 1"""
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    assert cout == 64 and ho % 16 == 0 and wo % 8 == 0, "stem+maxpool: geometry the fused entry refuses"
+    y = torch.empty((n, ho, wo, cout), dtype=out.dtype)
+    conv_stem(xpad, wgt, bias, n, h, w, cout, kh, kw, stride, pad, 1, y)
+    maxpool2d(y, 3, 2, 1, out)
+
+
 def conv2d(x, wgt, bias, cin, cout, kh, kw, stride=1, pad=0, dil=1, act=0, residual=None, res_after_act=False,
-           out=None, out_f32=False, grouped_block64=False, **_):
+           out=None, out_f32=False, grouped_block64=False, k_tail_shift=False, **_):
     assert cin % 8 == 0, "conv: cin must be a multiple of 8"
+    if k_tail_shift:   # include/eqxv_b200.h EQXV_FLAG_K_TAIL_SHIFT: the last chunk's overlap columns must be zero
+        from eqxvision_b200 import _pack
+
+        assert not grouped_block64 and cin > 64 and cin % 64 != 0 and wgt.shape[1] == kh * kw * 64 * -(-cin // 64)
+        kc, off = -(-cin // 64), 64 * -(-cin // 64) - cin
+        assert wgt.reshape(cout, kh * kw, 64 * kc)[..., 64 * (kc - 1):64 * (kc - 1) + off].abs().max() == 0
+        wgt = _pack.unshift_tail(wgt, kh * kw, cin)
     for t, what in ((x, "conv x"), (out, "conv y"), (residual, "conv residual")):
         _check_operand(t, what)
     assert out.stride(2) >= cout and (residual is None or residual.stride(2) >= cout)
@@ -152,10 +169,14 @@ def gemm_ln(a, wgt, bias, wsum, stats, eps, act, out, **_):
     _store(out, _act(y, act))
 
 
-def gemm_gated(a, gate, wgt, bias, rows_per_image, residual=None, out=None, **_):
+def gemm_gated(a, gate, wgt, bias, rows_per_image, residual=None, out=None, k_tail_shift=False, **_):
     """include/eqxv_b200.h K5 + K11: the SE gate multiplies the A operand (product rounded to the activation dtype, as
     the separate gate pass did), then the plain GEMM + bias (+ residual)"""
     k = a.shape[1]
+    if k_tail_shift:
+        from eqxvision_b200 import _pack
+
+        wgt = _pack.unshift_tail(wgt, 1, k)
     g = gate[:, :k].float().repeat_interleave(rows_per_image, 0)
     ag = (a.float() * g).to(a.dtype)
     gemm(ag, wgt, bias, 0, residual, False, out)
@@ -349,7 +370,7 @@ def u8_resize_bilinear(x, oh, ow, out, **_):
     out.copy_(y.round().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1))
 
 
-IMPLS = {f.__name__: f for f in (bottleneck64, gemm_gated, gemm_rowstats, gemm_ln, dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
+IMPLS = {f.__name__: f for f in (bottleneck64, conv_stem_maxpool, gemm_gated, gemm_rowstats, gemm_ln, dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
                                  nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
                                  maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d, patchify,
                                  vit_assemble_tokens, attention, attention_probs, gather_rows, resize_bilinear,

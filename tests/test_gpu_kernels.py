@@ -570,3 +570,74 @@ def test_bottleneck64_refuses_what_does_not_fit(device):
         ops.bottleneck64(t1, rb(device, 64, 576), b[:64], rb(device, 256, 128), b, x0=x0, w1n=rb(device, 128, 256), b1n=b[:128])
     with pytest.raises(_lib.EqxvError, match="exactly one"):
         ops.bottleneck64(t1, rb(device, 64, 576), b[:64], rb(device, 256, 64), b)
+
+
+# n, h, w, cin, cout, k, pad, dil, act, res   (cin > 64, cin % 64 != 0)
+TAIL_CASES = [(2, 56, 56, 144, 32, 1, 0, 1, 0, True),      # EfficientNet projection: three K chunks, single-CTA kernel
+              (2, 28, 28, 336, 56, 1, 0, 1, 0, False),     # six K chunks: CTA-pair kernel
+              (1, 14, 14, 1632, 272, 1, 0, 1, 2, False),   # 26 K chunks
+              (2, 30, 23, 72, 40, 3, 1, 1, 1, False),      # 3x3 through the halo kernel, two chunks per tap
+              (3, 17, 13, 200, 96, 3, 1, 1, 2, True),      # 3x3 through the generic kernel, ragged map
+              (2, 16, 16, 136, 64, 3, 2, 2, 0, False)]     # dilated
+
+
+@pytest.mark.parametrize("case", TAIL_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv2d_k_tail_shift(device, case):
+    """EQXV_FLAG_K_TAIL_SHIFT: the last K chunk fetched from channels [cin - 64, cin) (every TMA box in bounds) with the
+    filter packed to match: same result as the plain layout (to fp32 summation order) and as torch"""
+    from eqxvision_b200 import _pack, ops
+
+    n, h, w, cin, cout, k, pad, dil, act, res = case
+    x = rb(device, n, h, w, cin, seed=1)
+    wt = rb(device, cout, cin, k, k, scale=(k * k * cin) ** -0.5, seed=2).float().cpu()      # OIHW
+    bias = torch.randn(cout, generator=torch.Generator().manual_seed(3)).to(device)
+    ho, wo = ops.conv_out_size(h, k, 1, pad, dil), ops.conv_out_size(w, k, 1, pad, dil)
+    r = rb(device, n, ho, wo, cout, seed=4) if res else None
+    kw = dict(cin=cin, cout=cout, kh=k, kw=k, stride=1, pad=pad, dil=dil, act=act, residual=r)
+    plain = ops.conv2d(x, _pack.pack_conv_weight(wt, cin).to(device), bias, **kw)
+    ws = _pack.pack_conv_weight(wt, cin, tail_shift=True)
+    assert ws.shape == (cout, k * k * 64 * -(-cin // 64))
+    assert torch.equal(_pack.unshift_tail(ws, k * k, cin), _pack.pack_conv_weight(wt, cin))
+    y = ops.conv2d(x, ws.to(device), bias, k_tail_shift=True, **kw)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(device), bias, padding=pad, dilation=dil)
+    ref = ACTS[act](ref + (r.float().permute(0, 3, 1, 2) if res else 0)).permute(0, 2, 3, 1)
+    assert rel_l2(y, ref) < TOL_BF16 and rel_l2(y, plain) < 1e-3
+
+
+@pytest.mark.parametrize("k", [144, 336, 1632])
+def test_gemm_gated_k_tail_shift(device, k):
+    from eqxvision_b200 import _pack, ops
+
+    n_img, hw, n = 3, 196, 48
+    a = rb(device, n_img * hw, k, seed=1)
+    gate = torch.rand(n_img, k, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).to(device)
+    wt = rb(device, n, k, scale=k ** -0.5, seed=3).float().cpu()
+    bias = torch.randn(n, generator=torch.Generator().manual_seed(4)).to(device)
+    plain = ops.gemm_gated(a, gate, wt.to(torch.bfloat16).to(device), bias, rows_per_image=hw)
+    ws = _pack.pack_conv_weight(wt.reshape(n, k, 1, 1), k, tail_shift=True).to(device)
+    y = ops.gemm_gated(a, gate, ws, bias, rows_per_image=hw, k_tail_shift=True)
+    ag = (a.float() * gate.float().repeat_interleave(hw, 0)).to(torch.bfloat16).float()
+    assert rel_l2(y, ag @ wt.to(device).t() + bias) < TOL_BF16 and rel_l2(y, plain) < 1e-3
+    with pytest.raises(Exception):
+        ops.conv2d(rb(device, 1, 8, 8, 64), rb(device, 32, 64), bias[:32], cin=64, cout=32, kh=1, kw=1, k_tail_shift=True)
+
+
+@pytest.mark.parametrize("n,h,w", [(3, 224, 224), (2, 64, 64), (5, 96, 128), (37, 224, 224)])
+def test_stem_with_fused_maxpool(device, n, h, w):
+    """eqxv_conv_stem_maxpool_bf16 (resnet.py:243-253): must equal the two separate entries BITWISE - the convolution is
+    the same MMA sequence and max is exact, whatever the order the border contributions arrive in (red.global.max)."""
+    from eqxvision_b200 import _pack, ops
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(n, 3, h, w, generator=g).to(device)
+    wt = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    bias = torch.randn(64, generator=g).to(device)
+    xpad = ops.pack_stem_input(x)
+    wp = _pack.pack_stem_weight(wt).to(device)
+    y = ops.conv_stem(xpad, wp, bias, n=n, h=h, w=w, cout=64)
+    ref = ops.maxpool2d(y, k=3, stride=2, pad=1)
+    for _ in range(2):   # twice: the entry re-zeroes the border pixels itself
+        got = ops.conv_stem_maxpool(xpad, wp, bias, n=n, h=h, w=w, cout=64)
+        assert got.shape == ref.shape and torch.equal(got, ref)
+    with pytest.raises(Exception):   # 56x56 conv output does not tile into 16-row blocks
+        ops.conv_stem_maxpool(ops.pack_stem_input(x[:, :, :112, :112].contiguous()), wp, bias, n=n, h=112, w=112, cout=64)
