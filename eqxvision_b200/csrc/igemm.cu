@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(kEpi16 ? kThreads16 : kThreads, 1) igemm_kerne
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = p.stages;
-  const bool gather = kEpi16 && p.ga_on;   // narrow-K layers: A gathered by warp 0, filter resident (IgemmParams::ga_*)
+  const bool gather = (kEpi16 || kGate) && p.ga_on;   // narrow-K layers: A gathered by threads, filter resident (IgemmParams::ga_*)
   const uint32_t stage_bytes = gather ? (uint32_t)kABytes : (uint32_t)(kABytes + p.block_n * 128);
 
   const uint32_t bars = base + p.off_bars;
@@ -654,7 +654,9 @@ __global__ void __launch_bounds__(kEpi16 ? kThreads16 : kThreads, 1) igemm_kerne
   const uint32_t tmem_base = *tmem_slot_g;
 
 
-  if (gather && warp == 0) {
+  if (kGate && gather && warp == 0) {
+    // gated narrow-K layers: the gate warps below fetch, scale and stage the A rows themselves; nothing to do here
+  } else if (gather && warp == 0) {
     // ============================== gathering producer (narrow K, see IgemmParams::ga_*) ==============================
     // lane <-> rows lane, lane + 32, ... of a 128-row tile; chunk j of row r sits at r*128 + ((j ^ (r & 7)) << 4) (the
     // layout a SWIZZLE_128B TMA box would have written). The chunks beyond K are zeroed once per stage and never touched
@@ -747,6 +749,76 @@ __global__ void __launch_bounds__(kEpi16 ? kThreads16 : kThreads, 1) igemm_kerne
       }
     }
     __syncwarp();
+  } else if (kGate && warp >= 6 && gather) {
+    // ============================== SE gate + gather (narrow K: k < 64, one K chunk, <= 256 outputs) ==============================
+    // EfficientNet-B4's first two projections (48 -> 24 and 24 -> 24 @112^2, 1.6 M rows): the 64-channel TMA boxes of
+    // both operands reach past their tensors and crawl (116 + 201 us for 36 + 24 us of traffic). Here the four gate
+    // warps ARE the producers: thread = one row of the tile, read with 16-byte loads one tile ahead, multiplied by the
+    // image's gate (HMUL2: the rounding the separate pass had) and written straight into the 128B-swizzled operand
+    // layout; the K-pad chunks are zeroed once, the filter is staged once and stays resident.
+    const int r = (warp - 6) * 32 + lane;
+    const int k16 = p.ga_k16;
+    const uint32_t xor7 = (uint32_t)(r & 7);
+    for (int st = 0; st < S; ++st)
+      for (int j = k16; j < 8; ++j)
+        *reinterpret_cast<uint4*>(gbase + (uint32_t)st * stage_bytes + r * 128 + (((uint32_t)j ^ xor7) << 4)) =
+            make_uint4(0u, 0u, 0u, 0u);
+    for (int n = r; n < p.block_n; n += 128) {
+      uint8_t* brow = gbase + p.off_bres + n * 128;
+      const __nv_bfloat16* wrow = p.gb_ptr + (long long)min(n, p.cout - 1) * p.gb_pitch;
+      for (int j = 0; j < 8; ++j) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (j < k16 && n < p.cout) v = __ldg(reinterpret_cast<const uint4*>(wrow + 8 * j));
+        *reinterpret_cast<uint4*>(brow + (((uint32_t)j ^ (uint32_t)(n & 7)) << 4)) = v;
+      }
+    }
+    fence_proxy_async_smem();
+    auto load_row = [&](int tile, uint4* a) {
+      int row = tile < p.num_tiles ? decode_tile(p, tile).w0 + r : p.ga_rows;
+      const bool ok = row < p.ga_rows;
+      const __nv_bfloat16* src = p.ga_ptr + (long long)(ok ? row : 0) * p.ga_pitch;
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+        a[j] = (ok && j < k16) ? __ldg(reinterpret_cast<const uint4*>(src + 8 * j)) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    uint4 a[7], an[7];
+    load_row((int)blockIdx.x, a);
+    uint32_t eb = empty_bar(0), xb = bars + 8u * 32u;
+    const uint32_t eb0 = eb, xb0 = xb;
+    uint32_t phase = 0;
+    uint8_t* rowp = gbase + r * 128;
+    uint8_t* const row0 = rowp;
+    int sidx = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int row = min(t.w0 + r, p.ln_rows - 1);
+      const __nv_bfloat16* grow = p.gate + (long long)(row / p.gate_rpi) * p.gate_pitch;
+      uint4 g[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+        g[j] = j < k16 ? __ldg(reinterpret_cast<const uint4*>(grow + 8 * j)) : make_uint4(0u, 0u, 0u, 0u);
+      load_row(tile + (int)gridDim.x, an);   // next tile's row in flight behind this tile's arithmetic
+      mbar_wait(eb, phase ^ 1u);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        if (j < k16) {
+          __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a[j]);
+          const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g[j]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a2[e] = __hmul2(a2[e], g2[e]);
+          *reinterpret_cast<uint4*>(rowp + (((uint32_t)j ^ xor7) << 4)) = a[j];
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(xb);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) a[j] = an[j];
+      eb += 8, xb += 8, rowp += stage_bytes;
+      if (++sidx == S) {
+        sidx = 0, eb = eb0, xb = xb0, rowp = row0;
+        phase ^= 1u;
+      }
+    }
   } else if (kGate && warp >= 6) {
     // ============================== SE gate on the A operand (warps 6..9, kGate kernels) ==============================
     // SqueezeExcitation `x * scale` (layers/squeeze.py:61) feeding the project convolution (efficientnet.py:161-170):
@@ -1800,8 +1872,8 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
     static const bool no_gather = getenv("EQXV_NO_GATHER_A") != nullptr;
     const bool flat = q.tw == 128 && q.th == 1 && q.tn == 1 && q.kh == 1 && q.kw == 1;
     const long long a_pitch = (long long)(q.a.strides_bytes[0] / 2);
-    if (epi16 && flat && q.kchunks == 1 && q.cin_pack < 64 && q.cin_pack % 8 == 0 && a_pitch % 8 == 0 && !no_gather &&
-        p.n_tiles == 1 && q.ktot % 8 == 0) {
+    if ((epi16 || q.gate) && flat && q.kchunks == 1 && q.cin_pack < 64 && q.cin_pack % 8 == 0 && a_pitch % 8 == 0 &&
+        !no_gather && p.n_tiles == 1 && q.ktot % 8 == 0) {
       p.ga_on = 1;
       p.ga_ptr = static_cast<const __nv_bfloat16*>(q.a.base);
       p.gb_ptr = static_cast<const __nv_bfloat16*>(q.wgt);

@@ -484,7 +484,8 @@ def test_layernorm_folded_into_its_neighbour_gemms(device, m, d, n, act):
 
 
 @pytest.mark.parametrize("n_img,hw,k,n,res", [(3, 49, 2688, 448, False), (5, 196, 672, 112, True), (2, 3136, 192, 32, True),
-                                              (4, 12544, 48, 24, False), (7, 49, 1632, 272, True), (3, 100, 40, 24, False)])
+                                              (4, 12544, 48, 24, False), (7, 49, 1632, 272, True), (3, 100, 40, 24, False),
+                                              (5, 12544, 24, 24, True), (3, 1000, 56, 200, False), (40, 3136, 48, 24, True)])
 def test_gemm_with_se_gate_on_the_a_operand(device, n_img, hw, k, n, res):
     """eqxv_gemm_gated_bf16: out = (a * gate[image]) @ w^T + bias (+ residual) (squeeze.py:61 + efficientnet.py:161-170).
     Must equal the two-kernel path (eltwise gate, then GEMM) BITWISE: the in-smem product is rounded to bf16 exactly as
