@@ -596,7 +596,7 @@ __device__ __forceinline__ void epilogue_warps16(const IgemmParams& p, const uin
 // unrolled epilogue is straight-line code (a runtime flag doubled its instruction count and made the
 // epilogue warps issue-bound on the HBM-bound layers: profiles/r01_layers_v4).
 template <bool kOutF32, int kAct, int kRes, int kLN = 0, bool kGate = false, bool kEpi16 = false>
-__global__ void __launch_bounds__(kEpi16 ? kThreads16 : kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(kEpi16 ? kThreads16 : (kGate ? kThreads + 128 : kThreads), 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -827,7 +827,13 @@ __global__ void __launch_bounds__(kEpi16 ? kThreads16 : kThreads, 1) igemm_kerne
     // r*128 + ((j ^ (r & 7)) << 4); bf16 x bf16 products rounded to bf16 with HMUL2, exactly what the separate pass
     // stored - make the writes visible to the async proxy and arrive on xf[stage], which the MMA issuer waits for in
     // place of full[stage]. Flat GEMMs (1x1 convolutions) only; the epilogue runs on four warps (epi_sub == 1).
-    const int r = (warp - 6) * 32 + lane;
+    // One or two groups of four warps (blockDim decides): with two, the groups take alternate K blocks - the chain
+    // wait -> 8 LDS -> 32 HMUL2 -> 8 STS -> proxy fence -> arrive is ~500 cycles per K block and thread against 64..256
+    // tensor cycles, and it, not TMA or the tensor pipe, bounded every gated projection (144 -> 32 @56^2: 47 us gated,
+    // 27 us ungated).
+    const int ngrp = ((int)blockDim.x - 192) >> 7;
+    const int grp = (warp - 6) >> 2;
+    const int r = ((warp - 6) & 3) * 32 + lane;
     const uint32_t xor7 = (uint32_t)(r & 7);
     uint32_t fb = full_bar(0);
     const uint32_t fb0 = fb;
@@ -837,12 +843,23 @@ __global__ void __launch_bounds__(kEpi16 ? kThreads16 : kThreads, 1) igemm_kerne
     uint8_t* rowp = gbase + r * 128;
     uint8_t* const row0 = rowp;
     int sidx = 0;
+    int turn = 0;   // K blocks are dealt round-robin to the groups
     const int kchunks = p.kchunks;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int row = min(t.w0 + r, p.ln_rows - 1);   // rows past the end: zero-filled A, any gate will do
       const __nv_bfloat16* grow = p.gate + (long long)(row / p.gate_rpi) * p.gate_pitch;
       for (int i = 0; i < kchunks; ++i) {
+        const bool mine = turn == grp;
+        if (++turn == ngrp) turn = 0;
+        if (!mine) {
+          fb += 8, xb += 8, rowp += stage_bytes;
+          if (++sidx == S) {
+            sidx = 0, fb = fb0, xb = xb0, rowp = row0;
+            phase ^= 1u;
+          }
+          continue;
+        }
         const int k0 = (i == kchunks - 1 && p.a_tail >= 0) ? p.a_tail : i * kBlockK;
         uint4 g[8];
 #pragma unroll
@@ -1964,7 +1981,10 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   if (q.ln_mode == 2) fn = igemm_kernel<false, 0, 1, 2>;
   if (q.gate) fn = q.res ? igemm_kernel<false, 0, 1, 0, true> : igemm_kernel<false, 0, 0, 0, true>;
   if (epi16) fn = epi16_table(q.act);
-  EQXV_CUDA(launch_kernel(fn, dim3(grid), dim3(64 + 128 * p.epi_sub + (q.gate ? 128 : 0)), (size_t)(smem_bytes), stream, p));
+  // gate warps: two groups of four (alternate K blocks) unless the rows are gathered by them (one K block per tile)
+  static const int gate_groups_env = getenv("EQXV_GATE_GROUPS") ? atoi(getenv("EQXV_GATE_GROUPS")) : 0;
+  const int gate_groups = !q.gate ? 0 : ((p.ga_on || gate_groups_env == 1 || kblocks < 2) ? 1 : 2);
+  EQXV_CUDA(launch_kernel(fn, dim3(grid), dim3(64 + 128 * p.epi_sub + 128 * gate_groups), (size_t)(smem_bytes), stream, p));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }
