@@ -59,26 +59,53 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
 // ---------------------------------------------------------------------------------------------
 // stem input: fp32 NCHW [n,c<=8,h,w] -> bf16 [n, h+2*pad, w+8, 8], image at (pad,pad), zeros elsewhere
 // ---------------------------------------------------------------------------------------------
+constexpr int kPackRows = 8;
 __global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict__ y, int n, int c, int h,
                                  int w, int pad) {
   griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
   griddep_launch();
   // grid = (column blocks, padded rows, images): no index division at all (with a linear index the
   // kernel was ALU bound on the div/mod decomposition: issue slots 80 % busy, profiles/r01_ncu_stem_trio_v15.txt)
+  // Every thread walks kPackRows consecutive padded rows of its column: 58 880 one-row blocks of the ResNet-50 batch spent
+  // their time being scheduled (ncu: issue slots 83 % busy at 47 % of the DRAM throughput, ~180 warp instructions per
+  // 32 pixels); the loads of all rows are issued before the first conversion.
   const int wp = w + 8, hp = h + 2 * pad;
   const int pw = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ph = blockIdx.y, img = blockIdx.z;
+  const int ph0 = blockIdx.y * kPackRows, img = blockIdx.z;
   if (pw >= wp) return;
-  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int sh = ph - pad, sw = pw - pad;
-  if (sh >= 0 && sh < h && sw >= 0 && sw < w) {
-    const long long plane = (long long)h * w;
-    const float* src = x + (long long)img * c * plane + (long long)sh * w + sw;
+  const int sw = pw - pad;
+  const bool col_ok = sw >= 0 && sw < w;
+  const long long plane = (long long)h * w;
+  const float* src0 = x + (long long)img * c * plane + (col_ok ? sw : 0);
+  float f[kPackRows][3];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (q < c) f[q] = __ldg(src + q * plane);
+  for (int r = 0; r < kPackRows; ++r) {
+    const int sh = ph0 + r - pad;
+    const bool ok = col_ok && sh >= 0 && sh < h;
+    const float* src = src0 + (long long)(ok ? sh : 0) * w;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) f[r][q] = (ok && q < c) ? __ldg(src + q * plane) : 0.f;
   }
-  y[((long long)img * hp + ph) * wp + pw] = pack8(f);
+  bf16x8* dst = y + ((long long)img * hp + ph0) * wp + pw;
+  if (c <= 3) {
+#pragma unroll
+    for (int r = 0; r < kPackRows; ++r) {
+      if (ph0 + r < hp) {
+        const float g[8] = {f[r][0], f[r][1], f[r][2], 0.f, 0.f, 0.f, 0.f, 0.f};
+        dst[(long long)r * wp] = pack8(g);
+      }
+    }
+    return;
+  }
+  for (int r = 0; r < kPackRows; ++r) {   // 4..8 input channels (not an image; kept general)
+    if (ph0 + r >= hp) break;
+    float g[8] = {f[r][0], f[r][1], f[r][2], 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int sh = ph0 + r - pad;
+    if (col_ok && sh >= 0 && sh < h)
+      for (int q = 3; q < 8; ++q)
+        if (q < c) g[q] = __ldg(src0 + (long long)sh * w + q * plane);
+    dst[(long long)r * wp] = pack8(g);
+  }
 }
 
 // fp32 NCHW -> bf16 NHWC (channels padded with zeros to c_pad)
@@ -208,6 +235,25 @@ __global__ void pool2d_fixed_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
             x + (((long long)img * h + ihc) * w + iwc) * xp + g * 8));
       }
     }
+    if constexpr (kMax) {
+      // Out-of-range taps were fetched from the clamped coordinate, which lies inside the same window (2 pad <= k), so
+      // they repeat an in-range tap and cannot change the maximum: no predicate, and the maximum itself on packed
+      // bf16 pairs (HMNMX2, exact) - 32 instructions per output vector instead of ~150 unpack + compare + select +
+      // repack (ncu: the kernel was ISSUE bound, 71 % of the issue slots busy at 50 % of the DRAM throughput).
+      uint4 m = raw[0];
+#pragma unroll
+      for (int k = 1; k < K * K; ++k) {
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&m);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&raw[k]);
+        uint4 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o2[q] = __hmax2(a2[q], b2[q]);
+        m = o;
+      }
+      *reinterpret_cast<uint4*>(y + (((long long)img * ho + oh) * wo + ow) * yp + g * 8) = m;
+      continue;
+    }
     float acc[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = kMax ? -INFINITY : 0.f;
@@ -303,12 +349,12 @@ __global__ void __launch_bounds__(256) global_avgpool_small_kernel(const __nv_bf
   const __nv_bfloat16* base = x + (long long)img * hw * xp + g * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int p = 0;
-  for (; p + 3 < hw; p += 4) {
-    bf16x8 r[4];
+  for (; p + 6 < hw; p += 7) {   // seven 16-byte loads in flight per thread (a 7x7 map is seven rounds)
+    bf16x8 r[7];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const bf16x8*>(base + (long long)(p + u) * xp);
+    for (int u = 0; u < 7; ++u) r[u] = *reinterpret_cast<const bf16x8*>(base + (long long)(p + u) * xp);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 7; ++u) {
       float f[8];
       unpack8(r[u], f);
 #pragma unroll
@@ -623,8 +669,9 @@ extern "C" int eqxv_pack_stem_input(const float* x, void* xpad, int32_t n, int32
   EQXV_CHECK_ARG(x && xpad && n > 0 && h > 0 && w > 0 && c >= 1 && c <= 8 && pad >= 0 && pad <= 4,
                  "pack_stem_input: bad arguments");
   EQXV_CHECK_ARG(h + 2 * pad <= 65535 && n <= 65535, "pack_stem_input: image too tall / batch too large");
-  EQXV_CUDA(launch_kernel(pack_stem_kernel, dim3((unsigned)((w + 8 + 255) / 256), (unsigned)(h + 2 * pad), (unsigned)n),
-                          dim3(256), (size_t)0, (cudaStream_t)stream, x, reinterpret_cast<bf16x8*>(xpad), n, c, h, w,
+  EQXV_CUDA(launch_kernel(pack_stem_kernel,
+                          dim3((unsigned)((w + 8 + 127) / 128), (unsigned)((h + 2 * pad + kPackRows - 1) / kPackRows), (unsigned)n),
+                          dim3(128), (size_t)0, (cudaStream_t)stream, x, reinterpret_cast<bf16x8*>(xpad), n, c, h, w,
                           pad));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
@@ -804,8 +851,9 @@ extern "C" int eqxv_adaptive_avgpool_nhwc_bf16(const void* x, void* y, int32_t n
     // serial per-thread sum loses: EfficientNet-B4's 33 SE squeezes (128 images, 14x14 x 672..7x7 x 2688) measured
     // 1.12 ms with this kernel against 0.74 ms with the block kernel (profiles/r01_bench_v24.json vs v26).
     if (h * w <= 64 && (long long)n * (c / 8) >= 65536) {
-      dim3 sgrid((unsigned)((c / 8 + 255) / 256), (unsigned)n);
-      EQXV_CUDA(launch_kernel(global_avgpool_small_kernel, sgrid, dim3(256), (size_t)0, (cudaStream_t)stream,
+      // 64-thread blocks: 1024 blocks instead of 256 for the ResNet-50 head (the kernel was latency bound on 256 CTAs)
+      dim3 sgrid((unsigned)((c / 8 + 63) / 64), (unsigned)n);
+      EQXV_CUDA(launch_kernel(global_avgpool_small_kernel, sgrid, dim3(64), (size_t)0, (cudaStream_t)stream,
                               (const __nv_bfloat16*)x, (__nv_bfloat16*)y, h * w, c, x_pitch, y_pitch));
       EQXV_LAUNCH_CHECK();
       return EQXV_OK;
