@@ -508,16 +508,22 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
 // step's tcgen05.ld in flight (the fused bottleneck kernel's e3, csrc/bottleneck.cu): ~60 live registers, which is what
 // lets 18 warps share the register file. One staging slab per warp, bf16 output, no residual, no LayerNorm folding.
 constexpr int kThreads16 = 64 + 32 * 16;
-template <int kAct>
+// kRes != 0 (CTA-pair kernels, ResNet conv3 layers with K = 256 / 512): the warp's staging slab is also where the TMA
+// puts its residual - arithmetic in place, as in the fused bottleneck kernel - so sixteen warps need 64 KiB where the
+// eight-warp epilogue needs 32 + 64 KiB (staging + residual ring), and the K loop keeps its stages. The residual of the
+// warp's NEXT chunk is requested as soon as its store has read the slab; the K loop of the next tile hides the trip.
+template <int kAct, int kRes = 0, bool kPair = false>
 __device__ __forceinline__ void epilogue_warps16(const IgemmParams& p, const uint32_t base, uint8_t* gbase,
                                                  const uint32_t tmem_base, const int warp, const int lane) {
   const int S = p.stages;
-  const int t_first = (int)blockIdx.x, t_stride = (int)gridDim.x;
+  const int t_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t bars = base + p.off_bars;
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
   constexpr int CH = 64;
   constexpr int nsub = 4;
+  constexpr bool has_res = kRes != 0;
   const int quad = warp & 3;
   const int sub = (warp - 2) >> 2;
   const int wid = quad * nsub + sub;
@@ -528,17 +534,31 @@ __device__ __forceinline__ void epilogue_warps16(const IgemmParams& p, const uin
   constexpr uint32_t kSlab = 32 * 128;
   const uint32_t out_u32 = base + p.off_out + (uint32_t)wid * kSlab;
   uint8_t* out_row = gbase + p.off_out + (uint32_t)wid * kSlab;
+  const uint32_t rbar = bars + 8u * (48u + (uint32_t)wid);
   auto release_acc = [&](int ti) {
     tc_fence_before();
-    mbar_arrive(tempty_bar(ti & 1));
+    if constexpr (kPair) {
+      mbar_arrive_leader(tempty_bar(ti & 1));
+    } else {
+      mbar_arrive(tempty_bar(ti & 1));
+    }
+  };
+  auto issue_res = [&](int ti, int c) {   // ONE lane: the residual of chunk (ti, c) into this warp's slab
+    const long long tile = (long long)t_first + (long long)ti * t_stride;
+    if (tile >= p.num_tiles) return;
+    const TileCoord t = decode_tile<kPair>(p, (int)tile);
+    mbar_expect_tx(rbar, kSlab);
+    tma_load_4d(out_u32, &p.tmR, rbar, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off, t.n0 + n_off);
   };
   int cur_ti = -1;
   int ti = sub / cpt, c = sub - ti * cpt;
   int dec_ti = -1;
   TileCoord t{};
-  for (;;) {
+  if (has_res && lane == 0) issue_res(ti, c);
+  __syncwarp();
+  for (uint32_t l = 0;; ++l) {
     if (ti != dec_ti) {
-      t = decode_tile<false>(p, t_first + ti * t_stride);
+      t = decode_tile<kPair>(p, t_first + ti * t_stride);
       dec_ti = ti;
     }
     bool done = false;
@@ -558,18 +578,27 @@ __device__ __forceinline__ void epilogue_warps16(const IgemmParams& p, const uin
     const float* bias_c = s_bias + t.ncol0 + c * CH;
     float va[16], vb[16];
     tmem_ld_x16(t_acc, va);
-    if (lane == 0) tma_store_wait_read<0>();   // the store that last used this warp's slab has read it
-    __syncwarp();
+    if constexpr (has_res) {
+      mbar_wait(rbar, l & 1u);   // the residual slab has landed (requested after the previous store had read the slab)
+    } else {
+      if (lane == 0) tma_store_wait_read<0>();   // the store that last used this warp's slab has read it
+      __syncwarp();
+    }
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
       float* cur = (st & 1) ? vb : va;
       float* nxt = (st & 1) ? va : vb;
       uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
       if (st * 16 < ncols) {   // warp-uniform
+        uint4 r0 = o0, r1 = o0;
+        if constexpr (has_res) {
+          r0 = *reinterpret_cast<const uint4*>(out_row + sw128_off(lane, 2 * st));
+          r1 = *reinterpret_cast<const uint4*>(out_row + sw128_off(lane, 2 * st + 1));
+        }
         tmem_ld_wait();
         if (st < 3 && (st + 1) * 16 < ncols) tmem_ld_x16(t_acc + (uint32_t)(16 * (st + 1)), nxt);
-        o0 = epilogue8<kAct, 0>(&cur[0], bias_c + 16 * st, make_uint4(0u, 0u, 0u, 0u));
-        o1 = epilogue8<kAct, 0>(&cur[8], bias_c + 16 * st + 8, make_uint4(0u, 0u, 0u, 0u));
+        o0 = epilogue8<kAct, kRes>(&cur[0], bias_c + 16 * st, r0);
+        o1 = epilogue8<kAct, kRes>(&cur[8], bias_c + 16 * st + 8, r1);
       }
       *reinterpret_cast<uint4*>(out_row + sw128_off(lane, 2 * st)) = o0;
       *reinterpret_cast<uint4*>(out_row + sw128_off(lane, 2 * st + 1)) = o1;
@@ -577,16 +606,22 @@ __device__ __forceinline__ void epilogue_warps16(const IgemmParams& p, const uin
     if (c + nsub >= cpt) release_acc(ti);   // this warp's last chunk of the tile
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
-      tma_store_4d(&p.tmC, out_u32, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off, t.n0 + n_off);
-      tma_store_commit();
-    }
-    __syncwarp();
+    const int c_old = c, ti_old = ti;
     c += nsub;
     while (c >= cpt) {
       c -= cpt;
       ++ti;
     }
+    if (lane == 0) {
+      tma_store_4d(&p.tmC, out_u32, t.ncol0 + c_old * CH, t.w0 + w_off, t.h0 + h_off, t.n0 + n_off);
+      tma_store_commit();
+      if constexpr (has_res) {
+        tma_store_wait_read<0>();
+        issue_res(ti, c);
+      }
+    }
+    (void)ti_old;
+    __syncwarp();
   }
   if (lane == 0) tma_store_wait_all();
   __syncwarp();
@@ -948,7 +983,7 @@ __global__ void __launch_bounds__(kEpi16 ? kThreads16 : (kGate ? kThreads + 128 
     __syncwarp();
   } else {
     if constexpr (kEpi16) {
-      epilogue_warps16<kAct>(p, base, gbase, tmem_base, warp, lane);
+      epilogue_warps16<kAct, 0, false>(p, base, gbase, tmem_base, warp, lane);
     } else {
       epilogue_warps<kOutF32, kAct, kRes, false, kLN>(p, base, gbase, tmem_base, warp, lane);
     }
@@ -975,7 +1010,7 @@ __global__ void __launch_bounds__(kEpi16 ? kThreads16 : (kGate ? kThreads + 128 
 // Protocol: full[s] lives in the leader (both producers' TMA bytes are credited to it), the MMA
 // commits are multicast to empty[s] / tfull[a] of both CTAs, both epilogues arrive on the leader's
 // tempty[a]. The epilogue itself is the single-CTA one (each CTA drains its own 128 TMEM lanes).
-template <int kAct, int kRes, int kLN = 0>
+template <int kAct, int kRes, int kLN = 0, bool kEpi16 = false>
 __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -1103,7 +1138,11 @@ __device__ __forceinline__ void pair_kernel_body(const IgemmParams& p) {
     }
     __syncwarp();
   } else {
-    epilogue_warps<false, kAct, kRes, true, kLN>(p, base, gbase, tmem_base, warp, lane);
+    if constexpr (kEpi16) {
+      epilogue_warps16<kAct, kRes, true>(p, base, gbase, tmem_base, warp, lane);
+    } else {
+      epilogue_warps<false, kAct, kRes, true, kLN>(p, base, gbase, tmem_base, warp, lane);
+    }
   }
 
   // ---- teardown: neither CTA may leave while its peer can still touch its smem / TMEM / barriers ----
@@ -1120,6 +1159,11 @@ template <int kAct, int kRes, int kLN = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     pair_kernel(const __grid_constant__ IgemmParams p) {
   pair_kernel_body<kAct, kRes, kLN>(p);
+}
+template <int kAct, int kRes>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads16, 1)
+    pair_kernel16(const __grid_constant__ IgemmParams p) {
+  pair_kernel_body<kAct, kRes, 0, true>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1766,6 +1810,11 @@ static int choose_block_n_pair(int cout, long long pair_m_tiles, int kblocks, in
   return best_bn;
 }
 
+static KernelFn pair16_table(int act, int res_mode) {   // act none / relu / silu, residual before / after the activation
+  static const KernelFn t[2][3] = {{pair_kernel16<0, 1>, pair_kernel16<1, 1>, pair_kernel16<2, 1>},
+                                   {pair_kernel16<0, 2>, pair_kernel16<1, 2>, pair_kernel16<2, 2>}};
+  return (act >= 0 && act <= 2 && res_mode >= 1 && res_mode <= 2) ? t[res_mode - 1][act] : nullptr;
+}
 static KernelFn epi16_table(int act) {
   static const KernelFn t[kNumActs] = {
       igemm_kernel<false, 0, 0, 0, false, true>, igemm_kernel<false, 1, 0, 0, false, true>,
@@ -1881,6 +1930,20 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
       p.epi_sub = 4;
     }
   }
+  // ... and on the CTA-pair kernels with a residual (ResNet conv3 layers: 128 x 256 outputs + shortcut per CTA and tile
+  // against a 4..8-block K loop): ncu on l4.c3 showed the tensor pipe 38 % active with a flat stall profile - the
+  // four-warp epilogue (8000 cycles per tile) paced the 6000-cycle K loop, and eight warps cost a pipeline stage for
+  // their residual ring. Sixteen warps with the residual landing in the staging slab need 64 KiB in all.
+  bool pair16 = false;
+  {
+    static const bool no_pair16 = getenv("EQXV_NO_PAIR16") != nullptr;
+    const int res_mode_ = q.res ? ((q.flags & EQXV_FLAG_RES_AFTER_ACT) ? 2 : 1) : 0;
+    if (pair && q.res && q.ln_mode == 0 && !out_f32 && block_n % 16 == 0 && pair16_table(q.act, res_mode_) != nullptr &&
+        !no_pair16 && forced_sub == 0 && kblocks >= 8) {   // measured: l4.c3 (K = 512) 39.6 -> 36.2 us, l3.c3 (K = 256) 47.0 -> 48.7
+      pair16 = true;
+      p.epi_sub = 4;
+    }
+  }
   // eight-warp epilogue: ONE staging slab per warp means every chunk waits until the TMA store of the previous chunk
   // has finished reading it; with a second slab (32 KiB more, one pipeline stage less) the store of chunk l overlaps the
   // math of chunk l+1. Worth it where the epilogue bounds the layer and the K loop is short (ResNet c3 layers).
@@ -1897,7 +1960,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
       p.ga_pitch = (int)a_pitch, p.ga_rows = q.out_w, p.ga_k16 = q.cin_pack / 8, p.gb_pitch = q.ktot;
     }
   }
-  int out_bytes = epi16 ? 4 * kStageBuf : 2 * kStageBuf;   // sixteen warps: one 4 KiB slab each
+  int out_bytes = (epi16 || pair16) ? 4 * kStageBuf : 2 * kStageBuf;   // sixteen warps: one 4 KiB slab each
   p.epi_obufs = 0;
   // Measured on ResNet-50 (A/B in one call, 3.457 vs 3.43 ms per step): no gain - the c3 layers are not waiting on
   // their staging slab - so the second slab stays opt-in (EQXV_EPI_OBUFS=2).
@@ -1910,7 +1973,8 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   }
   const int bres_bytes = p.ga_on ? ceil_div(block_n * 128, 1024) * 1024 : 0;   // resident filter slab (gather mode)
   const int ring_stage = p.ga_on ? kABytes : stage_bytes;
-  const int fixed = out_bytes + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0) + bias_bytes + 512 + bres_bytes;
+  const int res_ring = (p.has_res && !pair16) ? 2 * p.epi_sub * kStageBuf : 0;   // pair16: the residual lands in the staging slab
+  const int fixed = out_bytes + res_ring + bias_bytes + 512 + bres_bytes;
   int stages = (kMaxSmem - 1024 - fixed) / ring_stage;
   stages = std::min(stages, 8);
   EQXV_CHECK_ARG(stages >= 2, "igemm: not enough shared memory for block_n=%d", block_n);
@@ -1919,7 +1983,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
   p.off_bres = stages * ring_stage;
   p.off_out = p.off_bres + bres_bytes;
   p.off_res = p.off_out + out_bytes;
-  p.off_bias = p.off_res + (p.has_res ? 2 * p.epi_sub * kStageBuf : 0);
+  p.off_bias = p.off_res + res_ring;
   p.off_wsum = p.off_bias + bias_one;
   p.off_bars = p.off_bias + bias_bytes;
   const int smem_bytes = p.off_bars + 512 + 1024;
@@ -1970,6 +2034,7 @@ static int launch_igemm(const IgemmProblem& q, cudaStream_t stream) {
     KernelFn pfn = pair_table(q.act, res_mode);
     if (q.ln_mode == 1) pfn = q.act == EQXV_ACT_NONE ? pair_kernel<0, 0, 1> : pair_kernel<EQXV_ACT_GELU_TANH, 0, 1>;
     if (q.ln_mode == 2) pfn = pair_kernel<0, 1, 2>;
+    if (pair16) pfn = pair16_table(q.act, res_mode);
     EQXV_CUDA(launch_kernel(pfn, dim3(2 * clusters), dim3(64 + 128 * p.epi_sub), (size_t)(smem_bytes), stream, p));
     EQXV_CUDA(cudaGetLastError());
     return EQXV_OK;
@@ -2015,6 +2080,9 @@ static StemFn stem_table(int act) {
 int igemm_init() {
   for (int a = 0; a < kNumActs; ++a)
     EQXV_CUDA(cudaFuncSetAttribute(epi16_table(a), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  for (int a = 0; a < 3; ++a)
+    for (int r = 1; r <= 2; ++r)
+      EQXV_CUDA(cudaFuncSetAttribute(pair16_table(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int i = 0; i < 8; ++i)
     EQXV_CUDA(cudaFuncSetAttribute(ln_kernels(i), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < kNumActs; ++a)
