@@ -44,28 +44,44 @@ __global__ void u8_to_nchw_f32_kernel(const uint8_t* __restrict__ x, const float
 
 // uint8 NHWC [n,h,w,c<=4] -> bf16 [n, h+2*pad, w+8, 8] (the layout eqxv_conv_stem_bf16 reads):
 // image at (pad, pad), zero border, channels >= c zero
+constexpr int kEdgeRows = 8;
 __global__ void u8_pack_stem_kernel(const uint8_t* __restrict__ x, const float* __restrict__ lut,
                                     bf16x8e* __restrict__ y, int c, int h, int w, int pad) {
   __shared__ float s[4 * 256];
   load_lut(s, lut, c);
   griddep_wait();
   griddep_launch();
+  // kEdgeRows padded rows per thread (the table is staged once per block for all of them; one-row blocks spent their time
+  // being scheduled and re-staging the table: see pack_stem_kernel in pointwise.cu)
   const int wp = w + 8, hp = h + 2 * pad;
   const int pw = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ph = blockIdx.y, img = blockIdx.z;
+  const int ph0 = blockIdx.y * kEdgeRows, img = blockIdx.z;
   if (pw >= wp) return;
-  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int sh = ph - pad, sw = pw - pad;
-  if (sh >= 0 && sh < h && sw >= 0 && sw < w) {
-    const uint8_t* src = x + (((long long)img * h + sh) * w + sw) * c;
+  const int sw = pw - pad;
+  const bool col_ok = sw >= 0 && sw < w;
+  uint8_t px[kEdgeRows][4];
+#pragma unroll
+  for (int r = 0; r < kEdgeRows; ++r) {
+    const int sh = ph0 + r - pad;
+    const bool ok = col_ok && sh >= 0 && sh < h;
+    const uint8_t* src = x + (((long long)img * h + (ok ? sh : 0)) * w + (ok ? sw : 0)) * c;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) px[r][q] = (ok && q < c) ? __ldg(src + q) : (uint8_t)0;
+  }
+#pragma unroll
+  for (int r = 0; r < kEdgeRows; ++r) {
+    const int sh = ph0 + r - pad;
+    if (ph0 + r >= hp) break;
+    const bool ok = col_ok && sh >= 0 && sh < h;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (q < c) f[q] = s[q * 256 + __ldg(src + q)];
-  }
-  bf16x8e r;
+      if (ok && q < c) f[q] = s[q * 256 + px[r][q]];
+    bf16x8e o;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) r.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  y[((long long)img * hp + ph) * wp + pw] = r;
+    for (int i = 0; i < 4; ++i) o.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    y[((long long)img * hp + ph0 + r) * wp + pw] = o;
+  }
 }
 
 // uint8 NHWC [n,h,w,c<=4] -> bf16 NHWC [n,h,w,8] (channels zero-padded to 8)
@@ -167,7 +183,7 @@ extern "C" int eqxv_u8hwc_pack_stem_input(const uint8_t* x, const float* lut, vo
                                           int32_t c, int32_t pad, void* stream) {
   EDGE_ARGS_OK("u8hwc_pack_stem_input");
   EQXV_CHECK_ARG(pad >= 0 && pad <= 4 && h + 2 * pad <= 65535, "u8hwc_pack_stem_input: pad out of range");
-  EQXV_CUDA(launch_kernel(u8_pack_stem_kernel, dim3((unsigned)ceil_div(w + 8, kEdgeThreads), (unsigned)(h + 2 * pad), (unsigned)n),
+  EQXV_CUDA(launch_kernel(u8_pack_stem_kernel, dim3((unsigned)ceil_div(w + 8, kEdgeThreads), (unsigned)ceil_div(h + 2 * pad, kEdgeRows), (unsigned)n),
                           dim3(kEdgeThreads), (size_t)0, (cudaStream_t)stream, x, lut, reinterpret_cast<bf16x8e*>(y), c, h,
                           w, pad));
   EQXV_CUDA(cudaGetLastError());
