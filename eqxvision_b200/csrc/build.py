@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(LIB_DIR, "libeqxv_b200.so")
 
-SOURCES = ["capi.cu", "igemm.cu", "bottleneck.cu", "pointwise.cu", "attention.cu", "depthwise.cu", "dwconv_img.cu", "segment.cu", "swin.cu", "input_edge.cu", "p2p.cu", "debug_umma.cu"]
+SOURCES = ["capi.cu", "igemm.cu", "bottleneck.cu", "gemv.cu", "pointwise.cu", "attention.cu", "depthwise.cu", "dwconv_img.cu", "segment.cu", "swin.cu", "input_edge.cu", "p2p.cu", "debug_umma.cu"]
 HEADERS = ["ptx.cuh", "epilogue.cuh", "common.h", os.path.join(ROOT, "include", "eqxv_b200.h")]
 
 NVCC_FLAGS = [

@@ -70,6 +70,7 @@ int encode_tmap(CUtensorMap* out, const TmapSpec& s) {
 int igemm_init();
 int attention_init();
 int bottleneck_init();
+int gemv_init();
 
 }  // namespace eqxv
 
@@ -112,6 +113,8 @@ extern "C" int eqxv_init(int device) {
   int rc = igemm_init();
   if (rc) return rc;
   rc = bottleneck_init();
+  if (rc) return rc;
+  rc = gemv_init();
   if (rc) return rc;
   rc = attention_init();
   if (rc) return rc;

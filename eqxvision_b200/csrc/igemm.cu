@@ -2249,6 +2249,11 @@ struct LnFold {
   int gate_pitch = 0, gate_rpi = 0;
 };
 static int conv_impl(const eqxv_conv_desc* d, const LnFold* ln, void* stream);
+namespace eqxv {
+bool gemv_applies(long long m, int n, int k);
+int launch_gemv(const void* a, long long lda, const void* w, long long ldw, int w_head, int w_off, const float* bias,
+                void* out, long long ldo, long long m, int n, int k, int act, bool out_f32, cudaStream_t stream);
+}  // namespace eqxv
 
 extern "C" int eqxv_conv2d_igemm_bf16(const eqxv_conv_desc* d, void* stream) { return conv_impl(d, nullptr, stream); }
 
@@ -2311,6 +2316,16 @@ static int conv_impl(const eqxv_conv_desc* d, const LnFold* ln, void* stream) {
   q.a.swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
 
   const bool pointwise = (d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0);
+  if (pointwise && !ln && !grouped && !d->residual) {
+    // ONE row (single-image classifier heads): one warp per output column, csrc/gemv.cu
+    const long long m_rows = (long long)d->n * d->h * d->w;
+    if (gemv_applies(m_rows, d->cout, d->cin)) {
+      const int kc = ceil_div(d->cin, kBlockK);
+      return launch_gemv(d->x, d->x_pitch, d->wgt, tail ? kc * kBlockK : d->cin, kBlockK * (kc - 1),
+                         tail ? kc * kBlockK - d->cin : 0, d->bias, d->y, d->y_pitch, m_rows, d->cout, d->cin, d->act, f32,
+                         (cudaStream_t)stream);
+    }
+  }
   if (pointwise) {
     // plain GEMM over the flattened pixel index
     const long long m = (long long)d->n * d->h * d->w;

@@ -122,6 +122,9 @@ GEMM_CASES = [
     # all-epilogue tiles (one K block, no residual, many chunks): the sixteen-warp epilogue (igemm.cu epilogue_warps16)
     (200704, 144, 24, 2, False, False), (100352, 192, 32, 2, False, False), (50176, 336, 56, 2, False, False),
     (160000, 64, 64, 1, False, False), (70000, 272, 128, 4, False, False),
+    # one row: one warp per output column (csrc/gemv.cu; AlexNet's single-image classifier)
+    (1, 4096, 9216, 1, False, False), (1, 1000, 4096, 0, False, True), (1, 272, 1632, 4, False, False), (1, 1000, 768, 0, False, True),
+    (1, 4096, 4096, 1, False, False), (1, 72, 40, 2, False, False),
 ]
 
 
@@ -579,7 +582,8 @@ TAIL_CASES = [(2, 56, 56, 144, 32, 1, 0, 1, 0, True),      # EfficientNet projec
               (1, 14, 14, 1632, 272, 1, 0, 1, 2, False),   # 26 K chunks
               (2, 30, 23, 72, 40, 3, 1, 1, 1, False),      # 3x3 through the halo kernel, two chunks per tap
               (3, 17, 13, 200, 96, 3, 1, 1, 2, True),      # 3x3 through the generic kernel, ragged map
-              (2, 16, 16, 136, 64, 3, 2, 2, 0, False)]     # dilated
+              (2, 16, 16, 136, 64, 3, 2, 2, 0, False),     # dilated
+              (1, 1, 1, 144, 72, 1, 0, 1, 2, False), (1, 1, 1, 1632, 272, 1, 0, 1, 2, False)]   # one row: gemv.cu reads the shifted filter
 
 
 @pytest.mark.parametrize("case", TAIL_CASES, ids=lambda c: "x".join(map(str, c)))

@@ -271,7 +271,9 @@ def test_single_sample_call_equals_batched_row(device, save_checkpoint):
     batched = eb.vmap(net, axis_name="batch")(x, key=keys(4))
     one = net(x[2], key=eb.random.PRNGKey(1))   # the reference's native per-sample convention
     assert one.shape == (1000,)
-    assert torch.equal(one, batched[2])
+    # identical up to the classifier: a ONE-row product runs on the matrix-vector kernel (csrc/gemv.cu), whose fp32
+    # summation order differs from the tensor-core path's; every batch of >= 2 images stays a bitwise map (next test)
+    assert ((one - batched[2]).norm() / batched[2].norm()).item() < 1e-5
     with pytest.raises(RuntimeError, match="PRNGKey"):
         net(x[0], key=None)
 
