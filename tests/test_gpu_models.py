@@ -141,7 +141,8 @@ def test_lraspp_mobilenet_v3_large_parity(device, save_checkpoint):
     ref = om.lraspp_mobilenet_v3_large(sd, x)
     with O.emulate_bf16():
         emu = om.lraspp_mobilenet_v3_large(sd, x)
-    assert rel(out, emu) < 4e-2 and rel(out, ref) < 1e-1, (rel(out, emu), rel(out, ref))
+    # measured on B200: 2.1e-3 / 4.8e-3
+    assert rel(out, emu) < 1e-2 and rel(out, ref) < 2e-2, (rel(out, emu), rel(out, ref))
     assert (out.cpu().argmax(1) == emu.argmax(1)).float().mean().item() > 0.9
 
 
@@ -443,6 +444,6 @@ def test_deeplabv3_512_baseline_shape(device, save_checkpoint):
              aux_r=rel(aux[idx], aux_r))
     print("deeplabv3@512 rel-L2:", r)
     assert r["out_e"] < 8e-2 and r["aux_e"] < 4e-2, r
-    assert r["out_r"] < 2e-1 and r["aux_r"] < 1e-1, r
+    assert r["out_r"] < 1.5e-1 and r["aux_r"] < 8e-2, r   # measured on B200: 5.5e-2 / 3.3e-2 (emulation), 8.6e-2 / 5.4e-2 (fp32)
     agree = (out[idx].cpu().argmax(1) == out_e.argmax(1)).float().mean().item()
     assert agree > 0.9, agree

@@ -124,8 +124,8 @@ ZOO = [("alexnet", "alexnet", 224, 3, 1e-2, 3e-2),
        ("convnext_tiny", "convnext", 224, 2, 1.5e-2, 4e-2),
        # untrained ShuffleNets amplify ANY rounding (fp32 oracle vs its own bf16 emulation: 6e-2 at 224): loose bounds
        # here, the lowering itself is pinned to 5e-4 on the CPU (tests/test_plan_lowering.py)
-       ("shufflenet_v2_x0_5", "shufflenet_v2", 224, 2, 8e-2, 2e-1),
-       ("shufflenet_v2_x1_0", "shufflenet_v2", 224, 2, 8e-2, 2e-1)]
+       ("shufflenet_v2_x0_5", "shufflenet_v2", 224, 2, 3e-2, 2e-1),    # measured on B200 vs the emulation: 6.2e-3
+       ("shufflenet_v2_x1_0", "shufflenet_v2", 224, 2, 3e-2, 2e-1)]    # 1.5e-2
 
 
 @pytest.mark.parametrize("arch,fn,hw,batch,tol_emu,tol_f32", ZOO, ids=[z[0] for z in ZOO])
@@ -236,5 +236,5 @@ def test_fcn_resnet50_parity(device, save_checkpoint):
     aux_r, out_r = om.fcn_resnet50(sd, x)
     with O.emulate_bf16():
         aux_e, out_e = om.fcn_resnet50(sd, x)
-    assert rel(out, out_e) < 1e-1 and rel(aux, aux_e) < 8e-2, (rel(out, out_e), rel(aux, aux_e))
+    assert rel(out, out_e) < 8e-2 and rel(aux, aux_e) < 5e-2, (rel(out, out_e), rel(aux, aux_e))   # measured: 5.1e-2 / 3.3e-2
     assert rel(out, out_r) < 2.5e-1 and rel(aux, aux_r) < 2e-1, (rel(out, out_r), rel(aux, aux_r))
