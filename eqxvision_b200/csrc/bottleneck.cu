@@ -171,6 +171,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
         mbar_wait(bar(kBarT1Empty + slot), ph ^ 1u);
         if (rank == 0) mbar_expect_tx(bar(kBarT1Full + slot), 2u * kT1Bytes);   // both CTAs' bytes land on this barrier
         tma_load_4d_pair(t1_s + slot * kT1Slot, &p.tmT1, bar(kBarT1Full + slot), 0, t.w0 - 1, t.h0 - 1, t.n0);
+        if (!kDown) {
+          // this tile's residual (16 slabs of 32 rows x 64 channels) on its way from HBM to L2: the producer runs one to
+          // two tiles ahead of the epilogue warps, which then fetch their slabs from L2. (Issued from the epilogue warps
+          // the prefetch instructions sat on their critical path: ~1500 cycles between two tiles.)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) tma_prefetch_l2_4d(&p.tmR, c * 64, t.w0, t.h0 + 4 * qq, t.n0);
+        }
         if (kDown) {
           mbar_wait(bar(kBarX0Empty), xph ^ 1u);
           if (rank == 0) mbar_expect_tx(bar(kBarX0Full), 2u * kTile);
@@ -305,11 +314,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBnThreads, 1)
     }
     for (int pi = p_first; pi < p.num_pairs; pi += p_stride, ++it) {
       const bool more = pi + p_stride < p.num_pairs;
-      if (more) {
-        tnext = bn_decode(p, 2 * (pi + p_stride) + (int)rank);
-        // the next tile's residual slab on its way from HBM to L2 while this tile is worked on
-        if (!kDown && lane == 0) tma_prefetch_l2_4d(&p.tmR, sub * 64, tnext.w0, tnext.h0 + 4 * q, tnext.n0);
-      }
+      if (more) tnext = bn_decode(p, 2 * (pi + p_stride) + (int)rank);
       // ---------------- e3: D3 (+ residual, in place) -> y ----------------
       mbar_wait(bar(kBarD3Full), tph);
       tc_fence_after();
