@@ -300,18 +300,25 @@ class Plan:
             self._input_nhwc[c_pad] = buf
         return self._input_nhwc[c_pad]
 
-    def _stem_input(self, ph: int, h: int, wd: int) -> torch.Tensor:
-        """the padded NHWC8 image the first-layer kernels read (eqxv_pack_stem_input / its uint8 twin), once per padding"""
-        if ph not in self._input_stem:
+    STEM_C4 = os.environ.get("EQXV_NO_STEM_C4") != "1"   # pixel-pair layout for stride-2 stems (A/B switch)
+
+    def _stem_input(self, ph: int, h: int, wd: int, c4: bool = False) -> torch.Tensor:
+        """the padded image the first-layer kernels read (eqxv_pack_stem_input[_c4] / their uint8 twins), once per padding
+        and layout: 8 channels per pixel, or - c4 - pairs of 4-channel pixels"""
+        key = (ph, c4)
+        if key not in self._input_stem:
             # the pack kernels write the zero border too: the whole buffer is rewritten every replay
-            xp = self.arena_ok(torch.zeros((self.n, h + 2 * ph, wd + 8, 8), dtype=BF16, device=self.device))
+            shape = (self.n, h + 2 * ph, (wd + 8) // 2, 8) if c4 else (self.n, h + 2 * ph, wd + 8, 8)
+            xp = self.arena_ok(torch.zeros(shape, dtype=BF16, device=self.device))
             self.act_bytes += xp.numel() * 2
             if self.u8 is not None:
-                self.step(ops.u8_pack_stem_input, x=self.x_in, lut=self.lut, pad=ph, out=xp)
+                self.step(ops.u8_pack_stem_input_c4 if c4 else ops.u8_pack_stem_input, x=self.x_in, lut=self.lut, pad=ph, out=xp)
+            elif c4:
+                self.step(ops.pack_stem_input_c4, x_nchw=self.x_in, pad=ph, out=xp)
             else:
                 self.step(ops.pack_stem_input, x_nchw=self.x_in, pad=ph, out=xp)
-            self._input_stem[ph] = xp
-        return self._input_stem[ph]
+            self._input_stem[key] = xp
+        return self._input_stem[key]
 
     # ---- conv --------------------------------------------------------------------------------
     @staticmethod
@@ -376,8 +383,10 @@ class Plan:
                     and res is None and not out_f32 and dst is None:
                 # first-layer conv on the raw image (resnet.py:243-251, vgg.py:137, efficientnet.py:327):
                 # padded NHWC8 image + one GEMM K-block per filter row (eqxv_conv_stem_bf16)
-                wp = self.const(_pack.pack_stem_weight(w))
-                self.step(ops.conv_stem, xpad=self._stem_input(ph, h, wd), wgt=wp, bias=bias_d, n=self.n, h=h, w=wd,
+                # stride-2 stems with <= 4 channels on an even width: pixel-pair layout (half the MMAs / staged bytes)
+                c4 = self.STEM_C4 and sh == 2 and c_in <= 4 and wd % 2 == 0 and cout <= 256
+                wp = self.const(_pack.pack_stem_weight_c4(w) if c4 else _pack.pack_stem_weight(w))
+                self.step(ops.conv_stem, xpad=self._stem_input(ph, h, wd, c4), wgt=wp, bias=bias_d, n=self.n, h=h, w=wd, c4=c4,
                           cout=cout, kh=kh, kw=kw, stride=sh, pad=ph, act=act, out=out.map(ho, wo))
                 return out
             xb = self.input_nhwc(_round8(c_in))

@@ -66,6 +66,8 @@ SIGNATURES = {
     "eqxv_conv_stem_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_conv_stem_maxpool_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_pack_stem_input": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_pack_stem_input_c4": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_conv_stem_c4_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_nhwc_bf16_to_nchw_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_maxpool2d_nhwc_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -93,6 +95,7 @@ SIGNATURES = {
     "eqxv_debug_bottleneck_timeline": [_vp],
     "eqxv_u8hwc_to_nchw_f32": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "eqxv_u8hwc_pack_stem_input": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "eqxv_u8hwc_pack_stem_input_c4": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_u8hwc_to_nhwc_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "eqxv_u8hwc_patchify_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_u8hwc_resize_bilinear": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
@@ -130,7 +133,7 @@ _initialised_device = None
 launch_count = 0  # number of kernel-launching C-ABI calls made by this process (bench bookkeeping)
 
 _LAUNCHING = {
-    "eqxv_conv2d_igemm_bf16", "eqxv_bottleneck64_fused_bf16", "eqxv_conv_stem_maxpool_bf16", "eqxv_gemm_bias_act_res_bf16", "eqxv_conv_stem_bf16",
+    "eqxv_conv2d_igemm_bf16", "eqxv_bottleneck64_fused_bf16", "eqxv_conv_stem_maxpool_bf16", "eqxv_conv_stem_c4_bf16", "eqxv_pack_stem_input_c4", "eqxv_u8hwc_pack_stem_input_c4", "eqxv_gemm_bias_act_res_bf16", "eqxv_conv_stem_bf16",
     "eqxv_pack_stem_input", "eqxv_nchw_f32_to_nhwc_bf16", "eqxv_nhwc_bf16_to_nchw_f32",
     "eqxv_maxpool2d_nhwc_bf16", "eqxv_maxpool2d_ceil_nhwc_bf16", "eqxv_avgpool2d_nhwc_bf16", "eqxv_adaptive_avgpool_nhwc_bf16",
     "eqxv_layernorm_bf16", "eqxv_attention_fwd_bf16", "eqxv_patchify_nchw_f32_bf16",

@@ -106,6 +106,16 @@ def pack_stem_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     return wp.reshape(o, kh * 64).to(torch.bfloat16).contiguous()
 
 
+def pack_stem_weight_c4(w_oihw: torch.Tensor) -> torch.Tensor:
+    """[O, I<=4, kh<=8, kw<=8] -> [O, kh(r), 64] bf16, K index 4*s + c (zeros beyond kw / cin and in the upper 32
+    columns): the filter of eqxv_conv_stem_c4_bf16 (pixel-pair layout)"""
+    o, i, kh, kw = w_oihw.shape
+    assert i <= 4 and kh <= 8 and kw <= 8
+    wp = torch.zeros(o, kh, 16, 4, dtype=torch.float32)
+    wp[:, :, :kw, :i] = w_oihw.permute(0, 2, 3, 1)
+    return wp.reshape(o, kh * 64).to(torch.bfloat16).contiguous()
+
+
 def pack_linear_weight(w: torch.Tensor, in_pad: int) -> torch.Tensor:
     o, i = w.shape
     if in_pad != i:

@@ -83,6 +83,7 @@ struct alignas(64) IgemmParams {
   int pool_h, pool_w, pool_pitch;
   // first-layer (halo) kernel only
   int h_stride, h_planes, h_px, h_rows, h_plane_pitch, h_stage_bytes, h_ksteps, h_off_b;
+  int h_stride_y;   // vertical stride (== h_stride except for the pixel-pair layout: horizontal 1, vertical 2)
   const void* h_src;  // padded NHWC8 image [n, in_h, in_w, 8]
 };
 
@@ -1192,7 +1193,8 @@ constexpr int kStemThreads = kThreads + 32 * (kStemProducers - 1);   // warps 0 
 // issue-bound on the address arithmetic (profiles/r01_stem_v2: the producer warp never idles), so the
 // rows of a tile are dealt round-robin to kStemProducers warps; every lane arrives on the stage's
 // barrier after ITS copies have landed and been fenced for the async proxy (tcgen05.mma reads).
-__device__ __forceinline__ void stem_gather(const IgemmParams& p, const uint32_t base, const int pw) {
+template <int kLookahead>   // tiles in flight per warp (cp.async groups); needs kLookahead + 2 stages
+__device__ __forceinline__ void stem_gather_la(const IgemmParams& p, const uint32_t base, const int pw) {
   const int S = p.stages;
   const uint32_t bars = base + p.off_bars;
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -1203,14 +1205,13 @@ __device__ __forceinline__ void stem_gather(const IgemmParams& p, const uint32_t
   const int span = p.h_px * p.h_stride;  // input pixels per halo row
   const long long row_b = (long long)wp * 16;
   const uint32_t drow_b = (uint32_t)(p.h_px * 16);
-  constexpr int kLookahead = 3;          // tiles in flight per warp (cp.async groups)
   int stage = 0, cstage = 0, pending = 0;
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const TileCoord t = decode_tile(p, tile);
     mbar_wait(empty_bar(stage), phase ^ 1u);
     const uint32_t a_dst = base + stage * p.h_stage_bytes;
-    const int gy0 = t.h0 * p.h_stride, gx0 = t.w0 * p.h_stride;
+    const int gy0 = t.h0 * p.h_stride_y, gx0 = t.w0 * p.h_stride;
     const int rows_ok = min(p.h_rows, hp - gy0);
     for (int px = lane; px < span; px += 32) {
       const int gx = gx0 + px;
@@ -1249,6 +1250,17 @@ __device__ __forceinline__ void stem_gather(const IgemmParams& p, const uint32_t
   for (; pending > 0; --pending) {
     mbar_arrive(full_bar(cstage));
     if (++cstage == S) cstage = 0;
+  }
+}
+
+// The gather is LATENCY bound: halving the staged bytes (pixel-pair layout), halving the MMAs and doubling the epilogue warps
+// each moved the ResNet stem by < 6 % - what sets its ~2000 cycles per tile is three tiles in flight per producer warp
+// against ~3 us of loaded HBM latency. Six in flight where the ring is deep enough.
+__device__ __forceinline__ void stem_gather(const IgemmParams& p, const uint32_t base, const int pw) {
+  if (p.stages >= 8) {
+    stem_gather_la<6>(p, base, pw);
+  } else {
+    stem_gather_la<3>(p, base, pw);
   }
 }
 
@@ -1343,8 +1355,9 @@ __device__ __forceinline__ void stem_pool_epilogue(const IgemmParams& p, const u
   }
 }
 
-template <int kAct, bool kPool = false>
-__global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_constant__ IgemmParams p) {
+constexpr int kStemThreads16 = kThreads16 + 32 * (kStemProducers - 1);   // sixteen epilogue warps (see epilogue_warps16)
+template <int kAct, bool kPool = false, bool kEpi16 = false>
+__global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) stem_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1407,7 +1420,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
     const uint64_t bdesc_hi = umma_desc_sw128(0);
     // A: SWIZZLE_NONE, K-major. LBO = byte distance tap 2j -> tap 2j+1, SBO = next output row.
     const uint32_t lbo = (p.h_stride == 1) ? 16u : (uint32_t)p.h_plane_pitch;
-    const uint32_t sbo = (uint32_t)(p.h_stride * p.h_px * 16);
+    const uint32_t sbo = (uint32_t)(p.h_stride_y * p.h_px * 16);
     const uint64_t adesc_hi = ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
     // per-K-step start offsets (tap 2j: plane (2j % stride), pixel 2j / stride), hoisted out of the
     // issue loop: the single issuing thread must not spend cycles on integer division
@@ -1454,6 +1467,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_kernel(const __grid_cons
   } else if (warp < 2 + 4 * p.epi_sub) {
     if constexpr (kPool) {
       stem_pool_epilogue(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
+    } else if constexpr (kEpi16) {
+      epilogue_warps16<kAct, 0, false>(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
     } else {
       epilogue_warps<false, kAct, 0>(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
     }
@@ -2071,13 +2086,23 @@ static KernelFn halo_table(int act, int res_mode) {
 }
 
 using StemFn = void (*)(const IgemmParams);
+static StemFn stem_table16(int act);
 static StemFn stem_table(int act) {
   static const StemFn t[kNumActs] = {stem_kernel<0>, stem_kernel<1>, stem_kernel<2>, stem_kernel<3>,
                                      stem_kernel<4>, stem_kernel<5>, stem_kernel<6>, stem_kernel<7>};
   return t[act];
 }
 
+static StemFn stem_table16(int act) {
+  static const StemFn t[kNumActs] = {stem_kernel<0, false, true>, stem_kernel<1, false, true>, stem_kernel<2, false, true>,
+                                     stem_kernel<3, false, true>, stem_kernel<4, false, true>, stem_kernel<5, false, true>,
+                                     stem_kernel<6, false, true>, stem_kernel<7, false, true>};
+  return t[act];
+}
+
 int igemm_init() {
+  for (int a = 0; a < kNumActs; ++a)
+    EQXV_CUDA(cudaFuncSetAttribute(stem_table16(a), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < kNumActs; ++a)
     EQXV_CUDA(cudaFuncSetAttribute(epi16_table(a), cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   for (int a = 0; a < 3; ++a)
@@ -2426,7 +2451,13 @@ extern "C" int eqxv_gemm_gated_bf16(const void* a, int64_t lda, const void* gate
 
 static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n, int32_t h, int32_t w,
                           int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t y_pitch, int32_t act,
-                          bool pool, void* stream);
+                          bool pool, void* stream, bool c4 = false);
+
+extern "C" int eqxv_conv_stem_c4_bf16(const void* xpad4, const void* wgt, const float* bias, void* y, int32_t n, int32_t h,
+                                      int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
+                                      int32_t y_pitch, int32_t act, void* stream) {
+  return conv_stem_impl(xpad4, wgt, bias, y, n, h, w, cout, kh, kw, stride, pad, y_pitch, act, false, stream, true);
+}
 
 extern "C" int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n,
                                    int32_t h, int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride,
@@ -2442,8 +2473,11 @@ extern "C" int eqxv_conv_stem_maxpool_bf16(const void* xpad, const void* wgt, co
 
 static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n, int32_t h, int32_t w,
                           int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t y_pitch, int32_t act,
-                          bool pool, void* stream) {
+                          bool pool, void* stream, bool c4) {
   EQXV_CHECK_ARG(xpad && wgt && y, "stem: null pointer");
+  if (c4)
+    EQXV_CHECK_ARG(stride == 2 && w % 2 == 0 && cout <= 256 && !pool,
+                   "stem(c4): the pixel-pair layout is for stride-2 first layers on even widths (stride %d, w %d)", stride, w);
   EQXV_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0, "stem: bad shape");
   EQXV_CHECK_ARG(kh >= 1 && kh <= 8 && kw >= 1 && kw <= 8 && stride >= 1 && stride <= 4 && pad >= 0 &&
                      2 * pad <= kw,
@@ -2451,7 +2485,8 @@ static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, 
   EQXV_CHECK_ARG(y_pitch % 8 == 0 && y_pitch >= cout, "stem: bad y_pitch");
   const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
   EQXV_CHECK_ARG(ho > 0 && wo > 0, "stem: empty output");
-  const int hp = h + 2 * pad, wp = w + 8;  // layout written by eqxv_pack_stem_input
+  // layout written by eqxv_pack_stem_input; c4: [n, hp, (w + 8) / 2 pixel pairs, 2 x 4 channels] (eqxv_pack_stem_input_c4)
+  const int hp = h + 2 * pad, wp = c4 ? (w + 8) / 2 : w + 8;
   EQXV_CHECK_ARG(act >= 0 && act < kNumActs, "stem: unknown activation %d", act);
   if (pool)
     EQXV_CHECK_ARG(cout == 64 && ho % 16 == 0 && wo % 8 == 0 && (stride == 1 || stride == 2 || stride == 4) && y_pitch % 8 == 0 &&
@@ -2475,30 +2510,38 @@ static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, 
     p.num_tiles = (int)num_tiles;
     p.kh = kh, p.kw = kw;
     p.cout = cout, p.act = act, p.bias = bias;
-    p.h_stride = stride, p.h_planes = stride;
-    p.h_ksteps = ceil_div(kw, 2);
+    // c4: a 16-byte unit is a PAIR of 4-channel pixels, so a stride-2 convolution walks the units with stride 1 (no
+    // phase planes), a filter row of kw taps is ceil(kw / 2) unit taps = ceil(kw / 4) K steps - half the MMAs, half the
+    // halo bytes and half the packed image of the 8-channel layout (ResNet stem: 28 -> 14 UMMAs per tile).
+    const int sx = c4 ? 1 : stride;
+    const int kw_u = c4 ? ceil_div(kw, 2) : kw;   // filter width in 16-byte units
+    p.h_stride = sx, p.h_planes = sx, p.h_stride_y = stride;
+    p.h_ksteps = ceil_div(kw_u, 2);
     const int kw_pad = 2 * p.h_ksteps;
-    p.h_px = p.tw + (kw_pad - 1) / stride;
+    p.h_px = p.tw + (kw_pad - 1) / sx;
     p.h_rows = (p.th - 1) * stride + kh;
     p.h_plane_pitch = ceil_div(p.h_rows * p.h_px * 16, 128) * 128;
     p.h_stage_bytes = ceil_div(p.h_plane_pitch * p.h_planes, 1024) * 1024;
     const int b_bytes = kh * block_n * 128;
     const int bias_bytes = ceil_div((block_n + 64) * 4, 1024) * 1024;
-    int stages = (kMaxSmem - 1024 - b_bytes - 2 * kStageBuf - bias_bytes - 256) / p.h_stage_bytes;
-    stages = std::min(stages, 6);
+    // EQXV_STEM_SUB: 1 / 2 / 4 epilogue warps per TMEM lane quadrant (default 2; 4 measured slower, see stem_gather)
+    static const int stem_sub = getenv("EQXV_STEM_SUB") ? atoi(getenv("EQXV_STEM_SUB")) : 0;
+    const bool epi16 = !pool && stem_sub == 4 && block_n % 16 == 0;   // measured: 182 vs 170 us with eight warps - opt-in only
+    const int out_bytes = epi16 ? 4 * kStageBuf : 2 * kStageBuf;
+    int stages = (kMaxSmem - 1024 - b_bytes - out_bytes - bias_bytes - 512) / p.h_stage_bytes;
+    stages = std::min(stages, 10);
     EQXV_CHECK_ARG(stages >= 2, "stem: not enough shared memory (k=%dx%d cout=%d)", kh, kw, cout);
     p.stages = stages;
     p.h_off_b = stages * p.h_stage_bytes;
     p.off_out = p.h_off_b + b_bytes;
-    p.off_res = p.off_out + 2 * kStageBuf;
+    p.off_res = p.off_out + out_bytes;
     // N = 64 is one chunk per tile and 28 MMAs (~900 tensor cycles): with one epilogue warp per quadrant its
     // ~2000-cycle chain per tile bounded the kernel (188 us against 98 us of HBM traffic); two warps per
     // quadrant take alternate tiles.
-    static const int stem_sub = getenv("EQXV_STEM_SUB") ? atoi(getenv("EQXV_STEM_SUB")) : 0;
-    p.epi_sub = (stem_sub == 1 && !pool) ? 1 : 2;   // the pooling epilogue is written for two groups of four warps
+    p.epi_sub = epi16 ? 4 : ((stem_sub == 1 && !pool) ? 1 : 2);   // the pooling epilogue is written for two groups of four warps
     p.off_bias = p.off_res;
   p.off_bars = p.off_bias + bias_bytes;
-    const int smem_bytes = p.off_bars + 256 + 1024;
+    const int smem_bytes = p.off_bars + 512 + 1024;   // barriers: 2 S + 15 slots of 8 bytes (S <= 10)
 
     p.h_src = xpad;
     p.in_h = hp, p.in_w = wp;
@@ -2544,7 +2587,8 @@ static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, 
     rc = encode_tmap(&p.tmC, c);
     if (rc) return rc;
     const int grid = std::min(p.num_tiles, device_sm_count());
-    EQXV_CUDA(launch_kernel(stem_table(act), dim3(grid), dim3(64 + 128 * p.epi_sub + 32 * (kStemProducers - 1)), (size_t)(smem_bytes), (cudaStream_t)stream, p));
+    EQXV_CUDA(launch_kernel(epi16 ? stem_table16(act) : stem_table(act), dim3(grid),
+                            dim3(64 + 128 * p.epi_sub + 32 * (kStemProducers - 1)), (size_t)(smem_bytes), (cudaStream_t)stream, p));
     EQXV_CUDA(cudaGetLastError());
     return EQXV_OK;
   }

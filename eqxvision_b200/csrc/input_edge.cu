@@ -84,6 +84,47 @@ __global__ void u8_pack_stem_kernel(const uint8_t* __restrict__ x, const float* 
   }
 }
 
+// ... and into the pixel-pair layout of eqxv_conv_stem_c4_bf16: [n, h+2*pad, (w+8)/2, 8], unit = padded columns (2u, 2u+1) x 4 ch
+__global__ void u8_pack_stem_c4_kernel(const uint8_t* __restrict__ x, const float* __restrict__ lut,
+                                       bf16x8e* __restrict__ y, int c, int h, int w, int pad) {
+  __shared__ float s[4 * 256];
+  load_lut(s, lut, c);
+  griddep_wait();
+  griddep_launch();
+  const int wu = (w + 8) / 2, hp = h + 2 * pad;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ph0 = blockIdx.y * kEdgeRows, img = blockIdx.z;
+  if (u >= wu) return;
+  uint8_t px[kEdgeRows][8];
+  bool okm[kEdgeRows][2];
+#pragma unroll
+  for (int r = 0; r < kEdgeRows; ++r) {
+    const int sh = ph0 + r - pad;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int sw = 2 * u + e - pad;
+      const bool ok = sh >= 0 && sh < h && sw >= 0 && sw < w;
+      okm[r][e] = ok;
+      const uint8_t* src = x + (((long long)img * h + (ok ? sh : 0)) * w + (ok ? sw : 0)) * c;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) px[r][4 * e + q] = (ok && q < c) ? __ldg(src + q) : (uint8_t)0;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kEdgeRows; ++r) {
+    if (ph0 + r >= hp) break;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) f[4 * e + q] = (okm[r][e] && q < c) ? s[q * 256 + px[r][4 * e + q]] : 0.f;
+    bf16x8e o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    y[((long long)img * hp + ph0 + r) * wu + u] = o;
+  }
+}
+
 // uint8 NHWC [n,h,w,c<=4] -> bf16 NHWC [n,h,w,8] (channels zero-padded to 8)
 __global__ void u8_to_nhwc8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ lut,
                                    bf16x8e* __restrict__ y, int c, long long pixels) {
@@ -186,6 +227,17 @@ extern "C" int eqxv_u8hwc_pack_stem_input(const uint8_t* x, const float* lut, vo
   EQXV_CUDA(launch_kernel(u8_pack_stem_kernel, dim3((unsigned)ceil_div(w + 8, kEdgeThreads), (unsigned)ceil_div(h + 2 * pad, kEdgeRows), (unsigned)n),
                           dim3(kEdgeThreads), (size_t)0, (cudaStream_t)stream, x, lut, reinterpret_cast<bf16x8e*>(y), c, h,
                           w, pad));
+  EQXV_CUDA(cudaGetLastError());
+  return EQXV_OK;
+}
+
+extern "C" int eqxv_u8hwc_pack_stem_input_c4(const uint8_t* x, const float* lut, void* y, int32_t n, int32_t h, int32_t w,
+                                             int32_t c, int32_t pad, void* stream) {
+  EDGE_ARGS_OK("u8hwc_pack_stem_input_c4");
+  EQXV_CHECK_ARG(pad >= 0 && pad <= 4 && w % 2 == 0, "u8hwc_pack_stem_input_c4: pad out of range / odd width");
+  EQXV_CUDA(launch_kernel(u8_pack_stem_c4_kernel,
+                          dim3((unsigned)ceil_div((w + 8) / 2, 128), (unsigned)ceil_div(h + 2 * pad, kEdgeRows), (unsigned)n),
+                          dim3(128), (size_t)0, (cudaStream_t)stream, x, lut, reinterpret_cast<bf16x8e*>(y), c, h, w, pad));
   EQXV_CUDA(cudaGetLastError());
   return EQXV_OK;
 }

@@ -108,6 +108,39 @@ __global__ void pack_stem_kernel(const float* __restrict__ x, bf16x8* __restrict
   }
 }
 
+// Pixel-pair layout for stride-2 first layers with <= 4 input channels (eqxv_conv_stem_c4_bf16): fp32 NCHW [n,c<=4,h,w] ->
+// bf16 [n, h+2*pad, (w+8)/2, 8]: one 16-byte unit = padded columns (2u, 2u+1) x 4 channels, image at (pad, pad), zeros
+// elsewhere. Half the bytes of the 8-channel layout, and the stride-2 convolution walks the units with stride 1.
+__global__ void pack_stem_c4_kernel(const float* __restrict__ x, bf16x8* __restrict__ y, int n, int c, int h, int w,
+                                    int pad) {
+  griddep_wait();   // PDL: the predecessor kernel has completed (ptx.cuh)
+  griddep_launch();
+  const int wu = (w + 8) / 2, hp = h + 2 * pad;
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ph0 = blockIdx.y * kPackRows, img = blockIdx.z;
+  if (u >= wu) return;
+  const long long plane = (long long)h * w;
+  const float* src0 = x + (long long)img * c * plane;
+  float f[kPackRows][8];
+#pragma unroll
+  for (int r = 0; r < kPackRows; ++r) {
+    const int sh = ph0 + r - pad;
+    const bool row_ok = sh >= 0 && sh < h;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int sw = 2 * u + e - pad;
+      const bool ok = row_ok && sw >= 0 && sw < w;
+      const float* src = src0 + (long long)(ok ? sh : 0) * w + (ok ? sw : 0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) f[r][4 * e + q] = (ok && q < c) ? __ldg(src + q * plane) : 0.f;
+    }
+  }
+  bf16x8* dst = y + ((long long)img * hp + ph0) * wu + u;
+#pragma unroll
+  for (int r = 0; r < kPackRows; ++r)
+    if (ph0 + r < hp) dst[(long long)r * wu] = pack8(f[r]);
+}
+
 // fp32 NCHW -> bf16 NHWC (channels padded with zeros to c_pad)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16x8* __restrict__ y, int n, int c,
                                     int h, int w, int c_pad) {
@@ -673,6 +706,19 @@ extern "C" int eqxv_pack_stem_input(const float* x, void* xpad, int32_t n, int32
                           dim3((unsigned)((w + 8 + 127) / 128), (unsigned)((h + 2 * pad + kPackRows - 1) / kPackRows), (unsigned)n),
                           dim3(128), (size_t)0, (cudaStream_t)stream, x, reinterpret_cast<bf16x8*>(xpad), n, c, h, w,
                           pad));
+  EQXV_LAUNCH_CHECK();
+  return EQXV_OK;
+}
+
+extern "C" int eqxv_pack_stem_input_c4(const float* x, void* xpad4, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
+                                       void* stream) {
+  EQXV_CHECK_ARG(x && xpad4 && n > 0 && h > 0 && w > 0 && w % 2 == 0 && c >= 1 && c <= 4 && pad >= 0 && pad <= 4,
+                 "pack_stem_input_c4: bad arguments (<= 4 channels, even width)");
+  EQXV_CHECK_ARG(h + 2 * pad <= 65535 * kPackRows && n <= 65535, "pack_stem_input_c4: image too tall / batch too large");
+  EQXV_CUDA(launch_kernel(pack_stem_c4_kernel,
+                          dim3((unsigned)(((w + 8) / 2 + 127) / 128), (unsigned)((h + 2 * pad + kPackRows - 1) / kPackRows),
+                               (unsigned)n),
+                          dim3(128), (size_t)0, (cudaStream_t)stream, x, reinterpret_cast<bf16x8*>(xpad4), n, c, h, w, pad));
   EQXV_LAUNCH_CHECK();
   return EQXV_OK;
 }

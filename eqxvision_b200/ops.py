@@ -145,13 +145,24 @@ def pack_stem_input(x_nchw, pad=3, out=None, stream=0):
     return out
 
 
-def conv_stem(xpad, wgt, bias, *, n, h, w, cout, kh=7, kw=7, stride=2, pad=3, act=1, out=None, stream=0):
+def pack_stem_input_c4(x_nchw, pad=3, out=None, stream=0):
+    """fp32 NCHW (<= 4 channels, even width) -> the pixel-pair layout [n, h+2*pad, (w+8)/2, 8] of conv_stem(c4=True)"""
+    _check_cuda(x_nchw, out)
+    n, c, h, w = x_nchw.shape
+    assert c <= 4 and w % 2 == 0 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    if out is None:
+        out = torch.empty((n, h + 2 * pad, (w + 8) // 2, 8), dtype=BF16, device=x_nchw.device)
+    call("eqxv_pack_stem_input_c4", ptr(x_nchw), ptr(out), n, c, h, w, pad, stream)
+    return out
+
+
+def conv_stem(xpad, wgt, bias, *, n, h, w, cout, kh=7, kw=7, stride=2, pad=3, act=1, out=None, c4=False, stream=0):
     _check_cuda(xpad, wgt, bias, out)
     ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
     if out is None:
         out = torch.empty((n, ho, wo, cout), dtype=BF16, device=xpad.device)
-    call("eqxv_conv_stem_bf16", ptr(xpad), ptr(wgt), ptr(bias), ptr(out), n, h, w, cout, kh, kw, stride, pad,
-         out.stride(2), act, stream)
+    call("eqxv_conv_stem_c4_bf16" if c4 else "eqxv_conv_stem_bf16", ptr(xpad), ptr(wgt), ptr(bias), ptr(out), n, h, w, cout,
+         kh, kw, stride, pad, out.stride(2), act, stream)
     return out
 
 
@@ -421,6 +432,15 @@ def u8_pack_stem_input(x, lut, pad=3, out=None, stream=0):
     if out is None:
         out = torch.empty((n, h + 2 * pad, w + 8, 8), dtype=BF16, device=x.device)
     call("eqxv_u8hwc_pack_stem_input", ptr(x), ptr(lut), ptr(out), n, h, w, c, pad, stream)
+    return out
+
+
+def u8_pack_stem_input_c4(x, lut, pad=3, out=None, stream=0):
+    _check_u8(x, lut)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, h + 2 * pad, (w + 8) // 2, 8), dtype=BF16, device=x.device)
+    call("eqxv_u8hwc_pack_stem_input_c4", ptr(x), ptr(lut), ptr(out), n, h, w, c, pad, stream)
     return out
 
 

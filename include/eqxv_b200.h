@@ -163,6 +163,17 @@ int eqxv_bottleneck64_fused_bf16(const eqxv_bottleneck64_desc* d, void* stream);
 int eqxv_conv_stem_bf16(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n, int32_t h,
                         int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
                         int32_t y_pitch, int32_t act, void* stream);
+/* Pixel-pair variant for stride-2 first layers with <= 4 input channels (the ResNet / EfficientNet / MobileNet stems): the
+ * padded image is bf16 [n, h+2*pad, (w+8)/2, 8] - one 16-byte unit = padded columns (2u, 2u+1) x 4 channels, written by
+ * eqxv_pack_stem_input_c4 / eqxv_u8hwc_pack_stem_input_c4 - and the filter is [cout, kh, 64] with K index 4*s + c
+ * (s < kw, c < cin; zeros elsewhere). A stride-2 convolution walks the units with stride 1, a 7-tap filter row is 4 unit
+ * taps = 2 K steps: half the MMAs, half the staged bytes and half the packed image of the 8-channel layout. Same
+ * arithmetic, same results. w must be even. */
+int eqxv_conv_stem_c4_bf16(const void* xpad4, const void* wgt, const float* bias, void* y, int32_t n, int32_t h, int32_t w,
+                           int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t y_pitch, int32_t act,
+                           void* stream);
+int eqxv_pack_stem_input_c4(const float* x_nchw, void* xpad4, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
+                            void* stream);
 /* ... with the max-pool that follows it in the ResNet stem (resnet.py:243-253: conv1 -> bn1 -> relu -> maxpool 3x3 /
  * stride 2 / pad 1) in the kernel's epilogue: y_pooled is bf16 [n, ho/2, wo/2, y_pitch]; the conv output itself (411 MB
  * for a 256-image batch) is never written. ReLU is implied (0 is then the identity of max, which is what lets the pooled
@@ -312,6 +323,9 @@ int eqxv_u8hwc_to_nchw_f32(const uint8_t* x, const float* lut, float* y, int32_t
 /* -> bf16 [n, h+2*pad, w+8, 8], the layout eqxv_conv_stem_bf16 reads (same as eqxv_pack_stem_input) */
 int eqxv_u8hwc_pack_stem_input(const uint8_t* x, const float* lut, void* xpad, int32_t n, int32_t h, int32_t w,
                                int32_t c, int32_t pad, void* stream);
+/* -> the pixel-pair layout of eqxv_conv_stem_c4_bf16 (same as eqxv_pack_stem_input_c4) */
+int eqxv_u8hwc_pack_stem_input_c4(const uint8_t* x, const float* lut, void* xpad4, int32_t n, int32_t h, int32_t w,
+                                  int32_t c, int32_t pad, void* stream);
 /* -> bf16 NHWC [n, h, w, 8] (channels zero-padded to 8), same as eqxv_nchw_f32_to_nhwc_bf16(c_pad = 8) */
 int eqxv_u8hwc_to_nhwc_bf16(const uint8_t* x, const float* lut, void* y, int32_t n, int32_t h, int32_t w, int32_t c,
                             void* stream);

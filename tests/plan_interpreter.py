@@ -77,7 +77,37 @@ def pack_stem_input(x_nchw, pad, out, **_):
     out[:, pad:pad + h, pad:pad + w, :c].copy_(x_nchw.permute(0, 2, 3, 1).to(out.dtype))
 
 
-def conv_stem(xpad, wgt, bias, n, h, w, cout, kh, kw, stride, pad, act, out, **_):
+def _unpair(xpad4, wgt4, cout, kh):
+    """pixel-pair layout (include/eqxv_b200.h, eqxv_conv_stem_c4_bf16) -> the 8-channel layout conv_stem() below reads"""
+    n, hp, wu, _ = xpad4.shape
+    x8 = torch.zeros((n, hp, 2 * wu, 8), dtype=xpad4.dtype)
+    x8[..., :4] = xpad4.reshape(n, hp, wu, 2, 4).reshape(n, hp, 2 * wu, 4)
+    w4 = wgt4.reshape(cout, kh, 16, 4)
+    assert w4[:, :, 8:].abs().max() == 0, "stem(c4): the upper 32 K columns of every filter row must be zero"
+    w8 = torch.zeros((cout, kh, 8, 8), dtype=wgt4.dtype)
+    w8[..., :4] = w4[:, :, :8]
+    return x8, w8.reshape(cout, kh * 64)
+
+
+def pack_stem_input_c4(x_nchw, pad, out, **_):
+    n, c, h, w = x_nchw.shape
+    assert c <= 4 and w % 2 == 0
+    x8 = torch.zeros((n, h + 2 * pad, w + 8, 8), dtype=out.dtype)
+    pack_stem_input(x_nchw, pad, x8)
+    out.copy_(x8[..., :4].reshape(n, h + 2 * pad, (w + 8) // 2, 8))
+
+
+def u8_pack_stem_input_c4(x, lut, pad, out, **_):
+    n, h, w, c = x.shape
+    x8 = torch.zeros((n, h + 2 * pad, w + 8, 8), dtype=out.dtype)
+    u8_pack_stem_input(x, lut, pad, x8)
+    out.copy_(x8[..., :4].reshape(n, h + 2 * pad, (w + 8) // 2, 8))
+
+
+def conv_stem(xpad, wgt, bias, n, h, w, cout, kh, kw, stride, pad, act, out, c4=False, **_):
+    if c4:
+        assert stride == 2 and w % 2 == 0
+        xpad, wgt = _unpair(xpad, wgt, cout, kh)
     # xpad [n, h+2p, w+8, 8] with the image at (pad, pad); wgt [cout, kh, 8(s), 8(c)] with zero taps for s >= kw
     img = xpad[:, :, : w + 2 * pad, :].float().permute(0, 3, 1, 2)
     wt = wgt.float().reshape(cout, kh, 8, 8)[:, :, :kw, :].permute(0, 3, 1, 2)
@@ -370,7 +400,7 @@ def u8_resize_bilinear(x, oh, ow, out, **_):
     out.copy_(y.round().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1))
 
 
-IMPLS = {f.__name__: f for f in (bottleneck64, conv_stem_maxpool, gemm_gated, gemm_rowstats, gemm_ln, dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
+IMPLS = {f.__name__: f for f in (bottleneck64, conv_stem_maxpool, pack_stem_input_c4, u8_pack_stem_input_c4, gemm_gated, gemm_rowstats, gemm_ln, dwconv_pool, u8_to_nchw_f32, u8_pack_stem_input, u8_to_nhwc, u8_patchify, u8_resize_bilinear,
                                  nchw_to_nhwc, nhwc_to_nchw, pack_stem_input, conv_stem, conv2d, gemm, dwconv,
                                  maxpool2d, avgpool2d, adaptive_avgpool, eltwise, layernorm, copy2d, patchify,
                                  vit_assemble_tokens, attention, attention_probs, gather_rows, resize_bilinear,

@@ -646,3 +646,33 @@ def test_stem_with_fused_maxpool(device, n, h, w):
         assert got.shape == ref.shape and torch.equal(got, ref)
     with pytest.raises(Exception):   # 56x56 conv output does not tile into 16-row blocks
         ops.conv_stem_maxpool(ops.pack_stem_input(x[:, :, :112, :112].contiguous()), wp, bias, n=n, h=112, w=112, cout=64)
+
+
+# n, cin, h, w, cout, k, pad, act
+STEM_C4_CASES = [(3, 3, 224, 224, 64, 7, 3, 1), (2, 3, 380, 380, 48, 3, 1, 2), (5, 3, 97, 130, 64, 7, 3, 1), (2, 1, 64, 64, 32, 5, 2, 0),
+                 (2, 4, 96, 64, 24, 3, 1, 4), (37, 3, 224, 224, 64, 7, 3, 1)]
+
+
+@pytest.mark.parametrize("case", STEM_C4_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_stem_pixel_pair_layout(device, case):
+    """eqxv_conv_stem_c4_bf16 (stride-2 first layers, <= 4 channels; resnet.py:243-251, efficientnet.py:327-337): pairs of
+    4-channel pixels per 16-byte unit, half the K steps of the 8-channel layout; against torch and against that layout."""
+    from eqxvision_b200 import _pack, ops
+
+    n, cin, h, w, cout, k, pad, act = case
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(n, cin, h, w, generator=g).to(device)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (cin * k * k) ** -0.5
+    bias = torch.randn(cout, generator=g).to(device)
+    y8 = ops.conv_stem(ops.pack_stem_input(x, pad=pad), _pack.pack_stem_weight(wt).to(device), bias, n=n, h=h, w=w, cout=cout,
+                       kh=k, kw=k, stride=2, pad=pad, act=act)
+    x4 = ops.pack_stem_input_c4(x, pad=pad)
+    assert x4.shape == (n, h + 2 * pad, (w + 8) // 2, 8)
+    y4 = ops.conv_stem(x4, _pack.pack_stem_weight_c4(wt).to(device), bias, n=n, h=h, w=w, cout=cout, kh=k, kw=k, stride=2, pad=pad,
+                       act=act, c4=True)
+    ref = F.conv2d(x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float().to(device), bias, stride=2, padding=pad)
+    ref = ACTS[act](ref).permute(0, 2, 3, 1)
+    assert rel_l2(y4, ref) < TOL_BF16 and rel_l2(y4, y8) < 1e-3
+    with pytest.raises(Exception):   # stride 1 has no pixel-pair variant
+        ops.conv_stem(x4, _pack.pack_stem_weight_c4(wt).to(device), bias, n=n, h=h, w=w, cout=cout, kh=k, kw=k, stride=1, pad=pad,
+                      act=act, c4=True)

@@ -81,7 +81,7 @@ def test_u8_plan_lowers_to_the_same_result_as_the_fp32_plan(arch, hw, tmp_path):
     got_f32, _ = PI.run(net, b.reference_pipeline())
     assert torch.equal(got_u8, got_f32)
     names = [fn.__name__ for fn, _ in plan.steps]
-    assert names[0] in ("u8_pack_stem_input", "u8_to_nhwc", "u8_patchify")
+    assert names[0] in ("u8_pack_stem_input", "u8_pack_stem_input_c4", "u8_to_nhwc", "u8_patchify")
     assert not any(n in ("pack_stem_input", "nchw_to_nhwc", "patchify", "u8_to_nchw_f32") for n in names)
 
 
@@ -112,6 +112,11 @@ def test_u8_kernels_bit_exact(device, n, h, w):
         a, bb = ops.u8_pack_stem_input(px, lut, pad=pad), ops.pack_stem_input(ref_d, pad=pad)
         torch.cuda.synchronize()
         assert torch.equal(a, bb)
+        if w % 2 == 0:   # pixel-pair layout: the same pixels, 4 channels each, two per 16-byte unit
+            a4, b4 = ops.u8_pack_stem_input_c4(px, lut, pad=pad), ops.pack_stem_input_c4(ref_d, pad=pad)
+            torch.cuda.synchronize()
+            assert torch.equal(a4, b4)
+            assert torch.equal(a4.reshape(n, h + 2 * pad, w + 8, 4), bb[..., :4]) and (bb[..., 4:] == 0).all()
     a, bb = ops.u8_to_nhwc(px, lut), ops.nchw_to_nhwc(ref_d, c_pad=8)
     torch.cuda.synchronize()
     assert torch.equal(a, bb)
