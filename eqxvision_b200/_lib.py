@@ -93,6 +93,7 @@ SIGNATURES = {
     "eqxv_patch_merge_bf16": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_debug_attention_timeline": [_vp],
     "eqxv_debug_bottleneck_timeline": [_vp],
+    "eqxv_debug_stem_timeline": [_vp],
     "eqxv_u8hwc_to_nchw_f32": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "eqxv_u8hwc_pack_stem_input": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "eqxv_u8hwc_pack_stem_input_c4": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],

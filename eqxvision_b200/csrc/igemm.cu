@@ -83,9 +83,16 @@ struct alignas(64) IgemmParams {
   int pool_h, pool_w, pool_pitch;
   // first-layer (halo) kernel only
   int h_stride, h_planes, h_px, h_rows, h_plane_pitch, h_stage_bytes, h_ksteps, h_off_b;
+  int h_tma;        // first-layer kernel, pixel-pair layout: the halo tile is ONE dense TMA box per tile (no gather warps)
+  long long* dbg;   // eqxv_debug_stem_timeline: clock64 stamps of CTA 0 (tools/stem_timeline.py), normally null
   int h_stride_y;   // vertical stride (== h_stride except for the pixel-pair layout: horizontal 1, vertical 2)
   const void* h_src;  // padded NHWC8 image [n, in_h, in_w, 8]
 };
+
+#define IG_STAMP(it, ev)                                                                        \
+  do {                                                                                          \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (it) < 24) p.dbg[(it) * 16 + (ev)] = clock64(); \
+  } while (0)
 
 struct TileCoord {
   int ncol0, w0, h0, n0;
@@ -411,6 +418,7 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
       if ((long long)t_first + (long long)ti * t_stride >= p.num_tiles) break;
       mbar_wait(tfull_bar(ti & 1), (uint32_t)((ti >> 1) & 1));
       tc_fence_after();
+      if (warp == 2 + 4 * sub && lane == 0) IG_STAMP(ti, 6);
     }
     const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((ti & 1) * p.acc_stride);
     const uint32_t ob = l & (obufs - 1u);
@@ -489,6 +497,7 @@ __device__ __forceinline__ void epilogue_warps(const IgemmParams& p, const uint3
       tma_store_4d(&p.tmC, out_u32 + ob * kSlab, t.ncol0 + c * CH, t.w0 + w_off, t.h0 + h_off, t.n0 + n_off);
       tma_store_commit();
       if (tma_res) issue_res(l + 2);
+      if (warp == 2 + 4 * sub) IG_STAMP(ti, 7);
     }
     __syncwarp();
     c += nsub;
@@ -1256,15 +1265,10 @@ __device__ __forceinline__ void stem_gather_la(const IgemmParams& p, const uint3
   }
 }
 
-// The gather is LATENCY bound: halving the staged bytes (pixel-pair layout), halving the MMAs and doubling the epilogue warps
-// each moved the ResNet stem by < 6 % - what sets its ~2000 cycles per tile is three tiles in flight per producer warp
-// against ~3 us of loaded HBM latency. Six in flight where the ring is deep enough.
+// Three tiles in flight per gather warp (a deeper ring bought nothing: the gather warps are ISSUE bound, see the TMA path
+// of the pixel-pair layout in stem_kernel).
 __device__ __forceinline__ void stem_gather(const IgemmParams& p, const uint32_t base, const int pw) {
-  if (p.stages >= 8) {
-    stem_gather_la<6>(p, base, pw);
-  } else {
-    stem_gather_la<3>(p, base, pw);
-  }
+  stem_gather_la<3>(p, base, pw);   // six in flight measured SLOWER on the 8-channel layout (199 vs 174 us)
 }
 
 // First-layer epilogue with the max-pool that follows it (resnet.py:243-253: conv1 -> bn1 -> relu -> maxpool 3x3 / 2 / 1):
@@ -1377,7 +1381,7 @@ __global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) ste
     tma_prefetch_desc(&p.tmB);
     if (!kPool) tma_prefetch_desc(&p.tmC);
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 32 * kStemProducers);  // every producer lane arrives once its copies landed
+      mbar_init(full_bar(s), p.h_tma ? 1u : 32u * kStemProducers);  // gather: every producer lane arrives once its copies landed
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -1412,7 +1416,33 @@ __global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) ste
       for (int r = 0; r < p.kh; ++r) tma_load_2d(b_smem + r * b_slab, &p.tmB, wfull_bar, r * kBlockK, 0);
     }
     __syncwarp();
-    stem_gather(p, base, 0);
+    if (p.h_tma) {
+      // Pixel-pair layout: the halo tile is a dense [h_rows x h_px units] window of the packed image - one TMA box per
+      // tile (out-of-bounds = zero fill). The clock64 timeline of the gather (tools/stem_timeline.py) showed each of the
+      // four gather warps busy ~1900 cycles per tile (~950 to get ten 16-byte LDGSTS per lane accepted, the rest in
+      // group waits / fences / arrives): THAT was the tile period, whatever else was changed.
+      if (elect_one()) {
+        tma_prefetch_desc(&p.tmA);
+        const uint32_t bytes = (uint32_t)(p.h_px * 16 * p.h_rows);
+        int stage = 0, it = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+          const TileCoord t = decode_tile(p, tile);
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          IG_STAMP(it, 3);
+          mbar_expect_tx(full_bar(stage), bytes);
+          tma_load_4d(base + stage * p.h_stage_bytes, &p.tmA, full_bar(stage), t.w0 * p.h_stride * 8, t.h0 * p.h_stride_y, t.n0, 0);
+          IG_STAMP(it, 4);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      stem_gather(p, base, 0);
+    }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
@@ -1436,9 +1466,12 @@ __global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) ste
       uint32_t acc_phase = 0;
       mbar_wait(wfull_bar, 0);
       const uint64_t bdesc0 = bdesc_hi | (uint64_t)((b_smem & 0x3FFFF) >> 4);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        IG_STAMP(it, 0);
         mbar_wait(full_bar(stage), phase);
+        IG_STAMP(it, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         const uint32_t a_src = base + stage * p.h_stage_bytes;
@@ -1454,6 +1487,7 @@ __global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) ste
         }
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(acc));
+        IG_STAMP(it, 2);
         if (++stage == S) {
           stage = 0;
           phase ^= 1u;
@@ -1472,7 +1506,7 @@ __global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) ste
       epilogue_warps<false, kAct, 0>(p, base, gbase, tmem_base, warp, threadIdx.x & 31);
     }
   } else {
-    stem_gather(p, base, warp - (1 + 4 * p.epi_sub));  // producer warps 1..3
+    if (!p.h_tma) stem_gather(p, base, warp - (1 + 4 * p.epi_sub));  // producer warps 1..3
   }
 
   tc_fence_before();
@@ -2451,6 +2485,11 @@ extern "C" int eqxv_gemm_gated_bf16(const void* a, int64_t lda, const void* gate
 static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, void* y, int32_t n, int32_t h, int32_t w,
                           int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t y_pitch, int32_t act,
                           bool pool, void* stream, bool c4 = false);
+static long long* g_stem_dbg = nullptr;
+extern "C" int eqxv_debug_stem_timeline(long long* ts) {
+  g_stem_dbg = ts;
+  return EQXV_OK;
+}
 
 extern "C" int eqxv_conv_stem_c4_bf16(const void* xpad4, const void* wgt, const float* bias, void* y, int32_t n, int32_t h,
                                       int32_t w, int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
@@ -2528,7 +2567,7 @@ static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, 
     const bool epi16 = !pool && stem_sub == 4 && block_n % 16 == 0;   // measured: 182 vs 170 us with eight warps - opt-in only
     const int out_bytes = epi16 ? 4 * kStageBuf : 2 * kStageBuf;
     int stages = (kMaxSmem - 1024 - b_bytes - out_bytes - bias_bytes - 512) / p.h_stage_bytes;
-    stages = std::min(stages, 10);
+    stages = std::min(stages, c4 ? 10 : 6);
     EQXV_CHECK_ARG(stages >= 2, "stem: not enough shared memory (k=%dx%d cout=%d)", kh, kw, cout);
     p.stages = stages;
     p.h_off_b = stages * p.h_stage_bytes;
@@ -2543,7 +2582,25 @@ static int conv_stem_impl(const void* xpad, const void* wgt, const float* bias, 
     const int smem_bytes = p.off_bars + 512 + 1024;   // barriers: 2 S + 15 slots of 8 bytes (S <= 10)
 
     p.h_src = xpad;
+    p.dbg = g_stem_dbg;
     p.in_h = hp, p.in_w = wp;
+    static const bool no_stem_tma = getenv("EQXV_NO_STEM_TMA") != nullptr;
+    if (c4 && !no_stem_tma && p.h_px * 8 <= 256 && p.h_rows <= 256) {
+      TmapSpec a{};
+      a.base = const_cast<void*>(xpad);
+      a.dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      a.rank = 4;
+      a.swizzle = CU_TENSOR_MAP_SWIZZLE_NONE;
+      a.dims[0] = (uint64_t)wp * 8, a.dims[1] = (uint64_t)hp, a.dims[2] = (uint64_t)n, a.dims[3] = 1;
+      a.strides_bytes[0] = (uint64_t)wp * 16;
+      a.strides_bytes[1] = a.strides_bytes[0] * (uint64_t)hp;
+      a.strides_bytes[2] = a.strides_bytes[1] * (uint64_t)n;
+      a.box[0] = (uint32_t)(p.h_px * 8), a.box[1] = (uint32_t)p.h_rows, a.box[2] = 1, a.box[3] = 1;
+      a.estride[0] = a.estride[1] = a.estride[2] = a.estride[3] = 1;
+      int rc_a = encode_tmap(&p.tmA, a);
+      if (rc_a) return rc_a;
+      p.h_tma = 1;
+    }
     EQXV_CHECK_ARG(stages >= 4, "stem: pipeline too shallow");
     int rc;
     TmapSpec b{};

@@ -305,6 +305,8 @@ int eqxv_patch_merge_bf16(const void* x, void* y, int32_t n, int32_t h, int32_t 
 int eqxv_debug_attention_timeline(long long* ts);
 /* same for the fused bottleneck kernel (int64 [16 tiles][16 events]; tools/bneck_timeline.py); NULL switches it off */
 int eqxv_debug_bottleneck_timeline(long long* ts);
+/* same for the first-layer kernel (int64 [24 tiles][16 events]; tools/stem_timeline.py) */
+int eqxv_debug_stem_timeline(long long* ts);
 /* K13 fallback: strided device-to-device copy (channel slices of a concat buffer) */
 int eqxv_copy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
                       int64_t width_bytes, int64_t rows, void* stream);
