@@ -1443,8 +1443,8 @@ __global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) ste
     } else {
       stem_gather(p, base, 0);
     }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
+  } else if (warp == 1 || (p.h_tma && warp == 2 + 4 * p.epi_sub)) {
+    // ============================== MMA issuer(s) ==============================
     const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.block_n);
     const uint64_t bdesc_hi = umma_desc_sw128(0);
     // A: SWIZZLE_NONE, K-major. LBO = byte distance tap 2j -> tap 2j+1, SBO = next output row.
@@ -1459,15 +1459,19 @@ __global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) ste
       joff[j] = (uint32_t)(((2 * j) % p.h_stride) * p.h_plane_pitch + ((2 * j) / p.h_stride) * 16) >> 4;
     const uint32_t row_step = (uint32_t)(p.h_px * 16) >> 4;
     const int ksteps = p.h_ksteps, kh = p.kh;
+    // TMA mode: TWO issuing threads (this warp: even tiles / accumulator 0; the first idle gather warp: odd tiles /
+    // accumulator 1). One thread spends ~500 cycles per tile between its last UMMA and the next tile's first (commits,
+    // two barrier waits, loop) while the tensor pipe drains: with two, the other tile's UMMAs are already queued.
+    const int it_step = p.h_tma ? 2 : 1;
+    const int it0 = (p.h_tma && warp != 1) ? 1 : 0;
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
       mbar_wait(wfull_bar, 0);
       const uint64_t bdesc0 = bdesc_hi | (uint64_t)((b_smem & 0x3FFFF) >> 4);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int it = it0;; it += it_step) {
+        const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+        if (tile >= p.num_tiles) break;
+        const int stage = it % S, acc = it & 1;
+        const uint32_t phase = (uint32_t)((it / S) & 1), acc_phase = (uint32_t)((it >> 1) & 1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         IG_STAMP(it, 0);
         mbar_wait(full_bar(stage), phase);
@@ -1477,6 +1481,21 @@ __global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) ste
         const uint32_t a_src = base + stage * p.h_stage_bytes;
         uint64_t adesc = adesc_hi | (uint64_t)((a_src & 0x3FFFF) >> 4);
         uint64_t bdesc = bdesc0;
+        if (p.h_stride == 1 && (ksteps == 2 || ksteps == 4)) {
+          // Lean issue for the unit-stride layouts (joff[j] == 2 j, the same +2 steps as the filter): 32-bit descriptor
+          // words, one asm block per 2 / 4 K steps. The generic loop below costs ~60 cycles per UMMA in the issuing
+          // thread (tools/stem_timeline.py: 850 cycles for the 14 UMMAs of a ResNet stem tile against 672 of execution).
+          uint32_t a_lo = (uint32_t)adesc, b_lo = (uint32_t)bdesc;
+          const uint32_t a_hi = (uint32_t)(adesc_hi >> 32), b_hi = (uint32_t)(bdesc_hi >> 32);
+          const uint32_t b_step = b_slab >> 4;
+          if (ksteps == 2) {
+            for (int r = 0; r < kh; ++r, a_lo += row_step, b_lo += b_step)
+              umma_bf16_2steps_nc(d_tmem, a_lo, b_lo, a_hi, b_hi, idesc, (uint32_t)(r != 0));
+          } else {
+            for (int r = 0; r < kh; ++r, a_lo += row_step, b_lo += b_step)
+              umma_bf16_kblock64_nc(d_tmem, a_lo, b_lo, a_hi, b_hi, idesc, (uint32_t)(r != 0));
+          }
+        } else
         for (int r = 0; r < kh; ++r) {
           umma_bf16(d_tmem, adesc + joff[0], bdesc, idesc, (uint32_t)(r != 0));
           if (ksteps > 1) umma_bf16(d_tmem, adesc + joff[1], bdesc + 2, idesc, 1u);
@@ -1488,12 +1507,6 @@ __global__ void __launch_bounds__(kEpi16 ? kStemThreads16 : kStemThreads, 1) ste
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(acc));
         IG_STAMP(it, 2);
-        if (++stage == S) {
-          stage = 0;
-          phase ^= 1u;
-        }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
     }
     __syncwarp();

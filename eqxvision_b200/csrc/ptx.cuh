@@ -259,6 +259,29 @@ __device__ __forceinline__ void umma_bf16_kblock64_nc(uint32_t tmem_d, uint32_t 
       "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Two K steps (2 x 16 deep) of one MMA group with +2 descriptor steps on both operands, no commit: one filter row of the
+// first-layer kernel in the pixel-pair layout (a_hi / b_hi are the constant high descriptor words).
+__device__ __forceinline__ void umma_bf16_2steps_nc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi,
+                                                    uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 a1, b1;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "setp.eq.b32 p, 0, 0;\n"
+      "add.u32 a1, %1, 2;\n"
+      "add.u32 b1, %2, 2;\n"
+      "mov.b64 da, {a1, %3};\n"
+      "mov.b64 db, {b1, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // All previously issued tcgen05.mma of this thread arrive on `bar` when complete.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
